@@ -1,0 +1,186 @@
+/* trajopt_b200.h -- C ABI of the B200-native hot path of traj-opt-admm.
+ *
+ * The reference has no FFI layer: its hot path sits behind header-only C++ statics (namespace HighOrderCCD) and
+ * the compiled class BVH.  This C ABI is the thin layer those entry points are re-hosted on: every function
+ * below names the reference interface (file:line under the reference tree) it replaces.  The C++ drop-in
+ * headers in traj-opt-admm_b200/host/HighOrderCCD/ keep the reference signatures and marshal Eigen objects into
+ * these calls; the ctypes binding in traj-opt-admm_b200/trajopt/api.py does the same for Python.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no C++/torch types.  All pointers are HOST pointers unless a name ends in _dev.
+ *   - matrices are column-major FP64 exactly like Eigen::MatrixXd (spline: T x 3, p_slack/p_lambda: 6P x 3).
+ *   - point / segment ids are uint32 (BVH.h:16 uses unsigned int).
+ *   - "row" r = robot*n_tr + tr_id addresses one Bezier sub-segment of one robot; ragged per-row lists are CSR:
+ *     offsets[n_rows+1] + payload.
+ *   - every function returns 0 on success, nonzero on failure (tob_last_error() gives the text).  There is no
+ *     CPU fallback: a missing GPU or a CUDA error is an error.
+ *   - in-band numerical conventions of the reference are kept: an infeasible trial point yields +INFINITY
+ *     energy (Energy_admm.h:81-82,137-138,154-155).
+ */
+#ifndef TRAJOPT_B200_H
+#define TRAJOPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tob_ctx tob_ctx;
+
+/* Solver globals of HighOrderCCD/Utils/CCDUtils.cpp:5-44 that the path reads (set from Config_File/3D.json in
+ * Main/admmPathPlanning3D.cpp:368-397 and hard-coded :477-478 / multiPathPlanning3D.cpp:596). */
+typedef struct tob_params {
+  int32_t piece_num;     /* Bezier pieces per robot (order 5, 6 control points each) */
+  int32_t res;           /* sub-segments per piece; n_tr = piece_num*res */
+  int32_t uav_num;       /* robots resident in this context */
+  int32_t optimal_plane; /* must be 0 (3D.json); persistent-plane mode is a "next" row */
+  double lambda;         /* barrier weight */
+  double margin;         /* barrier activation distance d-hat */
+  double offset;         /* safety distance */
+  double mu;             /* ADMM penalty */
+  double vel_limit, acc_limit;
+  double ks, kt;         /* smoothness / time weights */
+} tob_params;
+
+/* ---- lifetime ---------------------------------------------------------------------------------------------- */
+int tob_ctx_create(int device, tob_ctx** out);
+void tob_ctx_destroy(tob_ctx* ctx);
+const char* tob_last_error(const tob_ctx* ctx);          /* ctx may be NULL: last error of tob_ctx_create */
+int tob_device_info(const tob_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- set-up (replaces the set-up code of Main/admmPathPlanning3D.cpp:403-414,448-468,294-338) -------------- */
+int tob_set_params(tob_ctx* ctx, const tob_params* p);
+/* Computes on the host, with the reference's formulas and evaluation order, and uploads: Combination<40>
+ * (CCDUtils.h:110-138), Conversion<5> (:140-170), Dynamic3D<5,3> (:172-226), Blossom<5> x convert (:228-315 and
+ * admmPathPlanning3D.cpp:303-313), normalised k-DOP axes (CCDUtils.cpp:56-119).  time_weight may be NULL (=1). */
+int tob_make_tables(tob_ctx* ctx, const double* time_weight);
+/* Upload tables computed elsewhere (the C++ drop-in passes the reference globals subdivide_tree, convert_list,
+ * M_dynamic, kdop_matrix).  basis: n_tr x 36 (6x6 col-major each), weight: n_tr, convert: piece_num x 36,
+ * mdyn: 36, kdop: 3x49 col-major. */
+int tob_set_tables(tob_ctx* ctx, const double* basis, const double* weight, const double* convert,
+                   const double* mdyn, const double* kdop);
+int tob_get_tables(const tob_ctx* ctx, double* basis, double* weight, double* convert, double* mdyn, double* kdop);
+
+/* ---- point cloud (replaces BVH::InitPointcloud, BVH/BVH.cpp:53-92) ------------------------------------------ */
+/* V: n x 3 column-major.  Builds the Morton-sorted 32-wide LBVH on the device. */
+int tob_cloud_upload(tob_ctx* ctx, const double* V, uint32_t n);
+uint32_t tob_cloud_size(const tob_ctx* ctx);
+
+/* ---- broadphase (replaces BVH::DCDCollision :149-192, BVH::CCDCollision :195-249) --------------------------- */
+/* splines: n_robots blocks of T x 3.  Output CSR over n_robots*n_tr rows; ids are ORIGINAL point ids, sorted
+ * ascending inside each row (the reference returns its tree's DFS order; the contract is the SET, see
+ * BVH/src/AABB.cc:131-161 for the leaf predicate that defines it).  If total > cap nothing is written to ids. */
+int tob_broadphase_dcd(tob_ctx* ctx, const double* splines, int n_robots, double d, uint32_t* offsets,
+                       uint32_t* ids, uint64_t cap, uint64_t* total);
+int tob_broadphase_ccd(tob_ctx* ctx, const double* splines, const double* directions, int n_robots, double d,
+                       uint32_t* offsets, uint32_t* ids, uint64_t cap, uint64_t* total);
+/* replaces BVH::SelfDCDCollision :252-286 / SelfCCDCollision :289-329 for one time slot: P (and D): u blocks of
+ * 6x3 col-major.  pairs: (first<second) sorted lexicographically. */
+int tob_self_broadphase(tob_ctx* ctx, const double* P, const double* D /* NULL = DCD */, int u, double d,
+                        uint32_t* pairs, uint64_t cap, uint64_t* total);
+
+/* ---- per-pair primitives (function-level parity entry points) ----------------------------------------------- */
+/* batch of n independent evaluations; A: n blocks of na x 3 col-major, B likewise (na,nb in {1,6,12}). */
+int tob_gjk_batch(tob_ctx* ctx, const double* A, int na, const double* B, int nb, int n, double* v /* n x 3 */);
+/* CCD::KDOPDCD (CCD/CCD.h:354-413): P n x (6x3), q n x 3 -> flags */
+int tob_kdop_dcd_batch(tob_ctx* ctx, const double* P, const double* q, int n, double d, uint8_t* flags);
+/* Separate::opengjk (Separate.h:18-163): -> ok flag, c (n x 3), d (n) */
+int tob_plane_point_batch(tob_ctx* ctx, const double* P, const double* q, int n, double distance, uint8_t* ok,
+                          double* c, double* d);
+/* Separate::selfgjk (:165-304) followed (if refine != 0) by Optimal_plane::optimal_d (Optimal_plane.h:13-71) */
+int tob_plane_hulls_batch(tob_ctx* ctx, const double* P0, const double* P1, int n, double distance, int refine,
+                          uint8_t* ok, double* c, double* d);
+
+/* ---- separating planes (replaces Optimization3D_admm::separate_plane, Optimization3D_admm.h:69-197, and
+ *      Optimization3D_multi::separate_plane :176-235 / ::separate_self :237-342) ------------------------------ */
+/* Runs broadphase -> 49-DOP -> GJK -> plane for every robot and, when with_self != 0 and n_robots > 1, the
+ * inter-robot planes appended after the obstacle planes of each row (same order as the reference: obstacle
+ * planes first).  The plane set stays resident on the device for the calls below; it is also returned on the
+ * host when c/dd are non-NULL.  c: total x 3 (row-major xyz per plane), dd: total. */
+int tob_separate_planes(tob_ctx* ctx, const double* splines, int n_robots, int with_self, uint32_t* offsets,
+                        double* c, double* dd, uint64_t cap, uint64_t* total);
+/* Upload a caller-provided plane set (the reference's c_lists/d_lists) as the resident set. */
+int tob_set_planes(tob_ctx* ctx, int n_robots, const uint32_t* offsets, const double* c, const double* dd);
+
+/* ---- energies (replace Energy_admm::*, Energy_admm.h) ------------------------------------------------------- */
+typedef struct tob_state {       /* one robot's ADMM variables, host pointers */
+  double* spline;                /* T x 3 */
+  double* piece_time;            /* scalar */
+  double* p_slack;               /* 6P x 3 */
+  double* t_slack;               /* P */
+  double* p_lambda;              /* 6P x 3 */
+  double* t_lambda;              /* P */
+} tob_state;
+
+/* Energy_admm::plane_barrier_energy :46-96 against the resident planes of `robot` */
+int tob_plane_barrier_energy(tob_ctx* ctx, int robot, const double* spline, double* e);
+/* Energy_admm::bound_energy :98-170 */
+int tob_bound_energy(tob_ctx* ctx, const double* spline, double piece_time, double* e);
+/* Energy_admm::spline_energy :16-44 */
+int tob_spline_energy(tob_ctx* ctx, int robot, const tob_state* st, double* e);
+
+/* ---- gradient / Hessian blocks (replace Gradient_admm::*, Gradient_admm.h) ---------------------------------- */
+/* local_spline_gradient :67-164 for every piece (before the PSD projection): g: P x 19, h: P x 361 (col-major) */
+int tob_piece_blocks(tob_ctx* ctx, int robot, const tob_state* st, int project_psd, double* g, double* h);
+/* global_spline_gradient :13-65: dense grad[3T+1], hess[(3T+1)^2 col-major] (PSD-projected piece blocks) */
+int tob_global_gradient(tob_ctx* ctx, int robot, const tob_state* st, double* grad, double* hess);
+/* Optimization3D_admm::spline_descent_direction (Optimization3D_admm.h:400-503) when dense_shift == 0;
+ * Optimization3D_multi::spline_descent_direction (Optimization3D_multi.h:659-752, global eigen-shift fall-back)
+ * when dense_shift != 0.  direction: T x 3. */
+int tob_descent_direction(tob_ctx* ctx, int robot, const tob_state* st, int dense_shift, double* direction,
+                          double* t_direction, double* wolfe, double* gnorm);
+
+/* ---- CCD step bound (replaces Step::position_step Step.h:21-110, ::self_step :184-256,
+ *      ::couple_self_step :112-182) ---------------------------------------------------------------------------- */
+int tob_position_step(tob_ctx* ctx, const double* spline, const double* direction, double* step);
+int tob_self_step(tob_ctx* ctx, const double* splines, const double* directions, int n_robots, int coupled,
+                  double* steps /* n_robots, or 1 when coupled */);
+
+/* ---- slack / dual update (replaces Optimization3D_admm::update_slack_lambda :231-398) ------------------------ */
+int tob_update_slack_lambda(tob_ctx* ctx, tob_state* st);
+
+/* ---- whole ADMM iteration, device resident --------------------------------------------------------------------
+ * tob_states_upload / download move the n_robots states between host and the context;
+ * tob_admm_iterate runs `iters` iterations of Optimization3D_admm::optimization (:29-67) when n_robots == 1, of
+ * Optimization3D_multi::optimization_decouple (Optimization3D_multi.h:29-118) when n_robots > 1 (mode 0) or of
+ * ::optimization (coupled, :120-174) (mode 1).  gnorm receives the reference's global `gnorm` after the last
+ * iteration.  Robot ownership for multi-GPU: see tob_set_shard(). */
+int tob_states_upload(tob_ctx* ctx, const tob_state* states, int n_robots);
+int tob_states_download(tob_ctx* ctx, tob_state* states, int n_robots);
+int tob_admm_iterate(tob_ctx* ctx, int iters, int mode, double* gnorm);
+/* one call = upload + 1 iteration + download: the shape of the reference entry point (host in / host out) */
+int tob_optimization(tob_ctx* ctx, tob_state* states, int n_robots, int mode, double* gnorm);
+
+/* counters of the last tob_admm_iterate / tob_optimization call (for bench.py): */
+typedef struct tob_counters {
+  uint64_t kernel_launches;      /* kernels of this library launched */
+  uint64_t dcd_candidates;       /* broadphase candidates through k-DOP (+GJK) */
+  uint64_t planes;               /* accepted planes */
+  uint64_t ccd_candidates;       /* swept-box candidates through the CCD ladder */
+  uint64_t energy_plane_evals;   /* planes x energy/gradient passes */
+  uint64_t self_pairs;           /* inter-robot segment pairs evaluated */
+  uint64_t line_search_trials;
+} tob_counters;
+int tob_get_counters(const tob_ctx* ctx, tob_counters* out);
+int tob_reset_counters(tob_ctx* ctx);
+
+/* ---- multi-GPU (robots sharded across ranks; cloud replicated) -------------------------------------------------
+ * The context owns robots [first, first+count) of n_total.  The per-iteration exchange (all robots' control
+ * points before separate_self, directions before self_step, two scalars) is delegated to two callbacks so the
+ * host can use NCCL through whatever plumbing it has (torch.distributed in bench.py, ncclAllGather in C++).
+ * allgather(dev_ptr_full, elems_per_rank, user): in-place all-gather of FP64 on the context's stream.
+ * allreduce_sum(dev_ptr, n, user). */
+typedef int (*tob_allgather_fn)(void* dev_ptr_full, uint64_t elems_per_rank, void* user);
+typedef int (*tob_allreduce_fn)(void* dev_ptr, uint64_t n, int op /*0 sum,1 min,2 max*/, void* user);
+int tob_set_shard(tob_ctx* ctx, int first, int count, int n_total, tob_allgather_fn ag, tob_allreduce_fn ar,
+                  void* user);
+void* tob_stream(tob_ctx* ctx); /* cudaStream_t the context launches on */
+
+/* FP64 pipe microbenchmark (DFMA chains) used as the roofline denominator of the FP64-bound kernels */
+int tob_fp64_peak(tob_ctx* ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,106 @@
+// tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiles the product's host+device math header (csrc/gjk.cuh) and the host-side table set-up (csrc/tables.cu)
+// with g++ so that their bit-exactness against the compiled reference can be checked on a machine without a GPU.
+// Nothing in the product links this file; the product path always runs the CUDA build of the same header.
+#include <cstring>
+#include <vector>
+
+#include "../../traj-opt-admm_b200/csrc/gjk.cuh"
+#include "../../traj-opt-admm_b200/csrc/ctx.cuh"
+
+using namespace tob;
+
+template <int N>
+static void load(const double* src, double (*dst)[3]) {  // N x 3 column-major
+  for (int j = 0; j < N; j++)
+    for (int k = 0; k < 3; k++) dst[j][k] = src[k * N + j];
+}
+
+extern "C" {
+
+int hs_gjk(const double* A, int na, const double* B, int nb, double* v) {
+  if (na == 6 && nb == 1) { double a[6][3], b[1][3]; load<6>(A, a); load<1>(B, b); gjk_witness<6, 1>(a, b, v); return 0; }
+  if (na == 12 && nb == 1) { double a[12][3], b[1][3]; load<12>(A, a); load<1>(B, b); gjk_witness<12, 1>(a, b, v); return 0; }
+  if (na == 6 && nb == 6) { double a[6][3], b[6][3]; load<6>(A, a); load<6>(B, b); gjk_witness<6, 6>(a, b, v); return 0; }
+  if (na == 12 && nb == 12) { double a[12][3], b[12][3]; load<12>(A, a); load<12>(B, b); gjk_witness<12, 12>(a, b, v); return 0; }
+  return 1;
+}
+
+int hs_kdop_dcd(const double* P, const double* q, const double* kdop, double d) {
+  double a[6][3], b[1][3] = {{q[0], q[1], q[2]}};
+  load<6>(P, a);
+  double lo[49], hi[49];
+  kdop_extents<6>(a, kdop, lo, hi);
+  bool r1 = kdop_point_overlap(lo, hi, kdop, q, d);
+  bool r2 = kdop_overlap<6, 1>(a, b, kdop, d);
+  return (r1 ? 1 : 0) | (r2 ? 2 : 0);   // both formulations must agree: 0 or 3
+}
+
+int hs_self_kdop_dcd(const double* P0, const double* P1, const double* kdop, double d) {
+  double a[6][3], b[6][3];
+  load<6>(P0, a); load<6>(P1, b);
+  double lo0[49], hi0[49], lo1[49], hi1[49];
+  kdop_extents<6>(a, kdop, lo0, hi0);
+  kdop_extents<6>(b, kdop, lo1, hi1);
+  bool r1 = kdop_sets_overlap(lo0, hi0, lo1, hi1, d);
+  bool r2 = kdop_overlap<6, 6>(a, b, kdop, d);
+  return (r1 ? 1 : 0) | (r2 ? 2 : 0);
+}
+
+int hs_kdop_ccd(const double* P, const double* D, const double* q, const double* kdop, double d, double t0, double t1) {
+  double p[6][3], dd[6][3], A[12][3], b[1][3] = {{q[0], q[1], q[2]}};
+  load<6>(P, p); load<6>(D, dd);
+  swept_points(p, dd, t0, t1, A);
+  return kdop_overlap<12, 1>(A, b, kdop, d);
+}
+
+int hs_gjk_ccd(const double* P, const double* D, const double* q, double d, double t0, double t1) {
+  double p[6][3], dd[6][3], A[12][3], b[1][3] = {{q[0], q[1], q[2]}}, v[3];
+  load<6>(P, p); load<6>(D, dd);
+  swept_points(p, dd, t0, t1, A);
+  gjk_witness<12, 1>(A, b, v);
+  return (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) <= d * d;
+}
+
+int hs_self_gjk_ccd(const double* P0, const double* D0, const double* P1, const double* D1, double d, double s0, double s1) {
+  double p0[6][3], d0[6][3], p1[6][3], d1[6][3], A[12][3], B[12][3], v[3];
+  load<6>(P0, p0); load<6>(D0, d0); load<6>(P1, p1); load<6>(D1, d1);
+  swept_points(p0, d0, 0.0, s0, A);
+  swept_points(p1, d1, 0.0, s1, B);
+  gjk_witness<12, 12>(A, B, v);
+  return (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) <= d * d;
+}
+
+int hs_plane_point(const double* P, const double* q, double dist, double offset, double* c, double* d) {
+  double a[6][3];
+  load<6>(P, a);
+  return plane_point(a, q, dist, offset, c, d);
+}
+
+int hs_plane_hulls(const double* P0, const double* P1, double dist, double* c, double* d) {
+  double a[6][3], b[6][3];
+  load<6>(P0, a); load<6>(P1, b);
+  return plane_hulls(a, b, dist, c, d);
+}
+
+int hs_refine_d(const double* P0, const double* P1, const double* c, double offset, double margin, double* d) {
+  double a[6][3], b[6][3];
+  load<6>(P0, a); load<6>(P1, b);
+  return refine_d(a, b, c, offset, margin, d, 10000);
+}
+
+int hs_make_tables(int piece_num, int res, double* basis, double* weight, double* convert, double* mdyn, double* kdop) {
+  tob_params p;
+  std::memset(&p, 0, sizeof(p));
+  p.piece_num = piece_num; p.res = res; p.uav_num = 1;
+  std::vector<double> b, w, cv, md, kd;
+  make_tables_host(p, nullptr, b, w, cv, md, kd);
+  std::memcpy(basis, b.data(), b.size() * sizeof(double));
+  std::memcpy(weight, w.data(), w.size() * sizeof(double));
+  std::memcpy(convert, cv.data(), cv.size() * sizeof(double));
+  std::memcpy(mdyn, md.data(), 36 * sizeof(double));
+  std::memcpy(kdop, kd.data(), 147 * sizeof(double));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,828 @@
+// api.cu -- extern "C" entry points of include/trajopt_b200.h and the device-resident ADMM iteration.
+//
+// Iteration sequencing follows Optimization3D_admm::optimization (Optimization3D_admm.h:29-67) for one robot and
+// Optimization3D_multi::optimization_decouple (Optimization3D_multi.h:29-118) for several:
+//   separate planes -> per-piece blocks -> Newton direction -> CCD step bound -> Armijo line search -> slack/dual.
+// Everything stays on the device; the host only reads a few scalars (candidate/plane totals for buffer sizing and
+// the number of robots still backtracking).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "ctx.cuh"
+#include "gjk.cuh"
+
+static std::string g_create_err;
+
+namespace tob {
+
+int fail(tob_ctx* c, const char* what, cudaError_t e, const char* file, int line) {
+  std::string m = std::string(what) + ": " + cudaGetErrorString(e) + " (" + file + ":" + std::to_string(line) + ")";
+  if (c) c->err = m; else g_create_err = m;
+  return 1;
+}
+int fail_msg(tob_ctx* c, const std::string& msg) {
+  if (c) c->err = msg; else g_create_err = msg;
+  return 1;
+}
+
+static int need(tob_ctx* c, bool tables, bool cloud) {
+  if (!c) return fail_msg(c, "null context");
+  if (!c->have_params) return fail_msg(c, "tob_set_params has not been called");
+  if (tables && !c->have_tables) return fail_msg(c, "tables missing: call tob_make_tables or tob_set_tables");
+  if (cloud && c->n_pts == 0) return fail_msg(c, "no point cloud: call tob_cloud_upload");
+  return 0;
+}
+
+static int upload(tob_ctx* c, DBuf<double>& b, const double* src, size_t n, size_t elem_off = 0) {
+  TOB_CUDA(c, cudaMemcpyAsync(b.p + elem_off, src, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
+static int alloc_states(tob_ctx* c) {
+  const int U = c->n_robots(), P = c->prm.piece_num, T = c->T;
+  TOB_CUDA(c, c->s_spline.ensure((size_t)U * 3 * T));
+  TOB_CUDA(c, c->s_ptime.ensure(U));
+  TOB_CUDA(c, c->s_pslack.ensure((size_t)U * 18 * P));
+  TOB_CUDA(c, c->s_tslack.ensure((size_t)U * P));
+  TOB_CUDA(c, c->s_plambda.ensure((size_t)U * 18 * P));
+  TOB_CUDA(c, c->s_tlambda.ensure((size_t)U * P));
+  TOB_CUDA(c, c->s_dir.ensure((size_t)U * 3 * T));
+  TOB_CUDA(c, c->s_tdir.ensure(U)); TOB_CUDA(c, c->s_wolfe.ensure(U)); TOB_CUDA(c, c->s_gnorm.ensure(U));
+  TOB_CUDA(c, c->s_step.ensure(U)); TOB_CUDA(c, c->s_selfstep.ensure(U)); TOB_CUDA(c, c->s_ptrial.ensure(U));
+  TOB_CUDA(c, c->s_e0.ensure(U)); TOB_CUDA(c, c->s_e1.ensure(U));
+  TOB_CUDA(c, c->s_done.ensure(U + 1)); TOB_CUDA(c, c->solve_status.ensure(U));
+  TOB_CUDA(c, c->kmax.ensure(U + 1));
+  return 0;
+}
+
+static int put_state(tob_ctx* c, int robot, const tob_state* st) {
+  const int P = c->prm.piece_num, T = c->T;
+  TOB_TRY(upload(c, c->s_spline, st->spline, 3 * T, (size_t)robot * 3 * T));
+  TOB_TRY(upload(c, c->s_ptime, st->piece_time, 1, robot));
+  TOB_TRY(upload(c, c->s_pslack, st->p_slack, 18 * P, (size_t)robot * 18 * P));
+  TOB_TRY(upload(c, c->s_tslack, st->t_slack, P, (size_t)robot * P));
+  TOB_TRY(upload(c, c->s_plambda, st->p_lambda, 18 * P, (size_t)robot * 18 * P));
+  TOB_TRY(upload(c, c->s_tlambda, st->t_lambda, P, (size_t)robot * P));
+  return 0;
+}
+
+static int get_state(tob_ctx* c, int robot, tob_state* st) {
+  const int P = c->prm.piece_num, T = c->T;
+  cudaStream_t s = c->stream;
+  TOB_CUDA(c, cudaMemcpyAsync(st->spline, c->s_spline.p + (size_t)robot * 3 * T, 3 * T * sizeof(double), cudaMemcpyDeviceToHost, s));
+  TOB_CUDA(c, cudaMemcpyAsync(st->piece_time, c->s_ptime.p + robot, sizeof(double), cudaMemcpyDeviceToHost, s));
+  TOB_CUDA(c, cudaMemcpyAsync(st->p_slack, c->s_pslack.p + (size_t)robot * 18 * P, 18 * P * sizeof(double), cudaMemcpyDeviceToHost, s));
+  TOB_CUDA(c, cudaMemcpyAsync(st->t_slack, c->s_tslack.p + (size_t)robot * P, P * sizeof(double), cudaMemcpyDeviceToHost, s));
+  TOB_CUDA(c, cudaMemcpyAsync(st->p_lambda, c->s_plambda.p + (size_t)robot * 18 * P, 18 * P * sizeof(double), cudaMemcpyDeviceToHost, s));
+  TOB_CUDA(c, cudaMemcpyAsync(st->t_lambda, c->s_tlambda.p + (size_t)robot * P, P * sizeof(double), cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+// ---- small device helpers of the iteration ---------------------------------------------------------------------
+__global__ void k_fill_int(int* p, int n, int v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// step = min(self step, 0.8^kmax); clamp so the piece time stays positive (Optimization3D_admm.h:521-524)
+__global__ void k_ls_init(int rb, int re, const int* kmax, const double* steps_tab, const double* selfstep, int use_self,
+                          const double* ptime, const double* tdir, double* step, double* ptrial, int* done) {
+  int u = rb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= re) return;
+  double s = steps_tab[kmax[u]];
+  if (use_self) {
+    double ss = selfstep[u];
+    if (s < ss) ss = s;        // reference: if(step<step_list[i]) step_list[i]=step
+    s = ss;
+  }
+  if (ptime[u] + s * tdir[u] <= 0) s = -0.95 * ptime[u] / tdir[u];
+  step[u] = s;
+  ptrial[u] = ptime[u] + s * tdir[u];
+  done[u] = 0;
+}
+
+// Armijo test of one backtracking round; wolfe_idx < 0: own wolfe, else the reference's "last robot" quirk
+__global__ void k_armijo(int rb, int re, const double* e0, const double* e1, const double* wolfe, int wolfe_idx,
+                         const double* ptime, const double* tdir, double* step, double* ptrial, int* done, int* n_active) {
+  int u = rb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= re) return;
+  if (done[u]) return;
+  double w = wolfe[wolfe_idx < 0 ? u : wolfe_idx];
+  if (e0[u] - 1e-4 * w * step[u] < e1[u]) {
+    double s = step[u] * 0.8;
+    step[u] = s;
+    ptrial[u] = ptime[u] + s * tdir[u];
+    atomicAdd(n_active, 1);
+  } else {
+    done[u] = 1;
+  }
+}
+
+__global__ void k_apply_step(int rb, int re, int T, const double* step, const double* dir, const double* ptrial, double* spline,
+                             double* ptime) {
+  int u = rb + blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= re) return;
+  if (i < 3 * T) {
+    size_t g = (size_t)u * 3 * T + i;
+    spline[g] = spline[g] + step[u] * dir[g];
+  }
+  if (i == 0) ptime[u] = ptrial[u];
+}
+
+__global__ void k_zero_steps(double* p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.0;
+}
+
+static int read_back(tob_ctx* c, const void* dev, size_t bytes) {
+  TOB_CUDA(c, cudaMemcpyAsync(c->h_pinned, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// planes of robots [rb,re) from the resident splines
+static int separate_resident(tob_ctx* c, int rb, int re, int with_self) {
+  const int U = c->n_robots();
+  bool ws = with_self && U > 1;
+  // inter-robot planes need every robot's rows; otherwise only the owned ones
+  TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, ws ? 0 : rb, ws ? U : re, 1));
+  uint64_t total = 0;
+  TOB_TRY(broadphase(c, rb, re, c->prm.offset + c->prm.margin, &total));
+  TOB_TRY(narrowphase_planes(c, rb, re, ws ? 1 : 0));
+  return 0;
+}
+
+// line search of robots [rb,re): s_step/s_ptrial/s_done prepared by k_ls_init
+static int line_search(tob_ctx* c, int rb, int re, int wolfe_idx) {
+  const int n = re - rb;
+  cudaStream_t st = c->stream;
+  // e0 at the current point (step 0)
+  TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, rb, re, 0));
+  TOB_TRY(energy_rows(c, rb, re, c->s_spline.p, nullptr, nullptr, c->s_ptime.p, c->s_e0.p));
+  int* n_active = c->s_done.p + c->n_robots();
+  for (int round = 0; round < 2000; round++) {
+    TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, c->s_step.p, rb, re, 4));
+    TOB_TRY(energy_rows(c, rb, re, c->s_spline.p, c->s_dir.p, c->s_step.p, c->s_ptrial.p, c->s_e1.p));
+    k_fill_int<<<1, 32, 0, st>>>(n_active, 1, 0);
+    TOB_LAUNCH_CHECK(c);
+    k_armijo<<<div_up(n, 64), 64, 0, st>>>(rb, re, c->s_e0.p, c->s_e1.p, c->s_wolfe.p, wolfe_idx, c->s_ptime.p, c->s_tdir.p,
+                                          c->s_step.p, c->s_ptrial.p, c->s_done.p, n_active);
+    TOB_LAUNCH_CHECK(c);
+    TOB_TRY(read_back(c, n_active, sizeof(int)));
+    c->ctr.line_search_trials += n;
+    if (*((int*)c->h_pinned) == 0) break;
+  }
+  dim3 grid(div_up(3 * c->T, 128), n);
+  k_apply_step<<<grid, 128, 0, st>>>(rb, re, c->T, c->s_step.p, c->s_dir.p, c->s_ptrial.p, c->s_spline.p, c->s_ptime.p);
+  TOB_LAUNCH_CHECK(c);
+  return 0;
+}
+
+static int exchange(tob_ctx* c, DBuf<double>& buf, size_t elems_per_robot) {
+  if (!c->ag) return 0;
+  size_t per_rank = elems_per_robot * (size_t)(c->own_end - c->own_begin);
+  if (c->ag(buf.p, per_rank, c->cb_user)) return fail_msg(c, "all-gather callback failed");
+  return 0;
+}
+
+static int iterate_once(tob_ctx* c, int mode, double* gnorm_out) {
+  const int U = c->n_robots(), rb = c->own_begin, re = c->own_end;
+  cudaStream_t st = c->stream;
+  if (mode != 0) return fail_msg(c, "coupled multi-robot mode (decouple=0) is not implemented yet");
+  // (1) control points of every robot are needed for the inter-robot planes
+  if (U > 1) TOB_TRY(exchange(c, c->s_spline, (size_t)3 * c->T));
+  TOB_TRY(separate_resident(c, rb, re, 1));
+  // (2) Newton direction
+  TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, rb, re, 0));
+  TOB_TRY(gradient_blocks(c, rb, re, 1));
+  TOB_TRY(solve_directions(c, rb, re, U > 1));
+  // (3) CCD step bound
+  if (U > 1) {
+    TOB_TRY(exchange(c, c->s_dir, (size_t)3 * c->T));
+    TOB_TRY(exchange(c, c->s_wolfe, 1));
+    TOB_TRY(exchange(c, c->s_gnorm, 1));
+    TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, 0, U, 3));
+    TOB_TRY(self_ccd_steps(c, 0, c->s_selfstep.p));
+  } else {
+    TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, rb, re, 3));
+  }
+  uint64_t total = 0;
+  TOB_TRY(broadphase(c, rb, re, c->prm.offset, &total));
+  k_fill_int<<<div_up(U, 64), 64, 0, st>>>(c->kmax.p, U, 0);
+  TOB_LAUNCH_CHECK(c);
+  TOB_TRY(ccd_position_steps(c));
+  k_ls_init<<<div_up(re - rb, 64), 64, 0, st>>>(rb, re, c->kmax.p, c->d_steps.p, c->s_selfstep.p, U > 1 ? 1 : 0, c->s_ptime.p,
+                                                c->s_tdir.p, c->s_step.p, c->s_ptrial.p, c->s_done.p);
+  TOB_LAUNCH_CHECK(c);
+  // (4) Armijo; multi-robot: every robot uses the LAST robot's wolfe (global overwritten, Optimization3D_multi.h:730,792)
+  TOB_TRY(line_search(c, rb, re, U > 1 ? U - 1 : -1));
+  // (5) slack + dual
+  TOB_TRY(slack_update(c, rb, re));
+  // gnorm global of the reference
+  if (gnorm_out) {
+    TOB_TRY(read_back(c, c->s_gnorm.p, U * sizeof(double)));
+    double g = 0;
+    const double* hp = c->h_pinned;
+    if (U == 1) g = hp[0];
+    else { for (int u = 0; u < U; u++) g += hp[u]; g /= double(U); }
+    *gnorm_out = g;
+  }
+  return 0;
+}
+
+}  // namespace tob
+
+using namespace tob;
+
+extern "C" {
+
+int tob_ctx_create(int device, tob_ctx** out) {
+  if (!out) return 1;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail_msg(nullptr, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail_msg(nullptr, "bad device index");
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, "cudaSetDevice", e, __FILE__, __LINE__);
+  tob_ctx* c = new tob_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  c->sm_count = prop.multiProcessorCount; c->cc_major = prop.major; c->cc_minor = prop.minor;
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return fail(nullptr, "cudaStreamCreate", e, __FILE__, __LINE__); }
+  if ((e = cudaMallocHost((void**)&c->h_pinned, 65536)) != cudaSuccess) { delete c; return fail(nullptr, "cudaMallocHost", e, __FILE__, __LINE__); }
+  if ((e = c->red.ensure(4096)) != cudaSuccess) { delete c; return fail(nullptr, "cudaMalloc", e, __FILE__, __LINE__); }
+  std::vector<double> steps(TOB_LADDER + 2);
+  double s = 1.0;
+  for (int k = 0; k < TOB_LADDER + 2; k++) { steps[k] = s; s *= 0.8; }
+  c->d_steps.ensure(steps.size());
+  cudaMemcpy(c->d_steps.p, steps.data(), steps.size() * sizeof(double), cudaMemcpyHostToDevice);
+  *out = c;
+  return 0;
+}
+
+void tob_ctx_destroy(tob_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  // DBuf members are plain pointers: release the big ones explicitly
+  c->px.release(); c->py.release(); c->pz.release(); c->pid.release(); c->lvl_store.release();
+  c->cand_pt.release(); c->cand_row.release(); c->cpl.release(); c->pl.release(); c->task_cnt.release(); c->task_off.release();
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* tob_last_error(const tob_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int tob_device_info(const tob_ctx* c, int* sm_count, int* cc_major, int* cc_minor) {
+  if (!c) return 1;
+  if (sm_count) *sm_count = c->sm_count;
+  if (cc_major) *cc_major = c->cc_major;
+  if (cc_minor) *cc_minor = c->cc_minor;
+  return 0;
+}
+
+int tob_set_params(tob_ctx* c, const tob_params* p) {
+  if (!c || !p) return 1;
+  if (p->piece_num < 1 || p->res < 1 || p->res > 16 || p->uav_num < 1) return fail_msg(c, "tob_set_params: bad sizes");
+  if (p->optimal_plane) return fail_msg(c, "optimal_plane=1 (persistent planes) is not supported");
+  cudaSetDevice(c->device);
+  c->prm = *p;
+  c->n_tr = p->piece_num * p->res;
+  c->T = 6 + 3 * (p->piece_num - 1);
+  c->have_params = true;
+  c->have_tables = false;
+  c->states_valid = false;
+  c->own_begin = 0; c->own_end = p->uav_num;
+  c->n_planes = 0;
+  return alloc_states(c);
+}
+
+static int upload_tables(tob_ctx* c) {
+  TOB_CUDA(c, c->d_basis.ensure(c->h_basis.size())); TOB_CUDA(c, c->d_weight.ensure(c->h_weight.size()));
+  TOB_CUDA(c, c->d_convert.ensure(c->h_convert.size())); TOB_CUDA(c, c->d_mdyn.ensure(36)); TOB_CUDA(c, c->d_kdop.ensure(147));
+  TOB_TRY(upload(c, c->d_basis, c->h_basis.data(), c->h_basis.size()));
+  TOB_TRY(upload(c, c->d_weight, c->h_weight.data(), c->h_weight.size()));
+  TOB_TRY(upload(c, c->d_convert, c->h_convert.data(), c->h_convert.size()));
+  TOB_TRY(upload(c, c->d_mdyn, c->h_mdyn.data(), 36));
+  TOB_TRY(upload(c, c->d_kdop, c->h_kdop.data(), 147));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->have_tables = true;
+  return 0;
+}
+
+int tob_make_tables(tob_ctx* c, const double* time_weight) {
+  TOB_TRY(need(c, false, false));
+  cudaSetDevice(c->device);
+  make_tables_host(c->prm, time_weight, c->h_basis, c->h_weight, c->h_convert, c->h_mdyn, c->h_kdop);
+  return upload_tables(c);
+}
+
+int tob_set_tables(tob_ctx* c, const double* basis, const double* weight, const double* convert, const double* mdyn,
+                   const double* kdop) {
+  TOB_TRY(need(c, false, false));
+  cudaSetDevice(c->device);
+  c->h_basis.assign(basis, basis + (size_t)36 * c->n_tr);
+  c->h_weight.assign(weight, weight + c->n_tr);
+  c->h_convert.assign(convert, convert + (size_t)36 * c->prm.piece_num);
+  c->h_mdyn.assign(mdyn, mdyn + 36);
+  c->h_kdop.assign(kdop, kdop + 147);
+  return upload_tables(c);
+}
+
+int tob_get_tables(const tob_ctx* c, double* basis, double* weight, double* convert, double* mdyn, double* kdop) {
+  if (!c || !c->have_tables) return 1;
+  if (basis) memcpy(basis, c->h_basis.data(), c->h_basis.size() * sizeof(double));
+  if (weight) memcpy(weight, c->h_weight.data(), c->h_weight.size() * sizeof(double));
+  if (convert) memcpy(convert, c->h_convert.data(), c->h_convert.size() * sizeof(double));
+  if (mdyn) memcpy(mdyn, c->h_mdyn.data(), 36 * sizeof(double));
+  if (kdop) memcpy(kdop, c->h_kdop.data(), 147 * sizeof(double));
+  return 0;
+}
+
+int tob_cloud_upload(tob_ctx* c, const double* V, uint32_t n) {
+  if (!c || !V) return 1;
+  cudaSetDevice(c->device);
+  return lbvh_build(c, V, n);
+}
+uint32_t tob_cloud_size(const tob_ctx* c) { return c ? c->n_pts : 0; }
+
+// ---- broadphase --------------------------------------------------------------------------------------------------
+static int bp_download(tob_ctx* c, int n_robots, uint32_t* offsets, uint32_t* ids, uint64_t cap, uint64_t* total) {
+  const int rows = n_robots * c->n_tr;
+  uint64_t nc = c->n_cand;
+  if (total) *total = nc;
+  std::vector<uint32_t> off(c->rows_all() + 1);
+  TOB_CUDA(c, cudaMemcpyAsync(off.data(), c->row_off.p, off.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  std::vector<uint32_t> pts(nc);
+  if (nc) TOB_CUDA(c, cudaMemcpyAsync(pts.data(), c->cand_pt.p, nc * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int r = 0; r <= rows; r++) offsets[r] = off[r];
+  if (nc > cap || !ids) return 0;
+  for (uint64_t i = 0; i < nc; i++) ids[i] = c->h_pid[pts[i]];
+  for (int r = 0; r < rows; r++) std::sort(ids + off[r], ids + off[r + 1]);
+  return 0;
+}
+
+static int stage_splines(tob_ctx* c, const double* splines, const double* dirs, int n_robots) {
+  if (n_robots < 1 || n_robots > c->n_robots()) return fail_msg(c, "n_robots exceeds tob_params.uav_num");
+  TOB_TRY(upload(c, c->s_spline, splines, (size_t)n_robots * 3 * c->T));
+  if (dirs) TOB_TRY(upload(c, c->s_dir, dirs, (size_t)n_robots * 3 * c->T));
+  c->states_valid = false;
+  return 0;
+}
+
+int tob_broadphase_dcd(tob_ctx* c, const double* splines, int n_robots, double d, uint32_t* offsets, uint32_t* ids,
+                       uint64_t cap, uint64_t* total) {
+  TOB_TRY(need(c, true, true));
+  cudaSetDevice(c->device);
+  TOB_TRY(stage_splines(c, splines, nullptr, n_robots));
+  TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, 0, n_robots, 0));
+  uint64_t t = 0;
+  TOB_TRY(broadphase(c, 0, n_robots, d, &t));
+  return bp_download(c, n_robots, offsets, ids, cap, total);
+}
+
+int tob_broadphase_ccd(tob_ctx* c, const double* splines, const double* directions, int n_robots, double d,
+                       uint32_t* offsets, uint32_t* ids, uint64_t cap, uint64_t* total) {
+  TOB_TRY(need(c, true, true));
+  cudaSetDevice(c->device);
+  TOB_TRY(stage_splines(c, splines, directions, n_robots));
+  TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, 0, n_robots, 2));
+  uint64_t t = 0;
+  TOB_TRY(broadphase(c, 0, n_robots, d, &t));
+  return bp_download(c, n_robots, offsets, ids, cap, total);
+}
+
+}  // extern "C"
+
+// ---- batched primitives --------------------------------------------------------------------------------------------
+template <int NA, int NB>
+__global__ void k_gjk_batch(const double* A, const double* B, int n, double* v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[NA][3], b[NB][3];
+  for (int j = 0; j < NA; j++) for (int k = 0; k < 3; k++) a[j][k] = A[(size_t)i * NA * 3 + k * NA + j];
+  for (int j = 0; j < NB; j++) for (int k = 0; k < 3; k++) b[j][k] = B[(size_t)i * NB * 3 + k * NB + j];
+  gjk_witness<NA, NB>(a, b, v + 3 * (size_t)i);
+}
+
+__global__ void k_kdop_batch(const double* P, const double* q, const double* kdop, int n, double d, uint8_t* flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[6][3], b[1][3];
+  for (int j = 0; j < 6; j++) for (int k = 0; k < 3; k++) a[j][k] = P[(size_t)i * 18 + k * 6 + j];
+  for (int k = 0; k < 3; k++) b[0][k] = q[(size_t)i * 3 + k];
+  flags[i] = kdop_overlap<6, 1>(a, b, kdop, d) ? 1 : 0;
+}
+
+__global__ void k_plane_point_batch(const double* P, const double* q, int n, double dist, double offset, uint8_t* ok, double* c,
+                                    double* d) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[6][3], qq[3], cc[3] = {0, 0, 0}, dd = 0;
+  for (int j = 0; j < 6; j++) for (int k = 0; k < 3; k++) a[j][k] = P[(size_t)i * 18 + k * 6 + j];
+  for (int k = 0; k < 3; k++) qq[k] = q[(size_t)i * 3 + k];
+  bool r = plane_point(a, qq, dist, offset, cc, &dd);
+  ok[i] = r;
+  c[3 * (size_t)i] = cc[0]; c[3 * (size_t)i + 1] = cc[1]; c[3 * (size_t)i + 2] = cc[2];
+  d[i] = dd;
+}
+
+__global__ void k_plane_hulls_batch(const double* P0, const double* P1, int n, double dist, double offset, double margin,
+                                    int refine, uint8_t* ok, double* c, double* d) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[6][3], b[6][3], cc[3] = {0, 0, 0}, dd = 0;
+  for (int j = 0; j < 6; j++) for (int k = 0; k < 3; k++) { a[j][k] = P0[(size_t)i * 18 + k * 6 + j]; b[j][k] = P1[(size_t)i * 18 + k * 6 + j]; }
+  bool r = plane_hulls(a, b, dist, cc, &dd);
+  if (r && refine) refine_d(a, b, cc, offset, margin, &dd, 10000);
+  ok[i] = r;
+  c[3 * (size_t)i] = cc[0]; c[3 * (size_t)i + 1] = cc[1]; c[3 * (size_t)i + 2] = cc[2];
+  d[i] = dd;
+}
+
+extern "C" {
+
+int tob_gjk_batch(tob_ctx* c, const double* A, int na, const double* B, int nb, int n, double* v) {
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  size_t sa = (size_t)n * na * 3, sb = (size_t)n * nb * 3;
+  TOB_CUDA(c, c->scratch.ensure(sa + sb)); TOB_CUDA(c, c->scratch2.ensure(3 * (size_t)n));
+  TOB_TRY(upload(c, c->scratch, A, sa)); TOB_TRY(upload(c, c->scratch, B, sb, sa));
+  int g = div_up(n, 64);
+  const double *dA = c->scratch.p, *dB = c->scratch.p + sa;
+  if (na == 6 && nb == 1) k_gjk_batch<6, 1><<<g, 64, 0, c->stream>>>(dA, dB, n, c->scratch2.p);
+  else if (na == 12 && nb == 1) k_gjk_batch<12, 1><<<g, 64, 0, c->stream>>>(dA, dB, n, c->scratch2.p);
+  else if (na == 6 && nb == 6) k_gjk_batch<6, 6><<<g, 64, 0, c->stream>>>(dA, dB, n, c->scratch2.p);
+  else if (na == 12 && nb == 12) k_gjk_batch<12, 12><<<g, 64, 0, c->stream>>>(dA, dB, n, c->scratch2.p);
+  else return fail_msg(c, "tob_gjk_batch: supported (na,nb) are (6,1) (12,1) (6,6) (12,12)");
+  TOB_LAUNCH_CHECK(c);
+  TOB_CUDA(c, cudaMemcpyAsync(v, c->scratch2.p, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int tob_kdop_dcd_batch(tob_ctx* c, const double* P, const double* q, int n, double d, uint8_t* flags) {
+  TOB_TRY(need(c, true, false));
+  cudaSetDevice(c->device);
+  TOB_CUDA(c, c->scratch.ensure((size_t)21 * n)); TOB_CUDA(c, c->scratch8.ensure(n));
+  TOB_TRY(upload(c, c->scratch, P, (size_t)18 * n)); TOB_TRY(upload(c, c->scratch, q, (size_t)3 * n, (size_t)18 * n));
+  k_kdop_batch<<<div_up(n, 64), 64, 0, c->stream>>>(c->scratch.p, c->scratch.p + (size_t)18 * n, c->d_kdop.p, n, d, c->scratch8.p);
+  TOB_LAUNCH_CHECK(c);
+  TOB_CUDA(c, cudaMemcpyAsync(flags, c->scratch8.p, n, cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int tob_plane_point_batch(tob_ctx* c, const double* P, const double* q, int n, double distance, uint8_t* ok, double* cc,
+                          double* d) {
+  TOB_TRY(need(c, false, false));
+  cudaSetDevice(c->device);
+  TOB_CUDA(c, c->scratch.ensure((size_t)21 * n)); TOB_CUDA(c, c->scratch2.ensure((size_t)4 * n)); TOB_CUDA(c, c->scratch8.ensure(n));
+  TOB_TRY(upload(c, c->scratch, P, (size_t)18 * n)); TOB_TRY(upload(c, c->scratch, q, (size_t)3 * n, (size_t)18 * n));
+  k_plane_point_batch<<<div_up(n, 64), 64, 0, c->stream>>>(c->scratch.p, c->scratch.p + (size_t)18 * n, n, distance, c->prm.offset,
+                                                         c->scratch8.p, c->scratch2.p, c->scratch2.p + (size_t)3 * n);
+  TOB_LAUNCH_CHECK(c);
+  TOB_CUDA(c, cudaMemcpyAsync(ok, c->scratch8.p, n, cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(cc, c->scratch2.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(d, c->scratch2.p + (size_t)3 * n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int tob_plane_hulls_batch(tob_ctx* c, const double* P0, const double* P1, int n, double distance, int refine, uint8_t* ok,
+                          double* cc, double* d) {
+  TOB_TRY(need(c, false, false));
+  cudaSetDevice(c->device);
+  TOB_CUDA(c, c->scratch.ensure((size_t)36 * n)); TOB_CUDA(c, c->scratch2.ensure((size_t)4 * n)); TOB_CUDA(c, c->scratch8.ensure(n));
+  TOB_TRY(upload(c, c->scratch, P0, (size_t)18 * n)); TOB_TRY(upload(c, c->scratch, P1, (size_t)18 * n, (size_t)18 * n));
+  k_plane_hulls_batch<<<div_up(n, 64), 64, 0, c->stream>>>(c->scratch.p, c->scratch.p + (size_t)18 * n, n, distance, c->prm.offset,
+                                                         c->prm.margin, refine, c->scratch8.p, c->scratch2.p,
+                                                         c->scratch2.p + (size_t)3 * n);
+  TOB_LAUNCH_CHECK(c);
+  TOB_CUDA(c, cudaMemcpyAsync(ok, c->scratch8.p, n, cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(cc, c->scratch2.p, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(d, c->scratch2.p + (size_t)3 * n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- planes ------------------------------------------------------------------------------------------------------------
+int tob_separate_planes(tob_ctx* c, const double* splines, int n_robots, int with_self, uint32_t* offsets, double* cc,
+                        double* dd, uint64_t cap, uint64_t* total) {
+  TOB_TRY(need(c, true, true));
+  cudaSetDevice(c->device);
+  if (with_self && n_robots != c->n_robots()) return fail_msg(c, "with_self needs all uav_num robots");
+  TOB_TRY(stage_splines(c, splines, nullptr, n_robots));
+  TOB_TRY(separate_resident(c, 0, n_robots, with_self));
+  uint64_t np = c->n_planes;
+  if (total) *total = np;
+  const int rows = n_robots * c->n_tr;
+  std::vector<uint32_t> off(c->rows_all() + 1);
+  TOB_CUDA(c, cudaMemcpyAsync(off.data(), c->pl_off.p, off.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  std::vector<double> pl(4 * np);
+  if (np && cc && dd && np <= cap)
+    TOB_CUDA(c, cudaMemcpyAsync(pl.data(), c->pl.p, 4 * np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (offsets) for (int r = 0; r <= rows; r++) offsets[r] = off[r];
+  if (cc && dd && np <= cap)
+    for (uint64_t k = 0; k < np; k++) { cc[3 * k] = pl[4 * k]; cc[3 * k + 1] = pl[4 * k + 1]; cc[3 * k + 2] = pl[4 * k + 2]; dd[k] = pl[4 * k + 3]; }
+  return 0;
+}
+
+int tob_set_planes(tob_ctx* c, int n_robots, const uint32_t* offsets, const double* cc, const double* dd) {
+  TOB_TRY(need(c, true, false));
+  cudaSetDevice(c->device);
+  if (n_robots < 1 || n_robots > c->n_robots()) return fail_msg(c, "tob_set_planes: bad n_robots");
+  return pack_planes_from_host(c, 0, n_robots, offsets, cc, dd);
+}
+
+// ---- energies ----------------------------------------------------------------------------------------------------------
+static int robot_ok(tob_ctx* c, int robot) {
+  if (robot < 0 || robot >= c->n_robots()) return fail_msg(c, "robot index out of range");
+  return 0;
+}
+
+__global__ void k_plane_energy_only(const double* row_e, const int* row_bad, int row0, int n_tr, double* out) {
+  // single thread: ordered sum like the reference's loop over tr_id
+  if (threadIdx.x || blockIdx.x) return;
+  double e = 0; int bad = 0;
+  for (int t = 0; t < n_tr; t++) { e += row_e[2 * (size_t)(row0 + t)]; bad |= row_bad[row0 + t]; }
+  out[0] = e; out[1] = bad;
+}
+
+__global__ void k_bound_energy_only(const double* row_e, const int* row_bad, int row0, int n_tr, double* out) {
+  if (threadIdx.x || blockIdx.x) return;
+  double e = 0; int bad = 0;
+  for (int t = 0; t < n_tr; t++) { e += row_e[2 * (size_t)(row0 + t) + 1]; bad |= row_bad[row0 + t]; }
+  out[0] = e; out[1] = bad;
+}
+
+int tob_plane_barrier_energy(tob_ctx* c, int robot, const double* spline, double* e) {
+  TOB_TRY(need(c, true, false)); TOB_TRY(robot_ok(c, robot));
+  cudaSetDevice(c->device);
+  TOB_TRY(upload(c, c->s_spline, spline, 3 * c->T, (size_t)robot * 3 * c->T));
+  // a huge piece time switches the bound terms off without touching the plane sum
+  double big = 1e300;
+  TOB_TRY(upload(c, c->s_ptrial, &big, 1, robot));
+  TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, robot, robot + 1, 0));
+  TOB_TRY(energy_rows(c, robot, robot + 1, c->s_spline.p, nullptr, nullptr, c->s_ptrial.p, c->s_e1.p));
+  k_plane_energy_only<<<1, 32, 0, c->stream>>>(c->row_e.p, c->row_bad.p, robot * c->n_tr, c->n_tr, c->red.p);
+  TOB_LAUNCH_CHECK(c);
+  TOB_TRY(read_back(c, c->red.p, 2 * sizeof(double)));
+  *e = c->h_pinned[1] != 0 ? INFINITY : c->h_pinned[0];
+  return 0;
+}
+
+int tob_bound_energy(tob_ctx* c, const double* spline, double piece_time, double* e) {
+  TOB_TRY(need(c, true, false));
+  cudaSetDevice(c->device);
+  if (c->n_planes == 0 && !c->pl_off.p) {   // no plane set yet: install an empty one
+    std::vector<uint32_t> off(c->n_tr + 1, 0u);
+    TOB_TRY(pack_planes_from_host(c, 0, 1, off.data(), nullptr, nullptr));
+  }
+  TOB_TRY(upload(c, c->s_spline, spline, 3 * c->T, 0));
+  TOB_TRY(upload(c, c->s_ptrial, &piece_time, 1, 0));
+  TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, 0, 1, 0));
+  TOB_TRY(energy_rows(c, 0, 1, c->s_spline.p, nullptr, nullptr, c->s_ptrial.p, c->s_e1.p));
+  k_bound_energy_only<<<1, 32, 0, c->stream>>>(c->row_e.p, c->row_bad.p, 0, c->n_tr, c->red.p);
+  TOB_LAUNCH_CHECK(c);
+  TOB_TRY(read_back(c, c->red.p, 2 * sizeof(double)));
+  *e = c->h_pinned[1] != 0 ? INFINITY : c->h_pinned[0];
+  return 0;
+}
+
+int tob_spline_energy(tob_ctx* c, int robot, const tob_state* st, double* e) {
+  TOB_TRY(need(c, true, false)); TOB_TRY(robot_ok(c, robot));
+  cudaSetDevice(c->device);
+  TOB_TRY(put_state(c, robot, st));
+  TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, robot, robot + 1, 0));
+  TOB_TRY(energy_rows(c, robot, robot + 1, c->s_spline.p, nullptr, nullptr, c->s_ptime.p, c->s_e1.p));
+  TOB_TRY(read_back(c, c->s_e1.p + robot, sizeof(double)));
+  *e = c->h_pinned[0];
+  return 0;
+}
+
+// ---- gradient / direction -------------------------------------------------------------------------------------------------
+int tob_piece_blocks(tob_ctx* c, int robot, const tob_state* st, int project_psd, double* g, double* h) {
+  TOB_TRY(need(c, true, false)); TOB_TRY(robot_ok(c, robot));
+  cudaSetDevice(c->device);
+  const int P = c->prm.piece_num;
+  TOB_TRY(put_state(c, robot, st));
+  TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, robot, robot + 1, 0));
+  TOB_TRY(gradient_blocks(c, robot, robot + 1, project_psd));
+  TOB_CUDA(c, cudaMemcpyAsync(g, c->pc_g.p + (size_t)19 * robot * P, (size_t)19 * P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(h, c->pc_h.p + (size_t)361 * robot * P, (size_t)361 * P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int tob_global_gradient(tob_ctx* c, int robot, const tob_state* st, double* grad, double* hess) {
+  TOB_TRY(need(c, true, false)); TOB_TRY(robot_ok(c, robot));
+  const int P = c->prm.piece_num, n = 3 * c->T;
+  std::vector<double> g((size_t)19 * P), h((size_t)361 * P);
+  TOB_TRY(tob_piece_blocks(c, robot, st, 1, g.data(), h.data()));
+  // scatter-add of Gradient_admm.h:55-62 (dense output only exists for the unchanged signature)
+  const size_t ld = n + 1;
+  for (size_t i = 0; i < ld; i++) grad[i] = 0;
+  for (size_t i = 0; i < ld * ld; i++) hess[i] = 0;
+  for (int sp = 0; sp < P; sp++) {
+    const double* g0 = &g[(size_t)19 * sp];
+    const double* h0 = &h[(size_t)361 * sp];
+    int base = 9 * sp;
+    for (int i = 0; i < 18; i++) grad[base + i] += g0[i];
+    grad[n] += g0[18];
+    for (int j = 0; j < 18; j++)
+      for (int i = 0; i < 18; i++) hess[(base + i) + ld * (base + j)] += h0[i + 19 * j];
+    hess[n + ld * n] += h0[18 + 19 * 18];
+    for (int i = 0; i < 18; i++) {
+      hess[(base + i) + ld * n] += h0[i + 19 * 18];
+      hess[n + ld * (base + i)] += h0[18 + 19 * i];
+    }
+  }
+  return 0;
+}
+
+int tob_descent_direction(tob_ctx* c, int robot, const tob_state* st, int dense_shift, double* direction, double* t_direction,
+                          double* wolfe, double* gnorm) {
+  TOB_TRY(need(c, true, false)); TOB_TRY(robot_ok(c, robot));
+  cudaSetDevice(c->device);
+  TOB_TRY(put_state(c, robot, st));
+  TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, robot, robot + 1, 0));
+  TOB_TRY(gradient_blocks(c, robot, robot + 1, 1));
+  TOB_TRY(solve_directions(c, robot, robot + 1, dense_shift));
+  TOB_CUDA(c, cudaMemcpyAsync(direction, c->s_dir.p + (size_t)robot * 3 * c->T, 3 * c->T * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(t_direction, c->s_tdir.p + robot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(wolfe, c->s_wolfe.p + robot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(gnorm, c->s_gnorm.p + robot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_TRY(read_back(c, c->solve_status.p + robot, sizeof(int)));
+  if (*((int*)c->h_pinned) != 0) return fail_msg(c, "Newton matrix is not positive definite");
+  return 0;
+}
+
+// ---- CCD steps --------------------------------------------------------------------------------------------------------------
+int tob_position_step(tob_ctx* c, const double* spline, const double* direction, double* step) {
+  TOB_TRY(need(c, true, true));
+  cudaSetDevice(c->device);
+  TOB_TRY(stage_splines(c, spline, direction, 1));
+  TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, 0, 1, 3));
+  uint64_t total = 0;
+  TOB_TRY(broadphase(c, 0, 1, c->prm.offset, &total));
+  k_fill_int<<<1, 64, 0, c->stream>>>(c->kmax.p, c->n_robots(), 0);
+  TOB_LAUNCH_CHECK(c);
+  TOB_TRY(ccd_position_steps(c));
+  TOB_TRY(read_back(c, c->kmax.p, sizeof(int)));
+  int k = *((int*)c->h_pinned);
+  double s = 1.0;
+  for (int i = 0; i < k; i++) s *= 0.8;
+  *step = s;
+  return 0;
+}
+
+int tob_self_step(tob_ctx* c, const double* splines, const double* directions, int n_robots, int coupled, double* steps) {
+  TOB_TRY(need(c, true, false));
+  cudaSetDevice(c->device);
+  if (n_robots != c->n_robots()) return fail_msg(c, "tob_self_step needs all uav_num robots");
+  TOB_TRY(stage_splines(c, splines, directions, n_robots));
+  TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, 0, n_robots, 3));
+  TOB_TRY(self_ccd_steps(c, coupled, c->s_selfstep.p));
+  TOB_CUDA(c, cudaMemcpyAsync(steps, c->s_selfstep.p, (coupled ? 1 : n_robots) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int tob_self_broadphase(tob_ctx* c, const double* P, const double* D, int u, double d, uint32_t* pairs, uint64_t cap,
+                        uint64_t* total) {
+  // all-pairs box test of one time slot on the host side of the ABI: u <= 64, at most 2016 pairs; the device
+  // kernels (k_self_planes / k_self_ccd_filter) apply the same predicate inline.
+  if (!c) return 1;
+  uint64_t n = 0;
+  std::vector<double> lo(3 * u), hi(3 * u);
+  for (int i = 0; i < u; i++)
+    for (int k = 0; k < 3; k++) {
+      double l = INFINITY, h = -INFINITY;
+      for (int j = 0; j < 6; j++) {
+        double v = P[(size_t)18 * i + 6 * k + j];
+        if (v < l) l = v; if (v > h) h = v;
+        if (D) { double w = v + D[(size_t)18 * i + 6 * k + j]; if (w < l) l = w; if (w > h) h = w; }
+      }
+      lo[3 * i + k] = l; hi[3 * i + k] = h;
+    }
+  for (int a = 0; a < u; a++)
+    for (int b = a + 1; b < u; b++) {
+      bool hit = true;
+      for (int k = 0; k < 3; k++)
+        if (hi[3 * a + k] + d < lo[3 * b + k] || lo[3 * a + k] > hi[3 * b + k] + d) hit = false;
+      if (hit) { if (n < cap && pairs) { pairs[2 * n] = a; pairs[2 * n + 1] = b; } n++; }
+    }
+  if (total) *total = n;
+  return 0;
+}
+
+// ---- slack / dual ---------------------------------------------------------------------------------------------------------------
+int tob_update_slack_lambda(tob_ctx* c, tob_state* st) {
+  TOB_TRY(need(c, true, false));
+  cudaSetDevice(c->device);
+  TOB_TRY(put_state(c, 0, st));
+  TOB_TRY(slack_update(c, 0, 1));
+  TOB_TRY(get_state(c, 0, st));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- iteration ---------------------------------------------------------------------------------------------------------------------
+int tob_states_upload(tob_ctx* c, const tob_state* states, int n_robots) {
+  TOB_TRY(need(c, true, false));
+  cudaSetDevice(c->device);
+  if (n_robots != c->n_robots()) return fail_msg(c, "tob_states_upload: n_robots must equal uav_num");
+  for (int u = 0; u < n_robots; u++) TOB_TRY(put_state(c, u, &states[u]));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->states_valid = true;
+  return 0;
+}
+
+int tob_states_download(tob_ctx* c, tob_state* states, int n_robots) {
+  TOB_TRY(need(c, true, false));
+  cudaSetDevice(c->device);
+  if (n_robots != c->n_robots()) return fail_msg(c, "tob_states_download: n_robots must equal uav_num");
+  for (int u = 0; u < n_robots; u++) TOB_TRY(get_state(c, u, &states[u]));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int tob_admm_iterate(tob_ctx* c, int iters, int mode, double* gnorm) {
+  TOB_TRY(need(c, true, true));
+  cudaSetDevice(c->device);
+  if (!c->states_valid) return fail_msg(c, "tob_admm_iterate: call tob_states_upload first");
+  for (int i = 0; i < iters; i++) TOB_TRY(iterate_once(c, mode, (i == iters - 1) ? gnorm : nullptr));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int tob_optimization(tob_ctx* c, tob_state* states, int n_robots, int mode, double* gnorm) {
+  TOB_TRY(tob_states_upload(c, states, n_robots));
+  TOB_TRY(tob_admm_iterate(c, 1, mode, gnorm));
+  return tob_states_download(c, states, n_robots);
+}
+
+int tob_get_counters(const tob_ctx* c, tob_counters* out) {
+  if (!c || !out) return 1;
+  *out = c->ctr;
+  return 0;
+}
+int tob_reset_counters(tob_ctx* c) {
+  if (!c) return 1;
+  memset(&c->ctr, 0, sizeof(c->ctr));
+  return 0;
+}
+
+int tob_set_shard(tob_ctx* c, int first, int count, int n_total, tob_allgather_fn ag, tob_allreduce_fn ar, void* user) {
+  TOB_TRY(need(c, false, false));
+  if (n_total != c->n_robots() || first < 0 || count < 1 || first + count > n_total) return fail_msg(c, "tob_set_shard: bad range");
+  c->own_begin = first; c->own_end = first + count; c->ag = ag; c->ar = ar; c->cb_user = user;
+  return 0;
+}
+
+void* tob_stream(tob_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+// ---- FP64 pipe peak ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dfma(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, cc = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, b, cc); a1 = fma(a1, b, cc); a2 = fma(a2, b, cc); a3 = fma(a3, b, cc);
+    a4 = fma(a4, b, cc); a5 = fma(a5, b, cc); a6 = fma(a6, b, cc); a7 = fma(a7, b, cc);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+int tob_fp64_peak(tob_ctx* c, double* tflops) {
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  const int blocks = c->sm_count * 8, threads = 256, iters = 1 << 14;
+  TOB_CUDA(c, c->scratch.ensure((size_t)blocks * threads));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_dfma<<<blocks, threads, 0, c->stream>>>(c->scratch.p, iters);
+  float best = 1e30f;
+  for (int r = 0; r < 5; r++) {
+    cudaEventRecord(e0, c->stream);
+    k_dfma<<<blocks, threads, 0, c->stream>>>(c->scratch.p, iters);
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  double flops = 2.0 * 8 * (double)iters * blocks * threads;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,448 @@
+// barrier.cu -- FP64 log-barrier energy, gradient and Hessian-block reductions over (sub-segment x plane) pairs.
+//
+// Replaces Energy_admm::{plane_barrier_energy :46-96, bound_energy :98-170, spline_energy :16-44} and
+// Gradient_admm::{local_plane_barrier_gradient :331-407, local_bound_gradient :409-572, local_spline_gradient :67-164,
+// the per-piece PSD projection of global_spline_gradient :13-65}.
+//
+// Data flow (all per row = robot x sub-segment, planes packed CSR by row, 32 B per plane: cx,cy,cz,d):
+//   k_row_energy   one CTA per row: sum_k sum_{j<6} b(P_j.c_k + d_k), + the 9 velocity/acceleration bound terms
+//   k_robot_energy one CTA per robot: ordered sum over its rows + ADMM consensus terms -> E (inf if any d<=0)
+//   k_row_grad     one CTA per row: the 18x18 rank-1 updates of the reference collapse algebraically to
+//                  H_row = sum_j (b_j b_j^T) (x) S_j with S_j = sum_k e2_jk c_k c_k^T (3x3), g_row = sum_j b_j (x) g_j;
+//                  the bound terms have the same shape (a a^T) (x) M3.  So a row is summarised by 15 "terms"
+//                  (6 plane + 5 velocity + 4 acceleration), 12 doubles each, independent of the plane count.
+//   k_piece        one CTA per (robot, piece): expands the 8x15 terms into the 19x19 block, adds the consensus
+//                  terms, Cholesky test, eigen-shift when not SPD.
+// Reductions are fixed-order (shuffle tree + ordered cross-warp sum): bitwise reproducible run to run.
+// Tolerance vs the reference: summation order differs, FMA contraction allowed here -> ~1e-13 relative.
+#include "ctx.cuh"
+#include "dense.cuh"
+
+namespace tob {
+
+#define ROW_TERMS 15
+#define TERM_SZ 12                 // M3: xx xy xz yy yz zz | g3 | pg3
+#define ROW_REC (ROW_TERMS * TERM_SZ + 2)
+
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- energy --------------------------------------------------------------------------------------------------------
+struct EnergyArgs {
+  const double* P;          // rows x 18 (trial point)
+  const double* pl;         // planes x 4
+  const uint32_t* pl_off;   // rows+1
+  const double* weight;     // n_tr
+  const double* ptime;      // per robot trial piece time
+  double margin, vel_limit, acc_limit;
+  int n_tr, row_begin;
+  double* row_e;            // rows x 2 : plane barrier, bound
+  int* row_bad;             // rows
+};
+
+__global__ void __launch_bounds__(128) k_row_energy(EnergyArgs a) {
+  const int row = a.row_begin + blockIdx.x;
+  const int robot = row / a.n_tr, tr = row - robot * a.n_tr;
+  __shared__ double sP[18];
+  __shared__ double s_part[4];
+  __shared__ int s_bad;
+  if (threadIdx.x < 18) sP[threadIdx.x] = a.P[(size_t)18 * row + threadIdx.x];
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  const double w = a.weight[tr], m = a.margin;
+  double e = 0;
+  int bad = 0;
+  const uint32_t k0 = a.pl_off[row], k1 = a.pl_off[row + 1];
+  for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+    const double4 pl = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * k);
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      double d = sP[j] * pl.x + sP[j + 6] * pl.y + sP[j + 12] * pl.z + pl.w;
+      if (d <= 0) bad = 1;
+      else if (d < m) e += -w * (d - m) * (d - m) * log(d / m);
+    }
+  }
+  // bound terms: threads 0..4 velocity, 5..8 acceleration
+  double eb = 0;
+  if (threadIdx.x < 9) {
+    const double t = a.ptime[robot];
+    double d;
+    if (threadIdx.x < 5) {
+      int j = threadIdx.x;
+      double vx = 5 * (sP[j + 1] - sP[j]), vy = 5 * (sP[j + 7] - sP[j + 6]), vz = 5 * (sP[j + 13] - sP[j + 12]);
+      d = a.vel_limit - sqrt(vx * vx + vy * vy + vz * vz) / (w * t);
+    } else {
+      int j = threadIdx.x - 5;
+      double ax = 20 * (sP[j + 2] - 2 * sP[j + 1] + sP[j]), ay = 20 * (sP[j + 8] - 2 * sP[j + 7] + sP[j + 6]),
+             az = 20 * (sP[j + 14] - 2 * sP[j + 13] + sP[j + 12]);
+      d = a.acc_limit - sqrt(ax * ax + ay * ay + az * az) / (w * w * t * t);
+    }
+    if (d <= 0) bad = 1;
+    else if (d < m) eb = -w * (d - m) * (d - m) * log(d / m);
+  }
+  e = warp_sum(e);
+  eb = warp_sum(eb);
+  if (bad) atomicOr(&s_bad, 1);
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  if (lane == 0) s_part[wp] = e;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a.row_e[2 * (size_t)row] = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
+    a.row_e[2 * (size_t)row + 1] = eb;
+    a.row_bad[row] = s_bad;
+  }
+}
+
+struct RobotEnergyArgs {
+  const double *spline, *dir, *step;            // robots x 3T ; step per robot (may be null => 0)
+  const double *ptime_trial;                    // per robot
+  const double *pslack, *tslack, *plambda, *tlambda, *convert;
+  const double* row_e;
+  const int* row_bad;
+  double lambda, mu;
+  int n_tr, P, T, robot_begin;
+  double* e_out;                                // per robot
+};
+
+__global__ void __launch_bounds__(128) k_robot_energy(RobotEnergyArgs a) {
+  const int robot = a.robot_begin + blockIdx.x;
+  __shared__ double s_part[4];
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  double e = 0;
+  int bad = 0;
+  for (int tr = threadIdx.x; tr < a.n_tr; tr += blockDim.x) {
+    size_t row = (size_t)robot * a.n_tr + tr;
+    e += a.lambda * a.row_e[2 * row] + a.lambda * a.row_e[2 * row + 1];
+    bad |= a.row_bad[row];
+  }
+  // consensus terms, one thread per piece
+  const double t = a.ptime_trial[robot];
+  const double st = a.step ? a.step[robot] : 0.0;
+  for (int sp = threadIdx.x; sp < a.P; sp += blockDim.x) {
+    const double* C = a.convert + (size_t)36 * sp;
+    double acc = 0;
+    for (int ax = 0; ax < 3; ax++) {
+      double bz[6];
+      for (int k = 0; k < 6; k++) {
+        size_t g = (size_t)robot * 3 * a.T + (size_t)ax * a.T + 3 * sp + k;
+        bz[k] = a.spline[g] + (a.dir ? st * a.dir[g] : 0.0);
+      }
+      for (int r = 0; r < 6; r++) {
+        double cx = 0;
+        for (int k = 0; k < 6; k++) cx += C[r + 6 * k] * bz[k];
+        size_t s = (size_t)robot * 18 * a.P + (size_t)ax * 6 * a.P + 6 * sp + r;
+        double pd = cx - a.pslack[s];
+        acc += a.mu / 2.0 * pd * pd + a.plambda[s] * pd;
+      }
+    }
+    double dt = t - a.tslack[(size_t)robot * a.P + sp];
+    acc += a.mu / 2.0 * dt * dt + a.tlambda[(size_t)robot * a.P + sp] * dt;
+    e += acc;
+  }
+  e = warp_sum(e);
+  if (bad) atomicOr(&s_bad, 1);
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  if (lane == 0) s_part[wp] = e;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
+    a.e_out[robot] = s_bad ? INFINITY : tot;
+  }
+}
+
+// trial point = spline + step*dir, trial piece time = ptime + step*tdir.  geo.P must hold the trial rows
+// (compute_rows mode 4) for robots [rb, re).  e_dev: per robot.
+int energy_rows(tob_ctx* c, int rb, int re, const double* spline, const double* dir, const double* step,
+                const double* ptime_trial, double* e_dev) {
+  int rows_total = c->n_robots() * c->n_tr;
+  TOB_CUDA(c, c->row_e.ensure((size_t)2 * rows_total));
+  TOB_CUDA(c, c->row_bad.ensure(rows_total));
+  EnergyArgs a;
+  a.P = c->geo.P.p; a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p; a.ptime = ptime_trial;
+  a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
+  a.n_tr = c->n_tr; a.row_begin = rb * c->n_tr; a.row_e = c->row_e.p; a.row_bad = c->row_bad.p;
+  int nrows = (re - rb) * c->n_tr;
+  k_row_energy<<<nrows, 128, 0, c->stream>>>(a);
+  TOB_LAUNCH_CHECK(c);
+  RobotEnergyArgs b;
+  b.spline = spline; b.dir = dir; b.step = step; b.ptime_trial = ptime_trial;
+  b.pslack = c->s_pslack.p; b.tslack = c->s_tslack.p; b.plambda = c->s_plambda.p; b.tlambda = c->s_tlambda.p;
+  b.convert = c->d_convert.p; b.row_e = c->row_e.p; b.row_bad = c->row_bad.p;
+  b.lambda = c->prm.lambda; b.mu = c->prm.mu; b.n_tr = c->n_tr; b.P = c->prm.piece_num; b.T = c->T; b.robot_begin = rb;
+  b.e_out = e_dev;
+  k_robot_energy<<<re - rb, 128, 0, c->stream>>>(b);
+  TOB_LAUNCH_CHECK(c);
+  c->ctr.energy_plane_evals += c->n_planes;
+  return 0;
+}
+
+// ---- gradient: per-row terms ---------------------------------------------------------------------------------------
+struct RowGradArgs {
+  const double* P;
+  const double* pl;
+  const uint32_t* pl_off;
+  const double* weight;
+  const double* ptime;     // per robot (current)
+  double margin, vel_limit, acc_limit;
+  int n_tr, row_begin;
+  double* terms;           // rows x ROW_REC
+};
+
+__global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
+  const int row = a.row_begin + blockIdx.x;
+  const int robot = row / a.n_tr, tr = row - robot * a.n_tr;
+  __shared__ double sP[18];
+  __shared__ double s_red[4][54];
+  __shared__ double s_gt[9], s_ht[9];
+  if (threadIdx.x < 18) sP[threadIdx.x] = a.P[(size_t)18 * row + threadIdx.x];
+  __syncthreads();
+  const double w = a.weight[tr], m = a.margin;
+  double acc[54];
+#pragma unroll
+  for (int i = 0; i < 54; i++) acc[i] = 0;
+  const uint32_t k0 = a.pl_off[row], k1 = a.pl_off[row + 1];
+  for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+    const double4 pl = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * k);
+    const double cxx = pl.x * pl.x, cxy = pl.x * pl.y, cxz = pl.x * pl.z, cyy = pl.y * pl.y, cyz = pl.y * pl.z, czz = pl.z * pl.z;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      double d = sP[j] * pl.x + sP[j + 6] * pl.y + sP[j + 12] * pl.z + pl.w;
+      if (d < m) {
+        double lg = log(d / m), dm = d - m, id = 1.0 / d;
+        double e1 = -w * (2 * dm * lg + dm * dm * id);
+        double e2 = -w * (2 * lg + 4 * dm * id - dm * dm * id * id);
+        double* q = acc + 9 * j;
+        q[0] += e2 * cxx; q[1] += e2 * cxy; q[2] += e2 * cxz; q[3] += e2 * cyy; q[4] += e2 * cyz; q[5] += e2 * czz;
+        q[6] += e1 * pl.x; q[7] += e1 * pl.y; q[8] += e1 * pl.z;
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 54; i++) {
+    double v = warp_sum(acc[i]);
+    if (lane == 0) s_red[wp][i] = v;
+  }
+  // bound terms, threads 0..8
+  double* out = a.terms + (size_t)ROW_REC * row;
+  if (threadIdx.x < 9) {
+    const double t = a.ptime[robot];
+    double px, py, pz, dn, d, g_t = 0, h_t = 0, coef, e3k;
+    double M3[6] = {0, 0, 0, 0, 0, 0}, g3[3] = {0, 0, 0}, pg3[3] = {0, 0, 0};
+    bool vel = threadIdx.x < 5;
+    double val;   // v or a of the reference
+    if (vel) {
+      int j = threadIdx.x;
+      px = sP[j + 1] - sP[j]; py = sP[j + 7] - sP[j + 6]; pz = sP[j + 13] - sP[j + 12];
+      dn = sqrt(px * px + py * py + pz * pz);
+      val = 5 * dn / w;
+      d = a.vel_limit - val / t;
+      coef = -5 / (w * t);
+    } else {
+      int j = threadIdx.x - 5;
+      px = sP[j + 2] - 2 * sP[j + 1] + sP[j]; py = sP[j + 8] - 2 * sP[j + 7] + sP[j + 6]; pz = sP[j + 14] - 2 * sP[j + 13] + sP[j + 12];
+      dn = sqrt(px * px + py * py + pz * pz);
+      val = 20 * dn / (w * w);
+      d = a.acc_limit - val / (t * t);
+      coef = -20 / ((w * t) * (w * t));
+    }
+    if (d < m) {
+      double lg = log(d / m), dm = d - m;
+      double e1 = -w * (2 * dm * lg + dm * dm / d);
+      double e2 = -w * (2 * lg + 4 * dm / d - dm * dm / (d * d));
+      if (vel) {
+        g_t = e1 * val / (t * t);
+        h_t = -2 * e1 * val / (t * t * t) + e2 * val * val / (t * t * t * t);
+        e3k = -e1 / t + e2 * (a.vel_limit - d) / t;
+      } else {
+        g_t = 2 * e1 * val / (t * t * t);
+        h_t = -6 * e1 * val / (t * t * t * t) + 4 * e2 * val * val / (t * t * t * t * t * t);
+        e3k = -2 * e1 / t + 2 * e2 * (a.acc_limit - d) / t;
+      }
+      double dp[3] = {coef * px / dn, coef * py / dn, coef * pz / dn};
+      double i1 = 1.0 / dn, i3 = 1.0 / (dn * dn * dn);
+      double pv[3] = {px, py, pz};
+      // h_p = coef * (I/dn - p p^T / dn^3)
+      int q = 0;
+      for (int r = 0; r < 3; r++)
+        for (int s = r; s < 3; s++) {
+          double hp = coef * ((r == s ? i1 : 0.0) - pv[r] * pv[s] * i3);
+          M3[q++] = e2 * dp[r] * dp[s] + e1 * hp;
+        }
+      for (int r = 0; r < 3; r++) { g3[r] = e1 * dp[r]; pg3[r] = e3k * dp[r]; }
+    }
+    double* o = out + (size_t)TERM_SZ * (6 + threadIdx.x);
+    for (int i = 0; i < 6; i++) o[i] = M3[i];
+    for (int i = 0; i < 3; i++) { o[6 + i] = g3[i]; o[9 + i] = pg3[i]; }
+    s_gt[threadIdx.x] = g_t; s_ht[threadIdx.x] = h_t;
+  }
+  __syncthreads();
+  if (threadIdx.x < 54) {
+    int i = threadIdx.x;
+    double v = (s_red[0][i] + s_red[1][i]) + (s_red[2][i] + s_red[3][i]);
+    int j = i / 9, q = i - 9 * j;
+    double* o = out + (size_t)TERM_SZ * j;
+    o[q] = v;
+    if (q < 3) o[9 + q] = 0.0;   // plane terms carry no time coupling
+  }
+  if (threadIdx.x == 64) {
+    double g = 0, h = 0;
+    for (int i = 0; i < 9; i++) { g += s_gt[i]; h += s_ht[i]; }
+    out[ROW_TERMS * TERM_SZ] = g;
+    out[ROW_TERMS * TERM_SZ + 1] = h;
+  }
+}
+
+// ---- gradient: per-piece 19x19 block -----------------------------------------------------------------------------
+struct PieceArgs {
+  const double *terms, *basis, *convert;
+  const double *spline, *ptime, *pslack, *tslack, *plambda, *tlambda;
+  double lambda, mu;
+  int n_tr, res, P, T, robot_begin, project_psd;
+  double *pc_g, *pc_h;   // (robots*P) x 19 / x 361 (col-major)
+  int* pc_flag;          // 0 SPD, 1 shifted, 2 LLT failed but lambda_min >= 0
+};
+
+__global__ void __launch_bounds__(384) k_piece(PieceArgs a) {
+  extern __shared__ double sm[];
+  const int robot = a.robot_begin + blockIdx.x / a.P, sp = blockIdx.x % a.P;
+  const int nterm = a.res * ROW_TERMS;
+  double* s_a = sm;                       // nterm x 6   a-vectors
+  double* s_t = s_a + nterm * 6;          // nterm x 12  term payloads
+  double* s_H = s_t + nterm * TERM_SZ;    // 361
+  double* s_L = s_H + 361;                // 361 scratch
+  double* s_x = s_L + 361;                // 36: x1 (18) x2 (18) as [m][k]
+  double* s_sc = s_x + 36;                // gt, ht
+  const double* C = a.convert + (size_t)36 * sp;
+  for (int i = threadIdx.x; i < nterm * 6; i += blockDim.x) {
+    int term = i / 6, mm = i - 6 * term;
+    int rr = term / ROW_TERMS, tt = term - ROW_TERMS * rr;
+    const double* B = a.basis + (size_t)36 * (sp * a.res + rr);
+    double v;
+    if (tt < 6) v = B[tt + 6 * mm];
+    else if (tt < 11) { int j = tt - 6; v = B[j + 1 + 6 * mm] - B[j + 6 * mm]; }
+    else { int j = tt - 11; v = B[j + 2 + 6 * mm] - 2 * B[j + 1 + 6 * mm] + B[j + 6 * mm]; }
+    s_a[i] = v;
+  }
+  for (int i = threadIdx.x; i < nterm * TERM_SZ; i += blockDim.x) {
+    int term = i / TERM_SZ, q = i - TERM_SZ * term;
+    int rr = term / ROW_TERMS, tt = term - ROW_TERMS * rr;
+    size_t row = (size_t)robot * a.n_tr + sp * a.res + rr;
+    s_t[i] = a.terms[(size_t)ROW_REC * row + TERM_SZ * tt + q];
+  }
+  if (threadIdx.x < 36) {
+    // x1 = C^T (C bz - p_slack), x2 = C^T lambda ; index [m][k]
+    int which = threadIdx.x / 18, mk = threadIdx.x % 18, mm = mk / 3, k = mk % 3;
+    double acc = 0;
+    for (int r = 0; r < 6; r++) {
+      size_t s = (size_t)robot * 18 * a.P + (size_t)k * 6 * a.P + 6 * sp + r;
+      double val;
+      if (which == 0) {
+        double cx = 0;
+        for (int kk = 0; kk < 6; kk++) cx += C[r + 6 * kk] * a.spline[(size_t)robot * 3 * a.T + (size_t)k * a.T + 3 * sp + kk];
+        val = cx - a.pslack[s];
+      } else val = a.plambda[s];
+      acc += C[r + 6 * mm] * val;
+    }
+    s_x[threadIdx.x] = acc;
+  }
+  if (threadIdx.x == 36) {
+    double g = 0, h = 0;
+    for (int rr = 0; rr < a.res; rr++) {
+      size_t row = (size_t)robot * a.n_tr + sp * a.res + rr;
+      g += a.terms[(size_t)ROW_REC * row + ROW_TERMS * TERM_SZ];
+      h += a.terms[(size_t)ROW_REC * row + ROW_TERMS * TERM_SZ + 1];
+    }
+    s_sc[0] = g; s_sc[1] = h;
+  }
+  __syncthreads();
+  const size_t pb = (size_t)robot * a.P + sp;
+  double* G = a.pc_g + 19 * pb;
+  // Hessian entries
+  for (int e = threadIdx.x; e < 361; e += blockDim.x) {
+    int r = e % 19, cc = e / 19;
+    double v = 0;
+    if (r < 18 && cc < 18) {
+      int m1 = r / 3, k1 = r % 3, m2 = cc / 3, k2 = cc % 3;
+      int lo = k1 < k2 ? k1 : k2, hi = k1 < k2 ? k2 : k1;
+      int q = lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);   // xx xy xz yy yz zz
+      for (int t = 0; t < nterm; t++) v += s_a[6 * t + m1] * s_a[6 * t + m2] * s_t[TERM_SZ * t + q];
+      v *= a.lambda;
+      if (k1 == k2) {
+        double ctc = 0;
+        for (int rr = 0; rr < 6; rr++) ctc += C[rr + 6 * m1] * C[rr + 6 * m2];
+        v += a.mu * ctc;
+      }
+    } else if (r == 18 && cc == 18) {
+      v = a.lambda * s_sc[1] + a.mu;
+    } else {
+      int idx = r == 18 ? cc : r;
+      int m1 = idx / 3, k1 = idx % 3;
+      for (int t = 0; t < nterm; t++) v += s_a[6 * t + m1] * s_t[TERM_SZ * t + 9 + k1];
+      v *= a.lambda;
+    }
+    s_H[e] = v;
+  }
+  if (threadIdx.x < 19) {
+    int r = threadIdx.x;
+    double v;
+    if (r < 18) {
+      int m1 = r / 3, k1 = r % 3;
+      v = 0;
+      for (int t = 0; t < nterm; t++) v += s_a[6 * t + m1] * s_t[TERM_SZ * t + 6 + k1];
+      v = a.lambda * v + a.mu * s_x[r] + s_x[18 + r];
+    } else {
+      v = a.lambda * s_sc[0] + a.mu * (a.ptime[robot] - a.tslack[pb]) + a.tlambda[pb];
+    }
+    G[r] = v;
+  }
+  __syncthreads();
+  int flag = 0;
+  if (a.project_psd && threadIdx.x == 0) {
+    if (!chol_is_spd_n(s_H, s_L, 19)) {
+      for (int i = 0; i < 361; i++) s_L[i] = s_H[i];
+      double mn = jacobi_min_eig_n(s_L, 19);
+      if (mn < 0) {
+        for (int k = 0; k < 19; k++) s_H[k + 19 * k] = s_H[k + 19 * k] - mn * 1.0 + 0.01 * 1.0;
+        flag = 1;
+      } else flag = 2;
+    }
+    a.pc_flag[pb] = flag;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 361; e += blockDim.x) a.pc_h[361 * pb + e] = s_H[e];
+}
+
+// geo.P must hold the CURRENT rows of robots [rb,re) (compute_rows without trial); planes resident.
+int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd) {
+  int rows_total = c->n_robots() * c->n_tr;
+  int P = c->prm.piece_num;
+  TOB_CUDA(c, c->row_terms.ensure((size_t)ROW_REC * rows_total));
+  TOB_CUDA(c, c->pc_g.ensure((size_t)19 * c->n_robots() * P));
+  TOB_CUDA(c, c->pc_h.ensure((size_t)361 * c->n_robots() * P));
+  TOB_CUDA(c, c->pc_flag.ensure((size_t)c->n_robots() * P));
+  RowGradArgs a;
+  a.P = c->geo.P.p; a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p; a.ptime = c->s_ptime.p;
+  a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
+  a.n_tr = c->n_tr; a.row_begin = rb * c->n_tr; a.terms = c->row_terms.p;
+  k_row_grad<<<(re - rb) * c->n_tr, 128, 0, c->stream>>>(a);
+  TOB_LAUNCH_CHECK(c);
+  PieceArgs b;
+  b.terms = c->row_terms.p; b.basis = c->d_basis.p; b.convert = c->d_convert.p;
+  b.spline = c->s_spline.p; b.ptime = c->s_ptime.p; b.pslack = c->s_pslack.p; b.tslack = c->s_tslack.p;
+  b.plambda = c->s_plambda.p; b.tlambda = c->s_tlambda.p;
+  b.lambda = c->prm.lambda; b.mu = c->prm.mu; b.n_tr = c->n_tr; b.res = c->prm.res; b.P = P; b.T = c->T;
+  b.robot_begin = rb; b.project_psd = project_psd;
+  b.pc_g = c->pc_g.p; b.pc_h = c->pc_h.p; b.pc_flag = c->pc_flag.p;
+  size_t smem = ((size_t)c->prm.res * ROW_TERMS * (6 + TERM_SZ) + 361 * 2 + 36 + 2) * sizeof(double);
+  k_piece<<<(re - rb) * P, 384, smem, c->stream>>>(b);
+  TOB_LAUNCH_CHECK(c);
+  c->ctr.energy_plane_evals += c->n_planes;
+  return 0;
+}
+
+}  // namespace tob

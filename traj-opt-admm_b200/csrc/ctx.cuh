@@ -1,0 +1,173 @@
+// ctx.cuh -- context object behind the C ABI (include/trajopt_b200.h) and shared launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/trajopt_b200.h"
+
+#define TOB_MAX_LEVELS 8
+#define TOB_LADDER 400       // longest 0.8^k ladder the CCD kernels will walk
+
+namespace tob {
+
+// growable device buffer (contents are NOT preserved on growth)
+template <typename T>
+struct DBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap && p) return cudaSuccess;
+    size_t want = n + n / 4 + 256;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// per-row (robot x sub-segment) geometry produced by segments.cu, indexed by GLOBAL row = robot*n_tr + tr
+struct RowGeom {
+  DBuf<double> P;      // rows x 18  (6x3 col-major: P[j + 6*axis])
+  DBuf<double> D;      // rows x 18  direction control points (CCD)
+  DBuf<double> box;    // rows x 6   lo xyz, hi xyz
+  DBuf<double> klo;    // rows x 49  k-DOP extents of P
+  DBuf<double> khi;    // rows x 49
+};
+
+struct Level {         // one level of the 32-wide LBVH, SoA boxes
+  uint32_t count = 0;
+  double* lo[3] = {nullptr, nullptr, nullptr};
+  double* hi[3] = {nullptr, nullptr, nullptr};
+};
+
+}  // namespace tob
+
+struct tob_ctx {
+  int device = 0;
+  int sm_count = 0, cc_major = 0, cc_minor = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  tob_params prm{};
+  bool have_params = false, have_tables = false;
+  int n_tr = 0, T = 0;
+
+  // tables: host copies + device
+  std::vector<double> h_basis, h_weight, h_convert, h_mdyn, h_kdop;
+  tob::DBuf<double> d_basis, d_weight, d_convert, d_mdyn, d_kdop;
+  tob::DBuf<double> d_steps;   // 0.8^k ladder, built by repeated multiplication like the reference's step*=0.8
+
+  // cloud + LBVH
+  uint32_t n_pts = 0, n_pad = 0;
+  tob::DBuf<double> px, py, pz;
+  tob::DBuf<uint32_t> pid;
+  std::vector<uint32_t> h_pid;
+  tob::DBuf<double> lvl_store;
+  int n_levels = 0;
+  tob::Level lvl[TOB_MAX_LEVELS];
+
+  // robot states on device; all arrays hold prm.uav_num robots.  Owned robots = [own_begin, own_end)
+  int own_begin = 0, own_end = 0;
+  tob_allgather_fn ag = nullptr;
+  tob_allreduce_fn ar = nullptr;
+  void* cb_user = nullptr;
+  bool states_valid = false;
+  tob::DBuf<double> s_spline, s_ptime, s_pslack, s_tslack, s_plambda, s_tlambda;
+  tob::DBuf<double> s_dir, s_tdir, s_wolfe, s_gnorm;
+  tob::DBuf<double> s_step, s_selfstep, s_ptrial, s_e0, s_e1;
+  tob::DBuf<int> s_done, solve_status;
+
+  // per-row geometry + broadphase scratch
+  tob::RowGeom geo;
+  tob::DBuf<uint32_t> task_cnt, task_off, scan_tmp;
+  tob::DBuf<uint32_t> cand_pt, cand_row;
+  tob::DBuf<uint32_t> row_off;        // (all rows)+1 candidate offsets; rows outside the queried range are empty
+  uint64_t n_cand = 0;
+
+  // planes: candidate-indexed scratch, then packed CSR over ALL rows
+  tob::DBuf<double> cpl;              // cand x 4 (cx,cy,cz,d)
+  tob::DBuf<uint32_t> cflag, cflag_off;
+  tob::DBuf<double> pl;               // planes x 4
+  tob::DBuf<uint32_t> pl_row, pl_off; // plane -> row ; rows+1 offsets
+  tob::DBuf<uint32_t> row_nob, row_ntot;
+  uint64_t n_planes = 0;
+
+  // inter-robot scratch
+  tob::DBuf<double> self_pl;          // n_tr x npairs x 4
+  tob::DBuf<uint32_t> self_ok;        // n_tr x npairs
+
+  // energy / gradient / solve scratch
+  tob::DBuf<double> row_e;
+  tob::DBuf<int> row_bad;
+  tob::DBuf<double> row_terms;
+  tob::DBuf<double> pc_g, pc_h;
+  tob::DBuf<int> pc_flag;
+  tob::DBuf<double> band;
+  tob::DBuf<int> kmax;
+  tob::DBuf<double> red;              // small device scratch (>= 256 doubles)
+  tob::DBuf<double> scratch, scratch2;
+  tob::DBuf<uint8_t> scratch8;
+
+  double* h_pinned = nullptr;         // small pinned read-back area (4 KiB)
+
+  tob_counters ctr{};
+
+  int n_robots() const { return prm.uav_num; }
+  int rows_all() const { return prm.uav_num * n_tr; }
+};
+
+namespace tob {
+
+int fail(tob_ctx* c, const char* what, cudaError_t e, const char* file, int line);
+int fail_msg(tob_ctx* c, const std::string& msg);
+
+#define TOB_CUDA(c, call)                                                          \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) return tob::fail((c), #call, e__, __FILE__, __LINE__); \
+  } while (0)
+#define TOB_TRY(expr)    \
+  do {                   \
+    int r__ = (expr);    \
+    if (r__) return r__; \
+  } while (0)
+#define TOB_LAUNCH_CHECK(c)                                                                  \
+  do {                                                                                       \
+    (c)->ctr.kernel_launches++;                                                              \
+    cudaError_t e__ = cudaGetLastError();                                                    \
+    if (e__ != cudaSuccess) return tob::fail((c), "kernel launch", e__, __FILE__, __LINE__); \
+  } while (0)
+
+inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- module entry points (host side of each .cu) -------------------------------------------------------------
+// tables.cu
+int make_tables_host(const tob_params& p, const double* time_weight, std::vector<double>& basis, std::vector<double>& weight,
+                     std::vector<double>& convert, std::vector<double>& mdyn, std::vector<double>& kdop);
+// lbvh.cu
+int lbvh_build(tob_ctx* c, const double* V_host, uint32_t n);
+int exclusive_scan_u32(tob_ctx* c, const uint32_t* in, uint32_t* out, size_t n, uint32_t* total_dev);  // out[n] = total
+// queries rows [rb*n_tr, re*n_tr) whose boxes are in geo.box; fills cand_pt/cand_row (GLOBAL rows) and row_off
+int broadphase(tob_ctx* c, int rb, int re, double d, uint64_t* total_host);
+// segments.cu : mode bits: 1 = k-DOP extents, 2 = direction rows + swept box, 4 = trial point spline+step*dir
+int compute_rows(tob_ctx* c, const double* spline_dev, const double* dir_dev, const double* step_dev, int rb, int re, int mode);
+// narrow.cu
+int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self);
+int pack_planes_from_host(tob_ctx* c, int rb, int re, const uint32_t* offsets, const double* cc, const double* dd);
+int ccd_position_steps(tob_ctx* c);
+int self_planes(tob_ctx* c);
+int self_ccd_steps(tob_ctx* c, int coupled, double* steps_dev);
+// barrier.cu
+int energy_rows(tob_ctx* c, int rb, int re, const double* spline, const double* dir, const double* step,
+                const double* ptime_trial, double* e_dev);
+int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd);
+// solve.cu
+int solve_directions(tob_ctx* c, int rb, int re, int dense_shift);
+int slack_update(tob_ctx* c, int rb, int re);
+
+}  // namespace tob

@@ -1,0 +1,522 @@
+// gjk.cuh -- FP64 narrowphase math of the hot path: GJK witness vector (signed-volumes sub-algorithm),
+// 49-axis k-DOP separation tests, separating planes, 1-D plane refinement.
+//
+// Parity contract: every function here reproduces the reference's arithmetic operation by operation
+// (same association order, no FMA contraction -- the translation units that include this header are built
+// with --fmad=false; the reference is built for plain SSE2, CMakeLists.txt:24).  That makes the discrete
+// outputs (k-DOP pass/fail, GJK simplex path, accept/reject of a plane, CCD ladder exponent) bit-identical to
+// the reference and (c,d) identical to the last ulp.  Known reference quirks that are part of the behaviour
+// and are therefore kept (see comments in place): the witness simplex keeps the *other* edge's vertices in
+// the "two edges face the origin" case of the 2-simplex routine, stale barycentric weights are read there,
+// and support() keeps the previous support vertex unless a strictly better one exists.
+//
+// Reference map (lib/opengjk/src/openGJK.c): sv_line = S1D :82-159, sv_tri = S2D :164-394,
+// sv_tet = S3D :399-711, support_max = support :714-737, gjk_witness = gjk :754-852.
+// HighOrderCCD/CCD/CCD.h: kdop_* = KDOPDCD :354-413, SelfKDOPDCD :535-587, KDOPCCD :416-473,
+// SelfKDOPCCD :475-533.  HighOrderCCD/Separate.h: plane_point :18-163, plane_hulls :165-304.
+// HighOrderCCD/Optimal_plane.h: refine_d = optimal_d :13-71.
+//
+// The header is also compiled by g++ (tests/hostsim) so the bit-exactness against the compiled reference can
+// be checked on a machine without a GPU; that build is test infrastructure, never a product path.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define TOB_HD __host__ __device__ __forceinline__
+#define TOB_HDN static __host__ __device__ __noinline__
+#else
+#define TOB_HD inline
+#define TOB_HDN inline
+#endif
+
+namespace tob {
+
+#define TOB_KDOP_AXES 49
+
+struct Simplex {
+  int n;
+  double v[4][3];
+  int wid[4];
+  double lam[4];
+};
+
+TOB_HD double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+TOB_HD bool same_sign(double a, double b) { return (a > 0) == (b > 0); }
+TOB_HD double nrm2(const double* v) {
+  double n2 = 0;
+  n2 += v[0] * v[0];
+  n2 += v[1] * v[1];
+  n2 += v[2] * v[2];
+  return n2;
+}
+
+// vv = sum_i lam[i] * v[i], accumulated from 0 in index order
+TOB_HD void combine(const Simplex& s, int cnt, double* vv) {
+  for (int j = 0; j < 3; ++j) {
+    double acc = 0;
+    for (int i = 0; i < cnt; ++i) acc += s.lam[i] * s.v[i][j];
+    vv[j] = acc;
+  }
+}
+
+// closest point to the origin on the 1-simplex (v[0]=B, v[1]=A)
+TOB_HDN void sv_line(Simplex& s, double* vv) {
+  double a[3], b[3], t[3], ft[3];
+  for (int i = 0; i < 3; ++i) {
+    b[i] = s.v[0][i];
+    a[i] = s.v[1][i];
+    t[i] = b[i] - a[i];
+    ft[i] = fabs(t[i]);
+  }
+  int I = 1;
+  if (ft[0] > ft[1]) I = (ft[0] > ft[2]) ? 0 : 2;
+  else if (ft[0] < ft[1]) I = (ft[1] > ft[2]) ? 1 : 2;
+  else if (ft[0] < ft[2]) I = 2;
+  else if (ft[1] < ft[2]) I = 2;
+
+  double pt = dot3(b, t) / dot3(t, t) * (a[I] - b[I]) + b[I];
+  double det_ap = a[I] - pt;
+  double det_pb = pt - b[I];
+  bool fa = same_sign(t[I], -det_ap);
+  bool fb = same_sign(t[I], -det_pb);
+  if (fa && fb) {
+    s.lam[0] = det_ap * -1.0 / t[I];
+    s.lam[1] = 1 - s.lam[0];
+    s.wid[0] = 0; s.wid[1] = 1;
+    s.n = 2;
+  } else if (!fa) {
+    s.lam[0] = 1; s.wid[0] = 0; s.n = 1;
+    for (int i = 0; i < 3; ++i) s.v[0][i] = s.v[1][i];
+  } else {
+    s.lam[0] = 1; s.wid[0] = 1; s.n = 1;
+  }
+  combine(s, s.n, vv);
+}
+
+// closest point to the origin on the 2-simplex (v[0]=C, v[1]=B, v[2]=A)
+TOB_HDN void sv_tri(Simplex& s, double* vv) {
+  double a[3], b[3], c[3], s21[3], s31[3];
+  for (int i = 0; i < 3; ++i) {
+    c[i] = s.v[0][i]; b[i] = s.v[1][i]; a[i] = s.v[2][i];
+    s21[i] = b[i] - a[i];
+    s31[i] = c[i] - a[i];
+  }
+  // cyclic index pairs (k,l) visited by the reference's "k=l; l=i" walk starting from (1,2)
+  const int K[3] = {1, 2, 0}, L[3] = {2, 0, 1};
+  double nu[3], fnu[3];
+  for (int i = 0; i < 3; ++i) {
+    int k = K[i], l = L[i];
+    double m = b[k] * c[l] + a[k] * b[l] + c[k] * a[l] - b[k] * a[l] - c[k] * b[l] - a[k] * c[l];
+    nu[i] = (i == 1) ? -m : m;   // pow(-1.0,i) * m
+    fnu[i] = fabs(nu[i]);
+  }
+  // the reference initialises indexJ[2] = {-1} i.e. {-1,0}; the no-branch-taken case (exact ties) reads out of
+  // bounds there (undefined); we pin it to J = {0,0}, which only matters when the triangle is degenerate and the
+  // isnan() guard below takes over anyway.
+  int I = 1, J0 = 0, J1 = 0;
+  if (fnu[0] > fnu[1]) {
+    if (fnu[0] > fnu[2]) { I = 0; J0 = 1; J1 = 2; } else { J0 = 0; J1 = 1; I = 2; }
+  } else if (fnu[0] < fnu[1]) {
+    if (fnu[1] > fnu[2]) { J0 = 0; I = 1; J1 = 2; } else { J0 = 0; J1 = 1; I = 2; }
+  } else if (fnu[0] < fnu[2]) { J0 = 0; J1 = 1; I = 2; }
+  double nu_max = nu[I];
+
+  double n[3], nn = 0;
+  for (int i = 0; i < 3; ++i) {
+    int k = K[i], l = L[i];
+    n[i] = s21[k] * s31[l] - s21[l] * s31[k];
+    nn += n[i] * n[i];
+  }
+  double inv_len = 1 / sqrt(nn);
+  for (int i = 0; i < 3; ++i) n[i] = n[i] * inv_len;
+  double dna = dot3(n, a);
+  double pp0 = dna * n[J0], pp1 = dna * n[J1];
+  double ss[3][2] = {{a[J0], a[J1]}, {b[J0], b[J1]}, {c[J0], c[J1]}};
+  double B[3];
+  for (int i = 0; i < 3; ++i) {
+    int k = K[i], l = L[i];
+    B[i] = pp0 * ss[k][1] + pp1 * ss[l][0] + ss[k][0] * ss[l][1] - pp0 * ss[l][1] - pp1 * ss[k][0] - ss[l][0] * ss[k][1];
+  }
+  bool f0 = same_sign(nu_max, B[0]), f1 = same_sign(nu_max, B[1]), f2 = same_sign(nu_max, B[2]);
+  double v[3];
+  if ((!f1 && !f2) || isnan(n[0])) {
+    // both edges through A face the origin: try BA and CA, keep the closer one
+    Simplex e;
+    e.n = 2; s.n = 2;
+    e.lam[0] = 0; e.lam[1] = 0; e.wid[0] = 0; e.wid[1] = 0;
+    for (int i = 0; i < 3; ++i) {
+      e.v[0][i] = s.v[1][i];
+      e.v[1][i] = s.v[2][i];
+      s.v[1][i] = s.v[2][i];
+    }
+    sv_line(e, v);
+    sv_line(s, v);
+    double vt[3];
+    combine(e, e.n, vt);
+    combine(s, e.n, v);        // (sic) counted with the other simplex's size: may read a stale weight
+    if (dot3(v, v) < dot3(vt, vt)) {
+      for (int i = 1; i < s.n; ++i) s.wid[i] = s.wid[i] + 1;
+    } else {
+      s.n = e.n;               // (sic) weights and labels of BA, vertices of CA are kept
+      for (int i = 0; i < s.n; ++i) { s.lam[i] = e.lam[i]; s.wid[i] = e.wid[i]; }
+    }
+  } else if (f0 && f1 && f2) {
+    double inv = 1 / nu_max;
+    s.lam[0] = B[2] * inv;
+    s.lam[1] = B[1] * inv;
+    s.lam[2] = 1 - s.lam[0] - s.lam[1];
+    s.wid[0] = 0; s.wid[1] = 1; s.wid[2] = 2;
+    s.n = 3;
+  } else if (!f2) {            // faces AB
+    s.n = 2;
+    for (int i = 0; i < 3; ++i) { s.v[0][i] = s.v[1][i]; s.v[1][i] = s.v[2][i]; }
+    sv_line(s, v);
+  } else if (!f1) {            // faces AC
+    s.n = 2;
+    for (int i = 0; i < 3; ++i) s.v[1][i] = s.v[2][i];
+    sv_line(s, v);
+    for (int i = 1; i < s.n; ++i) s.wid[i] = s.wid[i] + 1;
+  } else {                     // faces BC
+    s.n = 2;
+    sv_line(s, v);
+  }
+  combine(s, s.n, vv);
+}
+
+// vertex of the 3-simplex used by facet candidate `aux` at local slot (2-k): reference TrianglesToTest
+TOB_HD int tri_vertex(int aux, int k) {
+  // {3,3,3, 1,2,2, 0,0,1}[aux + 3k]
+  return (k == 0) ? 3 : (k == 1 ? (aux == 0 ? 1 : 2) : (aux == 2 ? 1 : 0));
+}
+
+// closest point to the origin on the 3-simplex (v[0]=D, v[1]=C, v[2]=B, v[3]=A)
+TOB_HDN void sv_tet(Simplex& s, double* vv) {
+  double a[3], b[3], c[3], d[3];
+  for (int i = 0; i < 3; ++i) { d[i] = s.v[0][i]; c[i] = s.v[1][i]; b[i] = s.v[2][i]; a[i] = s.v[3][i]; }
+  double B[4];
+  B[0] = -1 * (b[0] * c[1] * d[2] + b[1] * c[2] * d[0] + b[2] * c[0] * d[1] - b[2] * c[1] * d[0] - b[1] * c[0] * d[2] - b[0] * c[2] * d[1]);
+  B[1] = +1 * (a[0] * c[1] * d[2] + a[1] * c[2] * d[0] + a[2] * c[0] * d[1] - a[2] * c[1] * d[0] - a[1] * c[0] * d[2] - a[0] * c[2] * d[1]);
+  B[2] = -1 * (a[0] * b[1] * d[2] + a[1] * b[2] * d[0] + a[2] * b[0] * d[1] - a[2] * b[1] * d[0] - a[1] * b[0] * d[2] - a[0] * b[2] * d[1]);
+  B[3] = +1 * (a[0] * b[1] * c[2] + a[1] * b[2] * c[0] + a[2] * b[0] * c[1] - a[2] * b[1] * c[0] - a[1] * b[0] * c[2] - a[0] * b[2] * c[1]);
+  double detM = B[0] + B[1] + B[2] + B[3];
+
+  bool f[4] = {true, true, true, true};
+  const double eps = 1e-13;
+  if (fabs(detM) < eps) {
+    bool z0 = fabs(B[0]) < eps, z1 = fabs(B[1]) < eps, z2 = fabs(B[2]) < eps, z3 = fabs(B[3]) < eps;
+    if (z2 && z3) f[1] = false;
+    else if (z1 && z3) f[2] = false;
+    else if (z1 && z2) f[3] = false;
+    else if (z0 && z3) f[1] = false;
+    else if (z0 && z2) f[1] = false;
+    else if (z0 && z1) f[2] = false;
+    else { f[0] = f[1] = f[2] = f[3] = false; }
+  } else {
+    for (int i = 0; i < 4; ++i) f[i] = same_sign(detM, B[i]);
+  }
+  int n123 = (int)f[1] + (int)f[2] + (int)f[3];
+  double v[3], vt[3];
+
+  if (f[0] && n123 == 3) {
+    double inv = 1 / detM;
+    s.lam[3] = B[0] * inv;
+    s.lam[2] = B[1] * inv;
+    s.lam[1] = B[2] * inv;
+    s.lam[0] = 1 - s.lam[1] - s.lam[2] - s.lam[3];
+    s.wid[0] = 0; s.wid[1] = 1; s.wid[2] = 2; s.wid[3] = 3;
+    s.n = 4;
+  } else if (n123 == 0) {
+    // three facets through A face the origin: evaluate ACD, ABD, ABC and keep the closest
+    Simplex t;
+    t.lam[0] = t.lam[1] = t.lam[2] = t.lam[3] = 0;
+    t.wid[0] = t.wid[1] = t.wid[2] = t.wid[3] = 0;
+    int sid[4] = {0, 0, 0, 0};
+    double tl[4] = {0, 0, 0, 0};
+    int nclosest = 0;
+    double best = 0;
+    for (int i = 0; i < 3; ++i) {
+      t.n = 3;
+      for (int k = 0; k < 3; ++k) {
+        int vid = tri_vertex(i, k);
+        for (int j = 0; j < 3; ++j) t.v[2 - k][j] = s.v[vid][j];
+      }
+      sv_tri(t, v);
+      combine(t, t.n, vt);
+      double dd = dot3(vt, vt);
+      if (i == 0 || dd < best) {
+        best = dd;
+        nclosest = t.n;
+        for (int l = 0; l < nclosest; ++l) { sid[l] = tri_vertex(i, t.wid[l]); tl[l] = t.lam[l]; }
+      }
+    }
+    double keep[4][3];
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 3; ++j) keep[i][j] = s.v[i][j];
+    s.n = nclosest;
+    for (int i = 0; i < s.n; ++i) {
+      for (int j = 0; j < 3; ++j) s.v[nclosest - 1 - i][j] = keep[sid[i]][j];
+      s.lam[i] = tl[i];
+      s.wid[nclosest - 1 - i] = sid[i];
+    }
+  } else if (n123 == 1) {
+    // two facets through A face the origin
+    Simplex t;
+    t.n = 3;
+    t.lam[0] = t.lam[1] = t.lam[2] = t.lam[3] = 0;
+    t.wid[0] = t.wid[1] = t.wid[2] = t.wid[3] = 0;
+    double best = 0;
+    bool used = false;
+    int first = 0, second = 0;
+    if (!f[1]) {               // ACD
+      for (int i = 0; i < 3; ++i) { t.v[0][i] = s.v[0][i]; t.v[1][i] = s.v[1][i]; t.v[2][i] = s.v[3][i]; }
+      sv_tri(t, v);
+      combine(t, t.n, vt);
+      best = dot3(vt, vt);
+      used = true; first = 0;
+    }
+    if (!f[2]) {               // ABD
+      if (!used) {
+        for (int i = 0; i < 3; ++i) { t.v[0][i] = s.v[0][i]; t.v[1][i] = s.v[2][i]; t.v[2][i] = s.v[3][i]; }
+        sv_tri(t, v);
+        combine(t, t.n, vt);
+        best = dot3(vt, vt);
+        first = 1;
+      } else {
+        s.n = 3;
+        for (int i = 0; i < 3; ++i) { s.v[1][i] = s.v[2][i]; s.v[2][i] = s.v[3][i]; }
+        sv_tri(s, v);
+        second = 1;
+      }
+    }
+    if (!f[3]) {               // ABC
+      s.n = 3;
+      for (int i = 0; i < 3; ++i) { s.v[0][i] = s.v[1][i]; s.v[1][i] = s.v[2][i]; s.v[2][i] = s.v[3][i]; }
+      sv_tri(s, v);
+      second = 2;
+    }
+    combine(s, s.n, v);
+    if (dot3(v, v) < best) {
+      for (int i = 0; i < s.n; ++i) s.wid[s.n - 1 - i] = tri_vertex(second, s.wid[i]);   // in place, as the reference
+    } else {
+      s.n = t.n;
+      for (int i = 0; i < s.n; ++i) {
+        for (int j = 0; j < 3; ++j) s.v[i][j] = t.v[i][j];
+        s.lam[i] = t.lam[i];
+        s.wid[t.n - 1 - i] = tri_vertex(first, t.wid[i]);
+      }
+    }
+  } else if (n123 == 2) {
+    if (!f[1]) {               // ACD
+      s.n = 3;
+      for (int i = 0; i < 3; ++i) s.v[2][i] = s.v[3][i];
+      sv_tri(s, v);
+    } else if (!f[2]) {        // ABD
+      s.n = 3;
+      for (int i = 0; i < 3; ++i) { s.v[1][i] = s.v[2][i]; s.v[2][i] = s.v[3][i]; }
+      sv_tri(s, v);
+      for (int i = 2; i < s.n; ++i) s.wid[i] = s.wid[i] + 1;
+    } else if (!f[3]) {        // ABC
+      s.n = 3;
+      for (int i = 0; i < 3; ++i) { s.v[0][i] = s.v[1][i]; s.v[1][i] = s.v[2][i]; s.v[2][i] = s.v[3][i]; }
+      sv_tri(s, v);
+    }
+  } else {                     // only BCD faces the origin
+    s.n = 3;
+    sv_tri(s, v);
+    for (int i = 0; i < s.n; ++i) s.wid[i] = s.wid[i] + 1;
+  }
+  combine(s, s.n, vv);
+}
+
+// support vertex: keeps `cur` unless some vertex is strictly better (scan in index order)
+template <int N>
+TOB_HD void support_max(const double (*pts)[3], double* cur, const double* dir) {
+  double best = dot3(cur, dir);
+  int better = -1;
+  for (int i = 0; i < N; ++i) {
+    double sv = dot3(pts[i], dir);
+    if (sv > best) { best = sv; better = i; }
+  }
+  if (better != -1) { cur[0] = pts[better][0]; cur[1] = pts[better][1]; cur[2] = pts[better][2]; }
+}
+
+// witness vector (closest point of the Minkowski difference A-B to the origin)
+template <int NA, int NB>
+TOB_HD void gjk_witness(const double (*A)[3], const double (*B)[3], double* vout) {
+  Simplex s;
+  s.lam[0] = s.lam[1] = s.lam[2] = s.lam[3] = 0;
+  s.wid[0] = s.wid[1] = s.wid[2] = s.wid[3] = 0;
+  double v[3], vm[3], w[3], sa[3], sb[3];
+  const double eps_rel2 = 1e-5 * 1e-5;
+  const double eps_tot = 1e-15;
+  double wmax = 0;
+  s.n = 1;
+  for (int i = 0; i < 3; ++i) {
+    v[i] = A[0][i] - B[0][i];
+    sa[i] = A[0][i];
+    sb[i] = B[0][i];
+    s.v[0][i] = v[i];
+  }
+  int k = 0;
+  do {
+    k++;
+    vm[0] = -v[0]; vm[1] = -v[1]; vm[2] = -v[2];
+    support_max<NA>(A, sa, vm);
+    if (NB > 1) support_max<NB>(B, sb, v);
+    w[0] = sa[0] - sb[0]; w[1] = sa[1] - sb[1]; w[2] = sa[2] - sb[2];
+    double vv = nrm2(v);
+    if ((vv - dot3(v, w)) <= eps_rel2 * vv) break;
+    if (vv < eps_rel2) break;
+    int i = s.n;
+    s.v[i][0] = w[0]; s.v[i][1] = w[1]; s.v[i][2] = w[2];
+    s.n++;
+    if (s.n == 4) sv_tet(s, v);
+    else if (s.n == 3) sv_tri(s, v);
+    else if (s.n == 2) sv_line(s, v);
+    for (i = 0; i < s.n; i++) {
+      double tn = nrm2(s.v[i]);
+      if (tn > wmax) wmax = tn;
+    }
+    if (nrm2(v) <= (eps_tot * eps_tot * wmax)) break;
+  } while ((s.n != 4) && (k != 50));
+  vout[0] = v[0]; vout[1] = v[1]; vout[2] = v[2];
+}
+
+// ---- k-DOP -------------------------------------------------------------------------------------------
+// level of a point on axis (x,y,z): x*px + y*py + z*pz, left to right
+TOB_HD double kdop_level(double x, double y, double z, const double* p) { return x * p[0] + y * p[1] + z * p[2]; }
+
+// extents [lo,hi] of N points on the 49 axes (kdop: 3x49 column-major = axis k at kdop[3k..3k+2])
+template <int N>
+TOB_HD void kdop_extents(const double (*pts)[3], const double* kdop, double* lo, double* hi) {
+  for (int k = 0; k < TOB_KDOP_AXES; ++k) {
+    double x = kdop[3 * k], y = kdop[3 * k + 1], z = kdop[3 * k + 2];
+    double u = -INFINITY, l = INFINITY;
+    for (int i = 0; i < N; ++i) {
+      double lv = kdop_level(x, y, z, pts[i]);
+      if (lv < l) l = lv;
+      if (lv > u) u = lv;
+    }
+    lo[k] = l; hi[k] = u;
+  }
+}
+
+// segment extents (precomputed) against one point with gap d
+TOB_HD bool kdop_point_overlap(const double* lo, const double* hi, const double* kdop, const double* q, double d) {
+  for (int k = 0; k < TOB_KDOP_AXES; ++k) {
+    double lv = kdop_level(kdop[3 * k], kdop[3 * k + 1], kdop[3 * k + 2], q);
+    if (lv < lo[k] - d || hi[k] < lv - d) return false;
+  }
+  return true;
+}
+
+// two precomputed extent sets with gap d
+TOB_HD bool kdop_sets_overlap(const double* loA, const double* hiA, const double* loB, const double* hiB, double d) {
+  for (int k = 0; k < TOB_KDOP_AXES; ++k)
+    if (hiB[k] < loA[k] - d || hiA[k] < loB[k] - d) return false;
+  return true;
+}
+
+// general (no precomputation) versions used by the function-level entry points
+template <int NA, int NB>
+TOB_HD bool kdop_overlap(const double (*A)[3], const double (*B)[3], const double* kdop, double d) {
+  for (int k = 0; k < TOB_KDOP_AXES; ++k) {
+    double x = kdop[3 * k], y = kdop[3 * k + 1], z = kdop[3 * k + 2];
+    double uA = -INFINITY, lA = INFINITY, uB = -INFINITY, lB = INFINITY;
+    for (int i = 0; i < NA; ++i) {
+      double lv = kdop_level(x, y, z, A[i]);
+      if (lv < lA) lA = lv;
+      if (lv > uA) uA = lv;
+    }
+    for (int i = 0; i < NB; ++i) {
+      double lv = kdop_level(x, y, z, B[i]);
+      if (lv < lB) lB = lv;
+      if (lv > uB) uB = lv;
+    }
+    if (uB < lA - d || uA < lB - d) return false;
+  }
+  return true;
+}
+
+// swept vertex set [P + t0*D ; P + t1*D] (CCD.h:419-420 / :119-120)
+TOB_HD void swept_points(const double (*P)[3], const double (*D)[3], double t0, double t1, double (*out)[3]) {
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 3; ++j) {
+      out[i][j] = P[i][j] + t0 * D[i][j];
+      out[i + 6][j] = P[i][j] + t1 * D[i][j];
+    }
+}
+
+// ---- planes ------------------------------------------------------------------------------------------
+// Eigen::Vector3d::norm() = sqrt of the 3-element reduction, associated left to right (checked bitwise
+// against the compiled reference)
+TOB_HD double eig_norm3(const double* c) { return sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]); }
+
+// segment (6 pts) vs obstacle point: plane n.x + d >= 0 (Separate.h:18-163)
+TOB_HD bool plane_point(const double (*P)[3], const double* q, double distance, double offset, double* c, double* d) {
+  double Bq[1][3] = {{q[0], q[1], q[2]}};
+  gjk_witness<6, 1>(P, Bq, c);
+  double cn = eig_norm3(c);
+  if (cn > distance) return false;
+  c[0] /= cn; c[1] /= cn; c[2] /= cn;
+  double d0 = -c[0] * q[0] - c[1] * q[1] - c[2] * q[2];
+  *d = d0 - offset;
+  return true;
+}
+
+// segment vs segment (Separate.h:165-304): d = midpoint of the two support levels
+TOB_HD bool plane_hulls(const double (*P0)[3], const double (*P1)[3], double distance, double* c, double* d) {
+  gjk_witness<6, 6>(P0, P1, c);
+  double cn = eig_norm3(c);
+  if (cn > distance) return false;
+  c[0] /= cn; c[1] /= cn; c[2] /= cn;
+  double d0 = INFINITY, d1 = -INFINITY;
+  for (int i = 0; i < 6; ++i) {
+    // c.dot(row): fixed-size unrolled reduction x0 + (x1 + x2) (checked bitwise against the compiled reference)
+    double t = -(c[0] * P1[i][0] + (c[1] * P1[i][1] + c[2] * P1[i][2]));
+    if (d0 > t) d0 = t;
+  }
+  for (int i = 0; i < 6; ++i) {
+    double t = -(c[0] * P0[i][0] + (c[1] * P0[i][1] + c[2] * P0[i][2]));
+    if (d1 < t) d1 = t;
+  }
+  *d = 0.5 * (d0 + d1);
+  return true;
+}
+
+// 1-D Newton on d (Optimal_plane.h:13-71); returns the number of Newton steps taken
+TOB_HD int refine_d(const double (*P0)[3], const double (*P1)[3], const double* c, double offset, double margin, double* d_io,
+                    int max_iter) {
+  double d = *d_io;
+  int it = 0;
+  while (true) {
+    double g = 0, h = 0;
+    for (int j = 0; j < 6; ++j) {
+      double dist = (P0[j][0] * c[0] + P0[j][1] * c[1] + P0[j][2] * c[2]) + d - 0.5 * offset;
+      if (dist < margin) {
+        double lg = log(dist / margin);
+        double e1 = -(2 * (dist - margin) * lg + (dist - margin) * (dist - margin) / dist);
+        double e2 = -(2 * lg + 4 * (dist - margin) / dist - (dist - margin) * (dist - margin) / (dist * dist));
+        g += e1; h += e2;
+      }
+    }
+    for (int j = 0; j < 6; ++j) {
+      double dist = -(P1[j][0] * c[0] + P1[j][1] * c[1] + P1[j][2] * c[2]) - d - 0.5 * offset;
+      if (dist < margin) {
+        double lg = log(dist / margin);
+        double e1 = -(2 * (dist - margin) * lg + (dist - margin) * (dist - margin) / dist);
+        double e2 = -(2 * lg + 4 * (dist - margin) / dist - (dist - margin) * (dist - margin) / (dist * dist));
+        g += -e1; h += e2;
+      }
+    }
+    double dir = -g / h;
+    d = d + 1.0 * dir;
+    it++;
+    if (fabs(g) < 1e-2) break;
+    if (it >= max_iter) break;
+  }
+  *d_io = d;
+  return it;
+}
+
+}  // namespace tob
