@@ -165,6 +165,11 @@ typedef struct tob_counters {
 int tob_get_counters(const tob_ctx* ctx, tob_counters* out);
 int tob_reset_counters(tob_ctx* ctx);
 
+/* per-kernel device time (CUDA events on the context's stream around each launch of this library's kernels);
+ * used by bench.py for the roofline of the dominant kernel.  kid = 0.. until the call returns nonzero. */
+int tob_profile_enable(tob_ctx* ctx, int on);
+int tob_profile_read(tob_ctx* ctx, int kid, double* ms_total, uint64_t* launches, const char** name);
+
 /* ---- multi-GPU (robots sharded across ranks; cloud replicated) -------------------------------------------------
  * The context owns robots [first, first+count) of n_total.  The per-iteration exchange (all robots' control
  * points before separate_self, directions before self_step, two scalars) is delegated to two callbacks so the

@@ -27,6 +27,16 @@ int fail_msg(tob_ctx* c, const std::string& msg) {
   return 1;
 }
 
+void prof_collect(tob_ctx* c) {
+  for (auto& r : c->prof_pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { c->prof_ms[r.kid] += ms; c->prof_n[r.kid]++; }
+    c->prof_pool.push_back(r.a);
+    c->prof_pool.push_back(r.b);
+  }
+  c->prof_pending.clear();
+}
+
 static int need(tob_ctx* c, bool tables, bool cloud) {
   if (!c) return fail_msg(c, "null context");
   if (!c->have_params) return fail_msg(c, "tob_set_params has not been called");
@@ -195,8 +205,7 @@ static int iterate_once(tob_ctx* c, int mode, double* gnorm_out) {
   // (1) control points of every robot are needed for the inter-robot planes
   if (U > 1) TOB_TRY(exchange(c, c->s_spline, (size_t)3 * c->T));
   TOB_TRY(separate_resident(c, rb, re, 1));
-  // (2) Newton direction
-  TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, rb, re, 0));
+  // (2) Newton direction (geo.P of the owned rows is still current from the plane pass)
   TOB_TRY(gradient_blocks(c, rb, re, 1));
   TOB_TRY(solve_directions(c, rb, re, U > 1));
   // (3) CCD step bound
@@ -778,6 +787,31 @@ int tob_get_counters(const tob_ctx* c, tob_counters* out) {
 int tob_reset_counters(tob_ctx* c) {
   if (!c) return 1;
   memset(&c->ctr, 0, sizeof(c->ctr));
+  return 0;
+}
+
+static const char* kKernelNames[K_COUNT] = {"k_rows", "k_broadphase<count>", "k_broadphase<fill>", "k_scan(3)", "k_narrow",
+                                            "k_pack_obstacle", "k_self_planes", "k_row_energy", "k_robot_energy", "k_row_grad",
+                                            "k_piece", "k_solve", "k_ccd", "k_self_ccd_filter", "k_slack", "misc"};
+
+int tob_profile_enable(tob_ctx* c, int on) {
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  prof_collect(c);
+  c->prof_on = on != 0;
+  if (on) for (int i = 0; i < 32; i++) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+  return 0;
+}
+
+int tob_profile_read(tob_ctx* c, int kid, double* ms_total, uint64_t* launches, const char** name) {
+  if (!c || kid < 0 || kid >= K_COUNT) return 1;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  prof_collect(c);
+  if (ms_total) *ms_total = c->prof_ms[kid];
+  if (launches) *launches = c->prof_n[kid];
+  if (name) *name = kKernelNames[kid];
   return 0;
 }
 

@@ -166,16 +166,22 @@ int energy_rows(tob_ctx* c, int rb, int re, const double* spline, const double* 
   a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
   a.n_tr = c->n_tr; a.row_begin = rb * c->n_tr; a.row_e = c->row_e.p; a.row_bad = c->row_bad.p;
   int nrows = (re - rb) * c->n_tr;
-  k_row_energy<<<nrows, 128, 0, c->stream>>>(a);
-  TOB_LAUNCH_CHECK(c);
+  {
+    Prof prof(c, K_ROW_ENERGY);
+    k_row_energy<<<nrows, 128, 0, c->stream>>>(a);
+    TOB_LAUNCH_CHECK(c);
+  }
   RobotEnergyArgs b;
   b.spline = spline; b.dir = dir; b.step = step; b.ptime_trial = ptime_trial;
   b.pslack = c->s_pslack.p; b.tslack = c->s_tslack.p; b.plambda = c->s_plambda.p; b.tlambda = c->s_tlambda.p;
   b.convert = c->d_convert.p; b.row_e = c->row_e.p; b.row_bad = c->row_bad.p;
   b.lambda = c->prm.lambda; b.mu = c->prm.mu; b.n_tr = c->n_tr; b.P = c->prm.piece_num; b.T = c->T; b.robot_begin = rb;
   b.e_out = e_dev;
-  k_robot_energy<<<re - rb, 128, 0, c->stream>>>(b);
-  TOB_LAUNCH_CHECK(c);
+  {
+    Prof prof(c, K_ROBOT_ENERGY);
+    k_robot_energy<<<re - rb, 128, 0, c->stream>>>(b);
+    TOB_LAUNCH_CHECK(c);
+  }
   c->ctr.energy_plane_evals += c->n_planes;
   return 0;
 }
@@ -401,17 +407,22 @@ __global__ void __launch_bounds__(384) k_piece(PieceArgs a) {
     G[r] = v;
   }
   __syncthreads();
-  int flag = 0;
-  if (a.project_psd && threadIdx.x == 0) {
-    if (!chol_is_spd_n(s_H, s_L, 19)) {
-      for (int i = 0; i < 361; i++) s_L[i] = s_H[i];
-      double mn = jacobi_min_eig_n(s_L, 19);
+  // PSD projection of Gradient_admm.h:40-53 by warp 0: Cholesky test, then h0 += (-lambda_min + 0.01) I if needed
+  if (a.project_psd && threadIdx.x < 32) {
+    for (int i = threadIdx.x; i < 361; i += 32) s_L[i] = s_H[i];
+    __syncwarp();
+    int flag = 0;
+    if (!warp_chol_is_spd(s_L, 19)) {
+      for (int i = threadIdx.x; i < 361; i += 32) s_L[i] = s_H[i];
+      __syncwarp();
+      double mn = warp_min_eig(s_L, 19, s_x, s_x + 19, s_a, s_a + 19);   // s_x / s_a are free by now (>= 38 doubles each)
+      __syncwarp();
       if (mn < 0) {
-        for (int k = 0; k < 19; k++) s_H[k + 19 * k] = s_H[k + 19 * k] - mn * 1.0 + 0.01 * 1.0;
+        if (threadIdx.x < 19) s_H[threadIdx.x * 20] = s_H[threadIdx.x * 20] - mn * 1.0 + 0.01 * 1.0;
         flag = 1;
       } else flag = 2;
     }
-    a.pc_flag[pb] = flag;
+    if (threadIdx.x == 0) a.pc_flag[pb] = flag;
   }
   __syncthreads();
   for (int e = threadIdx.x; e < 361; e += blockDim.x) a.pc_h[361 * pb + e] = s_H[e];
@@ -429,8 +440,11 @@ int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd) {
   a.P = c->geo.P.p; a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p; a.ptime = c->s_ptime.p;
   a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
   a.n_tr = c->n_tr; a.row_begin = rb * c->n_tr; a.terms = c->row_terms.p;
-  k_row_grad<<<(re - rb) * c->n_tr, 128, 0, c->stream>>>(a);
-  TOB_LAUNCH_CHECK(c);
+  {
+    Prof prof(c, K_ROW_GRAD);
+    k_row_grad<<<(re - rb) * c->n_tr, 128, 0, c->stream>>>(a);
+    TOB_LAUNCH_CHECK(c);
+  }
   PieceArgs b;
   b.terms = c->row_terms.p; b.basis = c->d_basis.p; b.convert = c->d_convert.p;
   b.spline = c->s_spline.p; b.ptime = c->s_ptime.p; b.pslack = c->s_pslack.p; b.tslack = c->s_tslack.p;
@@ -439,8 +453,11 @@ int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd) {
   b.robot_begin = rb; b.project_psd = project_psd;
   b.pc_g = c->pc_g.p; b.pc_h = c->pc_h.p; b.pc_flag = c->pc_flag.p;
   size_t smem = ((size_t)c->prm.res * ROW_TERMS * (6 + TERM_SZ) + 361 * 2 + 36 + 2) * sizeof(double);
-  k_piece<<<(re - rb) * P, 384, smem, c->stream>>>(b);
-  TOB_LAUNCH_CHECK(c);
+  {
+    Prof prof(c, K_PIECE);
+    k_piece<<<(re - rb) * P, 384, smem, c->stream>>>(b);
+    TOB_LAUNCH_CHECK(c);
+  }
   c->ctr.energy_plane_evals += c->n_planes;
   return 0;
 }

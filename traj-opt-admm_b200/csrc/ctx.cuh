@@ -113,9 +113,17 @@ struct tob_ctx {
   tob::DBuf<double> scratch, scratch2;
   tob::DBuf<uint8_t> scratch8;
 
-  double* h_pinned = nullptr;         // small pinned read-back area (4 KiB)
+  double* h_pinned = nullptr;         // small pinned read-back area (64 KiB)
 
   tob_counters ctr{};
+
+  // optional per-kernel CUDA-event timing (bench.py roofline): off by default
+  bool prof_on = false;
+  struct ProfRec { int kid; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[32] = {0};
+  uint64_t prof_n[32] = {0};
 
   int n_robots() const { return prm.uav_num; }
   int rows_all() const { return prm.uav_num * n_tr; }
@@ -144,6 +152,32 @@ int fail_msg(tob_ctx* c, const std::string& msg);
   } while (0)
 
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// kernel ids of the per-kernel timing (names in api.cu: kKernelNames)
+enum KernelId {
+  K_ROWS = 0, K_BP_COUNT, K_BP_FILL, K_SCAN, K_NARROW, K_PACK, K_SELF_PLANES, K_ROW_ENERGY, K_ROBOT_ENERGY, K_ROW_GRAD,
+  K_PIECE, K_SOLVE, K_CCD, K_SELF_CCD, K_SLACK, K_LINESEARCH_MISC, K_COUNT
+};
+
+// scoped CUDA-event pair around ONE kernel launch on the context's stream (no-op unless profiling is enabled)
+struct Prof {
+  tob_ctx* c;
+  bool on;
+  Prof(tob_ctx* ctx, int kid) : c(ctx), on(ctx->prof_on) {
+    if (!on) return;
+    cudaEvent_t ev[2];
+    for (int i = 0; i < 2; i++) {
+      if (!c->prof_pool.empty()) { ev[i] = c->prof_pool.back(); c->prof_pool.pop_back(); }
+      else cudaEventCreate(&ev[i]);
+    }
+    cudaEventRecord(ev[0], c->stream);
+    c->prof_pending.push_back({kid, ev[0], ev[1]});
+  }
+  ~Prof() {
+    if (on) cudaEventRecord(c->prof_pending.back().b, c->stream);
+  }
+};
+void prof_collect(tob_ctx* c);   // after a stream sync: fold pending event pairs into prof_ms / prof_n
 
 // ---- module entry points (host side of each .cu) -------------------------------------------------------------
 // tables.cu

@@ -280,6 +280,7 @@ int exclusive_scan_u32(tob_ctx* c, const uint32_t* in, uint32_t* out, size_t n, 
   uint32_t nb = (uint32_t)((n + SCAN_TILE - 1) / SCAN_TILE);
   if (nb == 0) nb = 1;
   TOB_CUDA(c, c->scan_tmp.ensure(nb + 1));
+  Prof prof(c, K_SCAN);   // the three scan kernels are timed as one unit
   k_scan_reduce<<<nb, SCAN_BLOCK, 0, c->stream>>>(in, n, c->scan_tmp.p);
   TOB_LAUNCH_CHECK(c);
   k_scan_top<<<1, 1024, 0, c->stream>>>(c->scan_tmp.p, nb);
@@ -378,8 +379,11 @@ int broadphase(tob_ctx* c, int rb, int re, double d, uint64_t* total_host) {
   a.task_cnt = c->task_cnt.p; a.task_off = c->task_off.p;
   a.cand_pt = nullptr; a.cand_row = nullptr;
   int nblk = div_up((size_t)a.n_tasks, 256);
-  k_broadphase<false><<<nblk, 256, 0, c->stream>>>(a);
-  TOB_LAUNCH_CHECK(c);
+  {
+    Prof prof(c, K_BP_COUNT);
+    k_broadphase<false><<<nblk, 256, 0, c->stream>>>(a);
+    TOB_LAUNCH_CHECK(c);
+  }
   uint32_t* tot_dev = (uint32_t*)c->red.p;
   TOB_TRY(exclusive_scan_u32(c, c->task_cnt.p, c->task_off.p, a.n_tasks, tot_dev));
   uint32_t* hp = (uint32_t*)c->h_pinned;
@@ -392,6 +396,7 @@ int broadphase(tob_ctx* c, int rb, int re, double d, uint64_t* total_host) {
   TOB_CUDA(c, c->cand_row.ensure(total + 1));
   a.cand_pt = c->cand_pt.p; a.cand_row = c->cand_row.p;
   if (total) {
+    Prof prof(c, K_BP_FILL);
     k_broadphase<true><<<nblk, 256, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }

@@ -168,6 +168,7 @@ int self_planes(tob_ctx* c) {
   a.dist = c->prm.offset + 2 * c->prm.margin; a.offset = c->prm.offset; a.margin = c->prm.margin;
   a.self_pl = c->self_pl.p; a.self_ok = c->self_ok.p;
   if (n) {
+    Prof prof(c, K_SELF_PLANES);
     k_self_planes<<<div_up(n, 64), 64, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
@@ -197,6 +198,7 @@ static int pack_rows(tob_ctx* c, int rb, int re, bool have_cand, bool ws) {
   TOB_CUDA(c, c->pl.ensure(4 * np + 4));
   TOB_CUDA(c, c->pl_row.ensure(np + 1));
   if (nc) {
+    Prof prof(c, K_PACK);
     k_pack_obstacle<<<div_up(nc, 256), 256, 0, st>>>((uint32_t)nc, c->cand_row.p, c->cflag.p, c->cflag_off.p, c->row_off.p,
                                                       c->pl_off.p, c->cpl.p, c->pl.p, c->pl_row.p);
     TOB_LAUNCH_CHECK(c);
@@ -225,6 +227,7 @@ int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self) {
     a.P = c->geo.P.p; a.klo = c->geo.klo.p; a.khi = c->geo.khi.p; a.kdop = c->d_kdop.p;
     a.dist = c->prm.offset + c->prm.margin; a.offset = c->prm.offset;
     a.cpl = c->cpl.p; a.cflag = c->cflag.p;
+    Prof prof(c, K_NARROW);
     k_narrow<<<div_up(nc, 128), 128, 0, st>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
@@ -321,6 +324,7 @@ int ccd_position_steps(tob_ctx* c) {
     a.P = c->geo.P.p; a.D = c->geo.D.p; a.klo = c->geo.klo.p; a.khi = c->geo.khi.p; a.kdop = c->d_kdop.p;
     a.steps = c->d_steps.p; a.offset = c->prm.offset; a.n_tr = c->n_tr; a.first_robot = 0;
     a.kmax = c->kmax.p;
+    Prof prof(c, K_CCD);
     k_ccd<<<div_up(nc, 128), 128, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
@@ -437,6 +441,7 @@ int self_ccd_steps(tob_ctx* c, int coupled, double* steps_dev) {
   a.P = c->geo.P.p; a.D = c->geo.D.p; a.kdop = c->d_kdop.p; a.steps = c->d_steps.p; a.offset = c->prm.offset;
   a.hit = c->self_ok.p; a.kmax = c->kmax.p;
   if (n) {
+    Prof prof(c, K_SELF_CCD);
     k_self_ccd_filter<<<div_up(n, 64), 64, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }

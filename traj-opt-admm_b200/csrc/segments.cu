@@ -98,6 +98,7 @@ int compute_rows(tob_ctx* c, const double* spline_dev, const double* dir_dev, co
   a.P = c->geo.P.p; a.D = c->geo.D.p; a.box = c->geo.box.p; a.klo = c->geo.klo.p; a.khi = c->geo.khi.p;
   a.n_tr = c->n_tr; a.res = c->prm.res; a.T = c->T; a.row_begin = rb * c->n_tr; a.row_end = re * c->n_tr; a.mode = mode;
   if (re > rb) {
+    Prof prof(c, K_ROWS);
     k_rows<<<div_up((re - rb) * c->n_tr, 4), 128, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
   double* vg = va + m;                   // gradient     -> z
   double* g0 = vg + m;                   // copy of the gradient
   double* gx = g0 + m;                   // unused spare
-  __shared__ double s_h, s_gt, s_piv;
+  __shared__ double s_h, s_gt;
   __shared__ int s_fail;
   const int tid = threadIdx.x;
   for (int i = tid; i < m * BW; i += blockDim.x) Bd[i] = 0;
@@ -79,46 +79,56 @@ __global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
     s_h = h; s_gt = gt;
   }
   __syncthreads();
-  // right-looking banded Cholesky, in place: Bd becomes L (L(r, r-k) at Bd[r*BW+k])
-  for (int j = 0; j < m; j++) {
-    if (tid == 0) {
-      double d = Bd[j * BW];
-      if (!(d > 0)) { s_fail = 1; d = 1; }
-      s_piv = sqrt(d);
-      Bd[j * BW] = s_piv;
-    }
-    __syncthreads();
-    const int cnt = (m - 1 - j) < 17 ? (m - 1 - j) : 17;   // rows below the pivot inside the band
-    if (tid < cnt) Bd[(j + 1 + tid) * BW + (tid + 1)] /= s_piv;
-    __syncthreads();
-    // trailing update: A(j+1+p, j+1+q) -= L(j+1+p, j) * L(j+1+q, j),  q <= p < cnt
-    for (int e = tid; e < cnt * (cnt + 1) / 2; e += blockDim.x) {
-      int p = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-      while ((p + 1) * (p + 2) / 2 <= e) p++;
-      while (p * (p + 1) / 2 > e) p--;
-      int q = e - p * (p + 1) / 2;
-      Bd[(j + 1 + p) * BW + (p - q)] -= Bd[(j + 1 + p) * BW + (p + 1)] * Bd[(j + 1 + q) * BW + (q + 1)];
-    }
-    __syncthreads();
-  }
-  // two right-hand sides (arrow column, gradient): warp 0 -> va, warp 1 -> vg
+  // right-looking banded Cholesky by ONE warp (no block barriers on the 3(T-4)-long dependency chain), in place:
+  // Bd becomes L (L(r, r-k) at Bd[r*BW+k]).  The two right-hand sides (arrow column va, gradient vg) ride along as
+  // extra rows, so the forward substitution L w = b is finished when the factorisation is.
   const int lane = tid & 31, wp = tid >> 5;
-  if (wp < 2) {
-    double* x = wp == 0 ? va : vg;
-    for (int r = 0; r < m; r++) {           // forward  L w = b
-      double s = 0;
-      int k = lane + 1;
-      if (k < BW && r - k >= 0) s = Bd[r * BW + k] * x[r - k];
-      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) x[r] = (x[r] - s) / Bd[r * BW];
+  if (wp == 0) {
+    int fail = 0;
+    // the diagonal stores 1/L(j,j): every division on the 3(T-4)-long dependency chain becomes a multiply
+    double piv = Bd[0];
+    if (!(piv > 0)) { fail = 1; piv = 1; }
+    double rinv = rsqrt(piv);
+    rinv = rinv * (1.5 - 0.5 * piv * rinv * rinv);            // one Newton step: full double accuracy
+    for (int j = 0; j < m; j++) {
+      const int cnt = (m - 1 - j) < 17 ? (m - 1 - j) : 17;   // rows below the pivot inside the band
+      double l = 0;
+      if (lane < cnt) l = Bd[(j + 1 + lane) * BW + lane + 1] * rinv;
+      const double ya = va[j] * rinv, yg = vg[j] * rinv;
+      // look-ahead: the next pivot only needs l of lane 0, start its reciprocal square root before the trailing update
+      const double l0 = __shfl_sync(0xffffffffu, l, 0);
+      double rinv_next = 0;
+      if (j + 1 < m) {
+        double pn = Bd[(j + 1) * BW] - l0 * l0;
+        if (!(pn > 0)) { fail = 1; pn = 1; }
+        rinv_next = rsqrt(pn);
+        rinv_next = rinv_next * (1.5 - 0.5 * pn * rinv_next * rinv_next);
+      }
+      __syncwarp();
+      if (lane < cnt) Bd[(j + 1 + lane) * BW + lane + 1] = l;
+      if (lane == 0) { Bd[j * BW] = rinv; va[j] = ya; vg[j] = yg; }
+      // trailing update A(j+1+p, j+1+q) -= L(j+1+p, j) L(j+1+q, j), q <= p: lane p owns row j+1+p
+      // fully unrolled so the 17 shared-memory read-modify-writes of a lane are independent instructions
+      {
+        double* rowp = Bd + (j + 1 + lane) * BW + lane;
+#pragma unroll
+        for (int q = 0; q < 17; q++) {
+          double lq = __shfl_sync(0xffffffffu, l, q);
+          if (lane < cnt && q <= lane) rowp[-q] -= l * lq;
+        }
+      }
+      if (lane < cnt) { va[j + 1 + lane] -= l * ya; vg[j + 1 + lane] -= l * yg; }
+      rinv = rinv_next;
       __syncwarp();
     }
-    for (int r = m - 1; r >= 0; r--) {      // backward L^T x = w
-      double s = 0;
+    if (lane == 0 && fail) s_fail = 1;
+    // backward substitution L^T x = w for both right-hand sides: lane k-1 holds the k-th sub-diagonal term
+    for (int r = m - 1; r >= 0; r--) {
+      double sa = 0, sg = 0;
       int k = lane + 1;
-      if (k < BW && r + k < m) s = Bd[(r + k) * BW + k] * x[r + k];
-      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) x[r] = (x[r] - s) / Bd[r * BW];
+      if (k < BW && r + k < m) { double lv = Bd[(r + k) * BW + k]; sa = lv * va[r + k]; sg = lv * vg[r + k]; }
+      for (int o = 16; o; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sg += __shfl_xor_sync(0xffffffffu, sg, o); }
+      if (lane == 0) { double dd = Bd[r * BW]; va[r] = (va[r] - sa) * dd; vg[r] = (vg[r] - sg) * dd; }
       __syncwarp();
     }
   }
@@ -211,6 +221,7 @@ int solve_directions(tob_ctx* c, int rb, int re, int dense_shift) {
       attr_set = true;
     }
   }
+  Prof prof(c, K_SOLVE);
   k_solve<<<re - rb, 256, smem, c->stream>>>(a);
   TOB_LAUNCH_CHECK(c);
   return 0;
@@ -377,6 +388,7 @@ int slack_update(tob_ctx* c, int rb, int re) {
   a.pslack = c->s_pslack.p; a.tslack = c->s_tslack.p; a.plambda = c->s_plambda.p; a.tlambda = c->s_tlambda.p;
   a.mu = c->prm.mu; a.ks = c->prm.ks; a.kt = c->prm.kt; a.P = c->prm.piece_num; a.T = c->T; a.robot_begin = rb;
   a.n = (re - rb) * c->prm.piece_num;
+  Prof prof(c, K_SLACK);
   k_slack<<<div_up(a.n, 32), 32, 0, c->stream>>>(a);
   TOB_LAUNCH_CHECK(c);
   return 0;

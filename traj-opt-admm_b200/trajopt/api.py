@@ -301,6 +301,21 @@ class Solver:
     def reset_counters(self):
         self.lib.tob_reset_counters(self.ctx)
 
+    def profile_enable(self, on=True):
+        self._ck(self.lib.tob_profile_enable(self.ctx, C.c_int(int(on))))
+
+    def profile_read(self):
+        """{kernel name: (total ms, launches)} accumulated since profile_enable(True)"""
+        out = {}
+        kid = 0
+        while True:
+            ms = C.c_double(0); n = C.c_uint64(0); name = C.c_char_p()
+            if self.lib.tob_profile_read(self.ctx, C.c_int(kid), C.byref(ms), C.byref(n), C.byref(name)):
+                break
+            out[name.value.decode()] = (ms.value, n.value)
+            kid += 1
+        return out
+
     def stream(self):
         return self.lib.tob_stream(self.ctx)
 
