@@ -1,0 +1,105 @@
+"""GPU parity tests of the multi-robot path (Optimization3D_multi::optimization_decouple) through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from trajopt import api, scenes
+from oracle import oracle_api as oa
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = 8
+
+
+def rows_sorted(off, c, d):
+    out = []
+    for r in range(len(off) - 1):
+        blk = np.column_stack([c[off[r]:off[r + 1]], d[off[r]:off[r + 1]]])
+        if len(blk):
+            blk = blk[np.lexsort(blk.T[::-1])]
+        out.append(blk)
+    return out
+
+
+@pytest.fixture(scope="module")
+def world(oracle_any):
+    sc = scenes.cross(n_pts=20000, seed=3)
+    U = sc["uav_num"]
+    o = oracle_any
+    o.setup(oa.Params(P, uav_num=U, ks=sc["ks"]))
+    o.init_pointcloud(sc["V"])
+    s = api.Solver(P, uav_num=U, ks=sc["ks"])
+    s.init_pointcloud(sc["V"])
+    st0 = scenes.initial_states(sc)
+    st = st0
+    for _ in range(3):
+        st = o.optimization_multi(st, coupled=False)
+    return dict(sc=sc, o=o, s=s, st0=st0, st=st, U=U)
+
+
+def test_hull_primitives_against_golden(world):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "multi.npz"))
+    s = world["s"]
+    ok, c, d = s.plane_hulls_batch(g["hh_P0"], g["hh_P1"], 0.3, refine=False)
+    assert np.array_equal(ok, g["hh_ok"])
+    m = g["hh_ok"]
+    assert np.array_equal(c[m], g["hh_c"][m]) and np.array_equal(d[m], g["hh_d"][m])
+    ok2, c2, d2 = s.plane_hulls_batch(g["hh_P0"], g["hh_P1"], 0.3, refine=True)
+    assert np.max(np.abs(d2[m] - g["hh_dref"][m])) <= 1e-12
+
+
+@pytest.mark.parametrize("which", ["st0", "st"])
+def test_planes_with_inter_robot_terms(world, which):
+    o, s, U = world["o"], world["s"], world["U"]
+    splines = [x["spline"] for x in world[which]]
+    go, gc, gd = s.separate_planes(splines, with_self=True)
+    so, sc_, sd = o.separate_self(splines)
+    n_tr = P * 8
+    n_self = 0
+    got = rows_sorted(go, gc, gd)
+    for u in range(U):
+        ro, rc, rd = o.separate_plane(splines[u])
+        for tr in range(n_tr):
+            r = u * n_tr + tr
+            ob = np.column_stack([rc[ro[tr]:ro[tr + 1]], rd[ro[tr]:ro[tr + 1]]])
+            se = np.column_stack([sc_[so[r]:so[r + 1]], sd[so[r]:so[r + 1]]])
+            n_self += len(se)
+            ref = np.vstack([ob, se])
+            assert len(ref) == len(got[r]), (u, tr)
+            if len(ref):
+                ref = ref[np.lexsort(ref.T[::-1])]
+                # obstacle planes bit-exact; inter-robot d comes out of a Newton loop using log(): 1e-12
+                assert np.max(np.abs(ref - got[r])) <= 1e-12
+    assert n_self > 0
+
+
+def test_self_step(world):
+    o, s, U = world["o"], world["s"], world["U"]
+    splines = [x["spline"] for x in world["st"]]
+    rng = np.random.default_rng(11)
+    seen = set()
+    for trial in range(4):
+        dirs = []
+        for sp in splines:
+            dd = np.zeros_like(sp); dd[2:-2] = rng.normal(size=(sp.shape[0] - 4, 3)) * (0.3 + 0.3 * trial)
+            dirs.append(np.asfortranarray(dd))
+        ref = o.self_step(splines, dirs)
+        got = s.self_step(splines, dirs)
+        assert np.all(got <= ref)
+        assert np.array_equal(got, ref)
+        seen.update(ref.tolist())
+        assert s.self_step(splines, dirs, coupled=True) == o.couple_self_step(splines, dirs)
+    assert len(seen) > 1
+
+
+def test_decoupled_iterations_track_reference(world):
+    o, s, U = world["o"], world["s"], world["U"]
+    a = b = world["st0"]
+    for it in range(8):
+        a = o.optimization_multi(a, coupled=False)
+        b = s.optimization(b)
+        for u in range(U):
+            assert np.max(np.abs(a[u]["spline"] - b[u]["spline"])) < 1e-6, (it, u)
+            assert abs(a[u]["piece_time"] - b[u]["piece_time"]) < 1e-6
+        assert abs(a[0]["gnorm"] - b[0]["gnorm"]) <= 1e-6 * max(1.0, a[0]["gnorm"])
