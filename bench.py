@@ -45,6 +45,10 @@ def workload(name, n_pts=None):
         sc = scenes.forest(n_pts=n_pts or 1_000_000)
     elif name == "bridge":
         sc = scenes.bridge(n_pts=n_pts or 100_000)
+    elif name == "circle64":      # BASELINE.json configs[3]: 64 UAVs, inter-robot planes, robots sharded over the ranks
+        sc = scenes.circle(n_uav=64, n_pts=n_pts or 20_000)
+    elif name == "cross8":        # configs[2]
+        sc = scenes.cross(n_pts=n_pts or 50_000)
     else:
         raise SystemExit("unknown workload " + name)
     return sc
@@ -117,11 +121,16 @@ def run_ours(args):
 
     sc = workload(args.workload, args.points)
     P = len(sc["way_points"][0]) - 1
-    s = api.Solver(P, ks=sc["ks"], device=local)
+    U = sc["uav_num"]
+    sharded = U > 1 and world > 1
+    s = api.Solver(P, uav_num=U, ks=sc["ks"], device=local)
     t0 = time.time()
     s.init_pointcloud(sc["V"])
     build_s = time.time() - t0
-    st0 = scenes.initial_states(sc)[0]
+    st0 = scenes.initial_states(sc)
+    if sharded:
+        from trajopt import dist as tdist
+        tdist.attach(s)
     ext = torch.cuda.ExternalStream(s.stream(), device=torch.device("cuda", local))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -132,7 +141,7 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     # ---- device-resident iterations: `value`
-    s.states_upload([st0])
+    s.states_upload(st0)
     for _ in range(args.warmup):
         s.iterate(1)
     s.reset_counters()
@@ -168,18 +177,21 @@ def run_ours(args):
     fp64_peak = s.fp64_peak_tflops()
 
     # ---- end to end through the host-in/host-out entry point
-    cur = pinned_state(s.states_download([st0])[0])
+    cur = [pinned_state(x) for x in s.states_download(st0)]
     barrier()
-    t0 = time.perf_counter()
+    e2e_s = 0.0
     for _ in range(args.steps):
-        res = s.optimization(cur)
-        for k in ("spline", "p_slack", "t_slack", "p_lambda", "t_lambda"):
-            cur[k][...] = res[k]
-        cur["piece_time"] = res["piece_time"]
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+        flush.fill_(1)                      # same L2 policy as the resident loop; not inside the timed call
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = s.optimization(cur)           # host buffers in -> H2D -> one ADMM iteration -> D2H -> host buffers out
+        e2e_s += time.perf_counter() - t0
+        for c_, r_ in zip(cur, res):
+            for k in ("spline", "p_slack", "t_slack", "p_lambda", "t_lambda"):
+                c_[k][...] = r_[k]
+            c_["piece_time"] = r_["piece_time"]
     T = s.T
-    state_bytes = (3 * T + 1 + 18 * P + P + 18 * P + P) * 8
+    state_bytes = U * (3 * T + 1 + 18 * P + P + 18 * P + P) * 8
 
     # max over ranks
     tt = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
@@ -191,7 +203,8 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    value = world * args.steps / (total_ms * 1e-3)
+    mult = 1 if sharded else world         # sharded: ONE problem over all ranks (strong); else N replicas (weak)
+    value = mult * args.steps / (total_ms * 1e-3)
     pair_evals = ctr["dcd_candidates"] + ctr["ccd_candidates"] + ctr["energy_plane_evals"]
     # dominant kernel by device time
     dom = max(prof.items(), key=lambda kv: kv[1][0])
@@ -225,14 +238,15 @@ def run_ours(args):
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "%s: 1 UAV, %d pts, %d Bezier pieces (%d sub-segments), 3D.json params" % (sc["name"], sc["V"].shape[0], P, P * 8),
+        "config": {"workload": "%s: %d UAV, %d pts, %d Bezier pieces (%d sub-segments each), 3D.json params" % (sc["name"], U, sc["V"].shape[0], P, P * 8),
                    "l2": "flushed between timed iterations (256 MiB rewrite outside the event brackets)",
-                   "multi_gpu": "replicas only" if world > 1 else "single", "lbvh_build_s": build_s, "gnorm_last": gn},
-        "pair_evals_per_s": pair_evals * world / (total_ms * 1e-3),
+                   "multi_gpu": ("robots sharded over ranks, NCCL all-gather of control points/directions" if sharded else
+                                 ("replicas only" if world > 1 else "single")), "lbvh_build_s": build_s, "gnorm_last": gn},
+        "pair_evals_per_s": pair_evals * mult / (total_ms * 1e-3),
         "pairs_per_step": {k: ctr[k] / args.steps for k in ("dcd_candidates", "planes", "ccd_candidates", "energy_plane_evals")},
-        "e2e": {"value": world * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes},
+        "e2e": {"value": mult * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes},
         "gpu_launches": int(ctr["kernel_launches"]),
         "clocks": summarize_clocks(lines),
         "roofline": roof,
@@ -251,18 +265,18 @@ def cpu_baseline(sc, P, budget_s, max_iters, sample_points=None):
     from oracle import oracle_api as oa
     from trajopt import scenes
     o = oa.get()
-    o.setup(oa.Params(P, ks=sc["ks"]))
+    o.setup(oa.Params(P, uav_num=sc["uav_num"], ks=sc["ks"]))
     V = sc["V"]
     # the reference's incremental tree build is O(minutes) for 1 M points in random order; Morton-free trick is not
     # available to it, so the build (one-time, outside the metric) is done on the full cloud and not timed.
     t0 = time.time()
     o.init_pointcloud(V)
     build = time.time() - t0
-    st = scenes.initial_states(sc)[0]
+    sts = scenes.initial_states(sc)
     n, t_used = 0, 0.0
     while n < max_iters and t_used < budget_s:
         t0 = time.perf_counter()
-        st = o.optimization(st)
+        sts = o.optimization_multi(sts, coupled=False) if len(sts) > 1 else [o.optimization(sts[0])]
         t_used += time.perf_counter() - t0
         n += 1
     return {"value": n / t_used, "unit": UNIT, "cores": 1, "kind": o.kind,
@@ -278,21 +292,22 @@ def run_reference(args):
     from oracle import oracle_api as oa
     from trajopt import scenes
     o = oa.get()
-    o.setup(oa.Params(P, ks=sc["ks"]))
+    o.setup(oa.Params(P, uav_num=sc["uav_num"], ks=sc["ks"]))
     t0 = time.time()
     o.init_pointcloud(sc["V"])
     build = time.time() - t0
-    st = scenes.initial_states(sc)[0]
+    sts = scenes.initial_states(sc)
+    step = (lambda x: o.optimization_multi(x, coupled=False)) if len(sts) > 1 else (lambda x: [o.optimization(x[0])])
     budget = 150.0
     t_all = 0.0
     for _ in range(args.warmup):
-        t0 = time.perf_counter(); st = o.optimization(st); t_all += time.perf_counter() - t0
+        t0 = time.perf_counter(); sts = step(sts); t_all += time.perf_counter() - t0
         if t_all > budget / 3:
             break
     n, t_used = 0, 0.0
     while n < args.steps and t_used < budget:
         t0 = time.perf_counter()
-        st = o.optimization(st)
+        sts = step(sts)
         t_used += time.perf_counter() - t0
         n += 1
     value = n / t_used
@@ -300,7 +315,7 @@ def run_reference(args):
     sample = "%d ADMM iterations (time-bounded from --steps %d) on 1 host core, tree build %.1f s excluded" % (n, args.steps, build)
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": n, "warmup": args.warmup,
            "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "%s: 1 UAV, %d pts, %d Bezier pieces (%d sub-segments), 3D.json params" % (sc["name"], sc["V"].shape[0], P, P * 8)},
+           "config": {"workload": "%s: %d UAV, %d pts, %d Bezier pieces (%d sub-segments each), 3D.json params" % (sc["name"], sc["uav_num"], sc["V"].shape[0], P, P * 8)},
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": o.kind, "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))

@@ -103,3 +103,17 @@ def test_decoupled_iterations_track_reference(world):
             assert np.max(np.abs(a[u]["spline"] - b[u]["spline"])) < 1e-6, (it, u)
             assert abs(a[u]["piece_time"] - b[u]["piece_time"]) < 1e-6
         assert abs(a[0]["gnorm"] - b[0]["gnorm"]) <= 1e-6 * max(1.0, a[0]["gnorm"])
+
+
+def test_sharded_two_gpus_equals_single():
+    """needs 2 GPUs: robots sharded over 2 ranks with the NCCL exchange == one context, and tracks the oracle"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(ROOT, "tests", "run_sharded_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "sharded==single:True" in out.stdout

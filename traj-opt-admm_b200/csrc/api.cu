@@ -62,6 +62,8 @@ static int alloc_states(tob_ctx* c) {
   TOB_CUDA(c, c->s_tdir.ensure(U)); TOB_CUDA(c, c->s_wolfe.ensure(U)); TOB_CUDA(c, c->s_gnorm.ensure(U));
   TOB_CUDA(c, c->s_step.ensure(U)); TOB_CUDA(c, c->s_selfstep.ensure(U)); TOB_CUDA(c, c->s_ptrial.ensure(U));
   TOB_CUDA(c, c->s_e0.ensure(U)); TOB_CUDA(c, c->s_e1.ensure(U));
+  TOB_CUDA(c, c->s_tstep.ensure((size_t)U * TOB_LS_TRIALS)); TOB_CUDA(c, c->s_ttime.ensure((size_t)U * TOB_LS_TRIALS));
+  TOB_CUDA(c, c->s_etr.ensure((size_t)U * TOB_LS_TRIALS));
   TOB_CUDA(c, c->s_done.ensure(U + 1)); TOB_CUDA(c, c->solve_status.ensure(U));
   TOB_CUDA(c, c->kmax.ensure(U + 1));
   return 0;
@@ -96,9 +98,10 @@ __global__ void k_fill_int(int* p, int n, int v) {
   if (i < n) p[i] = v;
 }
 
-// step = min(self step, 0.8^kmax); clamp so the piece time stays positive (Optimization3D_admm.h:521-524)
+// step = min(self step, 0.8^kmax); clamp so the piece time stays positive (Optimization3D_admm.h:521-524); then lay
+// out the first batch of trial points: k=0 the current point, k=1.. the ladder step, step*0.8, step*0.8*0.8, ...
 __global__ void k_ls_init(int rb, int re, const int* kmax, const double* steps_tab, const double* selfstep, int use_self,
-                          const double* ptime, const double* tdir, double* step, double* ptrial, int* done) {
+                          const double* ptime, const double* tdir, double* step, double* tstep, double* ttime, int* done) {
   int u = rb + blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= re) return;
   double s = steps_tab[kmax[u]];
@@ -109,25 +112,42 @@ __global__ void k_ls_init(int rb, int re, const int* kmax, const double* steps_t
   }
   if (ptime[u] + s * tdir[u] <= 0) s = -0.95 * ptime[u] / tdir[u];
   step[u] = s;
-  ptrial[u] = ptime[u] + s * tdir[u];
+  tstep[u * TOB_LS_TRIALS] = 0.0;
+  ttime[u * TOB_LS_TRIALS] = ptime[u];
+  for (int k = 1; k < TOB_LS_TRIALS; k++) {
+    tstep[u * TOB_LS_TRIALS + k] = s;
+    ttime[u * TOB_LS_TRIALS + k] = ptime[u] + s * tdir[u];
+    s *= 0.8;
+  }
   done[u] = 0;
 }
 
-// Armijo test of one backtracking round; wolfe_idx < 0: own wolfe, else the reference's "last robot" quirk
-__global__ void k_armijo(int rb, int re, const double* e0, const double* e1, const double* wolfe, int wolfe_idx,
-                         const double* ptime, const double* tdir, double* step, double* ptrial, int* done, int* n_active) {
+// Armijo backtracking over one batch of trial points, in ladder order exactly like the reference's
+// while(e-1e-4*wolfe*step < E(x+step*dir)) step*=0.8 (Optimization3D_admm.h:537-544): the first rung that fails the
+// while-condition is accepted.  wolfe_idx < 0: own wolfe, else the reference's "last robot" quirk.
+__global__ void k_armijo(int rb, int re, const double* etr, const double* wolfe, int wolfe_idx, const double* ptime,
+                         const double* tdir, double* step, double* ptrial, double* tstep, double* ttime, int* done, int* n_active) {
   int u = rb + blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= re) return;
   if (done[u]) return;
-  double w = wolfe[wolfe_idx < 0 ? u : wolfe_idx];
-  if (e0[u] - 1e-4 * w * step[u] < e1[u]) {
-    double s = step[u] * 0.8;
-    step[u] = s;
-    ptrial[u] = ptime[u] + s * tdir[u];
-    atomicAdd(n_active, 1);
-  } else {
-    done[u] = 1;
+  const double w = wolfe[wolfe_idx < 0 ? u : wolfe_idx];
+  const double e0 = etr[u * TOB_LS_TRIALS];
+  for (int k = 1; k < TOB_LS_TRIALS; k++) {
+    const double s = tstep[u * TOB_LS_TRIALS + k];
+    if (!(e0 - 1e-4 * w * s < etr[u * TOB_LS_TRIALS + k])) {
+      step[u] = s;
+      ptrial[u] = ttime[u * TOB_LS_TRIALS + k];
+      done[u] = 1;
+      return;
+    }
   }
+  double s = tstep[u * TOB_LS_TRIALS + TOB_LS_TRIALS - 1] * 0.8;
+  for (int k = 1; k < TOB_LS_TRIALS; k++) {
+    tstep[u * TOB_LS_TRIALS + k] = s;
+    ttime[u * TOB_LS_TRIALS + k] = ptime[u] + s * tdir[u];
+    s *= 0.8;
+  }
+  atomicAdd(n_active, 1);
 }
 
 __global__ void k_apply_step(int rb, int re, int T, const double* step, const double* dir, const double* ptrial, double* spline,
@@ -165,24 +185,22 @@ static int separate_resident(tob_ctx* c, int rb, int re, int with_self) {
   return 0;
 }
 
-// line search of robots [rb,re): s_step/s_ptrial/s_done prepared by k_ls_init
+// line search of robots [rb,re): s_step / trial tables / s_done prepared by k_ls_init
 static int line_search(tob_ctx* c, int rb, int re, int wolfe_idx) {
   const int n = re - rb;
   cudaStream_t st = c->stream;
-  // e0 at the current point (step 0)
-  TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, rb, re, 0));
-  TOB_TRY(energy_rows(c, rb, re, c->s_spline.p, nullptr, nullptr, c->s_ptime.p, c->s_e0.p));
   int* n_active = c->s_done.p + c->n_robots();
-  for (int round = 0; round < 2000; round++) {
-    TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, c->s_step.p, rb, re, 4));
-    TOB_TRY(energy_rows(c, rb, re, c->s_spline.p, c->s_dir.p, c->s_step.p, c->s_ptrial.p, c->s_e1.p));
+  for (int round = 0; round < 400; round++) {
+    // round 0 also evaluates trial 0 = the current point (the "e" of the reference)
+    TOB_TRY(energy_trials(c, rb, re, c->s_dir.p, c->s_tstep.p, c->s_ttime.p, TOB_LS_TRIALS, round == 0 ? 0 : 1, TOB_LS_TRIALS,
+                          c->s_etr.p));
     k_fill_int<<<1, 32, 0, st>>>(n_active, 1, 0);
     TOB_LAUNCH_CHECK(c);
-    k_armijo<<<div_up(n, 64), 64, 0, st>>>(rb, re, c->s_e0.p, c->s_e1.p, c->s_wolfe.p, wolfe_idx, c->s_ptime.p, c->s_tdir.p,
-                                          c->s_step.p, c->s_ptrial.p, c->s_done.p, n_active);
+    k_armijo<<<div_up(n, 64), 64, 0, st>>>(rb, re, c->s_etr.p, c->s_wolfe.p, wolfe_idx, c->s_ptime.p, c->s_tdir.p, c->s_step.p,
+                                          c->s_ptrial.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, n_active);
     TOB_LAUNCH_CHECK(c);
     TOB_TRY(read_back(c, n_active, sizeof(int)));
-    c->ctr.line_search_trials += n;
+    c->ctr.line_search_trials += (uint64_t)n * (TOB_LS_TRIALS - 1);
     if (*((int*)c->h_pinned) == 0) break;
   }
   dim3 grid(div_up(3 * c->T, 128), n);
@@ -224,7 +242,7 @@ static int iterate_once(tob_ctx* c, int mode, double* gnorm_out) {
   TOB_LAUNCH_CHECK(c);
   TOB_TRY(ccd_position_steps(c));
   k_ls_init<<<div_up(re - rb, 64), 64, 0, st>>>(rb, re, c->kmax.p, c->d_steps.p, c->s_selfstep.p, U > 1 ? 1 : 0, c->s_ptime.p,
-                                                c->s_tdir.p, c->s_step.p, c->s_ptrial.p, c->s_done.p);
+                                                c->s_tdir.p, c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p);
   TOB_LAUNCH_CHECK(c);
   // (4) Armijo; multi-robot: every robot uses the LAST robot's wolfe (global overwritten, Optimization3D_multi.h:730,792)
   TOB_TRY(line_search(c, rb, re, U > 1 ? U - 1 : -1));
@@ -579,8 +597,7 @@ int tob_plane_barrier_energy(tob_ctx* c, int robot, const double* spline, double
   // a huge piece time switches the bound terms off without touching the plane sum
   double big = 1e300;
   TOB_TRY(upload(c, c->s_ptrial, &big, 1, robot));
-  TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, robot, robot + 1, 0));
-  TOB_TRY(energy_rows(c, robot, robot + 1, c->s_spline.p, nullptr, nullptr, c->s_ptrial.p, c->s_e1.p));
+  TOB_TRY(energy_trials(c, robot, robot + 1, nullptr, nullptr, c->s_ptrial.p, 1, 0, 1, c->s_e1.p));
   k_plane_energy_only<<<1, 32, 0, c->stream>>>(c->row_e.p, c->row_bad.p, robot * c->n_tr, c->n_tr, c->red.p);
   TOB_LAUNCH_CHECK(c);
   TOB_TRY(read_back(c, c->red.p, 2 * sizeof(double)));
@@ -597,8 +614,7 @@ int tob_bound_energy(tob_ctx* c, const double* spline, double piece_time, double
   }
   TOB_TRY(upload(c, c->s_spline, spline, 3 * c->T, 0));
   TOB_TRY(upload(c, c->s_ptrial, &piece_time, 1, 0));
-  TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, 0, 1, 0));
-  TOB_TRY(energy_rows(c, 0, 1, c->s_spline.p, nullptr, nullptr, c->s_ptrial.p, c->s_e1.p));
+  TOB_TRY(energy_trials(c, 0, 1, nullptr, nullptr, c->s_ptrial.p, 1, 0, 1, c->s_e1.p));
   k_bound_energy_only<<<1, 32, 0, c->stream>>>(c->row_e.p, c->row_bad.p, 0, c->n_tr, c->red.p);
   TOB_LAUNCH_CHECK(c);
   TOB_TRY(read_back(c, c->red.p, 2 * sizeof(double)));
@@ -610,8 +626,7 @@ int tob_spline_energy(tob_ctx* c, int robot, const tob_state* st, double* e) {
   TOB_TRY(need(c, true, false)); TOB_TRY(robot_ok(c, robot));
   cudaSetDevice(c->device);
   TOB_TRY(put_state(c, robot, st));
-  TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, robot, robot + 1, 0));
-  TOB_TRY(energy_rows(c, robot, robot + 1, c->s_spline.p, nullptr, nullptr, c->s_ptime.p, c->s_e1.p));
+  TOB_TRY(energy_trials(c, robot, robot + 1, nullptr, nullptr, c->s_ptime.p, 1, 0, 1, c->s_e1.p));
   TOB_TRY(read_back(c, c->s_e1.p + robot, sizeof(double)));
   *e = c->h_pinned[0];
   return 0;

@@ -30,33 +30,51 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---- energy --------------------------------------------------------------------------------------------------------
+// One launch evaluates a BATCH of line-search trial points: blockIdx.y = trial k, trial spline = spline + tstep[u][k]*dir
+// (element-wise, then P = basis*bz with the reference's unfused left-to-right arithmetic: explicit __dmul_rn/__dadd_rn
+// because this file is compiled with FMA contraction on), trial piece time = ttime[u][k].
 struct EnergyArgs {
-  const double* P;          // rows x 18 (trial point)
-  const double* pl;         // planes x 4
-  const uint32_t* pl_off;   // rows+1
-  const double* weight;     // n_tr
-  const double* ptime;      // per robot trial piece time
+  const double *spline, *dir;   // robots x 3T ; dir may be null (trial == current point)
+  const double *tstep, *ttime;  // robots x KT ; tstep may be null (=0)
+  const double* basis;          // n_tr x 36
+  const double* pl;             // planes x 4
+  const uint32_t* pl_off;       // rows+1
+  const double* weight;         // n_tr
   double margin, vel_limit, acc_limit;
-  int n_tr, row_begin;
-  double* row_e;            // rows x 2 : plane barrier, bound
-  int* row_bad;             // rows
+  int n_tr, res, T, row_begin, rows_all, KT, k0;
+  double* row_e;                // KT x rows_all x 2 : plane barrier, bound
+  int* row_bad;                 // KT x rows_all
 };
 
 __global__ void __launch_bounds__(128) k_row_energy(EnergyArgs a) {
-  const int row = a.row_begin + blockIdx.x;
+  const int row = a.row_begin + blockIdx.x, k = a.k0 + blockIdx.y;
   const int robot = row / a.n_tr, tr = row - robot * a.n_tr;
-  __shared__ double sP[18];
+  __shared__ double sP[18], sBz[18];
   __shared__ double s_part[4];
   __shared__ int s_bad;
-  if (threadIdx.x < 18) sP[threadIdx.x] = a.P[(size_t)18 * row + threadIdx.x];
+  if (threadIdx.x < 18) {
+    const int mm = threadIdx.x % 6, ax = threadIdx.x / 6;
+    const size_t g = (size_t)robot * 3 * a.T + (size_t)ax * a.T + 3 * (tr / a.res) + mm;
+    double v = a.spline[g];
+    if (a.dir && a.tstep) v = __dadd_rn(v, __dmul_rn(a.tstep[robot * a.KT + k], a.dir[g]));
+    sBz[threadIdx.x] = v;
+  }
   if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  if (threadIdx.x < 18) {
+    const int j = threadIdx.x % 6, ax = threadIdx.x / 6;
+    const double* B = a.basis + (size_t)36 * tr;
+    double acc = 0;
+    for (int q = 0; q < 6; q++) acc = __dadd_rn(acc, __dmul_rn(B[j + 6 * q], sBz[q + 6 * ax]));
+    sP[threadIdx.x] = acc;
+  }
   __syncthreads();
   const double w = a.weight[tr], m = a.margin;
   double e = 0;
   int bad = 0;
-  const uint32_t k0 = a.pl_off[row], k1 = a.pl_off[row + 1];
-  for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
-    const double4 pl = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * k);
+  const uint32_t p0 = a.pl_off[row], p1 = a.pl_off[row + 1];
+  for (uint32_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+    const double4 pl = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * p);
 #pragma unroll
     for (int j = 0; j < 6; j++) {
       double d = sP[j] * pl.x + sP[j + 6] * pl.y + sP[j + 12] * pl.z + pl.w;
@@ -67,7 +85,7 @@ __global__ void __launch_bounds__(128) k_row_energy(EnergyArgs a) {
   // bound terms: threads 0..4 velocity, 5..8 acceleration
   double eb = 0;
   if (threadIdx.x < 9) {
-    const double t = a.ptime[robot];
+    const double t = a.ttime[robot * a.KT + k];
     double d;
     if (threadIdx.x < 5) {
       int j = threadIdx.x;
@@ -89,25 +107,25 @@ __global__ void __launch_bounds__(128) k_row_energy(EnergyArgs a) {
   if (lane == 0) s_part[wp] = e;
   __syncthreads();
   if (threadIdx.x == 0) {
-    a.row_e[2 * (size_t)row] = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
-    a.row_e[2 * (size_t)row + 1] = eb;
-    a.row_bad[row] = s_bad;
+    const size_t o = (size_t)k * a.rows_all + row;
+    a.row_e[2 * o] = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
+    a.row_e[2 * o + 1] = eb;
+    a.row_bad[o] = s_bad;
   }
 }
 
 struct RobotEnergyArgs {
-  const double *spline, *dir, *step;            // robots x 3T ; step per robot (may be null => 0)
-  const double *ptime_trial;                    // per robot
+  const double *spline, *dir, *tstep, *ttime;
   const double *pslack, *tslack, *plambda, *tlambda, *convert;
   const double* row_e;
   const int* row_bad;
   double lambda, mu;
-  int n_tr, P, T, robot_begin;
-  double* e_out;                                // per robot
+  int n_tr, P, T, robot_begin, rows_all, KT, k0;
+  double* e_out;                                // robots x KT
 };
 
 __global__ void __launch_bounds__(128) k_robot_energy(RobotEnergyArgs a) {
-  const int robot = a.robot_begin + blockIdx.x;
+  const int robot = a.robot_begin + blockIdx.x, k = a.k0 + blockIdx.y;
   __shared__ double s_part[4];
   __shared__ int s_bad;
   if (threadIdx.x == 0) s_bad = 0;
@@ -115,25 +133,25 @@ __global__ void __launch_bounds__(128) k_robot_energy(RobotEnergyArgs a) {
   double e = 0;
   int bad = 0;
   for (int tr = threadIdx.x; tr < a.n_tr; tr += blockDim.x) {
-    size_t row = (size_t)robot * a.n_tr + tr;
-    e += a.lambda * a.row_e[2 * row] + a.lambda * a.row_e[2 * row + 1];
-    bad |= a.row_bad[row];
+    size_t o = (size_t)k * a.rows_all + (size_t)robot * a.n_tr + tr;
+    e += a.lambda * a.row_e[2 * o] + a.lambda * a.row_e[2 * o + 1];
+    bad |= a.row_bad[o];
   }
   // consensus terms, one thread per piece
-  const double t = a.ptime_trial[robot];
-  const double st = a.step ? a.step[robot] : 0.0;
+  const double t = a.ttime[robot * a.KT + k];
+  const double st = (a.dir && a.tstep) ? a.tstep[robot * a.KT + k] : 0.0;
   for (int sp = threadIdx.x; sp < a.P; sp += blockDim.x) {
     const double* C = a.convert + (size_t)36 * sp;
     double acc = 0;
     for (int ax = 0; ax < 3; ax++) {
       double bz[6];
-      for (int k = 0; k < 6; k++) {
-        size_t g = (size_t)robot * 3 * a.T + (size_t)ax * a.T + 3 * sp + k;
-        bz[k] = a.spline[g] + (a.dir ? st * a.dir[g] : 0.0);
+      for (int q = 0; q < 6; q++) {
+        size_t g = (size_t)robot * 3 * a.T + (size_t)ax * a.T + 3 * sp + q;
+        bz[q] = a.dir ? __dadd_rn(a.spline[g], __dmul_rn(st, a.dir[g])) : a.spline[g];
       }
       for (int r = 0; r < 6; r++) {
         double cx = 0;
-        for (int k = 0; k < 6; k++) cx += C[r + 6 * k] * bz[k];
+        for (int q = 0; q < 6; q++) cx += C[r + 6 * q] * bz[q];
         size_t s = (size_t)robot * 18 * a.P + (size_t)ax * 6 * a.P + 6 * sp + r;
         double pd = cx - a.pslack[s];
         acc += a.mu / 2.0 * pd * pd + a.plambda[s] * pd;
@@ -150,39 +168,41 @@ __global__ void __launch_bounds__(128) k_robot_energy(RobotEnergyArgs a) {
   __syncthreads();
   if (threadIdx.x == 0) {
     double tot = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
-    a.e_out[robot] = s_bad ? INFINITY : tot;
+    a.e_out[robot * a.KT + k] = s_bad ? INFINITY : tot;
   }
 }
 
-// trial point = spline + step*dir, trial piece time = ptime + step*tdir.  geo.P must hold the trial rows
-// (compute_rows mode 4) for robots [rb, re).  e_dev: per robot.
-int energy_rows(tob_ctx* c, int rb, int re, const double* spline, const double* dir, const double* step,
-                const double* ptime_trial, double* e_dev) {
-  int rows_total = c->n_robots() * c->n_tr;
-  TOB_CUDA(c, c->row_e.ensure((size_t)2 * rows_total));
-  TOB_CUDA(c, c->row_bad.ensure(rows_total));
+// Energies of trial points k0..k1-1 of robots [rb,re): trial spline = s_spline + tstep[u*KT+k]*dir, time ttime[u*KT+k].
+// dir/tstep may be null (current point).  e_dev: robots x KT.
+int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* tstep, const double* ttime, int KT, int k0,
+                  int k1, double* e_dev) {
+  const int rows_all = c->rows_all();
+  TOB_CUDA(c, c->row_e.ensure((size_t)2 * rows_all * KT));
+  TOB_CUDA(c, c->row_bad.ensure((size_t)rows_all * KT));
   EnergyArgs a;
-  a.P = c->geo.P.p; a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p; a.ptime = ptime_trial;
+  a.spline = c->s_spline.p; a.dir = dir; a.tstep = tstep; a.ttime = ttime; a.basis = c->d_basis.p;
+  a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p;
   a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
-  a.n_tr = c->n_tr; a.row_begin = rb * c->n_tr; a.row_e = c->row_e.p; a.row_bad = c->row_bad.p;
-  int nrows = (re - rb) * c->n_tr;
+  a.n_tr = c->n_tr; a.res = c->prm.res; a.T = c->T; a.row_begin = rb * c->n_tr; a.rows_all = rows_all; a.KT = KT; a.k0 = k0;
+  a.row_e = c->row_e.p; a.row_bad = c->row_bad.p;
+  const int nrows = (re - rb) * c->n_tr, nk = k1 - k0;
   {
     Prof prof(c, K_ROW_ENERGY);
-    k_row_energy<<<nrows, 128, 0, c->stream>>>(a);
+    k_row_energy<<<dim3(nrows, nk), 128, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
   RobotEnergyArgs b;
-  b.spline = spline; b.dir = dir; b.step = step; b.ptime_trial = ptime_trial;
+  b.spline = c->s_spline.p; b.dir = dir; b.tstep = tstep; b.ttime = ttime;
   b.pslack = c->s_pslack.p; b.tslack = c->s_tslack.p; b.plambda = c->s_plambda.p; b.tlambda = c->s_tlambda.p;
   b.convert = c->d_convert.p; b.row_e = c->row_e.p; b.row_bad = c->row_bad.p;
   b.lambda = c->prm.lambda; b.mu = c->prm.mu; b.n_tr = c->n_tr; b.P = c->prm.piece_num; b.T = c->T; b.robot_begin = rb;
-  b.e_out = e_dev;
+  b.rows_all = rows_all; b.KT = KT; b.k0 = k0; b.e_out = e_dev;
   {
     Prof prof(c, K_ROBOT_ENERGY);
-    k_robot_energy<<<re - rb, 128, 0, c->stream>>>(b);
+    k_robot_energy<<<dim3(re - rb, nk), 128, 0, c->stream>>>(b);
     TOB_LAUNCH_CHECK(c);
   }
-  c->ctr.energy_plane_evals += c->n_planes;
+  c->ctr.energy_plane_evals += c->n_planes * (uint64_t)nk;
   return 0;
 }
 

@@ -9,6 +9,7 @@
 #include "../../include/trajopt_b200.h"
 
 #define TOB_MAX_LEVELS 8
+#define TOB_LS_TRIALS 9      // line-search trial points per launch: index 0 = current point, 1..8 = ladder rungs
 #define TOB_LADDER 400       // longest 0.8^k ladder the CCD kernels will walk
 
 namespace tob {
@@ -80,6 +81,7 @@ struct tob_ctx {
   tob::DBuf<double> s_spline, s_ptime, s_pslack, s_tslack, s_plambda, s_tlambda;
   tob::DBuf<double> s_dir, s_tdir, s_wolfe, s_gnorm;
   tob::DBuf<double> s_step, s_selfstep, s_ptrial, s_e0, s_e1;
+  tob::DBuf<double> s_tstep, s_ttime, s_etr;   // batched line-search trials: robots x TOB_LS_TRIALS
   tob::DBuf<int> s_done, solve_status;
 
   // per-row geometry + broadphase scratch
@@ -100,6 +102,7 @@ struct tob_ctx {
   // inter-robot scratch
   tob::DBuf<double> self_pl;          // n_tr x npairs x 4
   tob::DBuf<uint32_t> self_ok;        // n_tr x npairs
+  tob::DBuf<uint32_t> self_hits;      // inter-robot CCD: appended list of colliding (slot, pair) ids + count + overflow flag
 
   // energy / gradient / solve scratch
   tob::DBuf<double> row_e;
@@ -197,8 +200,8 @@ int ccd_position_steps(tob_ctx* c);
 int self_planes(tob_ctx* c);
 int self_ccd_steps(tob_ctx* c, int coupled, double* steps_dev);
 // barrier.cu
-int energy_rows(tob_ctx* c, int rb, int re, const double* spline, const double* dir, const double* step,
-                const double* ptime_trial, double* e_dev);
+int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* tstep, const double* ttime, int KT, int k0,
+                  int k1, double* e_dev);
 int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd);
 // solve.cu
 int solve_directions(tob_ctx* c, int rb, int re, int dense_shift);

@@ -337,7 +337,8 @@ struct SelfCcdArgs {
   int U, n_tr, npairs, coupled;
   const double *P, *D, *kdop, *steps;
   double offset;
-  uint32_t* hit;      // n_tr x npairs: collides at full steps (1,1)
+  uint32_t* hit;      // list of task ids (slot*npairs + pair) that collide at full steps (1,1); hit[cap] = count
+  uint32_t cap;
   int* kmax;          // [0]: shared exponent (coupled)
 };
 
@@ -392,17 +393,30 @@ __global__ void __launch_bounds__(64) k_self_ccd_filter(SelfCcdArgs a) {
       if (dist2 <= a.offset * a.offset) hit = 1;
     }
   }
-  a.hit[t] = hit;
+  if (hit) {
+    uint32_t k = atomicAdd(a.hit + a.cap, 1u);
+    if (k < a.cap) a.hit[k] = (uint32_t)t;
+  }
 }
 
-// phase 2 (one thread, sequential like the reference): resolve the colliding pairs in slot order
-__global__ void k_self_ccd_resolve(SelfCcdArgs a, double* steps_out) {
+// phase 2 (one thread, sequential like the reference): resolve the colliding pairs in (slot, pair) order.
+// The list is short (pairs that really collide when both robots take their full Newton step); it is sorted first so
+// the result does not depend on the order the filter threads appended it.
+__global__ void k_self_ccd_resolve(SelfCcdArgs a, double* steps_out, int* overflow) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   for (int u = 0; u < a.U; u++) steps_out[u] = 1.0;
   int kshared = 0;
-  for (int tr = 0; tr < a.n_tr; tr++)
-    for (int pi = 0; pi < a.npairs; pi++) {
-      if (!a.hit[(size_t)tr * a.npairs + pi]) continue;
+  uint32_t nh = a.hit[a.cap];
+  if (nh > a.cap) { *overflow = 1; nh = a.cap; }
+  for (uint32_t i = 1; i < nh; i++) {          // insertion sort
+    uint32_t v = a.hit[i];
+    int j = (int)i - 1;
+    while (j >= 0 && a.hit[j] > v) { a.hit[j + 1] = a.hit[j]; j--; }
+    a.hit[j + 1] = v;
+  }
+  for (uint32_t i = 0; i < nh; i++) {
+    {
+      const int tr = a.hit[i] / a.npairs, pi = a.hit[i] - tr * a.npairs;
       int p0, p1;
       pair_from_index(pi, a.U, &p0, &p1);
       size_t r0 = (size_t)p0 * a.n_tr + tr, r1 = (size_t)p1 * a.n_tr + tr;
@@ -427,6 +441,7 @@ __global__ void k_self_ccd_resolve(SelfCcdArgs a, double* steps_out) {
       }
       if (!a.coupled) { steps_out[p0] = s0; steps_out[p1] = s1; }
     }
+  }
   if (a.coupled) steps_out[0] = a.steps[kshared];
 }
 
@@ -435,17 +450,19 @@ int self_ccd_steps(tob_ctx* c, int coupled, double* steps_dev) {
   const int U = c->n_robots();
   int npairs = U * (U - 1) / 2;
   size_t n = (size_t)c->n_tr * npairs;
-  TOB_CUDA(c, c->self_ok.ensure(n + 1));
+  const uint32_t cap = 16384;
+  TOB_CUDA(c, c->self_hits.ensure(cap + 2));
   SelfCcdArgs a;
   a.U = U; a.n_tr = c->n_tr; a.npairs = npairs; a.coupled = coupled;
   a.P = c->geo.P.p; a.D = c->geo.D.p; a.kdop = c->d_kdop.p; a.steps = c->d_steps.p; a.offset = c->prm.offset;
-  a.hit = c->self_ok.p; a.kmax = c->kmax.p;
+  a.hit = c->self_hits.p; a.cap = cap; a.kmax = c->kmax.p;
+  TOB_CUDA(c, cudaMemsetAsync(c->self_hits.p + cap, 0, 2 * sizeof(uint32_t), c->stream));
   if (n) {
     Prof prof(c, K_SELF_CCD);
     k_self_ccd_filter<<<div_up(n, 64), 64, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
-  k_self_ccd_resolve<<<1, 32, 0, c->stream>>>(a, steps_dev);
+  k_self_ccd_resolve<<<1, 32, 0, c->stream>>>(a, steps_dev, (int*)(c->self_hits.p + cap + 1));
   TOB_LAUNCH_CHECK(c);
   c->ctr.self_pairs += n;
   return 0;

@@ -184,9 +184,11 @@ def cross(n_pts=50_000, seed=3, n_pieces=8):
     return dict(name="cross", V=np.asfortranarray(V), way_points=wps, uav_num=8, ks=1e-3)
 
 
-def circle(n_uav=64, n_pts=20_000, seed=4, n_pieces=8, radius=10.0, eps=0.35):
-    """C4: antipodal swap on a circle, goal = start rotated by pi-eps, altitude stagger 0.3*(i mod 4);
-    obstacle ring at radius 12 (heights around the flight band)."""
+def circle(n_uav=64, n_pts=20_000, seed=4, n_pieces=8, radius=10.0, eps=0.35, stagger=0.2):
+    """C4: antipodal swap on a circle, goal = start rotated by pi-eps, altitude stagger `stagger`*(i mod 4) (a pure
+    antipodal straight-line init is infeasible: all hulls meet at the centre).  With eps=0.35 all robots cross a ring
+    of radius R*sin(eps/2)=1.74 at mid-flight, neighbours 0.17 apart in xy and 0.2 apart in z: inside the inter-robot
+    activation distance offset+2*margin=0.3 and outside offset=0.1.  Obstacle ring at radius 12."""
     rng = np.random.Generator(np.random.PCG64(seed))
     ang = rng.uniform(0, 2 * np.pi, n_pts)
     V = np.empty((n_pts, 3))
@@ -195,7 +197,7 @@ def circle(n_uav=64, n_pts=20_000, seed=4, n_pieces=8, radius=10.0, eps=0.35):
     for i in range(n_uav):
         a0 = 2 * np.pi * i / n_uav
         a1 = a0 + np.pi - eps
-        z = 0.3 * (i % 4)
+        z = stagger * (i % 4)
         wps.append(straight_waypoints((radius * np.cos(a0), radius * np.sin(a0), z),
                                       (radius * np.cos(a1), radius * np.sin(a1), z), n_pieces))
     return dict(name="circle", V=np.asfortranarray(V), way_points=wps, uav_num=n_uav, ks=1e-3)
