@@ -760,11 +760,36 @@ int tob_update_slack_lambda(tob_ctx* c, tob_state* st) {
 }
 
 // ---- iteration ---------------------------------------------------------------------------------------------------------------------
+// all robots' states move in 6 transfers (one per array type) through a pinned staging area instead of 6 per robot
+static int stage_ensure(tob_ctx* c, size_t doubles) {
+  if (doubles <= c->h_stage_cap) return 0;
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  c->h_stage = nullptr; c->h_stage_cap = 0;
+  TOB_CUDA(c, cudaMallocHost((void**)&c->h_stage, doubles * sizeof(double)));
+  c->h_stage_cap = doubles;
+  return 0;
+}
+
 int tob_states_upload(tob_ctx* c, const tob_state* states, int n_robots) {
   TOB_TRY(need(c, true, false));
   cudaSetDevice(c->device);
   if (n_robots != c->n_robots()) return fail_msg(c, "tob_states_upload: n_robots must equal uav_num");
-  for (int u = 0; u < n_robots; u++) TOB_TRY(put_state(c, u, &states[u]));
+  const size_t U = n_robots, P = c->prm.piece_num, T = c->T;
+  const size_t n_sp = 3 * T, n_ps = 18 * P, n_ts = P;
+  TOB_TRY(stage_ensure(c, U * (n_sp + 1 + 2 * n_ps + 2 * n_ts)));
+  double* h = c->h_stage;
+  double *h_sp = h, *h_pt = h_sp + U * n_sp, *h_ps = h_pt + U, *h_ts = h_ps + U * n_ps, *h_pl = h_ts + U * n_ts, *h_tl = h_pl + U * n_ps;
+  for (size_t u = 0; u < U; u++) {
+    memcpy(h_sp + u * n_sp, states[u].spline, n_sp * sizeof(double));
+    h_pt[u] = *states[u].piece_time;
+    memcpy(h_ps + u * n_ps, states[u].p_slack, n_ps * sizeof(double));
+    memcpy(h_ts + u * n_ts, states[u].t_slack, n_ts * sizeof(double));
+    memcpy(h_pl + u * n_ps, states[u].p_lambda, n_ps * sizeof(double));
+    memcpy(h_tl + u * n_ts, states[u].t_lambda, n_ts * sizeof(double));
+  }
+  TOB_TRY(upload(c, c->s_spline, h_sp, U * n_sp)); TOB_TRY(upload(c, c->s_ptime, h_pt, U));
+  TOB_TRY(upload(c, c->s_pslack, h_ps, U * n_ps)); TOB_TRY(upload(c, c->s_tslack, h_ts, U * n_ts));
+  TOB_TRY(upload(c, c->s_plambda, h_pl, U * n_ps)); TOB_TRY(upload(c, c->s_tlambda, h_tl, U * n_ts));
   TOB_CUDA(c, cudaStreamSynchronize(c->stream));
   c->states_valid = true;
   return 0;
@@ -774,8 +799,27 @@ int tob_states_download(tob_ctx* c, tob_state* states, int n_robots) {
   TOB_TRY(need(c, true, false));
   cudaSetDevice(c->device);
   if (n_robots != c->n_robots()) return fail_msg(c, "tob_states_download: n_robots must equal uav_num");
-  for (int u = 0; u < n_robots; u++) TOB_TRY(get_state(c, u, &states[u]));
-  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  const size_t U = n_robots, P = c->prm.piece_num, T = c->T;
+  const size_t n_sp = 3 * T, n_ps = 18 * P, n_ts = P;
+  TOB_TRY(stage_ensure(c, U * (n_sp + 1 + 2 * n_ps + 2 * n_ts)));
+  double* h = c->h_stage;
+  double *h_sp = h, *h_pt = h_sp + U * n_sp, *h_ps = h_pt + U, *h_ts = h_ps + U * n_ps, *h_pl = h_ts + U * n_ts, *h_tl = h_pl + U * n_ps;
+  cudaStream_t st = c->stream;
+  TOB_CUDA(c, cudaMemcpyAsync(h_sp, c->s_spline.p, U * n_sp * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TOB_CUDA(c, cudaMemcpyAsync(h_pt, c->s_ptime.p, U * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TOB_CUDA(c, cudaMemcpyAsync(h_ps, c->s_pslack.p, U * n_ps * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TOB_CUDA(c, cudaMemcpyAsync(h_ts, c->s_tslack.p, U * n_ts * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TOB_CUDA(c, cudaMemcpyAsync(h_pl, c->s_plambda.p, U * n_ps * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TOB_CUDA(c, cudaMemcpyAsync(h_tl, c->s_tlambda.p, U * n_ts * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TOB_CUDA(c, cudaStreamSynchronize(st));
+  for (size_t u = 0; u < U; u++) {
+    memcpy(states[u].spline, h_sp + u * n_sp, n_sp * sizeof(double));
+    *states[u].piece_time = h_pt[u];
+    memcpy(states[u].p_slack, h_ps + u * n_ps, n_ps * sizeof(double));
+    memcpy(states[u].t_slack, h_ts + u * n_ts, n_ts * sizeof(double));
+    memcpy(states[u].p_lambda, h_pl + u * n_ps, n_ps * sizeof(double));
+    memcpy(states[u].t_lambda, h_tl + u * n_ts, n_ts * sizeof(double));
+  }
   return 0;
 }
 

@@ -117,6 +117,8 @@ struct tob_ctx {
   tob::DBuf<uint8_t> scratch8;
 
   double* h_pinned = nullptr;         // small pinned read-back area (64 KiB)
+  double* h_stage = nullptr;          // pinned staging for packed state transfers
+  size_t h_stage_cap = 0;
 
   tob_counters ctr{};
 

@@ -196,6 +196,290 @@ __global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
   }
 }
 
+// ---- block cyclic reduction ------------------------------------------------------------------------------------------
+// The banded matrix is block tridiagonal with N = P+1 blocks of 9 unknowns (3 control points): piece sp couples blocks
+// sp and sp+1.  Sequential Cholesky has a dependency chain of 3(T-4) pivots (~1 M cycles on one warp at P=64); cyclic
+// reduction eliminates every other block per level, all blocks of a level in parallel (one warp per block):
+//   eliminated block i (neighbours i-s, i+s):  D_i = L L^T,  U = L^-1 A(i,i-s),  V = L^-1 A(i,i+s),  c = L^-1 r_i
+//   surviving block j:  D_j -= V^T V (from j-s) + U^T U (from j+s),  r_j -= V^T c + U^T c,
+//                       A(j,j-2s) = -V^T U (from j-s),  A(j,j+2s) = -U^T V (from j+s)
+// log2(N) levels, then x_i = L^-T (c - U x_{i-s} - V x_{i+s}) in reverse.  SPD Schur complements stay SPD.
+// The 4 fixed end control points are kept as identity rows (x = 0) so every block has size 9.
+#define BS 9
+#define BLK (3 * 81 + 18 + 9)     // El, D, Eu (81 each), R (9x2), 1/diag(L) (9)
+
+__device__ __forceinline__ double rsqrt_full(double x) {
+  double r = rsqrt(x);
+  return r * (1.5 - 0.5 * x * r * r);
+}
+
+// in-place lower Cholesky of the 9x9 col-major matrix D by one warp; dinv receives 1/L(k,k).  Returns false on a
+// non-positive pivot (same value on every lane).
+__device__ inline bool warp_chol9(double* D, double* dinv) {
+  const int lane = threadIdx.x & 31;
+  bool ok = true;
+  for (int k = 0; k < BS; k++) {
+    double p = D[k + BS * k];
+    if (!(p > 0)) { ok = false; p = 1; }
+    const double ri = rsqrt_full(p);
+    double l = 0;
+    if (lane > k && lane < BS) l = D[lane + BS * k] * ri;
+    __syncwarp();
+    if (lane > k && lane < BS) D[lane + BS * k] = l;
+    if (lane == k) { D[k + BS * k] = p * ri; dinv[k] = ri; }
+    __syncwarp();
+    // trailing update of the lower triangle: entries (i,j), k < j <= i < 9
+    for (int e = lane; e < 36; e += 32) {
+      int i = 1, rem = e;                       // row-wise enumeration of the strict+diag lower triangle of an 8x8
+      while (rem >= i) { rem -= i; i++; }
+      int ii = i, jj = rem + 1;                 // 1 <= jj <= ii <= 8
+      if (jj > k && ii > k) D[ii + BS * jj] -= D[ii + BS * k] * D[jj + BS * k];
+    }
+    __syncwarp();
+  }
+  return ok;
+}
+
+struct BcrArgs {
+  const double *pc_g, *pc_h;
+  int P, T, robot_begin;
+  double *dir, *tdir, *wolfe, *gnorm;
+  int* status;
+};
+
+__global__ void __launch_bounds__(1024) k_solve_bcr(BcrArgs a) {
+  extern __shared__ double sm[];
+  const int robot = a.robot_begin + blockIdx.x;
+  const int N = a.P + 1, tid = threadIdx.x, lane = tid & 31, wp = tid >> 5, nw = blockDim.x >> 5;
+  double* blk = sm;                               // N x BLK
+  double* rhs0 = blk + (size_t)N * BLK;           // N x 18 : original [g | arrow] per block (for the Schur step)
+  __shared__ double s_h, s_gt, s_t;
+  __shared__ int s_fail;
+  __shared__ double s_red[32][4];
+  if (tid == 0) s_fail = 0;
+  const double* G = a.pc_g + (size_t)19 * robot * a.P;
+  const double* H = a.pc_h + (size_t)361 * robot * a.P;
+  // ---- assembly
+  for (int e = tid; e < N * 81; e += blockDim.x) {
+    const int b = e / 81, rc = e - 81 * b, r = rc % BS, cc = rc / BS;
+    double d = 0, el = 0, eu = 0;
+    if (b >= 1) { const double* h = H + (size_t)361 * (b - 1); d += h[(9 + r) + 19 * (9 + cc)]; el = h[(9 + r) + 19 * cc]; }
+    if (b < a.P) { const double* h = H + (size_t)361 * b; d += h[r + 19 * cc]; eu = h[r + 19 * (9 + cc)]; }
+    // fixed end control points: block 0 local 0..5, block N-1 local 3..8
+    const bool fr = (b == 0 && r < 6) || (b == N - 1 && r >= 3);
+    const bool fc = (b == 0 && cc < 6) || (b == N - 1 && cc >= 3);
+    if (fr || fc) d = (r == cc) ? 1.0 : 0.0;
+    if (fr || (b == 1 && cc < 6)) el = 0.0;            // A(1,0) columns of fixed unknowns
+    if (fr || (b == N - 2 && cc >= 3)) eu = 0.0;       // A(N-2,N-1) columns of fixed unknowns
+    double* o = blk + (size_t)b * BLK;
+    o[rc] = el; o[81 + rc] = d; o[162 + rc] = eu;
+  }
+  for (int e = tid; e < N * 18; e += blockDim.x) {
+    const int b = e / 18, q = e - 18 * b, r = q % BS, col = q / BS;
+    double v = 0;
+    if (b >= 1) v += col == 0 ? G[(size_t)19 * (b - 1) + 9 + r] : H[(size_t)361 * (b - 1) + (9 + r) + 19 * 18];
+    if (b < a.P) v += col == 0 ? G[(size_t)19 * b + r] : H[(size_t)361 * b + r + 19 * 18];
+    if ((b == 0 && r < 6) || (b == N - 1 && r >= 3)) v = 0.0;
+    blk[(size_t)b * BLK + 243 + q] = v;
+    rhs0[e] = v;
+  }
+  if (tid == 0) {
+    double h = 0, gt = 0;
+    for (int sp = 0; sp < a.P; sp++) { h += H[(size_t)361 * sp + 18 + 19 * 18]; gt += G[(size_t)19 * sp + 18]; }
+    s_h = h; s_gt = gt;
+  }
+  __syncthreads();
+  // ---- reduction
+  int s = 1;
+  for (; s < N; s <<= 1) {
+    // eliminate blocks i = s, 3s, 5s, ...
+    const int n_el = (N - 1 - s) / (2 * s) + 1;
+    for (int q = wp; q < n_el; q += nw) {
+      const int i = s + 2 * s * q;
+      double* B = blk + (size_t)i * BLK;
+      double *El = B, *D = B + 81, *Eu = B + 162, *R = B + 243, *dinv = B + 261;
+      const bool has_up = i + s < N;
+      if (!warp_chol9(D, dinv)) { if (lane == 0) s_fail = 1; }
+      // forward substitution L y = b for the 20 columns [El | Eu | R]
+      if (lane < 20) {
+        double* col = lane < 9 ? El + BS * lane : (lane < 18 ? Eu + BS * (lane - 9) : R + BS * (lane - 18));
+        double y[BS];
+        if (lane >= 9 && lane < 18 && !has_up) {
+#pragma unroll
+          for (int k = 0; k < BS; k++) col[k] = 0.0;
+        } else {
+#pragma unroll
+          for (int k = 0; k < BS; k++) {
+            double v = col[k];
+#pragma unroll
+            for (int j = 0; j < k; j++) v -= D[k + BS * j] * y[j];
+            y[k] = v * dinv[k];
+          }
+#pragma unroll
+          for (int k = 0; k < BS; k++) col[k] = y[k];
+        }
+      }
+    }
+    __syncthreads();
+    // update survivors j = 0, 2s, 4s, ...
+    const int n_sv = (N - 1) / (2 * s) + 1;
+    for (int q = wp; q < n_sv; q += nw) {
+      const int j = 2 * s * q;
+      double* B = blk + (size_t)j * BLK;
+      const double* lo = (j - s >= 0) ? blk + (size_t)(j - s) * BLK : nullptr;        // eliminated lower neighbour: uses its V, U, c
+      const double* up = (j + s < N) ? blk + (size_t)(j + s) * BLK : nullptr;         // eliminated upper neighbour: uses its U, V, c
+      for (int e = lane; e < 81; e += 32) {
+        const int r = e % BS, cc = e / BS;
+        double d = 0, nel = 0, neu = 0;
+        if (lo) {
+          const double *U = lo, *V = lo + 162;
+#pragma unroll
+          for (int k = 0; k < BS; k++) { d += V[k + BS * r] * V[k + BS * cc]; nel -= V[k + BS * r] * U[k + BS * cc]; }
+        }
+        if (up) {
+          const double *U = up, *V = up + 162;
+#pragma unroll
+          for (int k = 0; k < BS; k++) { d += U[k + BS * r] * U[k + BS * cc]; neu -= U[k + BS * r] * V[k + BS * cc]; }
+        }
+        B[81 + e] -= d;
+        B[e] = nel;          // A(j, j-2s)
+        B[162 + e] = neu;    // A(j, j+2s)
+      }
+      if (lane < 18) {
+        const int r = lane % BS, col = lane / BS;
+        double d = 0;
+        if (lo) {
+          const double *V = lo + 162, *cv = lo + 243 + BS * col;
+#pragma unroll
+          for (int k = 0; k < BS; k++) d += V[k + BS * r] * cv[k];
+        }
+        if (up) {
+          const double *U = up, *cv = up + 243 + BS * col;
+#pragma unroll
+          for (int k = 0; k < BS; k++) d += U[k + BS * r] * cv[k];
+        }
+        B[243 + lane] -= d;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- root block 0
+  if (wp == 0) {
+    double* B = blk;
+    double *D = B + 81, *R = B + 243, *dinv = B + 261;
+    if (!warp_chol9(D, dinv)) { if (lane == 0) s_fail = 1; }
+    if (lane < 2) {
+      double* col = R + BS * lane;
+      double y[BS];
+#pragma unroll
+      for (int k = 0; k < BS; k++) {
+        double v = col[k];
+#pragma unroll
+        for (int j = 0; j < k; j++) v -= D[k + BS * j] * y[j];
+        y[k] = v * dinv[k];
+      }
+#pragma unroll
+      for (int k = BS - 1; k >= 0; k--) {
+        double v = y[k];
+#pragma unroll
+        for (int j = k + 1; j < BS; j++) v -= D[j + BS * k] * y[j];
+        y[k] = v * dinv[k];
+      }
+#pragma unroll
+      for (int k = 0; k < BS; k++) col[k] = y[k];
+    }
+  }
+  __syncthreads();
+  // ---- back substitution, levels in reverse
+  for (s >>= 1; s >= 1; s >>= 1) {
+    const int n_el = (N - 1 - s) / (2 * s) + 1;
+    for (int q = wp; q < n_el; q += nw) {
+      const int i = s + 2 * s * q;
+      double* B = blk + (size_t)i * BLK;
+      const double *U = B, *D = B + 81, *V = B + 162, *dinv = B + 261;
+      double* R = B + 243;
+      const double* xl = blk + (size_t)(i - s) * BLK + 243;
+      const double* xu = (i + s < N) ? blk + (size_t)(i + s) * BLK + 243 : nullptr;
+      double t = 0;
+      if (lane < 18) {
+        const int r = lane % BS, col = lane / BS;
+        t = R[lane];
+#pragma unroll
+        for (int k = 0; k < BS; k++) t -= U[r + BS * k] * xl[k + BS * col];
+        if (xu) {
+#pragma unroll
+          for (int k = 0; k < BS; k++) t -= V[r + BS * k] * xu[k + BS * col];
+        }
+      }
+      __syncwarp();
+      if (lane < 18) R[lane] = t;
+      __syncwarp();
+      if (lane < 2) {
+        double* col = R + BS * lane;
+        double y[BS];
+#pragma unroll
+        for (int k = 0; k < BS; k++) y[k] = col[k];
+#pragma unroll
+        for (int k = BS - 1; k >= 0; k--) {
+          double v = y[k];
+#pragma unroll
+          for (int j = k + 1; j < BS; j++) v -= D[j + BS * k] * y[j];
+          y[k] = v * dinv[k];
+        }
+#pragma unroll
+        for (int k = 0; k < BS; k++) col[k] = y[k];
+      }
+    }
+    __syncthreads();
+  }
+  // ---- Schur complement for the arrow (shared piece time), direction, wolfe, gnorm.  z = B^-1 g (col 0), y = B^-1 a (col 1)
+  double ay = 0, az = 0, gg = 0;
+  for (int e = tid; e < N * BS; e += blockDim.x) {
+    const int b = e / BS, r = e - BS * b;
+    const double g0 = rhs0[b * 18 + r], a0 = rhs0[b * 18 + BS + r];
+    const double z = blk[(size_t)b * BLK + 243 + r], y = blk[(size_t)b * BLK + 243 + BS + r];
+    ay += a0 * y; az += a0 * z; gg += g0 * g0;
+  }
+  for (int o = 16; o; o >>= 1) {
+    ay += __shfl_xor_sync(0xffffffffu, ay, o);
+    az += __shfl_xor_sync(0xffffffffu, az, o);
+    gg += __shfl_xor_sync(0xffffffffu, gg, o);
+  }
+  if (lane == 0) { s_red[wp][0] = ay; s_red[wp][1] = az; s_red[wp][2] = gg; }
+  __syncthreads();
+  if (tid == 0) {
+    double AY = 0, AZ = 0, GG = 0;
+    for (int i = 0; i < nw; i++) { AY += s_red[i][0]; AZ += s_red[i][1]; GG += s_red[i][2]; }
+    const double schur = s_h - AY;
+    if (!(schur > 0)) s_fail = 1;
+    s_t = (AZ - s_gt) / schur;
+    a.tdir[robot] = s_t;
+    a.gnorm[robot] = sqrt(GG + s_gt * s_gt);
+  }
+  __syncthreads();
+  const double t = s_t;
+  double wl = 0;
+  double* dir = a.dir + (size_t)robot * 3 * a.T;
+  for (int e = tid; e < N * BS; e += blockDim.x) {       // full coordinate f = e: control point f/3, axis f%3
+    const int b = e / BS, r = e - BS * b;
+    const double z = blk[(size_t)b * BLK + 243 + r], y = blk[(size_t)b * BLK + 243 + BS + r];
+    const bool fixed = (b == 0 && r < 6) || (b == N - 1 && r >= 3);
+    const double x = fixed ? 0.0 : (-z - y * t);
+    wl += x * rhs0[b * 18 + r];
+    dir[(size_t)(e % 3) * a.T + e / 3] = x;
+  }
+  for (int o = 16; o; o >>= 1) wl += __shfl_xor_sync(0xffffffffu, wl, o);
+  if (lane == 0) s_red[wp][3] = wl;
+  __syncthreads();
+  if (tid == 0) {
+    double W = 0;
+    for (int i = 0; i < nw; i++) W += s_red[i][3];
+    W += t * s_gt;
+    a.wolfe[robot] = -W;
+    a.status[robot] = s_fail;
+  }
+}
+
 int solve_directions(tob_ctx* c, int rb, int re, int dense_shift) {
   int nr = c->n_robots();
   TOB_CUDA(c, c->s_dir.ensure((size_t)3 * c->T * nr));
@@ -203,26 +487,35 @@ int solve_directions(tob_ctx* c, int rb, int re, int dense_shift) {
   TOB_CUDA(c, c->s_wolfe.ensure(nr));
   TOB_CUDA(c, c->s_gnorm.ensure(nr));
   TOB_CUDA(c, c->solve_status.ensure(nr));
+  const int N = c->prm.piece_num + 1;
+  const size_t smem_bcr = ((size_t)N * BLK + (size_t)N * 18) * sizeof(double);
+  if (smem_bcr <= 220 * 1024) {
+    BcrArgs a;
+    a.pc_g = c->pc_g.p; a.pc_h = c->pc_h.p; a.P = c->prm.piece_num; a.T = c->T; a.robot_begin = rb;
+    a.dir = c->s_dir.p; a.tdir = c->s_tdir.p; a.wolfe = c->s_wolfe.p; a.gnorm = c->s_gnorm.p; a.status = c->solve_status.p;
+    static bool attr_set = false;
+    if (!attr_set) {
+      TOB_CUDA(c, cudaFuncSetAttribute(k_solve_bcr, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      attr_set = true;
+    }
+    int warps = (N + 1) / 2;
+    if (warps < 4) warps = 4;
+    if (warps > 32) warps = 32;
+    Prof prof(c, K_SOLVE);
+    k_solve_bcr<<<re - rb, warps * 32, smem_bcr, c->stream>>>(a);
+    TOB_LAUNCH_CHECK(c);
+    return 0;
+  }
+  // very long trajectories (P > ~100): sequential banded factorisation with a global-memory band
   SolveArgs a;
   a.pc_g = c->pc_g.p; a.pc_h = c->pc_h.p; a.P = c->prm.piece_num; a.T = c->T; a.robot_begin = rb; a.dense_shift = dense_shift;
   a.dir = c->s_dir.p; a.tdir = c->s_tdir.p; a.wolfe = c->s_wolfe.p; a.gnorm = c->s_gnorm.p; a.status = c->solve_status.p;
   int m = 3 * (c->T - 4);
-  size_t smem = (size_t)m * 22 * sizeof(double);
-  a.use_global = smem > 200 * 1024;
-  a.gband = nullptr;
-  if (a.use_global) {
-    TOB_CUDA(c, c->band.ensure((size_t)(re - rb) * m * 22));
-    a.gband = c->band.p;
-    smem = 0;
-  } else if (smem > 48 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      TOB_CUDA(c, cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
-    }
-  }
+  TOB_CUDA(c, c->band.ensure((size_t)(re - rb) * m * 22));
+  a.gband = c->band.p;
+  a.use_global = 1;
   Prof prof(c, K_SOLVE);
-  k_solve<<<re - rb, 256, smem, c->stream>>>(a);
+  k_solve<<<re - rb, 256, 0, c->stream>>>(a);
   TOB_LAUNCH_CHECK(c);
   return 0;
 }
