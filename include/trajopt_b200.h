@@ -80,9 +80,18 @@ int tob_broadphase_ccd(tob_ctx* ctx, const double* splines, const double* direct
 int tob_self_broadphase(tob_ctx* ctx, const double* P, const double* D /* NULL = DCD */, int u, double d,
                         uint32_t* pairs, uint64_t cap, uint64_t* total);
 
+/* replaces BVH::EdgeCollision (BVH/BVH.cpp:95-133, front-end path validation): all points within d of the box
+ * [lo,hi] (leaf predicate of AABB.cc:131-161); ids = original point ids, ascending. */
+int tob_box_query(tob_ctx* ctx, const double* lo, const double* hi, double d, uint32_t* ids, uint64_t cap,
+                  uint64_t* total);
+
 /* ---- per-pair primitives (function-level parity entry points) ----------------------------------------------- */
-/* batch of n independent evaluations; A: n blocks of na x 3 col-major, B likewise (na,nb in {1,6,12}). */
+/* batch of n independent evaluations of gjk() (lib/opengjk/src/openGJK.c:754-852) as marshalled by CCD::GJKDCD /
+ * GJKCCD / SelfGJKCCD (CCD/CCD.h:17-352); A: n blocks of na x 3 col-major, B likewise (1 <= na,nb <= 16). */
 int tob_gjk_batch(tob_ctx* ctx, const double* A, int na, const double* B, int nb, int n, double* v /* n x 3 */);
+/* 49-DOP separation test of two vertex sets with gap d: CCD::KDOPDCD :354-413 (6,1), SelfKDOPDCD :535-587 (6,6),
+ * KDOPCCD :416-473 (12,1), SelfKDOPCCD :475-533 (12,12); the swept sets [P+tMin*D; P+tMax*D] are formed by the caller */
+int tob_kdop_batch(tob_ctx* ctx, const double* A, int na, const double* B, int nb, int n, double d, uint8_t* flags);
 /* CCD::KDOPDCD (CCD/CCD.h:354-413): P n x (6x3), q n x 3 -> flags */
 int tob_kdop_dcd_batch(tob_ctx* ctx, const double* P, const double* q, int n, double d, uint8_t* flags);
 /* Separate::opengjk (Separate.h:18-163): -> ok flag, c (n x 3), d (n) */
@@ -92,6 +101,9 @@ int tob_plane_point_batch(tob_ctx* ctx, const double* P, const double* q, int n,
 int tob_plane_hulls_batch(tob_ctx* ctx, const double* P0, const double* P1, int n, double distance, int refine,
                           uint8_t* ok, double* c, double* d);
 
+/* Optimal_plane::optimal_d (Optimal_plane.h:13-71): 1-D Newton on d for n (P0, P1, c) triples; d_io in/out */
+int tob_refine_d_batch(tob_ctx* ctx, const double* P0, const double* P1, const double* c, int n, double* d_io);
+
 /* ---- separating planes (replaces Optimization3D_admm::separate_plane, Optimization3D_admm.h:69-197, and
  *      Optimization3D_multi::separate_plane :176-235 / ::separate_self :237-342) ------------------------------ */
 /* Runs broadphase -> 49-DOP -> GJK -> plane for every robot and, when with_self != 0 and n_robots > 1, the
@@ -100,6 +112,11 @@ int tob_plane_hulls_batch(tob_ctx* ctx, const double* P0, const double* P1, int 
  * host when c/dd are non-NULL.  c: total x 3 (row-major xyz per plane), dd: total. */
 int tob_separate_planes(tob_ctx* ctx, const double* splines, int n_robots, int with_self, uint32_t* offsets,
                         double* c, double* dd, uint64_t cap, uint64_t* total);
+/* Optimization3D_multi::separate_self (:237-342) alone: the inter-robot planes of every (robot, time slot) as a CSR over
+ * n_robots*n_tr rows, (c, d-offset/2) for the lower robot id of a pair and (-c, -d-offset/2) for the higher one.  They
+ * also become the resident plane set. */
+int tob_separate_self(tob_ctx* ctx, const double* splines, int n_robots, uint32_t* offsets, double* c, double* dd,
+                      uint64_t cap, uint64_t* total);
 /* Upload a caller-provided plane set (the reference's c_lists/d_lists) as the resident set. */
 int tob_set_planes(tob_ctx* ctx, int n_robots, const uint32_t* offsets, const double* c, const double* dd);
 
@@ -131,6 +148,21 @@ int tob_global_gradient(tob_ctx* ctx, int robot, const tob_state* st, double* gr
 int tob_descent_direction(tob_ctx* ctx, int robot, const tob_state* st, int dense_shift, double* direction,
                           double* t_direction, double* wolfe, double* gnorm);
 
+/* One sub-segment (row tr_id of robot 0) against the resident planes, in the 18 piece coordinates (control point m, axis k
+ * at index 3m+k), without the lambda factor: which = 0 -> Gradient_admm::local_plane_barrier_gradient (Gradient_admm.h:331-407);
+ * which = 1 -> local_bound_gradient (:409-572) incl. g_t, h_t and the mixed column partgrad.  hess324: 18x18 col-major. */
+int tob_row_blocks(tob_ctx* ctx, const double* spline, double piece_time, int tr_id, int which, double* grad18,
+                   double* hess324, double* g_t, double* h_t, double* partgrad18);
+
+/* ---- line search (replaces Optimization3D_admm::spline_line_search, Optimization3D_admm.h:505-557, when *step_io < 0:
+ *      the bound is Step::position_step; and Optimization3D_multi::spline_line_search :754-811 when 0 <= *step_io <= 1:
+ *      the caller's bound).  Armijo backtracking with factor 0.8 against the resident planes; st->spline and
+ *      st->piece_time are updated in place, *step_io receives the accepted step. */
+int tob_line_search(tob_ctx* ctx, int robot, tob_state* st, const double* direction, double t_direction, double wolfe,
+                    double* step_io);
+/* the reference's global `wolfe` as left by the direction solve of the last iteration (Optimization3D_admm.h:477) */
+int tob_last_wolfe(tob_ctx* ctx, double* wolfe);
+
 /* ---- CCD step bound (replaces Step::position_step Step.h:21-110, ::self_step :184-256,
  *      ::couple_self_step :112-182) ---------------------------------------------------------------------------- */
 int tob_position_step(tob_ctx* ctx, const double* spline, const double* direction, double* step);
@@ -140,12 +172,22 @@ int tob_self_step(tob_ctx* ctx, const double* splines, const double* directions,
 /* ---- slack / dual update (replaces Optimization3D_admm::update_slack_lambda :231-398) ------------------------ */
 int tob_update_slack_lambda(tob_ctx* ctx, tob_state* st);
 
+/* One piece of the slack problem.  consensus != 0: Energy_admm::slack_energy (Energy_admm.h:172-190) and
+ * Gradient_admm::slack_gradient (Gradient_admm.h:574-622).  consensus == 0: Energy_admm::dynamic_energy (:199-215) and
+ * Gradient_admm::dynamic_gradient (:633-671); then c_spline / p_lambda may be NULL, grad19[18] = g_t,
+ * hess361(18,18) = h_t and hess361(0..17,18) = partgrad.  c_spline, p_part, p_lambda: 6x3 column-major.
+ * energy / grad19 / hess361 (19x19 column-major) may each be NULL. */
+int tob_slack_terms(tob_ctx* ctx, const double* c_spline, double piece_time, const double* p_part, double t_part,
+                    const double* p_lambda, double t_lambda, int consensus, double* energy, double* grad19,
+                    double* hess361);
+
 /* ---- whole ADMM iteration, device resident --------------------------------------------------------------------
  * tob_states_upload / download move the n_robots states between host and the context;
  * tob_admm_iterate runs `iters` iterations of Optimization3D_admm::optimization (:29-67) when n_robots == 1, of
  * Optimization3D_multi::optimization_decouple (Optimization3D_multi.h:29-118) when n_robots > 1 (mode 0) or of
  * ::optimization (coupled, :120-174) (mode 1).  gnorm receives the reference's global `gnorm` after the last
- * iteration.  Robot ownership for multi-GPU: see tob_set_shard(). */
+ * iteration.  Mode 1 shares ONE piece time: states[u].piece_time may all point to the same double.  Robot ownership for
+ * multi-GPU: see tob_set_shard() (mode 0 only). */
 int tob_states_upload(tob_ctx* ctx, const tob_state* states, int n_robots);
 int tob_states_download(tob_ctx* ctx, tob_state* states, int n_robots);
 int tob_admm_iterate(tob_ctx* ctx, int iters, int mode, double* gnorm);

@@ -150,6 +150,56 @@ __global__ void k_armijo(int rb, int re, const double* etr, const double* wolfe,
   atomicAdd(n_active, 1);
 }
 
+// coupled mode (Optimization3D_multi::update_spline :585-636): ONE step and ONE piece time for all robots.
+// step = min(couple_self_step, min_u position_step_u), clamped so that the shared piece time stays positive.
+__global__ void k_ls_init_coupled(int U, const int* kmax, const double* steps_tab, const double* selfstep, const double* ptime,
+                                  const double* tdir, double* step, double* tstep, double* ttime, int* done) {
+  if (threadIdx.x || blockIdx.x) return;
+  int km = 0;
+  for (int u = 0; u < U; u++) if (kmax[u] > km) km = kmax[u];
+  double s = selfstep[0];
+  const double sp = steps_tab[km];
+  if (sp < s) s = sp;
+  if (ptime[0] + s * tdir[0] <= 0) s = -0.95 * ptime[0] / tdir[0];
+  for (int u = 0; u < U; u++) {
+    double sk = s;
+    step[u] = s;
+    tstep[u * TOB_LS_TRIALS] = 0.0;
+    ttime[u * TOB_LS_TRIALS] = ptime[0];
+    for (int k = 1; k < TOB_LS_TRIALS; k++) {
+      tstep[u * TOB_LS_TRIALS + k] = sk;
+      ttime[u * TOB_LS_TRIALS + k] = ptime[0] + sk * tdir[0];
+      sk *= 0.8;
+    }
+    done[u] = 0;
+  }
+}
+
+// joint Armijo test on the summed energy (robots in index order like the reference's loop, Optimization3D_multi.h:641-657)
+__global__ void k_armijo_coupled(int U, const double* etr, const double* wolfe, const double* ptime, const double* tdir, double* step,
+                                 double* ptrial, double* tstep, double* ttime, int* done, int* n_active) {
+  if (threadIdx.x || blockIdx.x) return;
+  if (done[0]) return;
+  double e0 = 0;
+  for (int u = 0; u < U; u++) e0 += etr[u * TOB_LS_TRIALS];
+  const double w = wolfe[0];
+  for (int k = 1; k < TOB_LS_TRIALS; k++) {
+    const double s = tstep[k];
+    double e1 = 0;
+    for (int u = 0; u < U; u++) e1 += etr[u * TOB_LS_TRIALS + k];
+    if (!(e0 - 1e-4 * w * s < e1)) {
+      for (int u = 0; u < U; u++) { step[u] = s; ptrial[u] = ttime[k]; done[u] = 1; }
+      return;
+    }
+  }
+  double s = tstep[TOB_LS_TRIALS - 1] * 0.8;
+  for (int k = 1; k < TOB_LS_TRIALS; k++) {
+    for (int u = 0; u < U; u++) { tstep[u * TOB_LS_TRIALS + k] = s; ttime[u * TOB_LS_TRIALS + k] = ptime[0] + s * tdir[0]; }
+    s *= 0.8;
+  }
+  atomicAdd(n_active, 1);
+}
+
 __global__ void k_apply_step(int rb, int re, int T, const double* step, const double* dir, const double* ptrial, double* spline,
                              double* ptime) {
   int u = rb + blockIdx.y;
@@ -186,7 +236,7 @@ static int separate_resident(tob_ctx* c, int rb, int re, int with_self) {
 }
 
 // line search of robots [rb,re): s_step / trial tables / s_done prepared by k_ls_init
-static int line_search(tob_ctx* c, int rb, int re, int wolfe_idx) {
+static int line_search(tob_ctx* c, int rb, int re, int wolfe_idx, bool coupled = false) {
   const int n = re - rb;
   cudaStream_t st = c->stream;
   int* n_active = c->s_done.p + c->n_robots();
@@ -196,8 +246,12 @@ static int line_search(tob_ctx* c, int rb, int re, int wolfe_idx) {
                           c->s_etr.p));
     k_fill_int<<<1, 32, 0, st>>>(n_active, 1, 0);
     TOB_LAUNCH_CHECK(c);
-    k_armijo<<<div_up(n, 64), 64, 0, st>>>(rb, re, c->s_etr.p, c->s_wolfe.p, wolfe_idx, c->s_ptime.p, c->s_tdir.p, c->s_step.p,
-                                          c->s_ptrial.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, n_active);
+    if (coupled)
+      k_armijo_coupled<<<1, 32, 0, st>>>(re - rb, c->s_etr.p, c->s_wolfe.p, c->s_ptime.p, c->s_tdir.p, c->s_step.p, c->s_ptrial.p,
+                                         c->s_tstep.p, c->s_ttime.p, c->s_done.p, n_active);
+    else
+      k_armijo<<<div_up(n, 64), 64, 0, st>>>(rb, re, c->s_etr.p, c->s_wolfe.p, wolfe_idx, c->s_ptime.p, c->s_tdir.p, c->s_step.p,
+                                            c->s_ptrial.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, n_active);
     TOB_LAUNCH_CHECK(c);
     TOB_TRY(read_back(c, n_active, sizeof(int)));
     c->ctr.line_search_trials += (uint64_t)n * (TOB_LS_TRIALS - 1);
@@ -219,20 +273,23 @@ static int exchange(tob_ctx* c, DBuf<double>& buf, size_t elems_per_robot) {
 static int iterate_once(tob_ctx* c, int mode, double* gnorm_out) {
   const int U = c->n_robots(), rb = c->own_begin, re = c->own_end;
   cudaStream_t st = c->stream;
-  if (mode != 0) return fail_msg(c, "coupled multi-robot mode (decouple=0) is not implemented yet");
+  const bool coupled = mode == 1;
+  if (mode != 0 && mode != 1) return fail_msg(c, "tob_admm_iterate: mode must be 0 (decoupled) or 1 (coupled)");
+  if (coupled && (c->ag || rb != 0 || re != U)) return fail_msg(c, "coupled mode is not sharded: run it on one context holding all robots");
   // (1) control points of every robot are needed for the inter-robot planes
   if (U > 1) TOB_TRY(exchange(c, c->s_spline, (size_t)3 * c->T));
   TOB_TRY(separate_resident(c, rb, re, 1));
   // (2) Newton direction (geo.P of the owned rows is still current from the plane pass)
   TOB_TRY(gradient_blocks(c, rb, re, 1));
-  TOB_TRY(solve_directions(c, rb, re, U > 1));
+  if (coupled) TOB_TRY(solve_coupled(c));
+  else TOB_TRY(solve_directions(c, rb, re, U > 1));
   // (3) CCD step bound
   if (U > 1) {
     TOB_TRY(exchange(c, c->s_dir, (size_t)3 * c->T));
     TOB_TRY(exchange(c, c->s_wolfe, 1));
     TOB_TRY(exchange(c, c->s_gnorm, 1));
     TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, 0, U, 3));
-    TOB_TRY(self_ccd_steps(c, 0, c->s_selfstep.p));
+    TOB_TRY(self_ccd_steps(c, coupled ? 1 : 0, c->s_selfstep.p));
   } else {
     TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, rb, re, 3));
   }
@@ -241,11 +298,19 @@ static int iterate_once(tob_ctx* c, int mode, double* gnorm_out) {
   k_fill_int<<<div_up(U, 64), 64, 0, st>>>(c->kmax.p, U, 0);
   TOB_LAUNCH_CHECK(c);
   TOB_TRY(ccd_position_steps(c));
-  k_ls_init<<<div_up(re - rb, 64), 64, 0, st>>>(rb, re, c->kmax.p, c->d_steps.p, c->s_selfstep.p, U > 1 ? 1 : 0, c->s_ptime.p,
-                                                c->s_tdir.p, c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p);
-  TOB_LAUNCH_CHECK(c);
-  // (4) Armijo; multi-robot: every robot uses the LAST robot's wolfe (global overwritten, Optimization3D_multi.h:730,792)
-  TOB_TRY(line_search(c, rb, re, U > 1 ? U - 1 : -1));
+  if (coupled) {
+    if (U == 1) { double one = 1.0; TOB_TRY(upload(c, c->s_selfstep, &one, 1)); }
+    k_ls_init_coupled<<<1, 32, 0, st>>>(U, c->kmax.p, c->d_steps.p, c->s_selfstep.p, c->s_ptime.p, c->s_tdir.p, c->s_step.p,
+                                        c->s_tstep.p, c->s_ttime.p, c->s_done.p);
+    TOB_LAUNCH_CHECK(c);
+    TOB_TRY(line_search(c, rb, re, 0, true));
+  } else {
+    k_ls_init<<<div_up(re - rb, 64), 64, 0, st>>>(rb, re, c->kmax.p, c->d_steps.p, c->s_selfstep.p, U > 1 ? 1 : 0, c->s_ptime.p,
+                                                  c->s_tdir.p, c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p);
+    TOB_LAUNCH_CHECK(c);
+    // (4) Armijo; multi-robot: every robot uses the LAST robot's wolfe (global overwritten, Optimization3D_multi.h:730,792)
+    TOB_TRY(line_search(c, rb, re, U > 1 ? U - 1 : -1));
+  }
   // (5) slack + dual
   TOB_TRY(slack_update(c, rb, re));
   // gnorm global of the reference
@@ -425,6 +490,25 @@ int tob_broadphase_ccd(tob_ctx* c, const double* splines, const double* directio
   return bp_download(c, n_robots, offsets, ids, cap, total);
 }
 
+int tob_box_query(tob_ctx* c, const double* lo, const double* hi, double d, uint32_t* ids, uint64_t cap, uint64_t* total) {
+  TOB_TRY(need(c, true, true));
+  cudaSetDevice(c->device);
+  TOB_CUDA(c, c->geo.box.ensure((size_t)6 * c->rows_all()));
+  double b[6] = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
+  TOB_TRY(upload(c, c->geo.box, b, 6));
+  c->states_valid = false;
+  uint64_t t = 0;
+  TOB_TRY(broadphase_rows(c, 0, 1, d, &t));
+  if (total) *total = t;
+  if (!ids || t > cap || t == 0) return 0;
+  std::vector<uint32_t> pts(t);
+  TOB_CUDA(c, cudaMemcpyAsync(pts.data(), c->cand_pt.p, t * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (uint64_t i = 0; i < t; i++) ids[i] = c->h_pid[pts[i]];
+  std::sort(ids, ids + t);
+  return 0;
+}
+
 }  // extern "C"
 
 // ---- batched primitives --------------------------------------------------------------------------------------------
@@ -436,6 +520,25 @@ __global__ void k_gjk_batch(const double* A, const double* B, int n, double* v) 
   for (int j = 0; j < NA; j++) for (int k = 0; k < 3; k++) a[j][k] = A[(size_t)i * NA * 3 + k * NA + j];
   for (int j = 0; j < NB; j++) for (int k = 0; k < 3; k++) b[j][k] = B[(size_t)i * NB * 3 + k * NB + j];
   gjk_witness<NA, NB>(a, b, v + 3 * (size_t)i);
+}
+
+#define TOB_DYN_MAX 16
+__global__ void k_gjk_batch_n(const double* A, int na, const double* B, int nb, int n, double* v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[TOB_DYN_MAX][3], b[TOB_DYN_MAX][3];
+  for (int j = 0; j < na; j++) for (int k = 0; k < 3; k++) a[j][k] = A[(size_t)i * na * 3 + k * na + j];
+  for (int j = 0; j < nb; j++) for (int k = 0; k < 3; k++) b[j][k] = B[(size_t)i * nb * 3 + k * nb + j];
+  gjk_witness_n(a, na, b, nb, v + 3 * (size_t)i);
+}
+
+__global__ void k_kdop_batch_n(const double* A, int na, const double* B, int nb, const double* kdop, int n, double d, uint8_t* flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[TOB_DYN_MAX][3], b[TOB_DYN_MAX][3];
+  for (int j = 0; j < na; j++) for (int k = 0; k < 3; k++) a[j][k] = A[(size_t)i * na * 3 + k * na + j];
+  for (int j = 0; j < nb; j++) for (int k = 0; k < 3; k++) b[j][k] = B[(size_t)i * nb * 3 + k * nb + j];
+  flags[i] = kdop_overlap_n(a, na, b, nb, kdop, d) ? 1 : 0;
 }
 
 __global__ void k_kdop_batch(const double* P, const double* q, const double* kdop, int n, double d, uint8_t* flags) {
@@ -473,6 +576,15 @@ __global__ void k_plane_hulls_batch(const double* P0, const double* P1, int n, d
   d[i] = dd;
 }
 
+__global__ void k_refine_d_batch(const double* P0, const double* P1, const double* cc, int n, double offset, double margin, double* d) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[6][3], b[6][3], c3[3] = {cc[3 * (size_t)i], cc[3 * (size_t)i + 1], cc[3 * (size_t)i + 2]}, dd = d[i];
+  for (int j = 0; j < 6; j++) for (int k = 0; k < 3; k++) { a[j][k] = P0[(size_t)i * 18 + k * 6 + j]; b[j][k] = P1[(size_t)i * 18 + k * 6 + j]; }
+  refine_d(a, b, c3, offset, margin, &dd, 10000);
+  d[i] = dd;
+}
+
 extern "C" {
 
 int tob_gjk_batch(tob_ctx* c, const double* A, int na, const double* B, int nb, int n, double* v) {
@@ -487,7 +599,8 @@ int tob_gjk_batch(tob_ctx* c, const double* A, int na, const double* B, int nb, 
   else if (na == 12 && nb == 1) k_gjk_batch<12, 1><<<g, 64, 0, c->stream>>>(dA, dB, n, c->scratch2.p);
   else if (na == 6 && nb == 6) k_gjk_batch<6, 6><<<g, 64, 0, c->stream>>>(dA, dB, n, c->scratch2.p);
   else if (na == 12 && nb == 12) k_gjk_batch<12, 12><<<g, 64, 0, c->stream>>>(dA, dB, n, c->scratch2.p);
-  else return fail_msg(c, "tob_gjk_batch: supported (na,nb) are (6,1) (12,1) (6,6) (12,12)");
+  else if (na >= 1 && nb >= 1 && na <= TOB_DYN_MAX && nb <= TOB_DYN_MAX) k_gjk_batch_n<<<g, 64, 0, c->stream>>>(dA, na, dB, nb, n, c->scratch2.p);
+  else return fail_msg(c, "tob_gjk_batch: vertex counts must be in 1..16");
   TOB_LAUNCH_CHECK(c);
   TOB_CUDA(c, cudaMemcpyAsync(v, c->scratch2.p, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   TOB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -500,6 +613,20 @@ int tob_kdop_dcd_batch(tob_ctx* c, const double* P, const double* q, int n, doub
   TOB_CUDA(c, c->scratch.ensure((size_t)21 * n)); TOB_CUDA(c, c->scratch8.ensure(n));
   TOB_TRY(upload(c, c->scratch, P, (size_t)18 * n)); TOB_TRY(upload(c, c->scratch, q, (size_t)3 * n, (size_t)18 * n));
   k_kdop_batch<<<div_up(n, 64), 64, 0, c->stream>>>(c->scratch.p, c->scratch.p + (size_t)18 * n, c->d_kdop.p, n, d, c->scratch8.p);
+  TOB_LAUNCH_CHECK(c);
+  TOB_CUDA(c, cudaMemcpyAsync(flags, c->scratch8.p, n, cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int tob_kdop_batch(tob_ctx* c, const double* A, int na, const double* B, int nb, int n, double d, uint8_t* flags) {
+  TOB_TRY(need(c, true, false));
+  cudaSetDevice(c->device);
+  if (na < 1 || nb < 1 || na > TOB_DYN_MAX || nb > TOB_DYN_MAX) return fail_msg(c, "tob_kdop_batch: vertex counts must be in 1..16");
+  size_t sa = (size_t)n * na * 3, sb = (size_t)n * nb * 3;
+  TOB_CUDA(c, c->scratch.ensure(sa + sb)); TOB_CUDA(c, c->scratch8.ensure(n));
+  TOB_TRY(upload(c, c->scratch, A, sa)); TOB_TRY(upload(c, c->scratch, B, sb, sa));
+  k_kdop_batch_n<<<div_up(n, 64), 64, 0, c->stream>>>(c->scratch.p, na, c->scratch.p + sa, nb, c->d_kdop.p, n, d, c->scratch8.p);
   TOB_LAUNCH_CHECK(c);
   TOB_CUDA(c, cudaMemcpyAsync(flags, c->scratch8.p, n, cudaMemcpyDeviceToHost, c->stream));
   TOB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -539,7 +666,44 @@ int tob_plane_hulls_batch(tob_ctx* c, const double* P0, const double* P1, int n,
   return 0;
 }
 
+int tob_refine_d_batch(tob_ctx* c, const double* P0, const double* P1, const double* cc, int n, double* d_io) {
+  TOB_TRY(need(c, false, false));
+  cudaSetDevice(c->device);
+  TOB_CUDA(c, c->scratch.ensure((size_t)36 * n)); TOB_CUDA(c, c->scratch2.ensure((size_t)4 * n));
+  TOB_TRY(upload(c, c->scratch, P0, (size_t)18 * n)); TOB_TRY(upload(c, c->scratch, P1, (size_t)18 * n, (size_t)18 * n));
+  TOB_TRY(upload(c, c->scratch2, cc, (size_t)3 * n)); TOB_TRY(upload(c, c->scratch2, d_io, n, (size_t)3 * n));
+  k_refine_d_batch<<<div_up(n, 64), 64, 0, c->stream>>>(c->scratch.p, c->scratch.p + (size_t)18 * n, c->scratch2.p, n, c->prm.offset,
+                                                      c->prm.margin, c->scratch2.p + (size_t)3 * n);
+  TOB_LAUNCH_CHECK(c);
+  TOB_CUDA(c, cudaMemcpyAsync(d_io, c->scratch2.p + (size_t)3 * n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 // ---- planes ------------------------------------------------------------------------------------------------------------
+int tob_separate_self(tob_ctx* c, const double* splines, int n_robots, uint32_t* offsets, double* cc, double* dd, uint64_t cap,
+                      uint64_t* total) {
+  TOB_TRY(need(c, true, false));
+  cudaSetDevice(c->device);
+  if (n_robots != c->n_robots()) return fail_msg(c, "tob_separate_self needs all uav_num robots");
+  TOB_TRY(stage_splines(c, splines, nullptr, n_robots));
+  TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, 0, n_robots, 1));
+  TOB_TRY(pack_self_only(c));
+  uint64_t np = c->n_planes;
+  if (total) *total = np;
+  const int rows = c->rows_all();
+  std::vector<uint32_t> off(rows + 1);
+  TOB_CUDA(c, cudaMemcpyAsync(off.data(), c->pl_off.p, off.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  std::vector<double> pl(4 * np);
+  const bool want = np && cc && dd && np <= cap;
+  if (want) TOB_CUDA(c, cudaMemcpyAsync(pl.data(), c->pl.p, 4 * np * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (offsets) for (int r = 0; r <= rows; r++) offsets[r] = off[r];
+  if (want)
+    for (uint64_t k = 0; k < np; k++) { cc[3 * k] = pl[4 * k]; cc[3 * k + 1] = pl[4 * k + 1]; cc[3 * k + 2] = pl[4 * k + 2]; dd[k] = pl[4 * k + 3]; }
+  return 0;
+}
+
 int tob_separate_planes(tob_ctx* c, const double* splines, int n_robots, int with_self, uint32_t* offsets, double* cc,
                         double* dd, uint64_t cap, uint64_t* total) {
   TOB_TRY(need(c, true, true));
@@ -748,14 +912,108 @@ int tob_self_broadphase(tob_ctx* c, const double* P, const double* D, int u, dou
   return 0;
 }
 
+// ---- line search -------------------------------------------------------------------------------------------------------------------
+int tob_line_search(tob_ctx* c, int robot, tob_state* st, const double* direction, double t_direction, double wolfe, double* step_io) {
+  TOB_TRY(need(c, true, false)); TOB_TRY(robot_ok(c, robot));
+  cudaSetDevice(c->device);
+  if (!step_io) return fail_msg(c, "tob_line_search: step_io is required");
+  const int T = c->T;
+  TOB_TRY(put_state(c, robot, st));
+  TOB_TRY(upload(c, c->s_dir, direction, 3 * T, (size_t)robot * 3 * T));
+  TOB_TRY(upload(c, c->s_tdir, &t_direction, 1, robot));
+  TOB_TRY(upload(c, c->s_wolfe, &wolfe, 1, robot));
+  k_fill_int<<<div_up(c->n_robots(), 64), 64, 0, c->stream>>>(c->kmax.p, c->n_robots(), 0);
+  TOB_LAUNCH_CHECK(c);
+  int use_self = 0;
+  if (*step_io < 0) {           // Optimization3D_admm::spline_line_search: the bound is Step::position_step
+    if (c->n_pts == 0) return fail_msg(c, "tob_line_search: no point cloud");
+    TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, robot, robot + 1, 3));
+    uint64_t total = 0;
+    TOB_TRY(broadphase(c, robot, robot + 1, c->prm.offset, &total));
+    TOB_TRY(ccd_position_steps(c));
+  } else {                      // Optimization3D_multi::spline_line_search: the caller's bound (<= 1)
+    if (*step_io > 1.0) return fail_msg(c, "tob_line_search: a caller-provided step bound must be <= 1");
+    TOB_TRY(upload(c, c->s_selfstep, step_io, 1, robot));
+    use_self = 1;
+  }
+  k_ls_init<<<1, 64, 0, c->stream>>>(robot, robot + 1, c->kmax.p, c->d_steps.p, c->s_selfstep.p, use_self, c->s_ptime.p, c->s_tdir.p,
+                                     c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p);
+  TOB_LAUNCH_CHECK(c);
+  TOB_TRY(line_search(c, robot, robot + 1, -1));
+  TOB_CUDA(c, cudaMemcpyAsync(st->spline, c->s_spline.p + (size_t)robot * 3 * T, 3 * T * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(st->piece_time, c->s_ptime.p + robot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_TRY(read_back(c, c->s_step.p + robot, sizeof(double)));
+  *step_io = c->h_pinned[0];
+  return 0;
+}
+
+int tob_last_wolfe(tob_ctx* c, double* wolfe) {
+  TOB_TRY(need(c, true, false));
+  cudaSetDevice(c->device);
+  if (!c->states_valid || !wolfe) return fail_msg(c, "tob_last_wolfe: no iteration has run");
+  // the reference's global `wolfe` after an iteration is the value left by update_slack_lambda's last piece; callers only
+  // consume the one written by the direction solve, which is what is kept here (last robot, Optimization3D_multi.h:730)
+  TOB_TRY(read_back(c, c->s_wolfe.p + (c->n_robots() - 1), sizeof(double)));
+  *wolfe = c->h_pinned[0];
+  return 0;
+}
+
+int tob_row_blocks(tob_ctx* c, const double* spline, double piece_time, int tr_id, int which, double* grad18, double* hess324,
+                   double* g_t, double* h_t, double* partgrad18) {
+  TOB_TRY(need(c, true, false));
+  cudaSetDevice(c->device);
+  if (tr_id < 0 || tr_id >= c->n_tr) return fail_msg(c, "tob_row_blocks: tr_id out of range");
+  if (!c->pl_off.p) {
+    std::vector<uint32_t> off(c->n_tr + 1, 0u);
+    TOB_TRY(pack_planes_from_host(c, 0, 1, off.data(), nullptr, nullptr));
+  }
+  TOB_TRY(upload(c, c->s_spline, spline, 3 * c->T, 0));
+  TOB_TRY(upload(c, c->s_ptime, &piece_time, 1, 0));
+  c->states_valid = false;
+  TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, 0, 1, 0));
+  TOB_CUDA(c, c->scratch2.ensure(362));
+  TOB_TRY(row_blocks(c, tr_id, which, c->scratch2.p));
+  TOB_TRY(read_back(c, c->scratch2.p, 362 * sizeof(double)));
+  const double* h = c->h_pinned;
+  if (grad18) memcpy(grad18, h, 18 * sizeof(double));
+  if (hess324) memcpy(hess324, h + 18, 324 * sizeof(double));
+  if (g_t) *g_t = h[342];
+  if (h_t) *h_t = h[343];
+  if (partgrad18) memcpy(partgrad18, h + 344, 18 * sizeof(double));
+  return 0;
+}
+
 // ---- slack / dual ---------------------------------------------------------------------------------------------------------------
 int tob_update_slack_lambda(tob_ctx* c, tob_state* st) {
   TOB_TRY(need(c, true, false));
   cudaSetDevice(c->device);
   TOB_TRY(put_state(c, 0, st));
   TOB_TRY(slack_update(c, 0, 1));
-  TOB_TRY(get_state(c, 0, st));
-  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int P = c->prm.piece_num;
+  cudaStream_t s = c->stream;   // spline and piece time are inputs only: not written back
+  TOB_CUDA(c, cudaMemcpyAsync(st->p_slack, c->s_pslack.p, 18 * P * sizeof(double), cudaMemcpyDeviceToHost, s));
+  TOB_CUDA(c, cudaMemcpyAsync(st->t_slack, c->s_tslack.p, P * sizeof(double), cudaMemcpyDeviceToHost, s));
+  TOB_CUDA(c, cudaMemcpyAsync(st->p_lambda, c->s_plambda.p, 18 * P * sizeof(double), cudaMemcpyDeviceToHost, s));
+  TOB_CUDA(c, cudaMemcpyAsync(st->t_lambda, c->s_tlambda.p, P * sizeof(double), cudaMemcpyDeviceToHost, s));
+  TOB_CUDA(c, cudaStreamSynchronize(s));
+  return 0;
+}
+
+int tob_slack_terms(tob_ctx* c, const double* c_spline, double piece_time, const double* p_part, double t_part,
+                    const double* p_lambda, double t_lambda, int consensus, double* energy, double* grad19, double* hess361) {
+  TOB_TRY(need(c, true, false));
+  cudaSetDevice(c->device);
+  if (!p_part) return fail_msg(c, "tob_slack_terms: p_part is required");
+  double in[57];
+  for (int i = 0; i < 18; i++) { in[i] = c_spline ? c_spline[i] : 0.0; in[18 + i] = p_part[i]; in[36 + i] = p_lambda ? p_lambda[i] : 0.0; }
+  in[54] = piece_time; in[55] = t_part; in[56] = t_lambda;
+  TOB_CUDA(c, c->scratch.ensure(57)); TOB_CUDA(c, c->scratch2.ensure(381));
+  TOB_TRY(upload(c, c->scratch, in, 57));
+  TOB_TRY(slack_terms(c, c->scratch.p, consensus, c->scratch2.p));
+  TOB_TRY(read_back(c, c->scratch2.p, 381 * sizeof(double)));
+  if (energy) *energy = c->h_pinned[0];
+  if (grad19) memcpy(grad19, c->h_pinned + 1, 19 * sizeof(double));
+  if (hess361) memcpy(hess361, c->h_pinned + 20, 361 * sizeof(double));
   return 0;
 }
 

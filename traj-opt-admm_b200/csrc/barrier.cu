@@ -448,6 +448,56 @@ __global__ void __launch_bounds__(384) k_piece(PieceArgs a) {
   for (int e = threadIdx.x; e < 361; e += blockDim.x) a.pc_h[361 * pb + e] = s_H[e];
 }
 
+// ---- function-level: one row's block in piece coordinates ------------------------------------------------------------
+// which = 0: Gradient_admm::local_plane_barrier_gradient :331-407 (terms 0..5); which = 1: local_bound_gradient :409-572
+// (terms 6..14, plus g_t, h_t and the mixed time column).  out: g[18] | H[324 col-major] | g_t | h_t | partgrad[18]
+__global__ void k_row_expand(const double* __restrict__ terms, const double* __restrict__ B, int which, double* __restrict__ out) {
+  __shared__ double s_a[ROW_TERMS * 6];
+  const int t0 = which ? 6 : 0, t1 = which ? ROW_TERMS : 6;
+  for (int i = threadIdx.x; i < ROW_TERMS * 6; i += blockDim.x) {
+    const int tt = i / 6, mm = i - 6 * tt;
+    double v;
+    if (tt < 6) v = B[tt + 6 * mm];
+    else if (tt < 11) { int j = tt - 6; v = B[j + 1 + 6 * mm] - B[j + 6 * mm]; }
+    else { int j = tt - 11; v = B[j + 2 + 6 * mm] - 2 * B[j + 1 + 6 * mm] + B[j + 6 * mm]; }
+    s_a[i] = v;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 324; e += blockDim.x) {
+    const int r = e % 18, cc = e / 18, m1 = r / 3, k1 = r % 3, m2 = cc / 3, k2 = cc % 3;
+    const int lo = k1 < k2 ? k1 : k2, hi = k1 < k2 ? k2 : k1;
+    const int q = lo == 0 ? hi : (lo == 1 ? 2 + hi : 5);
+    double v = 0;
+    for (int t = t0; t < t1; t++) v += s_a[6 * t + m1] * s_a[6 * t + m2] * terms[TERM_SZ * t + q];
+    out[18 + e] = v;
+  }
+  if (threadIdx.x < 18) {
+    const int m1 = threadIdx.x / 3, k1 = threadIdx.x % 3;
+    double g = 0, pg = 0;
+    for (int t = t0; t < t1; t++) { g += s_a[6 * t + m1] * terms[TERM_SZ * t + 6 + k1]; pg += s_a[6 * t + m1] * terms[TERM_SZ * t + 9 + k1]; }
+    out[threadIdx.x] = g;
+    out[18 + 324 + 2 + threadIdx.x] = pg;
+  }
+  if (threadIdx.x == 32) {
+    out[18 + 324] = which ? terms[ROW_TERMS * TERM_SZ] : 0.0;
+    out[18 + 324 + 1] = which ? terms[ROW_TERMS * TERM_SZ + 1] : 0.0;
+  }
+}
+
+// geo.P of robot 0 and the resident planes must be current; fills out_dev[362]
+int row_blocks(tob_ctx* c, int tr, int which, double* out_dev) {
+  TOB_CUDA(c, c->row_terms.ensure((size_t)ROW_REC * c->rows_all()));
+  RowGradArgs a;
+  a.P = c->geo.P.p; a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p; a.ptime = c->s_ptime.p;
+  a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
+  a.n_tr = c->n_tr; a.row_begin = tr; a.terms = c->row_terms.p;
+  k_row_grad<<<1, 128, 0, c->stream>>>(a);
+  TOB_LAUNCH_CHECK(c);
+  k_row_expand<<<1, 128, 0, c->stream>>>(c->row_terms.p + (size_t)ROW_REC * tr, c->d_basis.p + (size_t)36 * tr, which, out_dev);
+  TOB_LAUNCH_CHECK(c);
+  return 0;
+}
+
 // geo.P must hold the CURRENT rows of robots [rb,re) (compute_rows without trial); planes resident.
 int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd) {
   int rows_total = c->n_robots() * c->n_tr;

@@ -121,6 +121,7 @@ struct tob_ctx {
   size_t h_stage_cap = 0;
 
   tob_counters ctr{};
+  bool bcr_attr_set = false;          // cudaFuncSetAttribute(k_solve_bcr) done on this device
 
   // optional per-kernel CUDA-event timing (bench.py roofline): off by default
   bool prof_on = false;
@@ -193,6 +194,7 @@ int lbvh_build(tob_ctx* c, const double* V_host, uint32_t n);
 int exclusive_scan_u32(tob_ctx* c, const uint32_t* in, uint32_t* out, size_t n, uint32_t* total_dev);  // out[n] = total
 // queries rows [rb*n_tr, re*n_tr) whose boxes are in geo.box; fills cand_pt/cand_row (GLOBAL rows) and row_off
 int broadphase(tob_ctx* c, int rb, int re, double d, uint64_t* total_host);
+int broadphase_rows(tob_ctx* c, int row_base, int rows, double d, uint64_t* total_host);
 // segments.cu : mode bits: 1 = k-DOP extents, 2 = direction rows + swept box, 4 = trial point spline+step*dir
 int compute_rows(tob_ctx* c, const double* spline_dev, const double* dir_dev, const double* step_dev, int rb, int re, int mode);
 // narrow.cu
@@ -200,13 +202,17 @@ int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self);
 int pack_planes_from_host(tob_ctx* c, int rb, int re, const uint32_t* offsets, const double* cc, const double* dd);
 int ccd_position_steps(tob_ctx* c);
 int self_planes(tob_ctx* c);
+int pack_self_only(tob_ctx* c);
 int self_ccd_steps(tob_ctx* c, int coupled, double* steps_dev);
 // barrier.cu
 int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* tstep, const double* ttime, int KT, int k0,
                   int k1, double* e_dev);
 int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd);
+int row_blocks(tob_ctx* c, int tr, int which, double* out_dev);
 // solve.cu
 int solve_directions(tob_ctx* c, int rb, int re, int dense_shift);
+int solve_coupled(tob_ctx* c);
 int slack_update(tob_ctx* c, int rb, int re);
+int slack_terms(tob_ctx* c, const double* in57_dev, int consensus, double* out381_dev);
 
 }  // namespace tob

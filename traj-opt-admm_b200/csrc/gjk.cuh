@@ -382,6 +382,76 @@ TOB_HD void gjk_witness(const double (*A)[3], const double (*B)[3], double* vout
   vout[0] = v[0]; vout[1] = v[1]; vout[2] = v[2];
 }
 
+// runtime-sized variants (function-level entry points CCD::GJKDCD with edges / arbitrary vertex counts, CCD.h:17-114)
+TOB_HD void support_max_n(const double (*pts)[3], int n, double* cur, const double* dir) {
+  double best = dot3(cur, dir);
+  int better = -1;
+  for (int i = 0; i < n; ++i) {
+    double sv = dot3(pts[i], dir);
+    if (sv > best) { best = sv; better = i; }
+  }
+  if (better != -1) { cur[0] = pts[better][0]; cur[1] = pts[better][1]; cur[2] = pts[better][2]; }
+}
+
+TOB_HD void gjk_witness_n(const double (*A)[3], int na, const double (*B)[3], int nb, double* vout) {
+  Simplex s;
+  s.lam[0] = s.lam[1] = s.lam[2] = s.lam[3] = 0;
+  s.wid[0] = s.wid[1] = s.wid[2] = s.wid[3] = 0;
+  double v[3], vm[3], w[3], sa[3], sb[3];
+  const double eps_rel2 = 1e-5 * 1e-5;
+  const double eps_tot = 1e-15;
+  double wmax = 0;
+  s.n = 1;
+  for (int i = 0; i < 3; ++i) {
+    v[i] = A[0][i] - B[0][i];
+    sa[i] = A[0][i];
+    sb[i] = B[0][i];
+    s.v[0][i] = v[i];
+  }
+  int k = 0;
+  do {
+    k++;
+    vm[0] = -v[0]; vm[1] = -v[1]; vm[2] = -v[2];
+    support_max_n(A, na, sa, vm);
+    support_max_n(B, nb, sb, v);
+    w[0] = sa[0] - sb[0]; w[1] = sa[1] - sb[1]; w[2] = sa[2] - sb[2];
+    double vv = nrm2(v);
+    if ((vv - dot3(v, w)) <= eps_rel2 * vv) break;
+    if (vv < eps_rel2) break;
+    int i = s.n;
+    s.v[i][0] = w[0]; s.v[i][1] = w[1]; s.v[i][2] = w[2];
+    s.n++;
+    if (s.n == 4) sv_tet(s, v);
+    else if (s.n == 3) sv_tri(s, v);
+    else if (s.n == 2) sv_line(s, v);
+    for (i = 0; i < s.n; i++) {
+      double tn = nrm2(s.v[i]);
+      if (tn > wmax) wmax = tn;
+    }
+    if (nrm2(v) <= (eps_tot * eps_tot * wmax)) break;
+  } while ((s.n != 4) && (k != 50));
+  vout[0] = v[0]; vout[1] = v[1]; vout[2] = v[2];
+}
+
+TOB_HD bool kdop_overlap_n(const double (*A)[3], int na, const double (*B)[3], int nb, const double* kdop, double d) {
+  for (int k = 0; k < TOB_KDOP_AXES; ++k) {
+    double x = kdop[3 * k], y = kdop[3 * k + 1], z = kdop[3 * k + 2];
+    double uA = -INFINITY, lA = INFINITY, uB = -INFINITY, lB = INFINITY;
+    for (int i = 0; i < na; ++i) {
+      double lv = x * A[i][0] + y * A[i][1] + z * A[i][2];
+      if (lv < lA) lA = lv;
+      if (lv > uA) uA = lv;
+    }
+    for (int i = 0; i < nb; ++i) {
+      double lv = x * B[i][0] + y * B[i][1] + z * B[i][2];
+      if (lv < lB) lB = lv;
+      if (lv > uB) uB = lv;
+    }
+    if (uB < lA - d || uA < lB - d) return false;
+  }
+  return true;
+}
+
 // ---- k-DOP -------------------------------------------------------------------------------------------
 // level of a point on axis (x,y,z): x*px + y*py + z*pz, left to right
 TOB_HD double kdop_level(double x, double y, double z, const double* p) { return x * p[0] + y * p[1] + z * p[2]; }

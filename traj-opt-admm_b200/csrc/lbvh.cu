@@ -363,11 +363,15 @@ __global__ void k_row_offsets(const uint32_t* __restrict__ task_off, uint32_t ro
 
 // boxes of rows [rb*n_tr, re*n_tr) must be in c->geo.box.  Leaves c->cand_pt / cand_row / row_off, total on host.
 int broadphase(tob_ctx* c, int rb, int re, double d, uint64_t* total_host) {
+  return broadphase_rows(c, rb * c->n_tr, (re - rb) * c->n_tr, d, total_host);
+}
+
+// same for an arbitrary row range [row_base, row_base+rows) of geo.box (tob_box_query uses row 0 with a caller box)
+int broadphase_rows(tob_ctx* c, int row_base, int rows, double d, uint64_t* total_host) {
   if (c->n_pts == 0) return fail_msg(c, "broadphase: no point cloud uploaded");
-  const int rows = (re - rb) * c->n_tr;
   BpArgs a;
   a.box = c->geo.box.p;
-  a.rows = rows; a.n1 = c->lvl[1].count; a.n_tasks = (uint32_t)rows * a.n1; a.d = d; a.row_base = (uint32_t)rb * c->n_tr;
+  a.rows = rows; a.n1 = c->lvl[1].count; a.n_tasks = (uint32_t)rows * a.n1; a.d = d; a.row_base = (uint32_t)row_base;
   for (int k = 0; k < 3; k++) {
     a.l1lo[k] = c->lvl[1].lo[k]; a.l1hi[k] = c->lvl[1].hi[k];
     a.l0lo[k] = c->lvl[0].lo[k]; a.l0hi[k] = c->lvl[0].hi[k];

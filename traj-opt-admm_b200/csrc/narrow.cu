@@ -238,6 +238,18 @@ int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self) {
   return pack_rows(c, rb, re, true, ws);
 }
 
+// inter-robot planes only (Optimization3D_multi::separate_self on empty lists): geo of ALL robots must be current
+int pack_self_only(tob_ctx* c) {
+  const int rows = c->rows_all();
+  TOB_CUDA(c, c->row_off.ensure(rows + 2));
+  TOB_CUDA(c, c->cflag_off.ensure(2));
+  TOB_CUDA(c, cudaMemsetAsync(c->row_off.p, 0, (rows + 2) * sizeof(uint32_t), c->stream));
+  TOB_CUDA(c, cudaMemsetAsync(c->cflag_off.p, 0, 2 * sizeof(uint32_t), c->stream));
+  c->n_cand = 0;
+  TOB_TRY(self_planes(c));
+  return pack_rows(c, 0, c->n_robots(), false, true);
+}
+
 // caller-provided plane lists (the reference's c_lists/d_lists) for robots [rb,re): offsets over (re-rb)*n_tr rows
 int pack_planes_from_host(tob_ctx* c, int rb, int re, const uint32_t* offsets, const double* cc, const double* dd) {
   cudaStream_t st = c->stream;

@@ -245,6 +245,11 @@ struct BcrArgs {
   int P, T, robot_begin;
   double *dir, *tdir, *wolfe, *gnorm;
   int* status;
+  // coupled multi-robot system (Optimization3D_multi::update_spline :508-639): block diagonal per robot + ONE shared
+  // arrow row for the common piece time.  Each robot's CTA exports z = B^-1 g, y = B^-1 a and its partial sums; the
+  // Schur complement over all robots is closed by k_couple_finish.  Null for the decoupled / single-robot solve.
+  double* cpl_part;   // robots x 5 : a.y, a.z, g.g, h_t, g_t
+  double* cpl_zyg;    // robots x (N*9) x 3 : z, y, g
 };
 
 __global__ void __launch_bounds__(1024) k_solve_bcr(BcrArgs a) {
@@ -447,6 +452,23 @@ __global__ void __launch_bounds__(1024) k_solve_bcr(BcrArgs a) {
   }
   if (lane == 0) { s_red[wp][0] = ay; s_red[wp][1] = az; s_red[wp][2] = gg; }
   __syncthreads();
+  if (a.cpl_part) {
+    if (tid == 0) {
+      double AY = 0, AZ = 0, GG = 0;
+      for (int i = 0; i < nw; i++) { AY += s_red[i][0]; AZ += s_red[i][1]; GG += s_red[i][2]; }
+      double* o = a.cpl_part + 5 * (size_t)robot;
+      o[0] = AY; o[1] = AZ; o[2] = GG; o[3] = s_h; o[4] = s_gt;
+      a.status[robot] = s_fail;
+    }
+    double* o = a.cpl_zyg + (size_t)robot * N * BS * 3;
+    for (int e = tid; e < N * BS; e += blockDim.x) {
+      const int b = e / BS, r = e - BS * b;
+      o[3 * e] = blk[(size_t)b * BLK + 243 + r];
+      o[3 * e + 1] = blk[(size_t)b * BLK + 243 + BS + r];
+      o[3 * e + 2] = rhs0[b * 18 + r];
+    }
+    return;
+  }
   if (tid == 0) {
     double AY = 0, AZ = 0, GG = 0;
     for (int i = 0; i < nw; i++) { AY += s_red[i][0]; AZ += s_red[i][1]; GG += s_red[i][2]; }
@@ -480,6 +502,72 @@ __global__ void __launch_bounds__(1024) k_solve_bcr(BcrArgs a) {
   }
 }
 
+// closes the shared-time Schur complement of the coupled system: t = (sum a_i.z_i - sum g_t,i) / (sum h_t,i - sum a_i.y_i),
+// x_i = -z_i - y_i t, wolfe = -(sum x_i.g_i + t sum g_t,i), gnorm = |G| / U (Optimization3D_multi.h:553-583)
+__global__ void __launch_bounds__(256) k_couple_finish(const double* __restrict__ part, const double* __restrict__ zyg, int U, int N, int T,
+                                                       double* dir, double* tdir, double* wolfe, double* gnorm, int* status) {
+  __shared__ double s_t, s_gt, s_w[8];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    double AY = 0, AZ = 0, GG = 0, HT = 0, GT = 0;
+    for (int u = 0; u < U; u++) { AY += part[5 * u]; AZ += part[5 * u + 1]; GG += part[5 * u + 2]; HT += part[5 * u + 3]; GT += part[5 * u + 4]; }
+    const double schur = HT - AY;
+    if (!(schur > 0)) status[0] = 1;
+    s_t = (AZ - GT) / schur;
+    s_gt = GT;
+    const double gn = sqrt(GG + GT * GT) / double(U);
+    for (int u = 0; u < U; u++) { tdir[u] = s_t; gnorm[u] = gn; }
+  }
+  __syncthreads();
+  const double t = s_t;
+  double wl = 0;
+  const int per = N * BS;
+  for (int i = tid; i < U * per; i += blockDim.x) {
+    const int u = i / per, e = i - u * per, b = e / BS, r = e - BS * b;
+    const bool fixed = (b == 0 && r < 6) || (b == N - 1 && r >= 3);
+    const double x = fixed ? 0.0 : (-zyg[3 * (size_t)i] - zyg[3 * (size_t)i + 1] * t);
+    wl += x * zyg[3 * (size_t)i + 2];
+    dir[(size_t)u * 3 * T + (size_t)(e % 3) * T + e / 3] = x;
+  }
+  for (int o = 16; o; o >>= 1) wl += __shfl_xor_sync(0xffffffffu, wl, o);
+  if ((tid & 31) == 0) s_w[tid >> 5] = wl;
+  __syncthreads();
+  if (tid == 0) {
+    double W = 0;
+    for (int i = 0; i < 8; i++) W += s_w[i];
+    W += t * s_gt;
+    for (int u = 0; u < U; u++) wolfe[u] = -W;
+  }
+}
+
+int solve_coupled(tob_ctx* c) {
+  const int U = c->n_robots(), N = c->prm.piece_num + 1;
+  const size_t smem_bcr = ((size_t)N * BLK + (size_t)N * 18) * sizeof(double);
+  if (smem_bcr > 220 * 1024) return fail_msg(c, "coupled mode: trajectories with more than ~100 pieces are not supported");
+  TOB_CUDA(c, c->scratch.ensure((size_t)5 * U));
+  TOB_CUDA(c, c->scratch2.ensure((size_t)3 * U * N * BS));
+  BcrArgs a;
+  a.pc_g = c->pc_g.p; a.pc_h = c->pc_h.p; a.P = c->prm.piece_num; a.T = c->T; a.robot_begin = 0;
+  a.dir = c->s_dir.p; a.tdir = c->s_tdir.p; a.wolfe = c->s_wolfe.p; a.gnorm = c->s_gnorm.p; a.status = c->solve_status.p;
+  a.cpl_part = c->scratch.p; a.cpl_zyg = c->scratch2.p;
+  if (!c->bcr_attr_set) {
+    TOB_CUDA(c, cudaFuncSetAttribute(k_solve_bcr, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    c->bcr_attr_set = true;
+  }
+  int warps = (N + 1) / 2;
+  if (warps < 4) warps = 4;
+  if (warps > 32) warps = 32;
+  {
+    Prof prof(c, K_SOLVE);
+    k_solve_bcr<<<U, warps * 32, smem_bcr, c->stream>>>(a);
+    TOB_LAUNCH_CHECK(c);
+  }
+  k_couple_finish<<<1, 256, 0, c->stream>>>(c->scratch.p, c->scratch2.p, U, N, c->T, c->s_dir.p, c->s_tdir.p, c->s_wolfe.p, c->s_gnorm.p,
+                                            c->solve_status.p);
+  TOB_LAUNCH_CHECK(c);
+  return 0;
+}
+
 int solve_directions(tob_ctx* c, int rb, int re, int dense_shift) {
   int nr = c->n_robots();
   TOB_CUDA(c, c->s_dir.ensure((size_t)3 * c->T * nr));
@@ -493,10 +581,10 @@ int solve_directions(tob_ctx* c, int rb, int re, int dense_shift) {
     BcrArgs a;
     a.pc_g = c->pc_g.p; a.pc_h = c->pc_h.p; a.P = c->prm.piece_num; a.T = c->T; a.robot_begin = rb;
     a.dir = c->s_dir.p; a.tdir = c->s_tdir.p; a.wolfe = c->s_wolfe.p; a.gnorm = c->s_gnorm.p; a.status = c->solve_status.p;
-    static bool attr_set = false;
-    if (!attr_set) {
+    a.cpl_part = nullptr; a.cpl_zyg = nullptr;
+    if (!c->bcr_attr_set) {
       TOB_CUDA(c, cudaFuncSetAttribute(k_solve_bcr, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      attr_set = true;
+      c->bcr_attr_set = true;
     }
     int warps = (N + 1) / 2;
     if (warps < 4) warps = 4;
@@ -521,6 +609,9 @@ int solve_directions(tob_ctx* c, int rb, int re, int dense_shift) {
 }
 
 // ---- slack / dual update ---------------------------------------------------------------------------------------------
+// One WARP per (robot, piece); the 19x19 system lives in shared memory (lane i owns row i in the Cholesky and the
+// substitutions).  H = (ks/t^5) M_dynamic (x) I3 + mu I with one dense arrow row/column for the piece time; the reference
+// factors it with Eigen::LLT and falls back to an eigenvalue shift when that fails (Optimization3D_admm.h:313-327).
 struct SlackArgs {
   const double *spline, *ptime, *convert, *mdyn;
   double *pslack, *tslack, *plambda, *tlambda;
@@ -528,151 +619,187 @@ struct SlackArgs {
   int P, T, robot_begin, n;
 };
 
-__device__ double dyn_energy(const double* M, const double* p /*[6][3] as p[m*3+k]*/, double t, double ks, double kt) {
-  double e = 0;
-  double c5 = ks / pow(t, 5.0);
-  for (int k = 0; k < 3; k++) {
-    double q = 0;
-    for (int r = 0; r < 6; r++) {
-      double mx = 0;
-      for (int s = 0; s < 6; s++) mx += M[r + 6 * s] * p[s * 3 + k];
-      q += p[r * 3 + k] * mx;
+struct SlackWarp {       // per-warp shared scratch
+  double H[361];         // Gradient_admm::slack_gradient hessian, col-major ld 19
+  double A[361];         // reduced system -> Cholesky factor
+  double g[19], b[19], x[19];
+  double cs[18], p[18], lam[18], dir[18], pn[18];   // [m][k] flatten (row-major 6x3), as the reference's transposeInPlace + Map
+  double ws[4 * 19];
+};
+
+__device__ __forceinline__ double wsum(double v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Gradient_admm::dynamic_gradient :633-671 (consensus == 0: g[18] = g_t, H(18,18) = h_t, arrow = partgrad) or
+// Gradient_admm::slack_gradient :574-622 (consensus == 1) of the point S.p / t.  Returns the jerk energy.
+__device__ double slack_build_warp(SlackWarp& S, const double* __restrict__ M, double ptime, double t, double tlam, double mu,
+                                   double ks, double kt, int consensus) {
+  const int lane = threadIdx.x & 31;
+  const double c5 = ks / pow(t, 5.0);
+  double q = 0, gdyn = 0;
+  if (lane < 18) {
+    const int r = lane / 3, k = lane - 3 * r;
+    double mx = 0;
+#pragma unroll
+    for (int s2 = 0; s2 < 6; s2++) mx += M[r + 6 * s2] * S.p[s2 * 3 + k];
+    gdyn = c5 * mx;
+    q = S.p[lane] * mx;
+  }
+  const double dyn = c5 * 0.5 * wsum(q);
+  for (int e = lane; e < 361; e += 32) {
+    const int r = e % 19, cc = e / 19;
+    double v = 0;
+    if (r < 18 && cc < 18) {
+      if (r % 3 == cc % 3) v = c5 * M[r / 3 + 6 * (cc / 3)];
+      if (consensus && r == cc) v += mu;
     }
-    e += c5 * 0.5 * q;
+    S.H[e] = v;
+  }
+  __syncwarp();
+  if (lane < 18) {
+    const double pg = -5 * gdyn / t;
+    S.H[lane + 19 * 18] = pg;
+    S.H[18 + 19 * lane] = pg;
+    S.g[lane] = consensus ? gdyn + (mu * (S.p[lane] - S.cs[lane]) - S.lam[lane]) : gdyn;
+  }
+  if (lane == 0) {
+    double g_t = -5 * dyn / t + kt * 1.1 * pow(t, 0.1);
+    double h_t = 30 * dyn / (t * t) + kt * 0.11 * pow(t, -0.9);
+    if (consensus) { g_t += mu * (t - ptime) - tlam; h_t += mu; }
+    S.g[18] = g_t;
+    S.H[18 + 19 * 18] = h_t;
+  }
+  __syncwarp();
+  return dyn;
+}
+
+// Energy_admm::slack_energy :172-190 (consensus == 1) / dynamic_energy :199-215 (consensus == 0) of the point pv / t
+__device__ double slack_energy_warp(const SlackWarp& S, const double* pv, const double* __restrict__ M, double ptime, double t,
+                                    double tlam, double mu, double ks, double kt, int consensus) {
+  const int lane = threadIdx.x & 31;
+  double q = 0, sq = 0, lin = 0;
+  if (lane < 18) {
+    const int r = lane / 3, k = lane - 3 * r;
+    double mx = 0;
+#pragma unroll
+    for (int s2 = 0; s2 < 6; s2++) mx += M[r + 6 * s2] * pv[s2 * 3 + k];
+    q = pv[lane] * mx;
+    const double dlt = S.cs[lane] - pv[lane];
+    sq = dlt * dlt;
+    lin = S.lam[lane] * dlt;
+  }
+  q = wsum(q); sq = wsum(sq); lin = wsum(lin);
+  double e = ks / pow(t, 5.0) * 0.5 * q + kt * pow(t, 1.1);
+  if (consensus) {
+    e += mu / 2.0 * sq;
+    e += mu / 2.0 * (ptime - t) * (ptime - t);
+    e += lin;
+    e += tlam * (ptime - t);
   }
   return e;
 }
 
-__device__ double slack_energy_dev(const double* M, const double* cs, double ptime, const double* p, double t, const double* lam,
-                                   double tlam, double mu, double ks, double kt) {
-  double e = dyn_energy(M, p, t, ks, kt) + kt * pow(t, 1.1);
-  double sq = 0, lin = 0;
-  for (int i = 0; i < 18; i++) {
-    double dlt = cs[i] - p[i];
-    sq += dlt * dlt;
-    lin += lam[i] * dlt;
+// L L^T x = b by the warp (L col-major ld n in its lower triangle, lane i owns row i); v (shared) in: b, out: x
+__device__ void warp_chol_solve(const double* L, int n, double* v) {
+  const int lane = threadIdx.x & 31;
+  for (int k = 0; k < n; k++) {
+    if (lane == k) v[k] = v[k] / L[k + n * k];
+    __syncwarp();
+    if (lane > k && lane < n) v[lane] -= L[lane + n * k] * v[k];
+    __syncwarp();
   }
-  e += mu / 2.0 * sq;
-  e += mu / 2.0 * (ptime - t) * (ptime - t);
-  e += lin;
-  e += tlam * (ptime - t);
-  return e;
+  for (int k = n - 1; k >= 0; k--) {
+    if (lane == k) v[k] = v[k] / L[k + n * k];
+    __syncwarp();
+    if (lane < k) v[lane] -= L[k + n * lane] * v[k];
+    __syncwarp();
+  }
 }
 
-__global__ void __launch_bounds__(32) k_slack(SlackArgs a) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.n) return;
+#define SLACK_WARPS 4
+__global__ void __launch_bounds__(32 * SLACK_WARPS) k_slack(SlackArgs a) {
+  __shared__ SlackWarp sm[SLACK_WARPS];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int idx = blockIdx.x * SLACK_WARPS + wp;
+  if (idx >= a.n) return;                                     // whole warp leaves together
+  SlackWarp& S = sm[wp];
   const int robot = a.robot_begin + idx / a.P, sp = idx % a.P;
   const double* C = a.convert + (size_t)36 * sp;
   const double* M = a.mdyn;
   const double ptime = a.ptime[robot];
-  // local copies, layout [m][k] (row-major flatten of the 6x3 blocks, as the reference's transposeInPlace + Map)
-  double cs[18], p[18], lam[18];
-  for (int k = 0; k < 3; k++)
-    for (int r = 0; r < 6; r++) {
-      double acc = 0;
-      for (int kk = 0; kk < 6; kk++) acc += C[r + 6 * kk] * a.spline[(size_t)robot * 3 * a.T + (size_t)k * a.T + 3 * sp + kk];
-      cs[r * 3 + k] = acc;
-      size_t s = (size_t)robot * 18 * a.P + (size_t)k * 6 * a.P + 6 * sp + r;
-      p[r * 3 + k] = a.pslack[s];
-      lam[r * 3 + k] = a.plambda[s];
-    }
+  if (lane < 18) {
+    const int r = lane / 3, k = lane - 3 * r;
+    double acc = 0;
+#pragma unroll
+    for (int kk = 0; kk < 6; kk++) acc += C[r + 6 * kk] * a.spline[(size_t)robot * 3 * a.T + (size_t)k * a.T + 3 * sp + kk];
+    S.cs[lane] = acc;
+    const size_t s = (size_t)robot * 18 * a.P + (size_t)k * 6 * a.P + 6 * sp + r;
+    S.p[lane] = a.pslack[s];
+    S.lam[lane] = a.plambda[s];
+    S.dir[lane] = 0.0;
+  }
   const size_t pb = (size_t)robot * a.P + sp;
-  double t = a.tslack[pb], tlam = a.tlambda[pb];
-  // gradient / Hessian (19)
-  double g[19], H[19 * 19];
-  for (int i = 0; i < 361; i++) H[i] = 0;
-  const double c5 = a.ks / pow(t, 5.0);
-  double dyn = 0;
-  for (int k = 0; k < 3; k++) {
-    double q = 0;
-    for (int r = 0; r < 6; r++) {
-      double mx = 0;
-      for (int s = 0; s < 6; s++) mx += M[r + 6 * s] * p[s * 3 + k];
-      g[r * 3 + k] = c5 * mx;
-      q += p[r * 3 + k] * mx;
-    }
-    dyn += c5 * 0.5 * q;
-  }
-  for (int r = 0; r < 6; r++)
-    for (int s = 0; s < 6; s++)
-      for (int k = 0; k < 3; k++) H[(r * 3 + k) + 19 * (s * 3 + k)] = c5 * M[r + 6 * s];
-  double g_t = -5 * dyn / t + a.kt * 1.1 * pow(t, 0.1);
-  double h_t = 30 * dyn / (t * t) + a.kt * 0.11 * pow(t, -0.9);
-  for (int i = 0; i < 18; i++) {
-    double pg = -5 * g[i] / t;
-    H[i + 19 * 18] = pg;
-    H[18 + 19 * i] = pg;
-    g[i] += a.mu * (p[i] - cs[i]) - lam[i];
-    H[i + 19 * i] += a.mu;
-  }
-  g_t += a.mu * (t - ptime) - tlam;
-  h_t += a.mu;
-  g[18] = g_t;
-  H[18 + 19 * 18] = h_t;
+  const double t0 = a.tslack[pb], tlam = a.tlambda[pb];
+  __syncwarp();
+  slack_build_warp(S, M, ptime, t0, tlam, a.mu, a.ks, a.kt, 1);
   // reduced system: first piece drops control points 0,1; last piece drops control points 4,5
   int off = 0, tn = 6;
   if (sp == 0) { off = 6; tn = 4; }
   else if (sp == a.P - 1) { off = 0; tn = 4; }
   const int n = 3 * tn + 1;
-  double A[19 * 19], L[19 * 19], b[19], x[19];
-  auto gi = [&](int i) { return i < 3 * tn ? off + i : 18; };
-  for (int i = 0; i < n; i++) {
-    b[i] = g[gi(i)];
-    for (int j = 0; j < n; j++) A[i + n * j] = H[gi(i) + 19 * gi(j)];
+#define GI(i) ((i) < 3 * tn ? off + (i) : 18)
+  for (int e = lane; e < n * n; e += 32) { const int i = e % n, j = e / n; S.A[e] = S.H[GI(i) + 19 * GI(j)]; }
+  if (lane < n) { S.b[lane] = S.g[GI(lane)]; S.x[lane] = S.b[lane]; }
+  __syncwarp();
+  if (!warp_chol_is_spd(S.A, n)) {
+    __syncwarp();
+    for (int e = lane; e < n * n; e += 32) { const int i = e % n, j = e / n; S.A[e] = S.H[GI(i) + 19 * GI(j)]; }
+    __syncwarp();
+    const double mn = warp_min_eig(S.A, n, S.ws, S.ws + 19, S.ws + 38, S.ws + 57);
+    __syncwarp();
+    for (int e = lane; e < n * n; e += 32) {
+      const int i = e % n, j = e / n;
+      double v = S.H[GI(i) + 19 * GI(j)];
+      if (i == j && mn < 0) v = v - mn * 1.0 + 0.01 * 1.0;
+      S.A[e] = v;
+    }
+    __syncwarp();
+    warp_chol_is_spd(S.A, n);
   }
-  if (!chol_is_spd_n(A, L, n)) {
-    for (int i = 0; i < n * n; i++) L[i] = A[i];
-    double mn = jacobi_min_eig_n(L, n);
-    if (mn < 0)
-      for (int k = 0; k < n; k++) A[k + n * k] = A[k + n * k] - mn * 1.0 + 0.01 * 1.0;
-    chol_is_spd_n(A, L, n);
-  }
-  // x = -A^-1 b
-  for (int i = 0; i < n; i++) {
-    double s = b[i];
-    for (int j = 0; j < i; j++) s -= L[i + n * j] * x[j];
-    x[i] = s / L[i + n * i];
-  }
-  for (int i = n - 1; i >= 0; i--) {
-    double s = x[i];
-    for (int j = i + 1; j < n; j++) s -= L[j + n * i] * x[j];
-    x[i] = s / L[i + n * i];
-  }
-  double wolfe = 0;
-  for (int i = 0; i < n; i++) { x[i] = -x[i]; }
-  for (int i = 0; i < n; i++) wolfe += x[i] * b[i];
-  wolfe = -wolfe;
-  double dir[18];
-  for (int i = 0; i < 18; i++) dir[i] = 0;
-  {
-    int base = (sp == 0) ? 6 : 0;
-    for (int i = 0; i < 3 * tn; i++) dir[base + i] = x[i];
-  }
-  const double tdir = x[3 * tn];
+#undef GI
+  __syncwarp();
+  warp_chol_solve(S.A, n, S.x);                                // x = H^-1 g ; the Newton step is -x
+  double wl = (lane < n) ? S.x[lane] * S.b[lane] : 0.0;
+  const double wolfe = wsum(wl);                               // = -(-x).g
+  if (lane < 3 * tn) S.dir[(sp == 0 ? 6 : 0) + lane] = -S.x[lane];
+  __syncwarp();
+  const double tdir = -S.x[3 * tn];
   double step = 1.0;
-  if (t + step * tdir <= 0) step = -0.95 * t / tdir;
-  const double e0 = slack_energy_dev(M, cs, ptime, p, t, lam, tlam, a.mu, a.ks, a.kt);
-  const double t0 = t;
-  t = t0 + step * tdir;
-  double pn[18];
-  int guard = 0;
-  while (guard++ < 400) {
-    for (int i = 0; i < 18; i++) pn[i] = p[i] + step * dir[i];
-    double e1 = slack_energy_dev(M, cs, ptime, pn, t, lam, tlam, a.mu, a.ks, a.kt);
-    if (!(e0 - 1e-4 * wolfe * step < e1)) break;
+  if (t0 + step * tdir <= 0) step = -0.95 * t0 / tdir;
+  const double e0 = slack_energy_warp(S, S.p, M, ptime, t0, tlam, a.mu, a.ks, a.kt, 1);
+  double t = t0 + step * tdir;
+  for (int guard = 0; guard < 400; guard++) {
+    if (lane < 18) S.pn[lane] = S.p[lane] + step * S.dir[lane];
+    __syncwarp();
+    const double e1 = slack_energy_warp(S, S.pn, M, ptime, t, tlam, a.mu, a.ks, a.kt, 1);
+    if (!(e0 - 1e-4 * wolfe * step < e1)) break;               // uniform: e1 is identical on every lane
     step *= 0.8;
     t = t0 + step * tdir;
+    __syncwarp();
   }
-  for (int i = 0; i < 18; i++) pn[i] = p[i] + step * dir[i];
-  for (int k = 0; k < 3; k++)
-    for (int r = 0; r < 6; r++) {
-      size_t s = (size_t)robot * 18 * a.P + (size_t)k * 6 * a.P + 6 * sp + r;
-      a.pslack[s] = pn[r * 3 + k];
-      a.plambda[s] = lam[r * 3 + k] + a.mu * (cs[r * 3 + k] - pn[r * 3 + k]);
-    }
-  a.tslack[pb] = t;
-  a.tlambda[pb] = tlam + a.mu * (ptime - t);
+  if (lane < 18) {
+    const int r = lane / 3, k = lane - 3 * r;
+    const double pn = S.p[lane] + step * S.dir[lane];
+    const size_t s = (size_t)robot * 18 * a.P + (size_t)k * 6 * a.P + 6 * sp + r;
+    a.pslack[s] = pn;
+    a.plambda[s] = S.lam[lane] + a.mu * (S.cs[lane] - pn);
+  }
+  if (lane == 0) {
+    a.tslack[pb] = t;
+    a.tlambda[pb] = tlam + a.mu * (ptime - t);
+  }
 }
 
 int slack_update(tob_ctx* c, int rb, int re) {
@@ -682,7 +809,33 @@ int slack_update(tob_ctx* c, int rb, int re) {
   a.mu = c->prm.mu; a.ks = c->prm.ks; a.kt = c->prm.kt; a.P = c->prm.piece_num; a.T = c->T; a.robot_begin = rb;
   a.n = (re - rb) * c->prm.piece_num;
   Prof prof(c, K_SLACK);
-  k_slack<<<div_up(a.n, 32), 32, 0, c->stream>>>(a);
+  k_slack<<<div_up(a.n, SLACK_WARPS), 32 * SLACK_WARPS, 0, c->stream>>>(a);
+  TOB_LAUNCH_CHECK(c);
+  return 0;
+}
+
+// function-level entry point: one piece, one warp.  in: cs[18] p[18] lam[18] (6x3 col-major each), scal = {ptime, t, tlam}
+// out: energy, g[19], H[361]
+__global__ void k_slack_terms(const double* in, const double* mdyn, double mu, double ks, double kt, int consensus, double* out) {
+  __shared__ SlackWarp S;
+  const int lane = threadIdx.x & 31;
+  if (lane < 18) {
+    const int r = lane / 3, k = lane - 3 * r;          // [m][k] <- col-major 6x3
+    S.cs[lane] = in[r + 6 * k];
+    S.p[lane] = in[18 + r + 6 * k];
+    S.lam[lane] = in[36 + r + 6 * k];
+  }
+  __syncwarp();
+  const double ptime = in[54], t = in[55], tlam = in[56];
+  const double e = slack_energy_warp(S, S.p, mdyn, ptime, t, tlam, mu, ks, kt, consensus);
+  slack_build_warp(S, mdyn, ptime, t, tlam, mu, ks, kt, consensus);
+  if (lane == 0) out[0] = e;
+  if (lane < 19) out[1 + lane] = S.g[lane];
+  for (int i = lane; i < 361; i += 32) out[20 + i] = S.H[i];
+}
+
+int slack_terms(tob_ctx* c, const double* in57_dev, int consensus, double* out381_dev) {
+  k_slack_terms<<<1, 32, 0, c->stream>>>(in57_dev, c->d_mdyn.p, c->prm.mu, c->prm.ks, c->prm.kt, consensus, out381_dev);
   TOB_LAUNCH_CHECK(c);
   return 0;
 }

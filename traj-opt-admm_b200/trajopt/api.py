@@ -269,8 +269,11 @@ class Solver:
         arr = (TobState * len(hss))(*[h.c for h in hss])
         return hss, arr
 
-    def optimization(self, st, mode=0):
-        """host in / host out, the shape of Optimization3D_admm::optimization / _multi::optimization_decouple"""
+    def optimization(self, st, mode=0, coupled=False):
+        """host in / host out, the shape of Optimization3D_admm::optimization / _multi::optimization_decouple;
+        coupled=True (mode 1): Optimization3D_multi::optimization, one shared piece time"""
+        if coupled:
+            mode = 1
         single = isinstance(st, dict)
         sts = [st] if single else st
         hss, arr = self._states(sts)

@@ -217,3 +217,33 @@ def initial_states(scene, piece_time=20.0):
     single = scene["uav_num"] == 1
     f = init_spline_single if single else init_spline_multi
     return [init_state(f(wp), piece_time) for wp in scene["way_points"]]
+
+
+def write_reference_files(scene, root, name="scene.obj", config=None):
+    """Lay the scene out the way the reference executables read it (cwd = root):
+      Config_File/3D.json                      Main/admmPathPlanning3D.cpp:368-397 (note the underscore)
+      model/single/<name> | model/multiple/<name>   OBJ with `v x y z` lines (CCDUtils.h:317-391)
+      init/<name>_init_file.txt                one way-point per line (single, :82-101); all robots side by side, 3 columns
+                                               each (multi, multiPathPlanning3D.cpp:78-121)
+      result/                                  result file directory
+    The multi executable multiplies cloud and way-points by 5 (multiPathPlanning3D.cpp:107,536): files store /5."""
+    import json
+    import os
+    multi = scene["uav_num"] > 1
+    scale = 0.2 if multi else 1.0
+    for d in ("Config_File", "model/single", "model/multiple", "init", "result"):
+        os.makedirs(os.path.join(root, d), exist_ok=True)
+    cfg = {"lambda": 10, "epsilon": 0.1, "margin": 0.1, "offset": 0.1, "res": 8, "vel_limit": 2, "acc_limit": 2, "mu": 0.1,
+           "stop": 1e-2, "optimal_plane": 0, "decouple": 1, "init": 1, "init_ob": 1, "gui": 0, "exit": 0, "auto": 0}
+    cfg.update(config or {})
+    with open(os.path.join(root, "Config_File", "3D.json"), "w") as f:
+        json.dump(cfg, f, indent=1)
+    V = np.asarray(scene["V"]) * scale
+    with open(os.path.join(root, "model", "multiple" if multi else "single", name), "w") as f:
+        for p in V:
+            f.write("v %.17g %.17g %.17g\n" % (p[0], p[1], p[2]))
+    wps = [np.asarray(w) * scale for w in scene["way_points"]]
+    with open(os.path.join(root, "init", name + "_init_file.txt"), "w") as f:
+        for i in range(len(wps[0])):
+            f.write(" ".join("%.17g %.17g %.17g" % tuple(w[i]) for w in wps) + "\n")
+    return cfg
