@@ -33,10 +33,40 @@ import numpy as np  # noqa: E402
 METRIC = "ADMM iters/sec"
 UNIT = "iter/s"
 
-# algorithmic FP64 work per unit
-FLOP_PER_DCD_CANDIDATE = 3.0e3    # k-DOP 49x(7x5+4) worst case + GJK(6,1) ~3-6 iterations
-BYTES_PER_DCD_CANDIDATE = 28 + 32  # point + id read, plane write when accepted
-FLOP_PER_CCD_CANDIDATE = 3.4e3 + 1.5e3  # swept k-DOP on 12 points + >= one GJK(12,1)
+# ---- algorithmic work per unit; `roofline.achieved` is computed from these
+FLOP_PER_DCD_CANDIDATE = 3.0e3          # 49-DOP worst case 49x(7x5+4) + GJK(6,1), ~3-6 iterations
+BYTES_PER_DCD_CANDIDATE = 28 + 32       # point + id read, plane write when accepted
+FLOP_PER_CCD_CANDIDATE = 3.4e3 + 1.5e3  # swept 49-DOP on 12 points + >= one GJK(12,1)
+FLOP_PER_PLANE_EVAL = 36.0              # 6 control points x (3 mul + 3 add)
+FLOP_PER_ACTIVE_TERM_E = 45.0           # energy: 2 sub, 3 mul, 1 div, log ~35 DFMA-equivalents
+FLOP_PER_ACTIVE_TERM_G = 116.0          # gradient: e1,e2 (~95) + 3 + 6 accumulates x 2
+BYTES_PER_PLANE = 32.0
+
+
+def kernel_models(per_step, geo):
+    """kernel name -> (algorithmic FP64 flop per step, algorithmic bytes per step, bound) for the kernels of one ADMM
+    iteration.  per_step: counters of the profiled pass divided by its step count; geo: rows, n1 (level-1 nodes), P, T, U."""
+    rows, n1, P, T, U = geo["rows"], geo["n1"], geo["P"], geo["T"], geo["U"]
+    cand, ccd, planes = per_step["dcd_candidates"], per_step["ccd_candidates"], per_step["planes"]
+    evals, terms = per_step["energy_plane_evals"], per_step["barrier_terms"]
+    e_evals = max(evals - planes, 0.0)                      # line-search passes (the gradient pass streams each plane once)
+    g_share = planes / evals if evals else 0.0
+    n_sys = 3 * (T - 4) + 1
+    bp_bytes = 48.0 * rows + 48.0 * rows * n1 + 28.0 * cand  # row box + one level-1 box per (row, node) + candidate out
+    return {
+        "k_rows": (0.0, rows * (18 + 6 + 2 * 49) * 8.0 * 2, "hbm"),
+        "k_bp_count": (0.0, bp_bytes - 4.0 * cand, "hbm"),
+        "k_bp_fill": (0.0, bp_bytes, "hbm"),
+        "k_bp_ccd": (FLOP_PER_CCD_CANDIDATE * ccd, 48.0 * rows + 48.0 * rows * n1 + 24.0 * ccd, "hbm"),
+        "k_narrow": (FLOP_PER_DCD_CANDIDATE * cand, BYTES_PER_DCD_CANDIDATE * cand, "fp64"),
+        "k_pack": (0.0, 4.0 * cand + 72.0 * planes, "hbm"),
+        "k_row_energy": (FLOP_PER_PLANE_EVAL * e_evals + FLOP_PER_ACTIVE_TERM_E * terms * (1 - g_share), BYTES_PER_PLANE * e_evals, "fp64"),
+        "k_row_grad": (FLOP_PER_PLANE_EVAL * planes + FLOP_PER_ACTIVE_TERM_G * terms * g_share, BYTES_PER_PLANE * planes, "fp64"),
+        "k_piece": (6.0 * (18 + 171) * 2 * rows + U * P * 19 ** 3 / 3.0, U * P * (361 + 19) * 8.0, "fp64"),
+        "k_solve_bcr": (U * (n_sys * (17 ** 2 + 17) + 2 * n_sys * 17), U * P * (361 + 19) * 8.0, "fp64"),
+        "k_slack": (U * P * (19 ** 3 / 3.0 + 4 * 19 * 19), U * P * (4 * 19) * 8.0, "fp64"),
+        "k_robot_ls": (0.0, 9.0 * rows * 20, "hbm"),
+    }
 
 
 def workload(name, n_pts=None):
@@ -54,41 +84,71 @@ def workload(name, n_pts=None):
     return sc
 
 
-def clock_sampler(stop, out):
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)"""
-    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    try:
-        p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200", "-i",
-                              os.environ.get("LOCAL_RANK", "0")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-    except Exception:
-        return
-    def reader():
-        for line in p.stdout:
-            out.append(line.strip())
-    t = threading.Thread(target=reader, daemon=True)
-    t.start()
-    stop.wait()
-    p.terminate()
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons of the GPU this rank drives, sampled in-process through NVML every few ms DURING the timed
+    region (an `nvidia-smi -lms` child needs ~1 s to start and initialises the driver inside the timed region).  Falls back
+    to one `nvidia-smi` query per sample when pynvml is unavailable."""
 
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-def summarize_clocks(lines):
-    sm, smax, reasons = [], [], set()
-    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    for ln in lines:
-        f = [x.strip() for x in ln.split(",")]
-        if len(f) < 9:
-            continue
+    def __init__(self, cuda_index, period=0.004):
+        super().__init__(daemon=True)
+        self.period, self.sm, self.reasons, self.smax, self.h, self.nv = period, [], set(), None, None, None
+        self._stop_evt, self._on = threading.Event(), threading.Event()
         try:
-            sm.append(float(f[1])); smax.append(float(f[2]))
-        except ValueError:
-            continue
-        for i, nm in enumerate(names):
-            if f[5 + i].lower().startswith("active"):
-                reasons.add(nm)
-    if not sm:
-        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-    return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(cuda_index).uuid)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+            self.nv = pynvml
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        if self.nv is not None:
+            self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            r = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            for nm, bit in self.REASONS:
+                if r & bit:
+                    self.reasons.add(nm)
+        else:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            out = subprocess.run(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-i",
+                                  os.environ.get("LOCAL_RANK", "0")], capture_output=True, text=True).stdout
+            f = [x.strip() for x in out.strip().split(",")]
+            self.sm.append(float(f[0])); self.smax = float(f[1])
+            for (nm, _), v in zip(self.REASONS, f[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(nm)
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            if self._on.is_set():
+                try:
+                    self._sample()
+                except Exception:
+                    pass
+            time.sleep(self.period)
+
+    def begin(self):
+        self._on.set()
+
+    def end(self):
+        self._on.clear()
+
+    def close(self):
+        self._stop_evt.set()
+
+    def summary(self):
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.smax, "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def pinned_state(st):
@@ -145,10 +205,10 @@ def run_ours(args):
     for _ in range(args.warmup):
         s.iterate(1)
     s.reset_counters()
-    lines, stop = [], threading.Event()
-    th = threading.Thread(target=clock_sampler, args=(stop, lines), daemon=True)
-    th.start()
+    sampler = ClockSampler(local)
+    sampler.start()
     barrier()
+    sampler.begin()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     gn = 0.0
     for a, b in ev:
@@ -159,7 +219,7 @@ def run_ours(args):
             gn = s.iterate(1)
             b.record()
     barrier()
-    stop.set()
+    sampler.end()
     ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(ms))
     ctr = s.counters()
@@ -179,17 +239,18 @@ def run_ours(args):
     # ---- end to end through the host-in/host-out entry point
     cur = [pinned_state(x) for x in s.states_download(st0)]
     barrier()
+    sampler.begin()
     e2e_s = 0.0
     for _ in range(args.steps):
         flush.fill_(1)                      # same L2 policy as the resident loop; not inside the timed call
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        res = s.optimization(cur)           # host buffers in -> H2D -> one ADMM iteration -> D2H -> host buffers out
+        res = s.optimization(cur, inplace=True)   # host buffers in -> H2D -> one ADMM iteration -> D2H -> same host buffers
         e2e_s += time.perf_counter() - t0
         for c_, r_ in zip(cur, res):
-            for k in ("spline", "p_slack", "t_slack", "p_lambda", "t_lambda"):
-                c_[k][...] = r_[k]
             c_["piece_time"] = r_["piece_time"]
+    sampler.end()
+    sampler.close()
     T = s.T
     state_bytes = U * (3 * T + 1 + 18 * P + P + 18 * P + P) * 8
 
@@ -206,35 +267,49 @@ def run_ours(args):
     mult = 1 if sharded else world         # sharded: ONE problem over all ranks (strong); else N replicas (weak)
     value = mult * args.steps / (total_ms * 1e-3)
     pair_evals = ctr["dcd_candidates"] + ctr["ccd_candidates"] + ctr["energy_plane_evals"]
-    # dominant kernel by device time
-    dom = max(prof.items(), key=lambda kv: kv[1][0])
-    tot_prof_ms = sum(v[0] for v in prof.values())
-    roof = None
+    # ---- roofline: every kernel against its bound, `roofline` = the kernel with the largest share of device time
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
-    name, (kms, kn) = dom
-    if kn:
-        per_launch_s = kms * 1e-3 / kn
-        if name == "k_narrow":
-            units = pctr["dcd_candidates"] / kn
-            flops, byts = FLOP_PER_DCD_CANDIDATE * units, BYTES_PER_DCD_CANDIDATE * units
-        elif name == "k_ccd":
-            units = pctr["ccd_candidates"] / kn
-            flops, byts = FLOP_PER_CCD_CANDIDATE * units, 28 * units
-        else:
-            units, flops, byts = 0, 0.0, 0.0
-        roof = {"kernel": name, "bound": "fp64", "achieved": flops / per_launch_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": (flops / per_launch_s / 1e12) / fp64_peak if fp64_peak else None, "traffic": None,
-                "peak_source": "DFMA microbenchmark run in this process (tob_fp64_peak)",
-                "share_of_step": kms / tot_prof_ms if tot_prof_ms else None, "units_per_launch": units,
-                "avg_launch_ms": per_launch_s * 1e3,
-                "hbm": {"achieved": byts / per_launch_s / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": byts / per_launch_s / 1e9 / hbm_peak,
-                        "peak_source": peak_src}}
+    peak_src = "MEASURED_PEAKS.json (burst copy)" if "hbm_gbs" in peaks else "fallback of B200_PROFILING.md"
+    per_step = {k: pctr[k] / float(args.steps) for k in pctr}
+    n0 = -(-sc["V"].shape[0] // 32)
+    geo = {"rows": U * P * 8, "n1": -(-n0 // 32), "P": P, "T": T, "U": U}
+    models = kernel_models(per_step, geo)
+    tot_prof_ms = sum(v[0] for v in prof.values())
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(sc["name"], {})
+    except Exception:
+        pass
+    ktab = {}
+    for name, (kms, kn) in prof.items():
+        if not kn:
+            continue
+        flop, byts, bound = models.get(name, (0.0, 0.0, "hbm"))
+        sec = kms * 1e-3 / args.steps                         # all launches of this kernel in one step
+        ktab[name] = {"ms_per_step": kms / args.steps, "launches_per_step": kn / float(args.steps), "bound": bound,
+                      "tflops": flop / sec / 1e12, "gbs": byts / sec / 1e9,
+                      "frac": (flop / sec / 1e12 / fp64_peak) if bound == "fp64" and fp64_peak else byts / sec / 1e9 / hbm_peak,
+                      "share_of_step": kms / tot_prof_ms if tot_prof_ms else None}
+    roof = None
+    if ktab:
+        name = max(ktab, key=lambda k: ktab[k]["ms_per_step"])
+        kt = ktab[name]
+        lps = kt["launches_per_step"]
+        fp = kt["bound"] == "fp64"
+        roof = {"kernel": name, "bound": "fp64" if fp else "hbm",
+                "achieved": kt["tflops"] if fp else kt["gbs"], "peak": fp64_peak if fp else hbm_peak, "unit": "TFLOP/s" if fp else "GB/s",
+                "frac": kt["frac"], "traffic": traffic.get(name),
+                "peak_source": "FP64 DFMA microbenchmark run in this process (tob_fp64_peak); no FP64 figure in MEASURED_PEAKS.json" if fp else peak_src,
+                "share_of_step": kt["share_of_step"], "avg_launch_ms": kt["ms_per_step"] / lps, "launches_per_step": lps,
+                "algorithmic_flop_per_launch": models[name][0] / lps if name in models else None,
+                "algorithmic_bytes_per_launch": models[name][1] / lps if name in models else None,
+                "hbm": {"achieved": kt["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": kt["gbs"] / hbm_peak, "peak_source": peak_src},
+                "note": "single-problem kernels of ~10-100 us: latency-bound, see DESIGN.md section 3"}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -245,12 +320,12 @@ def run_ours(args):
                    "multi_gpu": ("robots sharded over ranks, NCCL all-gather of control points/directions" if sharded else
                                  ("replicas only" if world > 1 else "single")), "lbvh_build_s": build_s, "gnorm_last": gn},
         "pair_evals_per_s": pair_evals * mult / (total_ms * 1e-3),
-        "pairs_per_step": {k: ctr[k] / args.steps for k in ("dcd_candidates", "planes", "ccd_candidates", "energy_plane_evals")},
+        "pairs_per_step": {k: ctr[k] / args.steps for k in ("dcd_candidates", "planes", "ccd_candidates", "energy_plane_evals", "barrier_terms")},
         "e2e": {"value": mult * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes},
         "gpu_launches": int(ctr["kernel_launches"]),
-        "clocks": summarize_clocks(lines),
+        "clocks": sampler.summary(),
         "roofline": roof,
-        "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items() if v[1]},
+        "kernels": ktab,
     }
     # CPU baseline on a bounded sample, rank 0, N == 1 only
     if world == 1 and not args.no_cpu:
@@ -324,7 +399,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="forest")

@@ -203,6 +203,7 @@ typedef struct tob_counters {
   uint64_t energy_plane_evals;   /* planes x energy/gradient passes */
   uint64_t self_pairs;           /* inter-robot segment pairs evaluated */
   uint64_t line_search_trials;
+  uint64_t barrier_terms;        /* (control point, plane) terms inside the barrier band (d < margin) that were evaluated */
 } tob_counters;
 int tob_get_counters(const tob_ctx* ctx, tob_counters* out);
 int tob_reset_counters(tob_ctx* ctx);

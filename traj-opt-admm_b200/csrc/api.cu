@@ -101,8 +101,11 @@ __global__ void k_fill_int(int* p, int n, int v) {
 // step = min(self step, 0.8^kmax); clamp so the piece time stays positive (Optimization3D_admm.h:521-524); then lay
 // out the first batch of trial points: k=0 the current point, k=1.. the ladder step, step*0.8, step*0.8*0.8, ...
 __global__ void k_ls_init(int rb, int re, const int* kmax, const double* steps_tab, const double* selfstep, int use_self,
-                          const double* ptime, const double* tdir, double* step, double* tstep, double* ttime, int* done) {
+                          const double* ptime, const double* tdir, double* step, double* tstep, double* ttime, int* done,
+                          DevCounts* dc) {
   int u = rb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (u == rb)
+    for (int r = 0; r < TOB_LS_ROUNDS + 2; r++) dc->ls_pending[r] = 0;
   if (u >= re) return;
   double s = steps_tab[kmax[u]];
   if (use_self) {
@@ -122,39 +125,12 @@ __global__ void k_ls_init(int rb, int re, const int* kmax, const double* steps_t
   done[u] = 0;
 }
 
-// Armijo backtracking over one batch of trial points, in ladder order exactly like the reference's
-// while(e-1e-4*wolfe*step < E(x+step*dir)) step*=0.8 (Optimization3D_admm.h:537-544): the first rung that fails the
-// while-condition is accepted.  wolfe_idx < 0: own wolfe, else the reference's "last robot" quirk.
-__global__ void k_armijo(int rb, int re, const double* etr, const double* wolfe, int wolfe_idx, const double* ptime,
-                         const double* tdir, double* step, double* ptrial, double* tstep, double* ttime, int* done, int* n_active) {
-  int u = rb + blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= re) return;
-  if (done[u]) return;
-  const double w = wolfe[wolfe_idx < 0 ? u : wolfe_idx];
-  const double e0 = etr[u * TOB_LS_TRIALS];
-  for (int k = 1; k < TOB_LS_TRIALS; k++) {
-    const double s = tstep[u * TOB_LS_TRIALS + k];
-    if (!(e0 - 1e-4 * w * s < etr[u * TOB_LS_TRIALS + k])) {
-      step[u] = s;
-      ptrial[u] = ttime[u * TOB_LS_TRIALS + k];
-      done[u] = 1;
-      return;
-    }
-  }
-  double s = tstep[u * TOB_LS_TRIALS + TOB_LS_TRIALS - 1] * 0.8;
-  for (int k = 1; k < TOB_LS_TRIALS; k++) {
-    tstep[u * TOB_LS_TRIALS + k] = s;
-    ttime[u * TOB_LS_TRIALS + k] = ptime[u] + s * tdir[u];
-    s *= 0.8;
-  }
-  atomicAdd(n_active, 1);
-}
-
 // coupled mode (Optimization3D_multi::update_spline :585-636): ONE step and ONE piece time for all robots.
 // step = min(couple_self_step, min_u position_step_u), clamped so that the shared piece time stays positive.
 __global__ void k_ls_init_coupled(int U, const int* kmax, const double* steps_tab, const double* selfstep, const double* ptime,
-                                  const double* tdir, double* step, double* tstep, double* ttime, int* done) {
+                                  const double* tdir, double* step, double* tstep, double* ttime, int* done, DevCounts* dc) {
   if (threadIdx.x || blockIdx.x) return;
+  for (int r = 0; r < TOB_LS_ROUNDS + 2; r++) dc->ls_pending[r] = 0;
   int km = 0;
   for (int u = 0; u < U; u++) if (kmax[u] > km) km = kmax[u];
   double s = selfstep[0];
@@ -177,7 +153,7 @@ __global__ void k_ls_init_coupled(int U, const int* kmax, const double* steps_ta
 
 // joint Armijo test on the summed energy (robots in index order like the reference's loop, Optimization3D_multi.h:641-657)
 __global__ void k_armijo_coupled(int U, const double* etr, const double* wolfe, const double* ptime, const double* tdir, double* step,
-                                 double* ptrial, double* tstep, double* ttime, int* done, int* n_active) {
+                                 double* ptrial, double* tstep, double* ttime, int* done, int* n_active) {   // n_active: &dc->ls_pending[slot]
   if (threadIdx.x || blockIdx.x) return;
   if (done[0]) return;
   double e0 = 0;
@@ -201,10 +177,10 @@ __global__ void k_armijo_coupled(int U, const double* etr, const double* wolfe, 
 }
 
 __global__ void k_apply_step(int rb, int re, int T, const double* step, const double* dir, const double* ptrial, double* spline,
-                             double* ptime) {
+                             double* ptime, const DevCounts* guard) {
   int u = rb + blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= re) return;
+  if (u >= re || iteration_blocked(guard)) return;
   if (i < 3 * T) {
     size_t g = (size_t)u * 3 * T + i;
     spline[g] = spline[g] + step[u] * dir[g];
@@ -223,44 +199,99 @@ static int read_back(tob_ctx* c, const void* dev, size_t bytes) {
   return 0;
 }
 
-// planes of robots [rb,re) from the resident splines
+// device counts -> pinned mirror; the ONE host synchronisation of an iteration
+int sync_counts(tob_ctx* c) {
+  TOB_CUDA(c, cudaMemcpyAsync(c->h_dc, c->dc.p, sizeof(DevCounts), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_cand = c->h_dc->n_cand;
+  c->n_planes = c->h_dc->n_planes;
+  return 0;
+}
+
+static int clear_overflow(tob_ctx* c) {
+  TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->overflow, 0, sizeof(uint32_t), c->stream));
+  return 0;
+}
+
+int grow_cand_capacity(tob_ctx* c, uint64_t need) {
+  uint64_t cap = c->cand_cap ? c->cand_cap : (1u << 20);
+  while (cap < need + need / 4) cap *= 2;
+  if (cap > 0xfff00000ull) return fail_msg(c, "candidate count exceeds the 32-bit index range");
+  c->cand_cap = cap;
+  return ensure_query_buffers(c);
+}
+
+// run `launch` (asynchronous query kernels), read the counts, grow the candidate buffers and repeat on overflow
+template <class F>
+static int run_checked(tob_ctx* c, F&& launch) {
+  for (int attempt = 0; attempt < 8; attempt++) {
+    TOB_TRY(launch());
+    TOB_TRY(sync_counts(c));
+    if (!(c->h_dc->overflow & TOB_OVF_CAND)) return 0;
+    TOB_TRY(clear_overflow(c));
+    TOB_TRY(grow_cand_capacity(c, c->h_dc->n_cand));
+  }
+  return fail_msg(c, "candidate buffers keep overflowing");
+}
+
+// planes of robots [rb,re) from the resident splines (asynchronous)
 static int separate_resident(tob_ctx* c, int rb, int re, int with_self) {
   const int U = c->n_robots();
   bool ws = with_self && U > 1;
   // inter-robot planes need every robot's rows; otherwise only the owned ones
   TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, ws ? 0 : rb, ws ? U : re, 1));
-  uint64_t total = 0;
-  TOB_TRY(broadphase(c, rb, re, c->prm.offset + c->prm.margin, &total));
+  TOB_TRY(broadphase(c, rb, re, c->prm.offset + c->prm.margin, 1));
   TOB_TRY(narrowphase_planes(c, rb, re, ws ? 1 : 0));
   return 0;
 }
 
-// line search of robots [rb,re): s_step / trial tables / s_done prepared by k_ls_init
-static int line_search(tob_ctx* c, int rb, int re, int wolfe_idx, bool coupled = false) {
-  const int n = re - rb;
+// ---- line search of robots [rb,re): s_step / trial tables / s_done prepared by k_ls_init -------------------------------
+// round r >= 1 evaluates trials 1..8 (round 0 also trial 0 = the current point, the "e" of the reference)
+static int ls_round(tob_ctx* c, int rb, int re, int wolfe_idx, bool coupled, int round, int slot) {
   cudaStream_t st = c->stream;
-  int* n_active = c->s_done.p + c->n_robots();
-  for (int round = 0; round < 400; round++) {
-    // round 0 also evaluates trial 0 = the current point (the "e" of the reference)
-    TOB_TRY(energy_trials(c, rb, re, c->s_dir.p, c->s_tstep.p, c->s_ttime.p, TOB_LS_TRIALS, round == 0 ? 0 : 1, TOB_LS_TRIALS,
-                          c->s_etr.p));
-    k_fill_int<<<1, 32, 0, st>>>(n_active, 1, 0);
-    TOB_LAUNCH_CHECK(c);
-    if (coupled)
-      k_armijo_coupled<<<1, 32, 0, st>>>(re - rb, c->s_etr.p, c->s_wolfe.p, c->s_ptime.p, c->s_tdir.p, c->s_step.p, c->s_ptrial.p,
-                                         c->s_tstep.p, c->s_ttime.p, c->s_done.p, n_active);
-    else
-      k_armijo<<<div_up(n, 64), 64, 0, st>>>(rb, re, c->s_etr.p, c->s_wolfe.p, wolfe_idx, c->s_ptime.p, c->s_tdir.p, c->s_step.p,
-                                            c->s_ptrial.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, n_active);
-    TOB_LAUNCH_CHECK(c);
-    TOB_TRY(read_back(c, n_active, sizeof(int)));
-    c->ctr.line_search_trials += (uint64_t)n * (TOB_LS_TRIALS - 1);
-    if (*((int*)c->h_pinned) == 0) break;
-  }
-  dim3 grid(div_up(3 * c->T, 128), n);
-  k_apply_step<<<grid, 128, 0, st>>>(rb, re, c->T, c->s_step.p, c->s_dir.p, c->s_ptrial.p, c->s_spline.p, c->s_ptime.p);
+  if (!coupled) return line_search_round(c, rb, re, wolfe_idx, round == 0 ? 0 : 1, slot);
+  TOB_TRY(energy_trials(c, rb, re, c->s_dir.p, c->s_tstep.p, c->s_ttime.p, TOB_LS_TRIALS, round == 0 ? 0 : 1, TOB_LS_TRIALS, c->s_etr.p));
+  k_armijo_coupled<<<1, 32, 0, st>>>(re - rb, c->s_etr.p, c->s_wolfe.p, c->s_ptime.p, c->s_tdir.p, c->s_step.p, c->s_ptrial.p,
+                                     c->s_tstep.p, c->s_ttime.p, c->s_done.p, &c->dc.p->ls_pending[slot]);
+  TOB_LAUNCH_CHECK(c);
+  c->ctr.line_search_trials += (uint64_t)(re - rb) * (TOB_LS_TRIALS - 1);
+  return 0;
+}
+
+static int apply_step(tob_ctx* c, int rb, int re, bool guarded) {
+  dim3 grid(div_up(3 * c->T, 128), re - rb);
+  k_apply_step<<<grid, 128, 0, c->stream>>>(rb, re, c->T, c->s_step.p, c->s_dir.p, c->s_ptrial.p, c->s_spline.p, c->s_ptime.p,
+                                            guarded ? c->dc.p : nullptr);
   TOB_LAUNCH_CHECK(c);
   return 0;
+}
+
+// the rounds launched ahead of the host (TOB_LS_ROUNDS x 8 ladder rungs)
+static int ls_launch_ahead(tob_ctx* c, int rb, int re, int wolfe_idx, bool coupled) {
+  for (int r = 0; r < TOB_LS_ROUNDS; r++) TOB_TRY(ls_round(c, rb, re, wolfe_idx, coupled, r, r));
+  return 0;
+}
+
+// host-driven continuation for the rare robot that needs more than TOB_LS_ROUNDS x 8 rungs; h_dc must be current
+static int ls_finish(tob_ctx* c, int rb, int re, int wolfe_idx, bool coupled) {
+  const int slot = TOB_LS_ROUNDS;   // scratch slot, re-zeroed before every extra round
+  int pending = c->h_dc->ls_pending[TOB_LS_ROUNDS - 1];
+  for (int round = TOB_LS_ROUNDS; pending > 0 && round < 60; round++) {
+    TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->ls_pending[slot], 0, sizeof(int), c->stream));
+    TOB_TRY(ls_round(c, rb, re, wolfe_idx, coupled, round, slot));
+    TOB_TRY(sync_counts(c));
+    pending = c->h_dc->ls_pending[slot];
+  }
+  TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->ls_pending[TOB_LS_ROUNDS - 1], 0, sizeof(int), c->stream));
+  return 0;
+}
+
+// complete line search with the step applied (function-level entry points)
+static int line_search(tob_ctx* c, int rb, int re, int wolfe_idx, bool coupled = false) {
+  TOB_TRY(ls_launch_ahead(c, rb, re, wolfe_idx, coupled));
+  TOB_TRY(sync_counts(c));
+  TOB_TRY(ls_finish(c, rb, re, wolfe_idx, coupled));
+  return apply_step(c, rb, re, false);
 }
 
 static int exchange(tob_ctx* c, DBuf<double>& buf, size_t elems_per_robot) {
@@ -270,15 +301,34 @@ static int exchange(tob_ctx* c, DBuf<double>& buf, size_t elems_per_robot) {
   return 0;
 }
 
-static int iterate_once(tob_ctx* c, int mode, double* gnorm_out) {
+// buffers of the whole iteration, sized from the parameters and the candidate capacity: nothing is allocated (and no size
+// is read back) between the first and the last kernel of an iteration
+static int ensure_iter_buffers(tob_ctx* c) {
+  const size_t rows = (size_t)c->rows_all(), U = (size_t)c->n_robots(), P = (size_t)c->prm.piece_num;
+  TOB_TRY(ensure_query_buffers(c));
+  TOB_CUDA(c, c->geo.P.ensure(18 * rows)); TOB_CUDA(c, c->geo.D.ensure(18 * rows)); TOB_CUDA(c, c->geo.box.ensure(6 * rows));
+  TOB_CUDA(c, c->geo.klo.ensure(TOB_KDOP_AXES * rows)); TOB_CUDA(c, c->geo.khi.ensure(TOB_KDOP_AXES * rows));
+  TOB_CUDA(c, c->row_e.ensure(2 * rows * TOB_LS_TRIALS)); TOB_CUDA(c, c->row_bad.ensure(rows * TOB_LS_TRIALS));
+  TOB_CUDA(c, c->pc_g.ensure(19 * U * P)); TOB_CUDA(c, c->pc_h.ensure(361 * U * P)); TOB_CUDA(c, c->pc_flag.ensure(U * P));
+  if (U > 1) {
+    const size_t n = (size_t)c->n_tr * (U * (U - 1) / 2);
+    TOB_CUDA(c, c->self_pl.ensure(4 * n + 4)); TOB_CUDA(c, c->self_ok.ensure(n + 1));
+    TOB_CUDA(c, c->self_hits.ensure(16384 + 2));
+  }
+  return 0;
+}
+
+// One ADMM iteration, launched without any host read-back.  `deferred`: the state-changing tail (apply step, slack /
+// dual update) is guarded on the device by dc->overflow / dc->ls_pending and the caller inspects dc afterwards;
+// otherwise (sharded multi-GPU: collectives in the middle must stay matched across ranks) the host checks as it goes.
+static int iterate_launch(tob_ctx* c, int mode, bool deferred) {
   const int U = c->n_robots(), rb = c->own_begin, re = c->own_end;
   cudaStream_t st = c->stream;
   const bool coupled = mode == 1;
-  if (mode != 0 && mode != 1) return fail_msg(c, "tob_admm_iterate: mode must be 0 (decoupled) or 1 (coupled)");
-  if (coupled && (c->ag || rb != 0 || re != U)) return fail_msg(c, "coupled mode is not sharded: run it on one context holding all robots");
   // (1) control points of every robot are needed for the inter-robot planes
   if (U > 1) TOB_TRY(exchange(c, c->s_spline, (size_t)3 * c->T));
-  TOB_TRY(separate_resident(c, rb, re, 1));
+  if (deferred) TOB_TRY(separate_resident(c, rb, re, 1));
+  else TOB_TRY(run_checked(c, [&]() { return separate_resident(c, rb, re, 1); }));
   // (2) Newton direction (geo.P of the owned rows is still current from the plane pass)
   TOB_TRY(gradient_blocks(c, rb, re, 1));
   if (coupled) TOB_TRY(solve_coupled(c));
@@ -293,29 +343,114 @@ static int iterate_once(tob_ctx* c, int mode, double* gnorm_out) {
   } else {
     TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, rb, re, 3));
   }
-  uint64_t total = 0;
-  TOB_TRY(broadphase(c, rb, re, c->prm.offset, &total));
-  k_fill_int<<<div_up(U, 64), 64, 0, st>>>(c->kmax.p, U, 0);
-  TOB_LAUNCH_CHECK(c);
-  TOB_TRY(ccd_position_steps(c));
+  TOB_TRY(ccd_position_steps(c, rb, re));
+  // (4) Armijo; multi-robot: every robot uses the LAST robot's wolfe (global overwritten, Optimization3D_multi.h:730,792)
+  int wolfe_idx = -1;
   if (coupled) {
     if (U == 1) { double one = 1.0; TOB_TRY(upload(c, c->s_selfstep, &one, 1)); }
     k_ls_init_coupled<<<1, 32, 0, st>>>(U, c->kmax.p, c->d_steps.p, c->s_selfstep.p, c->s_ptime.p, c->s_tdir.p, c->s_step.p,
-                                        c->s_tstep.p, c->s_ttime.p, c->s_done.p);
+                                        c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p);
     TOB_LAUNCH_CHECK(c);
-    TOB_TRY(line_search(c, rb, re, 0, true));
+    wolfe_idx = 0;
   } else {
     k_ls_init<<<div_up(re - rb, 64), 64, 0, st>>>(rb, re, c->kmax.p, c->d_steps.p, c->s_selfstep.p, U > 1 ? 1 : 0, c->s_ptime.p,
-                                                  c->s_tdir.p, c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p);
+                                                  c->s_tdir.p, c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p);
     TOB_LAUNCH_CHECK(c);
-    // (4) Armijo; multi-robot: every robot uses the LAST robot's wolfe (global overwritten, Optimization3D_multi.h:730,792)
-    TOB_TRY(line_search(c, rb, re, U > 1 ? U - 1 : -1));
+    wolfe_idx = U > 1 ? U - 1 : -1;
   }
-  // (5) slack + dual
-  TOB_TRY(slack_update(c, rb, re));
+  TOB_TRY(ls_launch_ahead(c, rb, re, wolfe_idx, coupled));
+  if (!deferred) {
+    TOB_TRY(sync_counts(c));
+    TOB_TRY(ls_finish(c, rb, re, wolfe_idx, coupled));
+  }
+  // (5) step, slack + dual
+  TOB_TRY(apply_step(c, rb, re, deferred));
+  TOB_TRY(slack_update(c, rb, re, deferred ? 1 : 0));
+  return 0;
+}
+
+static void graph_drop(tob_ctx* c) {
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  c->graph_exec = nullptr;
+  c->graph_mode = -1;
+}
+
+// Launch one deferred iteration: through the captured CUDA graph when the buffers have not moved since the capture.
+static int iterate_submit(tob_ctx* c, int mode) {
+  const bool can_graph = c->use_graph && !c->prof_on && !c->ag && mode == 0;
+  if (!can_graph) return iterate_launch(c, mode, true);
+  if (c->graph_exec && (c->graph_gen != alloc_generation() || c->graph_mode != mode)) graph_drop(c);
+  if (!c->graph_exec) {
+    // capture only a launch sequence that a plain run has already executed without allocating
+    const unsigned long long gen0 = alloc_generation();
+    TOB_TRY(ensure_iter_buffers(c));
+    if (gen0 != alloc_generation() || c->graph_warm_gen != gen0) {
+      c->graph_warm_gen = alloc_generation();
+      TOB_TRY(iterate_launch(c, mode, true));
+      if (c->graph_warm_gen != alloc_generation()) c->graph_warm_gen = ~0ull;   // allocated on the way: warm up again
+      return 0;
+    }
+    cudaGraph_t g = nullptr;
+    const uint64_t l0 = c->ctr.kernel_launches;
+    TOB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    c->capturing = true;
+    int rc = iterate_launch(c, mode, true);
+    c->capturing = false;
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    c->graph_nodes = c->ctr.kernel_launches - l0;
+    c->ctr.kernel_launches = l0;
+    if (rc || e != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      c->use_graph = false;                      // fall back to plain stream launches for good
+      return iterate_launch(c, mode, true);
+    }
+    e = cudaGraphInstantiate(&c->graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { c->graph_exec = nullptr; c->use_graph = false; cudaGetLastError(); return iterate_launch(c, mode, true); }
+    c->graph_gen = alloc_generation();
+    c->graph_mode = mode;
+  }
+  TOB_CUDA(c, cudaGraphLaunch(c->graph_exec, c->stream));
+  c->ctr.kernel_launches += c->graph_nodes;
+  c->ctr.line_search_trials += (uint64_t)(c->own_end - c->own_begin) * (TOB_LS_TRIALS - 1) * TOB_LS_ROUNDS;
+  if (c->n_robots() > 1) c->ctr.self_pairs += (uint64_t)2 * c->n_tr * (c->n_robots() * (c->n_robots() - 1) / 2);
+  return 0;
+}
+
+static int iterate_once(tob_ctx* c, int mode, double* gnorm_out) {
+  const int U = c->n_robots(), rb = c->own_begin, re = c->own_end;
+  const bool coupled = mode == 1;
+  if (mode != 0 && mode != 1) return fail_msg(c, "tob_admm_iterate: mode must be 0 (decoupled) or 1 (coupled)");
+  if (coupled && (c->ag || rb != 0 || re != U)) return fail_msg(c, "coupled mode is not sharded: run it on one context holding all robots");
+  TOB_TRY(ensure_iter_buffers(c));
+  const int wolfe_idx = coupled ? 0 : (U > 1 ? U - 1 : -1);
+  if (c->ag) {
+    TOB_TRY(iterate_launch(c, mode, false));
+  } else {
+    for (int attempt = 0;; attempt++) {
+      const uint32_t done0 = c->h_dc->iters_done;
+      TOB_TRY(iterate_submit(c, mode));
+      TOB_CUDA(c, cudaMemcpyAsync(c->h_pinned, c->s_gnorm.p, U * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      TOB_TRY(sync_counts(c));
+      if (c->h_dc->iters_done != done0) break;                 // committed on the device
+      if (c->h_dc->overflow & TOB_OVF_SELFHITS) return fail_msg(c, "inter-robot CCD: more than 16384 colliding pairs");
+      if (c->h_dc->overflow & TOB_OVF_CAND) {                  // nothing was changed: grow and run the iteration again
+        if (attempt >= 8) return fail_msg(c, "candidate buffers keep overflowing");
+        TOB_TRY(clear_overflow(c));
+        TOB_TRY(grow_cand_capacity(c, c->h_dc->n_cand));
+        continue;
+      }
+      // a robot needs more than the rungs launched ahead: finish its search from the host, then commit
+      TOB_TRY(ls_finish(c, rb, re, wolfe_idx, coupled));
+      TOB_TRY(apply_step(c, rb, re, false));
+      TOB_TRY(slack_update(c, rb, re, 0));
+      break;
+    }
+  }
   // gnorm global of the reference
   if (gnorm_out) {
-    TOB_TRY(read_back(c, c->s_gnorm.p, U * sizeof(double)));
+    if (c->ag) TOB_TRY(read_back(c, c->s_gnorm.p, U * sizeof(double)));
     double g = 0;
     const double* hp = c->h_pinned;
     if (U == 1) g = hp[0];
@@ -347,6 +482,12 @@ int tob_ctx_create(int device, tob_ctx** out) {
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return fail(nullptr, "cudaStreamCreate", e, __FILE__, __LINE__); }
   if ((e = cudaMallocHost((void**)&c->h_pinned, 65536)) != cudaSuccess) { delete c; return fail(nullptr, "cudaMallocHost", e, __FILE__, __LINE__); }
   if ((e = c->red.ensure(4096)) != cudaSuccess) { delete c; return fail(nullptr, "cudaMalloc", e, __FILE__, __LINE__); }
+  if ((e = cudaMallocHost((void**)&c->h_dc, sizeof(DevCounts))) != cudaSuccess) { delete c; return fail(nullptr, "cudaMallocHost", e, __FILE__, __LINE__); }
+  memset(c->h_dc, 0, sizeof(DevCounts));
+  if ((e = cudaMalloc((void**)&c->dc.p, sizeof(DevCounts))) != cudaSuccess) { delete c; return fail(nullptr, "cudaMalloc", e, __FILE__, __LINE__); }
+  c->dc.cap = 1;
+  cudaMemset(c->dc.p, 0, sizeof(DevCounts));
+  if (const char* g = getenv("TRAJOPT_B200_NO_GRAPH")) c->use_graph = !(g[0] && g[0] != '0');
   std::vector<double> steps(TOB_LADDER + 2);
   double s = 1.0;
   for (int k = 0; k < TOB_LADDER + 2; k++) { steps[k] = s; s *= 0.8; }
@@ -364,6 +505,9 @@ void tob_ctx_destroy(tob_ctx* c) {
   c->px.release(); c->py.release(); c->pz.release(); c->pid.release(); c->lvl_store.release();
   c->cand_pt.release(); c->cand_row.release(); c->cpl.release(); c->pl.release(); c->task_cnt.release(); c->task_off.release();
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->h_dc) cudaFreeHost(c->h_dc);
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  c->dc.release();
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -446,7 +590,7 @@ uint32_t tob_cloud_size(const tob_ctx* c) { return c ? c->n_pts : 0; }
 // ---- broadphase --------------------------------------------------------------------------------------------------
 static int bp_download(tob_ctx* c, int n_robots, uint32_t* offsets, uint32_t* ids, uint64_t cap, uint64_t* total) {
   const int rows = n_robots * c->n_tr;
-  uint64_t nc = c->n_cand;
+  uint64_t nc = c->n_cand;   // host mirror: the caller went through run_checked()
   if (total) *total = nc;
   std::vector<uint32_t> off(c->rows_all() + 1);
   TOB_CUDA(c, cudaMemcpyAsync(off.data(), c->row_off.p, off.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -474,8 +618,7 @@ int tob_broadphase_dcd(tob_ctx* c, const double* splines, int n_robots, double d
   cudaSetDevice(c->device);
   TOB_TRY(stage_splines(c, splines, nullptr, n_robots));
   TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, 0, n_robots, 0));
-  uint64_t t = 0;
-  TOB_TRY(broadphase(c, 0, n_robots, d, &t));
+  TOB_TRY(run_checked(c, [&]() { return broadphase(c, 0, n_robots, d, 0); }));
   return bp_download(c, n_robots, offsets, ids, cap, total);
 }
 
@@ -485,8 +628,7 @@ int tob_broadphase_ccd(tob_ctx* c, const double* splines, const double* directio
   cudaSetDevice(c->device);
   TOB_TRY(stage_splines(c, splines, directions, n_robots));
   TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, 0, n_robots, 2));
-  uint64_t t = 0;
-  TOB_TRY(broadphase(c, 0, n_robots, d, &t));
+  TOB_TRY(run_checked(c, [&]() { return broadphase(c, 0, n_robots, d, 0); }));
   return bp_download(c, n_robots, offsets, ids, cap, total);
 }
 
@@ -497,8 +639,8 @@ int tob_box_query(tob_ctx* c, const double* lo, const double* hi, double d, uint
   double b[6] = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
   TOB_TRY(upload(c, c->geo.box, b, 6));
   c->states_valid = false;
-  uint64_t t = 0;
-  TOB_TRY(broadphase_rows(c, 0, 1, d, &t));
+  TOB_TRY(run_checked(c, [&]() { return broadphase_rows(c, 0, 1, d, 0); }));
+  uint64_t t = c->n_cand;
   if (total) *total = t;
   if (!ids || t > cap || t == 0) return 0;
   std::vector<uint32_t> pts(t);
@@ -689,6 +831,7 @@ int tob_separate_self(tob_ctx* c, const double* splines, int n_robots, uint32_t*
   TOB_TRY(stage_splines(c, splines, nullptr, n_robots));
   TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, 0, n_robots, 1));
   TOB_TRY(pack_self_only(c));
+  TOB_TRY(sync_counts(c));
   uint64_t np = c->n_planes;
   if (total) *total = np;
   const int rows = c->rows_all();
@@ -710,7 +853,7 @@ int tob_separate_planes(tob_ctx* c, const double* splines, int n_robots, int wit
   cudaSetDevice(c->device);
   if (with_self && n_robots != c->n_robots()) return fail_msg(c, "with_self needs all uav_num robots");
   TOB_TRY(stage_splines(c, splines, nullptr, n_robots));
-  TOB_TRY(separate_resident(c, 0, n_robots, with_self));
+  TOB_TRY(run_checked(c, [&]() { return separate_resident(c, 0, n_robots, with_self); }));
   uint64_t np = c->n_planes;
   if (total) *total = np;
   const int rows = n_robots * c->n_tr;
@@ -858,12 +1001,8 @@ int tob_position_step(tob_ctx* c, const double* spline, const double* direction,
   TOB_TRY(need(c, true, true));
   cudaSetDevice(c->device);
   TOB_TRY(stage_splines(c, spline, direction, 1));
-  TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, 0, 1, 3));
-  uint64_t total = 0;
-  TOB_TRY(broadphase(c, 0, 1, c->prm.offset, &total));
-  k_fill_int<<<1, 64, 0, c->stream>>>(c->kmax.p, c->n_robots(), 0);
-  TOB_LAUNCH_CHECK(c);
-  TOB_TRY(ccd_position_steps(c));
+  TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, 0, 1, 3));   // also resets kmax[0]
+  TOB_TRY(ccd_position_steps(c, 0, 1));
   TOB_TRY(read_back(c, c->kmax.p, sizeof(int)));
   int k = *((int*)c->h_pinned);
   double s = 1.0;
@@ -928,16 +1067,14 @@ int tob_line_search(tob_ctx* c, int robot, tob_state* st, const double* directio
   if (*step_io < 0) {           // Optimization3D_admm::spline_line_search: the bound is Step::position_step
     if (c->n_pts == 0) return fail_msg(c, "tob_line_search: no point cloud");
     TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, robot, robot + 1, 3));
-    uint64_t total = 0;
-    TOB_TRY(broadphase(c, robot, robot + 1, c->prm.offset, &total));
-    TOB_TRY(ccd_position_steps(c));
+    TOB_TRY(ccd_position_steps(c, robot, robot + 1));
   } else {                      // Optimization3D_multi::spline_line_search: the caller's bound (<= 1)
     if (*step_io > 1.0) return fail_msg(c, "tob_line_search: a caller-provided step bound must be <= 1");
     TOB_TRY(upload(c, c->s_selfstep, step_io, 1, robot));
     use_self = 1;
   }
   k_ls_init<<<1, 64, 0, c->stream>>>(robot, robot + 1, c->kmax.p, c->d_steps.p, c->s_selfstep.p, use_self, c->s_ptime.p, c->s_tdir.p,
-                                     c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p);
+                                     c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p);
   TOB_LAUNCH_CHECK(c);
   TOB_TRY(line_search(c, robot, robot + 1, -1));
   TOB_CUDA(c, cudaMemcpyAsync(st->spline, c->s_spline.p + (size_t)robot * 3 * T, 3 * T * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1085,6 +1222,7 @@ int tob_admm_iterate(tob_ctx* c, int iters, int mode, double* gnorm) {
   TOB_TRY(need(c, true, true));
   cudaSetDevice(c->device);
   if (!c->states_valid) return fail_msg(c, "tob_admm_iterate: call tob_states_upload first");
+  TOB_TRY(clear_overflow(c));
   for (int i = 0; i < iters; i++) TOB_TRY(iterate_once(c, mode, (i == iters - 1) ? gnorm : nullptr));
   TOB_CUDA(c, cudaStreamSynchronize(c->stream));
   return 0;
@@ -1096,20 +1234,30 @@ int tob_optimization(tob_ctx* c, tob_state* states, int n_robots, int mode, doub
   return tob_states_download(c, states, n_robots);
 }
 
-int tob_get_counters(const tob_ctx* c, tob_counters* out) {
-  if (!c || !out) return 1;
+int tob_get_counters(const tob_ctx* cc, tob_counters* out) {
+  if (!cc || !out) return 1;
+  tob_ctx* c = const_cast<tob_ctx*>(cc);
+  cudaSetDevice(c->device);
+  TOB_TRY(sync_counts(c));     // the pair counters are accumulated on the device
   *out = c->ctr;
+  out->dcd_candidates = c->h_dc->dcd_candidates;
+  out->planes = c->h_dc->planes;
+  out->ccd_candidates = c->h_dc->ccd_candidates;
+  out->energy_plane_evals = c->h_dc->energy_plane_evals;
+  out->barrier_terms = c->h_dc->barrier_terms;
   return 0;
 }
 int tob_reset_counters(tob_ctx* c) {
   if (!c) return 1;
+  cudaSetDevice(c->device);
   memset(&c->ctr, 0, sizeof(c->ctr));
+  TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->dcd_candidates, 0, 5 * sizeof(unsigned long long), c->stream));
   return 0;
 }
 
-static const char* kKernelNames[K_COUNT] = {"k_rows", "k_broadphase<count>", "k_broadphase<fill>", "k_scan(3)", "k_narrow",
-                                            "k_pack_obstacle", "k_self_planes", "k_row_energy", "k_robot_energy", "k_row_grad",
-                                            "k_piece", "k_solve", "k_ccd", "k_self_ccd_filter", "k_slack", "misc"};
+static const char* kKernelNames[K_COUNT] = {"k_rows", "k_bp_count", "k_bp_fill", "k_bp_top+k_np_top", "k_narrow",
+                                            "k_pack", "k_self_planes", "k_row_energy", "k_robot_ls", "k_row_grad",
+                                            "k_piece", "k_solve_bcr", "k_bp_ccd", "k_self_ccd_filter", "k_slack", "misc"};
 
 int tob_profile_enable(tob_ctx* c, int on) {
   if (!c) return 1;

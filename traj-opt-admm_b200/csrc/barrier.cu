@@ -41,58 +41,67 @@ struct EnergyArgs {
   const uint32_t* pl_off;       // rows+1
   const double* weight;         // n_tr
   double margin, vel_limit, acc_limit;
-  int n_tr, res, T, row_begin, rows_all, KT, k0;
+  int n_tr, res, T, row_begin, rows_all, KT, k0, nk;
   double* row_e;                // KT x rows_all x 2 : plane barrier, bound
   int* row_bad;                 // KT x rows_all
+  const int* done;              // per robot, may be null: robots whose line search has finished are skipped
+  DevCounts* dc;                // barrier_terms counter
 };
 
-__global__ void __launch_bounds__(128) k_row_energy(EnergyArgs a) {
-  const int row = a.row_begin + blockIdx.x, k = a.k0 + blockIdx.y;
+// One CTA per row, one WARP per trial point of the launch (blockDim = 32 * nk): the warps of a CTA stream the same planes
+// (L1 hits after the first warp), every warp keeps its own trial's control points in shared memory and reduces with
+// shuffles only -- no block-wide barrier, and the (row, trial) work items of a small problem still spread over
+// rows x nk warps.
+#define EN_MAXT TOB_LS_TRIALS
+__global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
+  const int row = a.row_begin + blockIdx.x;
   const int robot = row / a.n_tr, tr = row - robot * a.n_tr;
-  __shared__ double sP[18], sBz[18];
-  __shared__ double s_part[4];
-  __shared__ int s_bad;
-  if (threadIdx.x < 18) {
-    const int mm = threadIdx.x % 6, ax = threadIdx.x / 6;
+  const int lane = threadIdx.x & 31, kk = threadIdx.x >> 5, k = a.k0 + kk;
+  __shared__ double sPall[EN_MAXT][18], sBzall[EN_MAXT][18];
+  if (a.done && a.done[robot]) return;
+  double* sP = sPall[kk];
+  double* sBz = sBzall[kk];
+  if (lane < 18) {
+    const int mm = lane % 6, ax = lane / 6;
     const size_t g = (size_t)robot * 3 * a.T + (size_t)ax * a.T + 3 * (tr / a.res) + mm;
     double v = a.spline[g];
     if (a.dir && a.tstep) v = __dadd_rn(v, __dmul_rn(a.tstep[robot * a.KT + k], a.dir[g]));
-    sBz[threadIdx.x] = v;
+    sBz[lane] = v;
   }
-  if (threadIdx.x == 0) s_bad = 0;
-  __syncthreads();
-  if (threadIdx.x < 18) {
-    const int j = threadIdx.x % 6, ax = threadIdx.x / 6;
+  __syncwarp();
+  if (lane < 18) {
+    const int j = lane % 6, ax = lane / 6;
     const double* B = a.basis + (size_t)36 * tr;
     double acc = 0;
     for (int q = 0; q < 6; q++) acc = __dadd_rn(acc, __dmul_rn(B[j + 6 * q], sBz[q + 6 * ax]));
-    sP[threadIdx.x] = acc;
+    sP[lane] = acc;
   }
-  __syncthreads();
+  __syncwarp();
   const double w = a.weight[tr], m = a.margin;
   double e = 0;
   int bad = 0;
+  unsigned n_act = 0;
   const uint32_t p0 = a.pl_off[row], p1 = a.pl_off[row + 1];
-  for (uint32_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+  for (uint32_t p = p0 + lane; p < p1; p += 32) {
     const double4 pl = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * p);
 #pragma unroll
     for (int j = 0; j < 6; j++) {
       double d = sP[j] * pl.x + sP[j + 6] * pl.y + sP[j + 12] * pl.z + pl.w;
       if (d <= 0) bad = 1;
-      else if (d < m) e += -w * (d - m) * (d - m) * log(d / m);
+      else if (d < m) { e += -w * (d - m) * (d - m) * log(d / m); n_act++; }
     }
   }
-  // bound terms: threads 0..4 velocity, 5..8 acceleration
+  // bound terms: lanes 0..4 velocity, 5..8 acceleration
   double eb = 0;
-  if (threadIdx.x < 9) {
+  if (lane < 9) {
     const double t = a.ttime[robot * a.KT + k];
     double d;
-    if (threadIdx.x < 5) {
-      int j = threadIdx.x;
+    if (lane < 5) {
+      int j = lane;
       double vx = 5 * (sP[j + 1] - sP[j]), vy = 5 * (sP[j + 7] - sP[j + 6]), vz = 5 * (sP[j + 13] - sP[j + 12]);
       d = a.vel_limit - sqrt(vx * vx + vy * vy + vz * vz) / (w * t);
     } else {
-      int j = threadIdx.x - 5;
+      int j = lane - 5;
       double ax = 20 * (sP[j + 2] - 2 * sP[j + 1] + sP[j]), ay = 20 * (sP[j + 8] - 2 * sP[j + 7] + sP[j + 6]),
              az = 20 * (sP[j + 14] - 2 * sP[j + 13] + sP[j + 12]);
       d = a.acc_limit - sqrt(ax * ax + ay * ay + az * az) / (w * w * t * t);
@@ -102,15 +111,14 @@ __global__ void __launch_bounds__(128) k_row_energy(EnergyArgs a) {
   }
   e = warp_sum(e);
   eb = warp_sum(eb);
-  if (bad) atomicOr(&s_bad, 1);
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  if (lane == 0) s_part[wp] = e;
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  bad = __any_sync(0xffffffffu, bad);
+  for (int o = 16; o; o >>= 1) n_act += __shfl_xor_sync(0xffffffffu, n_act, o);
+  if (lane == 0) {
     const size_t o = (size_t)k * a.rows_all + row;
-    a.row_e[2 * o] = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
+    a.row_e[2 * o] = e;
     a.row_e[2 * o + 1] = eb;
-    a.row_bad[o] = s_bad;
+    a.row_bad[o] = bad;
+    if (n_act) atomicAdd(&a.dc->barrier_terms, (unsigned long long)n_act);
   }
 }
 
@@ -172,6 +180,85 @@ __global__ void __launch_bounds__(128) k_robot_energy(RobotEnergyArgs a) {
   }
 }
 
+// Decoupled line search, one CTA per robot: the robot sums of k_robot_energy for trials k0..KT-1 (same summation
+// order), then thread 0 takes the Armijo decision in ladder order exactly like the reference's
+//   while(e - 1e-4*wolfe*step < E(x + step*dir)) step *= 0.8     (Optimization3D_admm.h:537-544)
+// : the first rung that fails the while-condition is accepted; if all fail, the next 8 rungs are laid out and the
+// robot is counted in dc->ls_pending[slot].  wolfe_idx < 0: own wolfe, else the reference's "last robot" quirk
+// (Optimization3D_multi.h:730,792).
+struct RobotLsArgs {
+  RobotEnergyArgs e;
+  const double *wolfe, *ptime, *tdir;
+  double *step, *ptrial, *tstep, *ttime;
+  int* done;
+  int wolfe_idx, slot;
+  DevCounts* dc;
+};
+
+__global__ void __launch_bounds__(32 * TOB_LS_TRIALS) k_robot_ls(RobotLsArgs b) {
+  const RobotEnergyArgs& a = b.e;
+  const int robot = a.robot_begin + blockIdx.x;
+  if (b.done[robot]) return;
+  const int lane = threadIdx.x & 31, k = a.k0 + (threadIdx.x >> 5);   // one warp per trial point
+  if (k < a.KT) {
+    double e = 0;
+    int bad = 0;
+    for (int tr = lane; tr < a.n_tr; tr += 32) {
+      size_t o = (size_t)k * a.rows_all + (size_t)robot * a.n_tr + tr;
+      e += a.lambda * a.row_e[2 * o] + a.lambda * a.row_e[2 * o + 1];
+      bad |= a.row_bad[o];
+    }
+    const double t = a.ttime[robot * a.KT + k];
+    const double st = (a.dir && a.tstep) ? a.tstep[robot * a.KT + k] : 0.0;
+    for (int sp = lane; sp < a.P; sp += 32) {
+      const double* C = a.convert + (size_t)36 * sp;
+      double acc = 0;
+      for (int ax = 0; ax < 3; ax++) {
+        double bz[6];
+        for (int q = 0; q < 6; q++) {
+          size_t g = (size_t)robot * 3 * a.T + (size_t)ax * a.T + 3 * sp + q;
+          bz[q] = a.dir ? __dadd_rn(a.spline[g], __dmul_rn(st, a.dir[g])) : a.spline[g];
+        }
+        for (int r = 0; r < 6; r++) {
+          double cx = 0;
+          for (int q = 0; q < 6; q++) cx += C[r + 6 * q] * bz[q];
+          size_t s = (size_t)robot * 18 * a.P + (size_t)ax * 6 * a.P + 6 * sp + r;
+          double pd = cx - a.pslack[s];
+          acc += a.mu / 2.0 * pd * pd + a.plambda[s] * pd;
+        }
+      }
+      double dt = t - a.tslack[(size_t)robot * a.P + sp];
+      acc += a.mu / 2.0 * dt * dt + a.tlambda[(size_t)robot * a.P + sp] * dt;
+      e += acc;
+    }
+    e = warp_sum(e);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) a.e_out[robot * a.KT + k] = bad ? INFINITY : e;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const int KT = a.KT, u = robot;
+  if (blockIdx.x == 0) b.dc->energy_plane_evals += (unsigned long long)b.dc->n_planes * (unsigned)(KT - a.k0);
+  const double w = b.wolfe[b.wolfe_idx < 0 ? u : b.wolfe_idx];
+  const double e0 = a.e_out[u * KT];
+  for (int k = 1; k < KT; k++) {
+    const double s = b.tstep[u * KT + k];
+    if (!(e0 - 1e-4 * w * s < a.e_out[u * KT + k])) {
+      b.step[u] = s;
+      b.ptrial[u] = b.ttime[u * KT + k];
+      b.done[u] = 1;
+      return;
+    }
+  }
+  double s = b.tstep[u * KT + KT - 1] * 0.8;
+  for (int k = 1; k < KT; k++) {
+    b.tstep[u * KT + k] = s;
+    b.ttime[u * KT + k] = b.ptime[u] + s * b.tdir[u];
+    s *= 0.8;
+  }
+  atomicAdd(&b.dc->ls_pending[b.slot], 1);
+}
+
 // Energies of trial points k0..k1-1 of robots [rb,re): trial spline = s_spline + tstep[u*KT+k]*dir, time ttime[u*KT+k].
 // dir/tstep may be null (current point).  e_dev: robots x KT.
 int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* tstep, const double* ttime, int KT, int k0,
@@ -184,11 +271,13 @@ int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* t
   a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p;
   a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
   a.n_tr = c->n_tr; a.res = c->prm.res; a.T = c->T; a.row_begin = rb * c->n_tr; a.rows_all = rows_all; a.KT = KT; a.k0 = k0;
-  a.row_e = c->row_e.p; a.row_bad = c->row_bad.p;
+  a.row_e = c->row_e.p; a.row_bad = c->row_bad.p; a.done = nullptr; a.dc = c->dc.p;
   const int nrows = (re - rb) * c->n_tr, nk = k1 - k0;
   {
     Prof prof(c, K_ROW_ENERGY);
-    k_row_energy<<<dim3(nrows, nk), 128, 0, c->stream>>>(a);
+    a.nk = nk;
+    if (nk > EN_MAXT) return fail_msg(c, "energy_trials: too many trial points in one launch");
+    k_row_energy<<<nrows, 32 * nk, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
   RobotEnergyArgs b;
@@ -202,7 +291,38 @@ int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* t
     k_robot_energy<<<dim3(re - rb, nk), 128, 0, c->stream>>>(b);
     TOB_LAUNCH_CHECK(c);
   }
-  c->ctr.energy_plane_evals += c->n_planes * (uint64_t)nk;
+  return 0;
+}
+
+int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int slot) {
+  const int rows_all = c->rows_all(), KT = TOB_LS_TRIALS;
+  EnergyArgs a;
+  a.spline = c->s_spline.p; a.dir = c->s_dir.p; a.tstep = c->s_tstep.p; a.ttime = c->s_ttime.p; a.basis = c->d_basis.p;
+  a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p;
+  a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
+  a.n_tr = c->n_tr; a.res = c->prm.res; a.T = c->T; a.row_begin = rb * c->n_tr; a.rows_all = rows_all; a.KT = KT; a.k0 = k0;
+  a.row_e = c->row_e.p; a.row_bad = c->row_bad.p; a.done = c->s_done.p; a.dc = c->dc.p;
+  {
+    Prof prof(c, K_ROW_ENERGY);
+    a.nk = KT - k0;
+    k_row_energy<<<(re - rb) * c->n_tr, 32 * (KT - k0), 0, c->stream>>>(a);
+    TOB_LAUNCH_CHECK(c);
+  }
+  RobotLsArgs b;
+  b.e.spline = c->s_spline.p; b.e.dir = c->s_dir.p; b.e.tstep = c->s_tstep.p; b.e.ttime = c->s_ttime.p;
+  b.e.pslack = c->s_pslack.p; b.e.tslack = c->s_tslack.p; b.e.plambda = c->s_plambda.p; b.e.tlambda = c->s_tlambda.p;
+  b.e.convert = c->d_convert.p; b.e.row_e = c->row_e.p; b.e.row_bad = c->row_bad.p;
+  b.e.lambda = c->prm.lambda; b.e.mu = c->prm.mu; b.e.n_tr = c->n_tr; b.e.P = c->prm.piece_num; b.e.T = c->T; b.e.robot_begin = rb;
+  b.e.rows_all = rows_all; b.e.KT = KT; b.e.k0 = k0; b.e.e_out = c->s_etr.p;
+  b.wolfe = c->s_wolfe.p; b.ptime = c->s_ptime.p; b.tdir = c->s_tdir.p;
+  b.step = c->s_step.p; b.ptrial = c->s_ptrial.p; b.tstep = c->s_tstep.p; b.ttime = c->s_ttime.p; b.done = c->s_done.p;
+  b.wolfe_idx = wolfe_idx; b.slot = slot; b.dc = c->dc.p;
+  {
+    Prof prof(c, K_ROBOT_ENERGY);
+    k_robot_ls<<<re - rb, 32 * TOB_LS_TRIALS, 0, c->stream>>>(b);
+    TOB_LAUNCH_CHECK(c);
+  }
+  c->ctr.line_search_trials += (uint64_t)(re - rb) * (KT - 1);
   return 0;
 }
 
@@ -216,6 +336,7 @@ struct RowGradArgs {
   double margin, vel_limit, acc_limit;
   int n_tr, row_begin;
   double* terms;           // rows x ROW_REC
+  DevCounts* dc;           // barrier_terms counter
 };
 
 __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
@@ -228,6 +349,7 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
   __syncthreads();
   const double w = a.weight[tr], m = a.margin;
   double acc[54];
+  unsigned n_act = 0;
 #pragma unroll
   for (int i = 0; i < 54; i++) acc[i] = 0;
   const uint32_t k0 = a.pl_off[row], k1 = a.pl_off[row + 1];
@@ -238,6 +360,7 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
     for (int j = 0; j < 6; j++) {
       double d = sP[j] * pl.x + sP[j + 6] * pl.y + sP[j + 12] * pl.z + pl.w;
       if (d < m) {
+        n_act++;
         double lg = log(d / m), dm = d - m, id = 1.0 / d;
         double e1 = -w * (2 * dm * lg + dm * dm * id);
         double e2 = -w * (2 * lg + 4 * dm * id - dm * dm * id * id);
@@ -248,10 +371,16 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
     }
   }
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  for (int o = 16; o; o >>= 1) n_act += __shfl_xor_sync(0xffffffffu, n_act, o);
+  if (lane == 0 && n_act) atomicAdd(&a.dc->barrier_terms, (unsigned long long)n_act);
+  if (k0 + 32u * wp < k1) {            // this warp streamed at least one plane (warp-uniform)
 #pragma unroll
-  for (int i = 0; i < 54; i++) {
-    double v = warp_sum(acc[i]);
-    if (lane == 0) s_red[wp][i] = v;
+    for (int i = 0; i < 54; i++) {
+      double v = warp_sum(acc[i]);
+      if (lane == 0) s_red[wp][i] = v;
+    }
+  } else {
+    for (int i = lane; i < 54; i += 32) s_red[wp][i] = 0.0;
   }
   // bound terms, threads 0..8
   double* out = a.terms + (size_t)ROW_REC * row;
@@ -331,6 +460,7 @@ struct PieceArgs {
   int n_tr, res, P, T, robot_begin, project_psd;
   double *pc_g, *pc_h;   // (robots*P) x 19 / x 361 (col-major)
   int* pc_flag;          // 0 SPD, 1 shifted, 2 LLT failed but lambda_min >= 0
+  DevCounts* dc;         // planes x gradient passes counter
 };
 
 __global__ void __launch_bounds__(384) k_piece(PieceArgs a) {
@@ -376,6 +506,7 @@ __global__ void __launch_bounds__(384) k_piece(PieceArgs a) {
     }
     s_x[threadIdx.x] = acc;
   }
+  if (blockIdx.x == 0 && threadIdx.x == 37) a.dc->energy_plane_evals += a.dc->n_planes;
   if (threadIdx.x == 36) {
     double g = 0, h = 0;
     for (int rr = 0; rr < a.res; rr++) {
@@ -427,22 +558,24 @@ __global__ void __launch_bounds__(384) k_piece(PieceArgs a) {
     G[r] = v;
   }
   __syncthreads();
-  // PSD projection of Gradient_admm.h:40-53 by warp 0: Cholesky test, then h0 += (-lambda_min + 0.01) I if needed
+  // PSD projection of Gradient_admm.h:40-53 by warp 0 (rows in registers, shuffles): Cholesky test, then
+  // h0 += (-lambda_min + 0.01) I if needed
   if (a.project_psd && threadIdx.x < 32) {
-    for (int i = threadIdx.x; i < 361; i += 32) s_L[i] = s_H[i];
-    __syncwarp();
+    const int lane = threadIdx.x;
+    double r[19];
+#pragma unroll
+    for (int j = 0; j < 19; j++) r[j] = lane < 19 ? s_H[lane + 19 * j] : 0.0;
     int flag = 0;
-    if (!warp_chol_is_spd(s_L, 19)) {
-      for (int i = threadIdx.x; i < 361; i += 32) s_L[i] = s_H[i];
-      __syncwarp();
-      double mn = warp_min_eig(s_L, 19, s_x, s_x + 19, s_a, s_a + 19);   // s_x / s_a are free by now (>= 38 doubles each)
-      __syncwarp();
+    if (!warp_chol_roll<19>(r, nullptr)) {
+#pragma unroll
+      for (int j = 0; j < 19; j++) r[j] = lane < 19 ? s_H[lane + 19 * j] : 0.0;
+      const double mn = warp_min_eig_roll<19>(r, s_a, s_a + 19);   // s_a is free by now (>= 38 doubles)
       if (mn < 0) {
-        if (threadIdx.x < 19) s_H[threadIdx.x * 20] = s_H[threadIdx.x * 20] - mn * 1.0 + 0.01 * 1.0;
+        if (lane < 19) s_H[lane * 20] = s_H[lane * 20] - mn * 1.0 + 0.01 * 1.0;
         flag = 1;
       } else flag = 2;
     }
-    if (threadIdx.x == 0) a.pc_flag[pb] = flag;
+    if (lane == 0) a.pc_flag[pb] = flag;
   }
   __syncthreads();
   for (int e = threadIdx.x; e < 361; e += blockDim.x) a.pc_h[361 * pb + e] = s_H[e];
@@ -490,7 +623,7 @@ int row_blocks(tob_ctx* c, int tr, int which, double* out_dev) {
   RowGradArgs a;
   a.P = c->geo.P.p; a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p; a.ptime = c->s_ptime.p;
   a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
-  a.n_tr = c->n_tr; a.row_begin = tr; a.terms = c->row_terms.p;
+  a.n_tr = c->n_tr; a.row_begin = tr; a.terms = c->row_terms.p; a.dc = c->dc.p;
   k_row_grad<<<1, 128, 0, c->stream>>>(a);
   TOB_LAUNCH_CHECK(c);
   k_row_expand<<<1, 128, 0, c->stream>>>(c->row_terms.p + (size_t)ROW_REC * tr, c->d_basis.p + (size_t)36 * tr, which, out_dev);
@@ -509,7 +642,7 @@ int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd) {
   RowGradArgs a;
   a.P = c->geo.P.p; a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p; a.ptime = c->s_ptime.p;
   a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
-  a.n_tr = c->n_tr; a.row_begin = rb * c->n_tr; a.terms = c->row_terms.p;
+  a.n_tr = c->n_tr; a.row_begin = rb * c->n_tr; a.terms = c->row_terms.p; a.dc = c->dc.p;
   {
     Prof prof(c, K_ROW_GRAD);
     k_row_grad<<<(re - rb) * c->n_tr, 128, 0, c->stream>>>(a);
@@ -521,14 +654,13 @@ int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd) {
   b.plambda = c->s_plambda.p; b.tlambda = c->s_tlambda.p;
   b.lambda = c->prm.lambda; b.mu = c->prm.mu; b.n_tr = c->n_tr; b.res = c->prm.res; b.P = P; b.T = c->T;
   b.robot_begin = rb; b.project_psd = project_psd;
-  b.pc_g = c->pc_g.p; b.pc_h = c->pc_h.p; b.pc_flag = c->pc_flag.p;
+  b.pc_g = c->pc_g.p; b.pc_h = c->pc_h.p; b.pc_flag = c->pc_flag.p; b.dc = c->dc.p;
   size_t smem = ((size_t)c->prm.res * ROW_TERMS * (6 + TERM_SZ) + 361 * 2 + 36 + 2) * sizeof(double);
   {
     Prof prof(c, K_PIECE);
     k_piece<<<(re - rb) * P, 384, smem, c->stream>>>(b);
     TOB_LAUNCH_CHECK(c);
   }
-  c->ctr.energy_plane_evals += c->n_planes;
   return 0;
 }
 

@@ -1,0 +1,172 @@
+// bp.cuh -- block-cooperative walk of the 32-wide LBVH shared by the broadphase kernels (lbvh.cu: count / fill) and
+// the fused CCD kernel (narrow.cu: swept-box traversal with the CCD ladder run in place on every hit point).
+//
+// Work decomposition.  One task = (row, level-1 node).  A CTA owns tpc <= BP_THREADS consecutive tasks:
+//   phase A  thread per task: level-1 box test; hit tasks are compacted (ballot + prefix, deterministic) in shared memory
+//   phase B  warp per hit task: 32 lanes test its 32 leaf boxes -> leaf mask
+//   phase C  "items" = (hit task, hit leaf), enumerated task-major through a prefix over popc(leaf mask); the CTA's
+//            warps take items round-robin, 32 lanes = the 32 points of the leaf.
+// Items of one CTA are in (row, Morton position) order and CTAs cover consecutive tasks, so the candidate order is
+// deterministic without atomics: position = (exclusive scan of the CTA totals) + (prefix inside the CTA).
+// All warps of a CTA share its items, so one dense row (hundreds of hit leaves under a few level-1 nodes) no longer
+// serialises on a single warp.
+//
+// The leaf predicate is the reference's (AABB.cc:131-161 as called at :647), FP64, unfused:
+//     candidate  <=>  for every axis:  !(p + d < lo)  &&  !(p > hi + d)
+#pragma once
+#include "ctx.cuh"
+
+namespace tob {
+
+#define BP_THREADS 128
+#define BP_WARPS (BP_THREADS / 32)
+#define BP_BATCH 512   // items staged per batch by the fill pass
+
+struct BpArgs {
+  const double* box;           // rows_all x 6 (lo xyz, hi xyz)
+  uint32_t rows, n1, n_tasks, row_base, rows_all;
+  uint32_t tpc;                // tasks per CTA (<= BP_THREADS): small queries are spread over more CTAs
+  double d;
+  const double *l1lo[3], *l1hi[3], *l0lo[3], *l0hi[3];
+  const double *px, *py, *pz;
+  uint32_t* bsum;              // per-CTA candidate totals (count: out; fill: exclusive scan, in)
+  uint32_t *cand_pt, *cand_row, *row_off;
+  uint32_t cand_cap;
+  DevCounts* dc;
+};
+
+struct BpShared {
+  uint32_t hit_task[BP_THREADS];      // local task index of the h-th hit task
+  uint32_t lmask[BP_THREADS];         // its leaf mask
+  uint32_t item_base[BP_THREADS + 1]; // exclusive prefix of popc(lmask)
+  uint32_t wtmp[BP_WARPS + 1];
+  uint32_t n_hit;
+};
+
+void bp_args(tob_ctx* c, int row_base, int rows, double d, BpArgs& a);   // lbvh.cu
+
+// the reference predicate with the query box [qlo,qhi] as "this" and the node/point as the argument
+__device__ __forceinline__ bool box_hit(double nlo, double nhi, double qlo, double qhi, double d) {
+  return !(nhi + d < qlo) && !(nlo > qhi + d);
+}
+
+// exclusive prefix of v over the CTA (BP_THREADS threads); *total = CTA sum.  Contains two __syncthreads().
+__device__ __forceinline__ uint32_t bp_block_excl(uint32_t v, uint32_t* wtmp, uint32_t* total) {
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();                       // wtmp may still be read from a previous call
+  if (lane == 31) wtmp[w] = inc;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < BP_WARPS; i++) {
+    uint32_t x = wtmp[i];
+    if (i < (int)w) base += x;
+    tot += x;
+  }
+  *total = tot;
+  return base + inc - v;
+}
+
+// One CTA of 1024 threads: exclusive scan of v[0..n) in place; returns the total (uniform).  Used for the short arrays of
+// per-CTA / per-chunk / per-row totals that sit between a count pass and a fill pass.
+__device__ __forceinline__ uint32_t cta1024_scan_inplace(uint32_t* v, uint32_t n) {
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t s_tile;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < n; base += 1024) {
+    const uint32_t k = base + threadIdx.x;
+    const uint32_t x = k < n ? v[k] : 0;
+    uint32_t inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      const uint32_t sv = wsum[lane];
+      uint32_t si = sv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, si, o);
+        if (lane >= o) si += t;
+      }
+      wsum[lane] = si - sv;
+      if (lane == 31) s_tile = si;
+    }
+    __syncthreads();
+    if (k < n) v[k] = carry + wsum[w] + inc - x;
+    carry += s_tile;
+    __syncthreads();
+  }
+  return carry;
+}
+
+// phases A + B + item prefix.  Returns the number of items of this CTA; *my_rank = hit tasks before this thread's task.
+__device__ __forceinline__ uint32_t bp_prepare(const BpArgs& a, BpShared& s, uint32_t* my_rank) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t t = blockIdx.x * a.tpc + tid;
+  bool hit = false;
+  if (tid < a.tpc && t < a.n_tasks) {
+    const uint32_t r = t / a.n1, nd = t - r * a.n1;
+    const double* q = a.box + (size_t)6 * (a.row_base + r);
+    hit = box_hit(a.l1lo[0][nd], a.l1hi[0][nd], q[0], q[3], a.d) && box_hit(a.l1lo[1][nd], a.l1hi[1][nd], q[1], q[4], a.d) &&
+          box_hit(a.l1lo[2][nd], a.l1hi[2][nd], q[2], q[5], a.d);
+  }
+  uint32_t n_hit;
+  const uint32_t rank = bp_block_excl(hit ? 1u : 0u, s.wtmp, &n_hit);
+  *my_rank = rank;
+  if (hit) s.hit_task[rank] = tid;
+  if (tid == 0) s.n_hit = n_hit;
+  __syncthreads();
+  for (uint32_t h = w; h < n_hit; h += BP_WARPS) {
+    const uint32_t tt = blockIdx.x * a.tpc + s.hit_task[h];
+    const uint32_t r = tt / a.n1, nd = tt - r * a.n1;
+    const double* q = a.box + (size_t)6 * (a.row_base + r);
+    const uint32_t leaf = nd * 32 + lane;   // level-0 arrays are padded to 32 with empty boxes
+    const bool lh = box_hit(a.l0lo[0][leaf], a.l0hi[0][leaf], q[0], q[3], a.d) && box_hit(a.l0lo[1][leaf], a.l0hi[1][leaf], q[1], q[4], a.d) &&
+                    box_hit(a.l0lo[2][leaf], a.l0hi[2][leaf], q[2], q[5], a.d);
+    const uint32_t lm = __ballot_sync(0xffffffffu, lh);
+    if (lane == 0) s.lmask[h] = lm;
+  }
+  __syncthreads();
+  uint32_t n_items;
+  const uint32_t ib = bp_block_excl(tid < n_hit ? (uint32_t)__popc(s.lmask[tid]) : 0u, s.wtmp, &n_items);
+  if (tid < n_hit) s.item_base[tid] = ib;
+  if (tid == 0) s.item_base[n_hit] = n_items;
+  __syncthreads();
+  return n_items;
+}
+
+// item j -> hit task h (binary search over item_base, uniform in the warp) and the leaf it addresses
+__device__ __forceinline__ void bp_item(const BpArgs& a, const BpShared& s, uint32_t j, uint32_t* h_out, uint32_t* row, uint32_t* leaf) {
+  uint32_t lo = 0, hi = s.n_hit;            // largest h with item_base[h] <= j
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (s.item_base[mid] <= j) lo = mid; else hi = mid;
+  }
+  const uint32_t k = j - s.item_base[lo];
+  const uint32_t lb = __fns(s.lmask[lo], 0, k + 1);
+  const uint32_t tt = blockIdx.x * a.tpc + s.hit_task[lo];
+  const uint32_t r = tt / a.n1, nd = tt - r * a.n1;
+  *h_out = lo;
+  *row = a.row_base + r;
+  *leaf = nd * 32 + lb;
+}
+
+// 32 lanes = the 32 points of `leaf` against the box of `row`
+__device__ __forceinline__ bool bp_point_test(const BpArgs& a, uint32_t row, uint32_t p, double* x, double* y, double* z) {
+  const double* q = a.box + (size_t)6 * row;
+  *x = a.px[p]; *y = a.py[p]; *z = a.pz[p];
+  return box_hit(*x, *x, q[0], q[3], a.d) && box_hit(*y, *y, q[1], q[4], a.d) && box_hit(*z, *z, q[2], q[5], a.d);
+}
+
+}  // namespace tob

@@ -14,6 +14,12 @@
 
 namespace tob {
 
+// bumped whenever a device buffer is (re)allocated: a captured CUDA graph holds raw pointers and must be rebuilt
+inline unsigned long long& alloc_generation() {
+  static unsigned long long g = 0;
+  return g;
+}
+
 // growable device buffer (contents are NOT preserved on growth)
 template <typename T>
 struct DBuf {
@@ -24,11 +30,29 @@ struct DBuf {
     size_t want = n + n / 4 + 256;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
+    alloc_generation()++;
     cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
     if (e == cudaSuccess) cap = want;
     return e;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// Device-resident counts and flags.  The iteration never reads a size back to the host in the middle: kernels take
+// their trip counts from here, buffers have a fixed capacity, and an overflow / an unfinished line search turns the
+// state-changing kernels at the end of the iteration into no-ops; the host looks at this struct ONCE per iteration.
+#define TOB_OVF_CAND 1u      // broadphase produced more candidates than cand_cap
+#define TOB_OVF_SELFHITS 4u  // inter-robot CCD hit list overflow
+#define TOB_LS_ROUNDS 2      // Armijo rounds launched ahead (8 ladder rungs each) before the host is asked
+struct DevCounts {
+  uint32_t n_cand;           // candidates of the last broadphase fill (may exceed the capacity -> overflow)
+  uint32_t n_planes;         // planes of the last pack
+  uint32_t n_planes_ob;      // ... of which obstacle planes
+  uint32_t overflow;         // TOB_OVF_* bits, sticky until the host clears them
+  int32_t ls_pending[TOB_LS_ROUNDS + 2];   // robots still backtracking after Armijo round r
+  uint32_t iters_done;       // iterations fully committed (apply step + slack update ran)
+  uint32_t pad;
+  unsigned long long dcd_candidates, planes, ccd_candidates, energy_plane_evals, barrier_terms;   // cumulative since reset
 };
 
 // per-row (robot x sub-segment) geometry produced by segments.cu, indexed by GLOBAL row = robot*n_tr + tr
@@ -87,13 +111,20 @@ struct tob_ctx {
   // per-row geometry + broadphase scratch
   tob::RowGeom geo;
   tob::DBuf<uint32_t> task_cnt, task_off, scan_tmp;
+  tob::DBuf<uint32_t> bsum;           // per-CTA totals of the broadphase count pass, scanned in place
   tob::DBuf<uint32_t> cand_pt, cand_row;
   tob::DBuf<uint32_t> row_off;        // (all rows)+1 candidate offsets; rows outside the queried range are empty
-  uint64_t n_cand = 0;
+  uint64_t cand_cap = 0;              // capacity (candidates) of cand_pt / cand_row / cpl / cflag; planes: cand_cap + self
+  uint64_t n_cand = 0;                // host mirror, valid after sync_counts()
+  tob::DBuf<tob::DevCounts> dc;       // device counts (1 element)
+  tob::DevCounts* h_dc = nullptr;     // pinned mirror
 
   // planes: candidate-indexed scratch, then packed CSR over ALL rows
   tob::DBuf<double> cpl;              // cand x 4 (cx,cy,cz,d)
   tob::DBuf<uint32_t> cflag, cflag_off;
+  tob::DBuf<uint32_t> csum;           // accepted planes per 128-candidate chunk, scanned in place
+  tob::DBuf<uint32_t> selfpre;        // rows+1: exclusive scan of the inter-robot plane count per row
+  tob::DBuf<uint32_t> selfcnt;        // rows: inter-robot planes per row (integer atomics of k_self_planes)
   tob::DBuf<double> pl;               // planes x 4
   tob::DBuf<uint32_t> pl_row, pl_off; // plane -> row ; rows+1 offsets
   tob::DBuf<uint32_t> row_nob, row_ntot;
@@ -122,6 +153,15 @@ struct tob_ctx {
 
   tob_counters ctr{};
   bool bcr_attr_set = false;          // cudaFuncSetAttribute(k_solve_bcr) done on this device
+
+  // whole-iteration CUDA graph (single context, no callbacks, profiling off)
+  cudaGraphExec_t graph_exec = nullptr;
+  unsigned long long graph_gen = 0;   // alloc_generation() the graph was captured at
+  unsigned long long graph_warm_gen = ~0ull;   // generation at which a plain (uncaptured) iteration last ran allocation-free
+  int graph_mode = -1;
+  uint64_t graph_nodes = 0;           // kernel nodes per launch (for the launch counter)
+  bool use_graph = true;
+  bool capturing = false;
 
   // optional per-kernel CUDA-event timing (bench.py roofline): off by default
   bool prof_on = false;
@@ -159,6 +199,14 @@ int fail_msg(tob_ctx* c, const std::string& msg);
 
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+#ifdef __CUDACC__
+// the state-changing tail of an iteration (apply step, slack/dual update) runs only if nothing overflowed and every
+// robot finished its Armijo search in the rounds that were launched ahead
+__device__ __forceinline__ bool iteration_blocked(const DevCounts* dc) {
+  return dc != nullptr && (dc->overflow != 0u || dc->ls_pending[TOB_LS_ROUNDS - 1] > 0);
+}
+#endif
+
 // kernel ids of the per-kernel timing (names in api.cu: kKernelNames)
 enum KernelId {
   K_ROWS = 0, K_BP_COUNT, K_BP_FILL, K_SCAN, K_NARROW, K_PACK, K_SELF_PLANES, K_ROW_ENERGY, K_ROBOT_ENERGY, K_ROW_GRAD,
@@ -191,28 +239,36 @@ int make_tables_host(const tob_params& p, const double* time_weight, std::vector
                      std::vector<double>& convert, std::vector<double>& mdyn, std::vector<double>& kdop);
 // lbvh.cu
 int lbvh_build(tob_ctx* c, const double* V_host, uint32_t n);
-int exclusive_scan_u32(tob_ctx* c, const uint32_t* in, uint32_t* out, size_t n, uint32_t* total_dev);  // out[n] = total
-// queries rows [rb*n_tr, re*n_tr) whose boxes are in geo.box; fills cand_pt/cand_row (GLOBAL rows) and row_off
-int broadphase(tob_ctx* c, int rb, int re, double d, uint64_t* total_host);
-int broadphase_rows(tob_ctx* c, int row_base, int rows, double d, uint64_t* total_host);
+// queries rows [rb*n_tr, re*n_tr) whose boxes are in geo.box; fills cand_pt/cand_row (GLOBAL rows) and row_off.
+// Asynchronous: the total stays on the device (dc->n_cand); count_as = 1 adds it to the dcd_candidates counter.
+int broadphase(tob_ctx* c, int rb, int re, double d, int count_as);
+int broadphase_rows(tob_ctx* c, int row_base, int rows, double d, int count_as);
+int ensure_query_buffers(tob_ctx* c);
+// api.cu: device counts -> pinned mirror (one stream sync); capacity growth after an overflow
+int sync_counts(tob_ctx* c);
+int grow_cand_capacity(tob_ctx* c, uint64_t need);
 // segments.cu : mode bits: 1 = k-DOP extents, 2 = direction rows + swept box, 4 = trial point spline+step*dir
 int compute_rows(tob_ctx* c, const double* spline_dev, const double* dir_dev, const double* step_dev, int rb, int re, int mode);
 // narrow.cu
 int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self);
 int pack_planes_from_host(tob_ctx* c, int rb, int re, const uint32_t* offsets, const double* cc, const double* dd);
-int ccd_position_steps(tob_ctx* c);
+int ccd_position_steps(tob_ctx* c, int rb, int re);
 int self_planes(tob_ctx* c);
 int pack_self_only(tob_ctx* c);
 int self_ccd_steps(tob_ctx* c, int coupled, double* steps_dev);
 // barrier.cu
 int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* tstep, const double* ttime, int KT, int k0,
                   int k1, double* e_dev);
+// one Armijo round of robots [rb,re) (decoupled): trial energies k0..TOB_LS_TRIALS-1 + the ladder decision, robots that
+// are already done are skipped on the device; robots still backtracking are counted in dc->ls_pending[slot]
+int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int slot);
 int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd);
 int row_blocks(tob_ctx* c, int tr, int which, double* out_dev);
 // solve.cu
 int solve_directions(tob_ctx* c, int rb, int re, int dense_shift);
 int solve_coupled(tob_ctx* c);
-int slack_update(tob_ctx* c, int rb, int re);
+// guarded != 0: no-op when the iteration cannot be committed (overflow / line search unfinished); commits otherwise
+int slack_update(tob_ctx* c, int rb, int re, int guarded = 0);
 int slack_terms(tob_ctx* c, const double* in57_dev, int consensus, double* out381_dev);
 
 }  // namespace tob

@@ -164,4 +164,159 @@ __device__ inline double warp_min_eig(double* A, int n, double* d, double* e, do
   return 0.5 * (lo + hi);
 }
 
+// ---- register-resident warp versions (compile-time size N <= 32) ---------------------------------------------------
+// Lane i keeps row i of the matrix in registers; values travel between lanes with shuffles, so there is no shared-memory
+// round trip and no __syncwarp in the dependency chain.  The outer loops stay ROLLED (straight-line code that runs once
+// is instruction-fetch bound): the register window is shifted by one column per step so that the pivot column is always
+// w[0] and every register index is static.  Operands and operation order are those of the shared-memory versions above.
+
+// Cholesky with Eigen::LLT's pivot rule.  w[j] = A(lane, j) on entry (destroyed).  If Lsm != nullptr the factor is stored
+// there (col-major, ld N, lower triangle).  All 32 lanes must call; the return value is uniform.
+template <int N>
+__device__ __forceinline__ bool warp_chol_roll(double (&w)[N], double* Lsm) {
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+#pragma unroll 1
+  for (int k = 0; k < N; k++) {
+    const double x = __shfl_sync(full, w[0], k);
+    if (!(x > 0)) return false;
+    const double lkk = sqrt(x);
+    double lik = w[0] / lkk;
+    if (lane == k) lik = lkk;
+    if (Lsm && lane >= k && lane < N) Lsm[lane + N * k] = lik;
+#pragma unroll
+    for (int jj = 1; jj < N; jj++) {
+      const double ljk = __shfl_sync(full, lik, (k + jj) & 31);
+      if (k + jj < N && lane >= k + jj) w[jj] -= lik * ljk;
+    }
+#pragma unroll
+    for (int jj = 0; jj + 1 < N; jj++) w[jj] = w[jj + 1];
+  }
+  return true;
+}
+
+// L L^T x = b, L in shared memory (col-major, ld N) as left by warp_chol_roll.  Lane i passes b_i and receives x_i; the
+// vector stays in registers, the divisions by the diagonal are one reciprocal per lane.
+template <int N>
+__device__ __forceinline__ double warp_chol_solve_sm(const double* Lsm, double b) {
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  const double rd = lane < N ? 1.0 / Lsm[lane + N * lane] : 0.0;
+  double s = b;
+#pragma unroll 1
+  for (int k = 0; k < N; k++) {
+    const double yk = __shfl_sync(full, s * rd, k);
+    if (lane == k) s = yk;
+    else if (lane > k && lane < N) s -= Lsm[lane + N * k] * yk;
+  }
+#pragma unroll 1
+  for (int k = N - 1; k >= 0; k--) {
+    const double xk = __shfl_sync(full, s * rd, k);
+    if (lane == k) s = xk;
+    else if (lane < k) s -= Lsm[k + N * lane] * xk;
+  }
+  return s;
+}
+
+// smallest eigenvalue of the symmetric matrix whose row `lane` is in w[] (full rows; destroyed): Householder
+// tridiagonalisation with shuffles, then Sturm-count multisection (32 shifts per round) on the division-free
+// three-term recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (sign changes = eigenvalues below x), rescaled
+// against overflow.  d, e: shared scratch of N doubles each.  All 32 lanes must call; the result is uniform.
+template <int N>
+__device__ __forceinline__ double warp_min_eig_roll(double (&w)[N], double* d, double* e) {
+  const int lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+#pragma unroll 1
+  for (int k = 0; k + 2 < N; k++) {
+    const double xi = (lane > k && lane < N) ? w[0] : 0.0;
+    double sigma = xi * xi;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sigma += __shfl_xor_sync(full, sigma, o);
+    const double x0 = __shfl_sync(full, w[0], k + 1);
+    const double akk = __shfl_sync(full, w[0], k);
+    const double tail = sigma - x0 * x0;
+    if (lane == 0) d[k] = akk;
+    if (tail > 0) {                       // else: column already tridiagonal (uniform)
+      const double alpha = (x0 >= 0 ? -1.0 : 1.0) * sqrt(sigma);
+      double vi = xi;
+      if (lane == k + 1) vi = x0 - alpha;
+      const double vn2 = tail + (x0 - alpha) * (x0 - alpha);
+      const double beta = 2.0 / vn2;
+      double pi = 0;
+#pragma unroll
+      for (int jj = 1; jj < N; jj++) {
+        const double vj = __shfl_sync(full, vi, (k + jj) & 31);
+        if (k + jj < N) pi += w[jj] * vj;
+      }
+      if (!(lane > k && lane < N)) pi = 0;
+      pi *= beta;
+      double kk = pi * vi;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) kk += __shfl_xor_sync(full, kk, o);
+      kk *= 0.5 * beta;
+      const double wi = pi - kk * vi;
+#pragma unroll
+      for (int jj = 1; jj < N; jj++) {
+        const double wj = __shfl_sync(full, wi, (k + jj) & 31), vj = __shfl_sync(full, vi, (k + jj) & 31);
+        if (k + jj < N) w[jj] -= vi * wj + wi * vj;
+      }
+      if (lane == 0) e[k] = alpha;
+    } else if (lane == 0) e[k] = x0;
+#pragma unroll
+    for (int jj = 0; jj + 1 < N; jj++) w[jj] = w[jj + 1];
+  }
+  {   // window now starts at column N-2
+    const double dn2 = __shfl_sync(full, w[0], N - 2), en2 = __shfl_sync(full, w[0], N - 1);
+    const double dn1 = __shfl_sync(full, w[1], N - 1);
+    if (lane == 0) { d[N - 2] = dn2; e[N - 2] = en2; d[N - 1] = dn1; e[N - 1] = 0.0; }
+  }
+  __syncwarp();
+  // Gershgorin lower bound; lambda_min <= min d_i
+  double lo = INFINITY, hi = INFINITY;
+  if (lane < N) {
+    const double r = fabs(e[lane]) + (lane > 0 ? fabs(e[lane - 1]) : 0.0);
+    lo = d[lane] - r;
+    hi = d[lane];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(full, lo, o));
+    hi = fmin(hi, __shfl_xor_sync(full, hi, o));
+  }
+  if (!(hi > lo)) return hi;
+#pragma unroll 1
+  for (int round = 0; round < 14; round++) {
+    const double x = lo + (hi - lo) * ((lane + 1) / 33.0);
+    int cnt = 0;
+    double p0 = 1.0, p1 = d[0] - x;
+    bool neg = p1 < 0;                     // sign of the last non-zero term
+    if (neg) cnt++;
+#pragma unroll 1
+    for (int i = 1; i < N; i++) {
+      const double ei = e[i - 1];
+      double p2 = (d[i] - x) * p1 - (ei * ei) * p0;
+      const double m = fabs(p2);
+      if (m > 1e150) { p2 *= 1e-150; p1 *= 1e-150; }
+      else if (m < 1e-150 && m > 0) { p2 *= 1e150; p1 *= 1e150; }
+      if (p2 != 0) {
+        const bool n2 = p2 < 0;
+        if (n2 != neg) cnt++;
+        neg = n2;
+      }
+      p0 = p1; p1 = p2;
+    }
+    const unsigned mk = __ballot_sync(full, cnt >= 1);
+    double nlo = lo, nhi = hi;
+    if (mk == 0) nlo = __shfl_sync(full, x, 31);
+    else {
+      const int f = __ffs(mk) - 1;
+      nhi = __shfl_sync(full, x, f);
+      if (f > 0) nlo = __shfl_sync(full, x, f - 1);
+    }
+    lo = nlo; hi = nhi;
+    if (!(hi > lo)) break;
+  }
+  return 0.5 * (lo + hi);
+}
+
 }  // namespace tob

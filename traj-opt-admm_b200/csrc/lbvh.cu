@@ -11,15 +11,15 @@
 //   px,py,pz[n_pad], pid[n_pad]   points in Morton order, padded to a multiple of 32 with +inf
 //   level 0: one box per 32 consecutive points (a leaf = one warp-wide coalesced load)
 //   level 1: one box per 32 leaves.  Boxes are lo[3][count_pad], hi[3][count_pad].
-// Broadphase work decomposition: one task = (row, level-1 node).  A warp owns 32 consecutive tasks: every lane
-// pre-tests its task's node box, then the warp walks the hit tasks cooperatively (32 lanes = 32 leaf boxes, then
-// 32 lanes = 32 points of a hit leaf).  Two passes (count, exclusive scan, fill) give a deterministic candidate
-// order (row, Morton position) without atomics.
+// Broadphase work decomposition: one task = (row, level-1 node); a CTA owns 128 consecutive tasks and shares the hit
+// leaves among its warps (bp.cuh).  Two passes (count per CTA, scan of the CTA totals, fill) give a deterministic
+// candidate order (row, Morton position) without atomics; sizes stay on the device (DevCounts), nothing is read back.
 //
 // Algorithmic bytes: build 128 B/point; query 48 B/row + 16 B/(row x L1 node) + 28 B/candidate.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "ctx.cuh"
+#include "bp.cuh"
 
 namespace tob {
 
@@ -196,217 +196,184 @@ int lbvh_build(tob_ctx* c, const double* V_host, uint32_t n) {
   return 0;
 }
 
-// ---- exclusive scan (uint32) ---------------------------------------------------------------------------------
-#define SCAN_BLOCK 256
-#define SCAN_ITEMS 8
-#define SCAN_TILE (SCAN_BLOCK * SCAN_ITEMS)
-
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total, uint32_t* sm /*>=32*/) {
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  uint32_t inc = v;
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
+// ---- broadphase ------------------------------------------------------------------------------------------------
+// count pass: candidates per CTA (bp.cuh explains the walk)
+__global__ void __launch_bounds__(BP_THREADS) k_bp_count(BpArgs a) {
+  __shared__ BpShared s;
+  uint32_t rank;
+  const uint32_t n_items = bp_prepare(a, s, &rank);
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t cnt = 0;
+  for (uint32_t j = w; j < n_items; j += BP_WARPS) {
+    uint32_t h, row, leaf;
+    bp_item(a, s, j, &h, &row, &leaf);
+    double x, y, z;
+    const bool ok = bp_point_test(a, row, leaf * 32 + lane, &x, &y, &z);
+    cnt += __popc(__ballot_sync(0xffffffffu, ok));
   }
-  if (lane == 31) sm[w] = inc;
   __syncthreads();
-  if (w == 0) {
-    uint32_t s = lane < (blockDim.x >> 5) ? sm[lane] : 0;
-    uint32_t si = s;
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, si, o);
-      if (lane >= o) si += t;
+  if (lane == 0) s.wtmp[w] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t tot = 0;
+    for (int i = 0; i < BP_WARPS; i++) tot += s.wtmp[i];
+    a.bsum[blockIdx.x] = tot;
+  }
+}
+
+// one CTA: exclusive scan of the per-CTA totals; total -> dc->n_cand, sticky overflow bit, cumulative counter
+__global__ void __launch_bounds__(1024) k_bp_top(uint32_t* bsum, uint32_t nblk, uint32_t cap, int count_as, DevCounts* dc) {
+  const uint32_t total = cta1024_scan_inplace(bsum, nblk);
+  if (threadIdx.x == 0) {
+    bsum[nblk] = total;
+    dc->n_cand = total;
+    if (total > cap) dc->overflow |= TOB_OVF_CAND;
+    else if (count_as == 1) dc->dcd_candidates += total;
+  }
+}
+
+// fill pass: same walk; items are staged in batches so that the position of every candidate is
+//   (scanned CTA base) + (candidates of earlier items of this CTA) + (rank among the lanes of its leaf)
+__global__ void __launch_bounds__(BP_THREADS) k_bp_fill(BpArgs a) {
+  __shared__ BpShared s;
+  __shared__ uint32_t s_pm[BP_BATCH], s_pre[BP_BATCH], s_leaf[BP_BATCH], s_row[BP_BATCH];
+  __shared__ uint32_t s_taskcand[BP_THREADS + 1];   // candidates of this CTA before hit task h
+  const uint32_t total = a.dc->n_cand;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  // candidate offsets of the rows outside the queried range (empty lists)
+  if (blockIdx.x == 0)
+    for (uint32_t g = tid; g <= a.rows_all; g += BP_THREADS)
+      if (g < a.row_base || g >= a.row_base + a.rows) a.row_off[g] = g < a.row_base ? 0u : total;
+  if (total > a.cand_cap) return;   // overflow: the host grows the buffers and runs the query again
+  uint32_t rank;
+  const uint32_t n_items = bp_prepare(a, s, &rank);
+  const uint32_t n_hit = s.n_hit;
+  const uint32_t cta_base = a.bsum[blockIdx.x];
+  uint32_t run = 0;
+  for (uint32_t b0 = 0; b0 < n_items; b0 += BP_BATCH) {
+    const uint32_t nb = min((uint32_t)BP_BATCH, n_items - b0);
+    for (uint32_t jj = w; jj < nb; jj += BP_WARPS) {
+      uint32_t h, row, leaf;
+      bp_item(a, s, b0 + jj, &h, &row, &leaf);
+      double x, y, z;
+      const bool ok = bp_point_test(a, row, leaf * 32 + lane, &x, &y, &z);
+      const uint32_t pm = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) { s_pm[jj] = pm; s_leaf[jj] = leaf; s_row[jj] = row; }
     }
-    sm[lane] = si - s;
-    if (lane == 31) *total = si;
-  }
-  __syncthreads();
-  uint32_t r = sm[w] + inc - v;
-  __syncthreads();
-  return r;
-}
-
-__global__ void k_scan_reduce(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ bsum) {
-  size_t base = (size_t)blockIdx.x * SCAN_TILE;
-  uint32_t s = 0;
-  for (int i = 0; i < SCAN_ITEMS; i++) {
-    size_t k = base + (size_t)i * SCAN_BLOCK + threadIdx.x;
-    if (k < n) s += in[k];
-  }
-  __shared__ uint32_t sm[32];
-  __shared__ uint32_t tot;
-  block_excl_scan(s, &tot, sm);
-  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
-}
-
-// single block: exclusive scan of bsum[nb] in place, total to bsum[nb]
-__global__ void k_scan_top(uint32_t* bsum, uint32_t nb) {
-  __shared__ uint32_t sm[32];
-  __shared__ uint32_t tot;
-  uint32_t carry = 0;
-  for (uint32_t base = 0; base < nb; base += blockDim.x) {
-    uint32_t k = base + threadIdx.x;
-    uint32_t v = k < nb ? bsum[k] : 0;
-    uint32_t e = block_excl_scan(v, &tot, sm);
-    if (k < nb) bsum[k] = carry + e;
-    carry += tot;
+    __syncthreads();
+    // exclusive prefix of popc(pm) over the batch: BP_BATCH / BP_THREADS consecutive items per thread
+    constexpr int PER = BP_BATCH / BP_THREADS;
+    uint32_t loc[PER], sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+      const uint32_t jj = tid * PER + i;
+      loc[i] = jj < nb ? (uint32_t)__popc(s_pm[jj]) : 0u;
+      sum += loc[i];
+    }
+    uint32_t btot;
+    uint32_t e = bp_block_excl(sum, s.wtmp, &btot);
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+      const uint32_t jj = tid * PER + i;
+      if (jj < nb) s_pre[jj] = e;
+      e += loc[i];
+    }
+    __syncthreads();
+    if (tid < n_hit) {
+      const uint32_t ib = s.item_base[tid];
+      if (ib >= b0 && ib < b0 + nb) s_taskcand[tid] = run + s_pre[ib - b0];
+    }
+    for (uint32_t jj = w; jj < nb; jj += BP_WARPS) {
+      const uint32_t pm = s_pm[jj];
+      if (pm & (1u << lane)) {
+        const uint32_t pos = cta_base + run + s_pre[jj] + __popc(pm & ((1u << lane) - 1u));
+        a.cand_pt[pos] = s_leaf[jj] * 32 + lane;
+        a.cand_row[pos] = s_row[jj];
+      }
+    }
+    run += btot;
     __syncthreads();
   }
-  if (threadIdx.x == 0) bsum[nb] = carry;
-}
-
-__global__ void k_scan_down(const uint32_t* __restrict__ in, size_t n, const uint32_t* __restrict__ bsum, uint32_t nb,
-                            uint32_t* __restrict__ out, uint32_t* __restrict__ total_dev) {
-  __shared__ uint32_t sm[32];
-  __shared__ uint32_t tot;
-  size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
-  uint32_t v[SCAN_ITEMS], s = 0;
-  for (int i = 0; i < SCAN_ITEMS; i++) {
-    v[i] = (base + i < n) ? in[base + i] : 0;
-    s += v[i];
-  }
-  uint32_t e = block_excl_scan(s, &tot, sm) + bsum[blockIdx.x];
-  for (int i = 0; i < SCAN_ITEMS; i++) {
-    if (base + i < n) out[base + i] = e;
-    e += v[i];
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    out[n] = bsum[nb];
-    if (total_dev) *total_dev = bsum[nb];
+  if (tid < n_hit && s.item_base[tid] >= n_items) s_taskcand[tid] = run;
+  if (tid == 0) s_taskcand[n_hit] = run;
+  __syncthreads();
+  // first task of a row (level-1 node 0): the row's candidate list starts here
+  const uint32_t t = blockIdx.x * a.tpc + tid;
+  if (tid < a.tpc && t < a.n_tasks) {
+    const uint32_t r = t / a.n1;
+    if (t == r * a.n1) a.row_off[a.row_base + r] = cta_base + s_taskcand[rank];
   }
 }
 
-int exclusive_scan_u32(tob_ctx* c, const uint32_t* in, uint32_t* out, size_t n, uint32_t* total_dev) {
-  uint32_t nb = (uint32_t)((n + SCAN_TILE - 1) / SCAN_TILE);
-  if (nb == 0) nb = 1;
-  TOB_CUDA(c, c->scan_tmp.ensure(nb + 1));
-  Prof prof(c, K_SCAN);   // the three scan kernels are timed as one unit
-  k_scan_reduce<<<nb, SCAN_BLOCK, 0, c->stream>>>(in, n, c->scan_tmp.p);
-  TOB_LAUNCH_CHECK(c);
-  k_scan_top<<<1, 1024, 0, c->stream>>>(c->scan_tmp.p, nb);
-  TOB_LAUNCH_CHECK(c);
-  k_scan_down<<<nb, SCAN_BLOCK, 0, c->stream>>>(in, n, c->scan_tmp.p, nb, out, total_dev);
-  TOB_LAUNCH_CHECK(c);
-  return 0;
+// boxes of rows [rb*n_tr, re*n_tr) must be in c->geo.box.  Asynchronous: leaves c->cand_pt / cand_row / row_off and the
+// total in c->dc->n_cand (TOB_OVF_CAND set when it exceeds c->cand_cap; then nothing is written).
+int broadphase(tob_ctx* c, int rb, int re, double d, int count_as) {
+  return broadphase_rows(c, rb * c->n_tr, (re - rb) * c->n_tr, d, count_as);
 }
 
-// ---- broadphase ------------------------------------------------------------------------------------------------
-struct BpArgs {
-  const double* box;           // rows x 6
-  uint32_t rows, n1, n_tasks, row_base;
-  double d;
-  const double *l1lo[3], *l1hi[3], *l0lo[3], *l0hi[3];
-  const double *px, *py, *pz;
-  uint32_t* task_cnt;          // count pass: out
-  const uint32_t* task_off;    // fill pass: in
-  uint32_t *cand_pt, *cand_row;
-};
-
-// the reference predicate with the query box [qlo,qhi] as "this" and the node/point as the argument
-__device__ __forceinline__ bool box_hit(double nlo, double nhi, double qlo, double qhi, double d) {
-  return !(nhi + d < qlo) && !(nlo > qhi + d);
-}
-
-template <bool FILL>
-__global__ void __launch_bounds__(256) k_broadphase(BpArgs a) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t t = warp * 32 + lane;
-  bool hit = false;
-  if (t < a.n_tasks) {
-    uint32_t r = t / a.n1, nd = t - r * a.n1;
-    const double* q = a.box + (size_t)6 * (a.row_base + r);
-    hit = box_hit(a.l1lo[0][nd], a.l1hi[0][nd], q[0], q[3], a.d) && box_hit(a.l1lo[1][nd], a.l1hi[1][nd], q[1], q[4], a.d) &&
-          box_hit(a.l1lo[2][nd], a.l1hi[2][nd], q[2], q[5], a.d);
-    if (!FILL && !hit) a.task_cnt[t] = 0;
-  }
-  uint32_t mask = __ballot_sync(0xffffffffu, hit);
-  while (mask) {
-    uint32_t b = __ffs(mask) - 1;
-    mask &= mask - 1;
-    uint32_t tt = warp * 32 + b;
-    uint32_t r = tt / a.n1, nd = tt - r * a.n1;
-    const double* q = a.box + (size_t)6 * (a.row_base + r);
-    double q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5];
-    uint32_t leaf = nd * 32 + lane;   // level-0 arrays are padded to 32 with empty boxes
-    bool lh = box_hit(a.l0lo[0][leaf], a.l0hi[0][leaf], q0, q3, a.d) && box_hit(a.l0lo[1][leaf], a.l0hi[1][leaf], q1, q4, a.d) &&
-              box_hit(a.l0lo[2][leaf], a.l0hi[2][leaf], q2, q5, a.d);
-    uint32_t lmask = __ballot_sync(0xffffffffu, lh);
-    uint32_t cnt = 0;
-    uint32_t base = FILL ? a.task_off[tt] : 0;
-    while (lmask) {
-      uint32_t lb = __ffs(lmask) - 1;
-      lmask &= lmask - 1;
-      uint32_t p = (nd * 32 + lb) * 32 + lane;
-      double x = a.px[p], y = a.py[p], z = a.pz[p];
-      bool ok = box_hit(x, x, q0, q3, a.d) && box_hit(y, y, q1, q4, a.d) && box_hit(z, z, q2, q5, a.d);
-      uint32_t pm = __ballot_sync(0xffffffffu, ok);
-      if (FILL && ok) {
-        uint32_t pos = base + cnt + __popc(pm & ((1u << lane) - 1u));
-        a.cand_pt[pos] = p;
-        a.cand_row[pos] = a.row_base + r;
-      }
-      cnt += __popc(pm);
-    }
-    if (!FILL && lane == 0) a.task_cnt[tt] = cnt;
-  }
-}
-
-// candidate offsets for ALL rows of the context; rows outside the queried range [row_base, row_base+rows) are empty
-__global__ void k_row_offsets(const uint32_t* __restrict__ task_off, uint32_t rows, uint32_t row_base, uint32_t rows_all,
-                              uint32_t n1, uint32_t* __restrict__ row_off) {
-  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g > rows_all) return;
-  uint32_t lr = g < row_base ? 0u : (g - row_base > rows ? rows : g - row_base);
-  row_off[g] = task_off[(size_t)lr * n1];
-}
-
-// boxes of rows [rb*n_tr, re*n_tr) must be in c->geo.box.  Leaves c->cand_pt / cand_row / row_off, total on host.
-int broadphase(tob_ctx* c, int rb, int re, double d, uint64_t* total_host) {
-  return broadphase_rows(c, rb * c->n_tr, (re - rb) * c->n_tr, d, total_host);
-}
-
-// same for an arbitrary row range [row_base, row_base+rows) of geo.box (tob_box_query uses row 0 with a caller box)
-int broadphase_rows(tob_ctx* c, int row_base, int rows, double d, uint64_t* total_host) {
-  if (c->n_pts == 0) return fail_msg(c, "broadphase: no point cloud uploaded");
-  BpArgs a;
+void bp_args(tob_ctx* c, int row_base, int rows, double d, BpArgs& a) {
   a.box = c->geo.box.p;
   a.rows = rows; a.n1 = c->lvl[1].count; a.n_tasks = (uint32_t)rows * a.n1; a.d = d; a.row_base = (uint32_t)row_base;
+  a.rows_all = (uint32_t)c->rows_all();
   for (int k = 0; k < 3; k++) {
     a.l1lo[k] = c->lvl[1].lo[k]; a.l1hi[k] = c->lvl[1].hi[k];
     a.l0lo[k] = c->lvl[0].lo[k]; a.l0hi[k] = c->lvl[0].hi[k];
   }
   a.px = c->px.p; a.py = c->py.p; a.pz = c->pz.p;
-  TOB_CUDA(c, c->task_cnt.ensure(a.n_tasks + 1));
-  TOB_CUDA(c, c->task_off.ensure(a.n_tasks + 1));
-  TOB_CUDA(c, c->row_off.ensure(c->rows_all() + 2));
-  a.task_cnt = c->task_cnt.p; a.task_off = c->task_off.p;
-  a.cand_pt = nullptr; a.cand_row = nullptr;
-  int nblk = div_up((size_t)a.n_tasks, 256);
+  a.bsum = c->bsum.p;
+  a.cand_pt = c->cand_pt.p; a.cand_row = c->cand_row.p; a.row_off = c->row_off.p;
+  a.cand_cap = (uint32_t)c->cand_cap;
+  a.dc = c->dc.p;
+  // enough CTAs to cover the machine a few times over, at most BP_THREADS tasks each
+  uint32_t tpc = a.n_tasks / (4u * (uint32_t)c->sm_count);
+  a.tpc = tpc < 16u ? 16u : (tpc > (uint32_t)BP_THREADS ? (uint32_t)BP_THREADS : tpc);
+}
+
+// same for an arbitrary row range [row_base, row_base+rows) of geo.box (tob_box_query uses row 0 with a caller box)
+int broadphase_rows(tob_ctx* c, int row_base, int rows, double d, int count_as) {
+  if (c->n_pts == 0) return fail_msg(c, "broadphase: no point cloud uploaded");
+  TOB_TRY(ensure_query_buffers(c));
+  BpArgs a;
+  bp_args(c, row_base, rows, d, a);
+  const int nblk = div_up((size_t)a.n_tasks, a.tpc);
   {
     Prof prof(c, K_BP_COUNT);
-    k_broadphase<false><<<nblk, 256, 0, c->stream>>>(a);
+    k_bp_count<<<nblk, BP_THREADS, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
-  uint32_t* tot_dev = (uint32_t*)c->red.p;
-  TOB_TRY(exclusive_scan_u32(c, c->task_cnt.p, c->task_off.p, a.n_tasks, tot_dev));
-  uint32_t* hp = (uint32_t*)c->h_pinned;
-  TOB_CUDA(c, cudaMemcpyAsync(hp, tot_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
-  uint64_t total = hp[0];
-  c->n_cand = total;
-  *total_host = total;
-  TOB_CUDA(c, c->cand_pt.ensure(total + 1));
-  TOB_CUDA(c, c->cand_row.ensure(total + 1));
-  a.cand_pt = c->cand_pt.p; a.cand_row = c->cand_row.p;
-  if (total) {
+  {
+    Prof prof(c, K_SCAN);
+    k_bp_top<<<1, 1024, 0, c->stream>>>(c->bsum.p, (uint32_t)nblk, a.cand_cap, count_as, c->dc.p);
+    TOB_LAUNCH_CHECK(c);
+  }
+  {
     Prof prof(c, K_BP_FILL);
-    k_broadphase<true><<<nblk, 256, 0, c->stream>>>(a);
+    k_bp_fill<<<nblk, BP_THREADS, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
-  k_row_offsets<<<div_up(c->rows_all() + 1, 256), 256, 0, c->stream>>>(c->task_off.p, rows, a.row_base, c->rows_all(), a.n1,
-                                                                       c->row_off.p);
-  TOB_LAUNCH_CHECK(c);
+  return 0;
+}
+
+// every buffer whose size depends only on the parameters, the cloud and the candidate capacity: allocated up front so
+// that an iteration neither allocates nor reads a size back in the middle (CUDA-graph capturable)
+int ensure_query_buffers(tob_ctx* c) {
+  if (c->cand_cap == 0) c->cand_cap = 1u << 20;
+  const size_t rows = (size_t)c->rows_all(), U = (size_t)c->n_robots();
+  const size_t n1 = c->n_levels > 1 ? c->lvl[1].count : 1;
+  const size_t nblk = rows * n1 / 16 + 4 * (size_t)c->sm_count + 2;   // tasks per CTA >= 16
+  const size_t self_max = rows * (U > 1 ? U - 1 : 0);
+  TOB_CUDA(c, c->bsum.ensure(nblk + 1));
+  TOB_CUDA(c, c->row_off.ensure(rows + 2));
+  TOB_CUDA(c, c->cand_pt.ensure(c->cand_cap + 1));
+  TOB_CUDA(c, c->cand_row.ensure(c->cand_cap + 1));
+  TOB_CUDA(c, c->cpl.ensure(4 * c->cand_cap + 4));
+  TOB_CUDA(c, c->cflag.ensure(c->cand_cap + 1));
+  TOB_CUDA(c, c->csum.ensure(c->cand_cap / 128 + 4)   /* >= chunks + 1 for any chunk size >= 128 */);
+  TOB_CUDA(c, c->selfpre.ensure(rows + 2));
+  TOB_CUDA(c, c->selfcnt.ensure(rows + 2));
+  TOB_CUDA(c, c->pl.ensure(4 * (c->cand_cap + self_max) + 4));
+  TOB_CUDA(c, c->pl_row.ensure(c->cand_cap + self_max + 1));
+  TOB_CUDA(c, c->pl_off.ensure(rows + 2));
   return 0;
 }
 

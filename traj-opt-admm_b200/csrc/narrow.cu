@@ -8,6 +8,7 @@
 //     (Step::self_step :184-256, Step::couple_self_step :112-182)
 //   * packing of accepted planes into the per-row CSR the barrier kernels stream.
 #include "ctx.cuh"
+#include "bp.cuh"
 #include "gjk.cuh"
 
 namespace tob {
@@ -20,35 +21,86 @@ __device__ __forceinline__ void load_pts6(const double* __restrict__ src, double
 }
 
 // ---- obstacle planes -------------------------------------------------------------------------------------------
+// Candidates are processed in chunks of NP_CHUNK (one CTA iteration).  Inside a chunk: every thread runs the cheap
+// 49-DOP gate for NP_PER candidates, the survivors are compacted (ballot + prefix), and the threads then run GJK + plane
+// for the survivors, so the expensive divergent part executes on dense warps instead of on ~30 % of the lanes.
+// Per chunk the number of accepted planes goes to csum[chunk]; k_np_top scans it and k_pack scatters.
 struct NarrowArgs {
-  uint32_t n_cand;
+  const DevCounts* dc;
+  uint32_t cap;
   const uint32_t *cand_pt, *cand_row;
   const double *px, *py, *pz;
   const double *P, *klo, *khi, *kdop;
   double dist, offset;
-  double* cpl;       // n_cand x 4
-  uint32_t* cflag;   // n_cand
+  double* cpl;       // cap x 4
+  uint32_t* cflag;   // cap
+  uint32_t* csum;    // chunks + 1
 };
 
-__global__ void __launch_bounds__(128) k_narrow(NarrowArgs a) {
+#define NP_THREADS 128
+#define NP_PER 4
+#define NP_CHUNK (NP_THREADS * NP_PER)   // candidates per CTA iteration; their k-DOP survivors fill the GJK phase densely
+
+__global__ void __launch_bounds__(NP_THREADS) k_narrow(NarrowArgs a) {
   __shared__ double s_kdop[3 * TOB_KDOP_AXES];
+  __shared__ uint32_t s_surv[NP_CHUNK];
+  __shared__ uint32_t s_w[NP_THREADS / 32];
   for (int i = threadIdx.x; i < 3 * TOB_KDOP_AXES; i += blockDim.x) s_kdop[i] = a.kdop[i];
+  const uint32_t n = a.dc->n_cand;
+  if (n > a.cap) return;
+  const uint32_t n_chunks = (n + NP_CHUNK - 1) / NP_CHUNK;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   __syncthreads();
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n_cand) return;
-  uint32_t row = a.cand_row[i], p = a.cand_pt[i];
-  double q[3] = {a.px[p], a.py[p], a.pz[p]};
-  uint32_t ok = 0;
-  if (kdop_point_overlap(a.klo + (size_t)TOB_KDOP_AXES * row, a.khi + (size_t)TOB_KDOP_AXES * row, s_kdop, q, a.dist)) {
-    double P[6][3], c[3], d;
-    load_pts6(a.P + (size_t)18 * row, P);
-    if (plane_point(P, q, a.dist, a.offset, c, &d)) {
-      ok = 1;
-      double* o = a.cpl + (size_t)4 * i;
-      o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; o[3] = d;
+  for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    uint32_t n_surv = 0;   // uniform
+#pragma unroll
+    for (int q = 0; q < NP_PER; q++) {
+      const uint32_t loc = q * NP_THREADS + tid, i = chunk * NP_CHUNK + loc;
+      bool pass = false;
+      if (i < n) {
+        const uint32_t row = a.cand_row[i], p = a.cand_pt[i];
+        const double pt[3] = {a.px[p], a.py[p], a.pz[p]};
+        pass = kdop_point_overlap(a.klo + (size_t)TOB_KDOP_AXES * row, a.khi + (size_t)TOB_KDOP_AXES * row, s_kdop, pt, a.dist);
+        a.cflag[i] = 0;
+      }
+      const uint32_t bm = __ballot_sync(0xffffffffu, pass);
+      __syncthreads();                 // s_w of the previous pass has been consumed
+      if (lane == 0) s_w[w] = __popc(bm);
+      __syncthreads();
+      uint32_t base = n_surv, tot = 0;
+#pragma unroll
+      for (int k = 0; k < NP_THREADS / 32; k++) {
+        if (k < (int)w) base += s_w[k];
+        tot += s_w[k];
+      }
+      if (pass) s_surv[base + __popc(bm & ((1u << lane) - 1u))] = loc;
+      n_surv += tot;
+    }
+    __syncthreads();
+    uint32_t ok = 0;
+    for (uint32_t sidx = tid; sidx < n_surv; sidx += NP_THREADS) {
+      const uint32_t ii = chunk * NP_CHUNK + s_surv[sidx];
+      const uint32_t row = a.cand_row[ii], p = a.cand_pt[ii];
+      const double pt[3] = {a.px[p], a.py[p], a.pz[p]};
+      double P[6][3], c[3], d;
+      load_pts6(a.P + (size_t)18 * row, P);
+      if (plane_point(P, pt, a.dist, a.offset, c, &d)) {
+        ok++;
+        *reinterpret_cast<double4*>(a.cpl + (size_t)4 * ii) = make_double4(c[0], c[1], c[2], d);
+        a.cflag[ii] = 1;
+      }
+    }
+    // accepted planes of the chunk (integer sum: order-independent)
+    for (int o = 16; o; o >>= 1) ok += __shfl_xor_sync(0xffffffffu, ok, o);
+    __syncthreads();
+    if (lane == 0) s_w[w] = ok;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t cnt = 0;
+      for (int k = 0; k < NP_THREADS / 32; k++) cnt += s_w[k];
+      a.csum[chunk] = cnt;
     }
   }
-  a.cflag[i] = ok;
 }
 
 // ---- inter-robot planes ----------------------------------------------------------------------------------------
@@ -58,6 +110,7 @@ struct SelfArgs {
   double dist, offset, margin;
   double* self_pl;     // n_tr x npairs x 4
   uint32_t* self_ok;   // n_tr x npairs
+  uint32_t* selfcnt;   // rows: accepted inter-robot planes per row (zeroed before the launch)
 };
 
 __device__ __forceinline__ void pair_from_index(int idx, int U, int* p0, int* p1) {
@@ -89,70 +142,128 @@ __global__ void __launch_bounds__(64) k_self_planes(SelfArgs a) {
       ok = 1;
       double* o = a.self_pl + (size_t)4 * t;
       o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; o[3] = d;
+      atomicAdd(a.selfcnt + r0, 1u);
+      atomicAdd(a.selfcnt + r1, 1u);
     }
   }
   a.self_ok[t] = ok;
 }
 
 // ---- packing -----------------------------------------------------------------------------------------------------
-// per row: number of accepted obstacle planes and inter-robot planes
-__global__ void k_row_counts(int rows, int n_tr, int U, int npairs, int with_self, int self_begin, int self_end,
-                             const uint32_t* __restrict__ row_off, const uint32_t* __restrict__ cflag_off,
-                             const uint32_t* __restrict__ self_ok, uint32_t* __restrict__ row_nob,
-                             uint32_t* __restrict__ row_tot) {
-  int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= rows) return;
-  uint32_t nob = cflag_off[row_off[row + 1]] - cflag_off[row_off[row]];
-  uint32_t ns = 0;
-  if (with_self && row >= self_begin && row < self_end) {
-    int u = row / n_tr, tr = row - u * n_tr;
-    for (int v = 0; v < U; v++) {
-      if (v == u) continue;
-      int a = v < u ? v : u, b = v < u ? u : v;
-      int pi = a * (U - 1) - a * (a - 1) / 2 + (b - a - 1);
-      ns += self_ok[(size_t)tr * npairs + pi];
+// pair index of (lower, higher) robot in the lexicographic enumeration
+__device__ __forceinline__ int pair_index(int a, int b, int U) { return a * (U - 1) - a * (a - 1) / 2 + (b - a - 1); }
+
+struct PackArgs {
+  DevCounts* dc;
+  uint32_t cap;
+  int rows_all, n_tr, U, npairs, with_self, self_begin, self_end;
+  double offset;
+  const uint32_t *cand_row, *cflag, *row_off, *selfcnt;
+  uint32_t *csum, *selfpre;
+  const uint32_t* self_ok;
+  const double *cpl, *self_pl;
+  double* pl;
+  uint32_t *pl_row, *pl_off;
+};
+
+// one CTA: scan of the per-chunk obstacle-plane counts and of the per-row inter-robot plane counts
+__global__ void __launch_bounds__(1024) k_np_top(PackArgs a) {
+  const uint32_t n = a.dc->n_cand;
+  if (n > a.cap) return;
+  const uint32_t n_chunks = (n + NP_CHUNK - 1) / NP_CHUNK;
+  const uint32_t ob_total = cta1024_scan_inplace(a.csum, n_chunks);
+  for (int row = threadIdx.x; row < a.rows_all; row += 1024)
+    a.selfpre[row] = (a.with_self && row >= a.self_begin && row < a.self_end) ? a.selfcnt[row] : 0u;
+  __syncthreads();
+  const uint32_t self_total = cta1024_scan_inplace(a.selfpre, (uint32_t)a.rows_all);
+  if (threadIdx.x == 0) {
+    a.csum[n_chunks] = ob_total;
+    a.selfpre[a.rows_all] = self_total;
+    a.dc->n_planes = ob_total + self_total;
+    a.dc->n_planes_ob = ob_total;
+    a.dc->planes += ob_total + self_total;
+  }
+}
+
+// accepted obstacle planes before candidate idx (idx = a row boundary): scanned chunk base + the flags of the chunk in
+// front of idx, summed by the warp (uniform result)
+__device__ __forceinline__ uint32_t ob_prefix_warp(const PackArgs& a, uint32_t idx, uint32_t n, uint32_t n_chunks) {
+  if (idx >= n) return a.csum[n_chunks];
+  const uint32_t chunk = idx / NP_CHUNK, lane = threadIdx.x & 31;
+  uint32_t local = 0;
+  for (uint32_t j = chunk * NP_CHUNK + lane; j < idx; j += 32) local += a.cflag[j];
+  for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  return a.csum[chunk] + local;
+}
+
+// scatter: obstacle planes keep the candidate order (row, Morton position); the inter-robot planes of a row go behind
+// its obstacle planes: (c, d-offset/2) for the lower robot id, (-c, -d-offset/2) for the higher one
+// (Optimization3D_multi.h:300-304).  Also writes the CSR offsets pl_off[rows_all+1].
+__global__ void __launch_bounds__(NP_THREADS) k_pack(PackArgs a) {
+  __shared__ uint32_t s_w[NP_THREADS / 32];
+  const uint32_t n = a.dc->n_cand;
+  if (n > a.cap) return;
+  const uint32_t n_chunks = (n + NP_CHUNK - 1) / NP_CHUNK;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    uint32_t run = a.csum[chunk];     // uniform: planes before this pass of the chunk
+#pragma unroll
+    for (int q = 0; q < NP_PER; q++) {
+      const uint32_t i = chunk * NP_CHUNK + q * NP_THREADS + tid;
+      const bool f = i < n && a.cflag[i];
+      const uint32_t bm = __ballot_sync(0xffffffffu, f);
+      __syncthreads();
+      if (lane == 0) s_w[w] = __popc(bm);
+      __syncthreads();
+      uint32_t rank = __popc(bm & ((1u << lane) - 1u)), tot = 0;
+#pragma unroll
+      for (int k = 0; k < NP_THREADS / 32; k++) {
+        if (k < (int)w) rank += s_w[k];
+        tot += s_w[k];
+      }
+      if (f) {
+        const uint32_t row = a.cand_row[i];
+        const uint32_t dst = run + rank + a.selfpre[row];
+        const double4 v = *reinterpret_cast<const double4*>(a.cpl + (size_t)4 * i);
+        *reinterpret_cast<double4*>(a.pl + (size_t)4 * dst) = v;
+        a.pl_row[dst] = row;
+      }
+      run += tot;
     }
   }
-  row_nob[row] = nob;
-  row_tot[row] = nob + ns;
-}
-
-__global__ void k_pack_obstacle(uint32_t n_cand, const uint32_t* __restrict__ cand_row, const uint32_t* __restrict__ cflag,
-                                const uint32_t* __restrict__ cflag_off, const uint32_t* __restrict__ row_off,
-                                const uint32_t* __restrict__ pl_off, const double* __restrict__ cpl, double* __restrict__ pl,
-                                uint32_t* __restrict__ pl_row) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_cand || !cflag[i]) return;
-  uint32_t row = cand_row[i];
-  uint32_t dst = pl_off[row] + (cflag_off[i] - cflag_off[row_off[row]]);
-  const double* s = cpl + (size_t)4 * i;
-  double* o = pl + (size_t)4 * dst;
-  o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[3];
-  pl_row[dst] = row;
-}
-
-// inter-robot planes go behind the obstacle planes of their row: (c, d-offset/2) for the lower robot id,
-// (-c, -d-offset/2) for the higher one (Optimization3D_multi.h:300-304)
-__global__ void k_pack_self(int rows, int n_tr, int U, int npairs, int self_begin, int self_end, double offset,
-                            const uint32_t* __restrict__ self_ok, const double* __restrict__ self_pl,
-                            const uint32_t* __restrict__ pl_off, const uint32_t* __restrict__ row_nob, double* __restrict__ pl,
-                            uint32_t* __restrict__ pl_row) {
-  int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= rows || row < self_begin || row >= self_end) return;
-  int u = row / n_tr, tr = row - u * n_tr;
-  uint32_t dst = pl_off[row] + row_nob[row];
-  for (int v = 0; v < U; v++) {
-    if (v == u) continue;
-    int a = v < u ? v : u, b = v < u ? u : v;
-    int pi = a * (U - 1) - a * (a - 1) / 2 + (b - a - 1);
-    size_t t = (size_t)tr * npairs + pi;
-    if (!self_ok[t]) continue;
-    const double* s = self_pl + 4 * t;
-    double* o = pl + (size_t)4 * dst;
-    if (u == a) { o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[3] - 0.5 * offset; }
-    else { o[0] = -s[0]; o[1] = -s[1]; o[2] = -s[2]; o[3] = -s[3] - 0.5 * offset; }
-    pl_row[dst] = row;
-    dst++;
+  // CSR offsets and inter-robot planes: one warp per row
+  const int n_warps = gridDim.x * (NP_THREADS / 32);
+  for (int row = blockIdx.x * (NP_THREADS / 32) + w; row <= a.rows_all; row += n_warps) {
+    const uint32_t pre0 = ob_prefix_warp(a, a.row_off[row], n, n_chunks);
+    const uint32_t off = pre0 + a.selfpre[row];
+    if (lane == 0) a.pl_off[row] = off;
+    if (row < a.rows_all && a.with_self && row >= a.self_begin && row < a.self_end) {
+      const uint32_t pre1 = ob_prefix_warp(a, a.row_off[row + 1], n, n_chunks);
+      uint32_t dst = off + (pre1 - pre0);
+      const int u = row / a.n_tr, tr = row - u * a.n_tr;
+      for (int v0 = 0; v0 < a.U; v0 += 32) {
+        const int v = v0 + lane;
+        size_t t = 0;
+        bool okv = false;
+        int lo = 0;
+        if (v < a.U && v != u) {
+          lo = v < u ? v : u;
+          const int hi = v < u ? u : v;
+          t = (size_t)tr * a.npairs + pair_index(lo, hi, a.U);
+          okv = a.self_ok[t] != 0;
+        }
+        const uint32_t bm = __ballot_sync(0xffffffffu, okv);
+        if (okv) {
+          const uint32_t at = dst + __popc(bm & ((1u << lane) - 1u));
+          const double* sp = a.self_pl + 4 * t;
+          double* o = a.pl + (size_t)4 * at;
+          if (u == lo) { o[0] = sp[0]; o[1] = sp[1]; o[2] = sp[2]; o[3] = sp[3] - 0.5 * a.offset; }
+          else { o[0] = -sp[0]; o[1] = -sp[1]; o[2] = -sp[2]; o[3] = -sp[3] - 0.5 * a.offset; }
+          a.pl_row[at] = row;
+        }
+        dst += __popc(bm);
+      }
+    }
   }
 }
 
@@ -166,7 +277,8 @@ int self_planes(tob_ctx* c) {
   a.U = U; a.n_tr = c->n_tr; a.npairs = npairs;
   a.P = c->geo.P.p; a.D = nullptr; a.box = c->geo.box.p; a.klo = c->geo.klo.p; a.khi = c->geo.khi.p; a.kdop = c->d_kdop.p;
   a.dist = c->prm.offset + 2 * c->prm.margin; a.offset = c->prm.offset; a.margin = c->prm.margin;
-  a.self_pl = c->self_pl.p; a.self_ok = c->self_ok.p;
+  a.self_pl = c->self_pl.p; a.self_ok = c->self_ok.p; a.selfcnt = c->selfcnt.p;
+  TOB_CUDA(c, cudaMemsetAsync(c->selfcnt.p, 0, (size_t)c->rows_all() * sizeof(uint32_t), c->stream));
   if (n) {
     Prof prof(c, K_SELF_PLANES);
     k_self_planes<<<div_up(n, 64), 64, 0, c->stream>>>(a);
@@ -176,78 +288,62 @@ int self_planes(tob_ctx* c) {
   return 0;
 }
 
-// shared tail: per-row totals -> CSR offsets -> scatter.  have_cand: obstacle planes come from the candidate scratch
-static int pack_rows(tob_ctx* c, int rb, int re, bool have_cand, bool ws) {
+// shared tail: chunk / row scans -> scatter into the CSR.  Candidate flags (cflag, csum) and row_off must be current.
+static int pack_rows(tob_ctx* c, int rb, int re, bool ws) {
   cudaStream_t st = c->stream;
-  const int rows = c->rows_all(), U = c->n_robots(), npairs = U * (U - 1) / 2;
-  uint64_t nc = have_cand ? c->n_cand : 0;
-  TOB_CUDA(c, c->row_nob.ensure(rows + 1));
-  TOB_CUDA(c, c->row_ntot.ensure(rows + 1));
-  TOB_CUDA(c, c->pl_off.ensure(rows + 2));
+  const int U = c->n_robots();
   TOB_CUDA(c, c->self_ok.ensure(1));
-  k_row_counts<<<div_up(rows, 128), 128, 0, st>>>(rows, c->n_tr, U, npairs, ws ? 1 : 0, rb * c->n_tr, re * c->n_tr,
-                                                  c->row_off.p, c->cflag_off.p, c->self_ok.p, c->row_nob.p, c->row_ntot.p);
-  TOB_LAUNCH_CHECK(c);
-  uint32_t* tot_dev = (uint32_t*)c->red.p;
-  TOB_TRY(exclusive_scan_u32(c, c->row_ntot.p, c->pl_off.p, rows, tot_dev));
-  uint32_t* hp = (uint32_t*)c->h_pinned;
-  TOB_CUDA(c, cudaMemcpyAsync(hp, tot_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  TOB_CUDA(c, cudaStreamSynchronize(st));
-  uint64_t np = hp[0];
-  c->n_planes = np;
-  TOB_CUDA(c, c->pl.ensure(4 * np + 4));
-  TOB_CUDA(c, c->pl_row.ensure(np + 1));
-  if (nc) {
+  TOB_CUDA(c, c->self_pl.ensure(4));
+  PackArgs a;
+  a.dc = c->dc.p; a.cap = (uint32_t)c->cand_cap;
+  a.rows_all = c->rows_all(); a.n_tr = c->n_tr; a.U = U; a.npairs = U * (U - 1) / 2; a.with_self = ws ? 1 : 0;
+  a.self_begin = rb * c->n_tr; a.self_end = re * c->n_tr; a.offset = c->prm.offset;
+  a.cand_row = c->cand_row.p; a.cflag = c->cflag.p; a.row_off = c->row_off.p; a.csum = c->csum.p; a.selfpre = c->selfpre.p;
+  a.selfcnt = c->selfcnt.p;
+  a.self_ok = c->self_ok.p; a.cpl = c->cpl.p; a.self_pl = c->self_pl.p;
+  a.pl = c->pl.p; a.pl_row = c->pl_row.p; a.pl_off = c->pl_off.p;
+  {
+    Prof prof(c, K_SCAN);
+    k_np_top<<<1, 1024, 0, st>>>(a);
+    TOB_LAUNCH_CHECK(c);
+  }
+  {
     Prof prof(c, K_PACK);
-    k_pack_obstacle<<<div_up(nc, 256), 256, 0, st>>>((uint32_t)nc, c->cand_row.p, c->cflag.p, c->cflag_off.p, c->row_off.p,
-                                                      c->pl_off.p, c->cpl.p, c->pl.p, c->pl_row.p);
+    k_pack<<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
-  if (ws) {
-    k_pack_self<<<div_up(rows, 128), 128, 0, st>>>(rows, c->n_tr, U, npairs, rb * c->n_tr, re * c->n_tr, c->prm.offset,
-                                                   c->self_ok.p, c->self_pl.p, c->pl_off.p, c->row_nob.p, c->pl.p, c->pl_row.p);
-    TOB_LAUNCH_CHECK(c);
-  }
-  c->ctr.planes += np;
   return 0;
 }
 
-// candidates (c->cand_*, c->row_off, c->n_cand) + row geometry must be current.  Leaves the packed plane CSR.
-// Inter-robot planes need geo.P/box/klo/khi of ALL robots.
+// candidates (c->cand_*, c->row_off, dc->n_cand) + row geometry must be current.  Leaves the packed plane CSR.
+// Inter-robot planes need geo.P/box/klo/khi of ALL robots.  Asynchronous (no host read-back).
 int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self) {
   cudaStream_t st = c->stream;
-  uint64_t nc = c->n_cand;
-  TOB_CUDA(c, c->cpl.ensure(4 * nc + 4));
-  TOB_CUDA(c, c->cflag.ensure(nc + 1));
-  TOB_CUDA(c, c->cflag_off.ensure(nc + 2));
-  if (nc) {
-    NarrowArgs a;
-    a.n_cand = (uint32_t)nc; a.cand_pt = c->cand_pt.p; a.cand_row = c->cand_row.p;
-    a.px = c->px.p; a.py = c->py.p; a.pz = c->pz.p;
-    a.P = c->geo.P.p; a.klo = c->geo.klo.p; a.khi = c->geo.khi.p; a.kdop = c->d_kdop.p;
-    a.dist = c->prm.offset + c->prm.margin; a.offset = c->prm.offset;
-    a.cpl = c->cpl.p; a.cflag = c->cflag.p;
+  TOB_TRY(ensure_query_buffers(c));
+  NarrowArgs a;
+  a.dc = c->dc.p; a.cap = (uint32_t)c->cand_cap; a.cand_pt = c->cand_pt.p; a.cand_row = c->cand_row.p;
+  a.px = c->px.p; a.py = c->py.p; a.pz = c->pz.p;
+  a.P = c->geo.P.p; a.klo = c->geo.klo.p; a.khi = c->geo.khi.p; a.kdop = c->d_kdop.p;
+  a.dist = c->prm.offset + c->prm.margin; a.offset = c->prm.offset;
+  a.cpl = c->cpl.p; a.cflag = c->cflag.p; a.csum = c->csum.p;
+  {
     Prof prof(c, K_NARROW);
-    k_narrow<<<div_up(nc, 128), 128, 0, st>>>(a);
+    k_narrow<<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
-  TOB_TRY(exclusive_scan_u32(c, c->cflag.p, c->cflag_off.p, nc, nullptr));
   bool ws = with_self && c->n_robots() > 1;
   if (ws) TOB_TRY(self_planes(c));
-  c->ctr.dcd_candidates += nc;
-  return pack_rows(c, rb, re, true, ws);
+  return pack_rows(c, rb, re, ws);
 }
 
 // inter-robot planes only (Optimization3D_multi::separate_self on empty lists): geo of ALL robots must be current
 int pack_self_only(tob_ctx* c) {
   const int rows = c->rows_all();
-  TOB_CUDA(c, c->row_off.ensure(rows + 2));
-  TOB_CUDA(c, c->cflag_off.ensure(2));
+  TOB_TRY(ensure_query_buffers(c));
   TOB_CUDA(c, cudaMemsetAsync(c->row_off.p, 0, (rows + 2) * sizeof(uint32_t), c->stream));
-  TOB_CUDA(c, cudaMemsetAsync(c->cflag_off.p, 0, 2 * sizeof(uint32_t), c->stream));
-  c->n_cand = 0;
+  TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->n_cand, 0, sizeof(uint32_t), c->stream));
   TOB_TRY(self_planes(c));
-  return pack_rows(c, 0, c->n_robots(), false, true);
+  return pack_rows(c, 0, c->n_robots(), true);
 }
 
 // caller-provided plane lists (the reference's c_lists/d_lists) for robots [rb,re): offsets over (re-rb)*n_tr rows
@@ -255,6 +351,8 @@ int pack_planes_from_host(tob_ctx* c, int rb, int re, const uint32_t* offsets, c
   cudaStream_t st = c->stream;
   const int rows = c->rows_all(), nloc = (re - rb) * c->n_tr;
   uint64_t np = offsets[nloc];
+  if (np > c->cand_cap) TOB_TRY(grow_cand_capacity(c, np));
+  TOB_TRY(ensure_query_buffers(c));
   std::vector<uint32_t> off(rows + 1), prow(np + 1);
   std::vector<double> pl(4 * np + 4);
   for (int g = 0; g <= rows; g++) {
@@ -266,25 +364,26 @@ int pack_planes_from_host(tob_ctx* c, int rb, int re, const uint32_t* offsets, c
       pl[4 * k] = cc[3 * k]; pl[4 * k + 1] = cc[3 * k + 1]; pl[4 * k + 2] = cc[3 * k + 2]; pl[4 * k + 3] = dd[k];
       prow[k] = rb * c->n_tr + lr;
     }
-  TOB_CUDA(c, c->pl_off.ensure(rows + 2));
-  TOB_CUDA(c, c->pl.ensure(4 * np + 4));
-  TOB_CUDA(c, c->pl_row.ensure(np + 1));
+  uint32_t np32[2] = {(uint32_t)np, (uint32_t)np};
   TOB_CUDA(c, cudaMemcpyAsync(c->pl_off.p, off.data(), (rows + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   TOB_CUDA(c, cudaMemcpyAsync(c->pl.p, pl.data(), (4 * np + 4) * sizeof(double), cudaMemcpyHostToDevice, st));
   TOB_CUDA(c, cudaMemcpyAsync(c->pl_row.p, prow.data(), (np + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  TOB_CUDA(c, cudaMemcpyAsync(&c->dc.p->n_planes, np32, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   TOB_CUDA(c, cudaStreamSynchronize(st));
   c->n_planes = np;
   return 0;
 }
 
 // ---- CCD ladder vs the cloud -----------------------------------------------------------------------------------
+// Fused with the swept-box traversal (bp.cuh): the line search needs only max_k over all (sub-segment, point) pairs of
+// the 0.8^k ladder exponent, not a candidate list, so every lane whose point passes the leaf predicate runs the CCD
+// test in place (swept 49-DOP gate, then GJK on hull(P U P+sD) down the ladder) and atomicMax-es the exponent of its
+// robot.  No count / scan / fill, no candidate buffer, no host read-back.
 struct CcdArgs {
-  uint32_t n_cand;
-  const uint32_t *cand_pt, *cand_row;
-  const double *px, *py, *pz;
-  const double *P, *D, *klo, *khi, *kdop, *steps;
+  BpArgs bp;
+  const double *P, *D, *kdop, *steps;
   double offset;
-  int n_tr, first_robot;
+  int n_tr;
   int* kmax;   // per robot
 };
 
@@ -296,51 +395,60 @@ __device__ __forceinline__ void moved_points(const double (*P)[3], const double 
     }
 }
 
-__global__ void __launch_bounds__(128) k_ccd(CcdArgs a) {
+__global__ void __launch_bounds__(BP_THREADS) k_bp_ccd(CcdArgs a) {
+  __shared__ BpShared s;
   __shared__ double s_kdop[3 * TOB_KDOP_AXES];
   for (int i = threadIdx.x; i < 3 * TOB_KDOP_AXES; i += blockDim.x) s_kdop[i] = a.kdop[i];
-  __syncthreads();
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n_cand) return;
-  uint32_t row = a.cand_row[i], p = a.cand_pt[i];
-  int robot = row / a.n_tr;
-  double q[1][3] = {{a.px[p], a.py[p], a.pz[p]}};
-  double P[6][3], D[6][3], A[12][3];
-  load_pts6(a.P + (size_t)18 * row, P);
-  load_pts6(a.D + (size_t)18 * row, D);
-  int k = *((volatile int*)(a.kmax + robot));
-  double s = a.steps[k];
-  moved_points(P, D, s, A);
-  // CCD::KDOPCCD(P, D, q, offset, 0, step)
-  if (!kdop_overlap<12, 1>(A, q, s_kdop, a.offset)) return;
-  const double d2 = a.offset * a.offset;
-  while (k < TOB_MAX_LADDER) {
-    double v[3];
-    gjk_witness<12, 1>(A, q, v);
-    double dist2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
-    if (!(dist2 <= d2)) break;
-    k++;
-    s = a.steps[k];
-    moved_points(P, D, s, A);
+  uint32_t rank;
+  const uint32_t n_items = bp_prepare(a.bp, s, &rank);   // contains barriers: s_kdop is visible afterwards
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t cnt = 0;
+  for (uint32_t j = w; j < n_items; j += BP_WARPS) {
+    uint32_t h, row, leaf;
+    bp_item(a.bp, s, j, &h, &row, &leaf);
+    double q[1][3];
+    const bool ok = bp_point_test(a.bp, row, leaf * 32 + lane, &q[0][0], &q[0][1], &q[0][2]);
+    cnt += __popc(__ballot_sync(0xffffffffu, ok));
+    if (!ok) continue;
+    const int robot = row / a.n_tr;
+    double P[6][3], D[6][3], A[12][3];
+    load_pts6(a.P + (size_t)18 * row, P);
+    load_pts6(a.D + (size_t)18 * row, D);
+    // Step::position_step carries `step` across pairs; the swept hull shrinks monotonically with the step, so starting
+    // from the current exponent of the robot (a racy but always valid lower bound) gives the same result in any order
+    int k = *((volatile int*)(a.kmax + robot));
+    double st = a.steps[k];
+    moved_points(P, D, st, A);
+    // CCD::KDOPCCD(P, D, q, offset, 0, step)
+    if (!kdop_overlap<12, 1>(A, q, s_kdop, a.offset)) continue;
+    const double d2 = a.offset * a.offset;
+    while (k < TOB_MAX_LADDER) {
+      double v[3];
+      gjk_witness<12, 1>(A, q, v);
+      const double dist2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+      if (!(dist2 <= d2)) break;
+      k++;
+      st = a.steps[k];
+      moved_points(P, D, st, A);
+    }
+    atomicMax(a.kmax + robot, k);
   }
-  atomicMax(a.kmax + robot, k);
+  if (lane == 0 && cnt) atomicAdd(&a.bp.dc->ccd_candidates, (unsigned long long)cnt);
 }
 
-// c->cand_* must hold the swept-box candidates (global rows); c->kmax (per robot) must be zeroed by the caller.
-int ccd_position_steps(tob_ctx* c) {
-  uint64_t nc = c->n_cand;
-  if (nc) {
-    CcdArgs a;
-    a.n_cand = (uint32_t)nc; a.cand_pt = c->cand_pt.p; a.cand_row = c->cand_row.p;
-    a.px = c->px.p; a.py = c->py.p; a.pz = c->pz.p;
-    a.P = c->geo.P.p; a.D = c->geo.D.p; a.klo = c->geo.klo.p; a.khi = c->geo.khi.p; a.kdop = c->d_kdop.p;
-    a.steps = c->d_steps.p; a.offset = c->prm.offset; a.n_tr = c->n_tr; a.first_robot = 0;
-    a.kmax = c->kmax.p;
+// geo.P / geo.D / geo.box (swept) of robots [rb,re) must be current (compute_rows mode 3, which also zeroes kmax).
+int ccd_position_steps(tob_ctx* c, int rb, int re) {
+  if (c->n_pts == 0) return fail_msg(c, "CCD: no point cloud uploaded");
+  TOB_TRY(ensure_query_buffers(c));
+  CcdArgs a;
+  bp_args(c, rb * c->n_tr, (re - rb) * c->n_tr, c->prm.offset, a.bp);
+  a.P = c->geo.P.p; a.D = c->geo.D.p; a.kdop = c->d_kdop.p; a.steps = c->d_steps.p; a.offset = c->prm.offset; a.n_tr = c->n_tr;
+  a.kmax = c->kmax.p;
+  if (a.bp.n_tasks) {
     Prof prof(c, K_CCD);
-    k_ccd<<<div_up(nc, 128), 128, 0, c->stream>>>(a);
+    k_bp_ccd<<<div_up((size_t)a.bp.n_tasks, a.bp.tpc), BP_THREADS, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
-  c->ctr.ccd_candidates += nc;
   return 0;
 }
 
@@ -414,12 +522,12 @@ __global__ void __launch_bounds__(64) k_self_ccd_filter(SelfCcdArgs a) {
 // phase 2 (one thread, sequential like the reference): resolve the colliding pairs in (slot, pair) order.
 // The list is short (pairs that really collide when both robots take their full Newton step); it is sorted first so
 // the result does not depend on the order the filter threads appended it.
-__global__ void k_self_ccd_resolve(SelfCcdArgs a, double* steps_out, int* overflow) {
+__global__ void k_self_ccd_resolve(SelfCcdArgs a, double* steps_out, DevCounts* dc) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   for (int u = 0; u < a.U; u++) steps_out[u] = 1.0;
   int kshared = 0;
   uint32_t nh = a.hit[a.cap];
-  if (nh > a.cap) { *overflow = 1; nh = a.cap; }
+  if (nh > a.cap) { dc->overflow |= TOB_OVF_SELFHITS; nh = a.cap; }
   for (uint32_t i = 1; i < nh; i++) {          // insertion sort
     uint32_t v = a.hit[i];
     int j = (int)i - 1;
@@ -474,7 +582,7 @@ int self_ccd_steps(tob_ctx* c, int coupled, double* steps_dev) {
     k_self_ccd_filter<<<div_up(n, 64), 64, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
-  k_self_ccd_resolve<<<1, 32, 0, c->stream>>>(a, steps_dev, (int*)(c->self_hits.p + cap + 1));
+  k_self_ccd_resolve<<<1, 32, 0, c->stream>>>(a, steps_dev, c->dc.p);
   TOB_LAUNCH_CHECK(c);
   c->ctr.self_pairs += n;
   return 0;

@@ -20,6 +20,7 @@ struct RowArgs {
   const double* kdop;     // 147
   double *P, *D, *box, *klo, *khi;
   int n_tr, res, T, row_begin, row_end, mode;
+  int* kmax;              // mode & 2: per-robot CCD ladder exponent, reset here for the fused CCD kernel
 };
 
 __global__ void __launch_bounds__(128) k_rows(RowArgs a) {
@@ -30,6 +31,7 @@ __global__ void __launch_bounds__(128) k_rows(RowArgs a) {
   const int robot = live ? row / a.n_tr : 0, tr = live ? row - robot * a.n_tr : 0;
   const int piece = tr / a.res;
   const double* B = a.basis + (size_t)36 * tr;
+  if (live && (a.mode & 2) && a.kmax && tr == 0 && lane == 0) a.kmax[robot] = 0;
   if (live && lane < 18) {
     int m = lane % 6, ax = lane / 6;
     size_t g = (size_t)robot * 3 * a.T + (size_t)ax * a.T + 3 * piece + m;
@@ -97,6 +99,7 @@ int compute_rows(tob_ctx* c, const double* spline_dev, const double* dir_dev, co
   a.basis = c->d_basis.p; a.kdop = c->d_kdop.p;
   a.P = c->geo.P.p; a.D = c->geo.D.p; a.box = c->geo.box.p; a.klo = c->geo.klo.p; a.khi = c->geo.khi.p;
   a.n_tr = c->n_tr; a.res = c->prm.res; a.T = c->T; a.row_begin = rb * c->n_tr; a.row_end = re * c->n_tr; a.mode = mode;
+  a.kmax = c->kmax.p;
   if (re > rb) {
     Prof prof(c, K_ROWS);
     k_rows<<<div_up((re - rb) * c->n_tr, 4), 128, 0, c->stream>>>(a);

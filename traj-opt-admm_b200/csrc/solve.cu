@@ -617,6 +617,7 @@ struct SlackArgs {
   double *pslack, *tslack, *plambda, *tlambda;
   double mu, ks, kt;
   int P, T, robot_begin, n;
+  DevCounts* guard;   // non-null: skip when the iteration cannot be committed, else count it in guard->iters_done
 };
 
 struct SlackWarp {       // per-warp shared scratch
@@ -718,11 +719,42 @@ __device__ void warp_chol_solve(const double* L, int n, double* v) {
   }
 }
 
+// reduced Newton system of one piece (N = 19, or 13 at the two ends): Cholesky with the reference's eigenvalue-shift fall-back
+// (Optimization3D_admm.h:313-327), then x = H^-1 g.  S.A holds the reduced matrix (col-major, ld N) on entry and L on exit.
+template <int N>
+__device__ __forceinline__ void slack_newton_solve(SlackWarp& S) {
+  const int lane = threadIdx.x & 31;
+  double r[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) r[j] = lane < N ? S.A[lane + N * j] : 0.0;
+  const double b = lane < N ? S.x[lane] : 0.0;
+  double* L = S.H;                         // the full 19x19 Hessian has been consumed: its storage takes the factor
+  if (!warp_chol_roll<N>(r, L)) {
+#pragma unroll
+    for (int j = 0; j < N; j++) r[j] = lane < N ? S.A[lane + N * j] : 0.0;
+    const double mn = warp_min_eig_roll<N>(r, S.ws, S.ws + 19);
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      double v = lane < N ? S.A[lane + N * j] : 0.0;
+      if (lane == j && mn < 0) v = v - mn * 1.0 + 0.01 * 1.0;
+      r[j] = v;
+    }
+    __syncwarp();
+    warp_chol_roll<N>(r, L);
+  }
+  __syncwarp();
+  const double x = warp_chol_solve_sm<N>(L, b);
+  if (lane < N) S.x[lane] = x;
+  __syncwarp();
+}
+
 #define SLACK_WARPS 4
 __global__ void __launch_bounds__(32 * SLACK_WARPS) k_slack(SlackArgs a) {
   __shared__ SlackWarp sm[SLACK_WARPS];
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const int idx = blockIdx.x * SLACK_WARPS + wp;
+  if (iteration_blocked(a.guard)) return;                     // uniform over the grid: nothing in this kernel changes it
+  if (a.guard && blockIdx.x == 0 && threadIdx.x == 0) a.guard->iters_done++;
   if (idx >= a.n) return;                                     // whole warp leaves together
   SlackWarp& S = sm[wp];
   const int robot = a.robot_begin + idx / a.P, sp = idx % a.P;
@@ -753,24 +785,9 @@ __global__ void __launch_bounds__(32 * SLACK_WARPS) k_slack(SlackArgs a) {
   for (int e = lane; e < n * n; e += 32) { const int i = e % n, j = e / n; S.A[e] = S.H[GI(i) + 19 * GI(j)]; }
   if (lane < n) { S.b[lane] = S.g[GI(lane)]; S.x[lane] = S.b[lane]; }
   __syncwarp();
-  if (!warp_chol_is_spd(S.A, n)) {
-    __syncwarp();
-    for (int e = lane; e < n * n; e += 32) { const int i = e % n, j = e / n; S.A[e] = S.H[GI(i) + 19 * GI(j)]; }
-    __syncwarp();
-    const double mn = warp_min_eig(S.A, n, S.ws, S.ws + 19, S.ws + 38, S.ws + 57);
-    __syncwarp();
-    for (int e = lane; e < n * n; e += 32) {
-      const int i = e % n, j = e / n;
-      double v = S.H[GI(i) + 19 * GI(j)];
-      if (i == j && mn < 0) v = v - mn * 1.0 + 0.01 * 1.0;
-      S.A[e] = v;
-    }
-    __syncwarp();
-    warp_chol_is_spd(S.A, n);
-  }
 #undef GI
-  __syncwarp();
-  warp_chol_solve(S.A, n, S.x);                                // x = H^-1 g ; the Newton step is -x
+  if (n == 19) slack_newton_solve<19>(S);
+  else slack_newton_solve<13>(S);                               // x = H^-1 g ; the Newton step is -x
   double wl = (lane < n) ? S.x[lane] * S.b[lane] : 0.0;
   const double wolfe = wsum(wl);                               // = -(-x).g
   if (lane < 3 * tn) S.dir[(sp == 0 ? 6 : 0) + lane] = -S.x[lane];
@@ -802,8 +819,9 @@ __global__ void __launch_bounds__(32 * SLACK_WARPS) k_slack(SlackArgs a) {
   }
 }
 
-int slack_update(tob_ctx* c, int rb, int re) {
+int slack_update(tob_ctx* c, int rb, int re, int guarded) {
   SlackArgs a;
+  a.guard = guarded ? c->dc.p : nullptr;
   a.spline = c->s_spline.p; a.ptime = c->s_ptime.p; a.convert = c->d_convert.p; a.mdyn = c->d_mdyn.p;
   a.pslack = c->s_pslack.p; a.tslack = c->s_tslack.p; a.plambda = c->s_plambda.p; a.tlambda = c->s_tlambda.p;
   a.mu = c->prm.mu; a.ks = c->prm.ks; a.kt = c->prm.kt; a.P = c->prm.piece_num; a.T = c->T; a.robot_begin = rb;

@@ -33,7 +33,7 @@ class TobState(C.Structure):
 class TobCounters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("dcd_candidates", C.c_uint64), ("planes", C.c_uint64),
                 ("ccd_candidates", C.c_uint64), ("energy_plane_evals", C.c_uint64), ("self_pairs", C.c_uint64),
-                ("line_search_trials", C.c_uint64)]
+                ("line_search_trials", C.c_uint64), ("barrier_terms", C.c_uint64)]
 
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_void_p)
@@ -63,10 +63,13 @@ def load_library():
 class _HostState:
     """keeps the numpy buffers a tob_state points to alive"""
 
-    def __init__(self, st):
-        self.spline = F(st["spline"]); self.pt = np.array([st["piece_time"]], dtype=np.float64)
-        self.p_slack = F(st["p_slack"]); self.t_slack = F(st["t_slack"])
-        self.p_lambda = F(st["p_lambda"]); self.t_lambda = F(st["t_lambda"])
+    def __init__(self, st, inplace=False):
+        # inplace: the caller's own column-major float64 arrays are handed to the library and updated in place (what a C++
+        # caller does with its Eigen matrices); otherwise private copies are made and the inputs stay untouched
+        G = (lambda a: a if (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.f_contiguous) else F(a)) if inplace else F
+        self.spline = G(st["spline"]); self.pt = np.array([st["piece_time"]], dtype=np.float64)
+        self.p_slack = G(st["p_slack"]); self.t_slack = G(st["t_slack"])
+        self.p_lambda = G(st["p_lambda"]); self.t_lambda = G(st["t_lambda"])
         self.c = TobState(_d(self.spline), _d(self.pt), _d(self.p_slack), _d(self.t_slack), _d(self.p_lambda), _d(self.t_lambda))
 
     def to_dict(self, **extra):
@@ -264,19 +267,19 @@ class Solver:
         self._ck(self.lib.tob_update_slack_lambda(self.ctx, C.byref(hs.c)))
         return hs.to_dict()
 
-    def _states(self, sts):
-        hss = [_HostState(s) for s in sts]
+    def _states(self, sts, inplace=False):
+        hss = [_HostState(s, inplace) for s in sts]
         arr = (TobState * len(hss))(*[h.c for h in hss])
         return hss, arr
 
-    def optimization(self, st, mode=0, coupled=False):
+    def optimization(self, st, mode=0, coupled=False, inplace=False):
         """host in / host out, the shape of Optimization3D_admm::optimization / _multi::optimization_decouple;
         coupled=True (mode 1): Optimization3D_multi::optimization, one shared piece time"""
         if coupled:
             mode = 1
         single = isinstance(st, dict)
         sts = [st] if single else st
-        hss, arr = self._states(sts)
+        hss, arr = self._states(sts, inplace)
         gn = C.c_double(0)
         self._ck(self.lib.tob_optimization(self.ctx, arr, C.c_int(len(sts)), C.c_int(mode), C.byref(gn)))
         out = [h.to_dict(gnorm=gn.value) for h in hss]
