@@ -65,6 +65,11 @@ int tob_get_tables(const tob_ctx* ctx, double* basis, double* weight, double* co
 /* ---- point cloud (replaces BVH::InitPointcloud, BVH/BVH.cpp:53-92) ------------------------------------------ */
 /* V: n x 3 column-major.  Builds the Morton-sorted 32-wide LBVH on the device. */
 int tob_cloud_upload(tob_ctx* ctx, const double* V, uint32_t n);
+/* Batched independent problems (one BVH::InitPointcloud per problem): cloud b (n[b] x 3 column-major at V[b]) belongs to
+ * robot slot b, n_clouds == tob_params.uav_num.  The clouds are concatenated on the device (each padded to a multiple of
+ * 1024 points) and every row only walks the level-1 nodes of its own cloud.  Use with mode 2 of tob_admm_iterate /
+ * tob_optimization; call after tob_set_params.  Point ids returned by the broadphase entry points are cloud-local. */
+int tob_cloud_upload_batch(tob_ctx* ctx, const double* const* V, const uint32_t* n, int n_clouds);
 uint32_t tob_cloud_size(const tob_ctx* ctx);
 
 /* ---- broadphase (replaces BVH::DCDCollision :149-192, BVH::CCDCollision :195-249) --------------------------- */
@@ -185,8 +190,9 @@ int tob_slack_terms(tob_ctx* ctx, const double* c_spline, double piece_time, con
  * tob_states_upload / download move the n_robots states between host and the context;
  * tob_admm_iterate runs `iters` iterations of Optimization3D_admm::optimization (:29-67) when n_robots == 1, of
  * Optimization3D_multi::optimization_decouple (Optimization3D_multi.h:29-118) when n_robots > 1 (mode 0) or of
- * ::optimization (coupled, :120-174) (mode 1).  gnorm receives the reference's global `gnorm` after the last
- * iteration.  Mode 1 shares ONE piece time: states[u].piece_time may all point to the same double.  Robot ownership for
+ * ::optimization (coupled, :120-174) (mode 1); mode 2 treats the n_robots slots as INDEPENDENT single-UAV problems (each one
+ * iterates like Optimization3D_admm::optimization against its own cloud, no inter-robot terms; gnorm = mean over the
+ * problems).  gnorm receives the reference's global `gnorm` after the last iteration.  Mode 1 shares ONE piece time: states[u].piece_time may all point to the same double.  Robot ownership for
  * multi-GPU: see tob_set_shard() (mode 0 only). */
 int tob_states_upload(tob_ctx* ctx, const tob_state* states, int n_robots);
 int tob_states_download(tob_ctx* ctx, tob_state* states, int n_robots);

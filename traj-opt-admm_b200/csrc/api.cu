@@ -310,7 +310,7 @@ static int ensure_iter_buffers(tob_ctx* c) {
   TOB_CUDA(c, c->geo.klo.ensure(TOB_KDOP_AXES * rows)); TOB_CUDA(c, c->geo.khi.ensure(TOB_KDOP_AXES * rows));
   TOB_CUDA(c, c->row_e.ensure(2 * rows * TOB_LS_TRIALS)); TOB_CUDA(c, c->row_bad.ensure(rows * TOB_LS_TRIALS));
   TOB_CUDA(c, c->pc_g.ensure(19 * U * P)); TOB_CUDA(c, c->pc_h.ensure(361 * U * P)); TOB_CUDA(c, c->pc_flag.ensure(U * P));
-  if (U > 1) {
+  if (U > 1 && c->cloud_n1.empty()) {   // inter-robot scratch (never used by independent problems)
     const size_t n = (size_t)c->n_tr * (U * (U - 1) / 2);
     TOB_CUDA(c, c->self_pl.ensure(4 * n + 4)); TOB_CUDA(c, c->self_ok.ensure(n + 1));
     TOB_CUDA(c, c->self_hits.ensure(16384 + 2));
@@ -322,13 +322,16 @@ static int ensure_iter_buffers(tob_ctx* c) {
 // dual update) is guarded on the device by dc->overflow / dc->ls_pending and the caller inspects dc afterwards;
 // otherwise (sharded multi-GPU: collectives in the middle must stay matched across ranks) the host checks as it goes.
 static int iterate_launch(tob_ctx* c, int mode, bool deferred) {
-  const int U = c->n_robots(), rb = c->own_begin, re = c->own_end;
+  const int rb = c->own_begin, re = c->own_end;
+  // mode 2: the robot slots hold INDEPENDENT single-UAV problems (no inter-robot terms, no exchange): everything below that
+  // is conditional on "several robots" sees one robot
+  const int U = mode == 2 ? 1 : c->n_robots();
   cudaStream_t st = c->stream;
   const bool coupled = mode == 1;
   // (1) control points of every robot are needed for the inter-robot planes
   if (U > 1) TOB_TRY(exchange(c, c->s_spline, (size_t)3 * c->T));
-  if (deferred) TOB_TRY(separate_resident(c, rb, re, 1));
-  else TOB_TRY(run_checked(c, [&]() { return separate_resident(c, rb, re, 1); }));
+  if (deferred) TOB_TRY(separate_resident(c, rb, re, U > 1));
+  else TOB_TRY(run_checked(c, [&]() { return separate_resident(c, rb, re, U > 1); }));
   // (2) Newton direction (geo.P of the owned rows is still current from the plane pass)
   TOB_TRY(gradient_blocks(c, rb, re, 1));
   if (coupled) TOB_TRY(solve_coupled(c));
@@ -348,7 +351,7 @@ static int iterate_launch(tob_ctx* c, int mode, bool deferred) {
   int wolfe_idx = -1;
   if (coupled) {
     if (U == 1) { double one = 1.0; TOB_TRY(upload(c, c->s_selfstep, &one, 1)); }
-    k_ls_init_coupled<<<1, 32, 0, st>>>(U, c->kmax.p, c->d_steps.p, c->s_selfstep.p, c->s_ptime.p, c->s_tdir.p, c->s_step.p,
+    k_ls_init_coupled<<<1, 32, 0, st>>>(c->n_robots(), c->kmax.p, c->d_steps.p, c->s_selfstep.p, c->s_ptime.p, c->s_tdir.p, c->s_step.p,
                                         c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p);
     TOB_LAUNCH_CHECK(c);
     wolfe_idx = 0;
@@ -377,7 +380,7 @@ static void graph_drop(tob_ctx* c) {
 
 // Launch one deferred iteration: through the captured CUDA graph when the buffers have not moved since the capture.
 static int iterate_submit(tob_ctx* c, int mode) {
-  const bool can_graph = c->use_graph && !c->prof_on && !c->ag && mode == 0;
+  const bool can_graph = c->use_graph && !c->prof_on && !c->ag && (mode == 0 || mode == 2);
   if (!can_graph) return iterate_launch(c, mode, true);
   if (c->graph_exec && (c->graph_gen != alloc_generation() || c->graph_mode != mode)) graph_drop(c);
   if (!c->graph_exec) {
@@ -414,17 +417,18 @@ static int iterate_submit(tob_ctx* c, int mode) {
   TOB_CUDA(c, cudaGraphLaunch(c->graph_exec, c->stream));
   c->ctr.kernel_launches += c->graph_nodes;
   c->ctr.line_search_trials += (uint64_t)(c->own_end - c->own_begin) * (TOB_LS_TRIALS - 1) * TOB_LS_ROUNDS;
-  if (c->n_robots() > 1) c->ctr.self_pairs += (uint64_t)2 * c->n_tr * (c->n_robots() * (c->n_robots() - 1) / 2);
+  if (c->n_robots() > 1 && mode != 2) c->ctr.self_pairs += (uint64_t)2 * c->n_tr * (c->n_robots() * (c->n_robots() - 1) / 2);
   return 0;
 }
 
 static int iterate_once(tob_ctx* c, int mode, double* gnorm_out) {
   const int U = c->n_robots(), rb = c->own_begin, re = c->own_end;
   const bool coupled = mode == 1;
-  if (mode != 0 && mode != 1) return fail_msg(c, "tob_admm_iterate: mode must be 0 (decoupled) or 1 (coupled)");
+  if (mode < 0 || mode > 2) return fail_msg(c, "tob_admm_iterate: mode must be 0 (decoupled), 1 (coupled) or 2 (independent problems)");
+  if (mode != 2 && !c->cloud_n1.empty() && U > 1) return fail_msg(c, "per-robot clouds (tob_cloud_upload_batch) go with mode 2 (independent problems)");
   if (coupled && (c->ag || rb != 0 || re != U)) return fail_msg(c, "coupled mode is not sharded: run it on one context holding all robots");
   TOB_TRY(ensure_iter_buffers(c));
-  const int wolfe_idx = coupled ? 0 : (U > 1 ? U - 1 : -1);
+  const int wolfe_idx = coupled ? 0 : ((U > 1 && mode != 2) ? U - 1 : -1);
   if (c->ag) {
     TOB_TRY(iterate_launch(c, mode, false));
   } else {
@@ -454,7 +458,7 @@ static int iterate_once(tob_ctx* c, int mode, double* gnorm_out) {
     double g = 0;
     const double* hp = c->h_pinned;
     if (U == 1) g = hp[0];
-    else { for (int u = 0; u < U; u++) g += hp[u]; g /= double(U); }
+    else { for (int u = 0; u < U; u++) g += hp[u]; g /= double(U); }   // mode 2: mean over the independent problems
     *gnorm_out = g;
   }
   return 0;
@@ -535,6 +539,10 @@ int tob_set_params(tob_ctx* c, const tob_params* p) {
   c->states_valid = false;
   c->own_begin = 0; c->own_end = p->uav_num;
   c->n_planes = 0;
+  if (!c->cloud_n1.empty()) {      // per-robot clouds are tied to the row layout: upload them again
+    c->cloud_n1.clear(); c->cloud_l1.clear(); c->h_row_task.clear();
+    c->n_pts = 0;
+  }
   return alloc_states(c);
 }
 
@@ -584,6 +592,12 @@ int tob_cloud_upload(tob_ctx* c, const double* V, uint32_t n) {
   if (!c || !V) return 1;
   cudaSetDevice(c->device);
   return lbvh_build(c, V, n);
+}
+int tob_cloud_upload_batch(tob_ctx* c, const double* const* V, const uint32_t* n, int n_clouds) {
+  if (!c || !V || !n) return 1;
+  TOB_TRY(need(c, false, false));
+  cudaSetDevice(c->device);
+  return lbvh_build_batch(c, V, n, n_clouds);
 }
 uint32_t tob_cloud_size(const tob_ctx* c) { return c ? c->n_pts : 0; }
 

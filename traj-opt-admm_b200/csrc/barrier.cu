@@ -452,6 +452,159 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
   }
 }
 
+// ---- block-cooperative PSD projection of one 19x19 block (Gradient_admm.h:40-53) ------------------------------------------
+// A single warp walking the 19 pivots runs at ~10 cycles per instruction (nothing to overlap with), which made this step
+// 60 % of k_piece.  Here the 384 threads of the CTA share it:
+//   Cholesky test   thread per element, one barrier per pivot (the pivot column is double-buffered in shared memory);
+//                   same operands as Eigen's unblocked LLT: fails when a pivot is <= 0
+//   lambda_min      (only when the test fails) Householder tridiagonalisation with rows spread over the 12 warps (two rows
+//                   per warp, row sums by shuffles, two barriers per column), then Sturm-count multisection with 384
+//                   shifts per round on the division-free recurrence.
+// Returns 0 = SPD, 1 = shifted by (-lambda_min + 0.01) I in place, 2 = LLT failed but lambda_min >= 0.  All 384 threads call.
+__device__ __noinline__ int cta384_psd_shift19(double* s_H) {
+  constexpr int N = 19, NW = 12;
+  __shared__ double s_col[2][N + 1], s_v[2][N + 1], s_p[2][N + 1], s_d[N + 1], s_e[N + 1], s_sc[2][2];
+  __shared__ int s_first[2][NW];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const unsigned full = 0xffffffffu;
+  {
+    const int i = tid % N, j = tid / N;
+    const bool act = tid < N * N;
+    double aij = act ? s_H[tid] : 0.0;
+    bool spd = true;
+    for (int k = 0; k < N; k++) {
+      double* col = s_col[k & 1];
+      if (act && j == k && i >= k) col[i] = aij;
+      __syncthreads();
+      const double x = col[k];
+      if (!(x > 0)) { spd = false; break; }               // uniform
+      if (act && j > k && i >= j) {
+        const double lkk = sqrt(x);
+        aij -= (col[i] / lkk) * (col[j] / lkk);
+      }
+    }
+    if (spd) return 0;
+  }
+  __syncthreads();
+  // ---- tridiagonalisation: warp w keeps rows w and w+12, lane = column
+  const int rw1 = w + NW;
+  double r0 = lane < N ? s_H[w + N * lane] : 0.0;
+  double r1 = (rw1 < N && lane < N) ? s_H[rw1 + N * lane] : 0.0;
+  for (int k = 0; k + 2 < N; k++) {
+    const int b = k & 1;
+    if (w == k % NW) {                                     // owner of row k publishes v = A(k, k+1..), |v|^2 and A(k,k)
+      const double rk = k < NW ? r0 : r1;
+      const double xi = (lane > k && lane < N) ? rk : 0.0;
+      double sg = xi * xi;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) sg += __shfl_xor_sync(full, sg, o);
+      if (lane < N) s_v[b][lane] = xi;
+      if (lane == k) { s_sc[b][0] = sg; s_sc[b][1] = rk; }
+    }
+    __syncthreads();
+    const double sigma = s_sc[b][0], akk = s_sc[b][1], x0 = s_v[b][k + 1];
+    const double tail = sigma - x0 * x0;
+    if (tid == 0) s_d[k] = akk;
+    if (!(tail > 0)) {                                     // column already tridiagonal (uniform)
+      if (tid == 0) s_e[k] = x0;
+      continue;
+    }
+    const double alpha = (x0 >= 0 ? -1.0 : 1.0) * sqrt(sigma);
+    const double vk1 = x0 - alpha;
+    const double vl = lane == k + 1 ? vk1 : (lane < N ? s_v[b][lane] : 0.0);
+    const double beta = 2.0 / (tail + vk1 * vk1);
+    double p0 = r0 * vl, p1 = r1 * vl;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      p0 += __shfl_xor_sync(full, p0, o);
+      p1 += __shfl_xor_sync(full, p1, o);
+    }
+    p0 = w > k ? p0 * beta : 0.0;
+    p1 = (rw1 > k && rw1 < N) ? p1 * beta : 0.0;
+    if (lane == 0) {
+      s_p[b][w] = p0;
+      if (rw1 < N) s_p[b][rw1] = p1;
+    }
+    __syncthreads();
+    double kk = 0;
+    for (int i = 0; i < N; i++) kk += s_p[b][i] * (i == k + 1 ? vk1 : s_v[b][i]);
+    kk *= 0.5 * beta;
+    const double wl = lane < N ? s_p[b][lane] - kk * vl : 0.0;
+    const double v0 = w == k + 1 ? vk1 : s_v[b][w], w0 = s_p[b][w] - kk * v0;
+    double v1 = 0, w1 = 0;
+    if (rw1 < N) { v1 = rw1 == k + 1 ? vk1 : s_v[b][rw1]; w1 = s_p[b][rw1] - kk * v1; }
+    if (lane > k && lane < N) {
+      if (w > k) r0 -= v0 * wl + w0 * vl;
+      if (rw1 > k && rw1 < N) r1 -= v1 * wl + w1 * vl;
+    }
+    if (tid == 0) s_e[k] = alpha;
+  }
+  // trailing 2x2: rows 17 (warp 5, second slot) and 18 (warp 6, second slot)
+  if (w == (N - 2) - NW) {
+    if (lane == N - 2) s_d[N - 2] = r1;
+    if (lane == N - 1) s_e[N - 2] = r1;
+  }
+  if (w == (N - 1) - NW && lane == N - 1) { s_d[N - 1] = r1; s_e[N - 1] = 0.0; }
+  __syncthreads();
+  // Gershgorin lower bound; lambda_min <= min d_i
+  double lo = INFINITY, hi = INFINITY;
+  if (lane < N) {
+    const double r = fabs(s_e[lane]) + (lane > 0 ? fabs(s_e[lane - 1]) : 0.0);
+    lo = s_d[lane] - r;
+    hi = s_d[lane];
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(full, lo, o));
+    hi = fmin(hi, __shfl_xor_sync(full, hi, o));
+  }
+  double mn = hi;
+  if (hi > lo) {
+    constexpr int NT = 32 * NW;
+    for (int round = 0; round < 8; round++) {
+      const int b = round & 1;
+      const double x = lo + (hi - lo) * ((tid + 1) / (double)(NT + 1));
+      int cnt = 0;
+      double q0 = 1.0, q1 = s_d[0] - x;
+      bool neg = q1 < 0;                                   // sign of the last non-zero term
+      if (neg) cnt++;
+#pragma unroll 1
+      for (int i = 1; i < N; i++) {
+        const double ei = s_e[i - 1];
+        double q2 = (s_d[i] - x) * q1 - (ei * ei) * q0;
+        const double m = fabs(q2);
+        if (m > 1e150) { q2 *= 1e-150; q1 *= 1e-150; }
+        else if (m < 1e-150 && m > 0) { q2 *= 1e150; q1 *= 1e150; }
+        if (q2 != 0) {
+          const bool n2 = q2 < 0;
+          if (n2 != neg) cnt++;
+          neg = n2;
+        }
+        q0 = q1; q1 = q2;
+      }
+      const unsigned mk = __ballot_sync(full, cnt >= 1);
+      if (lane == 0) s_first[b][w] = mk ? w * 32 + (__ffs(mk) - 1) : -1;
+      __syncthreads();
+      int f = -1;
+      for (int ww = 0; ww < NW; ww++)
+        if (s_first[b][ww] >= 0) { f = s_first[b][ww]; break; }
+      const double width = hi - lo, base = lo;
+      if (f < 0) lo = base + width * (NT / (double)(NT + 1));
+      else {
+        hi = base + width * ((f + 1) / (double)(NT + 1));
+        if (f > 0) lo = base + width * (f / (double)(NT + 1));
+      }
+      if (!(hi > lo)) break;
+    }
+    mn = 0.5 * (lo + hi);
+  }
+  if (mn < 0) {
+    if (tid < N) s_H[tid * (N + 1)] = s_H[tid * (N + 1)] - mn * 1.0 + 0.01 * 1.0;
+    return 1;
+  }
+  return 2;
+}
+
 // ---- gradient: per-piece 19x19 block -----------------------------------------------------------------------------
 struct PieceArgs {
   const double *terms, *basis, *convert;
@@ -558,24 +711,10 @@ __global__ void __launch_bounds__(384) k_piece(PieceArgs a) {
     G[r] = v;
   }
   __syncthreads();
-  // PSD projection of Gradient_admm.h:40-53 by warp 0 (rows in registers, shuffles): Cholesky test, then
-  // h0 += (-lambda_min + 0.01) I if needed
-  if (a.project_psd && threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    double r[19];
-#pragma unroll
-    for (int j = 0; j < 19; j++) r[j] = lane < 19 ? s_H[lane + 19 * j] : 0.0;
-    int flag = 0;
-    if (!warp_chol_roll<19>(r, nullptr)) {
-#pragma unroll
-      for (int j = 0; j < 19; j++) r[j] = lane < 19 ? s_H[lane + 19 * j] : 0.0;
-      const double mn = warp_min_eig_roll<19>(r, s_a, s_a + 19);   // s_a is free by now (>= 38 doubles)
-      if (mn < 0) {
-        if (lane < 19) s_H[lane * 20] = s_H[lane * 20] - mn * 1.0 + 0.01 * 1.0;
-        flag = 1;
-      } else flag = 2;
-    }
-    if (lane == 0) a.pc_flag[pb] = flag;
+  // PSD projection of Gradient_admm.h:40-53 by the whole CTA
+  if (a.project_psd) {
+    const int flag = cta384_psd_shift19(s_H);
+    if (threadIdx.x == 0) a.pc_flag[pb] = flag;
   }
   __syncthreads();
   for (int e = threadIdx.x; e < 361; e += blockDim.x) a.pc_h[361 * pb + e] = s_H[e];

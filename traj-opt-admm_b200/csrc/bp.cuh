@@ -33,10 +33,15 @@ struct BpArgs {
   uint32_t *cand_pt, *cand_row, *row_off;
   uint32_t cand_cap;
   DevCounts* dc;
+  // one cloud per robot (batched independent problems): row r walks level-1 nodes [row_l1[r], row_l1[r] + n1(r)) and its
+  // tasks are [row_task[r], row_task[r+1]); null = one shared cloud, n1 nodes for every row
+  const uint32_t *row_task, *row_l1;
 };
 
 struct BpShared {
   uint32_t hit_task[BP_THREADS];      // local task index of the h-th hit task
+  uint32_t hit_row[BP_THREADS];       // its global row
+  uint32_t hit_nd[BP_THREADS];        // its level-1 node (global index)
   uint32_t lmask[BP_THREADS];         // its leaf mask
   uint32_t item_base[BP_THREADS + 1]; // exclusive prefix of popc(lmask)
   uint32_t wtmp[BP_WARPS + 1];
@@ -110,28 +115,48 @@ __device__ __forceinline__ uint32_t cta1024_scan_inplace(uint32_t* v, uint32_t n
   return carry;
 }
 
+// task (relative to the first queried row) -> global row, global level-1 node, "first node of its row"
+__device__ __forceinline__ void bp_task(const BpArgs& a, uint32_t t, uint32_t* row, uint32_t* nd, bool* first) {
+  if (a.row_task == nullptr) {
+    const uint32_t r = t / a.n1;
+    *row = a.row_base + r;
+    *nd = t - r * a.n1;
+    *first = t == r * a.n1;
+    return;
+  }
+  const uint32_t tg = t + a.row_task[a.row_base];
+  uint32_t lo = a.row_base, hi = a.row_base + a.rows;      // largest row with row_task[row] <= tg
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (a.row_task[mid] <= tg) lo = mid; else hi = mid;
+  }
+  *row = lo;
+  *nd = a.row_l1[lo] + (tg - a.row_task[lo]);
+  *first = tg == a.row_task[lo];
+}
+
 // phases A + B + item prefix.  Returns the number of items of this CTA; *my_rank = hit tasks before this thread's task.
 __device__ __forceinline__ uint32_t bp_prepare(const BpArgs& a, BpShared& s, uint32_t* my_rank) {
   const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t t = blockIdx.x * a.tpc + tid;
   bool hit = false;
+  uint32_t row = 0, nd = 0;
   if (tid < a.tpc && t < a.n_tasks) {
-    const uint32_t r = t / a.n1, nd = t - r * a.n1;
-    const double* q = a.box + (size_t)6 * (a.row_base + r);
+    bool first;
+    bp_task(a, t, &row, &nd, &first);
+    const double* q = a.box + (size_t)6 * row;
     hit = box_hit(a.l1lo[0][nd], a.l1hi[0][nd], q[0], q[3], a.d) && box_hit(a.l1lo[1][nd], a.l1hi[1][nd], q[1], q[4], a.d) &&
           box_hit(a.l1lo[2][nd], a.l1hi[2][nd], q[2], q[5], a.d);
   }
   uint32_t n_hit;
   const uint32_t rank = bp_block_excl(hit ? 1u : 0u, s.wtmp, &n_hit);
   *my_rank = rank;
-  if (hit) s.hit_task[rank] = tid;
+  if (hit) { s.hit_task[rank] = tid; s.hit_row[rank] = row; s.hit_nd[rank] = nd; }
   if (tid == 0) s.n_hit = n_hit;
   __syncthreads();
   for (uint32_t h = w; h < n_hit; h += BP_WARPS) {
-    const uint32_t tt = blockIdx.x * a.tpc + s.hit_task[h];
-    const uint32_t r = tt / a.n1, nd = tt - r * a.n1;
-    const double* q = a.box + (size_t)6 * (a.row_base + r);
-    const uint32_t leaf = nd * 32 + lane;   // level-0 arrays are padded to 32 with empty boxes
+    const double* q = a.box + (size_t)6 * s.hit_row[h];
+    const uint32_t leaf = s.hit_nd[h] * 32 + lane;   // level-0 arrays are padded to 32 with empty boxes
     const bool lh = box_hit(a.l0lo[0][leaf], a.l0hi[0][leaf], q[0], q[3], a.d) && box_hit(a.l0lo[1][leaf], a.l0hi[1][leaf], q[1], q[4], a.d) &&
                     box_hit(a.l0lo[2][leaf], a.l0hi[2][leaf], q[2], q[5], a.d);
     const uint32_t lm = __ballot_sync(0xffffffffu, lh);
@@ -155,11 +180,9 @@ __device__ __forceinline__ void bp_item(const BpArgs& a, const BpShared& s, uint
   }
   const uint32_t k = j - s.item_base[lo];
   const uint32_t lb = __fns(s.lmask[lo], 0, k + 1);
-  const uint32_t tt = blockIdx.x * a.tpc + s.hit_task[lo];
-  const uint32_t r = tt / a.n1, nd = tt - r * a.n1;
   *h_out = lo;
-  *row = a.row_base + r;
-  *leaf = nd * 32 + lb;
+  *row = s.hit_row[lo];
+  *leaf = s.hit_nd[lo] * 32 + lb;
 }
 
 // 32 lanes = the 32 points of `leaf` against the box of `row`

@@ -93,6 +93,10 @@ struct tob_ctx {
   tob::DBuf<uint32_t> pid;
   std::vector<uint32_t> h_pid;
   tob::DBuf<double> lvl_store;
+  // batched independent problems: one cloud per robot slot (empty vectors = one cloud shared by all robots)
+  std::vector<uint32_t> cloud_n1, cloud_l1;       // level-1 node count / first level-1 node of each cloud
+  std::vector<uint32_t> h_row_task;
+  tob::DBuf<uint32_t> row_task, row_l1;           // rows+1: exclusive prefix of broadphase tasks per row; first level-1 node
   int n_levels = 0;
   tob::Level lvl[TOB_MAX_LEVELS];
 
@@ -239,6 +243,7 @@ int make_tables_host(const tob_params& p, const double* time_weight, std::vector
                      std::vector<double>& convert, std::vector<double>& mdyn, std::vector<double>& kdop);
 // lbvh.cu
 int lbvh_build(tob_ctx* c, const double* V_host, uint32_t n);
+int lbvh_build_batch(tob_ctx* c, const double* const* V_host, const uint32_t* n, int n_clouds);
 // queries rows [rb*n_tr, re*n_tr) whose boxes are in geo.box; fills cand_pt/cand_row (GLOBAL rows) and row_off.
 // Asynchronous: the total stays on the device (dc->n_cand); count_as = 1 adds it to the dcd_candidates counter.
 int broadphase(tob_ctx* c, int rb, int re, double d, int count_as);

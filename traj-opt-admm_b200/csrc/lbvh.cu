@@ -113,10 +113,10 @@ __global__ void k_level(int from_points, uint32_t n_child, uint32_t n_parent_pad
   }
 }
 
-int lbvh_build(tob_ctx* c, const double* V_host, uint32_t n) {
-  if (n == 0) return fail_msg(c, "tob_cloud_upload: empty cloud");
+// Morton-sort one cloud into the concatenated SoA arrays at point offset `base` (a multiple of 1024); `slot` points are
+// reserved for it (padding = +inf points that can never be candidates).
+static int lbvh_sort_cloud(tob_ctx* c, const double* V_host, uint32_t n, size_t base, uint32_t slot) {
   cudaStream_t st = c->stream;
-  uint32_t n_pad = (n + 31u) & ~31u;
   DBuf<double> V;
   DBuf<uint64_t> key, key2;
   DBuf<uint32_t> idx, idx2;
@@ -124,7 +124,7 @@ int lbvh_build(tob_ctx* c, const double* V_host, uint32_t n) {
   DBuf<uint8_t> tmp;
   TOB_CUDA(c, V.ensure((size_t)3 * n));
   TOB_CUDA(c, cudaMemcpyAsync(V.p, V_host, (size_t)3 * n * sizeof(double), cudaMemcpyHostToDevice, st));
-  const int nb = 296;
+  const int nb = n < 65536 ? 32 : 296;
   TOB_CUDA(c, part.ensure(nb * 6));
   k_minmax<<<nb, 256, 0, st>>>(V.p, n, part.p);
   TOB_LAUNCH_CHECK(c);
@@ -150,16 +150,19 @@ int lbvh_build(tob_ctx* c, const double* V_host, uint32_t n) {
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key.p, key2.p, idx.p, idx2.p, (int)n, 0, 63, st);
   TOB_CUDA(c, tmp.ensure(tmp_bytes));
   TOB_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key.p, key2.p, idx.p, idx2.p, (int)n, 0, 63, st));
-
-  TOB_CUDA(c, c->px.ensure(n_pad)); TOB_CUDA(c, c->py.ensure(n_pad)); TOB_CUDA(c, c->pz.ensure(n_pad));
-  TOB_CUDA(c, c->pid.ensure(n_pad));
-  k_gather<<<div_up(n_pad, 256), 256, 0, st>>>(V.p, n, n_pad, idx2.p, c->px.p, c->py.p, c->pz.p, c->pid.p);
+  k_gather<<<div_up(slot, 256), 256, 0, st>>>(V.p, n, slot, idx2.p, c->px.p + base, c->py.p + base, c->pz.p + base, c->pid.p + base);
   TOB_LAUNCH_CHECK(c);
+  TOB_CUDA(c, cudaStreamSynchronize(st));
+  V.release(); key.release(); key2.release(); idx.release(); idx2.release(); part.release(); tmp.release();
+  return 0;
+}
 
-  // levels: 0 = leaves (32 points), then 32-ary up to a single node
+// levels over the concatenated, padded point array: 0 = leaves (32 points), then 32-ary up to a single node
+static int lbvh_levels(tob_ctx* c, size_t n_pad) {
+  cudaStream_t st = c->stream;
   uint32_t counts[TOB_MAX_LEVELS], pads[TOB_MAX_LEVELS];
   int nl = 0;
-  uint32_t cnt = n_pad / 32;
+  uint32_t cnt = (uint32_t)(n_pad / 32);
   while (true) {
     counts[nl] = cnt;
     pads[nl] = (cnt + 31u) & ~31u;
@@ -180,7 +183,7 @@ int lbvh_build(tob_ctx* c, const double* V_host, uint32_t n) {
   c->n_levels = nl;
   for (int l = 0; l < nl; l++) {
     Level& L = c->lvl[l];
-    uint32_t n_child = (l == 0) ? n_pad : counts[l - 1];
+    uint32_t n_child = (l == 0) ? (uint32_t)n_pad : counts[l - 1];
     const double *a0, *a1, *a2, *b0, *b1, *b2;
     if (l == 0) { a0 = b0 = c->px.p; a1 = b1 = c->py.p; a2 = b2 = c->pz.p; }
     else { Level& C = c->lvl[l - 1]; a0 = C.lo[0]; a1 = C.lo[1]; a2 = C.lo[2]; b0 = C.hi[0]; b1 = C.hi[1]; b2 = C.hi[2]; }
@@ -191,8 +194,61 @@ int lbvh_build(tob_ctx* c, const double* V_host, uint32_t n) {
   c->h_pid.resize(n_pad);
   TOB_CUDA(c, cudaMemcpyAsync(c->h_pid.data(), c->pid.p, n_pad * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   TOB_CUDA(c, cudaStreamSynchronize(st));
+  return 0;
+}
+
+// one cloud shared by every robot of the context (BVH::InitPointcloud)
+int lbvh_build(tob_ctx* c, const double* V_host, uint32_t n) {
+  if (n == 0) return fail_msg(c, "tob_cloud_upload: empty cloud");
+  uint32_t n_pad = (n + 31u) & ~31u;
+  TOB_CUDA(c, c->px.ensure(n_pad)); TOB_CUDA(c, c->py.ensure(n_pad)); TOB_CUDA(c, c->pz.ensure(n_pad));
+  TOB_CUDA(c, c->pid.ensure(n_pad));
+  TOB_TRY(lbvh_sort_cloud(c, V_host, n, 0, n_pad));
+  TOB_TRY(lbvh_levels(c, n_pad));
   c->n_pts = n; c->n_pad = n_pad;
-  V.release(); key.release(); key2.release(); idx.release(); idx2.release(); part.release(); tmp.release();
+  c->cloud_n1.clear(); c->cloud_l1.clear();
+  c->row_task.release(); c->row_l1.release();
+  return 0;
+}
+
+// one cloud per robot slot (batched independent problems): clouds are concatenated, each padded to a multiple of 1024
+// points so that neither a leaf (32 points) nor a level-1 node (32 leaves) straddles two clouds.  Per row the broadphase
+// then walks only the level-1 nodes of its own cloud (row_task / row_l1).
+int lbvh_build_batch(tob_ctx* c, const double* const* V_host, const uint32_t* n, int n_clouds) {
+  if (n_clouds != c->n_robots()) return fail_msg(c, "tob_cloud_upload_batch: one cloud per robot slot (uav_num) is required");
+  size_t total = 0;
+  std::vector<size_t> base(n_clouds);
+  std::vector<uint32_t> slot(n_clouds);
+  for (int b = 0; b < n_clouds; b++) {
+    if (n[b] == 0) return fail_msg(c, "tob_cloud_upload_batch: empty cloud");
+    base[b] = total;
+    slot[b] = (n[b] + 1023u) & ~1023u;
+    total += slot[b];
+  }
+  if (total > 0xfff00000ull) return fail_msg(c, "tob_cloud_upload_batch: more than 2^32 points");
+  TOB_CUDA(c, c->px.ensure(total)); TOB_CUDA(c, c->py.ensure(total)); TOB_CUDA(c, c->pz.ensure(total));
+  TOB_CUDA(c, c->pid.ensure(total));
+  for (int b = 0; b < n_clouds; b++) TOB_TRY(lbvh_sort_cloud(c, V_host[b], n[b], base[b], slot[b]));
+  TOB_TRY(lbvh_levels(c, total));
+  c->n_pts = (uint32_t)total; c->n_pad = (uint32_t)total;
+  c->cloud_n1.resize(n_clouds); c->cloud_l1.resize(n_clouds);
+  for (int b = 0; b < n_clouds; b++) { c->cloud_l1[b] = (uint32_t)(base[b] / 1024); c->cloud_n1[b] = slot[b] / 1024; }
+  // per-row task prefix and level-1 base
+  const int rows = c->rows_all();
+  std::vector<uint32_t> rt(rows + 1), rl(rows + 1);
+  uint64_t acc = 0;
+  for (int r = 0; r < rows; r++) {
+    const int u = r / c->n_tr;
+    rt[r] = (uint32_t)acc; rl[r] = c->cloud_l1[u];
+    acc += c->cloud_n1[u];
+    if (acc > 0xfff00000ull) return fail_msg(c, "tob_cloud_upload_batch: more than 2^32 broadphase tasks");
+  }
+  rt[rows] = (uint32_t)acc; rl[rows] = 0;
+  TOB_CUDA(c, c->row_task.ensure(rows + 1)); TOB_CUDA(c, c->row_l1.ensure(rows + 1));
+  TOB_CUDA(c, cudaMemcpyAsync(c->row_task.p, rt.data(), (rows + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(c->row_l1.p, rl.data(), (rows + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->h_row_task = rt;
   return 0;
 }
 
@@ -300,8 +356,10 @@ __global__ void __launch_bounds__(BP_THREADS) k_bp_fill(BpArgs a) {
   // first task of a row (level-1 node 0): the row's candidate list starts here
   const uint32_t t = blockIdx.x * a.tpc + tid;
   if (tid < a.tpc && t < a.n_tasks) {
-    const uint32_t r = t / a.n1;
-    if (t == r * a.n1) a.row_off[a.row_base + r] = cta_base + s_taskcand[rank];
+    uint32_t row, nd;
+    bool first;
+    bp_task(a, t, &row, &nd, &first);
+    if (first) a.row_off[row] = cta_base + s_taskcand[rank];
   }
 }
 
@@ -314,6 +372,11 @@ int broadphase(tob_ctx* c, int rb, int re, double d, int count_as) {
 void bp_args(tob_ctx* c, int row_base, int rows, double d, BpArgs& a) {
   a.box = c->geo.box.p;
   a.rows = rows; a.n1 = c->lvl[1].count; a.n_tasks = (uint32_t)rows * a.n1; a.d = d; a.row_base = (uint32_t)row_base;
+  a.row_task = nullptr; a.row_l1 = nullptr;
+  if (!c->cloud_n1.empty()) {          // one cloud per robot: only the level-1 nodes of the row's own cloud
+    a.row_task = c->row_task.p; a.row_l1 = c->row_l1.p;
+    a.n_tasks = c->h_row_task[row_base + rows] - c->h_row_task[row_base];
+  }
   a.rows_all = (uint32_t)c->rows_all();
   for (int k = 0; k < 3; k++) {
     a.l1lo[k] = c->lvl[1].lo[k]; a.l1hi[k] = c->lvl[1].hi[k];
@@ -360,8 +423,9 @@ int ensure_query_buffers(tob_ctx* c) {
   if (c->cand_cap == 0) c->cand_cap = 1u << 20;
   const size_t rows = (size_t)c->rows_all(), U = (size_t)c->n_robots();
   const size_t n1 = c->n_levels > 1 ? c->lvl[1].count : 1;
-  const size_t nblk = rows * n1 / 16 + 4 * (size_t)c->sm_count + 2;   // tasks per CTA >= 16
-  const size_t self_max = rows * (U > 1 ? U - 1 : 0);
+  const size_t tasks = c->cloud_n1.empty() ? rows * n1 : (size_t)c->h_row_task[rows];
+  const size_t nblk = tasks / 16 + 4 * (size_t)c->sm_count + 2;   // tasks per CTA >= 16
+  const size_t self_max = c->cloud_n1.empty() ? rows * (U > 1 ? U - 1 : 0) : 0;   // independent problems have no inter-robot planes
   TOB_CUDA(c, c->bsum.ensure(nblk + 1));
   TOB_CUDA(c, c->row_off.ensure(rows + 2));
   TOB_CUDA(c, c->cand_pt.ensure(c->cand_cap + 1));

@@ -41,7 +41,7 @@ struct NarrowArgs {
 #define NP_PER 4
 #define NP_CHUNK (NP_THREADS * NP_PER)   // candidates per CTA iteration; their k-DOP survivors fill the GJK phase densely
 
-__global__ void __launch_bounds__(NP_THREADS) k_narrow(NarrowArgs a) {
+__global__ void __launch_bounds__(NP_THREADS, 4) k_narrow(NarrowArgs a) {
   __shared__ double s_kdop[3 * TOB_KDOP_AXES];
   __shared__ uint32_t s_surv[NP_CHUNK];
   __shared__ uint32_t s_w[NP_THREADS / 32];

@@ -128,6 +128,13 @@ class Solver:
         V = F(V)
         self._ck(self.lib.tob_cloud_upload(self.ctx, _d(V), C.c_uint32(V.shape[0])))
 
+    def init_pointclouds(self, Vs):
+        """one cloud per robot slot (batched independent problems, mode 2)"""
+        Vs = [F(V) for V in Vs]
+        ptrs = (_dp * len(Vs))(*[_d(V) for V in Vs])
+        ns = (C.c_uint32 * len(Vs))(*[V.shape[0] for V in Vs])
+        self._ck(self.lib.tob_cloud_upload_batch(self.ctx, ptrs, ns, C.c_int(len(Vs))))
+
     def device_info(self):
         a, b, c = C.c_int(), C.c_int(), C.c_int()
         self.lib.tob_device_info(self.ctx, C.byref(a), C.byref(b), C.byref(c))
