@@ -69,7 +69,7 @@ def kernel_models(per_step, geo):
     }
 
 
-def workload(name, n_pts=None):
+def workload(name, n_pts=None, n_problems=None):
     from trajopt import scenes
     if name == "forest":
         sc = scenes.forest(n_pts=n_pts or 1_000_000)
@@ -79,6 +79,13 @@ def workload(name, n_pts=None):
         sc = scenes.circle(n_uav=64, n_pts=n_pts or 20_000)
     elif name == "cross8":        # configs[2]
         sc = scenes.cross(n_pts=n_pts or 50_000)
+    elif name == "batch":         # configs[4]: independent single-UAV problems, clouds log-uniform in [1e4, 1e6] points
+        rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+        total = n_problems or 1024
+        mine = list(range(rank, total, world))          # dealt round-robin over the ranks, no communication
+        ms = [scenes.batch_member(k) for k in mine]
+        sc = dict(name="batch", Vs=[m["V"] for m in ms], way_points=[m["way_points"][0] for m in ms], uav_num=len(ms), ks=1e-8,
+                  V=np.zeros((sum(m["V"].shape[0] for m in ms), 0)), n_total=total)
     else:
         raise SystemExit("unknown workload " + name)
     return sc
@@ -179,15 +186,20 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    sc = workload(args.workload, args.points)
+    sc = workload(args.workload, args.points, args.problems)
     P = len(sc["way_points"][0]) - 1
     U = sc["uav_num"]
-    sharded = U > 1 and world > 1
+    batch = "Vs" in sc
+    mode = 2 if batch else 0
+    sharded = U > 1 and world > 1 and not batch
     s = api.Solver(P, uav_num=U, ks=sc["ks"], device=local)
     t0 = time.time()
-    s.init_pointcloud(sc["V"])
+    if batch:
+        s.init_pointclouds(sc["Vs"])
+    else:
+        s.init_pointcloud(sc["V"])
     build_s = time.time() - t0
-    st0 = scenes.initial_states(sc)
+    st0 = [scenes.init_state(scenes.init_spline_single(wp)) for wp in sc["way_points"]] if batch else scenes.initial_states(sc)
     if sharded:
         from trajopt import dist as tdist
         tdist.attach(s)
@@ -203,7 +215,7 @@ def run_ours(args):
     # ---- device-resident iterations: `value`
     s.states_upload(st0)
     for _ in range(args.warmup):
-        s.iterate(1)
+        s.iterate(1, mode)
     s.reset_counters()
     sampler = ClockSampler(local)
     sampler.start()
@@ -216,7 +228,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         with torch.cuda.stream(ext):
             a.record()
-            gn = s.iterate(1)
+            gn = s.iterate(1, mode)
             b.record()
     barrier()
     sampler.end()
@@ -230,7 +242,7 @@ def run_ours(args):
     for _ in range(args.steps):
         flush.fill_(1)
         torch.cuda.synchronize()
-        s.iterate(1)
+        s.iterate(1, mode)
     prof = s.profile_read()
     s.profile_enable(False)
     pctr = s.counters()
@@ -245,7 +257,7 @@ def run_ours(args):
         flush.fill_(1)                      # same L2 policy as the resident loop; not inside the timed call
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        res = s.optimization(cur, inplace=True)   # host buffers in -> H2D -> one ADMM iteration -> D2H -> same host buffers
+        res = s.optimization(cur, mode=mode, inplace=True)   # host buffers in -> H2D -> one ADMM iteration -> D2H -> same host buffers
         e2e_s += time.perf_counter() - t0
         for c_, r_ in zip(cur, res):
             c_["piece_time"] = r_["piece_time"]
@@ -264,7 +276,9 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    mult = 1 if sharded else world         # sharded: ONE problem over all ranks (strong); else N replicas (weak)
+    # sharded: ONE problem over all ranks (strong); batch: every problem of every rank iterates once per step (strong: the
+    # set of problems is fixed); else N replicas (weak)
+    mult = 1 if sharded else (sc["n_total"] if batch else world)
     value = mult * args.steps / (total_ms * 1e-3)
     pair_evals = ctr["dcd_candidates"] + ctr["ccd_candidates"] + ctr["energy_plane_evals"]
     # ---- roofline: every kernel against its bound, `roofline` = the kernel with the largest share of device time
@@ -277,7 +291,8 @@ def run_ours(args):
     peak_src = "MEASURED_PEAKS.json (burst copy)" if "hbm_gbs" in peaks else "fallback of B200_PROFILING.md"
     per_step = {k: pctr[k] / float(args.steps) for k in pctr}
     n0 = -(-sc["V"].shape[0] // 32)
-    geo = {"rows": U * P * 8, "n1": -(-n0 // 32), "P": P, "T": T, "U": U}
+    n1 = float(np.mean([-(-v.shape[0] // 1024) for v in sc["Vs"]])) if batch else -(-n0 // 32)
+    geo = {"rows": U * P * 8, "n1": n1, "P": P, "T": T, "U": U}
     models = kernel_models(per_step, geo)
     tot_prof_ms = sum(v[0] for v in prof.values())
     traffic = {}
@@ -315,10 +330,13 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "%s: %d UAV, %d pts, %d Bezier pieces (%d sub-segments each), 3D.json params" % (sc["name"], U, sc["V"].shape[0], P, P * 8),
+        "config": {"workload": ("batch: %d independent single-UAV problems (%d on this rank), clouds 1e4..1e6 pts (%d pts on this rank), %d Bezier pieces each, 3D.json params"
+                                % (sc["n_total"], U, sc["V"].shape[0], P)) if batch else
+                               "%s: %d UAV, %d pts, %d Bezier pieces (%d sub-segments each), 3D.json params" % (sc["name"], U, sc["V"].shape[0], P, P * 8),
                    "l2": "flushed between timed iterations (256 MiB rewrite outside the event brackets)",
                    "multi_gpu": ("robots sharded over ranks, NCCL all-gather of control points/directions" if sharded else
-                                 ("replicas only" if world > 1 else "single")), "lbvh_build_s": build_s, "gnorm_last": gn},
+                                 ("independent problems dealt round-robin to the ranks, no communication" if batch else
+                                  ("replicas only" if world > 1 else "single"))), "lbvh_build_s": build_s, "gnorm_last": gn},
         "pair_evals_per_s": pair_evals * mult / (total_ms * 1e-3),
         "pairs_per_step": {k: ctr[k] / args.steps for k in ("dcd_candidates", "planes", "ccd_candidates", "energy_plane_evals", "barrier_terms")},
         "e2e": {"value": mult * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes},
@@ -328,7 +346,7 @@ def run_ours(args):
         "kernels": ktab,
     }
     # CPU baseline on a bounded sample, rank 0, N == 1 only
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and not batch:
         out["cpu_baseline"] = cpu_baseline(sc, P, budget_s=25.0, max_iters=6)
     print(json.dumps(out))
     if world > 1:
@@ -404,6 +422,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="forest")
     ap.add_argument("--points", type=int, default=None)
+    ap.add_argument("--problems", type=int, default=None, help="--workload batch: number of independent problems (default 1024)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

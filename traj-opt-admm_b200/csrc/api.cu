@@ -6,6 +6,8 @@
 // Everything stays on the device; the host only reads a few scalars (candidate/plane totals for buffer sizing and
 // the number of robots still backtracking).
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -102,10 +104,12 @@ __global__ void k_fill_int(int* p, int n, int v) {
 // out the first batch of trial points: k=0 the current point, k=1.. the ladder step, step*0.8, step*0.8*0.8, ...
 __global__ void k_ls_init(int rb, int re, const int* kmax, const double* steps_tab, const double* selfstep, int use_self,
                           const double* ptime, const double* tdir, double* step, double* tstep, double* ttime, int* done,
-                          DevCounts* dc) {
+                          DevCounts* dc, int ls_rounds) {
   int u = rb + blockIdx.x * blockDim.x + threadIdx.x;
-  if (u == rb)
-    for (int r = 0; r < TOB_LS_ROUNDS + 2; r++) dc->ls_pending[r] = 0;
+  if (u == rb) {
+    for (int r = 0; r < TOB_LS_MAXROUNDS + 1; r++) dc->ls_pending[r] = 0;
+    dc->ls_rounds = ls_rounds;
+  }
   if (u >= re) return;
   double s = steps_tab[kmax[u]];
   if (use_self) {
@@ -128,9 +132,11 @@ __global__ void k_ls_init(int rb, int re, const int* kmax, const double* steps_t
 // coupled mode (Optimization3D_multi::update_spline :585-636): ONE step and ONE piece time for all robots.
 // step = min(couple_self_step, min_u position_step_u), clamped so that the shared piece time stays positive.
 __global__ void k_ls_init_coupled(int U, const int* kmax, const double* steps_tab, const double* selfstep, const double* ptime,
-                                  const double* tdir, double* step, double* tstep, double* ttime, int* done, DevCounts* dc) {
+                                  const double* tdir, double* step, double* tstep, double* ttime, int* done, DevCounts* dc,
+                                  int ls_rounds) {
   if (threadIdx.x || blockIdx.x) return;
-  for (int r = 0; r < TOB_LS_ROUNDS + 2; r++) dc->ls_pending[r] = 0;
+  for (int r = 0; r < TOB_LS_MAXROUNDS + 1; r++) dc->ls_pending[r] = 0;
+  dc->ls_rounds = ls_rounds;
   int km = 0;
   for (int u = 0; u < U; u++) if (kmax[u] > km) km = kmax[u];
   double s = selfstep[0];
@@ -249,7 +255,7 @@ static int separate_resident(tob_ctx* c, int rb, int re, int with_self) {
 // round r >= 1 evaluates trials 1..8 (round 0 also trial 0 = the current point, the "e" of the reference)
 static int ls_round(tob_ctx* c, int rb, int re, int wolfe_idx, bool coupled, int round, int slot) {
   cudaStream_t st = c->stream;
-  if (!coupled) return line_search_round(c, rb, re, wolfe_idx, round == 0 ? 0 : 1, slot);
+  if (!coupled) return line_search_round(c, rb, re, wolfe_idx, round == 0 ? 0 : 1, round == 0 ? c->ls_kte0 : c->ls_kte, slot);
   TOB_TRY(energy_trials(c, rb, re, c->s_dir.p, c->s_tstep.p, c->s_ttime.p, TOB_LS_TRIALS, round == 0 ? 0 : 1, TOB_LS_TRIALS, c->s_etr.p));
   k_armijo_coupled<<<1, 32, 0, st>>>(re - rb, c->s_etr.p, c->s_wolfe.p, c->s_ptime.p, c->s_tdir.p, c->s_step.p, c->s_ptrial.p,
                                      c->s_tstep.p, c->s_ttime.p, c->s_done.p, &c->dc.p->ls_pending[slot]);
@@ -268,21 +274,21 @@ static int apply_step(tob_ctx* c, int rb, int re, bool guarded) {
 
 // the rounds launched ahead of the host (TOB_LS_ROUNDS x 8 ladder rungs)
 static int ls_launch_ahead(tob_ctx* c, int rb, int re, int wolfe_idx, bool coupled) {
-  for (int r = 0; r < TOB_LS_ROUNDS; r++) TOB_TRY(ls_round(c, rb, re, wolfe_idx, coupled, r, r));
+  for (int r = 0; r < c->ls_rounds; r++) TOB_TRY(ls_round(c, rb, re, wolfe_idx, coupled, r, r));
   return 0;
 }
 
 // host-driven continuation for the rare robot that needs more than TOB_LS_ROUNDS x 8 rungs; h_dc must be current
 static int ls_finish(tob_ctx* c, int rb, int re, int wolfe_idx, bool coupled) {
-  const int slot = TOB_LS_ROUNDS;   // scratch slot, re-zeroed before every extra round
-  int pending = c->h_dc->ls_pending[TOB_LS_ROUNDS - 1];
-  for (int round = TOB_LS_ROUNDS; pending > 0 && round < 60; round++) {
+  const int slot = TOB_LS_MAXROUNDS;   // scratch slot, re-zeroed before every extra round
+  int pending = c->h_dc->ls_pending[c->ls_rounds - 1];
+  for (int round = c->ls_rounds; pending > 0 && round < 400; round++) {
     TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->ls_pending[slot], 0, sizeof(int), c->stream));
     TOB_TRY(ls_round(c, rb, re, wolfe_idx, coupled, round, slot));
     TOB_TRY(sync_counts(c));
     pending = c->h_dc->ls_pending[slot];
   }
-  TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->ls_pending[TOB_LS_ROUNDS - 1], 0, sizeof(int), c->stream));
+  TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->ls_pending[c->ls_rounds - 1], 0, sizeof(int), c->stream));
   return 0;
 }
 
@@ -321,6 +327,21 @@ static int ensure_iter_buffers(tob_ctx* c) {
 // One ADMM iteration, launched without any host read-back.  `deferred`: the state-changing tail (apply step, slack /
 // dual update) is guarded on the device by dc->overflow / dc->ls_pending and the caller inspects dc afterwards;
 // otherwise (sharded multi-GPU: collectives in the middle must stay matched across ranks) the host checks as it goes.
+// few rows: cover 8 rungs per launch (latency); many rows: one rung per round (throughput), more rounds ahead
+static void ls_policy(tob_ctx* c, int rb, int re, bool coupled) {
+  const bool many = !coupled && (long long)(re - rb) * c->n_tr >= 4096;
+  c->ls_kte0 = many ? 3 : TOB_LS_TRIALS;
+  c->ls_kte = TOB_LS_TRIALS;
+  c->ls_rounds = many ? 3 : 2;
+  if (const char* e = getenv("TRAJOPT_B200_LS")) {          // "kte0,kte,rounds": tuning / experiments
+    int k0 = 0, k = 0, r = 0;
+    if (!coupled && sscanf(e, "%d,%d,%d", &k0, &k, &r) == 3 && k0 >= 2 && k0 <= TOB_LS_TRIALS && k >= 2 && k <= TOB_LS_TRIALS &&
+        r >= 1 && r <= TOB_LS_MAXROUNDS) {
+      c->ls_kte0 = k0; c->ls_kte = k; c->ls_rounds = r;
+    }
+  }
+}
+
 static int iterate_launch(tob_ctx* c, int mode, bool deferred) {
   const int rb = c->own_begin, re = c->own_end;
   // mode 2: the robot slots hold INDEPENDENT single-UAV problems (no inter-robot terms, no exchange): everything below that
@@ -349,15 +370,17 @@ static int iterate_launch(tob_ctx* c, int mode, bool deferred) {
   TOB_TRY(ccd_position_steps(c, rb, re));
   // (4) Armijo; multi-robot: every robot uses the LAST robot's wolfe (global overwritten, Optimization3D_multi.h:730,792)
   int wolfe_idx = -1;
+  ls_policy(c, rb, re, coupled);
   if (coupled) {
     if (U == 1) { double one = 1.0; TOB_TRY(upload(c, c->s_selfstep, &one, 1)); }
     k_ls_init_coupled<<<1, 32, 0, st>>>(c->n_robots(), c->kmax.p, c->d_steps.p, c->s_selfstep.p, c->s_ptime.p, c->s_tdir.p, c->s_step.p,
-                                        c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p);
+                                        c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p, c->ls_rounds);
     TOB_LAUNCH_CHECK(c);
     wolfe_idx = 0;
   } else {
     k_ls_init<<<div_up(re - rb, 64), 64, 0, st>>>(rb, re, c->kmax.p, c->d_steps.p, c->s_selfstep.p, U > 1 ? 1 : 0, c->s_ptime.p,
-                                                  c->s_tdir.p, c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p);
+                                                  c->s_tdir.p, c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p,
+                                                  c->ls_rounds);
     TOB_LAUNCH_CHECK(c);
     wolfe_idx = U > 1 ? U - 1 : -1;
   }
@@ -416,7 +439,7 @@ static int iterate_submit(tob_ctx* c, int mode) {
   }
   TOB_CUDA(c, cudaGraphLaunch(c->graph_exec, c->stream));
   c->ctr.kernel_launches += c->graph_nodes;
-  c->ctr.line_search_trials += (uint64_t)(c->own_end - c->own_begin) * (TOB_LS_TRIALS - 1) * TOB_LS_ROUNDS;
+  c->ctr.line_search_trials += (uint64_t)(c->own_end - c->own_begin) * ((c->ls_kte0 - 1) + (c->ls_kte - 1) * (c->ls_rounds - 1));
   if (c->n_robots() > 1 && mode != 2) c->ctr.self_pairs += (uint64_t)2 * c->n_tr * (c->n_robots() * (c->n_robots() - 1) / 2);
   return 0;
 }
@@ -1078,6 +1101,7 @@ int tob_line_search(tob_ctx* c, int robot, tob_state* st, const double* directio
   k_fill_int<<<div_up(c->n_robots(), 64), 64, 0, c->stream>>>(c->kmax.p, c->n_robots(), 0);
   TOB_LAUNCH_CHECK(c);
   int use_self = 0;
+  ls_policy(c, robot, robot + 1, false);
   if (*step_io < 0) {           // Optimization3D_admm::spline_line_search: the bound is Step::position_step
     if (c->n_pts == 0) return fail_msg(c, "tob_line_search: no point cloud");
     TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, robot, robot + 1, 3));
@@ -1088,7 +1112,7 @@ int tob_line_search(tob_ctx* c, int robot, tob_state* st, const double* directio
     use_self = 1;
   }
   k_ls_init<<<1, 64, 0, c->stream>>>(robot, robot + 1, c->kmax.p, c->d_steps.p, c->s_selfstep.p, use_self, c->s_ptime.p, c->s_tdir.p,
-                                     c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p);
+                                     c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p, c->ls_rounds);
   TOB_LAUNCH_CHECK(c);
   TOB_TRY(line_search(c, robot, robot + 1, -1));
   TOB_CUDA(c, cudaMemcpyAsync(st->spline, c->s_spline.p + (size_t)robot * 3 * T, 3 * T * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
   const int lane = threadIdx.x & 31, kk = threadIdx.x >> 5, k = a.k0 + kk;
   __shared__ double sPall[EN_MAXT][18], sBzall[EN_MAXT][18];
   if (a.done && a.done[robot]) return;
+  if (a.dc->overflow) return;      // the plane CSR of this iteration was not built: the host grows the buffers and retries
   double* sP = sPall[kk];
   double* sBz = sBzall[kk];
   if (lane < 18) {
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(128) k_robot_energy(RobotEnergyArgs a) {
 // (Optimization3D_multi.h:730,792).
 struct RobotLsArgs {
   RobotEnergyArgs e;
+  int kte;            // trial points valid in this round: k0 .. kte-1 (stride of the tables stays e.KT)
   const double *wolfe, *ptime, *tdir;
   double *step, *ptrial, *tstep, *ttime;
   int* done;
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(32 * TOB_LS_TRIALS) k_robot_ls(RobotLsArgs b) 
   const int robot = a.robot_begin + blockIdx.x;
   if (b.done[robot]) return;
   const int lane = threadIdx.x & 31, k = a.k0 + (threadIdx.x >> 5);   // one warp per trial point
-  if (k < a.KT) {
+  if (k < b.kte) {
     double e = 0;
     int bad = 0;
     for (int tr = lane; tr < a.n_tr; tr += 32) {
@@ -237,11 +239,11 @@ __global__ void __launch_bounds__(32 * TOB_LS_TRIALS) k_robot_ls(RobotLsArgs b) 
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
-  const int KT = a.KT, u = robot;
-  if (blockIdx.x == 0) b.dc->energy_plane_evals += (unsigned long long)b.dc->n_planes * (unsigned)(KT - a.k0);
+  const int KT = a.KT, u = robot, kte = b.kte;
+  if (blockIdx.x == 0) b.dc->energy_plane_evals += (unsigned long long)b.dc->n_planes * (unsigned)(kte - a.k0);
   const double w = b.wolfe[b.wolfe_idx < 0 ? u : b.wolfe_idx];
   const double e0 = a.e_out[u * KT];
-  for (int k = 1; k < KT; k++) {
+  for (int k = 1; k < kte; k++) {
     const double s = b.tstep[u * KT + k];
     if (!(e0 - 1e-4 * w * s < a.e_out[u * KT + k])) {
       b.step[u] = s;
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(32 * TOB_LS_TRIALS) k_robot_ls(RobotLsArgs b) 
       return;
     }
   }
-  double s = b.tstep[u * KT + KT - 1] * 0.8;
+  double s = b.tstep[u * KT + kte - 1] * 0.8;        // continue the ladder below the last rung that was evaluated
   for (int k = 1; k < KT; k++) {
     b.tstep[u * KT + k] = s;
     b.ttime[u * KT + k] = b.ptime[u] + s * b.tdir[u];
@@ -294,8 +296,9 @@ int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* t
   return 0;
 }
 
-int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int slot) {
+int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int kte, int slot) {
   const int rows_all = c->rows_all(), KT = TOB_LS_TRIALS;
+  if (kte < 2 || kte > KT || k0 >= kte) return fail_msg(c, "line_search_round: bad trial range");
   EnergyArgs a;
   a.spline = c->s_spline.p; a.dir = c->s_dir.p; a.tstep = c->s_tstep.p; a.ttime = c->s_ttime.p; a.basis = c->d_basis.p;
   a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p;
@@ -304,8 +307,8 @@ int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int slo
   a.row_e = c->row_e.p; a.row_bad = c->row_bad.p; a.done = c->s_done.p; a.dc = c->dc.p;
   {
     Prof prof(c, K_ROW_ENERGY);
-    a.nk = KT - k0;
-    k_row_energy<<<(re - rb) * c->n_tr, 32 * (KT - k0), 0, c->stream>>>(a);
+    a.nk = kte - k0;
+    k_row_energy<<<(re - rb) * c->n_tr, 32 * (kte - k0), 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
   RobotLsArgs b;
@@ -316,13 +319,13 @@ int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int slo
   b.e.rows_all = rows_all; b.e.KT = KT; b.e.k0 = k0; b.e.e_out = c->s_etr.p;
   b.wolfe = c->s_wolfe.p; b.ptime = c->s_ptime.p; b.tdir = c->s_tdir.p;
   b.step = c->s_step.p; b.ptrial = c->s_ptrial.p; b.tstep = c->s_tstep.p; b.ttime = c->s_ttime.p; b.done = c->s_done.p;
-  b.wolfe_idx = wolfe_idx; b.slot = slot; b.dc = c->dc.p;
+  b.wolfe_idx = wolfe_idx; b.slot = slot; b.dc = c->dc.p; b.kte = kte;
   {
     Prof prof(c, K_ROBOT_ENERGY);
-    k_robot_ls<<<re - rb, 32 * TOB_LS_TRIALS, 0, c->stream>>>(b);
+    k_robot_ls<<<re - rb, 32 * (kte - k0), 0, c->stream>>>(b);
     TOB_LAUNCH_CHECK(c);
   }
-  c->ctr.line_search_trials += (uint64_t)(re - rb) * (KT - 1);
+  c->ctr.line_search_trials += (uint64_t)(re - rb) * (kte - 1);
   return 0;
 }
 
@@ -345,6 +348,7 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
   __shared__ double sP[18];
   __shared__ double s_red[4][54];
   __shared__ double s_gt[9], s_ht[9];
+  if (a.dc->overflow) return;      // the plane CSR of this iteration was not built (see k_row_energy)
   if (threadIdx.x < 18) sP[threadIdx.x] = a.P[(size_t)18 * row + threadIdx.x];
   __syncthreads();
   const double w = a.weight[tr], m = a.margin;

@@ -43,13 +43,14 @@ struct DBuf {
 // state-changing kernels at the end of the iteration into no-ops; the host looks at this struct ONCE per iteration.
 #define TOB_OVF_CAND 1u      // broadphase produced more candidates than cand_cap
 #define TOB_OVF_SELFHITS 4u  // inter-robot CCD hit list overflow
-#define TOB_LS_ROUNDS 2      // Armijo rounds launched ahead (8 ladder rungs each) before the host is asked
+#define TOB_LS_MAXROUNDS 8   // most Armijo rounds launched ahead of the host (the count is a run-time choice, see ls_policy)
 struct DevCounts {
   uint32_t n_cand;           // candidates of the last broadphase fill (may exceed the capacity -> overflow)
   uint32_t n_planes;         // planes of the last pack
   uint32_t n_planes_ob;      // ... of which obstacle planes
   uint32_t overflow;         // TOB_OVF_* bits, sticky until the host clears them
-  int32_t ls_pending[TOB_LS_ROUNDS + 2];   // robots still backtracking after Armijo round r
+  int32_t ls_pending[TOB_LS_MAXROUNDS + 1];   // robots still backtracking after Armijo round r (last entry: host scratch)
+  int32_t ls_rounds;                          // rounds launched ahead in this iteration (written by k_ls_init)
   uint32_t iters_done;       // iterations fully committed (apply step + slack update ran)
   uint32_t pad;
   unsigned long long dcd_candidates, planes, ccd_candidates, energy_plane_evals, barrier_terms;   // cumulative since reset
@@ -166,6 +167,11 @@ struct tob_ctx {
   uint64_t graph_nodes = 0;           // kernel nodes per launch (for the launch counter)
   bool use_graph = true;
   bool capturing = false;
+  // line-search policy of the current iteration: trial points evaluated in the first round / in later rounds (index 0 =
+  // current point) and rounds launched ahead.  Few rows: 9, 9, 2 (one launch covers 8 rungs: latency).  Many rows: 3, 9, 3:
+  // most robots accept one of the first two rungs, so the first round only evaluates those for everybody (throughput),
+  // and the few robots that keep backtracking get 8 rungs per later round
+  int ls_kte0 = TOB_LS_TRIALS, ls_kte = TOB_LS_TRIALS, ls_rounds = 2;
 
   // optional per-kernel CUDA-event timing (bench.py roofline): off by default
   bool prof_on = false;
@@ -207,7 +213,7 @@ inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 // the state-changing tail of an iteration (apply step, slack/dual update) runs only if nothing overflowed and every
 // robot finished its Armijo search in the rounds that were launched ahead
 __device__ __forceinline__ bool iteration_blocked(const DevCounts* dc) {
-  return dc != nullptr && (dc->overflow != 0u || dc->ls_pending[TOB_LS_ROUNDS - 1] > 0);
+  return dc != nullptr && (dc->overflow != 0u || dc->ls_pending[dc->ls_rounds - 1] > 0);
 }
 #endif
 
@@ -264,9 +270,9 @@ int self_ccd_steps(tob_ctx* c, int coupled, double* steps_dev);
 // barrier.cu
 int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* tstep, const double* ttime, int KT, int k0,
                   int k1, double* e_dev);
-// one Armijo round of robots [rb,re) (decoupled): trial energies k0..TOB_LS_TRIALS-1 + the ladder decision, robots that
+// one Armijo round of robots [rb,re) (decoupled): trial energies k0..kte-1 (kte <= TOB_LS_TRIALS) + the ladder decision, robots that
 // are already done are skipped on the device; robots still backtracking are counted in dc->ls_pending[slot]
-int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int slot);
+int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int kte, int slot);
 int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd);
 int row_blocks(tob_ctx* c, int tr, int which, double* out_dev);
 // solve.cu
