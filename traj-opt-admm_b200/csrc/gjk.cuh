@@ -23,7 +23,11 @@
 
 #if defined(__CUDACC__)
 #define TOB_HD __host__ __device__ __forceinline__
+#ifdef TOB_GJK_INLINE
+#define TOB_HDN static __host__ __device__ __forceinline__
+#else
 #define TOB_HDN static __host__ __device__ __noinline__
+#endif
 #else
 #define TOB_HD inline
 #define TOB_HDN inline

@@ -9,6 +9,7 @@
 //   * packing of accepted planes into the per-row CSR the barrier kernels stream.
 #include "ctx.cuh"
 #include "bp.cuh"
+#define TOB_GJK_INLINE
 #include "gjk.cuh"
 
 namespace tob {
