@@ -37,6 +37,9 @@ namespace tob {
 
 #define TOB_KDOP_AXES 49
 
+// All indices into the simplex arrays below are compile-time constants after unrolling (run-time positions are handled
+// with selects / predicated copies): the simplex then lives in registers instead of local memory, which is what bounded
+// the narrowphase kernels.  Operands and operation order are unchanged.
 struct Simplex {
   int n;
   double v[4][3];
@@ -53,12 +56,16 @@ TOB_HD double nrm2(const double* v) {
   n2 += v[2] * v[2];
   return n2;
 }
+TOB_HD double sel3(const double* a, int i) { return i == 0 ? a[0] : (i == 1 ? a[1] : a[2]); }
 
 // vv = sum_i lam[i] * v[i], accumulated from 0 in index order
 TOB_HD void combine(const Simplex& s, int cnt, double* vv) {
+#pragma unroll
   for (int j = 0; j < 3; ++j) {
     double acc = 0;
-    for (int i = 0; i < cnt; ++i) acc += s.lam[i] * s.v[i][j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < cnt) acc += s.lam[i] * s.v[i][j];
     vv[j] = acc;
   }
 }
@@ -66,6 +73,7 @@ TOB_HD void combine(const Simplex& s, int cnt, double* vv) {
 // closest point to the origin on the 1-simplex (v[0]=B, v[1]=A)
 TOB_HDN void sv_line(Simplex& s, double* vv) {
   double a[3], b[3], t[3], ft[3];
+#pragma unroll
   for (int i = 0; i < 3; ++i) {
     b[i] = s.v[0][i];
     a[i] = s.v[1][i];
@@ -78,18 +86,20 @@ TOB_HDN void sv_line(Simplex& s, double* vv) {
   else if (ft[0] < ft[2]) I = 2;
   else if (ft[1] < ft[2]) I = 2;
 
-  double pt = dot3(b, t) / dot3(t, t) * (a[I] - b[I]) + b[I];
-  double det_ap = a[I] - pt;
-  double det_pb = pt - b[I];
-  bool fa = same_sign(t[I], -det_ap);
-  bool fb = same_sign(t[I], -det_pb);
+  const double aI = sel3(a, I), bI = sel3(b, I), tI = sel3(t, I);
+  double pt = dot3(b, t) / dot3(t, t) * (aI - bI) + bI;
+  double det_ap = aI - pt;
+  double det_pb = pt - bI;
+  bool fa = same_sign(tI, -det_ap);
+  bool fb = same_sign(tI, -det_pb);
   if (fa && fb) {
-    s.lam[0] = det_ap * -1.0 / t[I];
+    s.lam[0] = det_ap * -1.0 / tI;
     s.lam[1] = 1 - s.lam[0];
     s.wid[0] = 0; s.wid[1] = 1;
     s.n = 2;
   } else if (!fa) {
     s.lam[0] = 1; s.wid[0] = 0; s.n = 1;
+#pragma unroll
     for (int i = 0; i < 3; ++i) s.v[0][i] = s.v[1][i];
   } else {
     s.lam[0] = 1; s.wid[0] = 1; s.n = 1;
@@ -100,19 +110,20 @@ TOB_HDN void sv_line(Simplex& s, double* vv) {
 // closest point to the origin on the 2-simplex (v[0]=C, v[1]=B, v[2]=A)
 TOB_HDN void sv_tri(Simplex& s, double* vv) {
   double a[3], b[3], c[3], s21[3], s31[3];
+#pragma unroll
   for (int i = 0; i < 3; ++i) {
     c[i] = s.v[0][i]; b[i] = s.v[1][i]; a[i] = s.v[2][i];
     s21[i] = b[i] - a[i];
     s31[i] = c[i] - a[i];
   }
-  // cyclic index pairs (k,l) visited by the reference's "k=l; l=i" walk starting from (1,2)
-  const int K[3] = {1, 2, 0}, L[3] = {2, 0, 1};
+  // cyclic index pairs (k,l) visited by the reference's "k=l; l=i" walk starting from (1,2): (1,2), (2,0), (0,1)
   double nu[3], fnu[3];
-  for (int i = 0; i < 3; ++i) {
-    int k = K[i], l = L[i];
-    double m = b[k] * c[l] + a[k] * b[l] + c[k] * a[l] - b[k] * a[l] - c[k] * b[l] - a[k] * c[l];
-    nu[i] = (i == 1) ? -m : m;   // pow(-1.0,i) * m
-    fnu[i] = fabs(nu[i]);
+  {
+    double m0 = b[1] * c[2] + a[1] * b[2] + c[1] * a[2] - b[1] * a[2] - c[1] * b[2] - a[1] * c[2];
+    double m1 = b[2] * c[0] + a[2] * b[0] + c[2] * a[0] - b[2] * a[0] - c[2] * b[0] - a[2] * c[0];
+    double m2 = b[0] * c[1] + a[0] * b[1] + c[0] * a[1] - b[0] * a[1] - c[0] * b[1] - a[0] * c[1];
+    nu[0] = m0; nu[1] = -m1; nu[2] = m2;      // pow(-1.0,i) * m
+    fnu[0] = fabs(nu[0]); fnu[1] = fabs(nu[1]); fnu[2] = fabs(nu[2]);
   }
   // the reference initialises indexJ[2] = {-1} i.e. {-1,0}; the no-branch-taken case (exact ties) reads out of
   // bounds there (undefined); we pin it to J = {0,0}, which only matters when the triangle is degenerate and the
@@ -123,24 +134,24 @@ TOB_HDN void sv_tri(Simplex& s, double* vv) {
   } else if (fnu[0] < fnu[1]) {
     if (fnu[1] > fnu[2]) { J0 = 0; I = 1; J1 = 2; } else { J0 = 0; J1 = 1; I = 2; }
   } else if (fnu[0] < fnu[2]) { J0 = 0; J1 = 1; I = 2; }
-  double nu_max = nu[I];
+  double nu_max = sel3(nu, I);
 
   double n[3], nn = 0;
-  for (int i = 0; i < 3; ++i) {
-    int k = K[i], l = L[i];
-    n[i] = s21[k] * s31[l] - s21[l] * s31[k];
-    nn += n[i] * n[i];
-  }
+  n[0] = s21[1] * s31[2] - s21[2] * s31[1]; nn += n[0] * n[0];
+  n[1] = s21[2] * s31[0] - s21[0] * s31[2]; nn += n[1] * n[1];
+  n[2] = s21[0] * s31[1] - s21[1] * s31[0]; nn += n[2] * n[2];
   double inv_len = 1 / sqrt(nn);
+#pragma unroll
   for (int i = 0; i < 3; ++i) n[i] = n[i] * inv_len;
   double dna = dot3(n, a);
-  double pp0 = dna * n[J0], pp1 = dna * n[J1];
-  double ss[3][2] = {{a[J0], a[J1]}, {b[J0], b[J1]}, {c[J0], c[J1]}};
+  double pp0 = dna * sel3(n, J0), pp1 = dna * sel3(n, J1);
+  // ss[k] = projection of vertex k (0 = A, 1 = B, 2 = C) on the two kept axes
+  const double ss00 = sel3(a, J0), ss01 = sel3(a, J1), ss10 = sel3(b, J0), ss11 = sel3(b, J1), ss20 = sel3(c, J0), ss21 = sel3(c, J1);
   double B[3];
-  for (int i = 0; i < 3; ++i) {
-    int k = K[i], l = L[i];
-    B[i] = pp0 * ss[k][1] + pp1 * ss[l][0] + ss[k][0] * ss[l][1] - pp0 * ss[l][1] - pp1 * ss[k][0] - ss[l][0] * ss[k][1];
-  }
+  // (k,l) = (1,2), (2,0), (0,1)
+  B[0] = pp0 * ss11 + pp1 * ss20 + ss10 * ss21 - pp0 * ss21 - pp1 * ss10 - ss20 * ss11;
+  B[1] = pp0 * ss21 + pp1 * ss00 + ss20 * ss01 - pp0 * ss01 - pp1 * ss20 - ss00 * ss21;
+  B[2] = pp0 * ss01 + pp1 * ss10 + ss00 * ss11 - pp0 * ss11 - pp1 * ss00 - ss10 * ss01;
   bool f0 = same_sign(nu_max, B[0]), f1 = same_sign(nu_max, B[1]), f2 = same_sign(nu_max, B[2]);
   double v[3];
   if ((!f1 && !f2) || isnan(n[0])) {
@@ -148,10 +159,13 @@ TOB_HDN void sv_tri(Simplex& s, double* vv) {
     Simplex e;
     e.n = 2; s.n = 2;
     e.lam[0] = 0; e.lam[1] = 0; e.wid[0] = 0; e.wid[1] = 0;
+    e.lam[2] = 0; e.lam[3] = 0; e.wid[2] = 0; e.wid[3] = 0;
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
       e.v[0][i] = s.v[1][i];
       e.v[1][i] = s.v[2][i];
       s.v[1][i] = s.v[2][i];
+      e.v[2][i] = 0; e.v[3][i] = 0;
     }
     sv_line(e, v);
     sv_line(s, v);
@@ -159,10 +173,11 @@ TOB_HDN void sv_tri(Simplex& s, double* vv) {
     combine(e, e.n, vt);
     combine(s, e.n, v);        // (sic) counted with the other simplex's size: may read a stale weight
     if (dot3(v, v) < dot3(vt, vt)) {
-      for (int i = 1; i < s.n; ++i) s.wid[i] = s.wid[i] + 1;
+      if (s.n > 1) s.wid[1] = s.wid[1] + 1;      // for (i = 1; i < s.n; ++i) with s.n <= 2
     } else {
       s.n = e.n;               // (sic) weights and labels of BA, vertices of CA are kept
-      for (int i = 0; i < s.n; ++i) { s.lam[i] = e.lam[i]; s.wid[i] = e.wid[i]; }
+      s.lam[0] = e.lam[0]; s.wid[0] = e.wid[0];
+      if (s.n > 1) { s.lam[1] = e.lam[1]; s.wid[1] = e.wid[1]; }
     }
   } else if (f0 && f1 && f2) {
     double inv = 1 / nu_max;
@@ -173,13 +188,15 @@ TOB_HDN void sv_tri(Simplex& s, double* vv) {
     s.n = 3;
   } else if (!f2) {            // faces AB
     s.n = 2;
+#pragma unroll
     for (int i = 0; i < 3; ++i) { s.v[0][i] = s.v[1][i]; s.v[1][i] = s.v[2][i]; }
     sv_line(s, v);
   } else if (!f1) {            // faces AC
     s.n = 2;
+#pragma unroll
     for (int i = 0; i < 3; ++i) s.v[1][i] = s.v[2][i];
     sv_line(s, v);
-    for (int i = 1; i < s.n; ++i) s.wid[i] = s.wid[i] + 1;
+    if (s.n > 1) s.wid[1] = s.wid[1] + 1;
   } else {                     // faces BC
     s.n = 2;
     sv_line(s, v);
@@ -193,9 +210,23 @@ TOB_HD int tri_vertex(int aux, int k) {
   return (k == 0) ? 3 : (k == 1 ? (aux == 0 ? 1 : 2) : (aux == 2 ? 1 : 0));
 }
 
+// s.v[dst] = src (dst is a run-time slot)
+TOB_HD void put_vertex(Simplex& s, int dst, const double* src) {
+#pragma unroll
+  for (int d = 0; d < 4; ++d)
+    if (d == dst) { s.v[d][0] = src[0]; s.v[d][1] = src[1]; s.v[d][2] = src[2]; }
+}
+TOB_HD void put_wid(Simplex& s, int dst, int val) {
+#pragma unroll
+  for (int d = 0; d < 4; ++d)
+    if (d == dst) s.wid[d] = val;
+}
+TOB_HD int get_wid(const Simplex& s, int i) { return i == 0 ? s.wid[0] : (i == 1 ? s.wid[1] : (i == 2 ? s.wid[2] : s.wid[3])); }
+
 // closest point to the origin on the 3-simplex (v[0]=D, v[1]=C, v[2]=B, v[3]=A)
 TOB_HDN void sv_tet(Simplex& s, double* vv) {
   double a[3], b[3], c[3], d[3];
+#pragma unroll
   for (int i = 0; i < 3; ++i) { d[i] = s.v[0][i]; c[i] = s.v[1][i]; b[i] = s.v[2][i]; a[i] = s.v[3][i]; }
   double B[4];
   B[0] = -1 * (b[0] * c[1] * d[2] + b[1] * c[2] * d[0] + b[2] * c[0] * d[1] - b[2] * c[1] * d[0] - b[1] * c[0] * d[2] - b[0] * c[2] * d[1]);
@@ -204,24 +235,24 @@ TOB_HDN void sv_tet(Simplex& s, double* vv) {
   B[3] = +1 * (a[0] * b[1] * c[2] + a[1] * b[2] * c[0] + a[2] * b[0] * c[1] - a[2] * b[1] * c[0] - a[1] * b[0] * c[2] - a[0] * b[2] * c[1]);
   double detM = B[0] + B[1] + B[2] + B[3];
 
-  bool f[4] = {true, true, true, true};
+  bool f0 = true, f1 = true, f2 = true, f3 = true;
   const double eps = 1e-13;
   if (fabs(detM) < eps) {
     bool z0 = fabs(B[0]) < eps, z1 = fabs(B[1]) < eps, z2 = fabs(B[2]) < eps, z3 = fabs(B[3]) < eps;
-    if (z2 && z3) f[1] = false;
-    else if (z1 && z3) f[2] = false;
-    else if (z1 && z2) f[3] = false;
-    else if (z0 && z3) f[1] = false;
-    else if (z0 && z2) f[1] = false;
-    else if (z0 && z1) f[2] = false;
-    else { f[0] = f[1] = f[2] = f[3] = false; }
+    if (z2 && z3) f1 = false;
+    else if (z1 && z3) f2 = false;
+    else if (z1 && z2) f3 = false;
+    else if (z0 && z3) f1 = false;
+    else if (z0 && z2) f1 = false;
+    else if (z0 && z1) f2 = false;
+    else { f0 = f1 = f2 = f3 = false; }
   } else {
-    for (int i = 0; i < 4; ++i) f[i] = same_sign(detM, B[i]);
+    f0 = same_sign(detM, B[0]); f1 = same_sign(detM, B[1]); f2 = same_sign(detM, B[2]); f3 = same_sign(detM, B[3]);
   }
-  int n123 = (int)f[1] + (int)f[2] + (int)f[3];
+  int n123 = (int)f1 + (int)f2 + (int)f3;
   double v[3], vt[3];
 
-  if (f[0] && n123 == 3) {
+  if (f0 && n123 == 3) {
     double inv = 1 / detM;
     s.lam[3] = B[0] * inv;
     s.lam[2] = B[1] * inv;
@@ -234,14 +265,18 @@ TOB_HDN void sv_tet(Simplex& s, double* vv) {
     Simplex t;
     t.lam[0] = t.lam[1] = t.lam[2] = t.lam[3] = 0;
     t.wid[0] = t.wid[1] = t.wid[2] = t.wid[3] = 0;
-    int sid[4] = {0, 0, 0, 0};
-    double tl[4] = {0, 0, 0, 0};
+    t.v[3][0] = t.v[3][1] = t.v[3][2] = 0;
+    int sid0 = 0, sid1 = 0, sid2 = 0;
+    double tl0 = 0, tl1 = 0, tl2 = 0;
     int nclosest = 0;
     double best = 0;
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
       t.n = 3;
+#pragma unroll
       for (int k = 0; k < 3; ++k) {
-        int vid = tri_vertex(i, k);
+        const int vid = tri_vertex(i, k);     // compile-time after unrolling
+#pragma unroll
         for (int j = 0; j < 3; ++j) t.v[2 - k][j] = s.v[vid][j];
       }
       sv_tri(t, v);
@@ -250,17 +285,29 @@ TOB_HDN void sv_tet(Simplex& s, double* vv) {
       if (i == 0 || dd < best) {
         best = dd;
         nclosest = t.n;
-        for (int l = 0; l < nclosest; ++l) { sid[l] = tri_vertex(i, t.wid[l]); tl[l] = t.lam[l]; }
+        sid0 = tri_vertex(i, t.wid[0]); tl0 = t.lam[0];       // entries >= nclosest are never read
+        sid1 = tri_vertex(i, t.wid[1]); tl1 = t.lam[1];
+        sid2 = tri_vertex(i, t.wid[2]); tl2 = t.lam[2];
       }
     }
     double keep[4][3];
+#pragma unroll
     for (int i = 0; i < 4; ++i)
+#pragma unroll
       for (int j = 0; j < 3; ++j) keep[i][j] = s.v[i][j];
     s.n = nclosest;
-    for (int i = 0; i < s.n; ++i) {
-      for (int j = 0; j < 3; ++j) s.v[nclosest - 1 - i][j] = keep[sid[i]][j];
-      s.lam[i] = tl[i];
-      s.wid[nclosest - 1 - i] = sid[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (i < nclosest) {
+        const int sid = i == 0 ? sid0 : (i == 1 ? sid1 : sid2);
+        const double tl = i == 0 ? tl0 : (i == 1 ? tl1 : tl2);
+        double kv[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) kv[j] = sid == 0 ? keep[0][j] : (sid == 1 ? keep[1][j] : (sid == 2 ? keep[2][j] : keep[3][j]));
+        put_vertex(s, nclosest - 1 - i, kv);
+        s.lam[i] = tl;
+        put_wid(s, nclosest - 1 - i, sid);
+      }
     }
   } else if (n123 == 1) {
     // two facets through A face the origin
@@ -268,18 +315,23 @@ TOB_HDN void sv_tet(Simplex& s, double* vv) {
     t.n = 3;
     t.lam[0] = t.lam[1] = t.lam[2] = t.lam[3] = 0;
     t.wid[0] = t.wid[1] = t.wid[2] = t.wid[3] = 0;
+    t.v[3][0] = t.v[3][1] = t.v[3][2] = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { t.v[0][i] = 0; t.v[1][i] = 0; t.v[2][i] = 0; }
     double best = 0;
     bool used = false;
     int first = 0, second = 0;
-    if (!f[1]) {               // ACD
+    if (!f1) {                 // ACD
+#pragma unroll
       for (int i = 0; i < 3; ++i) { t.v[0][i] = s.v[0][i]; t.v[1][i] = s.v[1][i]; t.v[2][i] = s.v[3][i]; }
       sv_tri(t, v);
       combine(t, t.n, vt);
       best = dot3(vt, vt);
       used = true; first = 0;
     }
-    if (!f[2]) {               // ABD
+    if (!f2) {                 // ABD
       if (!used) {
+#pragma unroll
         for (int i = 0; i < 3; ++i) { t.v[0][i] = s.v[0][i]; t.v[1][i] = s.v[2][i]; t.v[2][i] = s.v[3][i]; }
         sv_tri(t, v);
         combine(t, t.n, vt);
@@ -287,47 +339,60 @@ TOB_HDN void sv_tet(Simplex& s, double* vv) {
         first = 1;
       } else {
         s.n = 3;
+#pragma unroll
         for (int i = 0; i < 3; ++i) { s.v[1][i] = s.v[2][i]; s.v[2][i] = s.v[3][i]; }
         sv_tri(s, v);
         second = 1;
       }
     }
-    if (!f[3]) {               // ABC
+    if (!f3) {                 // ABC
       s.n = 3;
+#pragma unroll
       for (int i = 0; i < 3; ++i) { s.v[0][i] = s.v[1][i]; s.v[1][i] = s.v[2][i]; s.v[2][i] = s.v[3][i]; }
       sv_tri(s, v);
       second = 2;
     }
     combine(s, s.n, v);
     if (dot3(v, v) < best) {
-      for (int i = 0; i < s.n; ++i) s.wid[s.n - 1 - i] = tri_vertex(second, s.wid[i]);   // in place, as the reference
+      // in place, as the reference: s.wid[s.n-1-i] = tri_vertex(second, s.wid[i]) for i = 0..s.n-1 (later reads see earlier writes)
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        if (i < s.n) put_wid(s, s.n - 1 - i, tri_vertex(second, get_wid(s, i)));
     } else {
       s.n = t.n;
-      for (int i = 0; i < s.n; ++i) {
-        for (int j = 0; j < 3; ++j) s.v[i][j] = t.v[i][j];
-        s.lam[i] = t.lam[i];
-        s.wid[t.n - 1 - i] = tri_vertex(first, t.wid[i]);
-      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        if (i < s.n) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) s.v[i][j] = t.v[i][j];
+          s.lam[i] = t.lam[i];
+          put_wid(s, t.n - 1 - i, tri_vertex(first, t.wid[i]));
+        }
     }
   } else if (n123 == 2) {
-    if (!f[1]) {               // ACD
+    if (!f1) {                 // ACD
       s.n = 3;
+#pragma unroll
       for (int i = 0; i < 3; ++i) s.v[2][i] = s.v[3][i];
       sv_tri(s, v);
-    } else if (!f[2]) {        // ABD
+    } else if (!f2) {          // ABD
       s.n = 3;
+#pragma unroll
       for (int i = 0; i < 3; ++i) { s.v[1][i] = s.v[2][i]; s.v[2][i] = s.v[3][i]; }
       sv_tri(s, v);
-      for (int i = 2; i < s.n; ++i) s.wid[i] = s.wid[i] + 1;
-    } else if (!f[3]) {        // ABC
+      if (s.n > 2) s.wid[2] = s.wid[2] + 1;          // for (i = 2; i < s.n; ++i)
+    } else if (!f3) {          // ABC
       s.n = 3;
+#pragma unroll
       for (int i = 0; i < 3; ++i) { s.v[0][i] = s.v[1][i]; s.v[1][i] = s.v[2][i]; s.v[2][i] = s.v[3][i]; }
       sv_tri(s, v);
     }
   } else {                     // only BCD faces the origin
     s.n = 3;
     sv_tri(s, v);
-    for (int i = 0; i < s.n; ++i) s.wid[i] = s.wid[i] + 1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if (i < s.n) s.wid[i] = s.wid[i] + 1;
   }
   combine(s, s.n, vv);
 }
@@ -336,12 +401,13 @@ TOB_HDN void sv_tet(Simplex& s, double* vv) {
 template <int N>
 TOB_HD void support_max(const double (*pts)[3], double* cur, const double* dir) {
   double best = dot3(cur, dir);
-  int better = -1;
+  double bx = cur[0], by = cur[1], bz = cur[2];
+#pragma unroll
   for (int i = 0; i < N; ++i) {
     double sv = dot3(pts[i], dir);
-    if (sv > best) { best = sv; better = i; }
+    if (sv > best) { best = sv; bx = pts[i][0]; by = pts[i][1]; bz = pts[i][2]; }
   }
-  if (better != -1) { cur[0] = pts[better][0]; cur[1] = pts[better][1]; cur[2] = pts[better][2]; }
+  cur[0] = bx; cur[1] = by; cur[2] = bz;
 }
 
 // witness vector (closest point of the Minkowski difference A-B to the origin)
@@ -350,11 +416,14 @@ TOB_HD void gjk_witness(const double (*A)[3], const double (*B)[3], double* vout
   Simplex s;
   s.lam[0] = s.lam[1] = s.lam[2] = s.lam[3] = 0;
   s.wid[0] = s.wid[1] = s.wid[2] = s.wid[3] = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i) { s.v[i][0] = 0; s.v[i][1] = 0; s.v[i][2] = 0; }
   double v[3], vm[3], w[3], sa[3], sb[3];
   const double eps_rel2 = 1e-5 * 1e-5;
   const double eps_tot = 1e-15;
   double wmax = 0;
   s.n = 1;
+#pragma unroll
   for (int i = 0; i < 3; ++i) {
     v[i] = A[0][i] - B[0][i];
     sa[i] = A[0][i];
@@ -371,16 +440,17 @@ TOB_HD void gjk_witness(const double (*A)[3], const double (*B)[3], double* vout
     double vv = nrm2(v);
     if ((vv - dot3(v, w)) <= eps_rel2 * vv) break;
     if (vv < eps_rel2) break;
-    int i = s.n;
-    s.v[i][0] = w[0]; s.v[i][1] = w[1]; s.v[i][2] = w[2];
+    put_vertex(s, s.n, w);
     s.n++;
     if (s.n == 4) sv_tet(s, v);
     else if (s.n == 3) sv_tri(s, v);
     else if (s.n == 2) sv_line(s, v);
-    for (i = 0; i < s.n; i++) {
-      double tn = nrm2(s.v[i]);
-      if (tn > wmax) wmax = tn;
-    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (i < s.n) {
+        double tn = nrm2(s.v[i]);
+        if (tn > wmax) wmax = tn;
+      }
     if (nrm2(v) <= (eps_tot * eps_tot * wmax)) break;
   } while ((s.n != 4) && (k != 50));
   vout[0] = v[0]; vout[1] = v[1]; vout[2] = v[2];
@@ -422,16 +492,16 @@ TOB_HD void gjk_witness_n(const double (*A)[3], int na, const double (*B)[3], in
     double vv = nrm2(v);
     if ((vv - dot3(v, w)) <= eps_rel2 * vv) break;
     if (vv < eps_rel2) break;
-    int i = s.n;
-    s.v[i][0] = w[0]; s.v[i][1] = w[1]; s.v[i][2] = w[2];
+    put_vertex(s, s.n, w);
     s.n++;
     if (s.n == 4) sv_tet(s, v);
     else if (s.n == 3) sv_tri(s, v);
     else if (s.n == 2) sv_line(s, v);
-    for (i = 0; i < s.n; i++) {
-      double tn = nrm2(s.v[i]);
-      if (tn > wmax) wmax = tn;
-    }
+    for (int i = 0; i < 4; i++)
+      if (i < s.n) {
+        double tn = nrm2(s.v[i]);
+        if (tn > wmax) wmax = tn;
+      }
     if (nrm2(v) <= (eps_tot * eps_tot * wmax)) break;
   } while ((s.n != 4) && (k != 50));
   vout[0] = v[0]; vout[1] = v[1]; vout[2] = v[2];

@@ -396,7 +396,7 @@ __device__ __forceinline__ void moved_points(const double (*P)[3], const double 
     }
 }
 
-__global__ void __launch_bounds__(BP_THREADS) k_bp_ccd(CcdArgs a) {
+__global__ void __launch_bounds__(BP_THREADS, 4) k_bp_ccd(CcdArgs a) {
   __shared__ BpShared s;
   __shared__ double s_kdop[3 * TOB_KDOP_AXES];
   for (int i = threadIdx.x; i < 3 * TOB_KDOP_AXES; i += blockDim.x) s_kdop[i] = a.kdop[i];
