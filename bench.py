@@ -82,7 +82,7 @@ def workload(name, n_pts=None, n_problems=None):
     elif name == "batch":         # configs[4]: independent single-UAV problems, clouds log-uniform in [1e4, 1e6] points
         rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
         total = n_problems or 1024
-        mine = list(range(rank, total, world))          # dealt round-robin over the ranks, no communication
+        mine = scenes.batch_partition(total, world, rank)   # balanced deal over the ranks, no communication
         ms = [scenes.batch_member(k) for k in mine]
         sc = dict(name="batch", Vs=[m["V"] for m in ms], way_points=[m["way_points"][0] for m in ms], uav_num=len(ms), ks=1e-8,
                   V=np.zeros((sum(m["V"].shape[0] for m in ms), 0)), n_total=total)
@@ -250,6 +250,7 @@ def run_ours(args):
 
     # ---- end to end through the host-in/host-out entry point
     cur = [pinned_state(x) for x in s.states_download(st0)]
+    bound = s.bind_states(cur)              # tob_state array over the pinned host buffers, built once like a C++ caller would
     barrier()
     sampler.begin()
     e2e_s = 0.0
@@ -257,10 +258,8 @@ def run_ours(args):
         flush.fill_(1)                      # same L2 policy as the resident loop; not inside the timed call
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        res = s.optimization(cur, mode=mode, inplace=True)   # host buffers in -> H2D -> one ADMM iteration -> D2H -> same host buffers
+        s.optimization_bound(bound, mode)   # host buffers in -> H2D -> one ADMM iteration -> D2H -> same host buffers
         e2e_s += time.perf_counter() - t0
-        for c_, r_ in zip(cur, res):
-            c_["piece_time"] = r_["piece_time"]
     sampler.end()
     sampler.close()
     T = s.T
@@ -328,7 +327,7 @@ def run_ours(args):
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if (sharded or batch) else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": ("batch: %d independent single-UAV problems (%d on this rank), clouds 1e4..1e6 pts (%d pts on this rank), %d Bezier pieces each, 3D.json params"
                                 % (sc["n_total"], U, sc["V"].shape[0], P)) if batch else

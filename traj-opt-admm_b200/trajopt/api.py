@@ -292,6 +292,17 @@ class Solver:
         out = [h.to_dict(gnorm=gn.value) for h in hss]
         return out[0] if single else out
 
+    def bind_states(self, sts):
+        """keep the tob_state array over the caller's own column-major float64 buffers (what a C++ caller holds anyway):
+        optimization_bound() then costs one C call, no per-call marshalling"""
+        return self._states(sts, inplace=True)
+
+    def optimization_bound(self, bound, mode=0):
+        hss, arr = bound
+        gn = C.c_double(0)
+        self._ck(self.lib.tob_optimization(self.ctx, arr, C.c_int(len(hss)), C.c_int(mode), C.byref(gn)))
+        return gn.value
+
     def states_upload(self, sts):
         hss, arr = self._states(sts)
         self._ck(self.lib.tob_states_upload(self.ctx, arr, C.c_int(len(sts))))

@@ -203,11 +203,31 @@ def circle(n_uav=64, n_pts=20_000, seed=4, n_pieces=8, radius=10.0, eps=0.35, st
     return dict(name="circle", V=np.asfortranarray(V), way_points=wps, uav_num=n_uav, ks=1e-3)
 
 
-def batch_member(k, n_pieces=8):
-    """C5: problem k of the 1024-problem sweep: cloud size log-uniform in [1e4,1e6], tube radius in [0.13,1.0]."""
+def batch_member_meta(k):
+    """(cloud size, tube radius) of problem k without generating the cloud"""
     rng = np.random.Generator(np.random.PCG64(1000 + k))
     n = int(round(10 ** rng.uniform(4, 6)))
     r = rng.uniform(0.13, 1.0)
+    return n, r
+
+
+def batch_partition(total, world, rank):
+    """problems of `rank`: sorted by expected pair work (points inside the 0.2 barrier band of the path: the whole tube when
+    its radius is below 0.3, nothing otherwise; then cloud size) and dealt in snake order, so every rank gets the same mix"""
+    meta = [batch_member_meta(k) for k in range(total)]
+    order = sorted(range(total), key=lambda k: (-(meta[k][0] if meta[k][1] < 0.3 else 0), -meta[k][0], k))
+    mine = []
+    for i, k in enumerate(order):
+        lap, pos = divmod(i, world)
+        owner = pos if lap % 2 == 0 else world - 1 - pos
+        if owner == rank:
+            mine.append(k)
+    return mine
+
+
+def batch_member(k, n_pieces=8):
+    """C5: problem k of the 1024-problem sweep: cloud size log-uniform in [1e4,1e6], tube radius in [0.13,1.0]."""
+    n, r = batch_member_meta(k)
     sc = tube(n, 1000 + k, r, n_pieces)
     sc["name"] = "batch%d" % k
     return sc
