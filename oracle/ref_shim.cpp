@@ -271,6 +271,44 @@ void ref_optimal_d(const double* P0, const double* P1, const double* c, double* 
   Optimal_plane::optimal_d(map_mat(P0, 6, 3), map_mat(P1, 6, 3), cv, *d);
 }
 
+
+// ---- persistent-plane mode ("optimal_plane": 1) ------------------------------------------------------------------------
+// Optimal_plane::optimal_cd (Optimal_plane.h:160-293): Newton on the tangent angles of c, d tied to the point.
+void ref_optimal_cd(const double* P, const double* q, double* c, double* d) {
+  Eigen::Vector3d cv(c[0], c[1], c[2]);
+  Optimal_plane::optimal_cd(map_mat(P, 6, 3), map_mat(q, 1, 3), cv, *d);
+  c[0] = cv(0); c[1] = cv(1); c[2] = cv(2);
+}
+// Optimal_plane::self_optimal_cd (Optimal_plane.h:620-773): 3-variable (theta, phi, d) Newton, inter-robot plane.
+void ref_self_optimal_cd(const double* P0, const double* P1, double* c, double* d) {
+  Eigen::Vector3d cv(c[0], c[1], c[2]);
+  Optimal_plane::self_optimal_cd(map_mat(P0, 6, 3), map_mat(P1, 6, 3), cv, *d);
+  c[0] = cv(0); c[1] = cv(1); c[2] = cv(2);
+}
+// the persistent state of Main/admmPathPlanning3D.cpp:342-351 and Main/multiPathPlanning3D.cpp:450-464, emptied.
+// dense N_tr x N_pts like the reference: only for small clouds.
+void ref_reset_persistent_planes() {
+  int n_tr = subdivide_tree.size();
+  size_t nv = g_vertex_list.size();
+  is_seperate.assign(n_tr, std::vector<bool>(nv, false));
+  seperate_c.assign(n_tr, std::vector<Eigen::Vector3d>(nv));
+  seperate_d.assign(n_tr, std::vector<double>(nv));
+  is_self_seperate.assign(n_tr, std::vector<std::vector<bool>>(uav_num, std::vector<bool>(uav_num, false)));
+  self_seperate_c.assign(n_tr, std::vector<std::vector<Eigen::Vector3d>>(uav_num, std::vector<Eigen::Vector3d>(uav_num)));
+  self_seperate_d.assign(n_tr, std::vector<std::vector<double>>(uav_num, std::vector<double>(uav_num)));
+}
+// live obstacle planes: (tr, point id) pairs with is_seperate set, in (tr, id) order; returns the count
+long ref_live_planes(unsigned* tr, unsigned* id, double* c, double* d, long cap) {
+  long n = 0;
+  for (size_t t = 0; t < is_seperate.size(); t++)
+    for (size_t k = 0; k < is_seperate[t].size(); k++)
+      if (is_seperate[t][k]) {
+        if (n < cap) { tr[n] = t; id[n] = k; c[3 * n] = seperate_c[t][k](0); c[3 * n + 1] = seperate_c[t][k](1); c[3 * n + 2] = seperate_c[t][k](2); d[n] = seperate_d[t][k]; }
+        n++;
+      }
+  return n;
+}
+
 // ---- planes -------------------------------------------------------------------
 long ref_separate_plane(const double* spline, unsigned* off, double* c, double* d, long cap) {
   Quiet q;

@@ -1,6 +1,9 @@
 """Summarise ncu outputs brought back in gpurun_out/ into small tracked text files under profiles/.
 usage: python profiles/summarize.py launches <launches.csv> <out.txt>
-       python profiles/summarize.py full <file.ncu-rep> <out.txt>"""
+       python profiles/summarize.py full <file.ncu-rep> <out.txt>
+       python profiles/summarize.py rawcsv <raw.csv from `ncu -i rep --page raw --csv`> <out.txt> [<workload name>]
+           (with a workload name: also folds the per-launch DRAM traffic of every kernel into profiles/ncu_traffic.json,
+            which bench.py reads for `roofline.traffic`)"""
 import csv
 import subprocess
 import sys
@@ -58,5 +61,54 @@ def full(src, dst):
             f.write("\n")
 
 
+def _num(x):
+    try:
+        return float(x.replace(",", ""))
+    except ValueError:
+        return None
+
+
+def rawcsv(src, dst, workload=None):
+    import json
+    import os
+    rows = list(csv.reader(l for l in open(src) if l.startswith('"')))
+    hdr, units = rows[0], rows[1]
+    per = defaultdict(list)
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        per[d.get("Kernel Name", "?").split("(")[0]].append(d)
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    traffic = {}
+    with open(dst, "w") as f:
+        f.write("# ncu --set full --clock-control none; source %s ; mean over the captured launches of each kernel\n" % src)
+        for k, lst in sorted(per.items()):
+            f.write("kernel: %s  (%d launches captured)\n" % (k, len(lst)))
+            for m in WANT:
+                if m in hdr:
+                    vals = [_num(d[m]) for d in lst if _num(d[m]) is not None]
+                    if vals:
+                        f.write("  %-66s %14.6g %s\n" % (m, sum(vals) / len(vals), units[hdr.index(m)]))
+            for m in hdr:
+                if "issue_stalled" in m and "per_issue_active" in m:
+                    vals = [_num(d[m]) for d in lst if _num(d[m]) is not None]
+                    if vals and sum(vals) / len(vals) > 0.4:
+                        f.write("  stall %-60s %.2f\n" % (m.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), sum(vals) / len(vals)))
+            tot = 0.0
+            for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                if m in hdr:
+                    u = scale.get(units[hdr.index(m)], 1.0)
+                    vals = [_num(d[m]) * u for d in lst if _num(d[m]) is not None]
+                    tot += sum(vals) / max(len(vals), 1)
+            traffic[k.replace("tob::", "")] = tot
+            f.write("  dram bytes per launch (read+write)                                   %.0f\n\n" % tot)
+    if workload:
+        tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_traffic.json")
+        cur = json.load(open(tj)) if os.path.exists(tj) else {}
+        cur[workload] = traffic
+        cur.setdefault("_note", "dram__bytes_read.sum + dram__bytes_write.sum per launch from one ncu --set full capture "
+                                "(profiles/run_ncu.sh); keyed by bench workload name, then kernel")
+        json.dump(cur, open(tj, "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "rawcsv": rawcsv}[sys.argv[1]](*sys.argv[2:])
