@@ -34,7 +34,8 @@ typedef struct tob_params {
   int32_t piece_num;     /* Bezier pieces per robot (order 5, 6 control points each) */
   int32_t res;           /* sub-segments per piece; n_tr = piece_num*res */
   int32_t uav_num;       /* robots resident in this context */
-  int32_t optimal_plane; /* must be 0 (3D.json); persistent-plane mode is a "next" row */
+  int32_t optimal_plane; /* is_optimal_plane: 0 (3D.json) = planes rebuilt every iteration; 1 = persistent planes refined by
+                          * Optimal_plane::optimal_cd / self_optimal_cd (see tob_planes_reset) */
   double lambda;         /* barrier weight */
   double margin;         /* barrier activation distance d-hat */
   double offset;         /* safety distance */
@@ -108,6 +109,26 @@ int tob_plane_hulls_batch(tob_ctx* ctx, const double* P0, const double* P1, int 
 
 /* Optimal_plane::optimal_d (Optimal_plane.h:13-71): 1-D Newton on d for n (P0, P1, c) triples; d_io in/out */
 int tob_refine_d_batch(tob_ctx* ctx, const double* P0, const double* P1, const double* c, int n, double* d_io);
+
+/* Optimal_plane::optimal_cd (Optimal_plane.h:160-293): Newton on the tangent angles of c for n (sub-segment P 6x3
+ * column-major, obstacle point q) pairs, d = -c.q - offset; c (n x 3) and d_io (n) in/out.  capped[i] != 0 (may be NULL):
+ * pair i left through a loop cap instead of one of the reference's two exits (its loops are unbounded). */
+int tob_optimal_cd_batch(tob_ctx* ctx, const double* P, const double* q, int n, double* c, double* d_io, uint8_t* capped);
+/* Optimal_plane::self_optimal_cd (Optimal_plane.h:620-773): (theta, phi, d) Newton for n inter-robot pairs */
+int tob_self_optimal_cd_batch(tob_ctx* ctx, const double* P0, const double* P1, int n, double* c, double* d_io, uint8_t* capped);
+
+/* ---- persistent planes (tob_params.optimal_plane = 1) ---------------------------------------------------------------
+ * Replaces the globals is_seperate / seperate_c / seperate_d (CCDUtils.cpp:34-36, sized N_tr x N_pts in
+ * Main/admmPathPlanning3D.cpp:342-351) and is_self_seperate / self_seperate_c / _d (CCDUtils.cpp:30-32,
+ * Main/multiPathPlanning3D.cpp:450-464).  The obstacle set is a sorted sparse list on the device (single-UAV contexts and
+ * batched independent problems; the multi-UAV separate_plane of the reference has no persistent branch), the inter-robot
+ * set a dense (slot, pair) table.  Every plane pass (tob_separate_planes, tob_admm_iterate, tob_optimization) adds the
+ * planes of pairs that were not live and refines ALL live planes, like Optimization3D_admm.h:126-193 /
+ * Optimization3D_multi.h:271-339.  tob_planes_reset empties both sets (also done by tob_set_params and a cloud upload). */
+int tob_planes_reset(tob_ctx* ctx);
+/* live obstacle planes in (row, position in the sorted cloud) order: rows[k] = robot*n_tr + tr, ids[k] = original point id
+ * (cloud-local for batched clouds), c (k x 3), d.  *total = live count; arrays are filled only when total <= cap. */
+int tob_live_planes(tob_ctx* ctx, uint32_t* rows, uint32_t* ids, double* c, double* d, uint64_t cap, uint64_t* total);
 
 /* ---- separating planes (replaces Optimization3D_admm::separate_plane, Optimization3D_admm.h:69-197, and
  *      Optimization3D_multi::separate_plane :176-235 / ::separate_self :237-342) ------------------------------ */
@@ -210,6 +231,8 @@ typedef struct tob_counters {
   uint64_t self_pairs;           /* inter-robot segment pairs evaluated */
   uint64_t line_search_trials;
   uint64_t barrier_terms;        /* (control point, plane) terms inside the barrier band (d < margin) that were evaluated */
+  uint64_t live_planes;          /* persistent-plane mode: live (sub-segment, point) planes */
+  uint64_t refine_capped;        /* plane refinements stopped by a loop cap (the reference's loops are unbounded) */
 } tob_counters;
 int tob_get_counters(const tob_ctx* ctx, tob_counters* out);
 int tob_reset_counters(tob_ctx* ctx);

@@ -167,6 +167,32 @@ class _Base:
         self._f("optimal_d")(_d(F(P0)), _d(F(P1)), _d(F(c)), C.byref(dd))
         return dd.value
 
+    # ---- persistent-plane mode (Params.optimal_plane = 1)
+    def optimal_cd(self, P, q, c, d):
+        """Optimal_plane::optimal_cd: refined (c, d) of one (sub-segment, point) plane"""
+        cc = np.array(c, dtype=np.float64); dd = C.c_double(d)
+        self._f("optimal_cd")(_d(F(P)), _d(np.ascontiguousarray(q, dtype=np.float64)), _d(cc), C.byref(dd))
+        return cc, dd.value
+
+    def self_optimal_cd(self, P0, P1, c, d):
+        """Optimal_plane::self_optimal_cd: refined (c, d) of one inter-robot plane"""
+        cc = np.array(c, dtype=np.float64); dd = C.c_double(d)
+        self._f("self_optimal_cd")(_d(F(P0)), _d(F(P1)), _d(cc), C.byref(dd))
+        return cc, dd.value
+
+    def reset_persistent_planes(self):
+        """empties is_seperate / is_self_seperate (the state init_variable allocates); call after setup + init_pointcloud"""
+        self._f("reset_persistent_planes")()
+
+    def live_planes(self):
+        """(tr, point id, c, d) of the live obstacle planes in (tr, id) order"""
+        f = self._f("live_planes", C.c_long)
+        n = f(None, None, None, None, C.c_long(0))
+        tr = np.zeros(max(n, 1), dtype=np.uint32); ids = np.zeros(max(n, 1), dtype=np.uint32)
+        c = np.zeros((max(n, 1), 3)); d = np.zeros(max(n, 1))
+        f(_u(tr), _u(ids), _d(c), _d(d), C.c_long(n))
+        return tr[:n], ids[:n], c[:n], d[:n]
+
     # ---- planes
     def separate_plane(self, spline, cap=1 << 20):
         p = self.p

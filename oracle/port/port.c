@@ -29,7 +29,9 @@ static const int kAxes[KDOP_AXES][3] = {   /* HighOrderCCD/Utils/CCDUtils.cpp:56
 
 void port_setup(int piece_num, int res, int uav_num, double lambda, double margin, double offset, double mu, double vel_limit,
                 double acc_limit, double ks, double kt, int optimal_plane) {
-  (void)optimal_plane;
+  G.optimal_plane = optimal_plane;
+  free(G.is_sep); free(G.sep_cd); free(G.is_self_sep); free(G.self_sep_cd);      /* sized by n_tr / uav_num: start empty */
+  G.is_sep = NULL; G.sep_cd = NULL; G.is_self_sep = NULL; G.self_sep_cd = NULL;
   const int N = ORDER, K = 3;
   G.piece_num = piece_num; G.res = res; G.uav_num = uav_num; G.n_tr = piece_num * res;
   G.T = (N + 1) + (piece_num - 1) * (N + 1 - 3);                       /* admmPathPlanning3D.cpp:255 */
@@ -143,6 +145,8 @@ static struct {
 } grid;
 
 void port_init_pointcloud(const double *V, int n) {
+  free(G.is_sep); free(G.sep_cd); free(G.is_self_sep); free(G.self_sep_cd);      /* sized by n_pts: start empty */
+  G.is_sep = NULL; G.sep_cd = NULL; G.is_self_sep = NULL; G.self_sep_cd = NULL;
   free(G.V);
   G.V = (double *)malloc(sizeof(double) * 3 * (size_t)n);
   memcpy(G.V, V, sizeof(double) * 3 * (size_t)n);
@@ -498,6 +502,26 @@ void port_optimal_d(const double *P0, const double *P1, const double *c, double 
   optimal_d(A, B, c, d);
 }
 
+/* the persistent state of Main/admmPathPlanning3D.cpp:342-351 and Main/multiPathPlanning3D.cpp:450-464, emptied */
+void port_reset_persistent_planes(void) {
+  free(G.is_sep); free(G.sep_cd); free(G.is_self_sep); free(G.self_sep_cd);
+  size_t n = (size_t)G.n_tr * (size_t)(G.n_pts > 0 ? G.n_pts : 1), m = (size_t)G.n_tr * G.uav_num * G.uav_num;
+  G.is_sep = (unsigned char *)calloc(n, 1); G.sep_cd = (double *)calloc(4 * n, sizeof(double));
+  G.is_self_sep = (unsigned char *)calloc(m, 1); G.self_sep_cd = (double *)calloc(4 * m, sizeof(double));
+}
+long port_live_planes(unsigned *tr, unsigned *id, double *c, double *d, long cap) {
+  long n = 0;
+  if (!G.is_sep) return 0;
+  for (int t = 0; t < G.n_tr; t++)
+    for (int k = 0; k < G.n_pts; k++)
+      if (G.is_sep[(size_t)t * G.n_pts + k]) {
+        const double *s = G.sep_cd + 4 * ((size_t)t * G.n_pts + k);
+        if (n < cap) { tr[n] = (unsigned)t; id[n] = (unsigned)k; c[3 * n] = s[0]; c[3 * n + 1] = s[1]; c[3 * n + 2] = s[2]; d[n] = s[3]; }
+        n++;
+      }
+  return n;
+}
+
 /* ragged plane lists of one robot */
 typedef struct { int n_tr; long *cnt, *cap; double **c; double **d; } Planes;
 static void planes_init(Planes *p, int n_tr) {
@@ -536,8 +560,10 @@ static long planes_to_csr(const Planes *p, unsigned *off, double *c, double *d, 
   return n;
 }
 
-/* Optimization3D_admm::separate_plane (HighOrderCCD/Optimization/Optimization3D_admm.h:69-197, optimal_plane = 0) */
-static void separate_plane(const double *spline, Planes *pl) {
+/* Optimization3D_admm::separate_plane (HighOrderCCD/Optimization/Optimization3D_admm.h:69-197); `persistent`: the
+ * is_optimal_plane branches :126-145 (a pair that separated once keeps its plane) and :164-193 (every live plane of the
+ * sub-segment is refined by optimal_cd and emitted in point-id order) */
+static void separate_plane_mode(const double *spline, Planes *pl, int persistent) {
   const double dist = G.offset + G.margin;
   const int np = G.n_pts;
   unsigned *ids = NULL;
@@ -551,11 +577,33 @@ static void separate_plane(const double *spline, Planes *pl) {
     for (long i = 0; i < n; i++) {
       double q[3] = {G.V[ids[i]], G.V[(size_t)np + ids[i]], G.V[(size_t)2 * np + ids[i]]};
       double B[1][3] = {{q[0], q[1], q[2]}}, c[3], d;
-      if (kdop_overlap(P, 6, B, 1, dist) && plane_point(P, q, dist, c, &d)) planes_push(pl, tr, c, d);
+      if (!kdop_overlap(P, 6, B, 1, dist)) continue;
+      if (persistent) {
+        size_t at = (size_t)tr * np + ids[i];
+        if (!G.is_sep[at] && plane_point(P, q, dist, c, &d)) {
+          G.is_sep[at] = 1;
+          G.sep_cd[4 * at] = c[0]; G.sep_cd[4 * at + 1] = c[1]; G.sep_cd[4 * at + 2] = c[2]; G.sep_cd[4 * at + 3] = d;
+        }
+      } else if (plane_point(P, q, dist, c, &d)) planes_push(pl, tr, c, d);
     }
+    if (persistent)
+      for (int ob = 0; ob < np; ob++) {
+        size_t at = (size_t)tr * np + ob;
+        if (!G.is_sep[at]) continue;
+        double q[3] = {G.V[ob], G.V[(size_t)np + ob], G.V[(size_t)2 * np + ob]};
+        double *s = G.sep_cd + 4 * at;
+        port_optimal_cd_impl(P, q, s, s + 3);
+        planes_push(pl, tr, s, s[3]);
+      }
   }
   free(ids);
 }
+static void separate_plane(const double *spline, Planes *pl) {
+  if (G.optimal_plane && !G.is_sep) port_reset_persistent_planes();
+  separate_plane_mode(spline, pl, G.optimal_plane);
+}
+/* Optimization3D_multi::separate_plane (Optimization3D_multi.h:176-235) has no is_optimal_plane branch */
+static void separate_plane_multi(const double *spline, Planes *pl) { separate_plane_mode(spline, pl, 0); }
 long port_separate_plane(const double *spline, unsigned *off, double *c, double *d, long cap) {
   Planes pl;
   planes_init(&pl, G.n_tr);
@@ -566,10 +614,12 @@ long port_separate_plane(const double *spline, unsigned *off, double *c, double 
   return n;
 }
 
-/* Optimization3D_multi::separate_self (Optimization/Optimization3D_multi.h:237-342, optimal_plane = 0): appends to the
- * lists of both robots of every accepted pair */
+/* Optimization3D_multi::separate_self (Optimization/Optimization3D_multi.h:237-342): appends to the lists of both robots of
+ * every accepted pair; is_optimal_plane: :271-284 (first separation is kept, no optimal_d) and :309-339 (all live pairs of
+ * the slot refined by self_optimal_cd, emitted in (p0, p1) order) */
 static void separate_self(const double *splines, int u, Planes *pls) {
   const double dist = G.offset + 2 * G.margin;
+  if (G.optimal_plane && !G.is_self_sep) port_reset_persistent_planes();
   const size_t ns = (size_t)3 * G.T;
   double (*Pl)[6][3] = malloc(sizeof(double[6][3]) * (size_t)u);
   double *lo = (double *)malloc(sizeof(double) * 3 * (size_t)u), *hi = (double *)malloc(sizeof(double) * 3 * (size_t)u);
@@ -580,12 +630,31 @@ static void separate_self(const double *splines, int u, Planes *pls) {
         if (!boxes_within(lo + 3 * p0, hi + 3 * p0, lo + 3 * p1, hi + 3 * p1, dist)) continue;
         if (!kdop_overlap(Pl[p0], 6, Pl[p1], 6, dist)) continue;
         double c[3], d;
+        if (G.optimal_plane) {
+          size_t at = ((size_t)tr * u + p0) * u + p1;
+          if (!G.is_self_sep[at] && plane_hulls(Pl[p0], Pl[p1], dist, c, &d)) {
+            G.is_self_sep[at] = 1;
+            G.self_sep_cd[4 * at] = c[0]; G.self_sep_cd[4 * at + 1] = c[1]; G.self_sep_cd[4 * at + 2] = c[2]; G.self_sep_cd[4 * at + 3] = d;
+          }
+          continue;
+        }
         if (!plane_hulls(Pl[p0], Pl[p1], dist, c, &d)) continue;
         optimal_d(Pl[p0], Pl[p1], c, &d);
         double cm[3] = {-c[0], -c[1], -c[2]};
         planes_push(&pls[p0], tr, c, d - 0.5 * G.offset);
         planes_push(&pls[p1], tr, cm, -d - 0.5 * G.offset);
       }
+    if (G.optimal_plane)
+      for (int p0 = 0; p0 < u; p0++)
+        for (int p1 = p0 + 1; p1 < u; p1++) {
+          size_t at = ((size_t)tr * u + p0) * u + p1;
+          if (!G.is_self_sep[at]) continue;
+          double *s = G.self_sep_cd + 4 * at;
+          port_self_optimal_cd_impl(Pl[p0], Pl[p1], s, s + 3);
+          double cm[3] = {-s[0], -s[1], -s[2]};
+          planes_push(&pls[p0], tr, s, s[3] - 0.5 * G.offset);
+          planes_push(&pls[p1], tr, cm, -s[3] - 0.5 * G.offset);
+        }
   }
   free(Pl); free(lo); free(hi);
 }
@@ -1156,7 +1225,7 @@ void port_optimization_multi(int coupled, int u, double *splines, double *piece_
   const int Pn = G.piece_num, T = G.T;
   const size_t ns = (size_t)3 * T, np = (size_t)18 * Pn;
   Planes *pls = (Planes *)malloc(sizeof(Planes) * (size_t)u);
-  for (int i = 0; i < u; i++) { planes_init(&pls[i], G.n_tr); separate_plane(splines + ns * i, &pls[i]); }
+  for (int i = 0; i < u; i++) { planes_init(&pls[i], G.n_tr); separate_plane_multi(splines + ns * i, &pls[i]); }
   separate_self(splines, u, pls);
   double *dirs = (double *)malloc(sizeof(double) * ns * (size_t)u), *tdir = (double *)malloc(sizeof(double) * (size_t)u);
   double *steps = (double *)malloc(sizeof(double) * (size_t)u);

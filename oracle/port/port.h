@@ -30,12 +30,23 @@ typedef struct {
   int n_pts;
   double *V;       /* n_pts x 3 col-major */
   double wolfe, gnorm;   /* the reference's globals of the same name (CCDUtils.cpp:8-15) */
+  /* persistent planes ("optimal_plane": 1): the reference's globals is_seperate / seperate_c / seperate_d (CCDUtils.cpp:34-36,
+   * dense N_tr x N_pts, Main/admmPathPlanning3D.cpp:342-351) and is_self_seperate / self_seperate_c / _d (:30-32) */
+  int optimal_plane;
+  unsigned char *is_sep;      /* n_tr x n_pts */
+  double *sep_cd;             /* n_tr x n_pts x 4 */
+  unsigned char *is_self_sep; /* n_tr x u x u */
+  double *self_sep_cd;        /* n_tr x u x u x 4 */
 } port_ctx;
 
 extern port_ctx g_port;
 
 /* port_gjk.c */
 void port_gjk_witness(const double (*A)[3], int na, const double (*B)[3], int nb, double *v);
+
+/* port_optplane.c */
+int port_optimal_cd_impl(const double (*P)[3], const double *q, double *c, double *d_io);
+int port_self_optimal_cd_impl(const double (*P0)[3], const double (*P1)[3], double *c, double *d_io);
 
 /* port_dense.c */
 int port_llt(const double *A, double *L, int n);                 /* 0 = Eigen::NumericalIssue */

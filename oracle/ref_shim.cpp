@@ -288,6 +288,11 @@ void ref_self_optimal_cd(const double* P0, const double* P1, double* c, double* 
 // the persistent state of Main/admmPathPlanning3D.cpp:342-351 and Main/multiPathPlanning3D.cpp:450-464, emptied.
 // dense N_tr x N_pts like the reference: only for small clouds.
 void ref_reset_persistent_planes() {
+#ifdef TRAJOPT_HOST_H   // built against the drop-in headers: the live planes are kept by the device context
+  tob_host::Session& S = tob_host::Session::get();
+  S.sync();
+  S.check(tob_planes_reset(S.ctx()), "tob_planes_reset");
+#endif
   int n_tr = subdivide_tree.size();
   size_t nv = g_vertex_list.size();
   is_seperate.assign(n_tr, std::vector<bool>(nv, false));
@@ -299,6 +304,14 @@ void ref_reset_persistent_planes() {
 }
 // live obstacle planes: (tr, point id) pairs with is_seperate set, in (tr, id) order; returns the count
 long ref_live_planes(unsigned* tr, unsigned* id, double* c, double* d, long cap) {
+#ifdef TRAJOPT_HOST_H
+  {
+    tob_host::Session& S = tob_host::Session::get();
+    uint64_t total = 0;
+    S.check(tob_live_planes(S.ctx(), tr, id, c, d, (uint64_t)cap, &total), "tob_live_planes");
+    return (long)total;
+  }
+#endif
   long n = 0;
   for (size_t t = 0; t < is_seperate.size(); t++)
     for (size_t k = 0; k < is_seperate[t].size(); k++)

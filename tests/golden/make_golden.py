@@ -4,6 +4,8 @@ port (oracle/port) and the CUDA path on machines where the reference is not avai
 
 single.npz : 1 UAV, bridge-shaped cloud (4000 pts, seed 21), 4 pieces
 multi.npz  : 4 UAVs crossing, floor/ceiling cloud (3000 pts, seed 23), 4 pieces
+optplane.npz : the same two scenes run with "optimal_plane": 1 (persistent planes refined by Optimal_plane::optimal_cd /
+             self_optimal_cd), plus per-pair refinement vectors
 """
 import os
 import sys
@@ -123,6 +125,95 @@ def multi():
     print("multi.npz: self planes", len(sd), "accepted hull pairs", int(np.sum(oks)), "self steps", out["self_steps"], out["couple_step"])
 
 
+def optplane():
+    out = {}
+    # ---- single UAV, persistent obstacle planes
+    sc = scenes.bridge(n_pts=4000, seed=21, n_pieces=4)
+    P = 4
+    o = oa.RefOracle(); o.setup(oa.Params(P, ks=sc["ks"], optimal_plane=1)); o.init_pointcloud(sc["V"]); o.reset_persistent_planes()
+    st = scenes.initial_states(sc)[0]
+    for i in range(1, 7):
+        st = o.optimization(st)
+        for k in ("spline", "p_slack", "t_slack", "p_lambda", "t_lambda"):
+            out["s_it%d_%s" % (i, k)] = st[k]
+        out["s_it%d_piece_time" % i] = st["piece_time"]; out["s_it%d_gnorm" % i] = st["gnorm"]
+        if i in (1, 3, 6):
+            tr, ids, c, d = o.live_planes()
+            out["s_it%d_live_tr" % i] = tr; out["s_it%d_live_id" % i] = ids; out["s_it%d_live_c" % i] = c; out["s_it%d_live_d" % i] = d
+    # per-pair optimal_cd on real candidates of the initial trajectory, started from the GJK plane
+    o.setup(oa.Params(P, ks=sc["ks"])); o.init_pointcloud(sc["V"])
+    sp = scenes.initial_states(sc)[0]["spline"]
+    off, ids = o.dcd_collision(sp, 0.2)
+    Pm = np.array([o.segment_points(sp, tr) for tr in range(P * 8)])
+    rng = np.random.default_rng(11)
+    pairs = [(tr, pid) for tr in range(P * 8) for pid in ids[off[tr]:off[tr + 1]]]
+    pairs = [pairs[i] for i in rng.choice(len(pairs), size=min(3000, len(pairs)), replace=False)]
+    rec = []
+    for tr, pid in pairs:
+        q = sc["V"][pid]
+        ok, c, d = o.opengjk(Pm[tr], q.reshape(1, 3), 0.2)
+        if ok:
+            c1, d1 = o.optimal_cd(Pm[tr], q, c, d)
+            rec.append((Pm[tr], q, c, d, c1, d1))
+        if len(rec) >= 400:
+            break
+    for j, nm in enumerate(("cd_P", "cd_q", "cd_c0", "cd_d0", "cd_c1", "cd_d1")):
+        out[nm] = np.array([r[j] for r in rec])
+    # ---- 4 UAVs crossing, persistent inter-robot planes
+    sc = scenes.cross(n_pts=3000, seed=23, n_pieces=4)
+    sc["way_points"] = sc["way_points"][:2] + sc["way_points"][4:6]
+    U = 4
+    o.setup(oa.Params(P, uav_num=U, ks=sc["ks"], optimal_plane=1)); o.init_pointcloud(sc["V"]); o.reset_persistent_planes()
+    sts = [scenes.init_state(scenes.init_spline_multi(wp)) for wp in sc["way_points"]]
+    # self_optimal_cd on the hull pairs of the initial trajectories
+    splines = [s["spline"] for s in sts]
+    rec = []
+    for tr in range(P * 8):
+        Pl = [o.segment_points(s, tr) for s in splines]
+        for a in range(U):
+            for b in range(a + 1, U):
+                ok, c, d = o.selfgjk(Pl[a], Pl[b], 0.3)
+                if ok:
+                    c1, d1 = o.self_optimal_cd(Pl[a], Pl[b], c, d)
+                    rec.append((Pl[a], Pl[b], c, d, c1, d1))
+    # ... and on random near-touching hull pairs.  self_optimal_cd shifts an indefinite 3x3 Hessian to a smallest eigenvalue
+    # of 1e-8 and may take thousands of tiny steps, so part of the pairs are ill-conditioned (the result moves by 1e-3 when
+    # an input moves by one ulp): `scd_stable` marks the pairs whose reference result is insensitive to such a perturbation;
+    # only those are compared tightly, the others through the stopping criterion and the barrier energy.
+    rng = np.random.default_rng(5)
+    while len(rec) < 300:
+        base = rng.uniform(-1, 1, 3)
+        dirn = rng.normal(size=3); dirn /= np.linalg.norm(dirn)
+        P0 = np.asfortranarray(base + np.outer(np.linspace(0, 0.6, 6), dirn) + rng.normal(scale=0.02, size=(6, 3)))
+        dir2 = rng.normal(size=3); dir2 /= np.linalg.norm(dir2)
+        sep = rng.normal(size=3); sep /= np.linalg.norm(sep)
+        P1 = np.asfortranarray(base + sep * rng.uniform(0.12, 0.3) + np.outer(np.linspace(-0.3, 0.3, 6), dir2) + rng.normal(scale=0.02, size=(6, 3)))
+        ok, c, d = o.selfgjk(P0, P1, 0.3)
+        # feasible pairs only (hull distance > offset, what the inter-robot CCD step maintains): from an infeasible start
+        # the reference's barrier is +inf / log of a negative number and the plane degenerates to NaN
+        if not ok or not np.isfinite(c).all() or np.linalg.norm(o.gjk(P0, P1)) < 0.105:
+            continue
+        c1, d1 = o.self_optimal_cd(P0, P1, c, d)
+        rec.append((P0, P1, c, d, c1, d1))
+    stable = []
+    for P0, P1, c, d, c1, d1 in rec:
+        c2, d2 = o.self_optimal_cd(P0 * (1 + 2e-16), P1, c, d)
+        stable.append(max(np.abs(c2 - c1).max(), abs(d2 - d1)) < 1e-9)
+    out["scd_stable"] = np.array(stable)
+    for j, nm in enumerate(("scd_P0", "scd_P1", "scd_c0", "scd_d0", "scd_c1", "scd_d1")):
+        out[nm] = np.array([r[j] for r in rec])
+    for i in range(1, 5):
+        sts = o.optimization_multi(sts, coupled=False)
+        for u, s in enumerate(sts):
+            out["m_it%d_u%d_spline" % (i, u)] = s["spline"]
+            out["m_it%d_u%d_piece_time" % (i, u)] = s["piece_time"]
+        out["m_it%d_gnorm" % i] = sts[0]["gnorm"]
+    np.savez_compressed(os.path.join(HERE, "optplane.npz"), **out)
+    print("optplane.npz: live planes", len(out["s_it6_live_d"]), "cd pairs", len(out["cd_d1"]), "self pairs", len(out["scd_d1"]),
+          "of which stable", int(np.sum(out["scd_stable"])))
+
+
 if __name__ == "__main__":
-    single()
-    multi()
+    which = sys.argv[1:] or ["single", "multi", "optplane"]
+    for w in which:
+        {"single": single, "multi": multi, "optplane": optplane}[w]()

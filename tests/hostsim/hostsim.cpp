@@ -7,6 +7,7 @@
 
 #include "../../traj-opt-admm_b200/csrc/gjk.cuh"
 #include "../../traj-opt-admm_b200/csrc/ctx.cuh"
+#include "../../traj-opt-admm_b200/csrc/optplane.cuh"
 
 using namespace tob;
 
@@ -87,6 +88,18 @@ int hs_refine_d(const double* P0, const double* P1, const double* c, double offs
   double a[6][3], b[6][3];
   load<6>(P0, a); load<6>(P1, b);
   return refine_d(a, b, c, offset, margin, d, 10000);
+}
+
+int hs_optimal_cd(const double* P, const double* q, double offset, double margin, double* c, double* d) {
+  double a[6][3];
+  load<6>(P, a);
+  return optimal_cd(a, q, offset, margin, c, d);
+}
+
+int hs_self_optimal_cd(const double* P0, const double* P1, double offset, double margin, double* c, double* d) {
+  double a[6][3], b[6][3];
+  load<6>(P0, a); load<6>(P1, b);
+  return self_optimal_cd(a, b, offset, margin, c, d);
 }
 
 int hs_make_tables(int piece_num, int res, double* basis, double* weight, double* convert, double* mdyn, double* kdop) {

@@ -14,6 +14,7 @@
 
 #include "ctx.cuh"
 #include "gjk.cuh"
+#include "optplane.cuh"
 
 static std::string g_create_err;
 
@@ -233,9 +234,11 @@ static int run_checked(tob_ctx* c, F&& launch) {
   for (int attempt = 0; attempt < 8; attempt++) {
     TOB_TRY(launch());
     TOB_TRY(sync_counts(c));
-    if (!(c->h_dc->overflow & TOB_OVF_CAND)) return 0;
+    if (!(c->h_dc->overflow & (TOB_OVF_CAND | TOB_OVF_LIVE))) return 0;
+    const uint32_t ovf = c->h_dc->overflow;
     TOB_TRY(clear_overflow(c));
-    TOB_TRY(grow_cand_capacity(c, c->h_dc->n_cand));
+    if (ovf & TOB_OVF_CAND) TOB_TRY(grow_cand_capacity(c, c->h_dc->n_cand));
+    if (ovf & TOB_OVF_LIVE) TOB_TRY(ensure_live_buffers(c, (uint64_t)c->h_dc->n_live + c->h_dc->n_new + 1));
   }
   return fail_msg(c, "candidate buffers keep overflowing");
 }
@@ -312,6 +315,7 @@ static int exchange(tob_ctx* c, DBuf<double>& buf, size_t elems_per_robot) {
 static int ensure_iter_buffers(tob_ctx* c) {
   const size_t rows = (size_t)c->rows_all(), U = (size_t)c->n_robots(), P = (size_t)c->prm.piece_num;
   TOB_TRY(ensure_query_buffers(c));
+  if (c->live_planes()) TOB_TRY(ensure_live_buffers(c, c->live_cap ? c->live_cap : 1));
   TOB_CUDA(c, c->geo.P.ensure(18 * rows)); TOB_CUDA(c, c->geo.D.ensure(18 * rows)); TOB_CUDA(c, c->geo.box.ensure(6 * rows));
   TOB_CUDA(c, c->geo.klo.ensure(TOB_KDOP_AXES * rows)); TOB_CUDA(c, c->geo.khi.ensure(TOB_KDOP_AXES * rows));
   TOB_CUDA(c, c->row_e.ensure(2 * rows * TOB_LS_TRIALS)); TOB_CUDA(c, c->row_bad.ensure(rows * TOB_LS_TRIALS));
@@ -462,10 +466,12 @@ static int iterate_once(tob_ctx* c, int mode, double* gnorm_out) {
       TOB_TRY(sync_counts(c));
       if (c->h_dc->iters_done != done0) break;                 // committed on the device
       if (c->h_dc->overflow & TOB_OVF_SELFHITS) return fail_msg(c, "inter-robot CCD: more than 16384 colliding pairs");
-      if (c->h_dc->overflow & TOB_OVF_CAND) {                  // nothing was changed: grow and run the iteration again
+      if (c->h_dc->overflow & (TOB_OVF_CAND | TOB_OVF_LIVE)) {  // nothing was changed: grow and run the iteration again
         if (attempt >= 8) return fail_msg(c, "candidate buffers keep overflowing");
+        const uint32_t ovf = c->h_dc->overflow;
         TOB_TRY(clear_overflow(c));
-        TOB_TRY(grow_cand_capacity(c, c->h_dc->n_cand));
+        if (ovf & TOB_OVF_CAND) TOB_TRY(grow_cand_capacity(c, c->h_dc->n_cand));
+        if (ovf & TOB_OVF_LIVE) TOB_TRY(ensure_live_buffers(c, (uint64_t)c->h_dc->n_live + c->h_dc->n_new + 1));
         continue;
       }
       // a robot needs more than the rungs launched ahead: finish its search from the host, then commit
@@ -552,9 +558,9 @@ int tob_device_info(const tob_ctx* c, int* sm_count, int* cc_major, int* cc_mino
 int tob_set_params(tob_ctx* c, const tob_params* p) {
   if (!c || !p) return 1;
   if (p->piece_num < 1 || p->res < 1 || p->res > 16 || p->uav_num < 1) return fail_msg(c, "tob_set_params: bad sizes");
-  if (p->optimal_plane) return fail_msg(c, "optimal_plane=1 (persistent planes) is not supported");
   cudaSetDevice(c->device);
   c->prm = *p;
+  c->prm.optimal_plane = p->optimal_plane ? 1 : 0;
   c->n_tr = p->piece_num * p->res;
   c->T = 6 + 3 * (p->piece_num - 1);
   c->have_params = true;
@@ -566,6 +572,7 @@ int tob_set_params(tob_ctx* c, const tob_params* p) {
     c->cloud_n1.clear(); c->cloud_l1.clear(); c->h_row_task.clear();
     c->n_pts = 0;
   }
+  TOB_TRY(reset_live_planes(c));     // is_seperate / is_self_seperate start empty (init_variable)
   return alloc_states(c);
 }
 
@@ -614,12 +621,14 @@ int tob_get_tables(const tob_ctx* c, double* basis, double* weight, double* conv
 int tob_cloud_upload(tob_ctx* c, const double* V, uint32_t n) {
   if (!c || !V) return 1;
   cudaSetDevice(c->device);
+  TOB_TRY(reset_live_planes(c));     // live planes are keyed by the position in the sorted cloud
   return lbvh_build(c, V, n);
 }
 int tob_cloud_upload_batch(tob_ctx* c, const double* const* V, const uint32_t* n, int n_clouds) {
   if (!c || !V || !n) return 1;
   TOB_TRY(need(c, false, false));
   cudaSetDevice(c->device);
+  TOB_TRY(reset_live_planes(c));
   return lbvh_build_batch(c, V, n, n_clouds);
 }
 uint32_t tob_cloud_size(const tob_ctx* c) { return c ? c->n_pts : 0; }
@@ -755,6 +764,29 @@ __global__ void k_plane_hulls_batch(const double* P0, const double* P1, int n, d
   d[i] = dd;
 }
 
+__global__ void k_optimal_cd_batch(const double* P, const double* q, int n, double offset, double margin, double* cc, double* d,
+                                   uint8_t* capped) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[6][3], qq[3], c3[3] = {cc[3 * (size_t)i], cc[3 * (size_t)i + 1], cc[3 * (size_t)i + 2]}, dd = d[i];
+  for (int j = 0; j < 6; j++) for (int k = 0; k < 3; k++) a[j][k] = P[(size_t)i * 18 + k * 6 + j];
+  for (int k = 0; k < 3; k++) qq[k] = q[(size_t)i * 3 + k];
+  capped[i] = (uint8_t)optimal_cd(a, qq, offset, margin, c3, &dd);
+  cc[3 * (size_t)i] = c3[0]; cc[3 * (size_t)i + 1] = c3[1]; cc[3 * (size_t)i + 2] = c3[2];
+  d[i] = dd;
+}
+
+__global__ void k_self_optimal_cd_batch(const double* P0, const double* P1, int n, double offset, double margin, double* cc, double* d,
+                                        uint8_t* capped) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[6][3], b[6][3], c3[3] = {cc[3 * (size_t)i], cc[3 * (size_t)i + 1], cc[3 * (size_t)i + 2]}, dd = d[i];
+  for (int j = 0; j < 6; j++) for (int k = 0; k < 3; k++) { a[j][k] = P0[(size_t)i * 18 + k * 6 + j]; b[j][k] = P1[(size_t)i * 18 + k * 6 + j]; }
+  capped[i] = (uint8_t)self_optimal_cd(a, b, offset, margin, c3, &dd);
+  cc[3 * (size_t)i] = c3[0]; cc[3 * (size_t)i + 1] = c3[1]; cc[3 * (size_t)i + 2] = c3[2];
+  d[i] = dd;
+}
+
 __global__ void k_refine_d_batch(const double* P0, const double* P1, const double* cc, int n, double offset, double margin, double* d) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -860,6 +892,72 @@ int tob_refine_d_batch(tob_ctx* c, const double* P0, const double* P1, const dou
 }
 
 // ---- planes ------------------------------------------------------------------------------------------------------------
+int tob_optimal_cd_batch(tob_ctx* c, const double* P, const double* q, int n, double* cc, double* d_io, uint8_t* capped) {
+  TOB_TRY(need(c, false, false));
+  cudaSetDevice(c->device);
+  if (n <= 0) return 0;
+  TOB_CUDA(c, c->scratch.ensure((size_t)n * 25 + 8));
+  TOB_CUDA(c, c->scratch8.ensure(n));
+  double *dP = c->scratch.p, *dq = dP + (size_t)18 * n, *dc3 = dq + (size_t)3 * n, *dd = dc3 + (size_t)3 * n;
+  TOB_CUDA(c, cudaMemcpyAsync(dP, P, (size_t)18 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(dq, q, (size_t)3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(dc3, cc, (size_t)3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(dd, d_io, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  k_optimal_cd_batch<<<div_up(n, 64), 64, 0, c->stream>>>(dP, dq, n, c->prm.offset, c->prm.margin, dc3, dd, c->scratch8.p);
+  TOB_LAUNCH_CHECK(c);
+  TOB_CUDA(c, cudaMemcpyAsync(cc, dc3, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(d_io, dd, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (capped) TOB_CUDA(c, cudaMemcpyAsync(capped, c->scratch8.p, n, cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int tob_self_optimal_cd_batch(tob_ctx* c, const double* P0, const double* P1, int n, double* cc, double* d_io, uint8_t* capped) {
+  TOB_TRY(need(c, false, false));
+  cudaSetDevice(c->device);
+  if (n <= 0) return 0;
+  TOB_CUDA(c, c->scratch.ensure((size_t)n * 40 + 8));
+  TOB_CUDA(c, c->scratch8.ensure(n));
+  double *d0 = c->scratch.p, *d1 = d0 + (size_t)18 * n, *dc3 = d1 + (size_t)18 * n, *dd = dc3 + (size_t)3 * n;
+  TOB_CUDA(c, cudaMemcpyAsync(d0, P0, (size_t)18 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(d1, P1, (size_t)18 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(dc3, cc, (size_t)3 * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(dd, d_io, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  k_self_optimal_cd_batch<<<div_up(n, 64), 64, 0, c->stream>>>(d0, d1, n, c->prm.offset, c->prm.margin, dc3, dd, c->scratch8.p);
+  TOB_LAUNCH_CHECK(c);
+  TOB_CUDA(c, cudaMemcpyAsync(cc, dc3, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaMemcpyAsync(d_io, dd, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (capped) TOB_CUDA(c, cudaMemcpyAsync(capped, c->scratch8.p, n, cudaMemcpyDeviceToHost, c->stream));
+  TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int tob_planes_reset(tob_ctx* c) {
+  if (!c) return 1;
+  cudaSetDevice(c->device);
+  return reset_live_planes(c);
+}
+
+int tob_live_planes(tob_ctx* c, uint32_t* rows, uint32_t* ids, double* cc, double* dd, uint64_t cap, uint64_t* total) {
+  TOB_TRY(need(c, false, false));
+  cudaSetDevice(c->device);
+  TOB_TRY(sync_counts(c));
+  const uint64_t n = c->live_key.p ? c->h_dc->n_live : 0;
+  if (total) *total = n;
+  if (!n || n > cap || !rows || !ids || !cc || !dd) return 0;
+  std::vector<unsigned long long> key(n);
+  std::vector<double> pl(4 * n);
+  TOB_CUDA(c, cudaMemcpy(key.data(), c->live_key.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  TOB_CUDA(c, cudaMemcpy(pl.data(), c->live_pl.p, 4 * n * sizeof(double), cudaMemcpyDeviceToHost));
+  for (uint64_t k = 0; k < n; k++) {
+    const uint32_t p = (uint32_t)(key[k] & 0xffffffffu);
+    rows[k] = (uint32_t)(key[k] >> 32);
+    ids[k] = p < c->h_pid.size() ? c->h_pid[p] : p;
+    cc[3 * k] = pl[4 * k]; cc[3 * k + 1] = pl[4 * k + 1]; cc[3 * k + 2] = pl[4 * k + 2]; dd[k] = pl[4 * k + 3];
+  }
+  return 0;
+}
+
 int tob_separate_self(tob_ctx* c, const double* splines, int n_robots, uint32_t* offsets, double* cc, double* dd, uint64_t cap,
                       uint64_t* total) {
   TOB_TRY(need(c, true, false));
@@ -1283,6 +1381,8 @@ int tob_get_counters(const tob_ctx* cc, tob_counters* out) {
   out->ccd_candidates = c->h_dc->ccd_candidates;
   out->energy_plane_evals = c->h_dc->energy_plane_evals;
   out->barrier_terms = c->h_dc->barrier_terms;
+  out->live_planes = c->h_dc->n_live;
+  out->refine_capped = c->h_dc->opt_capped;
   return 0;
 }
 int tob_reset_counters(tob_ctx* c) {
@@ -1295,7 +1395,8 @@ int tob_reset_counters(tob_ctx* c) {
 
 static const char* kKernelNames[K_COUNT] = {"k_rows", "k_bp_count", "k_bp_fill", "k_bp_top+k_np_top", "k_narrow",
                                             "k_pack", "k_self_planes", "k_row_energy", "k_robot_ls", "k_row_grad",
-                                            "k_piece", "k_solve_bcr", "k_bp_ccd", "k_self_ccd_filter", "k_slack", "misc"};
+                                            "k_piece", "k_solve_bcr", "k_bp_ccd", "k_self_ccd_filter", "k_slack", "misc",
+                                            "k_live_refine"};
 
 int tob_profile_enable(tob_ctx* c, int on) {
   if (!c) return 1;

@@ -43,6 +43,7 @@ struct DBuf {
 // state-changing kernels at the end of the iteration into no-ops; the host looks at this struct ONCE per iteration.
 #define TOB_OVF_CAND 1u      // broadphase produced more candidates than cand_cap
 #define TOB_OVF_SELFHITS 4u  // inter-robot CCD hit list overflow
+#define TOB_OVF_LIVE 8u      // persistent-plane mode: live planes + new planes exceed live_cap
 #define TOB_LS_MAXROUNDS 8   // most Armijo rounds launched ahead of the host (the count is a run-time choice, see ls_policy)
 struct DevCounts {
   uint32_t n_cand;           // candidates of the last broadphase fill (may exceed the capacity -> overflow)
@@ -54,6 +55,11 @@ struct DevCounts {
   uint32_t iters_done;       // iterations fully committed (apply step + slack update ran)
   uint32_t pad;
   unsigned long long dcd_candidates, planes, ccd_candidates, energy_plane_evals, barrier_terms;   // cumulative since reset
+  // persistent-plane mode ("optimal_plane": 1)
+  uint32_t n_live;           // live (row, point) obstacle planes
+  uint32_t n_live_next;      // n_live + new planes of this pass (written by the merge, consumed by the refinement)
+  uint32_t n_new;            // planes accepted for pairs that were not live yet
+  uint32_t opt_capped;       // plane refinements that hit a loop cap (the reference's loops are unbounded)
 };
 
 // per-row (robot x sub-segment) geometry produced by segments.cu, indexed by GLOBAL row = robot*n_tr + tr
@@ -135,6 +141,14 @@ struct tob_ctx {
   tob::DBuf<uint32_t> row_nob, row_ntot;
   uint64_t n_planes = 0;
 
+  // persistent planes ("optimal_plane": 1; the reference's is_seperate / seperate_c / seperate_d, Main/admmPathPlanning3D.cpp
+  // :342-351, as a sorted sparse set instead of dense N_tr x N_pts arrays): key = row << 32 | index into the sorted cloud
+  tob::DBuf<unsigned long long> live_key, live_key_t, new_key;
+  tob::DBuf<double> live_pl, live_pl_t, new_pl;   // x 4 (cx, cy, cz, d)
+  uint64_t live_cap = 0;
+  tob::DBuf<uint32_t> self_live;      // n_tr x npairs: is_self_seperate (Main/multiPathPlanning3D.cpp:450-464)
+  tob::DBuf<double> self_lpl;         // n_tr x npairs x 4: self_seperate_c / _d
+
   // inter-robot scratch
   tob::DBuf<double> self_pl;          // n_tr x npairs x 4
   tob::DBuf<uint32_t> self_ok;        // n_tr x npairs
@@ -181,6 +195,9 @@ struct tob_ctx {
   double prof_ms[32] = {0};
   uint64_t prof_n[32] = {0};
 
+  // persistent OBSTACLE planes exist only on the single-UAV path (Optimization3D_admm::separate_plane :126-193; the multi-UAV
+  // separate_plane, Optimization3D_multi.h:176-235, has no such branch): one robot, or independent problems
+  bool live_planes() const { return prm.optimal_plane != 0 && (prm.uav_num == 1 || !cloud_n1.empty()); }
   int n_robots() const { return prm.uav_num; }
   int rows_all() const { return prm.uav_num * n_tr; }
 };
@@ -220,7 +237,7 @@ __device__ __forceinline__ bool iteration_blocked(const DevCounts* dc) {
 // kernel ids of the per-kernel timing (names in api.cu: kKernelNames)
 enum KernelId {
   K_ROWS = 0, K_BP_COUNT, K_BP_FILL, K_SCAN, K_NARROW, K_PACK, K_SELF_PLANES, K_ROW_ENERGY, K_ROBOT_ENERGY, K_ROW_GRAD,
-  K_PIECE, K_SOLVE, K_CCD, K_SELF_CCD, K_SLACK, K_LINESEARCH_MISC, K_COUNT
+  K_PIECE, K_SOLVE, K_CCD, K_SELF_CCD, K_SLACK, K_LINESEARCH_MISC, K_LIVE_REFINE, K_COUNT
 };
 
 // scoped CUDA-event pair around ONE kernel launch on the context's stream (no-op unless profiling is enabled)
@@ -266,6 +283,8 @@ int pack_planes_from_host(tob_ctx* c, int rb, int re, const uint32_t* offsets, c
 int ccd_position_steps(tob_ctx* c, int rb, int re);
 int self_planes(tob_ctx* c);
 int pack_self_only(tob_ctx* c);
+int ensure_live_buffers(tob_ctx* c, uint64_t need);     // persistent-plane set: grows preserving the live planes
+int reset_live_planes(tob_ctx* c);
 int self_ccd_steps(tob_ctx* c, int coupled, double* steps_dev);
 // barrier.cu
 int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* tstep, const double* ttime, int KT, int k0,

@@ -435,8 +435,9 @@ int ensure_query_buffers(tob_ctx* c) {
   TOB_CUDA(c, c->csum.ensure(c->cand_cap / 128 + 4)   /* >= chunks + 1 for any chunk size >= 128 */);
   TOB_CUDA(c, c->selfpre.ensure(rows + 2));
   TOB_CUDA(c, c->selfcnt.ensure(rows + 2));
-  TOB_CUDA(c, c->pl.ensure(4 * (c->cand_cap + self_max) + 4));
-  TOB_CUDA(c, c->pl_row.ensure(c->cand_cap + self_max + 1));
+  const size_t ob_max = c->cand_cap > c->live_cap ? c->cand_cap : c->live_cap;   // persistent mode: every live plane is listed
+  TOB_CUDA(c, c->pl.ensure(4 * (ob_max + self_max) + 4));
+  TOB_CUDA(c, c->pl_row.ensure(ob_max + self_max + 1));
   TOB_CUDA(c, c->pl_off.ensure(rows + 2));
   return 0;
 }

@@ -7,10 +7,15 @@
 //     atomicMax of the ladder exponent (Step::position_step, Step.h:21-110); inter-robot variants
 //     (Step::self_step :184-256, Step::couple_self_step :112-182)
 //   * packing of accepted planes into the per-row CSR the barrier kernels stream.
+//   * persistent-plane mode ("optimal_plane": 1): sorted sparse set of live (row, point) planes, merged with the planes
+//     of pairs that were not live yet and refined in place every iteration by Optimal_plane::optimal_cd
+//     (Optimization3D_admm.h:126-193); inter-robot planes kept per (slot, pair) and refined by self_optimal_cd
+//     (Optimization3D_multi.h:271-339).
 #include "ctx.cuh"
 #include "bp.cuh"
 #define TOB_GJK_INLINE
 #include "gjk.cuh"
+#include "optplane.cuh"
 
 namespace tob {
 
@@ -36,7 +41,18 @@ struct NarrowArgs {
   double* cpl;       // cap x 4
   uint32_t* cflag;   // cap
   uint32_t* csum;    // chunks + 1
+  const unsigned long long* live_key;   // persistent-plane mode: sorted keys of the live planes (else nullptr)
 };
+
+// index of the first key >= x in the sorted array k[0..n)
+__device__ __forceinline__ uint32_t lower_bound_u64(const unsigned long long* __restrict__ k, uint32_t n, unsigned long long x) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (k[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
 
 #define NP_THREADS 128
 #define NP_PER 4
@@ -51,6 +67,7 @@ __global__ void __launch_bounds__(NP_THREADS, 4) k_narrow(NarrowArgs a) {
   if (n > a.cap) return;
   const uint32_t n_chunks = (n + NP_CHUNK - 1) / NP_CHUNK;
   const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const uint32_t n_live = a.live_key ? a.dc->n_live : 0u;
   __syncthreads();
   for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     uint32_t n_surv = 0;   // uniform
@@ -82,6 +99,11 @@ __global__ void __launch_bounds__(NP_THREADS, 4) k_narrow(NarrowArgs a) {
     for (uint32_t sidx = tid; sidx < n_surv; sidx += NP_THREADS) {
       const uint32_t ii = chunk * NP_CHUNK + s_surv[sidx];
       const uint32_t row = a.cand_row[ii], p = a.cand_pt[ii];
+      if (n_live) {   // is_seperate[tr_id][ob_id] (Optimization3D_admm.h:128): a live pair keeps its plane
+        const unsigned long long key = ((unsigned long long)row << 32) | p;
+        const uint32_t at = lower_bound_u64(a.live_key, n_live, key);
+        if (at < n_live && a.live_key[at] == key) continue;
+      }
       const double pt[3] = {a.px[p], a.py[p], a.pz[p]};
       double P[6][3], c[3], d;
       load_pts6(a.P + (size_t)18 * row, P);
@@ -112,6 +134,10 @@ struct SelfArgs {
   double* self_pl;     // n_tr x npairs x 4
   uint32_t* self_ok;   // n_tr x npairs
   uint32_t* selfcnt;   // rows: accepted inter-robot planes per row (zeroed before the launch)
+  // persistent mode (is_optimal_plane): live flag + plane per (slot, pair); nullptr otherwise
+  uint32_t* live;
+  double* lpl;
+  DevCounts* dc;
 };
 
 __device__ __forceinline__ void pair_from_index(int idx, int U, int* p0, int* p1) {
@@ -133,8 +159,37 @@ __global__ void __launch_bounds__(64) k_self_planes(SelfArgs a) {
   bool hit = true;
   for (int k = 0; k < 3; k++)
     if (b0[3 + k] + a.dist < b1[k] || b0[k] > b1[3 + k] + a.dist) hit = false;
-  if (hit && kdop_sets_overlap(a.klo + TOB_KDOP_AXES * r0, a.khi + TOB_KDOP_AXES * r0, a.klo + TOB_KDOP_AXES * r1,
-                               a.khi + TOB_KDOP_AXES * r1, a.dist)) {
+  hit = hit && kdop_sets_overlap(a.klo + TOB_KDOP_AXES * r0, a.khi + TOB_KDOP_AXES * r0, a.klo + TOB_KDOP_AXES * r1,
+                                 a.khi + TOB_KDOP_AXES * r1, a.dist);
+  if (a.live) {
+    // Optimization3D_multi.h:271-339: a pair that ever separated keeps its plane; every live plane is refined by
+    // self_optimal_cd each iteration (also when the boxes no longer overlap) and always emitted.  Nothing is touched when
+    // the iteration is going to be repeated (candidate overflow).
+    if (a.dc->overflow) { a.self_ok[t] = 0; return; }
+    uint32_t lv = a.live[t];
+    if (!lv && !hit) { a.self_ok[t] = 0; return; }
+    double P0[6][3], P1[6][3], c[3], d;
+    load_pts6(a.P + 18 * r0, P0);
+    load_pts6(a.P + 18 * r1, P1);
+    double* st = a.lpl + (size_t)4 * t;
+    if (!lv) {
+      if (plane_hulls(P0, P1, a.dist, c, &d)) lv = 1;
+    } else {
+      c[0] = st[0]; c[1] = st[1]; c[2] = st[2]; d = st[3];
+    }
+    if (lv) {
+      if (self_optimal_cd(P0, P1, a.offset, a.margin, c, &d)) atomicAdd(&a.dc->opt_capped, 1u);
+      st[0] = c[0]; st[1] = c[1]; st[2] = c[2]; st[3] = d;
+      a.live[t] = 1;
+      double* o = a.self_pl + (size_t)4 * t;
+      o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; o[3] = d;
+      atomicAdd(a.selfcnt + r0, 1u);
+      atomicAdd(a.selfcnt + r1, 1u);
+    }
+    a.self_ok[t] = lv;
+    return;
+  }
+  if (hit) {
     double P0[6][3], P1[6][3], c[3], d;
     load_pts6(a.P + 18 * r0, P0);
     load_pts6(a.P + 18 * r1, P1);
@@ -165,6 +220,8 @@ struct PackArgs {
   const double *cpl, *self_pl;
   double* pl;
   uint32_t *pl_row, *pl_off;
+  int live;             // persistent-plane mode: the accepted planes are NEW members of the live set, not the plane list
+  uint32_t live_cap;
 };
 
 // one CTA: scan of the per-chunk obstacle-plane counts and of the per-row inter-robot plane counts
@@ -177,7 +234,12 @@ __global__ void __launch_bounds__(1024) k_np_top(PackArgs a) {
     a.selfpre[row] = (a.with_self && row >= a.self_begin && row < a.self_end) ? a.selfcnt[row] : 0u;
   __syncthreads();
   const uint32_t self_total = cta1024_scan_inplace(a.selfpre, (uint32_t)a.rows_all);
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && a.live) {
+    a.csum[n_chunks] = ob_total;
+    a.selfpre[a.rows_all] = 0;
+    a.dc->n_new = ob_total;
+    if ((unsigned long long)a.dc->n_live + ob_total > a.live_cap) a.dc->overflow |= TOB_OVF_LIVE;
+  } else if (threadIdx.x == 0) {
     a.csum[n_chunks] = ob_total;
     a.selfpre[a.rows_all] = self_total;
     a.dc->n_planes = ob_total + self_total;
@@ -268,6 +330,175 @@ __global__ void __launch_bounds__(NP_THREADS) k_pack(PackArgs a) {
   }
 }
 
+// ---- persistent planes -------------------------------------------------------------------------------------------
+struct LiveArgs {
+  DevCounts* dc;
+  uint32_t cap;          // candidate capacity
+  int rows_all;
+  const uint32_t *cand_pt, *cand_row, *cflag, *csum;
+  const double* cpl;
+  unsigned long long *live_key, *tmp_key, *new_key;
+  double *live_pl, *tmp_pl, *new_pl;
+  const double *px, *py, *pz, *P;
+  double offset, margin;
+  double* pl;
+  uint32_t *pl_row, *pl_off;
+};
+
+// planes accepted for pairs that were not live: compacted in candidate order = (row, Morton position) = key order
+__global__ void __launch_bounds__(NP_THREADS) k_live_compact(LiveArgs a) {
+  __shared__ uint32_t s_w[NP_THREADS / 32];
+  const uint32_t n = a.dc->n_cand;
+  if (a.dc->overflow) return;
+  const uint32_t n_chunks = (n + NP_CHUNK - 1) / NP_CHUNK;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    uint32_t run = a.csum[chunk];
+#pragma unroll
+    for (int q = 0; q < NP_PER; q++) {
+      const uint32_t i = chunk * NP_CHUNK + q * NP_THREADS + tid;
+      const bool f = i < n && a.cflag[i];
+      const uint32_t bm = __ballot_sync(0xffffffffu, f);
+      __syncthreads();
+      if (lane == 0) s_w[w] = __popc(bm);
+      __syncthreads();
+      uint32_t rank = __popc(bm & ((1u << lane) - 1u)), tot = 0;
+#pragma unroll
+      for (int k = 0; k < NP_THREADS / 32; k++) {
+        if (k < (int)w) rank += s_w[k];
+        tot += s_w[k];
+      }
+      if (f) {
+        const uint32_t dst = run + rank;
+        a.new_key[dst] = ((unsigned long long)a.cand_row[i] << 32) | a.cand_pt[i];
+        *reinterpret_cast<double4*>(a.new_pl + (size_t)4 * dst) = *reinterpret_cast<const double4*>(a.cpl + (size_t)4 * i);
+      }
+      run += tot;
+    }
+  }
+}
+
+// merge of the two sorted, disjoint key sets (live, new) into tmp: every element finds its place by one binary search
+__global__ void __launch_bounds__(256) k_live_merge(LiveArgs a) {
+  if (a.dc->overflow) return;
+  const uint32_t n_old = a.dc->n_live, n_new = a.dc->n_new;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_old + n_new; idx += stride) {
+    unsigned long long key;
+    uint32_t pos;
+    const double* src;
+    if (idx < n_old) {
+      key = a.live_key[idx];
+      pos = idx + lower_bound_u64(a.new_key, n_new, key);
+      src = a.live_pl + (size_t)4 * idx;
+    } else {
+      const uint32_t j = idx - n_old;
+      key = a.new_key[j];
+      pos = j + lower_bound_u64(a.live_key, n_old, key);
+      src = a.new_pl + (size_t)4 * j;
+    }
+    a.tmp_key[pos] = key;
+    *reinterpret_cast<double4*>(a.tmp_pl + (size_t)4 * pos) = *reinterpret_cast<const double4*>(src);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.dc->n_live_next = n_old + n_new;
+}
+
+// Optimal_plane::optimal_cd on every live plane (Optimization3D_admm.h:164-193), one plane per thread; the refined planes
+// are both the persistent state (live_*) and the plane list of this iteration (pl / pl_row / pl_off, CSR over rows)
+__global__ void __launch_bounds__(128) k_live_refine(LiveArgs a) {
+  if (a.dc->overflow) return;
+  const uint32_t n = a.dc->n_live_next;
+  const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t i = t0; i < n; i += stride) {
+    const unsigned long long key = a.tmp_key[i];
+    const uint32_t row = (uint32_t)(key >> 32), p = (uint32_t)(key & 0xffffffffu);
+    double4 v = *reinterpret_cast<const double4*>(a.tmp_pl + (size_t)4 * i);
+    const double q[3] = {a.px[p], a.py[p], a.pz[p]};
+    double P[6][3], c[3] = {v.x, v.y, v.z}, d = v.w;
+    load_pts6(a.P + (size_t)18 * row, P);
+    if (optimal_cd(P, q, a.offset, a.margin, c, &d)) atomicAdd(&a.dc->opt_capped, 1u);
+    v = make_double4(c[0], c[1], c[2], d);
+    a.live_key[i] = key;
+    *reinterpret_cast<double4*>(a.live_pl + (size_t)4 * i) = v;
+    *reinterpret_cast<double4*>(a.pl + (size_t)4 * i) = v;
+    a.pl_row[i] = row;
+  }
+  for (uint32_t row = t0; row <= (uint32_t)a.rows_all; row += stride)
+    a.pl_off[row] = lower_bound_u64(a.tmp_key, n, (unsigned long long)row << 32);
+  if (t0 == 0) {
+    a.dc->n_live = n;
+    a.dc->n_planes = n;
+    a.dc->n_planes_ob = n;
+    a.dc->planes += n;
+  }
+}
+
+// (re)allocates the persistent set for `need` planes, keeping the live ones; also sizes the plane list for them
+int ensure_live_buffers(tob_ctx* c, uint64_t need) {
+  if (c->live_cap >= need && c->live_key.p) return 0;
+  uint64_t cap = c->live_cap;
+  if (!cap) {
+    cap = 1u << 20;
+    if (const char* e = getenv("TRAJOPT_B200_LIVE_CAP")) { long v = atol(e); if (v >= 16) cap = (uint64_t)v; }   // tests: force growth
+  }
+  while (cap < need) cap *= 2;
+  if (cap > 0xfff00000ull) return fail_msg(c, "live plane count exceeds the 32-bit index range");
+  uint32_t n_live = 0;
+  if (c->live_key.p && c->dc.p) {
+    TOB_CUDA(c, cudaStreamSynchronize(c->stream));
+    TOB_CUDA(c, cudaMemcpy(&n_live, &c->dc.p->n_live, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  }
+  DBuf<unsigned long long> nk;
+  DBuf<double> np;
+  TOB_CUDA(c, nk.ensure(cap + 1));
+  TOB_CUDA(c, np.ensure(4 * cap + 4));
+  if (n_live) {
+    TOB_CUDA(c, cudaMemcpy(nk.p, c->live_key.p, (size_t)n_live * sizeof(unsigned long long), cudaMemcpyDeviceToDevice));
+    TOB_CUDA(c, cudaMemcpy(np.p, c->live_pl.p, (size_t)4 * n_live * sizeof(double), cudaMemcpyDeviceToDevice));
+  }
+  c->live_key.release(); c->live_pl.release();
+  c->live_key = nk; c->live_pl = np;
+  TOB_CUDA(c, c->live_key_t.ensure(cap + 1)); TOB_CUDA(c, c->live_pl_t.ensure(4 * cap + 4));
+  TOB_CUDA(c, c->new_key.ensure(cap + 1)); TOB_CUDA(c, c->new_pl.ensure(4 * cap + 4));
+  c->live_cap = cap;
+  return ensure_query_buffers(c);
+}
+
+int reset_live_planes(tob_ctx* c) {
+  if (c->dc.p) TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->n_live, 0, 4 * sizeof(uint32_t), c->stream));
+  if (c->self_live.p) TOB_CUDA(c, cudaMemsetAsync(c->self_live.p, 0, c->self_live.cap * sizeof(uint32_t), c->stream));
+  return 0;
+}
+
+// tail of the plane pass in persistent mode: new planes -> compact -> merge with the live set -> refine all -> CSR
+static int live_rows(tob_ctx* c) {
+  cudaStream_t st = c->stream;
+  LiveArgs a;
+  a.dc = c->dc.p; a.cap = (uint32_t)c->cand_cap; a.rows_all = c->rows_all();
+  a.cand_pt = c->cand_pt.p; a.cand_row = c->cand_row.p; a.cflag = c->cflag.p; a.csum = c->csum.p; a.cpl = c->cpl.p;
+  a.live_key = c->live_key.p; a.tmp_key = c->live_key_t.p; a.new_key = c->new_key.p;
+  a.live_pl = c->live_pl.p; a.tmp_pl = c->live_pl_t.p; a.new_pl = c->new_pl.p;
+  a.px = c->px.p; a.py = c->py.p; a.pz = c->pz.p; a.P = c->geo.P.p;
+  a.offset = c->prm.offset; a.margin = c->prm.margin;
+  a.pl = c->pl.p; a.pl_row = c->pl_row.p; a.pl_off = c->pl_off.p;
+  {
+    Prof prof(c, K_PACK);
+    k_live_compact<<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
+    TOB_LAUNCH_CHECK(c);
+  }
+  {
+    Prof prof(c, K_PACK);
+    k_live_merge<<<c->sm_count * 4, 256, 0, st>>>(a);
+    TOB_LAUNCH_CHECK(c);
+  }
+  {
+    Prof prof(c, K_LIVE_REFINE);
+    k_live_refine<<<c->sm_count * 8, 128, 0, st>>>(a);
+    TOB_LAUNCH_CHECK(c);
+  }
+  return 0;
+}
+
 int self_planes(tob_ctx* c) {
   const int U = c->n_robots();
   int npairs = U * (U - 1) / 2;
@@ -279,6 +510,15 @@ int self_planes(tob_ctx* c) {
   a.P = c->geo.P.p; a.D = nullptr; a.box = c->geo.box.p; a.klo = c->geo.klo.p; a.khi = c->geo.khi.p; a.kdop = c->d_kdop.p;
   a.dist = c->prm.offset + 2 * c->prm.margin; a.offset = c->prm.offset; a.margin = c->prm.margin;
   a.self_pl = c->self_pl.p; a.self_ok = c->self_ok.p; a.selfcnt = c->selfcnt.p;
+  a.live = nullptr; a.lpl = nullptr; a.dc = c->dc.p;
+  if (c->prm.optimal_plane) {
+    if (!c->self_live.p || c->self_live.cap < n + 1) {     // first use (or more pairs): all pairs start non-live
+      TOB_CUDA(c, c->self_live.ensure(n + 1));
+      TOB_CUDA(c, c->self_lpl.ensure(4 * n + 4));
+      TOB_CUDA(c, cudaMemsetAsync(c->self_live.p, 0, c->self_live.cap * sizeof(uint32_t), c->stream));
+    }
+    a.live = c->self_live.p; a.lpl = c->self_lpl.p;
+  }
   TOB_CUDA(c, cudaMemsetAsync(c->selfcnt.p, 0, (size_t)c->rows_all() * sizeof(uint32_t), c->stream));
   if (n) {
     Prof prof(c, K_SELF_PLANES);
@@ -290,7 +530,7 @@ int self_planes(tob_ctx* c) {
 }
 
 // shared tail: chunk / row scans -> scatter into the CSR.  Candidate flags (cflag, csum) and row_off must be current.
-static int pack_rows(tob_ctx* c, int rb, int re, bool ws) {
+static int pack_rows(tob_ctx* c, int rb, int re, bool ws, bool live = false) {
   cudaStream_t st = c->stream;
   const int U = c->n_robots();
   TOB_CUDA(c, c->self_ok.ensure(1));
@@ -303,11 +543,13 @@ static int pack_rows(tob_ctx* c, int rb, int re, bool ws) {
   a.selfcnt = c->selfcnt.p;
   a.self_ok = c->self_ok.p; a.cpl = c->cpl.p; a.self_pl = c->self_pl.p;
   a.pl = c->pl.p; a.pl_row = c->pl_row.p; a.pl_off = c->pl_off.p;
+  a.live = live ? 1 : 0; a.live_cap = (uint32_t)c->live_cap;
   {
     Prof prof(c, K_SCAN);
     k_np_top<<<1, 1024, 0, st>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
+  if (live) return live_rows(c);
   {
     Prof prof(c, K_PACK);
     k_pack<<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
@@ -327,6 +569,12 @@ int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self) {
   a.P = c->geo.P.p; a.klo = c->geo.klo.p; a.khi = c->geo.khi.p; a.kdop = c->d_kdop.p;
   a.dist = c->prm.offset + c->prm.margin; a.offset = c->prm.offset;
   a.cpl = c->cpl.p; a.cflag = c->cflag.p; a.csum = c->csum.p;
+  const bool live = c->live_planes();
+  if (live) {
+    if (rb != 0 || re != c->n_robots()) return fail_msg(c, "persistent planes: the plane pass must cover every robot slot of the context");
+    TOB_TRY(ensure_live_buffers(c, c->live_cap ? c->live_cap : 1));
+  }
+  a.live_key = live ? c->live_key.p : nullptr;
   {
     Prof prof(c, K_NARROW);
     k_narrow<<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
@@ -334,7 +582,7 @@ int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self) {
   }
   bool ws = with_self && c->n_robots() > 1;
   if (ws) TOB_TRY(self_planes(c));
-  return pack_rows(c, rb, re, ws);
+  return pack_rows(c, rb, re, ws, live);
 }
 
 // inter-robot planes only (Optimization3D_multi::separate_self on empty lists): geo of ALL robots must be current

@@ -33,7 +33,8 @@ class TobState(C.Structure):
 class TobCounters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("dcd_candidates", C.c_uint64), ("planes", C.c_uint64),
                 ("ccd_candidates", C.c_uint64), ("energy_plane_evals", C.c_uint64), ("self_pairs", C.c_uint64),
-                ("line_search_trials", C.c_uint64), ("barrier_terms", C.c_uint64)]
+                ("line_search_trials", C.c_uint64), ("barrier_terms", C.c_uint64), ("live_planes", C.c_uint64),
+                ("refine_capped", C.c_uint64)]
 
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_void_p)
@@ -81,7 +82,7 @@ class _HostState:
 
 class Solver:
     def __init__(self, piece_num, res=8, uav_num=1, lam=10.0, margin=0.1, offset=0.1, mu=0.1, vel_limit=2.0, acc_limit=2.0,
-                 ks=1e-8, kt=1.0, device=0):
+                 ks=1e-8, kt=1.0, device=0, optimal_plane=0):
         self.lib = load_library()
         self.lib.tob_last_error.restype = C.c_char_p
         self.lib.tob_stream.restype = C.c_void_p
@@ -92,7 +93,7 @@ class Solver:
         self.piece_num, self.res, self.uav_num = piece_num, res, uav_num
         self.n_tr = piece_num * res
         self.T = 6 + 3 * (piece_num - 1)
-        self.prm = TobParams(piece_num, res, uav_num, 0, lam, margin, offset, mu, vel_limit, acc_limit, ks, kt)
+        self.prm = TobParams(piece_num, res, uav_num, int(optimal_plane), lam, margin, offset, mu, vel_limit, acc_limit, ks, kt)
         self._ck(self.lib.tob_set_params(self.ctx, C.byref(self.prm)))
         self._ck(self.lib.tob_make_tables(self.ctx, None))
         self._cb = None
@@ -201,6 +202,35 @@ class Solver:
         self._ck(self.lib.tob_plane_hulls_batch(self.ctx, _d(self._pack(P0)), _d(self._pack(P1)), C.c_int(n), C.c_double(dist),
                                                 C.c_int(int(refine)), ok.ctypes.data_as(_bp), _d(c), _d(d)))
         return ok.astype(bool), c, d
+
+    def optimal_cd_batch(self, P, q, c, d):
+        """Optimal_plane::optimal_cd on n (P 6x3, q) pairs starting from planes (c, d); returns (c, d, capped)"""
+        n = len(P); c = np.ascontiguousarray(c, dtype=np.float64).copy(); d = np.ascontiguousarray(d, dtype=np.float64).copy()
+        q = np.ascontiguousarray(q, dtype=np.float64); cap = np.zeros(n, dtype=np.uint8)
+        self._ck(self.lib.tob_optimal_cd_batch(self.ctx, _d(self._pack(P)), _d(q), C.c_int(n), _d(c), _d(d), cap.ctypes.data_as(_bp)))
+        return c, d, cap.astype(bool)
+
+    def self_optimal_cd_batch(self, P0, P1, c, d):
+        """Optimal_plane::self_optimal_cd on n inter-robot pairs; returns (c, d, capped)"""
+        n = len(P0); c = np.ascontiguousarray(c, dtype=np.float64).copy(); d = np.ascontiguousarray(d, dtype=np.float64).copy()
+        cap = np.zeros(n, dtype=np.uint8)
+        self._ck(self.lib.tob_self_optimal_cd_batch(self.ctx, _d(self._pack(P0)), _d(self._pack(P1)), C.c_int(n), _d(c), _d(d),
+                                                    cap.ctypes.data_as(_bp)))
+        return c, d, cap.astype(bool)
+
+    # ---- persistent planes (optimal_plane=1)
+    def planes_reset(self):
+        self._ck(self.lib.tob_planes_reset(self.ctx))
+
+    def live_planes(self):
+        """(rows, original point ids, c, d) of the live obstacle planes"""
+        total = C.c_uint64(0)
+        self._ck(self.lib.tob_live_planes(self.ctx, None, None, None, None, C.c_uint64(0), C.byref(total)))
+        n = int(total.value)
+        rows = np.zeros(max(n, 1), dtype=np.uint32); ids = np.zeros(max(n, 1), dtype=np.uint32)
+        c = np.zeros((max(n, 1), 3)); d = np.zeros(max(n, 1))
+        self._ck(self.lib.tob_live_planes(self.ctx, _u(rows), _u(ids), _d(c), _d(d), C.c_uint64(n), C.byref(total)))
+        return rows[:n], ids[:n], c[:n], d[:n]
 
     # ---- planes
     def separate_planes(self, splines, with_self=False, cap=1 << 20):
