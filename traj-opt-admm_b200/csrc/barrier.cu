@@ -78,20 +78,36 @@ __global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
     sP[lane] = acc;
   }
   __syncwarp();
-  const double w = a.weight[tr], m = a.margin;
+  const double w = a.weight[tr], m = a.margin, inv_m = 1.0 / m;
   double e = 0;
   int bad = 0;
   unsigned n_act = 0;
   const uint32_t p0 = a.pl_off[row], p1 = a.pl_off[row + 1];
-  for (uint32_t p = p0 + lane; p < p1; p += 32) {
-    const double4 pl = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * p);
+  // Branch-free over the 6 control points: a lane whose term is outside the barrier band evaluates log(1) * 0, so the six
+  // logarithms of a plane are independent instruction streams the scheduler can interleave (with 32 lanes per warp some
+  // lane is inside the band for nearly every j anyway, so no work is added); the next plane is loaded one trip ahead.
+  uint32_t p = p0 + lane;
+  double4 nxt = make_double4(0, 0, 0, 0);
+  if (p < p1) nxt = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * p);
+  double cp[18];
+#pragma unroll
+  for (int i = 0; i < 18; i++) cp[i] = sP[i];
+  for (; p < p1; p += 32) {
+    const double4 pl = nxt;
+    if (p + 32 < p1) nxt = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * (p + 32));
+    double acc[6];
 #pragma unroll
     for (int j = 0; j < 6; j++) {
-      double d = sP[j] * pl.x + sP[j + 6] * pl.y + sP[j + 12] * pl.z + pl.w;
-      if (d <= 0) bad = 1;
-      else if (d < m) { e += -w * (d - m) * (d - m) * log(d / m); n_act++; }
+      const double d = cp[j] * pl.x + cp[j + 6] * pl.y + cp[j + 12] * pl.z + pl.w;
+      const bool act = d > 0 && d < m;
+      bad |= (d <= 0);
+      n_act += act;
+      const double dm = act ? d - m : 0.0;
+      acc[j] = (dm * dm) * log(act ? d * inv_m : 1.0);
     }
+    e += ((acc[0] + acc[1]) + (acc[2] + acc[3])) + (acc[4] + acc[5]);
   }
+  e *= -w;
   // bound terms: lanes 0..4 velocity, 5..8 acceleration
   double eb = 0;
   if (lane < 9) {

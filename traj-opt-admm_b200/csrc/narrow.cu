@@ -42,6 +42,7 @@ struct NarrowArgs {
   uint32_t* cflag;   // cap
   uint32_t* csum;    // chunks + 1
   const unsigned long long* live_key;   // persistent-plane mode: sorted keys of the live planes (else nullptr)
+  uint32_t np_grid;                     // CTAs of the narrowphase grid (np_per_of)
 };
 
 // index of the first key >= x in the sorted array k[0..n)
@@ -56,7 +57,16 @@ __device__ __forceinline__ uint32_t lower_bound_u64(const unsigned long long* __
 
 #define NP_THREADS 128
 #define NP_PER 4
-#define NP_CHUNK (NP_THREADS * NP_PER)   // candidates per CTA iteration; their k-DOP survivors fill the GJK phase densely
+#define NP_CHUNK (NP_THREADS * NP_PER)   // most candidates per CTA iteration; their k-DOP survivors fill the GJK phase densely
+
+// Candidates per thread and chunk (1, 2 or 4), chosen on the device from the candidate count so that a small query (one
+// UAV: ~1e5 candidates) still spreads over every CTA of the grid instead of serialising two GJK rounds on half of them.
+// k_narrow, k_np_top, k_pack and k_live_compact must agree: all derive it from (n_cand, np_grid).
+__device__ __forceinline__ uint32_t np_per_of(uint32_t n, uint32_t grid) {
+  if ((n + NP_CHUNK - 1) / NP_CHUNK >= grid) return 4;
+  if ((n + 2 * NP_THREADS - 1) / (2 * NP_THREADS) >= grid) return 2;
+  return 1;
+}
 
 __global__ void __launch_bounds__(NP_THREADS, 4) k_narrow(NarrowArgs a) {
   __shared__ double s_kdop[3 * TOB_KDOP_AXES];
@@ -65,15 +75,17 @@ __global__ void __launch_bounds__(NP_THREADS, 4) k_narrow(NarrowArgs a) {
   for (int i = threadIdx.x; i < 3 * TOB_KDOP_AXES; i += blockDim.x) s_kdop[i] = a.kdop[i];
   const uint32_t n = a.dc->n_cand;
   if (n > a.cap) return;
-  const uint32_t n_chunks = (n + NP_CHUNK - 1) / NP_CHUNK;
+  const uint32_t per = np_per_of(n, a.np_grid), chunk_sz = per * NP_THREADS;
+  const uint32_t n_chunks = (n + chunk_sz - 1) / chunk_sz;
   const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t n_live = a.live_key ? a.dc->n_live : 0u;
   __syncthreads();
   for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     uint32_t n_surv = 0;   // uniform
 #pragma unroll
-    for (int q = 0; q < NP_PER; q++) {
-      const uint32_t loc = q * NP_THREADS + tid, i = chunk * NP_CHUNK + loc;
+    for (uint32_t q = 0; q < NP_PER; q++) {
+      if (q >= per) break;   // uniform
+      const uint32_t loc = q * NP_THREADS + tid, i = chunk * chunk_sz + loc;
       bool pass = false;
       if (i < n) {
         const uint32_t row = a.cand_row[i], p = a.cand_pt[i];
@@ -97,7 +109,7 @@ __global__ void __launch_bounds__(NP_THREADS, 4) k_narrow(NarrowArgs a) {
     __syncthreads();
     uint32_t ok = 0;
     for (uint32_t sidx = tid; sidx < n_surv; sidx += NP_THREADS) {
-      const uint32_t ii = chunk * NP_CHUNK + s_surv[sidx];
+      const uint32_t ii = chunk * chunk_sz + s_surv[sidx];
       const uint32_t row = a.cand_row[ii], p = a.cand_pt[ii];
       if (n_live) {   // is_seperate[tr_id][ob_id] (Optimization3D_admm.h:128): a live pair keeps its plane
         const unsigned long long key = ((unsigned long long)row << 32) | p;
@@ -222,13 +234,15 @@ struct PackArgs {
   uint32_t *pl_row, *pl_off;
   int live;             // persistent-plane mode: the accepted planes are NEW members of the live set, not the plane list
   uint32_t live_cap;
+  uint32_t np_grid;
 };
 
 // one CTA: scan of the per-chunk obstacle-plane counts and of the per-row inter-robot plane counts
 __global__ void __launch_bounds__(1024) k_np_top(PackArgs a) {
   const uint32_t n = a.dc->n_cand;
   if (n > a.cap) return;
-  const uint32_t n_chunks = (n + NP_CHUNK - 1) / NP_CHUNK;
+  const uint32_t chunk_sz = np_per_of(n, a.np_grid) * NP_THREADS;
+  const uint32_t n_chunks = (n + chunk_sz - 1) / chunk_sz;
   const uint32_t ob_total = cta1024_scan_inplace(a.csum, n_chunks);
   for (int row = threadIdx.x; row < a.rows_all; row += 1024)
     a.selfpre[row] = (a.with_self && row >= a.self_begin && row < a.self_end) ? a.selfcnt[row] : 0u;
@@ -250,11 +264,11 @@ __global__ void __launch_bounds__(1024) k_np_top(PackArgs a) {
 
 // accepted obstacle planes before candidate idx (idx = a row boundary): scanned chunk base + the flags of the chunk in
 // front of idx, summed by the warp (uniform result)
-__device__ __forceinline__ uint32_t ob_prefix_warp(const PackArgs& a, uint32_t idx, uint32_t n, uint32_t n_chunks) {
+__device__ __forceinline__ uint32_t ob_prefix_warp(const PackArgs& a, uint32_t idx, uint32_t n, uint32_t n_chunks, uint32_t chunk_sz) {
   if (idx >= n) return a.csum[n_chunks];
-  const uint32_t chunk = idx / NP_CHUNK, lane = threadIdx.x & 31;
+  const uint32_t chunk = idx / chunk_sz, lane = threadIdx.x & 31;
   uint32_t local = 0;
-  for (uint32_t j = chunk * NP_CHUNK + lane; j < idx; j += 32) local += a.cflag[j];
+  for (uint32_t j = chunk * chunk_sz + lane; j < idx; j += 32) local += a.cflag[j];
   for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
   return a.csum[chunk] + local;
 }
@@ -266,13 +280,15 @@ __global__ void __launch_bounds__(NP_THREADS) k_pack(PackArgs a) {
   __shared__ uint32_t s_w[NP_THREADS / 32];
   const uint32_t n = a.dc->n_cand;
   if (n > a.cap) return;
-  const uint32_t n_chunks = (n + NP_CHUNK - 1) / NP_CHUNK;
+  const uint32_t per = np_per_of(n, a.np_grid), chunk_sz = per * NP_THREADS;
+  const uint32_t n_chunks = (n + chunk_sz - 1) / chunk_sz;
   const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     uint32_t run = a.csum[chunk];     // uniform: planes before this pass of the chunk
 #pragma unroll
-    for (int q = 0; q < NP_PER; q++) {
-      const uint32_t i = chunk * NP_CHUNK + q * NP_THREADS + tid;
+    for (uint32_t q = 0; q < NP_PER; q++) {
+      if (q >= per) break;   // uniform
+      const uint32_t i = chunk * chunk_sz + q * NP_THREADS + tid;
       const bool f = i < n && a.cflag[i];
       const uint32_t bm = __ballot_sync(0xffffffffu, f);
       __syncthreads();
@@ -297,11 +313,11 @@ __global__ void __launch_bounds__(NP_THREADS) k_pack(PackArgs a) {
   // CSR offsets and inter-robot planes: one warp per row
   const int n_warps = gridDim.x * (NP_THREADS / 32);
   for (int row = blockIdx.x * (NP_THREADS / 32) + w; row <= a.rows_all; row += n_warps) {
-    const uint32_t pre0 = ob_prefix_warp(a, a.row_off[row], n, n_chunks);
+    const uint32_t pre0 = ob_prefix_warp(a, a.row_off[row], n, n_chunks, chunk_sz);
     const uint32_t off = pre0 + a.selfpre[row];
     if (lane == 0) a.pl_off[row] = off;
     if (row < a.rows_all && a.with_self && row >= a.self_begin && row < a.self_end) {
-      const uint32_t pre1 = ob_prefix_warp(a, a.row_off[row + 1], n, n_chunks);
+      const uint32_t pre1 = ob_prefix_warp(a, a.row_off[row + 1], n, n_chunks, chunk_sz);
       uint32_t dst = off + (pre1 - pre0);
       const int u = row / a.n_tr, tr = row - u * a.n_tr;
       for (int v0 = 0; v0 < a.U; v0 += 32) {
@@ -343,6 +359,7 @@ struct LiveArgs {
   double offset, margin;
   double* pl;
   uint32_t *pl_row, *pl_off;
+  uint32_t np_grid;
 };
 
 // planes accepted for pairs that were not live: compacted in candidate order = (row, Morton position) = key order
@@ -350,13 +367,15 @@ __global__ void __launch_bounds__(NP_THREADS) k_live_compact(LiveArgs a) {
   __shared__ uint32_t s_w[NP_THREADS / 32];
   const uint32_t n = a.dc->n_cand;
   if (a.dc->overflow) return;
-  const uint32_t n_chunks = (n + NP_CHUNK - 1) / NP_CHUNK;
+  const uint32_t per = np_per_of(n, a.np_grid), chunk_sz = per * NP_THREADS;
+  const uint32_t n_chunks = (n + chunk_sz - 1) / chunk_sz;
   const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     uint32_t run = a.csum[chunk];
 #pragma unroll
-    for (int q = 0; q < NP_PER; q++) {
-      const uint32_t i = chunk * NP_CHUNK + q * NP_THREADS + tid;
+    for (uint32_t q = 0; q < NP_PER; q++) {
+      if (q >= per) break;   // uniform
+      const uint32_t i = chunk * chunk_sz + q * NP_THREADS + tid;
       const bool f = i < n && a.cflag[i];
       const uint32_t bm = __ballot_sync(0xffffffffu, f);
       __syncthreads();
@@ -481,6 +500,7 @@ static int live_rows(tob_ctx* c) {
   a.px = c->px.p; a.py = c->py.p; a.pz = c->pz.p; a.P = c->geo.P.p;
   a.offset = c->prm.offset; a.margin = c->prm.margin;
   a.pl = c->pl.p; a.pl_row = c->pl_row.p; a.pl_off = c->pl_off.p;
+  a.np_grid = (uint32_t)c->sm_count * 4;
   {
     Prof prof(c, K_PACK);
     k_live_compact<<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
@@ -543,7 +563,7 @@ static int pack_rows(tob_ctx* c, int rb, int re, bool ws, bool live = false) {
   a.selfcnt = c->selfcnt.p;
   a.self_ok = c->self_ok.p; a.cpl = c->cpl.p; a.self_pl = c->self_pl.p;
   a.pl = c->pl.p; a.pl_row = c->pl_row.p; a.pl_off = c->pl_off.p;
-  a.live = live ? 1 : 0; a.live_cap = (uint32_t)c->live_cap;
+  a.live = live ? 1 : 0; a.live_cap = (uint32_t)c->live_cap; a.np_grid = (uint32_t)c->sm_count * 4;
   {
     Prof prof(c, K_SCAN);
     k_np_top<<<1, 1024, 0, st>>>(a);
@@ -575,6 +595,7 @@ int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self) {
     TOB_TRY(ensure_live_buffers(c, c->live_cap ? c->live_cap : 1));
   }
   a.live_key = live ? c->live_key.p : nullptr;
+  a.np_grid = (uint32_t)c->sm_count * 4;
   {
     Prof prof(c, K_NARROW);
     k_narrow<<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
