@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
   if (a.dc->overflow) return;      // the plane CSR of this iteration was not built (see k_row_energy)
   if (threadIdx.x < 18) sP[threadIdx.x] = a.P[(size_t)18 * row + threadIdx.x];
   __syncthreads();
-  const double w = a.weight[tr], m = a.margin;
+  const double w = a.weight[tr], m = a.margin, inv_m = 1.0 / m;
   double acc[54];
   unsigned n_act = 0;
 #pragma unroll
@@ -376,18 +376,19 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
   for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
     const double4 pl = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * k);
     const double cxx = pl.x * pl.x, cxy = pl.x * pl.y, cxz = pl.x * pl.z, cyy = pl.y * pl.y, cyz = pl.y * pl.z, czz = pl.z * pl.z;
+    // branch-free like k_row_energy: a term outside the band contributes e1 = e2 = 0 through log(1) and dm = 0, so the six
+    // log / reciprocal chains of a plane are independent and interleave
 #pragma unroll
     for (int j = 0; j < 6; j++) {
-      double d = sP[j] * pl.x + sP[j + 6] * pl.y + sP[j + 12] * pl.z + pl.w;
-      if (d < m) {
-        n_act++;
-        double lg = log(d / m), dm = d - m, id = 1.0 / d;
-        double e1 = -w * (2 * dm * lg + dm * dm * id);
-        double e2 = -w * (2 * lg + 4 * dm * id - dm * dm * id * id);
-        double* q = acc + 9 * j;
-        q[0] += e2 * cxx; q[1] += e2 * cxy; q[2] += e2 * cxz; q[3] += e2 * cyy; q[4] += e2 * cyz; q[5] += e2 * czz;
-        q[6] += e1 * pl.x; q[7] += e1 * pl.y; q[8] += e1 * pl.z;
-      }
+      const double d = sP[j] * pl.x + sP[j + 6] * pl.y + sP[j + 12] * pl.z + pl.w;
+      const bool act = d < m;
+      n_act += act;
+      const double lg = log(act ? d * inv_m : 1.0), dm = act ? d - m : 0.0, id = 1.0 / (act ? d : 1.0);
+      const double e1 = -w * (2 * dm * lg + dm * dm * id);
+      const double e2 = -w * (2 * lg + 4 * dm * id - dm * dm * id * id);
+      double* q = acc + 9 * j;
+      q[0] += e2 * cxx; q[1] += e2 * cxy; q[2] += e2 * cxz; q[3] += e2 * cyy; q[4] += e2 * cyz; q[5] += e2 * czz;
+      q[6] += e1 * pl.x; q[7] += e1 * pl.y; q[8] += e1 * pl.z;
     }
   }
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;

@@ -214,30 +214,36 @@ __device__ __forceinline__ double rsqrt_full(double x) {
 }
 
 // in-place lower Cholesky of the 9x9 col-major matrix D by one warp; dinv receives 1/L(k,k).  Returns false on a
-// non-positive pivot (same value on every lane).
+// non-positive pivot (same value on every lane).  Lane j keeps column j in registers (static indices, fully unrolled); per
+// pivot the owner lane scales its column into shared memory, one warp barrier, and the lanes to its right update their
+// columns from it: one barrier and one shared-memory round trip per pivot, no index arithmetic.
 __device__ inline bool warp_chol9(double* D, double* dinv) {
   const int lane = threadIdx.x & 31;
-  bool ok = true;
+  double c[BS];
+#pragma unroll
+  for (int i = 0; i < BS; i++) c[i] = lane < BS ? D[i + BS * lane] : 0.0;
+  int ok = 1;
+#pragma unroll
   for (int k = 0; k < BS; k++) {
-    double p = D[k + BS * k];
-    if (!(p > 0)) { ok = false; p = 1; }
-    const double ri = rsqrt_full(p);
-    double l = 0;
-    if (lane > k && lane < BS) l = D[lane + BS * k] * ri;
-    __syncwarp();
-    if (lane > k && lane < BS) D[lane + BS * k] = l;
-    if (lane == k) { D[k + BS * k] = p * ri; dinv[k] = ri; }
-    __syncwarp();
-    // trailing update of the lower triangle: entries (i,j), k < j <= i < 9
-    for (int e = lane; e < 36; e += 32) {
-      int i = 1, rem = e;                       // row-wise enumeration of the strict+diag lower triangle of an 8x8
-      while (rem >= i) { rem -= i; i++; }
-      int ii = i, jj = rem + 1;                 // 1 <= jj <= ii <= 8
-      if (jj > k && ii > k) D[ii + BS * jj] -= D[ii + BS * k] * D[jj + BS * k];
+    if (lane == k) {
+      double p = c[k];
+      if (!(p > 0)) { ok = 0; p = 1; }
+      const double ri = rsqrt_full(p);
+      D[k + BS * k] = p * ri;
+      dinv[k] = ri;
+#pragma unroll
+      for (int i = k + 1; i < BS; i++) D[i + BS * k] = c[i] * ri;
     }
     __syncwarp();
+    if (lane > k && lane < BS) {
+      const double ljk = D[lane + BS * k];
+#pragma unroll
+      for (int i = k + 1; i < BS; i++)
+        if (i >= lane) c[i] -= D[i + BS * k] * ljk;
+    }
   }
-  return ok;
+  __syncwarp();
+  return __all_sync(0xffffffffu, ok) != 0;
 }
 
 struct BcrArgs {
