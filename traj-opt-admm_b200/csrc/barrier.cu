@@ -474,131 +474,126 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
 }
 
 // ---- block-cooperative PSD projection of one 19x19 block (Gradient_admm.h:40-53) ------------------------------------------
-// A single warp walking the 19 pivots runs at ~10 cycles per instruction (nothing to overlap with), which made this step
-// 60 % of k_piece.  Here the 384 threads of the CTA share it:
-//   Cholesky test   thread per element, one barrier per pivot (the pivot column is double-buffered in shared memory);
-//                   same operands as Eigen's unblocked LLT: fails when a pivot is <= 0
-//   lambda_min      (only when the test fails) Householder tridiagonalisation with rows spread over the 12 warps (two rows
-//                   per warp, row sums by shuffles, two barriers per column), then Sturm-count multisection with 384
-//                   shifts per round on the division-free recurrence.
+// The reference tests the block with Eigen's LLT and, when that fails, shifts it by (-lambda_min + 0.01) I if lambda_min < 0.
+// Away from the boundary the LLT outcome IS the sign of lambda_min (a pivot <= 0 needs lambda_min <~ n eps |H|), so the
+// order is turned around: lambda_min first, the Cholesky test only when |lambda_min| is within 1e-11 of the scale of H.
+// Once the bound barriers are active most blocks of an iteration are indefinite, and "Cholesky test, then eigenvalues" cost
+// 52 us per launch against 21 us when every block was SPD.
+//   lambda_min      warp 0: Householder tridiagonalisation with lane j keeping column j of the symmetric block in registers
+//                   (row k of the matrix is spread over the lanes by symmetry, A v needs no reduction, the two rank-1 vectors
+//                   go through shared memory with one warp barrier each), then Sturm-count multisection by the whole CTA:
+//                   384 shifts per round on the division-free recurrence
+//   Cholesky test   (borderline blocks only) thread per element, one barrier per pivot; same operands as Eigen's unblocked LLT
 // Returns 0 = SPD, 1 = shifted by (-lambda_min + 0.01) I in place, 2 = LLT failed but lambda_min >= 0.  All 384 threads call.
-__device__ __noinline__ int cta384_psd_shift19(double* s_H) {
-  constexpr int N = 19, NW = 12;
-  __shared__ double s_col[2][N + 1], s_v[2][N + 1], s_p[2][N + 1], s_d[N + 1], s_e[N + 1], s_sc[2][2];
-  __shared__ int s_first[2][NW];
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+__device__ __forceinline__ void warp_tridiag19(const double* s_H, double* s_d, double* s_e, double* s_v, double* s_w) {
+  constexpr int N = 19;
+  const int lane = threadIdx.x & 31;
   const unsigned full = 0xffffffffu;
-  {
-    const int i = tid % N, j = tid / N;
-    const bool act = tid < N * N;
-    double aij = act ? s_H[tid] : 0.0;
-    bool spd = true;
-    for (int k = 0; k < N; k++) {
-      double* col = s_col[k & 1];
-      if (act && j == k && i >= k) col[i] = aij;
-      __syncthreads();
-      const double x = col[k];
-      if (!(x > 0)) { spd = false; break; }               // uniform
-      if (act && j > k && i >= j) {
-        const double lkk = sqrt(x);
-        aij -= (col[i] / lkk) * (col[j] / lkk);
-      }
-    }
-    if (spd) return 0;
-  }
-  __syncthreads();
-  // ---- tridiagonalisation: warp w keeps rows w and w+12, lane = column
-  const int rw1 = w + NW;
-  double r0 = lane < N ? s_H[w + N * lane] : 0.0;
-  double r1 = (rw1 < N && lane < N) ? s_H[rw1 + N * lane] : 0.0;
-  for (int k = 0; k + 2 < N; k++) {
-    const int b = k & 1;
-    if (w == k % NW) {                                     // owner of row k publishes v = A(k, k+1..), |v|^2 and A(k,k)
-      const double rk = k < NW ? r0 : r1;
-      const double xi = (lane > k && lane < N) ? rk : 0.0;
-      double sg = xi * xi;
+  double a[N];
 #pragma unroll
-      for (int o = 16; o; o >>= 1) sg += __shfl_xor_sync(full, sg, o);
-      if (lane < N) s_v[b][lane] = xi;
-      if (lane == k) { s_sc[b][0] = sg; s_sc[b][1] = rk; }
-    }
-    __syncthreads();
-    const double sigma = s_sc[b][0], akk = s_sc[b][1], x0 = s_v[b][k + 1];
+  for (int i = 0; i < N; i++) a[i] = lane < N ? s_H[i + N * lane] : 0.0;
+#pragma unroll
+  for (int k = 0; k + 2 < N; k++) {
+    // x = A(k, k+1..): lane j > k holds x_j = a[k] (symmetry)
+    const double xj = (lane > k && lane < N) ? a[k] : 0.0;
+    double sigma = xj * xj;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sigma += __shfl_xor_sync(full, sigma, o);
+    const double x0 = __shfl_sync(full, a[k], k + 1);
     const double tail = sigma - x0 * x0;
-    if (tid == 0) s_d[k] = akk;
+    if (lane == k) s_d[k] = a[k];
     if (!(tail > 0)) {                                     // column already tridiagonal (uniform)
-      if (tid == 0) s_e[k] = x0;
+      if (lane == k) s_e[k] = x0;
       continue;
     }
     const double alpha = (x0 >= 0 ? -1.0 : 1.0) * sqrt(sigma);
     const double vk1 = x0 - alpha;
-    const double vl = lane == k + 1 ? vk1 : (lane < N ? s_v[b][lane] : 0.0);
     const double beta = 2.0 / (tail + vk1 * vk1);
-    double p0 = r0 * vl, p1 = r1 * vl;
+    const double vj = lane == k + 1 ? vk1 : xj;
+    __syncwarp();
+    if (lane < N) s_v[lane] = vj;
+    __syncwarp();
+    // p = beta A v: lane j owns column j = row j
+    double p0 = 0, p1 = 0, p2 = 0;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      p0 += __shfl_xor_sync(full, p0, o);
-      p1 += __shfl_xor_sync(full, p1, o);
+    for (int i = k + 1; i < N; i += 3) {
+      p0 += a[i] * s_v[i];
+      if (i + 1 < N) p1 += a[i + 1] * s_v[i + 1];
+      if (i + 2 < N) p2 += a[i + 2] * s_v[i + 2];
     }
-    p0 = w > k ? p0 * beta : 0.0;
-    p1 = (rw1 > k && rw1 < N) ? p1 * beta : 0.0;
-    if (lane == 0) {
-      s_p[b][w] = p0;
-      if (rw1 < N) s_p[b][rw1] = p1;
-    }
-    __syncthreads();
-    double kk = 0;
-    for (int i = 0; i < N; i++) kk += s_p[b][i] * (i == k + 1 ? vk1 : s_v[b][i]);
+    const double pj = (lane > k && lane < N) ? beta * ((p0 + p1) + p2) : 0.0;
+    double kk = pj * vj;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) kk += __shfl_xor_sync(full, kk, o);
     kk *= 0.5 * beta;
-    const double wl = lane < N ? s_p[b][lane] - kk * vl : 0.0;
-    const double v0 = w == k + 1 ? vk1 : s_v[b][w], w0 = s_p[b][w] - kk * v0;
-    double v1 = 0, w1 = 0;
-    if (rw1 < N) { v1 = rw1 == k + 1 ? vk1 : s_v[b][rw1]; w1 = s_p[b][rw1] - kk * v1; }
+    const double wj = pj - kk * vj;
+    if (lane < N) s_w[lane] = wj;
+    __syncwarp();
     if (lane > k && lane < N) {
-      if (w > k) r0 -= v0 * wl + w0 * vl;
-      if (rw1 > k && rw1 < N) r1 -= v1 * wl + w1 * vl;
+#pragma unroll
+      for (int i = k + 1; i < N; i++) a[i] -= s_v[i] * wj + s_w[i] * vj;
     }
-    if (tid == 0) s_e[k] = alpha;
+    if (lane == k) s_e[k] = alpha;
   }
-  // trailing 2x2: rows 17 (warp 5, second slot) and 18 (warp 6, second slot)
-  if (w == (N - 2) - NW) {
-    if (lane == N - 2) s_d[N - 2] = r1;
-    if (lane == N - 1) s_e[N - 2] = r1;
-  }
-  if (w == (N - 1) - NW && lane == N - 1) { s_d[N - 1] = r1; s_e[N - 1] = 0.0; }
+  if (lane == N - 2) { s_d[N - 2] = a[N - 2]; s_e[N - 2] = a[N - 1]; }
+  if (lane == N - 1) { s_d[N - 1] = a[N - 1]; s_e[N - 1] = 0.0; }
+}
+
+__device__ __forceinline__ int cta384_psd_shift19(double* s_H) {
+  constexpr int N = 19, NW = 12;
+  __shared__ double s_col[2][N + 1], s_v[N + 1], s_w[N + 1], s_d[N + 1], s_e[N + 1], s_e2[N + 1];
+  __shared__ int s_first[2][NW];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const unsigned full = 0xffffffffu;
+  if (w == 0) warp_tridiag19(s_H, s_d, s_e, s_v, s_w);
   __syncthreads();
-  // Gershgorin lower bound; lambda_min <= min d_i
-  double lo = INFINITY, hi = INFINITY;
+  // Gershgorin bounds of the tridiagonal matrix; lambda_min <= min d_i
+  double lo = INFINITY, hi = INFINITY, sc = 0.0;
   if (lane < N) {
     const double r = fabs(s_e[lane]) + (lane > 0 ? fabs(s_e[lane - 1]) : 0.0);
     lo = s_d[lane] - r;
     hi = s_d[lane];
+    sc = fabs(s_d[lane]) + r;
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
     lo = fmin(lo, __shfl_xor_sync(full, lo, o));
     hi = fmin(hi, __shfl_xor_sync(full, hi, o));
+    sc = fmax(sc, __shfl_xor_sync(full, sc, o));
   }
   double mn = hi;
   if (hi > lo) {
+    // Sturm counts on the division-free recurrence q_i = (d_i - x) q_{i-1} - e_{i-1}^2 q_{i-2}.  FP64 results take ~40 cycles
+    // on this part, so the loop is laid out for the shortest dependent chain: d_i and e_i^2 come from shared memory at
+    // static addresses (loads hoisted by the unrolling), (d_i - x) and
+    // e^2 q_{i-2} do not depend on q_{i-1}, which leaves ONE fused multiply-add per step on the critical path; the sign
+    // bookkeeping runs beside it and the range guard only every sixth step (19 factors of <= 1e12 cannot overflow between
+    // two guards).  Rounds stop as soon as the bracket is below 1e-14 of the scale of the block.
     constexpr int NT = 32 * NW;
+    if (tid < N) s_e2[tid] = tid ? s_e[tid - 1] * s_e[tid - 1] : 0.0;
+    __syncthreads();
+    const double* dd = s_d;          // static addresses in the unrolled loop: the loads are issued ahead of the chain
+    const double* e2 = s_e2;
+    const double stop = 1e-14 * sc;
     for (int round = 0; round < 8; round++) {
       const int b = round & 1;
       const double x = lo + (hi - lo) * ((tid + 1) / (double)(NT + 1));
       int cnt = 0;
-      double q0 = 1.0, q1 = s_d[0] - x;
+      double q0 = 1.0, q1 = dd[0] - x;
       bool neg = q1 < 0;                                   // sign of the last non-zero term
       if (neg) cnt++;
-#pragma unroll 1
+#pragma unroll
       for (int i = 1; i < N; i++) {
-        const double ei = s_e[i - 1];
-        double q2 = (s_d[i] - x) * q1 - (ei * ei) * q0;
-        const double m = fabs(q2);
-        if (m > 1e150) { q2 *= 1e-150; q1 *= 1e-150; }
-        else if (m < 1e-150 && m > 0) { q2 *= 1e150; q1 *= 1e150; }
+        const double t = e2[i] * q0;
+        double q2 = fma(dd[i] - x, q1, -t);
+        if (i % 6 == 0) {
+          const double m = fabs(q2);
+          if (m > 1e100) { q2 *= 1e-100; q1 *= 1e-100; }
+          else if (m < 1e-100 && m > 0) { q2 *= 1e100; q1 *= 1e100; }
+        }
         if (q2 != 0) {
           const bool n2 = q2 < 0;
-          if (n2 != neg) cnt++;
+          cnt += (n2 != neg);
           neg = n2;
         }
         q0 = q1; q1 = q2;
@@ -615,11 +610,34 @@ __device__ __noinline__ int cta384_psd_shift19(double* s_H) {
         hi = base + width * ((f + 1) / (double)(NT + 1));
         if (f > 0) lo = base + width * (f / (double)(NT + 1));
       }
-      if (!(hi > lo)) break;
+      if (!(hi - lo > stop)) break;
     }
     mn = 0.5 * (lo + hi);
   }
+  const double band = 1e-11 * sc;
+  bool llt_ok = mn > 0;
+  if (fabs(mn) <= band) {
+    // borderline: the reference's decision is the outcome of Eigen's unblocked LLT on these very operands
+    const int i = tid % N, j = tid / N;
+    const bool act = tid < N * N;
+    double aij = act ? s_H[tid] : 0.0;
+    llt_ok = true;
+    __syncthreads();
+    for (int k = 0; k < N; k++) {
+      double* col = s_col[k & 1];
+      if (act && j == k && i >= k) col[i] = aij;
+      __syncthreads();
+      const double x = col[k];
+      if (!(x > 0)) { llt_ok = false; break; }             // uniform
+      if (act && j > k && i >= j) {
+        const double lkk = sqrt(x);
+        aij -= (col[i] / lkk) * (col[j] / lkk);
+      }
+    }
+  }
+  if (llt_ok) return 0;
   if (mn < 0) {
+    __syncthreads();
     if (tid < N) s_H[tid * (N + 1)] = s_H[tid * (N + 1)] - mn * 1.0 + 0.01 * 1.0;
     return 1;
   }
@@ -816,6 +834,15 @@ int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd) {
   b.robot_begin = rb; b.project_psd = project_psd;
   b.pc_g = c->pc_g.p; b.pc_h = c->pc_h.p; b.pc_flag = c->pc_flag.p; b.dc = c->dc.p;
   size_t smem = ((size_t)c->prm.res * ROW_TERMS * (6 + TERM_SZ) + 361 * 2 + 36 + 2) * sizeof(double);
+  // Few CTAs (one UAV: P of them): the block scheduler co-locates several on one SM, where they share the FP64 pipe, the
+  // shared-memory port and the barrier unit (measured 2.7x per CTA).  Asking for more than half of the SM's shared memory
+  // makes every CTA the only resident of its SM.
+  static bool attr_set = false;
+  if (!attr_set) {
+    TOB_CUDA(c, cudaFuncSetAttribute(k_piece, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    attr_set = true;
+  }
+  if ((re - rb) * P <= c->sm_count && smem < (size_t)120 * 1024 && !getenv("TRAJOPT_B200_NO_SPREAD")) smem = (size_t)120 * 1024;
   {
     Prof prof(c, K_PIECE);
     k_piece<<<(re - rb) * P, 384, smem, c->stream>>>(b);

@@ -208,10 +208,9 @@ __global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
 #define BS 9
 #define BLK (3 * 81 + 18 + 9)     // El, D, Eu (81 each), R (9x2), 1/diag(L) (9)
 
-__device__ __forceinline__ double rsqrt_full(double x) {
-  double r = rsqrt(x);
-  return r * (1.5 - 0.5 * x * r * r);
-}
+// 1/sqrt(x).  CUDA's double rsqrt() is within 1-2 ulp; a further Newton step would add three dependent FP64 operations
+// (~120 cycles) to every pivot of the block Cholesky, whose dependency chain IS the latency of the solve.
+__device__ __forceinline__ double rsqrt_full(double x) { return rsqrt(x); }
 
 // in-place lower Cholesky of the 9x9 col-major matrix D by one warp; dinv receives 1/L(k,k).  Returns false on a
 // non-positive pivot (same value on every lane).  Lane j keeps column j in registers (static indices, fully unrolled); per
@@ -319,12 +318,15 @@ __global__ void __launch_bounds__(1024) k_solve_bcr(BcrArgs a) {
 #pragma unroll
           for (int k = 0; k < BS; k++) col[k] = 0.0;
         } else {
+          // right-looking: once y[k] is known the remaining rows are updated by independent multiply-adds, so the
+          // dependency chain is 9 x (mul + fma) instead of the 45 chained fma of the dot-product form
+#pragma unroll
+          for (int k = 0; k < BS; k++) y[k] = col[k];
 #pragma unroll
           for (int k = 0; k < BS; k++) {
-            double v = col[k];
+            y[k] *= dinv[k];
 #pragma unroll
-            for (int j = 0; j < k; j++) v -= D[k + BS * j] * y[j];
-            y[k] = v * dinv[k];
+            for (int i = k + 1; i < BS; i++) y[i] -= D[i + BS * k] * y[k];
           }
 #pragma unroll
           for (int k = 0; k < BS; k++) col[k] = y[k];
@@ -383,18 +385,18 @@ __global__ void __launch_bounds__(1024) k_solve_bcr(BcrArgs a) {
       double* col = R + BS * lane;
       double y[BS];
 #pragma unroll
-      for (int k = 0; k < BS; k++) {
-        double v = col[k];
+      for (int k = 0; k < BS; k++) y[k] = col[k];
 #pragma unroll
-        for (int j = 0; j < k; j++) v -= D[k + BS * j] * y[j];
-        y[k] = v * dinv[k];
+      for (int k = 0; k < BS; k++) {
+        y[k] *= dinv[k];
+#pragma unroll
+        for (int i = k + 1; i < BS; i++) y[i] -= D[i + BS * k] * y[k];
       }
 #pragma unroll
       for (int k = BS - 1; k >= 0; k--) {
-        double v = y[k];
+        y[k] *= dinv[k];
 #pragma unroll
-        for (int j = k + 1; j < BS; j++) v -= D[j + BS * k] * y[j];
-        y[k] = v * dinv[k];
+        for (int i = 0; i < k; i++) y[i] -= D[k + BS * i] * y[k];
       }
 #pragma unroll
       for (int k = 0; k < BS; k++) col[k] = y[k];
@@ -432,10 +434,9 @@ __global__ void __launch_bounds__(1024) k_solve_bcr(BcrArgs a) {
         for (int k = 0; k < BS; k++) y[k] = col[k];
 #pragma unroll
         for (int k = BS - 1; k >= 0; k--) {
-          double v = y[k];
+          y[k] *= dinv[k];
 #pragma unroll
-          for (int j = k + 1; j < BS; j++) v -= D[j + BS * k] * y[j];
-          y[k] = v * dinv[k];
+          for (int i = 0; i < k; i++) y[i] -= D[k + BS * i] * y[k];
         }
 #pragma unroll
         for (int k = 0; k < BS; k++) col[k] = y[k];
