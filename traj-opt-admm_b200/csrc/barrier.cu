@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
     a.row_e[2 * o + 1] = eb;
     a.row_bad[o] = bad;
     if (n_act) atomicAdd(&a.dc->barrier_terms, (unsigned long long)n_act);
+    if (p1 > p0) atomicAdd(&a.dc->energy_plane_evals, (unsigned long long)(p1 - p0));   // planes x trials really evaluated
   }
 }
 
@@ -256,7 +257,6 @@ __global__ void __launch_bounds__(32 * TOB_LS_TRIALS) k_robot_ls(RobotLsArgs b) 
   __syncthreads();
   if (threadIdx.x != 0) return;
   const int KT = a.KT, u = robot, kte = b.kte;
-  if (blockIdx.x == 0) b.dc->energy_plane_evals += (unsigned long long)b.dc->n_planes * (unsigned)(kte - a.k0);
   const double w = b.wolfe[b.wolfe_idx < 0 ? u : b.wolfe_idx];
   const double e0 = a.e_out[u * KT];
   for (int k = 1; k < kte; k++) {
