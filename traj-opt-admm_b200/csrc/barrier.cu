@@ -271,7 +271,9 @@ __global__ void __launch_bounds__(32 * TOB_LS_TRIALS) k_robot_ls(RobotLsArgs b) 
   double s = b.tstep[u * KT + kte - 1] * 0.8;        // continue the ladder below the last rung that was evaluated
   for (int k = 1; k < KT; k++) {
     b.tstep[u * KT + k] = s;
-    b.ttime[u * KT + k] = b.ptime[u] + s * b.tdir[u];
+    // unfused like k_ls_init (api.cu is built without FMA contraction, this file with): a rung must get the same trial time
+    // whichever kernel lays it out, or the result would depend on the line-search policy in the last bit
+    b.ttime[u * KT + k] = __dadd_rn(b.ptime[u], __dmul_rn(s, b.tdir[u]));
     s *= 0.8;
   }
   atomicAdd(&b.dc->ls_pending[b.slot], 1);
