@@ -140,6 +140,36 @@ def test_global_gradient_and_direction(world):
     assert abs(gn - gn_ref) <= 1e-9 * abs(gn_ref)
 
 
+def test_psd_projection_of_indefinite_blocks(world):
+    """Gradient_admm.h:40-53: a piece block that fails Eigen's LLT is shifted by (-lambda_min + 0.01) I.  Short piece times
+    switch the velocity / acceleration barriers on, whose time coupling makes blocks indefinite; the kernel decides by
+    lambda_min first and must reproduce the reference's shifted blocks."""
+    st, o, s = world["st"], world["o"], world["s"]
+    planes = o.separate_plane(st["spline"])
+    s.set_planes(planes)
+    shifted = 0
+    for t in np.linspace(2.10, 2.20, 21):          # just above the shortest feasible piece time of this state (~2.12)
+        st2 = dict(st, piece_time=float(t))
+        if not np.isfinite(o.spline_energy(st2, planes)):
+            continue
+        g_ref, h_ref = o.global_spline_gradient(st2, planes)
+        g, h = s.global_spline_gradient(st2)
+        assert rel(g, g_ref) < 1e-9 and rel(h, h_ref) < 1e-9, t
+        _, h_raw = s.piece_blocks(st2, project_psd=False)
+        _, h_psd = s.piece_blocks(st2, project_psd=True)
+        n = sum(1 for sp in range(P) if not np.array_equal(h_raw[sp], h_psd[sp]))
+        for sp in range(P):
+            if not np.array_equal(h_raw[sp], h_psd[sp]):      # shifted: exactly a multiple of the identity, lambda_min + 0.01 > 0
+                dlt = h_psd[sp] - h_raw[sp]
+                assert np.allclose(dlt, dlt[0, 0] * np.eye(19), rtol=0, atol=1e-12 * abs(dlt[0, 0])) and dlt[0, 0] > 0.01
+                assert abs(np.linalg.eigvalsh(h_psd[sp])[0] - 0.01) < 1e-9 * max(1.0, np.abs(h_raw[sp]).max())
+        shifted += n
+        d_ref, td_ref, w_ref, gn_ref = o.descent_direction(st2, planes)
+        d, td, w, gn = s.descent_direction(st2)
+        assert rel(d, d_ref) < 1e-7, t
+    assert shifted > 0
+
+
 def test_position_step_equals_reference(world):
     st, o, s = world["st"], world["o"], world["s"]
     planes = o.separate_plane(st["spline"])
