@@ -267,10 +267,12 @@ def run_ours(args):
     T = s.T
     state_bytes = U * (3 * T + 1 + 18 * P + P + 18 * P + P) * 8
 
-    # max over ranks
+    # max over ranks; pair counters: every rank counts the pairs of its own rows -> sum over ranks
     tt = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+    pe = torch.tensor([float(ctr["dcd_candidates"] + ctr["ccd_candidates"] + ctr["energy_plane_evals"])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pe, op=dist.ReduceOp.SUM)
     total_ms, e2e_s = float(tt[0]), float(tt[1])
     if rank != 0:
         if world > 1:
@@ -281,7 +283,7 @@ def run_ours(args):
     # set of problems is fixed); else N replicas (weak)
     mult = 1 if sharded else (sc["n_total"] if batch else world)
     value = mult * args.steps / (total_ms * 1e-3)
-    pair_evals = ctr["dcd_candidates"] + ctr["ccd_candidates"] + ctr["energy_plane_evals"]
+    pair_evals = float(pe[0])      # all ranks, all problems / robots / replicas of the timed steps
     # ---- roofline: every kernel against its bound, `roofline` = the kernel with the largest share of device time
     peaks = {}
     try:
@@ -298,7 +300,8 @@ def run_ours(args):
     tot_prof_ms = sum(v[0] for v in prof.values())
     traffic = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(sc["name"], {})
+        tkey = "batch%d" % sc["n_total"] if batch else sc["name"]     # the capture is specific to the problem count
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(tkey, {})
     except Exception:
         pass
     ktab = {}
@@ -338,7 +341,7 @@ def run_ours(args):
                    "multi_gpu": ("robots sharded over ranks, NCCL all-gather of control points/directions" if sharded else
                                  ("independent problems dealt round-robin to the ranks, no communication" if batch else
                                   ("replicas only" if world > 1 else "single"))), "lbvh_build_s": build_s, "gnorm_last": gn},
-        "pair_evals_per_s": pair_evals * mult / (total_ms * 1e-3),
+        "pair_evals_per_s": pair_evals / (total_ms * 1e-3),
         "pairs_per_step": {k: ctr[k] / args.steps for k in ("dcd_candidates", "planes", "ccd_candidates", "energy_plane_evals", "barrier_terms")},
         "e2e": {"value": mult * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes},
         "gpu_launches": int(ctr["kernel_launches"]),

@@ -15,5 +15,5 @@ ncu -i gpurun_out/full_${tag}.ncu-rep --page raw --csv > gpurun_out/raw_${tag}.c
 ncu --set full --clock-control none --launch-skip 18 -c 9 \
     -k regex:'k_narrow|k_row_energy|k_row_grad|k_bp_count|k_bp_fill|k_pack' \
     -o /tmp/full_batch_${tag} -f python bench.py --workload batch --problems 256 --steps 2 --warmup 3 > gpurun_out/ncu_full_batch_${tag}.log 2>&1
-ncu -i /tmp/full_batch_${tag}.ncu-rep --page raw --csv > gpurun_out/raw_batch_${tag}.csv 2>/dev/null
+ncu -i /tmp/full_batch_${tag}.ncu-rep --page raw --csv > gpurun_out/raw_batch_${tag}.csv 2>/dev/null   # summarise with: python profiles/summarize.py rawcsv ... batch256
 du -sh gpurun_out

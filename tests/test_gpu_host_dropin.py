@@ -154,6 +154,38 @@ def test_single_uav_iterations(pair):
         assert abs(a["gnorm"] - b["gnorm"]) <= 1e-6 * max(1.0, abs(a["gnorm"]))
 
 
+def test_persistent_plane_mode_through_the_shadow_headers(oracle_ref):
+    """is_optimal_plane = 1: the reference's caller code (Optimization3D_admm::optimization, separate_plane and the
+    Optimal_plane statics) against the shadow headers, live planes kept by the device context"""
+    if not os.path.exists(HOSTSHIM):
+        pytest.skip("host drop-in not built")
+    sc = scenes.bridge(n_pts=8000, seed=3)
+    ref, dev = oracle_ref, HostDropIn()
+    for o in (ref, dev):
+        o.setup(oa.Params(P, ks=sc["ks"], optimal_plane=1))
+        o.init_pointcloud(sc["V"])
+        o.reset_persistent_planes()
+    a = b = scenes.initial_states(sc)[0]
+    for it in range(5):
+        a, b = ref.optimization(a), dev.optimization(b)
+        assert np.max(np.abs(a["spline"] - b["spline"])) < 1e-6, it
+        ta, ia, ca, da = ref.live_planes()
+        tb, ib, cb, db = dev.live_planes()
+        k = np.lexsort((ib, tb))
+        assert np.array_equal(ta, tb[k]) and np.array_equal(ia, ib[k]), it
+        assert np.max(np.abs(ca - cb[k])) < 1e-8 and np.max(np.abs(da - db[k])) < 1e-8
+    assert len(ta) > 1500
+    # the per-pair statics: Optimal_plane::optimal_cd / self_optimal_cd through the shadow header
+    Pm = ref.segment_points(a["spline"], 20)
+    q = sc["V"][int(ia[np.searchsorted(ta, 20)])] if (ta == 20).any() else sc["V"][int(ia[0])]
+    ok, c0, d0 = ref.opengjk(Pm, q.reshape(1, 3), 10.0)
+    c1, d1 = ref.optimal_cd(Pm, q, c0, d0)
+    c2, d2 = dev.optimal_cd(Pm, q, c0, d0)
+    assert np.max(np.abs(c1 - c2)) < 1e-9 and abs(d1 - d2) < 1e-9
+    for o in (ref, dev):
+        o.setup(oa.Params(P, ks=sc["ks"]))      # back to the default mode for the other tests
+
+
 @pytest.mark.parametrize("coupled", [False, True])
 def test_multi_uav_iterations(oracle_ref, coupled):
     if not os.path.exists(HOSTSHIM):
