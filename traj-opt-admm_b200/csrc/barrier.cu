@@ -836,15 +836,6 @@ int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd) {
   b.robot_begin = rb; b.project_psd = project_psd;
   b.pc_g = c->pc_g.p; b.pc_h = c->pc_h.p; b.pc_flag = c->pc_flag.p; b.dc = c->dc.p;
   size_t smem = ((size_t)c->prm.res * ROW_TERMS * (6 + TERM_SZ) + 361 * 2 + 36 + 2) * sizeof(double);
-  // Few CTAs (one UAV: P of them): the block scheduler co-locates several on one SM, where they share the FP64 pipe, the
-  // shared-memory port and the barrier unit (measured 2.7x per CTA).  Asking for more than half of the SM's shared memory
-  // makes every CTA the only resident of its SM.
-  static bool attr_set = false;
-  if (!attr_set) {
-    TOB_CUDA(c, cudaFuncSetAttribute(k_piece, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
-    attr_set = true;
-  }
-  if ((re - rb) * P <= c->sm_count && smem < (size_t)120 * 1024 && !getenv("TRAJOPT_B200_NO_SPREAD")) smem = (size_t)120 * 1024;
   {
     Prof prof(c, K_PIECE);
     k_piece<<<(re - rb) * P, 384, smem, c->stream>>>(b);

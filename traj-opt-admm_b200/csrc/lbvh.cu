@@ -420,7 +420,10 @@ int broadphase_rows(tob_ctx* c, int row_base, int rows, double d, int count_as) 
 // every buffer whose size depends only on the parameters, the cloud and the candidate capacity: allocated up front so
 // that an iteration neither allocates nor reads a size back in the middle (CUDA-graph capturable)
 int ensure_query_buffers(tob_ctx* c) {
-  if (c->cand_cap == 0) c->cand_cap = 1u << 20;
+  if (c->cand_cap == 0) {
+    c->cand_cap = 1u << 20;
+    if (const char* e = getenv("TRAJOPT_B200_CAND_CAP")) { long v = atol(e); if (v >= 256) c->cand_cap = (uint64_t)v; }   // tests: force the overflow path
+  }
   const size_t rows = (size_t)c->rows_all(), U = (size_t)c->n_robots();
   const size_t n1 = c->n_levels > 1 ? c->lvl[1].count : 1;
   const size_t tasks = c->cloud_n1.empty() ? rows * n1 : (size_t)c->h_row_task[rows];
