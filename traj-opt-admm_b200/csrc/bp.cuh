@@ -42,6 +42,7 @@ struct BpShared {
   uint32_t hit_task[BP_THREADS];      // local task index of the h-th hit task
   uint32_t hit_row[BP_THREADS];       // its global row
   uint32_t hit_nd[BP_THREADS];        // its level-1 node (global index)
+  double hit_q[BP_THREADS][6];        // the query box of its row (lo xyz, hi xyz): read once from global memory in phase A
   uint32_t lmask[BP_THREADS];         // its leaf mask
   uint32_t item_base[BP_THREADS + 1]; // exclusive prefix of popc(lmask)
   uint32_t wtmp[BP_WARPS + 1];
@@ -53,6 +54,14 @@ void bp_args(tob_ctx* c, int row_base, int rows, double d, BpArgs& a);   // lbvh
 // the reference predicate with the query box [qlo,qhi] as "this" and the node/point as the argument
 __device__ __forceinline__ bool box_hit(double nlo, double nhi, double qlo, double qhi, double d) {
   return !(nhi + d < qlo) && !(nlo > qhi + d);
+}
+// all three axes, operands already in registers.  The callers load every operand BEFORE the tests: written as
+// box_hit(load x) && box_hit(load y) && ... the short-circuit evaluation turns the loads of y and z into dependent global
+// loads behind a branch, three memory round trips instead of one (measured: 3.4 k cycles per phase, 2.6 k per item).
+__device__ __forceinline__ bool box_hit3(const double* nlo, const double* nhi, const double* q, double d) {
+  const bool hx = box_hit(nlo[0], nhi[0], q[0], q[3], d), hy = box_hit(nlo[1], nhi[1], q[1], q[4], d),
+             hz = box_hit(nlo[2], nhi[2], q[2], q[5], d);
+  return hx & hy & hz;
 }
 
 // exclusive prefix of v over the CTA (BP_THREADS threads); *total = CTA sum.  Contains two __syncthreads().
@@ -141,24 +150,34 @@ __device__ __forceinline__ uint32_t bp_prepare(const BpArgs& a, BpShared& s, uin
   const uint32_t t = blockIdx.x * a.tpc + tid;
   bool hit = false;
   uint32_t row = 0, nd = 0;
+  double q[6] = {0, 0, 0, 0, 0, 0};
   if (tid < a.tpc && t < a.n_tasks) {
     bool first;
     bp_task(a, t, &row, &nd, &first);
-    const double* q = a.box + (size_t)6 * row;
-    hit = box_hit(a.l1lo[0][nd], a.l1hi[0][nd], q[0], q[3], a.d) && box_hit(a.l1lo[1][nd], a.l1hi[1][nd], q[1], q[4], a.d) &&
-          box_hit(a.l1lo[2][nd], a.l1hi[2][nd], q[2], q[5], a.d);
+    const double* qb = a.box + (size_t)6 * row;
+    double nlo[3], nhi[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { nlo[k] = a.l1lo[k][nd]; nhi[k] = a.l1hi[k][nd]; }
+#pragma unroll
+    for (int k = 0; k < 6; k++) q[k] = qb[k];
+    hit = box_hit3(nlo, nhi, q, a.d);
   }
   uint32_t n_hit;
   const uint32_t rank = bp_block_excl(hit ? 1u : 0u, s.wtmp, &n_hit);
   *my_rank = rank;
-  if (hit) { s.hit_task[rank] = tid; s.hit_row[rank] = row; s.hit_nd[rank] = nd; }
+  if (hit) {
+    s.hit_task[rank] = tid; s.hit_row[rank] = row; s.hit_nd[rank] = nd;
+#pragma unroll
+    for (int k = 0; k < 6; k++) s.hit_q[rank][k] = q[k];
+  }
   if (tid == 0) s.n_hit = n_hit;
   __syncthreads();
   for (uint32_t h = w; h < n_hit; h += BP_WARPS) {
-    const double* q = a.box + (size_t)6 * s.hit_row[h];
     const uint32_t leaf = s.hit_nd[h] * 32 + lane;   // level-0 arrays are padded to 32 with empty boxes
-    const bool lh = box_hit(a.l0lo[0][leaf], a.l0hi[0][leaf], q[0], q[3], a.d) && box_hit(a.l0lo[1][leaf], a.l0hi[1][leaf], q[1], q[4], a.d) &&
-                    box_hit(a.l0lo[2][leaf], a.l0hi[2][leaf], q[2], q[5], a.d);
+    double nlo[3], nhi[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { nlo[k] = a.l0lo[k][leaf]; nhi[k] = a.l0hi[k][leaf]; }
+    const bool lh = box_hit3(nlo, nhi, s.hit_q[h], a.d);
     const uint32_t lm = __ballot_sync(0xffffffffu, lh);
     if (lane == 0) s.lmask[h] = lm;
   }
@@ -185,11 +204,11 @@ __device__ __forceinline__ void bp_item(const BpArgs& a, const BpShared& s, uint
   *leaf = s.hit_nd[lo] * 32 + lb;
 }
 
-// 32 lanes = the 32 points of `leaf` against the box of `row`
-__device__ __forceinline__ bool bp_point_test(const BpArgs& a, uint32_t row, uint32_t p, double* x, double* y, double* z) {
-  const double* q = a.box + (size_t)6 * row;
-  *x = a.px[p]; *y = a.py[p]; *z = a.pz[p];
-  return box_hit(*x, *x, q[0], q[3], a.d) && box_hit(*y, *y, q[1], q[4], a.d) && box_hit(*z, *z, q[2], q[5], a.d);
+// 32 lanes = the 32 points of a leaf against the box of hit task h (its row's box sits in shared memory)
+__device__ __forceinline__ bool bp_point_test(const BpArgs& a, const BpShared& s, uint32_t h, uint32_t p, double* x, double* y, double* z) {
+  const double pt[3] = {a.px[p], a.py[p], a.pz[p]};
+  *x = pt[0]; *y = pt[1]; *z = pt[2];
+  return box_hit3(pt, pt, s.hit_q[h], a.d);
 }
 
 }  // namespace tob

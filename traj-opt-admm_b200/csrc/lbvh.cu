@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(BP_THREADS) k_bp_count(BpArgs a) {
     uint32_t h, row, leaf;
     bp_item(a, s, j, &h, &row, &leaf);
     double x, y, z;
-    const bool ok = bp_point_test(a, row, leaf * 32 + lane, &x, &y, &z);
+    const bool ok = bp_point_test(a, s, h, leaf * 32 + lane, &x, &y, &z);
     cnt += __popc(__ballot_sync(0xffffffffu, ok));
   }
   __syncthreads();
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(BP_THREADS) k_bp_fill(BpArgs a) {
       uint32_t h, row, leaf;
       bp_item(a, s, b0 + jj, &h, &row, &leaf);
       double x, y, z;
-      const bool ok = bp_point_test(a, row, leaf * 32 + lane, &x, &y, &z);
+      const bool ok = bp_point_test(a, s, h, leaf * 32 + lane, &x, &y, &z);
       const uint32_t pm = __ballot_sync(0xffffffffu, ok);
       if (lane == 0) { s_pm[jj] = pm; s_leaf[jj] = leaf; s_row[jj] = row; }
     }

@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(BP_THREADS, 4) k_bp_ccd(CcdArgs a) {
     uint32_t h, row, leaf;
     bp_item(a.bp, s, j, &h, &row, &leaf);
     double q[1][3];
-    const bool ok = bp_point_test(a.bp, row, leaf * 32 + lane, &q[0][0], &q[0][1], &q[0][2]);
+    const bool ok = bp_point_test(a.bp, s, h, leaf * 32 + lane, &q[0][0], &q[0][1], &q[0][2]);
     cnt += __popc(__ballot_sync(0xffffffffu, ok));
     if (!ok) continue;
     const int robot = row / a.n_tr;
