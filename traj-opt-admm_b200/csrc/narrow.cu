@@ -82,15 +82,28 @@ __global__ void __launch_bounds__(NP_THREADS, 4) k_narrow(NarrowArgs a) {
   __syncthreads();
   for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     uint32_t n_surv = 0;   // uniform
+    // the candidates of this thread are gathered first (index -> row / point -> coordinates are two dependent global loads
+    // each; one after the other behind the block barriers of the compaction they cost four round trips instead of one)
+    uint32_t c_row[NP_PER];
+    double c_pt[NP_PER][3];
+#pragma unroll
+    for (uint32_t q = 0; q < NP_PER; q++) {
+      const uint32_t i = chunk * chunk_sz + q * NP_THREADS + tid;
+      c_row[q] = 0; c_pt[q][0] = c_pt[q][1] = c_pt[q][2] = 0.0;
+      if (q < per && i < n) {
+        const uint32_t p = a.cand_pt[i];
+        c_row[q] = a.cand_row[i];
+        c_pt[q][0] = a.px[p]; c_pt[q][1] = a.py[p]; c_pt[q][2] = a.pz[p];
+      }
+    }
 #pragma unroll
     for (uint32_t q = 0; q < NP_PER; q++) {
       if (q >= per) break;   // uniform
       const uint32_t loc = q * NP_THREADS + tid, i = chunk * chunk_sz + loc;
       bool pass = false;
       if (i < n) {
-        const uint32_t row = a.cand_row[i], p = a.cand_pt[i];
-        const double pt[3] = {a.px[p], a.py[p], a.pz[p]};
-        pass = kdop_point_overlap(a.klo + (size_t)TOB_KDOP_AXES * row, a.khi + (size_t)TOB_KDOP_AXES * row, s_kdop, pt, a.dist);
+        const uint32_t row = c_row[q];
+        pass = kdop_point_overlap(a.klo + (size_t)TOB_KDOP_AXES * row, a.khi + (size_t)TOB_KDOP_AXES * row, s_kdop, c_pt[q], a.dist);
         a.cflag[i] = 0;
       }
       const uint32_t bm = __ballot_sync(0xffffffffu, pass);
