@@ -1217,11 +1217,91 @@ void port_optimization(double *spline, double *piece_time, double *p_slack, doub
   planes_free(&pl);
 }
 
-/* Optimization3D_multi::optimization_decouple (Optimization3D_multi.h:29-118).  The coupled variant (:120-174) is not
- * restated here (the compiled reference covers it). */
+/* Optimization3D_multi::update_spline (Optimization3D_multi.h:508-639): the coupled Newton step.  Unknowns: the free control
+ * points of every robot (3(T-4) each) + ONE shared piece time; the matrix is block diagonal per robot with a shared arrow
+ * row / column (:519-549; the reference factors its sparse view with SimplicialLLT, here dense LLT: same system).  One step
+ * for everybody: couple_self_step (:586), the smallest position_step (:589-594), joint Armijo on the summed energies (:605-636). */
+static void update_spline_coupled(int u, double *splines, double *piece_time, const double *p_slack, const double *t_slack,
+                                  const double *p_lambda, const double *t_lambda, const Planes *pls) {
+  const int Pn = G.piece_num, T = G.T, n = 3 * T, ld = n + 1, num = 3 * (T - 4), N = u * num + 1;
+  const size_t ns = (size_t)3 * T, np = (size_t)18 * Pn;
+  double *Gv = (double *)calloc((size_t)N, sizeof(double)), *H = (double *)calloc((size_t)N * N, sizeof(double));
+  double *grad = (double *)malloc(sizeof(double) * (size_t)ld), *hess = (double *)malloc(sizeof(double) * (size_t)ld * ld);
+  for (int i = 0; i < u; i++) {
+    global_spline_gradient(splines + ns * i, *piece_time, p_slack + np * i, t_slack + (size_t)Pn * i, p_lambda + np * i,
+                           t_lambda + (size_t)Pn * i, &pls[i], grad, hess);
+    for (int r = 0; r < num; r++) Gv[i * num + r] = grad[6 + r];
+    Gv[u * num] += grad[n];
+    for (int c = 0; c < num; c++)
+      for (int r = 0; r < num; r++) H[(i * num + r) + (size_t)N * (i * num + c)] = hess[(6 + r) + (size_t)ld * (6 + c)];
+    for (int r = 0; r < num; r++) {
+      H[(i * num + r) + (size_t)N * (u * num)] = hess[(6 + r) + (size_t)ld * n];
+      H[(u * num) + (size_t)N * (i * num + r)] = hess[(6 + r) + (size_t)ld * n];
+    }
+    H[(u * num) + (size_t)N * (u * num)] += hess[n + (size_t)ld * n];
+  }
+  double *L = (double *)malloc(sizeof(double) * (size_t)N * N), *x = (double *)malloc(sizeof(double) * (size_t)N);
+  port_llt(H, L, N);
+  for (int i = 0; i < N; i++) x[i] = Gv[i];
+  port_llt_solve(L, N, x);
+  double wl = 0, gn = 0;
+  for (int i = 0; i < N; i++) { x[i] = -x[i]; wl += x[i] * Gv[i]; gn += Gv[i] * Gv[i]; }
+  const double wolfe = -wl;
+  G.wolfe = wolfe;
+  G.gnorm = sqrt(gn) / (double)u;                                               /* :583 */
+  double *dirs = (double *)calloc(ns * (size_t)u, sizeof(double));
+  for (int i = 0; i < u; i++)
+    for (int p = 0; p < T - 4; p++) for (int k = 0; k < 3; k++) dirs[ns * i + (size_t)k * T + 2 + p] = x[i * num + 3 * p + k];
+  const double t_direction = x[u * num];
+  double *st = (double *)malloc(sizeof(double) * (size_t)u);
+  self_steps(splines, dirs, u, 1, st);
+  double step = st[0];
+  for (int i = 0; i < u; i++) {
+    const double s0 = position_step(splines + ns * i, dirs + ns * i);
+    if (s0 < step) step = s0;
+  }
+  if (*piece_time + step * t_direction <= 0) step = -0.95 * *piece_time / t_direction;
+  double e0 = 0;
+  for (int i = 0; i < u; i++)
+    e0 += spline_energy(splines + ns * i, *piece_time, p_slack + np * i, t_slack + (size_t)Pn * i, p_lambda + np * i,
+                        t_lambda + (size_t)Pn * i, &pls[i]);
+  const double init_time = *piece_time;
+  double *trial = (double *)malloc(sizeof(double) * ns * (size_t)u);
+  double t = init_time + step * t_direction;
+  for (int guard = 0; guard < 2000; guard++) {
+    double e1 = 0;
+    for (size_t k = 0; k < ns * (size_t)u; k++) trial[k] = splines[k] + step * dirs[k];
+    for (int i = 0; i < u; i++)
+      e1 += spline_energy(trial + ns * i, t, p_slack + np * i, t_slack + (size_t)Pn * i, p_lambda + np * i,
+                          t_lambda + (size_t)Pn * i, &pls[i]);
+    if (!(e0 - 1e-4 * wolfe * step < e1)) break;
+    step *= 0.8;
+    t = init_time + step * t_direction;
+  }
+  for (size_t k = 0; k < ns * (size_t)u; k++) splines[k] = splines[k] + step * dirs[k];
+  *piece_time = t;
+  free(Gv); free(H); free(grad); free(hess); free(L); free(x); free(dirs); free(st); free(trial);
+}
+
+/* Optimization3D_multi::optimization_decouple (Optimization3D_multi.h:29-118) and, with coupled != 0, ::optimization
+ * (:120-174: same plane passes, update_spline, then the slack update of every robot with the shared piece time) */
 void port_optimization_multi(int coupled, int u, double *splines, double *piece_time, double *p_slack, double *t_slack,
                              double *p_lambda, double *t_lambda, double *gnorm_out) {
-  if (coupled) { fprintf(stderr, "oracle port: coupled multi-robot mode is not restated (use oracle/_ref)\n"); abort(); }
+  if (coupled) {
+    const int Pc = G.piece_num;
+    const size_t nsc = (size_t)3 * G.T, npc = (size_t)18 * Pc;
+    Planes *plc = (Planes *)malloc(sizeof(Planes) * (size_t)u);
+    for (int i = 0; i < u; i++) { planes_init(&plc[i], G.n_tr); separate_plane_multi(splines + nsc * i, &plc[i]); }
+    separate_self(splines, u, plc);
+    update_spline_coupled(u, splines, piece_time, p_slack, t_slack, p_lambda, t_lambda, plc);
+    for (int i = 0; i < u; i++)
+      update_slack_lambda(splines + nsc * i, piece_time[0], p_slack + npc * i, t_slack + (size_t)Pc * i, p_lambda + npc * i,
+                          t_lambda + (size_t)Pc * i);
+    if (gnorm_out) *gnorm_out = G.gnorm;
+    for (int i = 0; i < u; i++) planes_free(&plc[i]);
+    free(plc);
+    return;
+  }
   const int Pn = G.piece_num, T = G.T;
   const size_t ns = (size_t)3 * T, np = (size_t)18 * Pn;
   Planes *pls = (Planes *)malloc(sizeof(Planes) * (size_t)u);

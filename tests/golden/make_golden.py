@@ -4,6 +4,7 @@ port (oracle/port) and the CUDA path on machines where the reference is not avai
 
 single.npz : 1 UAV, bridge-shaped cloud (4000 pts, seed 21), 4 pieces
 multi.npz  : 4 UAVs crossing, floor/ceiling cloud (3000 pts, seed 23), 4 pieces
+coupled.npz  : the 4-UAV scene through Optimization3D_multi::optimization (coupled: one shared piece time)
 optplane.npz : the same two scenes run with "optimal_plane": 1 (persistent planes refined by Optimal_plane::optimal_cd /
              self_optimal_cd), plus per-pair refinement vectors
 """
@@ -125,6 +126,23 @@ def multi():
     print("multi.npz: self planes", len(sd), "accepted hull pairs", int(np.sum(oks)), "self steps", out["self_steps"], out["couple_step"])
 
 
+def coupled():
+    sc = scenes.cross(n_pts=3000, seed=23, n_pieces=4)
+    sc["way_points"] = sc["way_points"][:2] + sc["way_points"][4:6]
+    U, P = 4, 4
+    o = oa.RefOracle(); o.setup(oa.Params(P, uav_num=U, ks=sc["ks"])); o.init_pointcloud(sc["V"])
+    sts = [scenes.init_state(scenes.init_spline_multi(wp)) for wp in sc["way_points"]]
+    out = {}
+    for i in range(1, 7):
+        sts = o.optimization_multi(sts, coupled=True)
+        for u, s in enumerate(sts):
+            for k in ("spline", "p_slack", "t_slack", "p_lambda", "t_lambda"):
+                out["it%d_u%d_%s" % (i, u, k)] = s[k]
+        out["it%d_piece_time" % i] = sts[0]["piece_time"]; out["it%d_gnorm" % i] = sts[0]["gnorm"]
+    np.savez_compressed(os.path.join(HERE, "coupled.npz"), **out)
+    print("coupled.npz: piece_time", [float(out["it%d_piece_time" % i]) for i in range(1, 7)])
+
+
 def optplane():
     out = {}
     # ---- single UAV, persistent obstacle planes
@@ -214,6 +232,6 @@ def optplane():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["single", "multi", "optplane"]
+    which = sys.argv[1:] or ["single", "multi", "coupled", "optplane"]
     for w in which:
-        {"single": single, "multi": multi, "optplane": optplane}[w]()
+        {"single": single, "multi": multi, "coupled": coupled, "optplane": optplane}[w]()

@@ -100,6 +100,28 @@ def test_oracle_multi_against_golden(gm, kind):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["ref", "port"])
+def test_oracle_coupled_multi_against_golden(kind):
+    """Optimization3D_multi::optimization (Optimization3D_multi.h:120-174): joint Newton system with one shared piece time"""
+    if kind not in oa.available():
+        pytest.skip(kind + " oracle not built")
+    g = np.load(os.path.join(GOLD, "coupled.npz"))
+    sc = scenes.cross(n_pts=3000, seed=23, n_pieces=4)
+    wps = sc["way_points"][:2] + sc["way_points"][4:6]
+    o = oa.get(kind)
+    o.setup(oa.Params(4, uav_num=4, ks=sc["ks"])); o.init_pointcloud(sc["V"])
+    sts = [scenes.init_state(scenes.init_spline_multi(wp)) for wp in wps]
+    tol = 1e-13 if kind == "ref" else 1e-9
+    for i in range(1, 7):
+        sts = o.optimization_multi(sts, coupled=True)
+        for u, s in enumerate(sts):
+            for k in ("spline", "p_slack", "t_slack", "p_lambda", "t_lambda"):
+                assert np.max(np.abs(s[k] - g["it%d_u%d_%s" % (i, u, k)])) < tol, (i, u, k)
+        assert abs(sts[0]["piece_time"] - float(g["it%d_piece_time" % i])) < tol
+        assert abs(sts[0]["gnorm"] - float(g["it%d_gnorm" % i])) < 1e-9 * max(1.0, float(g["it%d_gnorm" % i]))
+    o.setup(oa.Params(4, ks=sc["ks"]))
+
+
 def test_hostsim_tables_bit_exact(hostsim, gs):
     P = 4
     b = np.zeros((P * 8, 36)); w = np.zeros(P * 8); cv = np.zeros((P, 36)); md = np.zeros(36); kd = np.zeros(147)

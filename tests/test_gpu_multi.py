@@ -117,3 +117,21 @@ def test_sharded_two_gpus_equals_single():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "sharded==single:True" in out.stdout
+
+
+def test_coupled_iterations_against_golden():
+    """mode 1 (Optimization3D_multi::optimization, one shared piece time) against tests/golden/coupled.npz, which travels
+    without the reference"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "coupled.npz"))
+    sc = scenes.cross(n_pts=3000, seed=23, n_pieces=4)
+    wps = sc["way_points"][:2] + sc["way_points"][4:6]
+    s = api.Solver(4, uav_num=4, ks=sc["ks"])
+    s.init_pointcloud(sc["V"])
+    sts = [scenes.init_state(scenes.init_spline_multi(wp)) for wp in wps]
+    for i in range(1, 7):
+        sts = s.optimization(sts, coupled=True)
+        for u, st in enumerate(sts):
+            assert np.max(np.abs(st["spline"] - g["it%d_u%d_spline" % (i, u)])) < 1e-6, (i, u)
+            assert np.max(np.abs(st["p_slack"] - g["it%d_u%d_p_slack" % (i, u)])) < 1e-6, (i, u)
+        assert abs(sts[0]["piece_time"] - float(g["it%d_piece_time" % i])) < 1e-6
