@@ -1,20 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- ADMM iterations/s (and segment-point pair evaluations/s) of the B200 hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload forest|bridge]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload batch|forest|bridge|cross8|circle64|circle64c] [--problems M]
 
-One "step" = one ADMM iteration (Optimization3D_admm::optimization, Optimization3D_admm.h:29-67) on the
-BASELINE.json configs[1] workload: single UAV, synthetic dense-forest cloud of 1 M points, 64 Bezier pieces
-(512 sub-segments), FP64, Config File/3D.json parameters, straight-line initial trajectory.
+Default workload = BASELINE.json configs[4], the configuration the metric is quoted on at 1/2/4/8 GPUs: the batched sweep
+of 1024 independent single-UAV problems (tube clouds of 1e4..1e6 points, 214.6 M points in total, 8 Bezier pieces = 64
+sub-segments each, FP64, Config File/3D.json parameters, straight-line initial trajectories).  One "step" = one ADMM
+iteration (Optimization3D_admm::optimization, Optimization3D_admm.h:29-67) of EVERY problem; the fixed set of problems is
+dealt over the ranks (strong scaling, no communication: SURVEY.md 8(e)).  --workload forest is configs[1] (one UAV, 1 M
+points, 64 pieces: latency regime, replicas only on N > 1), circle64 / circle64c are configs[3] (64 UAVs sharded over the
+ranks, decoupled / coupled, native NCCL exchange inside the iteration's CUDA graph), cross8 is configs[2].
 
-  value  : iterations/s with the state resident in HBM (tob_admm_iterate), CUDA events on the library's stream,
-           L2 flushed between iterations (a 256 MiB buffer is rewritten outside the timed brackets).
-  e2e    : the same metric through the reference-shaped entry point (host buffers in, host buffers out:
-           tob_optimization = upload + iterate + download per call), pinned host memory, wall clock around the call.
-  N > 1  : single-UAV problems do not shard ("replicas only"): every rank runs its own replica of the
-           problem; value = total iterations of all ranks / max-over-ranks time ("weak").
-  --impl reference : the reference's own CPU implementation (oracle/_ref = the unmodified sources compiled here,
-           else the C port) on the same scene, 1 core (the reference has no parallel region), rank 0 only.
+  value  : problem-iterations/s (iterations/s for the single-problem workloads) with the state resident in HBM
+           (tob_admm_iterate), CUDA events on the library's stream, L2 flushed between iterations (a 256 MiB buffer is
+           rewritten outside the timed brackets), iterations W .. W+K-1 from the initial state.
+  e2e    : the same iterations through the reference-shaped entry point with HOST buffers (tob_optimization = H2D of every
+           problem's state + one iteration + D2H per call), wall clock around the call.
+  --impl reference : the reference's own CPU implementation (oracle/_ref = the unmodified sources compiled here, else the
+           C port) on the box's host cores, rank 0 only.  Batch: the reference is single-threaded and non-reentrant
+           (globals), so independent oracle PROCESSES run a stratified sample of the problems concurrently, one per core.
 """
 import argparse
 import json
@@ -33,32 +38,38 @@ import numpy as np  # noqa: E402
 METRIC = "ADMM iters/sec"
 UNIT = "iter/s"
 
-# ---- algorithmic work per unit; `roofline.achieved` is computed from these
-FLOP_PER_DCD_CANDIDATE = 3.0e3          # 49-DOP worst case 49x(7x5+4) + GJK(6,1), ~3-6 iterations
-BYTES_PER_DCD_CANDIDATE = 28 + 32       # point + id read, plane write when accepted
-FLOP_PER_CCD_CANDIDATE = 3.4e3 + 1.5e3  # swept 49-DOP on 12 points + >= one GJK(12,1)
+# ---- algorithmic work per unit.  The pair kernels are costed from COUNTED work (device counters: 49-DOP groups evaluated,
+# GJK rounds run, barrier terms inside the band), not from a worst-case constant per candidate; per-unit flop figures:
+FLOP_KDOP_GROUP = 7 * (5 + 2)           # one group of 7 axes against precomputed extents: level (3 mul 2 add) + 2 subtractions
+FLOP_GJK61_ROUND = 45 + 120             # support over 6 points (30) + tests (15) + signed-volume sub-algorithm (S1D 30 / S2D 130 / S3D 330)
+FLOP_GJK121_ROUND = 75 + 120            # same with 12 swept points
+FLOP_PLANE_FINISH = 30                  # norm, normalise, d
+FLOP_KDOP_SWEPT = 49 * (13 * 5 + 4)     # swept 49-DOP of a candidate that passes (general 12+1 point version)
 FLOP_PER_PLANE_EVAL = 36.0              # 6 control points x (3 mul + 3 add)
 FLOP_PER_ACTIVE_TERM_E = 45.0           # energy: 2 sub, 3 mul, 1 div, log ~35 DFMA-equivalents
-FLOP_PER_ACTIVE_TERM_G = 116.0          # gradient: e1,e2 (~95) + 3 + 6 accumulates x 2
+FLOP_PER_ACTIVE_TERM_G = 116.0          # gradient: e1, e2 (~95) + 3 + 6 accumulates x 2
 BYTES_PER_PLANE = 32.0
+BYTES_PER_BUILD_POINT = 128.0           # SURVEY 8(d) U-build
 
 
 def kernel_models(per_step, geo):
-    """kernel name -> (algorithmic FP64 flop per step, algorithmic bytes per step, bound) for the kernels of one ADMM
-    iteration.  per_step: counters of the profiled pass divided by its step count; geo: rows, n1 (level-1 nodes), P, T, U."""
-    rows, n1, P, T, U = geo["rows"], geo["n1"], geo["P"], geo["T"], geo["U"]
+    """kernel -> (counted FP64 flop per step, SURVEY algorithmic bytes per step, bound).  Bytes follow SURVEY 8(d):
+    U-bp = 48 B per row + 28 B per candidate (the level-1 pass over (row x node) boxes is served from L1/L2 and is NOT
+    counted), U-np = 28 B read per candidate + 32 B per accepted plane."""
+    rows, P, T, U = geo["rows"], geo["P"], geo["T"], geo["U"]
     cand, ccd, planes = per_step["dcd_candidates"], per_step["ccd_candidates"], per_step["planes"]
     evals, terms = per_step["energy_plane_evals"], per_step["barrier_terms"]
     e_evals = max(evals - planes, 0.0)                      # line-search passes (the gradient pass streams each plane once)
     g_share = planes / evals if evals else 0.0
     n_sys = 3 * (T - 4) + 1
-    bp_bytes = 48.0 * rows + 48.0 * rows * n1 + 28.0 * cand  # row box + one level-1 box per (row, node) + candidate out
+    np_flop = FLOP_KDOP_GROUP * per_step["np_kdop_groups"] + FLOP_GJK61_ROUND * per_step["np_gjk_iters"] + FLOP_PLANE_FINISH * planes
+    ccd_flop = FLOP_KDOP_SWEPT * per_step["ccd_kdop_pass"] + FLOP_GJK121_ROUND * per_step["ccd_gjk_iters"]
     return {
         "k_rows": (0.0, rows * (18 + 6 + 2 * 49) * 8.0 * 2, "hbm"),
-        "k_bp_count": (0.0, bp_bytes - 4.0 * cand, "hbm"),
-        "k_bp_fill": (0.0, bp_bytes, "hbm"),
-        "k_bp_ccd": (FLOP_PER_CCD_CANDIDATE * ccd, 48.0 * rows + 48.0 * rows * n1 + 24.0 * ccd, "hbm"),
-        "k_narrow": (FLOP_PER_DCD_CANDIDATE * cand, BYTES_PER_DCD_CANDIDATE * cand, "fp64"),
+        "k_bp_count": (0.0, 48.0 * rows + 24.0 * cand, "hbm"),
+        "k_bp_fill": (0.0, 48.0 * rows + 28.0 * cand, "hbm"),
+        "k_bp_ccd": (ccd_flop, 48.0 * rows + 24.0 * ccd, "hbm"),
+        "k_narrow": (np_flop, 28.0 * cand + 32.0 * planes, "fp64"),
         "k_pack": (0.0, 4.0 * cand + 72.0 * planes, "hbm"),
         "k_row_energy": (FLOP_PER_PLANE_EVAL * e_evals + FLOP_PER_ACTIVE_TERM_E * terms * (1 - g_share), BYTES_PER_PLANE * e_evals, "fp64"),
         "k_row_grad": (FLOP_PER_PLANE_EVAL * planes + FLOP_PER_ACTIVE_TERM_G * terms * g_share, BYTES_PER_PLANE * planes, "fp64"),
@@ -69,26 +80,60 @@ def kernel_models(per_step, geo):
     }
 
 
-def workload(name, n_pts=None, n_problems=None):
+# ---- workloads ------------------------------------------------------------------------------------------------------
+def batch_order(total):
+    """the order batch_partition deals the problems in (expected pair work, then cloud size)"""
     from trajopt import scenes
-    if name == "forest":
-        sc = scenes.forest(n_pts=n_pts or 1_000_000)
-    elif name == "bridge":
-        sc = scenes.bridge(n_pts=n_pts or 100_000)
-    elif name == "circle64":      # BASELINE.json configs[3]: 64 UAVs, inter-robot planes, robots sharded over the ranks
-        sc = scenes.circle(n_uav=64, n_pts=n_pts or 20_000)
-    elif name == "cross8":        # configs[2]
-        sc = scenes.cross(n_pts=n_pts or 50_000)
-    elif name == "batch":         # configs[4]: independent single-UAV problems, clouds log-uniform in [1e4, 1e6] points
-        rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-        total = n_problems or 1024
-        mine = scenes.batch_partition(total, world, rank)   # balanced deal over the ranks, no communication
-        ms = [scenes.batch_member(k) for k in mine]
-        sc = dict(name="batch", Vs=[m["V"] for m in ms], way_points=[m["way_points"][0] for m in ms], uav_num=len(ms), ks=1e-8,
-                  V=np.zeros((sum(m["V"].shape[0] for m in ms), 0)), n_total=total)
+    meta = [scenes.batch_member_meta(k) for k in range(total)]
+    return sorted(range(total), key=lambda k: (-(meta[k][0] if meta[k][1] < 0.3 else 0), -meta[k][0], k)), meta
+
+
+def describe(args, world):
+    """the `config` object: a pure function of the command line and the world size, identical in both arms"""
+    from trajopt import scenes
+    name = args.workload
+    if name == "batch":
+        total = args.problems or 1024
+        pts = sum(scenes.batch_member_meta(k)[0] for k in range(total))
+        wl = ("batch: %d independent single-UAV problems, tube clouds 1e4..1e6 pts (%.1f M pts in total), 8 Bezier pieces "
+              "(64 sub-segments) each, 3D.json params" % (total, pts / 1e6))
+        mg = "single" if world == 1 else "independent problems dealt over the ranks by expected work, no communication"
     else:
-        raise SystemExit("unknown workload " + name)
-    return sc
+        shape = {"forest": (1, args.points or 1_000_000, 64), "bridge": (1, args.points or 100_000, 8),
+                 "cross8": (8, args.points or 50_000, 8), "circle64": (64, args.points or 20_000, 8),
+                 "circle64c": (64, args.points or 20_000, 8)}[name]
+        wl = "%s: %d UAV, %d pts, %d Bezier pieces (%d sub-segments each), 3D.json params" % ((name,) + shape + (shape[2] * 8,))
+        if name == "circle64c":
+            wl += ", coupled (decouple=0)"
+        if shape[0] > 1 and world > 1:
+            mg = "robots sharded over the ranks, cloud replicated, native NCCL all-gathers inside the iteration's CUDA graph"
+        else:
+            mg = "single" if world == 1 else "replicas only"
+    return {"workload": wl, "l2": "flushed between timed iterations (256 MiB rewrite outside the event brackets)", "multi_gpu": mg}
+
+
+def workload(args, rank, world):
+    from trajopt import scenes
+    name, n_pts = args.workload, args.points
+    if name == "forest":
+        return scenes.forest(n_pts=n_pts or 1_000_000)
+    if name == "bridge":
+        return scenes.bridge(n_pts=n_pts or 100_000)
+    if name in ("circle64", "circle64c"):      # BASELINE.json configs[3]
+        return scenes.circle(n_uav=64, n_pts=n_pts or 20_000)
+    if name == "cross8":                       # configs[2]
+        return scenes.cross(n_pts=n_pts or 50_000)
+    if name == "batch":                        # configs[4]
+        total = args.problems or 1024
+        if args.emulate_rank:                  # profiling aid: the share rank r of w would get, on one GPU (never a bench value)
+            r, w = (int(x) for x in args.emulate_rank.split("/"))
+            mine = scenes.batch_partition(total, w, r)
+        else:
+            mine = scenes.batch_partition(total, world, rank)
+        ms = [scenes.batch_member(k) for k in mine]
+        return dict(name="batch", Vs=[m["V"] for m in ms], way_points=[m["way_points"][0] for m in ms], uav_num=len(ms), ks=1e-8,
+                    n_points=sum(m["V"].shape[0] for m in ms), n_total=total)
+    raise SystemExit("unknown workload " + name)
 
 
 class ClockSampler(threading.Thread):
@@ -167,21 +212,93 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.smax, "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
-def pinned_state(st):
-    import torch
-    out = {}
-    for k, v in st.items():
-        if isinstance(v, np.ndarray):
-            t = torch.empty(v.size, dtype=torch.float64).pin_memory()
-            a = t.numpy().reshape(v.shape, order="F")
-            a[...] = v
-            out[k] = a
-            out["_keep_" + k] = t
-        else:
-            out[k] = v
-    return out
+# ---- CPU side: the reference on the host cores ----------------------------------------------------------------------
+def _cpu_batch_worker(job):
+    """one oracle process: its problems one after the other (the reference is non-reentrant: one problem per process)"""
+    ks, warm, steps, budget = job
+    sys.path.insert(0, os.path.join(ROOT, "traj-opt-admm_b200")); sys.path.insert(0, ROOT)
+    from oracle import oracle_api as oa
+    from trajopt import scenes
+    o = oa.get()
+    out = []
+    for k in ks:
+        m = scenes.batch_member(k)
+        o.setup(oa.Params(len(m["way_points"][0]) - 1, ks=m["ks"]))
+        t0 = time.perf_counter()
+        o.init_pointcloud(m["V"])
+        build = time.perf_counter() - t0
+        st = scenes.init_state(scenes.init_spline_single(m["way_points"][0]))
+        for _ in range(warm):
+            st = o.optimization(st)
+        n, t = 0, 0.0
+        while n < steps and (n == 0 or t < budget):
+            t0 = time.perf_counter()
+            st = o.optimization(st)
+            t += time.perf_counter() - t0
+            n += 1
+        out.append((k, n, t, build, m["V"].shape[0]))
+    return o.kind, out
 
 
+def cpu_batch(total, warm, steps, budget_s, max_procs=128):
+    """aggregate problem-iterations/s of `procs` concurrent oracle processes on a stratified sample of the batch (every
+    (total/procs)-th problem of the work-sorted order, so the sample has the mix of the whole set).  With per-iteration
+    times tau_k measured under that concurrency, one iteration of all problems on `procs` cores takes (total/S) sum tau_k /
+    procs, i.e. the job runs at procs * S / sum tau_k problem-iterations/s."""
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    procs = max(1, min(cores, max_procs, total))
+    order, _ = batch_order(total)
+    per = 1 if procs >= 32 else -(-32 // procs)              # few cores: several problems per process, still >= 32 samples
+    n_s = min(total, procs * per)
+    sample = [order[int((i + 0.5) * total / n_s)] for i in range(n_s)]
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_cpu_batch_worker, [(sample[i::procs], warm, steps, budget_s / per) for i in range(procs)], chunksize=1)
+    wall = time.perf_counter() - t0
+    kind = res[0][0]
+    rows = [r for _, lst in res for r in lst]
+    tau = [t / n for _, n, t, _, _ in rows]
+    value = procs * len(rows) / sum(tau)
+    its = sorted(n for _, n, _, _, _ in rows)
+    text = ("%d concurrent oracle processes (%d host cores visible), stratified sample of %d of the %d problems "
+            "(clouds %d..%d pts); per problem %d untimed + %d..%d timed ADMM iterations from the initial state (time-bounded), "
+            "tree builds excluded (%.0f s summed); wall %.0f s"
+            % (procs, cores, len(rows), total, min(r[4] for r in rows), max(r[4] for r in rows), warm, its[0], its[-1],
+               sum(r[3] for r in rows), wall))
+    return {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": text}
+
+
+def cpu_single(sc, P, budget_s, max_iters, warm=0):
+    """the reference's CPU path on ONE scene: 1 core (the reference has no parallel region and is non-reentrant)"""
+    from oracle import oracle_api as oa
+    from trajopt import scenes
+    o = oa.get()
+    o.setup(oa.Params(P, uav_num=sc["uav_num"], ks=sc["ks"]))
+    t0 = time.time()
+    o.init_pointcloud(sc["V"])
+    build = time.time() - t0
+    sts = scenes.initial_states(sc)
+    coupled = sc.get("coupled", False)
+    step = (lambda x: o.optimization_multi(x, coupled=coupled)) if len(sts) > 1 else (lambda x: [o.optimization(x[0])])
+    t_w = 0.0
+    for _ in range(warm):
+        t0 = time.perf_counter(); sts = step(sts); t_w += time.perf_counter() - t0
+        if t_w > budget_s / 3:
+            break
+    n, t_used = 0, 0.0
+    while n < max_iters and (n == 0 or t_used < budget_s):
+        t0 = time.perf_counter()
+        sts = step(sts)
+        t_used += time.perf_counter() - t0
+        n += 1
+    return {"value": n / t_used, "unit": UNIT, "cores": 1, "kind": o.kind,
+            "sample": "%d ADMM iterations of the same scene from the initial state after %d untimed ones, 1 host core "
+                      "(tree build %.1f s excluded)" % (n, warm, build)}
+
+
+# ---- our arm --------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -195,11 +312,12 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    sc = workload(args.workload, args.points, args.problems)
+    sc = workload(args, rank, world)
     P = len(sc["way_points"][0]) - 1
     U = sc["uav_num"]
     batch = "Vs" in sc
-    mode = 2 if batch else 0
+    coupled = args.workload == "circle64c"
+    mode = 2 if batch else (1 if coupled else 0)
     sharded = U > 1 and world > 1 and not batch
     s = api.Solver(P, uav_num=U, ks=sc["ks"], device=local)
     t0 = time.time()
@@ -208,10 +326,12 @@ def run_ours(args):
     else:
         s.init_pointcloud(sc["V"])
     build_s = time.time() - t0
+    build_ms, build_pts = s.build_stats()
     st0 = [scenes.init_state(scenes.init_spline_single(wp)) for wp in sc["way_points"]] if batch else scenes.initial_states(sc)
+    first, count = 0, U
     if sharded:
         from trajopt import dist as tdist
-        tdist.attach(s)
+        first, count = tdist.attach_nccl(s)          # the library's own NCCL communicator; exchanges run inside its CUDA graph
     ext = torch.cuda.ExternalStream(s.stream(), device=torch.device("cuda", local))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     if os.environ.get("TRAJOPT_BENCH_NOFLUSH"):      # experiment only (cold- vs warm-cache kernel times); never a bench value
@@ -223,7 +343,7 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-resident iterations: `value`
+    # ---- device-resident iterations: `value` (iterations W .. W+K-1 from the initial state)
     s.states_upload(st0)
     for _ in range(args.warmup):
         s.iterate(1, mode)
@@ -249,21 +369,12 @@ def run_ours(args):
     total_ms = float(sum(ms))
     ctr = s.counters()
 
-    # ---- per-kernel timing pass (same problem, next iterations) for the roofline of the dominant kernel
-    s.profile_enable(True)
-    s.reset_counters()
-    for _ in range(args.steps):
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        s.iterate(1, mode)
-    prof = s.profile_read()
-    s.profile_enable(False)
-    pctr = s.counters()
-    fp64_peak = s.fp64_peak_tflops()
-
-    # ---- end to end through the host-in/host-out entry point
-    cur = [pinned_state(x) for x in s.states_download(st0)]
-    bound = s.bind_states(cur)              # tob_state array over the pinned host buffers, built once like a C++ caller would
+    # ---- end to end through the host-in/host-out entry point: the SAME iterations (restart from the initial state)
+    cur = [dict(x, spline=x["spline"].copy(order="F"), p_slack=x["p_slack"].copy(order="F"), t_slack=x["t_slack"].copy(),
+                p_lambda=x["p_lambda"].copy(order="F"), t_lambda=x["t_lambda"].copy()) for x in st0]
+    bound = s.bind_states(cur)              # tob_state array over the caller's host buffers, built once like a C++ caller would
+    for _ in range(args.warmup):
+        s.optimization_bound(bound, mode)
     barrier()
     sampler.begin()
     e2e_s = 0.0
@@ -272,17 +383,35 @@ def run_ours(args):
         torch.cuda.synchronize()
         sampler.hold()
         t0 = time.perf_counter()
-        s.optimization_bound(bound, mode)   # host buffers in -> H2D -> one ADMM iteration -> D2H -> same host buffers
+        s.optimization_bound(bound, mode)   # host buffers -> pinned staging -> H2D -> one ADMM iteration -> D2H -> host buffers
         e2e_s += time.perf_counter() - t0
         sampler.release()
+    barrier()
     sampler.end()
     sampler.close()
     T = s.T
     state_bytes = U * (3 * T + 1 + 18 * P + P + 18 * P + P) * 8
 
+    # ---- per-kernel timing pass (same problem, following iterations) for the roofline of the dominant kernel
+    s.states_upload(st0)
+    for _ in range(args.warmup):
+        s.iterate(1, mode)
+    s.profile_enable(True)
+    s.reset_counters()
+    psteps = min(args.steps, 10)
+    for _ in range(psteps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        s.iterate(1, mode)
+    prof = s.profile_read()
+    s.profile_enable(False)
+    pctr = s.counters()
+    fp64_peak = s.fp64_peak_tflops()
+
     # max over ranks; pair counters: every rank counts the pairs of its own rows -> sum over ranks
     tt = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
-    pe = torch.tensor([float(ctr["dcd_candidates"] + ctr["ccd_candidates"] + ctr["energy_plane_evals"])], dtype=torch.float64, device="cuda")
+    pe = torch.tensor([float(ctr["dcd_candidates"] + ctr["ccd_candidates"] + ctr["energy_plane_evals"]), float(ctr["kernel_launches"])],
+                      dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(pe, op=dist.ReduceOp.SUM)
@@ -294,7 +423,7 @@ def run_ours(args):
 
     # sharded: ONE problem over all ranks (strong); batch: every problem of every rank iterates once per step (strong: the
     # set of problems is fixed); else N replicas (weak)
-    mult = 1 if sharded else (sc["n_total"] if batch else world)
+    mult = 1 if sharded else (sc["n_total"] if batch and not args.emulate_rank else (U if batch else world))
     value = mult * args.steps / (total_ms * 1e-3)
     pair_evals = float(pe[0])      # all ranks, all problems / robots / replicas of the timed steps
     # ---- roofline: every kernel against its bound, `roofline` = the kernel with the largest share of device time
@@ -305,16 +434,14 @@ def run_ours(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "MEASURED_PEAKS.json (burst copy)" if "hbm_gbs" in peaks else "fallback of B200_PROFILING.md"
-    per_step = {k: pctr[k] / float(args.steps) for k in pctr}
-    n0 = -(-sc["V"].shape[0] // 32)
-    n1 = float(np.mean([-(-v.shape[0] // 1024) for v in sc["Vs"]])) if batch else -(-n0 // 32)
-    geo = {"rows": U * P * 8, "n1": n1, "P": P, "T": T, "U": U}
+    per_step = {k: pctr[k] / float(psteps) for k in pctr}
+    geo = {"rows": (count if sharded else U) * P * 8, "P": P, "T": T, "U": count if sharded else U}
     models = kernel_models(per_step, geo)
     tot_prof_ms = sum(v[0] for v in prof.values())
-    traffic = {}
+    ncu = {}
     try:
-        tkey = "batch%d" % sc["n_total"] if batch else sc["name"]     # the capture is specific to the problem count
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(tkey, {})
+        tkey = ("batch%d" % U) if batch else sc["name"]     # a capture is specific to the problem set on one GPU
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_metrics.json"))).get(tkey, {})
     except Exception:
         pass
     ktab = {}
@@ -322,9 +449,14 @@ def run_ours(args):
         if not kn:
             continue
         flop, byts, bound = models.get(name, (0.0, 0.0, "hbm"))
-        sec = kms * 1e-3 / args.steps                         # all launches of this kernel in one step
-        ktab[name] = {"ms_per_step": kms / args.steps, "launches_per_step": kn / float(args.steps), "bound": bound,
-                      "tflops": flop / sec / 1e12, "gbs": byts / sec / 1e9,
+        sec = kms * 1e-3 / psteps                              # all launches of this kernel in one step
+        m = ncu.get(name, {})
+        dram = m.get("dram_bytes")                             # measured DRAM read+write per launch (ncu --set full)
+        lps = kn / float(psteps)
+        ktab[name] = {"ms_per_step": kms / psteps, "launches_per_step": lps, "bound": bound,
+                      "tflops_counted": flop / sec / 1e12, "gbs_algorithmic": byts / sec / 1e9,
+                      "gbs_dram_ncu": (dram * lps / sec / 1e9) if dram else None,
+                      "fp64_pipe_active_pct_ncu": m.get("fp64_pipe_pct"),
                       "frac": (flop / sec / 1e12 / fp64_peak) if bound == "fp64" and fp64_peak else byts / sec / 1e9 / hbm_peak,
                       "share_of_step": kms / tot_prof_ms if tot_prof_ms else None}
     roof = None
@@ -333,100 +465,74 @@ def run_ours(args):
         kt = ktab[name]
         lps = kt["launches_per_step"]
         fp = kt["bound"] == "fp64"
+        m = ncu.get(name, {})
         roof = {"kernel": name, "bound": "fp64" if fp else "hbm",
-                "achieved": kt["tflops"] if fp else kt["gbs"], "peak": fp64_peak if fp else hbm_peak, "unit": "TFLOP/s" if fp else "GB/s",
-                "frac": kt["frac"], "traffic": traffic.get(name),
+                "achieved": kt["tflops_counted"] if fp else kt["gbs_algorithmic"], "peak": fp64_peak if fp else hbm_peak,
+                "unit": "TFLOP/s" if fp else "GB/s", "frac": kt["frac"], "traffic": m.get("dram_bytes"),
                 "peak_source": "FP64 DFMA microbenchmark run in this process (tob_fp64_peak); no FP64 figure in MEASURED_PEAKS.json" if fp else peak_src,
                 "share_of_step": kt["share_of_step"], "avg_launch_ms": kt["ms_per_step"] / lps, "launches_per_step": lps,
                 "algorithmic_flop_per_launch": models[name][0] / lps if name in models else None,
                 "algorithmic_bytes_per_launch": models[name][1] / lps if name in models else None,
-                "hbm": {"achieved": kt["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": kt["gbs"] / hbm_peak, "peak_source": peak_src},
-                "note": "single-problem kernels of ~10-100 us: latency-bound, see DESIGN.md section 3"}
+                "fp64_pipe_active_pct_ncu": m.get("fp64_pipe_pct"),
+                "hbm": {"achieved_algorithmic": kt["gbs_algorithmic"], "achieved_dram_ncu": kt["gbs_dram_ncu"], "peak": hbm_peak,
+                        "unit": "GB/s", "frac": kt["gbs_algorithmic"] / hbm_peak, "peak_source": peak_src},
+                "work": "flops from device counters of the work really executed (49-DOP groups, GJK rounds, in-band barrier "
+                        "terms), see kernel_models(); ncu columns come from profiles/ncu_metrics.json (captured once per round)"}
+    build = None
+    if build_ms and build_pts:
+        bsec = build_ms * 1e-3
+        build = {"points": int(build_pts), "device_ms": build_ms, "host_wall_s": build_s, "gbs_algorithmic": BYTES_PER_BUILD_POINT * build_pts / bsec / 1e9,
+                 "frac_hbm": BYTES_PER_BUILD_POINT * build_pts / bsec / 1e9 / hbm_peak, "h2d_gbs": 24.0 * build_pts / bsec / 1e9,
+                 "note": "one-time per problem; the device time includes the host-to-device copy of the clouds (24 B/pt), which bounds it"}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if (sharded or batch) else "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": ("batch: %d independent single-UAV problems (%d on this rank), clouds 1e4..1e6 pts (%d pts on this rank), %d Bezier pieces each, 3D.json params"
-                                % (sc["n_total"], U, sc["V"].shape[0], P)) if batch else
-                               "%s: %d UAV, %d pts, %d Bezier pieces (%d sub-segments each), 3D.json params" % (sc["name"], U, sc["V"].shape[0], P, P * 8),
-                   "l2": "flushed between timed iterations (256 MiB rewrite outside the event brackets)",
-                   "multi_gpu": ("robots sharded over ranks, NCCL all-gather of control points/directions" if sharded else
-                                 ("independent problems dealt round-robin to the ranks, no communication" if batch else
-                                  ("replicas only" if world > 1 else "single"))), "lbvh_build_s": build_s, "gnorm_last": gn},
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if (sharded or batch) else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": describe(args, world),
         "pair_evals_per_s": pair_evals / (total_ms * 1e-3),
         "pairs_per_step": {k: ctr[k] / args.steps for k in ("dcd_candidates", "planes", "ccd_candidates", "energy_plane_evals", "barrier_terms")},
-        "e2e": {"value": mult * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes},
-        "gpu_launches": int(ctr["kernel_launches"]),
+        "e2e": {"value": mult * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": state_bytes * world, "d2h_bytes_per_step": state_bytes * world},
+        "gpu_launches": int(pe[1]),
         "clocks": sampler.summary(),
         "roofline": roof,
         "kernels": ktab,
+        "build": build,
+        "run": {"problems_on_rank0": U, "points_on_rank0": int(sc.get("n_points", sc["V"].shape[0] if "V" in sc else 0)), "gnorm_last": gn,
+                "emulated_rank": args.emulate_rank},
     }
     # CPU baseline on a bounded sample, rank 0, N == 1 only
-    if world == 1 and not args.no_cpu and not batch:
-        out["cpu_baseline"] = cpu_baseline(sc, P, budget_s=25.0, max_iters=6)
+    if world == 1 and not args.no_cpu:
+        if batch:
+            out["cpu_baseline"] = cpu_batch(sc["n_total"], warm=1, steps=2, budget_s=6.0)
+        else:
+            sc["coupled"] = coupled
+            out["cpu_baseline"] = cpu_single(sc, P, budget_s=25.0, max_iters=6)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(sc, P, budget_s, max_iters, sample_points=None):
-    """the reference's CPU path timed on this box's host cores (1 core: the reference has no parallel region)"""
-    from oracle import oracle_api as oa
-    from trajopt import scenes
-    o = oa.get()
-    o.setup(oa.Params(P, uav_num=sc["uav_num"], ks=sc["ks"]))
-    V = sc["V"]
-    # the reference's incremental tree build is O(minutes) for 1 M points in random order; Morton-free trick is not
-    # available to it, so the build (one-time, outside the metric) is done on the full cloud and not timed.
-    t0 = time.time()
-    o.init_pointcloud(V)
-    build = time.time() - t0
-    sts = scenes.initial_states(sc)
-    n, t_used = 0, 0.0
-    while n < max_iters and t_used < budget_s:
-        t0 = time.perf_counter()
-        sts = o.optimization_multi(sts, coupled=False) if len(sts) > 1 else [o.optimization(sts[0])]
-        t_used += time.perf_counter() - t0
-        n += 1
-    return {"value": n / t_used, "unit": UNIT, "cores": 1, "kind": o.kind,
-            "sample": "first %d ADMM iterations of the same scene from the same initial state (tree build %.1f s excluded)" % (n, build)}
-
-
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    sc = workload(args.workload, args.points)
-    P = len(sc["way_points"][0]) - 1
-    from oracle import oracle_api as oa
-    from trajopt import scenes
-    o = oa.get()
-    o.setup(oa.Params(P, uav_num=sc["uav_num"], ks=sc["ks"]))
-    t0 = time.time()
-    o.init_pointcloud(sc["V"])
-    build = time.time() - t0
-    sts = scenes.initial_states(sc)
-    step = (lambda x: o.optimization_multi(x, coupled=False)) if len(sts) > 1 else (lambda x: [o.optimization(x[0])])
-    budget = 150.0
-    t_all = 0.0
-    for _ in range(args.warmup):
-        t0 = time.perf_counter(); sts = step(sts); t_all += time.perf_counter() - t0
-        if t_all > budget / 3:
-            break
-    n, t_used = 0, 0.0
-    while n < args.steps and t_used < budget:
-        t0 = time.perf_counter()
-        sts = step(sts)
-        t_used += time.perf_counter() - t0
-        n += 1
-    value = n / t_used
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    sample = "%d ADMM iterations (time-bounded from --steps %d) on 1 host core, tree build %.1f s excluded" % (n, args.steps, build)
-    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": n, "warmup": args.warmup,
-           "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "%s: %d UAV, %d pts, %d Bezier pieces (%d sub-segments each), 3D.json params" % (sc["name"], sc["uav_num"], sc["V"].shape[0], P, P * 8)},
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": o.kind, "sample": sample},
+    if args.workload == "batch":
+        cb = cpu_batch(args.problems or 1024, warm=min(args.warmup, 3), steps=args.steps, budget_s=100.0)
+        steps = args.steps
+    else:
+        sc = workload(args, 0, 1)
+        sc["coupled"] = args.workload == "circle64c"
+        P = len(sc["way_points"][0]) - 1
+        cb = cpu_single(sc, P, budget_s=150.0, max_iters=args.steps, warm=args.warmup)
+        steps = args.steps
+    value = cb["value"]
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "strong" if args.workload in ("batch", "circle64", "circle64c", "cross8") else "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": describe(args, world),
+           "cpu_baseline": cb,
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -434,12 +540,13 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="forest")
+    ap.add_argument("--workload", default="batch", choices=["batch", "forest", "bridge", "cross8", "circle64", "circle64c"])
     ap.add_argument("--points", type=int, default=None)
     ap.add_argument("--problems", type=int, default=None, help="--workload batch: number of independent problems (default 1024)")
+    ap.add_argument("--emulate-rank", default=None, help="--workload batch, one GPU: run the share of rank R of W ('R/W'); profiling aid")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

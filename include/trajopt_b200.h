@@ -91,6 +91,11 @@ int tob_self_broadphase(tob_ctx* ctx, const double* P, const double* D /* NULL =
 int tob_box_query(tob_ctx* ctx, const double* lo, const double* hi, double d, uint32_t* ids, uint64_t cap,
                   uint64_t* total);
 
+/* The obstacle loop of the front end's motion validator (HighOrderCCD/OMPL/OMPL.cpp:36-96: BVH::EdgeCollision, then
+ * CCD::GJKDCD(edge, point, d) per candidate, CCD/CCD.h:17-114; invalid at the first collision), batched: edges = n x 2 x 3
+ * (edge, endpoint, xyz); valid[i] = 1 iff no cloud point is within d of the segment i.  One launch for all edges. */
+int tob_edge_validity_batch(tob_ctx* ctx, const double* edges, int n, double d, uint8_t* valid);
+
 /* ---- per-pair primitives (function-level parity entry points) ----------------------------------------------- */
 /* batch of n independent evaluations of gjk() (lib/opengjk/src/openGJK.c:754-852) as marshalled by CCD::GJKDCD /
  * GJKCCD / SelfGJKCCD (CCD/CCD.h:17-352); A: n blocks of na x 3 col-major, B likewise (1 <= na,nb <= 16). */
@@ -233,6 +238,11 @@ typedef struct tob_counters {
   uint64_t barrier_terms;        /* (control point, plane) terms inside the barrier band (d < margin) that were evaluated */
   uint64_t live_planes;          /* persistent-plane mode: live (sub-segment, point) planes */
   uint64_t refine_capped;        /* plane refinements stopped by a loop cap (the reference's loops are unbounded) */
+  /* counted work (not a model): what the narrowphase / CCD kernels really executed */
+  uint64_t np_kdop_groups;       /* 7-axis groups of the 49-DOP gate evaluated (49 axes = 7 groups, early exit between groups) */
+  uint64_t np_gjk_iters;         /* GJK(6,1) rounds run for the k-DOP survivors */
+  uint64_t ccd_gjk_iters;        /* GJK(12,1) rounds run by the CCD ladder */
+  uint64_t ccd_kdop_pass;        /* swept candidates that passed the swept 49-DOP gate */
 } tob_counters;
 int tob_get_counters(const tob_ctx* ctx, tob_counters* out);
 int tob_reset_counters(tob_ctx* ctx);
@@ -243,16 +253,47 @@ int tob_profile_enable(tob_ctx* ctx, int on);
 int tob_profile_read(tob_ctx* ctx, int kid, double* ms_total, uint64_t* launches, const char** name);
 
 /* ---- multi-GPU (robots sharded across ranks; cloud replicated) -------------------------------------------------
- * The context owns robots [first, first+count) of n_total.  The per-iteration exchange (all robots' control
- * points before separate_self, directions before self_step, two scalars) is delegated to two callbacks so the
- * host can use NCCL through whatever plumbing it has (torch.distributed in bench.py, ncclAllGather in C++).
- * allgather(dev_ptr_full, elems_per_rank, user): in-place all-gather of FP64 on the context's stream.
- * allreduce_sum(dev_ptr, n, user). */
+ * The reference iterates over the robots serially (Optimization3D_multi.h:40-49,59-71,78-89); here every rank (one process
+ * or host thread per GPU, one context each) owns a contiguous block of the uav_num robots and the per-iteration exchange
+ * runs over NCCL on the context's stream, inside the iteration's CUDA graph:
+ *   decoupled (mode 0): all-gather of the control points before separate_self (Optimization3D_multi.h:51), then ONE
+ *                       grouped all-gather of directions + wolfe + gnorm before Step::self_step (:72-76)
+ *   coupled   (mode 1): additionally the seven Schur sums of every robot's block of the joint Newton system (:519-557),
+ *                       the CCD ladder exponents (shared step = min over robots, :586-594) and the trial energies of each
+ *                       Armijo round (:605-636); all sums are taken locally in robot order after the all-gather.
+ * A sharded run is bitwise equal to the same problem in one context.  NCCL is bound at run time (dlopen of libnccl.so.2,
+ * reusing a copy the process has already loaded); every rank calls the same sequence of tob_admm_iterate /
+ * tob_optimization.  tob_states_upload takes ALL uav_num states on every rank (only the owned ones are used);
+ * tob_states_download returns valid data for the owned robots [first, first+count).
+ *
+ *   tob_nccl_unique_id   rank 0: 128-byte ncclUniqueId to hand to the other ranks (MPI, a file, torch.distributed ...)
+ *   tob_nccl_init_rank   ncclCommInitRank on the context's device; the communicator is owned by the context
+ *   tob_nccl_attach      use a communicator the host already has (ncclComm_t; not destroyed with the context)
+ *   tob_nccl_init_all    one process driving n GPUs (one context each, one host thread per context while iterating):
+ *                        ncclCommInitAll over the contexts' devices
+ *   tob_nccl_detach      back to an unsharded context
+ *   tob_shard_range      robots owned by this context: first = rank*floor(U/W) + min(rank, U mod W)            */
+int tob_nccl_available(int* version /* may be NULL; NCCL_VERSION_CODE of the library that was bound */);
+int tob_nccl_unique_id(void* id128);
+int tob_nccl_init_rank(tob_ctx* ctx, const void* id128, int rank, int world);
+int tob_nccl_attach(tob_ctx* ctx, void* nccl_comm);
+int tob_nccl_init_all(tob_ctx** ctxs, int n_ctx);
+int tob_nccl_detach(tob_ctx* ctx);
+int tob_shard_range(const tob_ctx* ctx, int* first, int* count, int* rank, int* world);
+
+/* Legacy exchange through host callbacks (decoupled mode, equal blocks only, not graph-captured): the context owns robots
+ * [first, first+count) of n_total and calls
+ *   allgather(dev_ptr_full, elems_per_rank, user): in-place all-gather of FP64 on the context's stream.
+ * for every exchange above (allreduce is unused: sums are taken locally after the all-gather). */
 typedef int (*tob_allgather_fn)(void* dev_ptr_full, uint64_t elems_per_rank, void* user);
 typedef int (*tob_allreduce_fn)(void* dev_ptr, uint64_t n, int op /*0 sum,1 min,2 max*/, void* user);
 int tob_set_shard(tob_ctx* ctx, int first, int count, int n_total, tob_allgather_fn ag, tob_allreduce_fn ar,
                   void* user);
 void* tob_stream(tob_ctx* ctx); /* cudaStream_t the context launches on */
+
+/* LBVH build of the last tob_cloud_upload / tob_cloud_upload_batch: device time (H2D of the clouds + Morton keys + radix
+ * sort + gather, CUDA events on the context's stream) and points; the build streams 128 B per point. */
+int tob_build_stats(const tob_ctx* ctx, double* ms, uint64_t* points);
 
 /* FP64 pipe microbenchmark (DFMA chains) used as the roofline denominator of the FP64-bound kernels */
 int tob_fp64_peak(tob_ctx* ctx, double* tflops);

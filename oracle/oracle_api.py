@@ -252,6 +252,60 @@ class _Base:
         self._f(name)(*self._state_args(st), *self._plane_args(planes), _d(direction), C.byref(td), C.byref(w), C.byref(gn))
         return direction, td.value, w.value, gn.value
 
+    # ---- function-level rows behind the remaining C-ABI entries (reference oracle / host drop-in only, not in the C port)
+    def local_plane_barrier_gradient(self, spline, tr_id, c, d):
+        c = np.ascontiguousarray(c, dtype=np.float64).reshape(-1, 3); d = np.ascontiguousarray(d, dtype=np.float64)
+        g = np.zeros(18); h = np.zeros((18, 18), order="F")
+        self._f("local_plane_barrier_gradient")(_d(F(spline)), C.c_int(tr_id), _d(c), _d(d), C.c_int(len(d)), _d(g), _d(h))
+        return g, h
+
+    def local_bound_gradient(self, spline, tr_id, piece_time):
+        g = np.zeros(18); h = np.zeros((18, 18), order="F"); pg = np.zeros(18); gt = C.c_double(0); ht = C.c_double(0)
+        self._f("local_bound_gradient")(_d(F(spline)), C.c_int(tr_id), C.c_double(piece_time), _d(g), _d(h), C.byref(gt), C.byref(ht), _d(pg))
+        return g, h, gt.value, ht.value, pg
+
+    def slack_energy(self, c_spline, piece_time, p_part, t_part, p_lambda, t_lambda):
+        return self._f("slack_energy", C.c_double)(_d(F(c_spline)), C.c_double(piece_time), _d(F(p_part)), C.c_double(t_part),
+                                                   _d(F(p_lambda)), C.c_double(t_lambda))
+
+    def slack_gradient(self, c_spline, piece_time, p_part, t_part, p_lambda, t_lambda):
+        g = np.zeros(19); h = np.zeros((19, 19), order="F")
+        self._f("slack_gradient")(_d(F(c_spline)), C.c_double(piece_time), _d(F(p_part)), C.c_double(t_part), _d(F(p_lambda)),
+                                  C.c_double(t_lambda), _d(g), _d(h))
+        return g, h
+
+    def dynamic_energy(self, p_part, t_part):
+        return self._f("dynamic_energy", C.c_double)(_d(F(p_part)), C.c_double(t_part))
+
+    def dynamic_gradient(self, p_part, t_part):
+        g = np.zeros(18); h = np.zeros((18, 18), order="F"); pg = np.zeros(18); gt = C.c_double(0); ht = C.c_double(0)
+        self._f("dynamic_gradient")(_d(F(p_part)), C.c_double(t_part), _d(g), _d(h), C.byref(gt), C.byref(ht), _d(pg))
+        return g, h, gt.value, ht.value, pg
+
+    def line_search(self, st, direction, t_direction, wolfe, planes, step=None):
+        """Optimization3D_admm::spline_line_search (step None: bound = Step::position_step) or the multi-UAV variant with the
+        caller's bound `step`; returns (spline, piece_time[, accepted step])"""
+        sp = F(st["spline"]); pt = C.c_double(st["piece_time"])
+        args = (_d(sp), C.byref(pt), _d(F(direction)), C.c_double(t_direction), C.c_double(wolfe), _d(F(st["p_slack"])),
+                _d(F(st["t_slack"])), _d(F(st["p_lambda"])), _d(F(st["t_lambda"])), *self._plane_args(planes))
+        if step is None:
+            self._f("line_search")(*args)
+            return sp, pt.value
+        s_io = C.c_double(step)
+        self._f("line_search_multi")(*args, C.byref(s_io))
+        return sp, pt.value, s_io.value
+
+    def edge_collision(self, edge, d, cap=1 << 16):
+        ids = np.zeros(cap, dtype=np.uint32)
+        n = self._f("edge_collision", C.c_long)(_d(F(edge)), C.c_double(d), _u(ids), C.c_long(cap))
+        if n > cap:
+            return self.edge_collision(edge, d, int(n))
+        return ids[:n]
+
+    def gjk_dcd(self, A, B, d):
+        A = F(np.atleast_2d(A)); B = F(np.atleast_2d(B))
+        return bool(self._f("gjk_dcd", C.c_int)(_d(A), C.c_int(A.shape[0]), _d(B), C.c_int(B.shape[0]), C.c_double(d)))
+
     # ---- steps
     def position_step(self, spline, direction):
         return self._f("position_step", C.c_double)(_d(F(spline)), _d(F(direction)))

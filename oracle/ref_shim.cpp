@@ -548,4 +548,91 @@ long ref_separate_self(const double* splines, int u, unsigned* off, double* c, d
   return n;
 }
 
+// ---- function-level entry points behind the remaining C-ABI rows (tests/test_gpu_abi_entries.py) ---------------------
+// Gradient_admm::local_plane_barrier_gradient (Gradient_admm.h:331-407): one sub-segment against its plane list
+void ref_local_plane_barrier_gradient(const double* spline, int tr_id, const double* c, const double* d, int n, double* grad18,
+                                      double* hess324) {
+  std::vector<Eigen::Vector3d> cl; std::vector<double> dl;
+  for (int k = 0; k < n; k++) { cl.push_back(Eigen::Vector3d(c[3 * k], c[3 * k + 1], c[3 * k + 2])); dl.push_back(d[k]); }
+  Eigen::VectorXd g; Eigen::MatrixXd h;
+  Gradient_admm::local_plane_barrier_gradient(tr_id, map_mat(spline, trajectory_num, 3), cl, dl, g, h);
+  std::memcpy(grad18, g.data(), 18 * sizeof(double));
+  std::memcpy(hess324, h.data(), 324 * sizeof(double));
+}
+// Gradient_admm::local_bound_gradient (Gradient_admm.h:409-572)
+void ref_local_bound_gradient(const double* spline, int tr_id, double piece_time, double* grad18, double* hess324, double* g_t,
+                              double* h_t, double* partgrad18) {
+  Eigen::VectorXd g, pg; Eigen::MatrixXd h;
+  Gradient_admm::local_bound_gradient(tr_id, map_mat(spline, trajectory_num, 3), piece_time, g, h, *g_t, *h_t, pg);
+  std::memcpy(grad18, g.data(), 18 * sizeof(double));
+  std::memcpy(hess324, h.data(), 324 * sizeof(double));
+  std::memcpy(partgrad18, pg.data(), 18 * sizeof(double));
+}
+// Gradient_admm::slack_gradient (Gradient_admm.h:574-622): grad[19], hessian[19x19 col-major]
+void ref_slack_gradient(const double* c_spline, double piece_time, const double* p_part, double t_part, const double* p_lambda,
+                        double t_lambda, double* grad19, double* hess361) {
+  Eigen::VectorXd g; Eigen::MatrixXd h;
+  Gradient_admm::slack_gradient(map_mat(c_spline, 6, 3), piece_time, map_mat(p_part, 6, 3), t_part, map_mat(p_lambda, 6, 3),
+                                t_lambda, g, h);
+  std::memcpy(grad19, g.data(), 19 * sizeof(double));
+  std::memcpy(hess361, h.data(), 361 * sizeof(double));
+}
+// Energy_admm::dynamic_energy (Energy_admm.h:199-215), Gradient_admm::dynamic_gradient (Gradient_admm.h:633-671)
+double ref_dynamic_energy(const double* p_part, double t_part) { return Energy_admm::dynamic_energy(map_mat(p_part, 6, 3), t_part); }
+void ref_dynamic_gradient(const double* p_part, double t_part, double* grad18, double* hess324, double* g_t, double* h_t,
+                          double* partgrad18) {
+  Eigen::VectorXd g, pg; Eigen::MatrixXd h;
+  Gradient_admm::dynamic_gradient(map_mat(p_part, 6, 3), t_part, g, h, *g_t, *h_t, pg);
+  std::memcpy(grad18, g.data(), 18 * sizeof(double));
+  std::memcpy(hess324, h.data(), 324 * sizeof(double));
+  std::memcpy(partgrad18, pg.data(), 18 * sizeof(double));
+}
+// Optimization3D_admm::spline_line_search (Optimization3D_admm.h:505-557): CCD bound from Step::position_step, then Armijo
+// against the given planes with the global `wolfe`; spline / piece_time in-out
+void ref_line_search(double* spline, double* piece_time, const double* direction, double t_direction, double wolfe_in,
+                     const double* p_slack, const double* t_slack, const double* p_lambda, const double* t_lambda,
+                     const unsigned* off, const double* c, const double* d) {
+  Quiet q;
+  std::vector<std::vector<Eigen::Vector3d>> cl; std::vector<std::vector<double>> dl;
+  planes_from_csr(off, c, d, subdivide_tree.size(), cl, dl);
+  Eigen::VectorXd ts = Eigen::Map<const Eigen::VectorXd>(t_slack, piece_num);
+  Eigen::VectorXd tl = Eigen::Map<const Eigen::VectorXd>(t_lambda, piece_num);
+  Data sp = map_mat(spline, trajectory_num, 3);
+  double pt = *piece_time;
+  wolfe = wolfe_in;
+  Optimization3D_admm::spline_line_search(sp, map_mat(direction, trajectory_num, 3), pt, t_direction,
+                                          map_mat(p_slack, 6 * piece_num, 3), ts, map_mat(p_lambda, 6 * piece_num, 3), tl,
+                                          g_vertex_list, *g_bvh, cl, dl);
+  std::memcpy(spline, sp.data(), 3 * trajectory_num * sizeof(double));
+  *piece_time = pt;
+}
+// Optimization3D_multi::spline_line_search (Optimization3D_multi.h:754-811): the caller's step bound, in-out
+void ref_line_search_multi(double* spline, double* piece_time, const double* direction, double t_direction, double wolfe_in,
+                           const double* p_slack, const double* t_slack, const double* p_lambda, const double* t_lambda,
+                           const unsigned* off, const double* c, const double* d, double* step_io) {
+  Quiet q;
+  std::vector<std::vector<Eigen::Vector3d>> cl; std::vector<std::vector<double>> dl;
+  planes_from_csr(off, c, d, subdivide_tree.size(), cl, dl);
+  Eigen::VectorXd ts = Eigen::Map<const Eigen::VectorXd>(t_slack, piece_num);
+  Eigen::VectorXd tl = Eigen::Map<const Eigen::VectorXd>(t_lambda, piece_num);
+  Data sp = map_mat(spline, trajectory_num, 3);
+  double pt = *piece_time, st = *step_io;
+  wolfe = wolfe_in;
+  Optimization3D_multi::spline_line_search(sp, map_mat(direction, trajectory_num, 3), pt, t_direction,
+                                           map_mat(p_slack, 6 * piece_num, 3), ts, map_mat(p_lambda, 6 * piece_num, 3), tl, cl, dl, st);
+  std::memcpy(spline, sp.data(), 3 * trajectory_num * sizeof(double));
+  *piece_time = pt; *step_io = st;
+}
+// BVH::EdgeCollision (BVH.cpp:95-133): ids of all points within d of the box of a 2-point edge (2x3 col-major)
+long ref_edge_collision(const double* edge, double d, unsigned* ids, long cap) {
+  std::vector<unsigned int> cp;
+  g_bvh->EdgeCollision(map_mat(edge, 2, 3), cp, d);
+  for (size_t k = 0; k < cp.size() && (long)k < cap; k++) ids[k] = cp[k];
+  return (long)cp.size();
+}
+// CCD::GJKDCD (CCD.h:17-114)
+int ref_gjk_dcd(const double* A, int na, const double* B, int nb, double d) {
+  return CCD::GJKDCD(map_mat(A, na, 3), map_mat(B, nb, 3), d) ? 1 : 0;
+}
+
 }  // extern "C"

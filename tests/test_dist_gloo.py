@@ -33,8 +33,11 @@ def _worker(rank, world, port, n_robots, per_robot, q):
 def test_partition_blocks():
     assert tdist.partition(64, 8, 3) == (24, 8)
     assert tdist.partition(8, 2, 1) == (4, 4)
+    # unequal shares (native NCCL path: one grouped broadcast per rank): the first (n mod world) ranks own one robot more
+    assert [tdist.partition(10, 4, r) for r in range(4)] == [(0, 3), (3, 3), (6, 2), (8, 2)]
+    assert sum(tdist.partition(9, 2, r)[1] for r in range(2)) == 9
     with pytest.raises(ValueError):
-        tdist.partition(10, 4, 0)
+        tdist.partition(3, 4, 0)
 
 
 def test_allgather_layout_world2():

@@ -105,18 +105,20 @@ def test_decoupled_iterations_track_reference(world):
         assert abs(a[0]["gnorm"] - b[0]["gnorm"]) <= 1e-6 * max(1.0, a[0]["gnorm"])
 
 
-def test_sharded_two_gpus_equals_single():
-    """needs 2 GPUs: robots sharded over 2 ranks with the NCCL exchange == one context, and tracks the oracle"""
+@pytest.mark.parametrize("ranks", [2, 4, 8])
+def test_sharded_equals_single(ranks):
+    """needs `ranks` GPUs: robots sharded over the ranks with the native NCCL exchange (decoupled, coupled, unequal shares,
+    overflow agreement, legacy callbacks) == one context bitwise, and tracks the oracle (tests/run_sharded_check.py)"""
     import subprocess
     import sys
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(ROOT, "tests", "run_sharded_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "sharded==single:True" in out.stdout
+    if torch.cuda.device_count() < ranks:
+        pytest.skip("needs %d GPUs" % ranks)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(ranks), "--master-addr", "127.0.0.1",
+           "--master-port", str(29517 + ranks), os.path.join(ROOT, "tests", "run_sharded_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "SHARDED_CHECK ALL ranks=%d ok:True" % ranks in out.stdout, out.stdout[-3000:]
 
 
 def test_coupled_iterations_against_golden():

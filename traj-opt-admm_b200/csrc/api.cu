@@ -53,6 +53,8 @@ static int upload(tob_ctx* c, DBuf<double>& b, const double* src, size_t n, size
   return 0;
 }
 
+static int pinned_ensure(tob_ctx* c, size_t bytes);
+
 static int alloc_states(tob_ctx* c) {
   const int U = c->n_robots(), P = c->prm.piece_num, T = c->T;
   TOB_CUDA(c, c->s_spline.ensure((size_t)U * 3 * T));
@@ -69,6 +71,7 @@ static int alloc_states(tob_ctx* c) {
   TOB_CUDA(c, c->s_etr.ensure((size_t)U * TOB_LS_TRIALS));
   TOB_CUDA(c, c->s_done.ensure(U + 1)); TOB_CUDA(c, c->solve_status.ensure(U));
   TOB_CUDA(c, c->kmax.ensure(U + 1));
+  TOB_TRY(pinned_ensure(c, (size_t)U * sizeof(double) + 64));   // gnorm of every robot is read back once per iteration
   return 0;
 }
 
@@ -183,16 +186,30 @@ __global__ void k_armijo_coupled(int U, const double* etr, const double* wolfe, 
   atomicAdd(n_active, 1);
 }
 
-__global__ void k_apply_step(int rb, int re, int T, const double* step, const double* dir, const double* ptrial, double* spline,
-                             double* ptime, const DevCounts* guard) {
+// robots [rb,re): piece time <- accepted trial time; the control points move only for the robots this context owns
+// ([ob,oe): coupled sharded runs keep the ONE shared piece time current in every robot slot)
+__global__ void k_apply_step(int rb, int re, int ob, int oe, int T, const double* step, const double* dir, const double* ptrial,
+                             double* spline, double* ptime, const DevCounts* guard) {
   int u = rb + blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= re || iteration_blocked(guard)) return;
-  if (i < 3 * T) {
+  if (i < 3 * T && u >= ob && u < oe) {
     size_t g = (size_t)u * 3 * T + i;
     spline[g] = spline[g] + step[u] * dir[g];
   }
   if (i == 0) ptime[u] = ptrial[u];
+}
+
+// sharded runs: every rank publishes its overflow / error bits, and adopts the others' so that all ranks take the same
+// decision about committing the iteration (a rank that repeated the iteration alone would leave the collectives unmatched)
+__global__ void k_flags_pack(const DevCounts* dc, double* all, int rank) { all[rank] = (double)dc->overflow; }
+__global__ void k_flags_merge(DevCounts* dc, const double* all, int rank, int world) {
+  uint32_t remote = 0;
+  for (int r = 0; r < world; r++) if (r != rank) remote |= (uint32_t)all[r];
+  uint32_t add = 0;
+  if (remote & TOB_ERR_SOLVE) add |= TOB_ERR_SOLVE;
+  if (remote & (TOB_OVF_CAND | TOB_OVF_LIVE | TOB_OVF_REMOTE)) add |= TOB_OVF_REMOTE;
+  if (add) dc->overflow |= add;
 }
 
 __global__ void k_zero_steps(double* p, int n) {
@@ -200,7 +217,19 @@ __global__ void k_zero_steps(double* p, int n) {
   if (i < n) p[i] = 0.0;
 }
 
+// pinned read-back area: at least `bytes`
+static int pinned_ensure(tob_ctx* c, size_t bytes) {
+  if (bytes <= c->h_pinned_bytes) return 0;
+  size_t want = bytes < 65536 ? 65536 : bytes + bytes / 4;
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  c->h_pinned = nullptr; c->h_pinned_bytes = 0;
+  TOB_CUDA(c, cudaMallocHost((void**)&c->h_pinned, want));
+  c->h_pinned_bytes = want;
+  return 0;
+}
+
 static int read_back(tob_ctx* c, const void* dev, size_t bytes) {
+  TOB_TRY(pinned_ensure(c, bytes));
   TOB_CUDA(c, cudaMemcpyAsync(c->h_pinned, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
   TOB_CUDA(c, cudaStreamSynchronize(c->stream));
   return 0;
@@ -260,16 +289,18 @@ static int ls_round(tob_ctx* c, int rb, int re, int wolfe_idx, bool coupled, int
   cudaStream_t st = c->stream;
   if (!coupled) return line_search_round(c, rb, re, wolfe_idx, round == 0 ? 0 : 1, round == 0 ? c->ls_kte0 : c->ls_kte, slot);
   TOB_TRY(energy_trials(c, rb, re, c->s_dir.p, c->s_tstep.p, c->s_ttime.p, TOB_LS_TRIALS, round == 0 ? 0 : 1, TOB_LS_TRIALS, c->s_etr.p));
-  k_armijo_coupled<<<1, 32, 0, st>>>(re - rb, c->s_etr.p, c->s_wolfe.p, c->s_ptime.p, c->s_tdir.p, c->s_step.p, c->s_ptrial.p,
+  TOB_TRY(exchange_robots(c, c->s_etr.p, TOB_LS_TRIALS, sizeof(double)));   // joint Armijo: every rank sums all robots in robot order
+  k_armijo_coupled<<<1, 32, 0, st>>>(c->n_robots(), c->s_etr.p, c->s_wolfe.p, c->s_ptime.p, c->s_tdir.p, c->s_step.p, c->s_ptrial.p,
                                      c->s_tstep.p, c->s_ttime.p, c->s_done.p, &c->dc.p->ls_pending[slot]);
   TOB_LAUNCH_CHECK(c);
   c->ctr.line_search_trials += (uint64_t)(re - rb) * (TOB_LS_TRIALS - 1);
   return 0;
 }
 
-static int apply_step(tob_ctx* c, int rb, int re, bool guarded) {
-  dim3 grid(div_up(3 * c->T, 128), re - rb);
-  k_apply_step<<<grid, 128, 0, c->stream>>>(rb, re, c->T, c->s_step.p, c->s_dir.p, c->s_ptrial.p, c->s_spline.p, c->s_ptime.p,
+static int apply_step(tob_ctx* c, int rb, int re, bool guarded, bool coupled = false) {
+  const int b = coupled ? 0 : rb, e = coupled ? c->n_robots() : re;
+  dim3 grid(div_up(3 * c->T, 128), e - b);
+  k_apply_step<<<grid, 128, 0, c->stream>>>(b, e, rb, re, c->T, c->s_step.p, c->s_dir.p, c->s_ptrial.p, c->s_spline.p, c->s_ptime.p,
                                             guarded ? c->dc.p : nullptr);
   TOB_LAUNCH_CHECK(c);
   return 0;
@@ -291,6 +322,7 @@ static int ls_finish(tob_ctx* c, int rb, int re, int wolfe_idx, bool coupled) {
     TOB_TRY(sync_counts(c));
     pending = c->h_dc->ls_pending[slot];
   }
+  if (pending > 0) return fail_msg(c, "line search: no Armijo rung accepted after 400 rounds of the 0.8 ladder (step < 1e-300)");
   TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->ls_pending[c->ls_rounds - 1], 0, sizeof(int), c->stream));
   return 0;
 }
@@ -300,14 +332,7 @@ static int line_search(tob_ctx* c, int rb, int re, int wolfe_idx, bool coupled =
   TOB_TRY(ls_launch_ahead(c, rb, re, wolfe_idx, coupled));
   TOB_TRY(sync_counts(c));
   TOB_TRY(ls_finish(c, rb, re, wolfe_idx, coupled));
-  return apply_step(c, rb, re, false);
-}
-
-static int exchange(tob_ctx* c, DBuf<double>& buf, size_t elems_per_robot) {
-  if (!c->ag) return 0;
-  size_t per_rank = elems_per_robot * (size_t)(c->own_end - c->own_begin);
-  if (c->ag(buf.p, per_rank, c->cb_user)) return fail_msg(c, "all-gather callback failed");
-  return 0;
+  return apply_step(c, rb, re, false, coupled);
 }
 
 // buffers of the whole iteration, sized from the parameters and the candidate capacity: nothing is allocated (and no size
@@ -323,14 +348,15 @@ static int ensure_iter_buffers(tob_ctx* c) {
   if (U > 1 && c->cloud_n1.empty()) {   // inter-robot scratch (never used by independent problems)
     const size_t n = (size_t)c->n_tr * (U * (U - 1) / 2);
     TOB_CUDA(c, c->self_pl.ensure(4 * n + 4)); TOB_CUDA(c, c->self_ok.ensure(n + 1));
-    TOB_CUDA(c, c->self_hits.ensure(16384 + 2));
+    TOB_CUDA(c, c->self_hits.ensure(2 * (n ? n : 1) + 2));
   }
   return 0;
 }
 
-// One ADMM iteration, launched without any host read-back.  `deferred`: the state-changing tail (apply step, slack /
-// dual update) is guarded on the device by dc->overflow / dc->ls_pending and the caller inspects dc afterwards;
-// otherwise (sharded multi-GPU: collectives in the middle must stay matched across ranks) the host checks as it goes.
+// One ADMM iteration, launched without any host read-back: the state-changing tail (apply step, slack / dual update) is
+// guarded on the device by dc->overflow / dc->ls_pending and the caller inspects dc afterwards.  Sharded multi-GPU runs
+// take the same path: the exchanges are enqueued on the stream like kernels, and the overflow / error bits of every rank
+// travel with the second exchange so that all ranks agree on whether the iteration commits.
 // few rows: cover 8 rungs per launch (latency); many rows: one rung per round (throughput), more rounds ahead
 static void ls_policy(tob_ctx* c, int rb, int re, bool coupled) {
   const bool many = !coupled && (long long)(re - rb) * c->n_tr >= 4096;
@@ -346,26 +372,38 @@ static void ls_policy(tob_ctx* c, int rb, int re, bool coupled) {
   }
 }
 
-static int iterate_launch(tob_ctx* c, int mode, bool deferred) {
+static int iterate_launch(tob_ctx* c, int mode) {
   const int rb = c->own_begin, re = c->own_end;
   // mode 2: the robot slots hold INDEPENDENT single-UAV problems (no inter-robot terms, no exchange): everything below that
   // is conditional on "several robots" sees one robot
   const int U = mode == 2 ? 1 : c->n_robots();
   cudaStream_t st = c->stream;
   const bool coupled = mode == 1;
+  const bool shard = c->sharded() && U > 1;
   // (1) control points of every robot are needed for the inter-robot planes
-  if (U > 1) TOB_TRY(exchange(c, c->s_spline, (size_t)3 * c->T));
-  if (deferred) TOB_TRY(separate_resident(c, rb, re, U > 1));
-  else TOB_TRY(run_checked(c, [&]() { return separate_resident(c, rb, re, U > 1); }));
+  if (shard) TOB_TRY(exchange_robots(c, c->s_spline.p, (size_t)3 * c->T, sizeof(double)));
+  TOB_TRY(separate_resident(c, rb, re, U > 1));
   // (2) Newton direction (geo.P of the owned rows is still current from the plane pass)
   TOB_TRY(gradient_blocks(c, rb, re, 1));
   if (coupled) TOB_TRY(solve_coupled(c));
   else TOB_TRY(solve_directions(c, rb, re, U > 1));
   // (3) CCD step bound
   if (U > 1) {
-    TOB_TRY(exchange(c, c->s_dir, (size_t)3 * c->T));
-    TOB_TRY(exchange(c, c->s_wolfe, 1));
-    TOB_TRY(exchange(c, c->s_gnorm, 1));
+    if (shard) {
+      // one grouped exchange: directions (+ wolfe, gnorm of the decoupled solves) and every rank's overflow / error bits
+      k_flags_pack<<<1, 1, 0, st>>>(c->dc.p, c->ovf_all.p, c->comm_rank);
+      TOB_LAUNCH_CHECK(c);
+      TOB_TRY(exchange_group_begin(c));
+      TOB_TRY(exchange_robots(c, c->s_dir.p, (size_t)3 * c->T, sizeof(double)));
+      if (!coupled) {
+        TOB_TRY(exchange_robots(c, c->s_wolfe.p, 1, sizeof(double)));
+        TOB_TRY(exchange_robots(c, c->s_gnorm.p, 1, sizeof(double)));
+      }
+      TOB_TRY(exchange_ranks(c, c->ovf_all.p));
+      TOB_TRY(exchange_group_end(c));
+      k_flags_merge<<<1, 1, 0, st>>>(c->dc.p, c->ovf_all.p, c->comm_rank, c->comm_world);
+      TOB_LAUNCH_CHECK(c);
+    }
     TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, 0, U, 3));
     TOB_TRY(self_ccd_steps(c, coupled ? 1 : 0, c->s_selfstep.p));
   } else {
@@ -376,7 +414,8 @@ static int iterate_launch(tob_ctx* c, int mode, bool deferred) {
   int wolfe_idx = -1;
   ls_policy(c, rb, re, coupled);
   if (coupled) {
-    if (U == 1) { double one = 1.0; TOB_TRY(upload(c, c->s_selfstep, &one, 1)); }
+    if (U == 1) { TOB_CUDA(c, cudaMemcpyAsync(c->s_selfstep.p, c->d_steps.p, sizeof(double), cudaMemcpyDeviceToDevice, st)); }   // 0.8^0 = 1
+    if (shard) TOB_TRY(exchange_robots(c, c->kmax.p, 1, sizeof(int)));   // shared step = min over ALL robots' position steps
     k_ls_init_coupled<<<1, 32, 0, st>>>(c->n_robots(), c->kmax.p, c->d_steps.p, c->s_selfstep.p, c->s_ptime.p, c->s_tdir.p, c->s_step.p,
                                         c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p, c->ls_rounds);
     TOB_LAUNCH_CHECK(c);
@@ -389,13 +428,9 @@ static int iterate_launch(tob_ctx* c, int mode, bool deferred) {
     wolfe_idx = U > 1 ? U - 1 : -1;
   }
   TOB_TRY(ls_launch_ahead(c, rb, re, wolfe_idx, coupled));
-  if (!deferred) {
-    TOB_TRY(sync_counts(c));
-    TOB_TRY(ls_finish(c, rb, re, wolfe_idx, coupled));
-  }
-  // (5) step, slack + dual
-  TOB_TRY(apply_step(c, rb, re, deferred));
-  TOB_TRY(slack_update(c, rb, re, deferred ? 1 : 0));
+  // (5) step, slack + dual: guarded on the device (see iterate_once)
+  TOB_TRY(apply_step(c, rb, re, true, coupled));
+  TOB_TRY(slack_update(c, rb, re, 1));
   return 0;
 }
 
@@ -407,8 +442,10 @@ static void graph_drop(tob_ctx* c) {
 
 // Launch one deferred iteration: through the captured CUDA graph when the buffers have not moved since the capture.
 static int iterate_submit(tob_ctx* c, int mode) {
-  const bool can_graph = c->use_graph && !c->prof_on && !c->ag && (mode == 0 || mode == 2);
-  if (!can_graph) return iterate_launch(c, mode, true);
+  // NCCL calls are captured like kernels; the legacy callback exchange (a host function enqueuing work through another
+  // library) and the per-launch profiling events are not
+  const bool can_graph = c->use_graph && !c->prof_on && !c->ag && (mode == 0 || mode == 2 || (mode == 1 && c->n_robots() > 1));
+  if (!can_graph) return iterate_launch(c, mode);
   if (c->graph_exec && (c->graph_gen != alloc_generation() || c->graph_mode != mode)) graph_drop(c);
   if (!c->graph_exec) {
     // capture only a launch sequence that a plain run has already executed without allocating
@@ -416,7 +453,7 @@ static int iterate_submit(tob_ctx* c, int mode) {
     TOB_TRY(ensure_iter_buffers(c));
     if (gen0 != alloc_generation() || c->graph_warm_gen != gen0) {
       c->graph_warm_gen = alloc_generation();
-      TOB_TRY(iterate_launch(c, mode, true));
+      TOB_TRY(iterate_launch(c, mode));
       if (c->graph_warm_gen != alloc_generation()) c->graph_warm_gen = ~0ull;   // allocated on the way: warm up again
       return 0;
     }
@@ -424,7 +461,7 @@ static int iterate_submit(tob_ctx* c, int mode) {
     const uint64_t l0 = c->ctr.kernel_launches;
     TOB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     c->capturing = true;
-    int rc = iterate_launch(c, mode, true);
+    int rc = iterate_launch(c, mode);
     c->capturing = false;
     cudaError_t e = cudaStreamEndCapture(c->stream, &g);
     c->graph_nodes = c->ctr.kernel_launches - l0;
@@ -433,11 +470,11 @@ static int iterate_submit(tob_ctx* c, int mode) {
       if (g) cudaGraphDestroy(g);
       cudaGetLastError();
       c->use_graph = false;                      // fall back to plain stream launches for good
-      return iterate_launch(c, mode, true);
+      return iterate_launch(c, mode);
     }
     e = cudaGraphInstantiate(&c->graph_exec, g, 0);
     cudaGraphDestroy(g);
-    if (e != cudaSuccess) { c->graph_exec = nullptr; c->use_graph = false; cudaGetLastError(); return iterate_launch(c, mode, true); }
+    if (e != cudaSuccess) { c->graph_exec = nullptr; c->use_graph = false; cudaGetLastError(); return iterate_launch(c, mode); }
     c->graph_gen = alloc_generation();
     c->graph_mode = mode;
   }
@@ -453,37 +490,37 @@ static int iterate_once(tob_ctx* c, int mode, double* gnorm_out) {
   const bool coupled = mode == 1;
   if (mode < 0 || mode > 2) return fail_msg(c, "tob_admm_iterate: mode must be 0 (decoupled), 1 (coupled) or 2 (independent problems)");
   if (mode != 2 && !c->cloud_n1.empty() && U > 1) return fail_msg(c, "per-robot clouds (tob_cloud_upload_batch) go with mode 2 (independent problems)");
-  if (coupled && (c->ag || rb != 0 || re != U)) return fail_msg(c, "coupled mode is not sharded: run it on one context holding all robots");
+  if (coupled && c->ag) return fail_msg(c, "coupled mode over several GPUs needs the native NCCL exchange (tob_nccl_init_rank / tob_nccl_attach), not the tob_set_shard callbacks");
+  if (mode == 2 && c->sharded() && (rb != 0 || re != U)) return fail_msg(c, "independent problems (mode 2) are not sharded: give every GPU its own context and problems");
   TOB_TRY(ensure_iter_buffers(c));
   const int wolfe_idx = coupled ? 0 : ((U > 1 && mode != 2) ? U - 1 : -1);
-  if (c->ag) {
-    TOB_TRY(iterate_launch(c, mode, false));
-  } else {
-    for (int attempt = 0;; attempt++) {
-      const uint32_t done0 = c->h_dc->iters_done;
-      TOB_TRY(iterate_submit(c, mode));
-      TOB_CUDA(c, cudaMemcpyAsync(c->h_pinned, c->s_gnorm.p, U * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-      TOB_TRY(sync_counts(c));
-      if (c->h_dc->iters_done != done0) break;                 // committed on the device
-      if (c->h_dc->overflow & TOB_OVF_SELFHITS) return fail_msg(c, "inter-robot CCD: more than 16384 colliding pairs");
-      if (c->h_dc->overflow & (TOB_OVF_CAND | TOB_OVF_LIVE)) {  // nothing was changed: grow and run the iteration again
-        if (attempt >= 8) return fail_msg(c, "candidate buffers keep overflowing");
-        const uint32_t ovf = c->h_dc->overflow;
-        TOB_TRY(clear_overflow(c));
-        if (ovf & TOB_OVF_CAND) TOB_TRY(grow_cand_capacity(c, c->h_dc->n_cand));
-        if (ovf & TOB_OVF_LIVE) TOB_TRY(ensure_live_buffers(c, (uint64_t)c->h_dc->n_live + c->h_dc->n_new + 1));
-        continue;
-      }
-      // a robot needs more than the rungs launched ahead: finish its search from the host, then commit
-      TOB_TRY(ls_finish(c, rb, re, wolfe_idx, coupled));
-      TOB_TRY(apply_step(c, rb, re, false));
-      TOB_TRY(slack_update(c, rb, re, 0));
-      break;
+  for (int attempt = 0;; attempt++) {
+    const uint32_t done0 = c->h_dc->iters_done;
+    TOB_TRY(iterate_submit(c, mode));
+    TOB_CUDA(c, cudaMemcpyAsync(c->h_pinned, c->s_gnorm.p, U * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    TOB_TRY(sync_counts(c));
+    if (c->h_dc->iters_done != done0) break;                 // committed on the device
+    const uint32_t ovf = c->h_dc->overflow;
+    if (ovf & TOB_ERR_SOLVE) {                               // same on every rank of a sharded run
+      TOB_TRY(clear_overflow(c));
+      return fail_msg(c, "Newton matrix is not positive definite (Cholesky pivot or Schur complement <= 0): iteration not committed");
     }
+    if (ovf & (TOB_OVF_CAND | TOB_OVF_LIVE | TOB_OVF_REMOTE)) {   // nothing was changed: grow and run the iteration again
+      if (attempt >= 8) return fail_msg(c, "candidate buffers keep overflowing");
+      TOB_TRY(clear_overflow(c));
+      if (ovf & TOB_OVF_CAND) TOB_TRY(grow_cand_capacity(c, c->h_dc->n_cand));
+      if (ovf & TOB_OVF_LIVE) TOB_TRY(ensure_live_buffers(c, (uint64_t)c->h_dc->n_live + c->h_dc->n_new + 1));
+      continue;
+    }
+    // a robot needs more than the rungs launched ahead: finish its search from the host, then commit.  (Decoupled: the
+    // search is rank-local.  Coupled: every rank holds the same energies and takes the same decisions, exchanges matched.)
+    TOB_TRY(ls_finish(c, rb, re, wolfe_idx, coupled));
+    TOB_TRY(apply_step(c, rb, re, false, coupled));
+    TOB_TRY(slack_update(c, rb, re, 0));
+    break;
   }
   // gnorm global of the reference
   if (gnorm_out) {
-    if (c->ag) TOB_TRY(read_back(c, c->s_gnorm.p, U * sizeof(double)));
     double g = 0;
     const double* hp = c->h_pinned;
     if (U == 1) g = hp[0];
@@ -514,6 +551,7 @@ int tob_ctx_create(int device, tob_ctx** out) {
   c->sm_count = prop.multiProcessorCount; c->cc_major = prop.major; c->cc_minor = prop.minor;
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return fail(nullptr, "cudaStreamCreate", e, __FILE__, __LINE__); }
   if ((e = cudaMallocHost((void**)&c->h_pinned, 65536)) != cudaSuccess) { delete c; return fail(nullptr, "cudaMallocHost", e, __FILE__, __LINE__); }
+  c->h_pinned_bytes = 65536;
   if ((e = c->red.ensure(4096)) != cudaSuccess) { delete c; return fail(nullptr, "cudaMalloc", e, __FILE__, __LINE__); }
   if ((e = cudaMallocHost((void**)&c->h_dc, sizeof(DevCounts))) != cudaSuccess) { delete c; return fail(nullptr, "cudaMallocHost", e, __FILE__, __LINE__); }
   memset(c->h_dc, 0, sizeof(DevCounts));
@@ -533,16 +571,8 @@ int tob_ctx_create(int device, tob_ctx** out) {
 void tob_ctx_destroy(tob_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
-  // DBuf members are plain pointers: release the big ones explicitly
-  c->px.release(); c->py.release(); c->pz.release(); c->pid.release(); c->lvl_store.release();
-  c->cand_pt.release(); c->cand_row.release(); c->cpl.release(); c->pl.release(); c->task_cnt.release(); c->task_off.release();
-  if (c->h_pinned) cudaFreeHost(c->h_pinned);
-  if (c->h_dc) cudaFreeHost(c->h_dc);
-  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
-  c->dc.release();
-  cudaStreamDestroy(c->stream);
-  delete c;
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  delete c;   // ~tob_ctx: graph, events, pinned areas, stream; every DBuf frees its own allocation
 }
 
 const char* tob_last_error(const tob_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
@@ -567,6 +597,10 @@ int tob_set_params(tob_ctx* c, const tob_params* p) {
   c->have_tables = false;
   c->states_valid = false;
   c->own_begin = 0; c->own_end = p->uav_num;
+  if (c->nccl_comm) {
+    if (c->comm_world > p->uav_num) return fail_msg(c, "tob_set_params: fewer robots than ranks of the attached communicator");
+    shard_partition(c);
+  } else { c->ag = nullptr; c->ar = nullptr; c->comm_rank = 0; c->comm_world = 1; }
   c->n_planes = 0;
   if (!c->cloud_n1.empty()) {      // per-robot clouds are tied to the row layout: upload them again
     c->cloud_n1.clear(); c->cloud_l1.clear(); c->h_row_task.clear();
@@ -695,6 +729,13 @@ int tob_box_query(tob_ctx* c, const double* lo, const double* hi, double d, uint
   for (uint64_t i = 0; i < t; i++) ids[i] = c->h_pid[pts[i]];
   std::sort(ids, ids + t);
   return 0;
+}
+
+int tob_edge_validity_batch(tob_ctx* c, const double* edges, int n, double d, uint8_t* valid) {
+  TOB_TRY(need(c, true, true));
+  cudaSetDevice(c->device);
+  if (!edges || !valid) return fail_msg(c, "tob_edge_validity_batch: null argument");
+  return edge_validity(c, edges, n, d, valid);
 }
 
 }  // extern "C"
@@ -1383,6 +1424,10 @@ int tob_get_counters(const tob_ctx* cc, tob_counters* out) {
   out->barrier_terms = c->h_dc->barrier_terms;
   out->live_planes = c->h_dc->n_live;
   out->refine_capped = c->h_dc->opt_capped;
+  out->np_kdop_groups = c->h_dc->np_kdop_groups;
+  out->np_gjk_iters = c->h_dc->np_gjk_iters;
+  out->ccd_gjk_iters = c->h_dc->ccd_gjk_iters;
+  out->ccd_kdop_pass = c->h_dc->ccd_kdop_pass;
   return 0;
 }
 int tob_reset_counters(tob_ctx* c) {
@@ -1390,6 +1435,7 @@ int tob_reset_counters(tob_ctx* c) {
   cudaSetDevice(c->device);
   memset(&c->ctr, 0, sizeof(c->ctr));
   TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->dcd_candidates, 0, 5 * sizeof(unsigned long long), c->stream));
+  TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->np_kdop_groups, 0, 4 * sizeof(unsigned long long), c->stream));
   return 0;
 }
 
@@ -1422,11 +1468,23 @@ int tob_profile_read(tob_ctx* c, int kid, double* ms_total, uint64_t* launches, 
 int tob_set_shard(tob_ctx* c, int first, int count, int n_total, tob_allgather_fn ag, tob_allreduce_fn ar, void* user) {
   TOB_TRY(need(c, false, false));
   if (n_total != c->n_robots() || first < 0 || count < 1 || first + count > n_total) return fail_msg(c, "tob_set_shard: bad range");
+  if (c->nccl_comm) return fail_msg(c, "tob_set_shard: a NCCL communicator is attached (tob_nccl_detach first)");
+  if (ag && (n_total % count || first % count)) return fail_msg(c, "tob_set_shard: the callback exchange needs equal blocks (n_total divisible by count)");
   c->own_begin = first; c->own_end = first + count; c->ag = ag; c->ar = ar; c->cb_user = user;
+  c->comm_world = ag ? n_total / count : 1; c->comm_rank = ag ? first / count : 0;
+  TOB_CUDA(c, c->ovf_all.ensure((size_t)c->comm_world + 1));
+  graph_drop(c);
   return 0;
 }
 
 void* tob_stream(tob_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int tob_build_stats(const tob_ctx* c, double* ms, uint64_t* points) {
+  if (!c) return 1;
+  if (ms) *ms = c->build_ms;
+  if (points) *points = c->build_points;
+  return 0;
+}
 
 // ---- FP64 pipe peak ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_dfma(double* out, int iters) {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -12,19 +13,30 @@
 #define TOB_LS_TRIALS 9      // line-search trial points per launch: index 0 = current point, 1..8 = ladder rungs
 #define TOB_LADDER 400       // longest 0.8^k ladder the CCD kernels will walk
 
+struct tob_ctx;
+
 namespace tob {
 
 // bumped whenever a device buffer is (re)allocated: a captured CUDA graph holds raw pointers and must be rebuilt
-inline unsigned long long& alloc_generation() {
-  static unsigned long long g = 0;
+inline std::atomic<unsigned long long>& alloc_generation() {   // process-wide: contexts of several host threads share it
+  static std::atomic<unsigned long long> g{0};
   return g;
 }
 
-// growable device buffer (contents are NOT preserved on growth)
+// growable device buffer (contents are NOT preserved on growth); owns its allocation (move-only)
 template <typename T>
 struct DBuf {
   T* p = nullptr;
   size_t cap = 0;
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  DBuf(DBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+  DBuf& operator=(DBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; }
+    return *this;
+  }
+  ~DBuf() { release(); }
   cudaError_t ensure(size_t n) {
     if (n <= cap && p) return cudaSuccess;
     size_t want = n + n / 4 + 256;
@@ -42,8 +54,9 @@ struct DBuf {
 // their trip counts from here, buffers have a fixed capacity, and an overflow / an unfinished line search turns the
 // state-changing kernels at the end of the iteration into no-ops; the host looks at this struct ONCE per iteration.
 #define TOB_OVF_CAND 1u      // broadphase produced more candidates than cand_cap
-#define TOB_OVF_SELFHITS 4u  // inter-robot CCD hit list overflow
 #define TOB_OVF_LIVE 8u      // persistent-plane mode: live planes + new planes exceed live_cap
+#define TOB_OVF_REMOTE 16u   // sharded: another rank overflowed (every rank repeats the iteration, only the flagged ones grow)
+#define TOB_ERR_SOLVE 32u    // Newton system not positive definite (Cholesky pivot / Schur complement <= 0): nothing is committed
 #define TOB_LS_MAXROUNDS 8   // most Armijo rounds launched ahead of the host (the count is a run-time choice, see ls_policy)
 struct DevCounts {
   uint32_t n_cand;           // candidates of the last broadphase fill (may exceed the capacity -> overflow)
@@ -60,6 +73,11 @@ struct DevCounts {
   uint32_t n_live_next;      // n_live + new planes of this pass (written by the merge, consumed by the refinement)
   uint32_t n_new;            // planes accepted for pairs that were not live yet
   uint32_t opt_capped;       // plane refinements that hit a loop cap (the reference's loops are unbounded)
+  // counted work of the narrowphase / CCD kernels (cumulative since reset; bench.py turns them into algorithmic flops)
+  unsigned long long np_kdop_groups;   // 7-axis groups of the 49-DOP gate really evaluated by k_narrow
+  unsigned long long np_gjk_iters;     // GJK(6,1) rounds (support + sub-algorithm) run by k_narrow
+  unsigned long long ccd_gjk_iters;    // GJK(12,1) rounds run by the CCD ladder of k_bp_ccd
+  unsigned long long ccd_kdop_pass;    // swept candidates that passed the swept 49-DOP gate (each runs >= 1 ladder rung)
 };
 
 // per-row (robot x sub-segment) geometry produced by segments.cu, indexed by GLOBAL row = robot*n_tr + tr
@@ -76,6 +94,8 @@ struct Level {         // one level of the 32-wide LBVH, SoA boxes
   double* lo[3] = {nullptr, nullptr, nullptr};
   double* hi[3] = {nullptr, nullptr, nullptr};
 };
+
+void comm_release(tob_ctx* c);   // comm.cu: destroys an owned NCCL communicator
 
 }  // namespace tob
 
@@ -109,9 +129,17 @@ struct tob_ctx {
 
   // robot states on device; all arrays hold prm.uav_num robots.  Owned robots = [own_begin, own_end)
   int own_begin = 0, own_end = 0;
-  tob_allgather_fn ag = nullptr;
+  tob_allgather_fn ag = nullptr;      // legacy exchange through host callbacks (tob_set_shard); FP64 payloads only
   tob_allreduce_fn ar = nullptr;
   void* cb_user = nullptr;
+  // native NCCL exchange (comm.cu): communicator over the ranks that share the robots of this context
+  void* nccl_comm = nullptr;          // ncclComm_t
+  bool nccl_owned = false;
+  int comm_rank = 0, comm_world = 1;
+  std::vector<int> shard_first, shard_count;   // robot range of every rank (block partition)
+  tob::DBuf<double> ovf_all;          // one word per rank: its overflow / error bits of the current iteration
+  tob::DBuf<double> cpl_part, cpl_zy; // coupled solve: 7 Schur sums per robot (exchanged) / z, y of the owned robots
+  bool sharded() const { return ag != nullptr || nccl_comm != nullptr; }
   bool states_valid = false;
   tob::DBuf<double> s_spline, s_ptime, s_pslack, s_tslack, s_plambda, s_tlambda;
   tob::DBuf<double> s_dir, s_tdir, s_wolfe, s_gnorm;
@@ -152,7 +180,7 @@ struct tob_ctx {
   // inter-robot scratch
   tob::DBuf<double> self_pl;          // n_tr x npairs x 4
   tob::DBuf<uint32_t> self_ok;        // n_tr x npairs
-  tob::DBuf<uint32_t> self_hits;      // inter-robot CCD: appended list of colliding (slot, pair) ids + count + overflow flag
+  tob::DBuf<uint32_t> self_hits;      // inter-robot CCD: colliding (slot, pair) ids [cap] + count [2] + the sorted list [cap]; cap = all tasks
 
   // energy / gradient / solve scratch
   tob::DBuf<double> row_e;
@@ -166,9 +194,13 @@ struct tob_ctx {
   tob::DBuf<double> scratch, scratch2;
   tob::DBuf<uint8_t> scratch8;
 
-  double* h_pinned = nullptr;         // small pinned read-back area (64 KiB)
+  double* h_pinned = nullptr;         // pinned read-back area (>= 64 KiB, grown with uav_num: holds one double per robot)
+  size_t h_pinned_bytes = 0;
   double* h_stage = nullptr;          // pinned staging for packed state transfers
   size_t h_stage_cap = 0;
+  // LBVH build: device time and points of the last tob_cloud_upload[_batch] (roofline entry of the build, 128 B / point)
+  double build_ms = 0;
+  uint64_t build_points = 0;
 
   tob_counters ctr{};
   bool bcr_attr_set = false;          // cudaFuncSetAttribute(k_solve_bcr) done on this device
@@ -197,6 +229,19 @@ struct tob_ctx {
 
   // persistent OBSTACLE planes exist only on the single-UAV path (Optimization3D_admm::separate_plane :126-193; the multi-UAV
   // separate_plane, Optimization3D_multi.h:176-235, has no such branch): one robot, or independent problems
+  tob_ctx() = default;
+  tob_ctx(const tob_ctx&) = delete;
+  tob_ctx& operator=(const tob_ctx&) = delete;
+  ~tob_ctx() {                        // device buffers release themselves (DBuf); the rest is owned here
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    tob::comm_release(this);
+    for (auto& r : prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : prof_pool) cudaEventDestroy(e);
+    if (h_pinned) cudaFreeHost(h_pinned);
+    if (h_stage) cudaFreeHost(h_stage);
+    if (h_dc) cudaFreeHost(h_dc);
+    if (stream) cudaStreamDestroy(stream);
+  }
   bool live_planes() const { return prm.optimal_plane != 0 && (prm.uav_num == 1 || !cloud_n1.empty()); }
   int n_robots() const { return prm.uav_num; }
   int rows_all() const { return prm.uav_num * n_tr; }
@@ -286,6 +331,7 @@ int pack_self_only(tob_ctx* c);
 int ensure_live_buffers(tob_ctx* c, uint64_t need);     // persistent-plane set: grows preserving the live planes
 int reset_live_planes(tob_ctx* c);
 int self_ccd_steps(tob_ctx* c, int coupled, double* steps_dev);
+int edge_validity(tob_ctx* c, const double* edges_host, int n, double d, uint8_t* valid_host);
 // barrier.cu
 int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* tstep, const double* ttime, int KT, int k0,
                   int k1, double* e_dev);
@@ -294,6 +340,12 @@ int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* t
 int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int kte, int slot);
 int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd);
 int row_blocks(tob_ctx* c, int tr, int which, double* out_dev);
+// comm.cu: in-place exchange of robot-indexed device arrays between the ranks (no-op when the context is not sharded)
+int exchange_robots(tob_ctx* c, void* buf, size_t elems_per_robot, size_t elem_size);
+int exchange_ranks(tob_ctx* c, double* buf);    // one FP64 word per rank
+int exchange_group_begin(tob_ctx* c);
+int exchange_group_end(tob_ctx* c);
+void shard_partition(tob_ctx* c);
 // solve.cu
 int solve_directions(tob_ctx* c, int rb, int re, int dense_shift);
 int solve_coupled(tob_ctx* c);

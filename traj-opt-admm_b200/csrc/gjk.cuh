@@ -412,7 +412,7 @@ TOB_HD void support_max(const double (*pts)[3], double* cur, const double* dir) 
 
 // witness vector (closest point of the Minkowski difference A-B to the origin)
 template <int NA, int NB>
-TOB_HD void gjk_witness(const double (*A)[3], const double (*B)[3], double* vout) {
+TOB_HD void gjk_witness(const double (*A)[3], const double (*B)[3], double* vout, unsigned* iters = nullptr) {
   Simplex s;
   s.lam[0] = s.lam[1] = s.lam[2] = s.lam[3] = 0;
   s.wid[0] = s.wid[1] = s.wid[2] = s.wid[3] = 0;
@@ -454,6 +454,7 @@ TOB_HD void gjk_witness(const double (*A)[3], const double (*B)[3], double* vout
     if (nrm2(v) <= (eps_tot * eps_tot * wmax)) break;
   } while ((s.n != 4) && (k != 50));
   vout[0] = v[0]; vout[1] = v[1]; vout[2] = v[2];
+  if (iters) *iters += (unsigned)k;   // work counter (bench.py roofline): support + sub-algorithm rounds really executed
 }
 
 // runtime-sized variants (function-level entry points CCD::GJKDCD with edges / arbitrary vertex counts, CCD.h:17-114)
@@ -550,9 +551,11 @@ TOB_HD void kdop_extents(const double (*pts)[3], const double* kdop, double* lo,
 // and the 7 level computations are independent instruction streams (an FP64 result takes ~40 cycles on B200: one axis at
 // a time is a ~200-cycle dependent chain per axis, ~10 k cycles for a candidate that passes).  Same comparisons, same
 // decision as the axis-by-axis loop of the reference (CCD.h:376-389).
-TOB_HD bool kdop_point_overlap(const double* lo, const double* hi, const double* kdop, const double* q, double d) {
+TOB_HD bool kdop_point_overlap(const double* lo, const double* hi, const double* kdop, const double* q, double d,
+                               unsigned* groups = nullptr) {
   for (int g = 0; g < TOB_KDOP_AXES; g += 7) {
     bool sep = false;
+    if (groups) ++*groups;            // work counter (bench.py roofline): 7-axis groups really evaluated
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
       const int k = g + j;
@@ -616,9 +619,10 @@ TOB_HD void swept_points(const double (*P)[3], const double (*D)[3], double t0, 
 TOB_HD double eig_norm3(const double* c) { return sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]); }
 
 // segment (6 pts) vs obstacle point: plane n.x + d >= 0 (Separate.h:18-163)
-TOB_HD bool plane_point(const double (*P)[3], const double* q, double distance, double offset, double* c, double* d) {
+TOB_HD bool plane_point(const double (*P)[3], const double* q, double distance, double offset, double* c, double* d,
+                        unsigned* gjk_iters = nullptr) {
   double Bq[1][3] = {{q[0], q[1], q[2]}};
-  gjk_witness<6, 1>(P, Bq, c);
+  gjk_witness<6, 1>(P, Bq, c, gjk_iters);
   double cn = eig_norm3(c);
   if (cn > distance) return false;
   c[0] /= cn; c[1] /= cn; c[2] /= cn;

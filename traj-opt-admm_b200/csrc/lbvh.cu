@@ -16,6 +16,8 @@
 // candidate order (row, Morton position) without atomics; sizes stay on the device (DevCounts), nothing is read back.
 //
 // Algorithmic bytes: build 128 B/point; query 48 B/row + 16 B/(row x L1 node) + 28 B/candidate.
+#include <string.h>
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "ctx.cuh"
@@ -61,10 +63,25 @@ __device__ __forceinline__ uint64_t spread21(uint64_t x) {
   return x;
 }
 
-__global__ void k_morton(const double* __restrict__ V, uint32_t n, double lx, double ly, double lz, double sx, double sy,
-                         double sz, uint64_t* __restrict__ key, uint32_t* __restrict__ idx) {
+// second stage of the cloud bounds: folds the per-CTA partials; bnd = lo[3] | scale[3] (quantisation to 21 bits per axis)
+__global__ void k_minmax_final(const double* __restrict__ part, int nb, double* __restrict__ bnd) {
+  const int a = threadIdx.x;
+  if (a >= 3) return;
+  double lo = INFINITY, hi = -INFINITY;
+  for (int b = 0; b < nb; b++) {
+    lo = fmin(lo, part[b * 6 + a]);
+    hi = fmax(hi, part[b * 6 + 3 + a]);
+  }
+  const double ext = hi - lo;
+  bnd[a] = lo;
+  bnd[3 + a] = ext > 0 ? 2097151.0 / ext : 0.0;
+}
+
+__global__ void k_morton(const double* __restrict__ V, uint32_t n, const double* __restrict__ bnd, uint64_t* __restrict__ key,
+                         uint32_t* __restrict__ idx) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const double lx = bnd[0], ly = bnd[1], lz = bnd[2], sx = bnd[3], sy = bnd[4], sz = bnd[5];
   double x = (V[i] - lx) * sx, y = (V[(size_t)n + i] - ly) * sy, z = (V[(size_t)2 * n + i] - lz) * sz;
   uint64_t qx = (uint64_t)fmin(fmax(x, 0.0), 2097151.0);
   uint64_t qy = (uint64_t)fmin(fmax(y, 0.0), 2097151.0);
@@ -113,47 +130,63 @@ __global__ void k_level(int from_points, uint32_t n_child, uint32_t n_parent_pad
   }
 }
 
-// Morton-sort one cloud into the concatenated SoA arrays at point offset `base` (a multiple of 1024); `slot` points are
-// reserved for it (padding = +inf points that can never be candidates).
-static int lbvh_sort_cloud(tob_ctx* c, const double* V_host, uint32_t n, size_t base, uint32_t slot) {
+// Morton-sort the clouds into the concatenated SoA arrays: cloud b goes to point offset base[b] and owns slot[b] points
+// (padding = +inf points that can never be candidates).  One workspace sized for the largest cloud serves all of them and
+// nothing is read back per cloud: the bounds stay on the device, the host only refills one of two pinned staging buffers
+// while the stream sorts the previous cloud.
+static int lbvh_sort_clouds(tob_ctx* c, const double* const* V_host, const uint32_t* n, const size_t* base, const uint32_t* slot,
+                            int n_clouds) {
   cudaStream_t st = c->stream;
-  DBuf<double> V;
+  uint32_t nmax = 0;
+  for (int b = 0; b < n_clouds; b++) nmax = n[b] > nmax ? n[b] : nmax;
+  const int NB = 296;
+  DBuf<double> V, part, bnd;
   DBuf<uint64_t> key, key2;
   DBuf<uint32_t> idx, idx2;
-  DBuf<double> part;
   DBuf<uint8_t> tmp;
-  TOB_CUDA(c, V.ensure((size_t)3 * n));
-  TOB_CUDA(c, cudaMemcpyAsync(V.p, V_host, (size_t)3 * n * sizeof(double), cudaMemcpyHostToDevice, st));
-  const int nb = n < 65536 ? 32 : 296;
-  TOB_CUDA(c, part.ensure(nb * 6));
-  k_minmax<<<nb, 256, 0, st>>>(V.p, n, part.p);
-  TOB_LAUNCH_CHECK(c);
-  std::vector<double> hp(nb * 6);
-  TOB_CUDA(c, cudaMemcpyAsync(hp.data(), part.p, nb * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  TOB_CUDA(c, cudaStreamSynchronize(st));
-  double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  for (int b = 0; b < nb; b++)
-    for (int a = 0; a < 3; a++) {
-      lo[a] = fmin(lo[a], hp[b * 6 + a]);
-      hi[a] = fmax(hi[a], hp[b * 6 + 3 + a]);
-    }
-  double sc[3];
-  for (int a = 0; a < 3; a++) {
-    double ext = hi[a] - lo[a];
-    sc[a] = ext > 0 ? 2097151.0 / ext : 0.0;
-  }
-  TOB_CUDA(c, key.ensure(n)); TOB_CUDA(c, key2.ensure(n));
-  TOB_CUDA(c, idx.ensure(n)); TOB_CUDA(c, idx2.ensure(n));
-  k_morton<<<div_up(n, 256), 256, 0, st>>>(V.p, n, lo[0], lo[1], lo[2], sc[0], sc[1], sc[2], key.p, idx.p);
-  TOB_LAUNCH_CHECK(c);
+  TOB_CUDA(c, V.ensure((size_t)3 * nmax)); TOB_CUDA(c, part.ensure(NB * 6)); TOB_CUDA(c, bnd.ensure(8));
+  TOB_CUDA(c, key.ensure(nmax)); TOB_CUDA(c, key2.ensure(nmax)); TOB_CUDA(c, idx.ensure(nmax)); TOB_CUDA(c, idx2.ensure(nmax));
   size_t tmp_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key.p, key2.p, idx.p, idx2.p, (int)n, 0, 63, st);
+  TOB_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key.p, key2.p, idx.p, idx2.p, (int)nmax, 0, 63, st));
   TOB_CUDA(c, tmp.ensure(tmp_bytes));
-  TOB_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key.p, key2.p, idx.p, idx2.p, (int)n, 0, 63, st));
-  k_gather<<<div_up(slot, 256), 256, 0, st>>>(V.p, n, slot, idx2.p, c->px.p + base, c->py.p + base, c->pz.p + base, c->pid.p + base);
-  TOB_LAUNCH_CHECK(c);
-  TOB_CUDA(c, cudaStreamSynchronize(st));
-  V.release(); key.release(); key2.release(); idx.release(); idx2.release(); part.release(); tmp.release();
+  struct Pinned {
+    double* p[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    ~Pinned() { for (int i = 0; i < 2; i++) { if (p[i]) cudaFreeHost(p[i]); if (ev[i]) cudaEventDestroy(ev[i]); } }
+  } pin;
+  for (int i = 0; i < 2; i++) {
+    TOB_CUDA(c, cudaMallocHost((void**)&pin.p[i], (size_t)3 * nmax * sizeof(double)));
+    TOB_CUDA(c, cudaEventCreateWithFlags(&pin.ev[i], cudaEventDisableTiming));
+  }
+  cudaEvent_t t0, t1;
+  TOB_CUDA(c, cudaEventCreate(&t0)); TOB_CUDA(c, cudaEventCreate(&t1));
+  TOB_CUDA(c, cudaEventRecord(t0, st));
+  for (int b = 0; b < n_clouds; b++) {
+    const int q = b & 1;
+    const uint32_t nb = n[b];
+    if (b >= 2) TOB_CUDA(c, cudaEventSynchronize(pin.ev[q]));          // the copy out of this staging buffer has finished
+    memcpy(pin.p[q], V_host[b], (size_t)3 * nb * sizeof(double));
+    TOB_CUDA(c, cudaMemcpyAsync(V.p, pin.p[q], (size_t)3 * nb * sizeof(double), cudaMemcpyHostToDevice, st));
+    TOB_CUDA(c, cudaEventRecord(pin.ev[q], st));
+    const int blocks = nb < 65536 ? 32 : NB;
+    k_minmax<<<blocks, 256, 0, st>>>(V.p, nb, part.p);
+    TOB_LAUNCH_CHECK(c);
+    k_minmax_final<<<1, 32, 0, st>>>(part.p, blocks, bnd.p);
+    TOB_LAUNCH_CHECK(c);
+    k_morton<<<div_up(nb, 256), 256, 0, st>>>(V.p, nb, bnd.p, key.p, idx.p);
+    TOB_LAUNCH_CHECK(c);
+    TOB_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key.p, key2.p, idx.p, idx2.p, (int)nb, 0, 63, st));
+    k_gather<<<div_up(slot[b], 256), 256, 0, st>>>(V.p, nb, slot[b], idx2.p, c->px.p + base[b], c->py.p + base[b], c->pz.p + base[b],
+                                                  c->pid.p + base[b]);
+    TOB_LAUNCH_CHECK(c);
+  }
+  TOB_CUDA(c, cudaEventRecord(t1, st));
+  cudaError_t e = cudaStreamSynchronize(st);
+  float ms = 0;
+  if (e == cudaSuccess) cudaEventElapsedTime(&ms, t0, t1);
+  cudaEventDestroy(t0); cudaEventDestroy(t1);
+  TOB_CUDA(c, e);
+  c->build_ms = ms;
   return 0;
 }
 
@@ -203,9 +236,10 @@ int lbvh_build(tob_ctx* c, const double* V_host, uint32_t n) {
   uint32_t n_pad = (n + 31u) & ~31u;
   TOB_CUDA(c, c->px.ensure(n_pad)); TOB_CUDA(c, c->py.ensure(n_pad)); TOB_CUDA(c, c->pz.ensure(n_pad));
   TOB_CUDA(c, c->pid.ensure(n_pad));
-  TOB_TRY(lbvh_sort_cloud(c, V_host, n, 0, n_pad));
+  const size_t base0 = 0;
+  TOB_TRY(lbvh_sort_clouds(c, &V_host, &n, &base0, &n_pad, 1));
   TOB_TRY(lbvh_levels(c, n_pad));
-  c->n_pts = n; c->n_pad = n_pad;
+  c->n_pts = n; c->n_pad = n_pad; c->build_points = n;
   c->cloud_n1.clear(); c->cloud_l1.clear();
   c->row_task.release(); c->row_l1.release();
   return 0;
@@ -228,8 +262,10 @@ int lbvh_build_batch(tob_ctx* c, const double* const* V_host, const uint32_t* n,
   if (total > 0xfff00000ull) return fail_msg(c, "tob_cloud_upload_batch: more than 2^32 points");
   TOB_CUDA(c, c->px.ensure(total)); TOB_CUDA(c, c->py.ensure(total)); TOB_CUDA(c, c->pz.ensure(total));
   TOB_CUDA(c, c->pid.ensure(total));
-  for (int b = 0; b < n_clouds; b++) TOB_TRY(lbvh_sort_cloud(c, V_host[b], n[b], base[b], slot[b]));
+  TOB_TRY(lbvh_sort_clouds(c, V_host, n, base.data(), slot.data(), n_clouds));
   TOB_TRY(lbvh_levels(c, total));
+  c->build_points = 0;
+  for (int b = 0; b < n_clouds; b++) c->build_points += n[b];
   c->n_pts = (uint32_t)total; c->n_pad = (uint32_t)total;
   c->cloud_n1.resize(n_clouds); c->cloud_l1.resize(n_clouds);
   for (int b = 0; b < n_clouds; b++) { c->cloud_l1[b] = (uint32_t)(base[b] / 1024); c->cloud_n1[b] = slot[b] / 1024; }

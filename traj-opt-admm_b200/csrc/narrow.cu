@@ -11,6 +11,10 @@
 //     of pairs that were not live yet and refined in place every iteration by Optimal_plane::optimal_cd
 //     (Optimization3D_admm.h:126-193); inter-robot planes kept per (slot, pair) and refined by self_optimal_cd
 //     (Optimization3D_multi.h:271-339).
+#include <algorithm>
+#include <utility>
+#include <vector>
+
 #include "ctx.cuh"
 #include "bp.cuh"
 #define TOB_GJK_INLINE
@@ -32,7 +36,7 @@ __device__ __forceinline__ void load_pts6(const double* __restrict__ src, double
 // for the survivors, so the expensive divergent part executes on dense warps instead of on ~30 % of the lanes.
 // Per chunk the number of accepted planes goes to csum[chunk]; k_np_top scans it and k_pack scatters.
 struct NarrowArgs {
-  const DevCounts* dc;
+  DevCounts* dc;
   uint32_t cap;
   const uint32_t *cand_pt, *cand_row;
   const double *px, *py, *pz;
@@ -79,6 +83,7 @@ __global__ void __launch_bounds__(NP_THREADS, 4) k_narrow(NarrowArgs a) {
   const uint32_t n_chunks = (n + chunk_sz - 1) / chunk_sz;
   const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t n_live = a.live_key ? a.dc->n_live : 0u;
+  unsigned w_groups = 0, w_iters = 0;   // counted work of this thread
   __syncthreads();
   for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     uint32_t n_surv = 0;   // uniform
@@ -103,7 +108,8 @@ __global__ void __launch_bounds__(NP_THREADS, 4) k_narrow(NarrowArgs a) {
       bool pass = false;
       if (i < n) {
         const uint32_t row = c_row[q];
-        pass = kdop_point_overlap(a.klo + (size_t)TOB_KDOP_AXES * row, a.khi + (size_t)TOB_KDOP_AXES * row, s_kdop, c_pt[q], a.dist);
+        pass = kdop_point_overlap(a.klo + (size_t)TOB_KDOP_AXES * row, a.khi + (size_t)TOB_KDOP_AXES * row, s_kdop, c_pt[q], a.dist,
+                                  &w_groups);
         a.cflag[i] = 0;
       }
       const uint32_t bm = __ballot_sync(0xffffffffu, pass);
@@ -132,7 +138,7 @@ __global__ void __launch_bounds__(NP_THREADS, 4) k_narrow(NarrowArgs a) {
       const double pt[3] = {a.px[p], a.py[p], a.pz[p]};
       double P[6][3], c[3], d;
       load_pts6(a.P + (size_t)18 * row, P);
-      if (plane_point(P, pt, a.dist, a.offset, c, &d)) {
+      if (plane_point(P, pt, a.dist, a.offset, c, &d, &w_iters)) {
         ok++;
         *reinterpret_cast<double4*>(a.cpl + (size_t)4 * ii) = make_double4(c[0], c[1], c[2], d);
         a.cflag[ii] = 1;
@@ -148,6 +154,14 @@ __global__ void __launch_bounds__(NP_THREADS, 4) k_narrow(NarrowArgs a) {
       for (int k = 0; k < NP_THREADS / 32; k++) cnt += s_w[k];
       a.csum[chunk] = cnt;
     }
+  }
+  for (int o = 16; o; o >>= 1) {
+    w_groups += __shfl_xor_sync(0xffffffffu, w_groups, o);
+    w_iters += __shfl_xor_sync(0xffffffffu, w_iters, o);
+  }
+  if (lane == 0 && w_groups) {
+    atomicAdd(&a.dc->np_kdop_groups, (unsigned long long)w_groups);
+    atomicAdd(&a.dc->np_gjk_iters, (unsigned long long)w_iters);
   }
 }
 
@@ -488,8 +502,8 @@ int ensure_live_buffers(tob_ctx* c, uint64_t need) {
     TOB_CUDA(c, cudaMemcpy(nk.p, c->live_key.p, (size_t)n_live * sizeof(unsigned long long), cudaMemcpyDeviceToDevice));
     TOB_CUDA(c, cudaMemcpy(np.p, c->live_pl.p, (size_t)4 * n_live * sizeof(double), cudaMemcpyDeviceToDevice));
   }
-  c->live_key.release(); c->live_pl.release();
-  c->live_key = nk; c->live_pl = np;
+  c->live_key = std::move(nk); c->live_pl = std::move(np);
+  alloc_generation()++;
   TOB_CUDA(c, c->live_key_t.ensure(cap + 1)); TOB_CUDA(c, c->live_pl_t.ensure(4 * cap + 4));
   TOB_CUDA(c, c->new_key.ensure(cap + 1)); TOB_CUDA(c, c->new_pl.ensure(4 * cap + 4));
   c->live_cap = cap;
@@ -686,6 +700,7 @@ __global__ void __launch_bounds__(BP_THREADS, 4) k_bp_ccd(CcdArgs a) {
   const uint32_t n_items = bp_prepare(a.bp, s, &rank);   // contains barriers: s_kdop is visible afterwards
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   uint32_t cnt = 0;
+  unsigned w_iters = 0, w_pass = 0;
   for (uint32_t j = w; j < n_items; j += BP_WARPS) {
     uint32_t h, row, leaf;
     bp_item(a.bp, s, j, &h, &row, &leaf);
@@ -704,10 +719,11 @@ __global__ void __launch_bounds__(BP_THREADS, 4) k_bp_ccd(CcdArgs a) {
     moved_points(P, D, st, A);
     // CCD::KDOPCCD(P, D, q, offset, 0, step)
     if (!kdop_overlap<12, 1>(A, q, s_kdop, a.offset)) continue;
+    w_pass++;
     const double d2 = a.offset * a.offset;
     while (k < TOB_MAX_LADDER) {
       double v[3];
-      gjk_witness<12, 1>(A, q, v);
+      gjk_witness<12, 1>(A, q, v, &w_iters);
       const double dist2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
       if (!(dist2 <= d2)) break;
       k++;
@@ -717,6 +733,12 @@ __global__ void __launch_bounds__(BP_THREADS, 4) k_bp_ccd(CcdArgs a) {
     atomicMax(a.kmax + robot, k);
   }
   if (lane == 0 && cnt) atomicAdd(&a.bp.dc->ccd_candidates, (unsigned long long)cnt);
+  w_iters = __reduce_add_sync(0xffffffffu, w_iters);
+  w_pass = __reduce_add_sync(0xffffffffu, w_pass);
+  if (lane == 0 && w_pass) {
+    atomicAdd(&a.bp.dc->ccd_gjk_iters, (unsigned long long)w_iters);
+    atomicAdd(&a.bp.dc->ccd_kdop_pass, (unsigned long long)w_pass);
+  }
 }
 
 // geo.P / geo.D / geo.box (swept) of robots [rb,re) must be current (compute_rows mode 3, which also zeroes kmax).
@@ -802,48 +824,50 @@ __global__ void __launch_bounds__(64) k_self_ccd_filter(SelfCcdArgs a) {
   }
 }
 
-// phase 2 (one thread, sequential like the reference): resolve the colliding pairs in (slot, pair) order.
-// The list is short (pairs that really collide when both robots take their full Newton step); it is sorted first so
-// the result does not depend on the order the filter threads appended it.
-__global__ void k_self_ccd_resolve(SelfCcdArgs a, double* steps_out, DevCounts* dc) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// phase 2 (one warp; the resolution itself is sequential like the reference): resolve the colliding pairs in (slot, pair)
+// order.  The list is short (pairs that really collide when both robots take their full Newton step) and can never
+// overflow: its capacity is the number of (slot, pair) tasks.  It is sorted first so the result does not depend on the
+// order the filter threads appended it: every lane ranks its elements by counting the smaller ones (ids are unique).
+__global__ void __launch_bounds__(32) k_self_ccd_resolve(SelfCcdArgs a, double* steps_out, uint32_t* sorted) {
+  const uint32_t lane = threadIdx.x;
+  const uint32_t nh = min(a.hit[a.cap], a.cap);
+  for (uint32_t i = lane; i < nh; i += 32) {
+    const uint32_t v = a.hit[i];
+    uint32_t r = 0;
+    for (uint32_t j = 0; j < nh; j++) r += a.hit[j] < v;
+    sorted[r] = v;
+  }
+  __syncwarp();
+  if (lane != 0) return;
   for (int u = 0; u < a.U; u++) steps_out[u] = 1.0;
   int kshared = 0;
-  uint32_t nh = a.hit[a.cap];
-  if (nh > a.cap) { dc->overflow |= TOB_OVF_SELFHITS; nh = a.cap; }
-  for (uint32_t i = 1; i < nh; i++) {          // insertion sort
-    uint32_t v = a.hit[i];
-    int j = (int)i - 1;
-    while (j >= 0 && a.hit[j] > v) { a.hit[j + 1] = a.hit[j]; j--; }
-    a.hit[j + 1] = v;
-  }
   for (uint32_t i = 0; i < nh; i++) {
-    {
-      const int tr = a.hit[i] / a.npairs, pi = a.hit[i] - tr * a.npairs;
-      int p0, p1;
-      pair_from_index(pi, a.U, &p0, &p1);
-      size_t r0 = (size_t)p0 * a.n_tr + tr, r1 = (size_t)p1 * a.n_tr + tr;
-      double P0[6][3], D0[6][3], P1[6][3], D1[6][3], A[12][3], B[12][3];
-      load_pts6(a.P + 18 * r0, P0); load_pts6(a.D + 18 * r0, D0);
-      load_pts6(a.P + 18 * r1, P1); load_pts6(a.D + 18 * r1, D1);
-      double s0 = a.coupled ? a.steps[kshared] : steps_out[p0];
-      double s1 = a.coupled ? a.steps[kshared] : steps_out[p1];
+    const int tr = sorted[i] / a.npairs, pi = sorted[i] - tr * a.npairs;
+    int p0, p1;
+    pair_from_index(pi, a.U, &p0, &p1);
+    size_t r0 = (size_t)p0 * a.n_tr + tr, r1 = (size_t)p1 * a.n_tr + tr;
+    double P0[6][3], D0[6][3], P1[6][3], D1[6][3], A[12][3], B[12][3];
+    load_pts6(a.P + 18 * r0, P0); load_pts6(a.D + 18 * r0, D0);
+    load_pts6(a.P + 18 * r1, P1); load_pts6(a.D + 18 * r1, D1);
+    double s0 = a.coupled ? a.steps[kshared] : steps_out[p0];
+    double s1 = a.coupled ? a.steps[kshared] : steps_out[p1];
+    swept12(P0, D0, 0.0, s0, A);
+    swept12(P1, D1, 0.0, s1, B);
+    if (!kdop_overlap<12, 12>(A, B, a.kdop, a.offset)) continue;
+    int guard = 0;
+    // the ladder table has TOB_LADDER + 2 entries: a shared exponent that reaches TOB_LADDER stays there (0.8^400 ~ 1e-39:
+    // two robots that are already closer than `offset` never separate; the reference would loop forever)
+    while (guard++ < TOB_MAX_LADDER && kshared < TOB_LADDER) {
+      double v[3];
+      gjk_witness<12, 12>(A, B, v);
+      double dist2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+      if (!(dist2 <= a.offset * a.offset)) break;
+      if (a.coupled) { kshared++; s0 = s1 = a.steps[kshared]; }
+      else { s0 *= 0.8; s1 *= 0.8; }
       swept12(P0, D0, 0.0, s0, A);
       swept12(P1, D1, 0.0, s1, B);
-      if (!kdop_overlap<12, 12>(A, B, a.kdop, a.offset)) continue;
-      int guard = 0;
-      while (guard++ < TOB_MAX_LADDER) {
-        double v[3];
-        gjk_witness<12, 12>(A, B, v);
-        double dist2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
-        if (!(dist2 <= a.offset * a.offset)) break;
-        if (a.coupled) { kshared++; s0 = s1 = a.steps[kshared]; }
-        else { s0 *= 0.8; s1 *= 0.8; }
-        swept12(P0, D0, 0.0, s0, A);
-        swept12(P1, D1, 0.0, s1, B);
-      }
-      if (!a.coupled) { steps_out[p0] = s0; steps_out[p1] = s1; }
     }
+    if (!a.coupled) { steps_out[p0] = s0; steps_out[p1] = s1; }
   }
   if (a.coupled) steps_out[0] = a.steps[kshared];
 }
@@ -853,8 +877,8 @@ int self_ccd_steps(tob_ctx* c, int coupled, double* steps_dev) {
   const int U = c->n_robots();
   int npairs = U * (U - 1) / 2;
   size_t n = (size_t)c->n_tr * npairs;
-  const uint32_t cap = 16384;
-  TOB_CUDA(c, c->self_hits.ensure(cap + 2));
+  const uint32_t cap = (uint32_t)(n ? n : 1);   // every task can be listed: the list cannot overflow
+  TOB_CUDA(c, c->self_hits.ensure(2 * (size_t)cap + 2));
   SelfCcdArgs a;
   a.U = U; a.n_tr = c->n_tr; a.npairs = npairs; a.coupled = coupled;
   a.P = c->geo.P.p; a.D = c->geo.D.p; a.kdop = c->d_kdop.p; a.steps = c->d_steps.p; a.offset = c->prm.offset;
@@ -865,9 +889,93 @@ int self_ccd_steps(tob_ctx* c, int coupled, double* steps_dev) {
     k_self_ccd_filter<<<div_up(n, 64), 64, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
-  k_self_ccd_resolve<<<1, 32, 0, c->stream>>>(a, steps_dev, c->dc.p);
+  k_self_ccd_resolve<<<1, 32, 0, c->stream>>>(a, steps_dev, c->self_hits.p + cap + 2);
   TOB_LAUNCH_CHECK(c);
   c->ctr.self_pairs += n;
+  return 0;
+}
+
+// ---- front end: batched edge validity ------------------------------------------------------------------
+// The reference's RRT motion validator (OMPL.cpp:36-96) checks one straight edge at a time: BVH::EdgeCollision (all points
+// within d of the edge's box, BVH.cpp:95-133) and then CCD::GJKDCD(edge, point, d) (CCD.h:17-114) per candidate, invalid at
+// the first collision.  Here many edges are checked in one launch: same walk as the broadphase with one "row" per edge, and
+// every point that passes the leaf predicate runs GJK(2,1) in place; the answer per edge is an OR, so no candidate list.
+struct EdgeArgs {
+  BpArgs bp;
+  const double* E;      // edges x 6: a xyz, b xyz
+  double d;
+  uint32_t* invalid;    // edges: set to 1 when some point is within d of the edge
+};
+
+__global__ void __launch_bounds__(BP_THREADS, 4) k_bp_edge(EdgeArgs a) {
+  __shared__ BpShared s;
+  uint32_t rank;
+  const uint32_t n_items = bp_prepare(a.bp, s, &rank);
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const double d2 = a.d * a.d;
+  for (uint32_t j = w; j < n_items; j += BP_WARPS) {
+    uint32_t h, row, leaf;
+    bp_item(a.bp, s, j, &h, &row, &leaf);
+    double q[1][3];
+    const bool ok = bp_point_test(a.bp, s, h, leaf * 32 + lane, &q[0][0], &q[0][1], &q[0][2]);
+    if (!ok) continue;
+    if (*((volatile uint32_t*)(a.invalid + row))) continue;     // already decided by another point
+    double A[2][3], v[3];
+    const double* e = a.E + (size_t)6 * row;
+    for (int k = 0; k < 3; k++) { A[0][k] = e[k]; A[1][k] = e[3 + k]; }
+    gjk_witness<2, 1>(A, q, v);
+    const double dist2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    if (dist2 <= d2) a.invalid[row] = 1u;
+  }
+}
+
+// edges_host: n x 2 x 3 (edge, endpoint, xyz).  valid_host[i] = 1 when no cloud point is within d of edge i.
+int edge_validity(tob_ctx* c, const double* edges_host, int n, double d, uint8_t* valid_host) {
+  if (c->n_pts == 0) return fail_msg(c, "tob_edge_validity: no point cloud uploaded");
+  if (!c->cloud_n1.empty()) return fail_msg(c, "tob_edge_validity: one shared cloud is required (not per-problem clouds)");
+  if (n <= 0) return 0;
+  cudaStream_t st = c->stream;
+  const uint32_t n1 = c->lvl[1].count;
+  const int chunk_max = (int)std::min<uint64_t>((uint64_t)n, 0x7fffffffull / (n1 ? n1 : 1));
+  if (chunk_max < 1) return fail_msg(c, "tob_edge_validity: cloud too large");
+  std::vector<double> box((size_t)6 * n);
+  for (int i = 0; i < n; i++)
+    for (int k = 0; k < 3; k++) {
+      const double p0 = edges_host[(size_t)6 * i + k], p1 = edges_host[(size_t)6 * i + 3 + k];
+      // BVH.cpp:104-127: running min / max over the two endpoints, starting from +-inf
+      double lo = INFINITY, hi = -INFINITY;
+      if (p0 < lo) lo = p0; if (p0 > hi) hi = p0;
+      if (p1 < lo) lo = p1; if (p1 > hi) hi = p1;
+      box[(size_t)6 * i + k] = lo; box[(size_t)6 * i + 3 + k] = hi;
+    }
+  TOB_CUDA(c, c->scratch.ensure((size_t)12 * n));
+  DBuf<uint32_t> inv;
+  TOB_CUDA(c, inv.ensure(n));
+  TOB_CUDA(c, cudaMemcpyAsync(c->scratch.p, box.data(), (size_t)6 * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  TOB_CUDA(c, cudaMemcpyAsync(c->scratch.p + (size_t)6 * n, edges_host, (size_t)6 * n * sizeof(double), cudaMemcpyHostToDevice, st));
+  TOB_CUDA(c, cudaMemsetAsync(inv.p, 0, (size_t)n * sizeof(uint32_t), st));
+  for (int b0 = 0; b0 < n; b0 += chunk_max) {
+    const int nb = std::min(chunk_max, n - b0);
+    EdgeArgs a;
+    a.bp.box = c->scratch.p + (size_t)6 * b0;
+    a.bp.rows = (uint32_t)nb; a.bp.n1 = n1; a.bp.n_tasks = (uint32_t)nb * n1; a.bp.row_base = 0; a.bp.rows_all = (uint32_t)nb;
+    a.bp.d = d; a.bp.row_task = nullptr; a.bp.row_l1 = nullptr;
+    for (int k = 0; k < 3; k++) {
+      a.bp.l1lo[k] = c->lvl[1].lo[k]; a.bp.l1hi[k] = c->lvl[1].hi[k];
+      a.bp.l0lo[k] = c->lvl[0].lo[k]; a.bp.l0hi[k] = c->lvl[0].hi[k];
+    }
+    a.bp.px = c->px.p; a.bp.py = c->py.p; a.bp.pz = c->pz.p;
+    a.bp.bsum = nullptr; a.bp.cand_pt = nullptr; a.bp.cand_row = nullptr; a.bp.row_off = nullptr; a.bp.cand_cap = 0; a.bp.dc = c->dc.p;
+    uint32_t tpc = a.bp.n_tasks / (4u * (uint32_t)c->sm_count);
+    a.bp.tpc = tpc < 16u ? 16u : (tpc > (uint32_t)BP_THREADS ? (uint32_t)BP_THREADS : tpc);
+    a.E = c->scratch.p + (size_t)6 * n + (size_t)6 * b0; a.d = d; a.invalid = inv.p + b0;
+    k_bp_edge<<<div_up((size_t)a.bp.n_tasks, a.bp.tpc), BP_THREADS, 0, st>>>(a);
+    TOB_LAUNCH_CHECK(c);
+  }
+  std::vector<uint32_t> h(n);
+  TOB_CUDA(c, cudaMemcpyAsync(h.data(), inv.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  TOB_CUDA(c, cudaStreamSynchronize(st));
+  for (int i = 0; i < n; i++) valid_host[i] = h[i] ? 0 : 1;
   return 0;
 }
 

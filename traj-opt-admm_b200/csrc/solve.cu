@@ -29,6 +29,7 @@ struct SolveArgs {
   int* status;       // robots: 0 ok, 1 not SPD
   double* gband;     // optional global workspace (robots x m x 22) when shared memory is too small
   int use_global;
+  DevCounts* dc;     // a failed factorisation sets TOB_ERR_SOLVE: the iteration is not committed
 };
 
 __global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
     W += t * s_gt;
     a.wolfe[robot] = -W;
     a.status[robot] = s_fail;
+    if (s_fail && a.dc) atomicOr(&a.dc->overflow, TOB_ERR_SOLVE);
   }
 }
 
@@ -253,8 +255,9 @@ struct BcrArgs {
   // coupled multi-robot system (Optimization3D_multi::update_spline :508-639): block diagonal per robot + ONE shared
   // arrow row for the common piece time.  Each robot's CTA exports z = B^-1 g, y = B^-1 a and its partial sums; the
   // Schur complement over all robots is closed by k_couple_finish.  Null for the decoupled / single-robot solve.
-  double* cpl_part;   // robots x 5 : a.y, a.z, g.g, h_t, g_t
+  double* cpl_part;   // robots x 7 : a.y, a.z, g.g, h_t, g_t, z.g, y.g
   double* cpl_zyg;    // robots x (N*9) x 3 : z, y, g
+  DevCounts* dc;      // a failed factorisation sets TOB_ERR_SOLVE: the iteration is not committed
 };
 
 __global__ void __launch_bounds__(1024) k_solve_bcr(BcrArgs a) {
@@ -460,19 +463,33 @@ __global__ void __launch_bounds__(1024) k_solve_bcr(BcrArgs a) {
   if (lane == 0) { s_red[wp][0] = ay; s_red[wp][1] = az; s_red[wp][2] = gg; }
   __syncthreads();
   if (a.cpl_part) {
-    if (tid == 0) {
-      double AY = 0, AZ = 0, GG = 0;
-      for (int i = 0; i < nw; i++) { AY += s_red[i][0]; AZ += s_red[i][1]; GG += s_red[i][2]; }
-      double* o = a.cpl_part + 5 * (size_t)robot;
-      o[0] = AY; o[1] = AZ; o[2] = GG; o[3] = s_h; o[4] = s_gt;
-      a.status[robot] = s_fail;
-    }
-    double* o = a.cpl_zyg + (size_t)robot * N * BS * 3;
+    // coupled system: this robot's contributions to the shared-time Schur complement and to wolfe = -(x.g + t g_t) with
+    // x_i = -z_i - y_i t, i.e. x_i.g_i = -(z_i.g_i) - t (y_i.g_i): seven sums per robot, closed over ALL robots (in robot
+    // order, whichever rank computed them) by k_couple_finish
+    double zg = 0, yg = 0;
     for (int e = tid; e < N * BS; e += blockDim.x) {
       const int b = e / BS, r = e - BS * b;
-      o[3 * e] = blk[(size_t)b * BLK + 243 + r];
-      o[3 * e + 1] = blk[(size_t)b * BLK + 243 + BS + r];
-      o[3 * e + 2] = rhs0[b * 18 + r];
+      const double g0 = rhs0[b * 18 + r];
+      zg += blk[(size_t)b * BLK + 243 + r] * g0;
+      yg += blk[(size_t)b * BLK + 243 + BS + r] * g0;
+    }
+    for (int o = 16; o; o >>= 1) { zg += __shfl_xor_sync(0xffffffffu, zg, o); yg += __shfl_xor_sync(0xffffffffu, yg, o); }
+    __shared__ double s_red2[32][2];
+    if (lane == 0) { s_red2[wp][0] = zg; s_red2[wp][1] = yg; }
+    __syncthreads();
+    if (tid == 0) {
+      double AY = 0, AZ = 0, GG = 0, ZG = 0, YG = 0;
+      for (int i = 0; i < nw; i++) { AY += s_red[i][0]; AZ += s_red[i][1]; GG += s_red[i][2]; ZG += s_red2[i][0]; YG += s_red2[i][1]; }
+      double* o = a.cpl_part + 7 * (size_t)robot;
+      o[0] = AY; o[1] = AZ; o[2] = GG; o[3] = s_h; o[4] = s_gt; o[5] = ZG; o[6] = YG;
+      a.status[robot] = s_fail;
+      if (s_fail && a.dc) atomicOr(&a.dc->overflow, TOB_ERR_SOLVE);
+    }
+    double* o = a.cpl_zyg + (size_t)robot * N * BS * 2;
+    for (int e = tid; e < N * BS; e += blockDim.x) {
+      const int b = e / BS, r = e - BS * b;
+      o[2 * e] = blk[(size_t)b * BLK + 243 + r];
+      o[2 * e + 1] = blk[(size_t)b * BLK + 243 + BS + r];
     }
     return;
   }
@@ -506,57 +523,56 @@ __global__ void __launch_bounds__(1024) k_solve_bcr(BcrArgs a) {
     W += t * s_gt;
     a.wolfe[robot] = -W;
     a.status[robot] = s_fail;
+    if (s_fail && a.dc) atomicOr(&a.dc->overflow, TOB_ERR_SOLVE);
   }
 }
 
 // closes the shared-time Schur complement of the coupled system: t = (sum a_i.z_i - sum g_t,i) / (sum h_t,i - sum a_i.y_i),
-// x_i = -z_i - y_i t, wolfe = -(sum x_i.g_i + t sum g_t,i), gnorm = |G| / U (Optimization3D_multi.h:553-583)
-__global__ void __launch_bounds__(256) k_couple_finish(const double* __restrict__ part, const double* __restrict__ zyg, int U, int N, int T,
-                                                       double* dir, double* tdir, double* wolfe, double* gnorm, int* status) {
-  __shared__ double s_t, s_gt, s_w[8];
+// x_i = -z_i - y_i t, wolfe = -(sum x_i.g_i + t sum g_t,i), gnorm = |G| / U (Optimization3D_multi.h:553-583).  `part` holds
+// the seven sums of EVERY robot (sharded: all-gathered), summed in robot order, so every rank gets bitwise the same t, wolfe
+// and gnorm as a single context; the directions are written for the owned robots [rb, re).
+__global__ void __launch_bounds__(256) k_couple_finish(const double* __restrict__ part, const double* __restrict__ zy, int U, int rb,
+                                                       int re, int N, int T, double* dir, double* tdir, double* wolfe, double* gnorm,
+                                                       DevCounts* dc) {
+  __shared__ double s_t;
   const int tid = threadIdx.x;
   if (tid == 0) {
-    double AY = 0, AZ = 0, GG = 0, HT = 0, GT = 0;
-    for (int u = 0; u < U; u++) { AY += part[5 * u]; AZ += part[5 * u + 1]; GG += part[5 * u + 2]; HT += part[5 * u + 3]; GT += part[5 * u + 4]; }
+    double AY = 0, AZ = 0, GG = 0, HT = 0, GT = 0, ZG = 0, YG = 0;
+    for (int u = 0; u < U; u++) {
+      const double* p = part + 7 * (size_t)u;
+      AY += p[0]; AZ += p[1]; GG += p[2]; HT += p[3]; GT += p[4]; ZG += p[5]; YG += p[6];
+    }
     const double schur = HT - AY;
-    if (!(schur > 0)) status[0] = 1;
-    s_t = (AZ - GT) / schur;
-    s_gt = GT;
+    if (!(schur > 0)) atomicOr(&dc->overflow, TOB_ERR_SOLVE);
+    const double t = (AZ - GT) / schur;
+    s_t = t;
     const double gn = sqrt(GG + GT * GT) / double(U);
-    for (int u = 0; u < U; u++) { tdir[u] = s_t; gnorm[u] = gn; }
+    const double w = (ZG + t * YG) - t * GT;
+    for (int u = 0; u < U; u++) { tdir[u] = t; gnorm[u] = gn; wolfe[u] = w; }
   }
   __syncthreads();
   const double t = s_t;
-  double wl = 0;
   const int per = N * BS;
-  for (int i = tid; i < U * per; i += blockDim.x) {
-    const int u = i / per, e = i - u * per, b = e / BS, r = e - BS * b;
+  for (int i = tid; i < (re - rb) * per; i += blockDim.x) {
+    const int u = rb + i / per, e = i % per, b = e / BS, r = e - BS * b;
+    const size_t g = (size_t)u * per + e;
     const bool fixed = (b == 0 && r < 6) || (b == N - 1 && r >= 3);
-    const double x = fixed ? 0.0 : (-zyg[3 * (size_t)i] - zyg[3 * (size_t)i + 1] * t);
-    wl += x * zyg[3 * (size_t)i + 2];
+    const double x = fixed ? 0.0 : (-zy[2 * g] - zy[2 * g + 1] * t);
     dir[(size_t)u * 3 * T + (size_t)(e % 3) * T + e / 3] = x;
-  }
-  for (int o = 16; o; o >>= 1) wl += __shfl_xor_sync(0xffffffffu, wl, o);
-  if ((tid & 31) == 0) s_w[tid >> 5] = wl;
-  __syncthreads();
-  if (tid == 0) {
-    double W = 0;
-    for (int i = 0; i < 8; i++) W += s_w[i];
-    W += t * s_gt;
-    for (int u = 0; u < U; u++) wolfe[u] = -W;
   }
 }
 
+// coupled Newton direction of the owned robots.  Sharded: the per-robot Schur sums are exchanged between the two kernels.
 int solve_coupled(tob_ctx* c) {
-  const int U = c->n_robots(), N = c->prm.piece_num + 1;
+  const int U = c->n_robots(), N = c->prm.piece_num + 1, rb = c->own_begin, re = c->own_end;
   const size_t smem_bcr = ((size_t)N * BLK + (size_t)N * 18) * sizeof(double);
   if (smem_bcr > 220 * 1024) return fail_msg(c, "coupled mode: trajectories with more than ~100 pieces are not supported");
-  TOB_CUDA(c, c->scratch.ensure((size_t)5 * U));
-  TOB_CUDA(c, c->scratch2.ensure((size_t)3 * U * N * BS));
+  TOB_CUDA(c, c->cpl_part.ensure((size_t)7 * U));
+  TOB_CUDA(c, c->cpl_zy.ensure((size_t)2 * U * N * BS));
   BcrArgs a;
-  a.pc_g = c->pc_g.p; a.pc_h = c->pc_h.p; a.P = c->prm.piece_num; a.T = c->T; a.robot_begin = 0;
+  a.pc_g = c->pc_g.p; a.pc_h = c->pc_h.p; a.P = c->prm.piece_num; a.T = c->T; a.robot_begin = rb;
   a.dir = c->s_dir.p; a.tdir = c->s_tdir.p; a.wolfe = c->s_wolfe.p; a.gnorm = c->s_gnorm.p; a.status = c->solve_status.p;
-  a.cpl_part = c->scratch.p; a.cpl_zyg = c->scratch2.p;
+  a.cpl_part = c->cpl_part.p; a.cpl_zyg = c->cpl_zy.p; a.dc = c->dc.p;
   if (!c->bcr_attr_set) {
     TOB_CUDA(c, cudaFuncSetAttribute(k_solve_bcr, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     c->bcr_attr_set = true;
@@ -566,11 +582,12 @@ int solve_coupled(tob_ctx* c) {
   if (warps > 32) warps = 32;
   {
     Prof prof(c, K_SOLVE);
-    k_solve_bcr<<<U, warps * 32, smem_bcr, c->stream>>>(a);
+    k_solve_bcr<<<re - rb, warps * 32, smem_bcr, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
-  k_couple_finish<<<1, 256, 0, c->stream>>>(c->scratch.p, c->scratch2.p, U, N, c->T, c->s_dir.p, c->s_tdir.p, c->s_wolfe.p, c->s_gnorm.p,
-                                            c->solve_status.p);
+  TOB_TRY(exchange_robots(c, c->cpl_part.p, 7, sizeof(double)));
+  k_couple_finish<<<1, 256, 0, c->stream>>>(c->cpl_part.p, c->cpl_zy.p, U, rb, re, N, c->T, c->s_dir.p, c->s_tdir.p, c->s_wolfe.p,
+                                            c->s_gnorm.p, c->dc.p);
   TOB_LAUNCH_CHECK(c);
   return 0;
 }
@@ -588,7 +605,7 @@ int solve_directions(tob_ctx* c, int rb, int re, int dense_shift) {
     BcrArgs a;
     a.pc_g = c->pc_g.p; a.pc_h = c->pc_h.p; a.P = c->prm.piece_num; a.T = c->T; a.robot_begin = rb;
     a.dir = c->s_dir.p; a.tdir = c->s_tdir.p; a.wolfe = c->s_wolfe.p; a.gnorm = c->s_gnorm.p; a.status = c->solve_status.p;
-    a.cpl_part = nullptr; a.cpl_zyg = nullptr;
+    a.cpl_part = nullptr; a.cpl_zyg = nullptr; a.dc = c->dc.p;
     if (!c->bcr_attr_set) {
       TOB_CUDA(c, cudaFuncSetAttribute(k_solve_bcr, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
       c->bcr_attr_set = true;
@@ -609,6 +626,7 @@ int solve_directions(tob_ctx* c, int rb, int re, int dense_shift) {
   TOB_CUDA(c, c->band.ensure((size_t)(re - rb) * m * 22));
   a.gband = c->band.p;
   a.use_global = 1;
+  a.dc = c->dc.p;
   Prof prof(c, K_SOLVE);
   k_solve<<<re - rb, 256, 0, c->stream>>>(a);
   TOB_LAUNCH_CHECK(c);

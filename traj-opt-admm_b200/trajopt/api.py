@@ -34,7 +34,8 @@ class TobCounters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("dcd_candidates", C.c_uint64), ("planes", C.c_uint64),
                 ("ccd_candidates", C.c_uint64), ("energy_plane_evals", C.c_uint64), ("self_pairs", C.c_uint64),
                 ("line_search_trials", C.c_uint64), ("barrier_terms", C.c_uint64), ("live_planes", C.c_uint64),
-                ("refine_capped", C.c_uint64)]
+                ("refine_capped", C.c_uint64), ("np_kdop_groups", C.c_uint64), ("np_gjk_iters", C.c_uint64),
+                ("ccd_gjk_iters", C.c_uint64), ("ccd_kdop_pass", C.c_uint64)]
 
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_void_p)
@@ -53,6 +54,13 @@ def _u(a):
 
 def F(a):
     return np.array(a, dtype=np.float64, order="F")
+
+
+def Fview(a):
+    """column-major float64 view when the array already is one (no copy), else a copy"""
+    if isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.f_contiguous:
+        return a
+    return F(a)
 
 
 def load_library():
@@ -126,12 +134,18 @@ class Solver:
                                          _d(np.ascontiguousarray(t["kdop"]))))
 
     def init_pointcloud(self, V):
-        V = F(V)
+        V = Fview(V)
         self._ck(self.lib.tob_cloud_upload(self.ctx, _d(V), C.c_uint32(V.shape[0])))
+
+    def build_stats(self):
+        """(device ms, points) of the last LBVH build"""
+        ms = C.c_double(0); n = C.c_uint64(0)
+        self.lib.tob_build_stats(self.ctx, C.byref(ms), C.byref(n))
+        return ms.value, n.value
 
     def init_pointclouds(self, Vs):
         """one cloud per robot slot (batched independent problems, mode 2)"""
-        Vs = [F(V) for V in Vs]
+        Vs = [Fview(V) for V in Vs]
         ptrs = (_dp * len(Vs))(*[_d(V) for V in Vs])
         ns = (C.c_uint32 * len(Vs))(*[V.shape[0] for V in Vs])
         self._ck(self.lib.tob_cloud_upload_batch(self.ctx, ptrs, ns, C.c_int(len(Vs))))
@@ -171,6 +185,13 @@ class Solver:
         self._ck(self.lib.tob_self_broadphase(self.ctx, _d(P), Dp, C.c_int(u), C.c_double(d), _u(pairs), C.c_uint64(u * u // 2 + 1),
                                               C.byref(total)))
         return pairs[:2 * total.value].reshape(-1, 2)
+
+    def edge_validity(self, edges, d):
+        """edges: (n, 2, 3); True where no cloud point is within d of the segment (the motion validator's obstacle test)"""
+        E = np.ascontiguousarray(edges, dtype=np.float64)
+        n = E.shape[0]; out = np.zeros(max(n, 1), dtype=np.uint8)
+        self._ck(self.lib.tob_edge_validity_batch(self.ctx, _d(E), C.c_int(n), C.c_double(d), out.ctypes.data_as(_bp)))
+        return out[:n].astype(bool)
 
     # ---- batched primitives (inputs: (n, rows, 3) arrays)
     @staticmethod
@@ -377,6 +398,26 @@ class Solver:
         t = C.c_double(0)
         self._ck(self.lib.tob_fp64_peak(self.ctx, C.byref(t)))
         return t.value
+
+    # ---- multi-GPU: robots sharded over the ranks of a NCCL communicator (see include/trajopt_b200.h)
+    def nccl_unique_id(self):
+        buf = (C.c_uint8 * 128)()
+        if self.lib.tob_nccl_unique_id(buf):
+            raise RuntimeError("tob_nccl_unique_id: " + self.lib.tob_last_error(None).decode())
+        return bytes(buf)
+
+    def nccl_init_rank(self, uid, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._ck(self.lib.tob_nccl_init_rank(self.ctx, buf, C.c_int(rank), C.c_int(world)))
+        return self.shard_range()
+
+    def nccl_detach(self):
+        self._ck(self.lib.tob_nccl_detach(self.ctx))
+
+    def shard_range(self):
+        a, b, r, w = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self.lib.tob_shard_range(self.ctx, C.byref(a), C.byref(b), C.byref(r), C.byref(w))
+        return a.value, b.value
 
     def set_shard(self, first, count, allgather, allreduce):
         self._cb = (ALLGATHER_FN(allgather), ALLREDUCE_FN(allreduce))

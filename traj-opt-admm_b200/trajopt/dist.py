@@ -14,11 +14,23 @@ import torch.distributed as dist
 
 
 def partition(n_robots, world, rank):
-    """contiguous equal blocks; the in-place all-gather needs equal counts"""
-    if n_robots % world:
-        raise ValueError("n_robots (%d) must be divisible by the number of ranks (%d)" % (n_robots, world))
-    c = n_robots // world
-    return rank * c, c
+    """contiguous blocks, the first (n_robots mod world) ranks own one robot more -- the partition the C library applies
+    when a NCCL communicator is attached (comm.cu: shard_partition)"""
+    if world > n_robots:
+        raise ValueError("more ranks (%d) than robots (%d)" % (world, n_robots))
+    base, rem = divmod(n_robots, world)
+    return rank * base + min(rank, rem), base + (1 if rank < rem else 0)
+
+
+def attach_nccl(solver, group=None):
+    """native path: the C library creates its own NCCL communicator over the ranks of `group` (the ncclUniqueId travels
+    through torch.distributed, whatever its backend) and issues every exchange itself, on its stream, inside its CUDA graph"""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [solver.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    first, count = solver.nccl_init_rank(box[0], rank, world)
+    assert (first, count) == partition(solver.uav_num, world, rank)
+    return first, count
 
 
 class _DevArray:
@@ -43,8 +55,11 @@ def allgather_inplace(full, per_rank, rank, group=None):
 
 
 def attach(solver, group=None):
-    """shard solver.uav_num robots over the process group and install the exchange callbacks"""
+    """legacy path: shard solver.uav_num robots over the process group and install exchange callbacks that go through
+    torch.distributed (equal blocks only; kept for hosts that already own a process group and for the CPU/gloo tests)"""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if solver.uav_num % world:
+        raise ValueError("the callback exchange needs equal blocks: n_robots (%d) %% ranks (%d) != 0" % (solver.uav_num, world))
     first, count = partition(solver.uav_num, world, rank)
     dev = torch.device("cuda", torch.cuda.current_device())
     ext = torch.cuda.ExternalStream(solver.stream(), device=dev)
