@@ -142,8 +142,10 @@ def test_row_blocks_plane_and_bound(pair):
         else:
             assert np.abs(h1).max() == 0 and np.abs(g1).max() == 0
     n_active = 0
-    for t in (st["piece_time"], 2.6, 2.2):       # short piece times switch the velocity / acceleration barriers on
-        for tr in (0, 7, 23, 40, 63):
+    # short piece times switch the velocity / acceleration barriers on (inf below the shortest feasible time: skipped)
+    # (the barrier is active in the narrow band vel_limit - margin < v < vel_limit: a fine grid of times over all rows)
+    for t in [st["piece_time"]] + list(np.linspace(1.7, 2.2, 26)):
+        for tr in range(0, P * 8, 3):
             a = ref.local_bound_gradient(st["spline"], tr, t)
             b = dev.local_bound_gradient(st["spline"], tr, t)
             if not np.all(np.isfinite(a[0])):

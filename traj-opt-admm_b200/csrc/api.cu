@@ -208,7 +208,7 @@ __global__ void k_flags_merge(DevCounts* dc, const double* all, int rank, int wo
   for (int r = 0; r < world; r++) if (r != rank) remote |= (uint32_t)all[r];
   uint32_t add = 0;
   if (remote & TOB_ERR_SOLVE) add |= TOB_ERR_SOLVE;
-  if (remote & (TOB_OVF_CAND | TOB_OVF_LIVE | TOB_OVF_REMOTE)) add |= TOB_OVF_REMOTE;
+  if (remote & TOB_OVF_RETRY) add |= TOB_OVF_REMOTE;
   if (add) dc->overflow |= add;
 }
 
@@ -343,7 +343,7 @@ static int ensure_iter_buffers(tob_ctx* c) {
   if (c->live_planes()) TOB_TRY(ensure_live_buffers(c, c->live_cap ? c->live_cap : 1));
   TOB_CUDA(c, c->geo.P.ensure(18 * rows)); TOB_CUDA(c, c->geo.D.ensure(18 * rows)); TOB_CUDA(c, c->geo.box.ensure(6 * rows));
   TOB_CUDA(c, c->geo.klo.ensure(TOB_KDOP_AXES * rows)); TOB_CUDA(c, c->geo.khi.ensure(TOB_KDOP_AXES * rows));
-  TOB_CUDA(c, c->row_e.ensure(2 * rows * TOB_LS_TRIALS)); TOB_CUDA(c, c->row_bad.ensure(rows * TOB_LS_TRIALS));
+  TOB_CUDA(c, c->row_e.ensure(TOB_EN_REC * rows * TOB_LS_TRIALS)); TOB_CUDA(c, c->row_bad.ensure(U * TOB_LS_TRIALS + 1));
   TOB_CUDA(c, c->pc_g.ensure(19 * U * P)); TOB_CUDA(c, c->pc_h.ensure(361 * U * P)); TOB_CUDA(c, c->pc_flag.ensure(U * P));
   if (U > 1 && c->cloud_n1.empty()) {   // inter-robot scratch (never used by independent problems)
     const size_t n = (size_t)c->n_tr * (U * (U - 1) / 2);
@@ -427,6 +427,7 @@ static int iterate_launch(tob_ctx* c, int mode) {
     TOB_LAUNCH_CHECK(c);
     wolfe_idx = U > 1 ? U - 1 : -1;
   }
+  if (!coupled) TOB_TRY(line_search_begin(c, rb, re));
   TOB_TRY(ls_launch_ahead(c, rb, re, wolfe_idx, coupled));
   // (5) step, slack + dual: guarded on the device (see iterate_once)
   TOB_TRY(apply_step(c, rb, re, true, coupled));
@@ -501,16 +502,16 @@ static int iterate_once(tob_ctx* c, int mode, double* gnorm_out) {
     TOB_TRY(sync_counts(c));
     if (c->h_dc->iters_done != done0) break;                 // committed on the device
     const uint32_t ovf = c->h_dc->overflow;
-    if (ovf & TOB_ERR_SOLVE) {                               // same on every rank of a sharded run
-      TOB_TRY(clear_overflow(c));
-      return fail_msg(c, "Newton matrix is not positive definite (Cholesky pivot or Schur complement <= 0): iteration not committed");
-    }
-    if (ovf & (TOB_OVF_CAND | TOB_OVF_LIVE | TOB_OVF_REMOTE)) {   // nothing was changed: grow and run the iteration again
+    if (ovf & TOB_OVF_RETRY) {                               // nothing was changed: grow and run the iteration again
       if (attempt >= 8) return fail_msg(c, "candidate buffers keep overflowing");
       TOB_TRY(clear_overflow(c));
       if (ovf & TOB_OVF_CAND) TOB_TRY(grow_cand_capacity(c, c->h_dc->n_cand));
       if (ovf & TOB_OVF_LIVE) TOB_TRY(ensure_live_buffers(c, (uint64_t)c->h_dc->n_live + c->h_dc->n_new + 1));
       continue;
+    }
+    if (ovf & TOB_ERR_SOLVE) {                               // same on every rank of a sharded run
+      TOB_TRY(clear_overflow(c));
+      return fail_msg(c, "Newton matrix is not positive definite (Cholesky pivot or Schur complement <= 0): iteration not committed");
     }
     // a robot needs more than the rungs launched ahead: finish its search from the host, then commit.  (Decoupled: the
     // search is rank-local.  Coupled: every rank holds the same energies and takes the same decisions, exchanges matched.)
@@ -1058,19 +1059,24 @@ static int robot_ok(tob_ctx* c, int robot) {
   return 0;
 }
 
-__global__ void k_plane_energy_only(const double* row_e, const int* row_bad, int row0, int n_tr, double* out) {
+// row_e record of (trial 0, row): up to 8 plane-energy partials (one per 256 planes of the row, barrier.cu) + the bound energy
+__global__ void k_plane_energy_only(const double* row_e, const int* bad, const uint32_t* pl_off, int row0, int n_tr, double* out) {
   // single thread: ordered sum like the reference's loop over tr_id
   if (threadIdx.x || blockIdx.x) return;
-  double e = 0; int bad = 0;
-  for (int t = 0; t < n_tr; t++) { e += row_e[2 * (size_t)(row0 + t)]; bad |= row_bad[row0 + t]; }
-  out[0] = e; out[1] = bad;
+  double e = 0;
+  for (int t = 0; t < n_tr; t++) {
+    const uint32_t np = pl_off[row0 + t + 1] - pl_off[row0 + t];
+    int V = (int)((np + 255) / 256); V = V < 1 ? 1 : (V > 8 ? 8 : V);
+    for (int v = 0; v < V; v++) e += row_e[TOB_EN_REC * (size_t)(row0 + t) + v];
+  }
+  out[0] = e; out[1] = bad[0];
 }
 
-__global__ void k_bound_energy_only(const double* row_e, const int* row_bad, int row0, int n_tr, double* out) {
+__global__ void k_bound_energy_only(const double* row_e, const int* bad, int row0, int n_tr, double* out) {
   if (threadIdx.x || blockIdx.x) return;
-  double e = 0; int bad = 0;
-  for (int t = 0; t < n_tr; t++) { e += row_e[2 * (size_t)(row0 + t) + 1]; bad |= row_bad[row0 + t]; }
-  out[0] = e; out[1] = bad;
+  double e = 0;
+  for (int t = 0; t < n_tr; t++) e += row_e[TOB_EN_REC * (size_t)(row0 + t) + (TOB_EN_REC - 1)];
+  out[0] = e; out[1] = bad[0];
 }
 
 int tob_plane_barrier_energy(tob_ctx* c, int robot, const double* spline, double* e) {
@@ -1081,7 +1087,7 @@ int tob_plane_barrier_energy(tob_ctx* c, int robot, const double* spline, double
   double big = 1e300;
   TOB_TRY(upload(c, c->s_ptrial, &big, 1, robot));
   TOB_TRY(energy_trials(c, robot, robot + 1, nullptr, nullptr, c->s_ptrial.p, 1, 0, 1, c->s_e1.p));
-  k_plane_energy_only<<<1, 32, 0, c->stream>>>(c->row_e.p, c->row_bad.p, robot * c->n_tr, c->n_tr, c->red.p);
+  k_plane_energy_only<<<1, 32, 0, c->stream>>>(c->row_e.p, c->row_bad.p + robot, c->pl_off.p, robot * c->n_tr, c->n_tr, c->red.p);
   TOB_LAUNCH_CHECK(c);
   TOB_TRY(read_back(c, c->red.p, 2 * sizeof(double)));
   *e = c->h_pinned[1] != 0 ? INFINITY : c->h_pinned[0];
@@ -1253,6 +1259,7 @@ int tob_line_search(tob_ctx* c, int robot, tob_state* st, const double* directio
   k_ls_init<<<1, 64, 0, c->stream>>>(robot, robot + 1, c->kmax.p, c->d_steps.p, c->s_selfstep.p, use_self, c->s_ptime.p, c->s_tdir.p,
                                      c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p, c->ls_rounds);
   TOB_LAUNCH_CHECK(c);
+  TOB_TRY(line_search_begin(c, robot, robot + 1));
   TOB_TRY(line_search(c, robot, robot + 1, -1));
   TOB_CUDA(c, cudaMemcpyAsync(st->spline, c->s_spline.p + (size_t)robot * 3 * T, 3 * T * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   TOB_CUDA(c, cudaMemcpyAsync(st->piece_time, c->s_ptime.p + robot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));

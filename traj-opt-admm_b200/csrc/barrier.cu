@@ -15,6 +15,8 @@
 //                  terms, Cholesky test, eigen-shift when not SPD.
 // Reductions are fixed-order (shuffle tree + ordered cross-warp sum): bitwise reproducible run to run.
 // Tolerance vs the reference: summation order differs, FMA contraction allowed here -> ~1e-13 relative.
+#include <stdlib.h>
+
 #include "ctx.cuh"
 #include "dense.cuh"
 
@@ -30,9 +32,29 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---- energy --------------------------------------------------------------------------------------------------------
-// One launch evaluates a BATCH of line-search trial points: blockIdx.y = trial k, trial spline = spline + tstep[u][k]*dir
-// (element-wise, then P = basis*bz with the reference's unfused left-to-right arithmetic: explicit __dmul_rn/__dadd_rn
-// because this file is compiled with FMA contraction on), trial piece time = ttime[u][k].
+// One launch evaluates a BATCH of line-search trial points: trial k of robot u is spline + tstep[u][k]*dir (element-wise,
+// then P = basis*bz with the reference's unfused left-to-right arithmetic: explicit __dmul_rn/__dadd_rn because this file
+// is compiled with FMA contraction on), trial piece time = ttime[u][k].
+//
+// Summation structure (what makes the result independent of the launch shape, of the batch a problem sits in and of the
+// sharding): the planes of a row are dealt in chunks of 32 to V(row) = clamp(ceil(planes / 256), 1, 8) VIRTUAL WARPS
+// (chunk i belongs to virtual warp i mod V); a virtual warp sums its terms lane-wise in chunk order, reduces with the
+// xor-shuffle tree and stores ONE partial; the robot kernels add the V partials of a row in order.  V depends on the row's
+// plane count only.  How many physical warps / CTAs execute the virtual warps of a row is a free scheduling choice (VL).
+//
+// Early exit (Energy_admm.h:81-82: the reference returns INFINITY at the first d <= 0): a warp that meets a violated plane
+// raises the flag of its (robot, trial) and stops; every other warp of that trial -- of any row of the robot -- polls the
+// flag and stops too.  An infeasible trial costs a few plane chunks instead of a full pass.
+// In-band compaction: only terms inside the barrier band (0 < d < margin) need a logarithm; they are queued per warp
+// (ballot + prefix, deterministic order) and evaluated on dense lanes.
+#define EN_VMAX 8
+#define EN_VPLANES 256
+#define EN_REC (EN_VMAX + 1)        // per (trial, row): EN_VMAX plane-energy partials + the bound energy
+__host__ __device__ __forceinline__ int en_vwarps(uint32_t np) {
+  const int v = (int)((np + EN_VPLANES - 1) / EN_VPLANES);
+  return v < 1 ? 1 : (v > EN_VMAX ? EN_VMAX : v);
+}
+
 struct EnergyArgs {
   const double *spline, *dir;   // robots x 3T ; dir may be null (trial == current point)
   const double *tstep, *ttime;  // robots x KT ; tstep may be null (=0)
@@ -42,31 +64,36 @@ struct EnergyArgs {
   const double* weight;         // n_tr
   double margin, vel_limit, acc_limit;
   int n_tr, res, T, row_begin, rows_all, KT, k0, nk;
-  double* row_e;                // KT x rows_all x 2 : plane barrier, bound
-  int* row_bad;                 // KT x rows_all
+  int VL;                       // CTAs per row (gridDim.y): CTA g runs virtual warps g, g+VL, ...
+  double* row_e;                // KT x rows_all x EN_REC
+  int* bad;                     // robots x KT: trial infeasible (some d <= 0); raised here, cleared by the caller
   const int* done;              // per robot, may be null: robots whose line search has finished are skipped
   DevCounts* dc;                // barrier_terms counter
 };
 
-// One CTA per row, one WARP per trial point of the launch (blockDim = 32 * nk): the warps of a CTA stream the same planes
-// (L1 hits after the first warp), every warp keeps its own trial's control points in shared memory and reduces with
-// shuffles only -- no block-wide barrier, and the (row, trial) work items of a small problem still spread over
-// rows x nk warps.
 #define EN_MAXT TOB_LS_TRIALS
 __global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
   const int row = a.row_begin + blockIdx.x;
   const int robot = row / a.n_tr, tr = row - robot * a.n_tr;
   const int lane = threadIdx.x & 31, kk = threadIdx.x >> 5, k = a.k0 + kk;
   __shared__ double sPall[EN_MAXT][18], sBzall[EN_MAXT][18];
+  __shared__ double sQ[EN_MAXT][192];          // in-band terms of one chunk (32 planes x 6 control points)
   if (a.done && a.done[robot]) return;
   if (a.dc->overflow) return;      // the plane CSR of this iteration was not built: the host grows the buffers and retries
+  const uint32_t p0 = a.pl_off[row], p1 = a.pl_off[row + 1];
+  const int V = en_vwarps(p1 - p0);
+  const int g = blockIdx.y;
+  if (g >= V) return;              // nothing for this CTA (virtual warp 0 also carries the bound terms)
+  volatile int* flag = a.bad + robot * a.KT + k;
+  double* out = a.row_e + ((size_t)k * a.rows_all + row) * EN_REC;
+  if (*flag) return;               // the trial is already known to be infeasible: its energy is +inf whatever this row adds
   double* sP = sPall[kk];
   double* sBz = sBzall[kk];
   if (lane < 18) {
     const int mm = lane % 6, ax = lane / 6;
-    const size_t g = (size_t)robot * 3 * a.T + (size_t)ax * a.T + 3 * (tr / a.res) + mm;
-    double v = a.spline[g];
-    if (a.dir && a.tstep) v = __dadd_rn(v, __dmul_rn(a.tstep[robot * a.KT + k], a.dir[g]));
+    const size_t gi = (size_t)robot * 3 * a.T + (size_t)ax * a.T + 3 * (tr / a.res) + mm;
+    double v = a.spline[gi];
+    if (a.dir && a.tstep) v = __dadd_rn(v, __dmul_rn(a.tstep[robot * a.KT + k], a.dir[gi]));
     sBz[lane] = v;
   }
   __syncwarp();
@@ -79,72 +106,97 @@ __global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
   }
   __syncwarp();
   const double w = a.weight[tr], m = a.margin, inv_m = 1.0 / m;
-  double e = 0;
-  int bad = 0;
-  unsigned n_act = 0;
-  const uint32_t p0 = a.pl_off[row], p1 = a.pl_off[row + 1];
-  // Branch-free over the 6 control points: a lane whose term is outside the barrier band evaluates log(1) * 0, so the six
-  // logarithms of a plane are independent instruction streams the scheduler can interleave (with 32 lanes per warp some
-  // lane is inside the band for nearly every j anyway, so no work is added); the next plane is loaded one trip ahead.
-  uint32_t p = p0 + lane;
-  double4 nxt = make_double4(0, 0, 0, 0);
-  if (p < p1) nxt = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * p);
   double cp[18];
 #pragma unroll
   for (int i = 0; i < 18; i++) cp[i] = sP[i];
-  for (; p < p1; p += 32) {
-    const double4 pl = nxt;
-    if (p + 32 < p1) nxt = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * (p + 32));
-    double acc[6];
+  double* q = sQ[kk];
+  unsigned n_act = 0, n_pl = 0;
+  bool stop = false;
+  for (int v = g; v < V && !stop; v += a.VL) {
+    double e = 0;
+    uint32_t p = p0 + (uint32_t)v * 32u + lane;
+    const uint32_t stride = 32u * (uint32_t)V;
+    double4 nxt = make_double4(0, 0, 0, 0);
+    if (p < p1) nxt = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * p);
+    for (uint32_t base = p0 + (uint32_t)v * 32u; base < p1; base += stride, p += stride) {
+      const double4 pl = nxt;
+      const bool have = p < p1;
+      if (p + stride < p1) nxt = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * (p + stride));
+      double d[6];
+      bool bad = false;
+      unsigned cnt = 0;
 #pragma unroll
-    for (int j = 0; j < 6; j++) {
-      const double d = cp[j] * pl.x + cp[j + 6] * pl.y + cp[j + 12] * pl.z + pl.w;
-      const bool act = d > 0 && d < m;
-      bad |= (d <= 0);
-      n_act += act;
-      const double dm = act ? d - m : 0.0;
-      acc[j] = (dm * dm) * log(act ? d * inv_m : 1.0);
+      for (int j = 0; j < 6; j++) {
+        d[j] = cp[j] * pl.x + cp[j + 6] * pl.y + cp[j + 12] * pl.z + pl.w;
+        bad |= have && (d[j] <= 0);
+        const bool act = have && d[j] > 0 && d[j] < m;
+        const unsigned bm = __ballot_sync(0xffffffffu, act);
+        if (act) q[cnt + __popc(bm & ((1u << lane) - 1u))] = d[j];
+        cnt += __popc(bm);             // uniform
+      }
+      n_pl += have;
+      if (__any_sync(0xffffffffu, bad) || *flag) { stop = true; if (lane == 0) *flag = 1; break; }
+      __syncwarp();
+      for (unsigned t = lane; t < cnt; t += 32) {
+        const double dd = q[t], dm = dd - m;
+        e += (dm * dm) * log(dd * inv_m);
+      }
+      n_act += cnt;                    // counted once per warp below (uniform value)
+      __syncwarp();
     }
-    e += ((acc[0] + acc[1]) + (acc[2] + acc[3])) + (acc[4] + acc[5]);
+    if (stop) break;
+    e = warp_sum(e) * -w;
+    if (lane == 0) out[v] = e;
   }
-  e *= -w;
-  // bound terms: lanes 0..4 velocity, 5..8 acceleration
-  double eb = 0;
-  if (lane < 9) {
-    const double t = a.ttime[robot * a.KT + k];
-    double d;
-    if (lane < 5) {
-      int j = lane;
-      double vx = 5 * (sP[j + 1] - sP[j]), vy = 5 * (sP[j + 7] - sP[j + 6]), vz = 5 * (sP[j + 13] - sP[j + 12]);
-      d = a.vel_limit - sqrt(vx * vx + vy * vy + vz * vz) / (w * t);
-    } else {
-      int j = lane - 5;
-      double ax = 20 * (sP[j + 2] - 2 * sP[j + 1] + sP[j]), ay = 20 * (sP[j + 8] - 2 * sP[j + 7] + sP[j + 6]),
-             az = 20 * (sP[j + 14] - 2 * sP[j + 13] + sP[j + 12]);
-      d = a.acc_limit - sqrt(ax * ax + ay * ay + az * az) / (w * w * t * t);
+  // bound terms: virtual warp 0 only; lanes 0..4 velocity, 5..8 acceleration
+  if (g == 0 && !stop) {
+    double eb = 0;
+    int bad = 0;
+    if (lane < 9) {
+      const double t = a.ttime[robot * a.KT + k];
+      double d;
+      if (lane < 5) {
+        int j = lane;
+        double vx = 5 * (sP[j + 1] - sP[j]), vy = 5 * (sP[j + 7] - sP[j + 6]), vz = 5 * (sP[j + 13] - sP[j + 12]);
+        d = a.vel_limit - sqrt(vx * vx + vy * vy + vz * vz) / (w * t);
+      } else {
+        int j = lane - 5;
+        double ax = 20 * (sP[j + 2] - 2 * sP[j + 1] + sP[j]), ay = 20 * (sP[j + 8] - 2 * sP[j + 7] + sP[j + 6]),
+               az = 20 * (sP[j + 14] - 2 * sP[j + 13] + sP[j + 12]);
+        d = a.acc_limit - sqrt(ax * ax + ay * ay + az * az) / (w * w * t * t);
+      }
+      if (d <= 0) bad = 1;
+      else if (d < m) eb = -w * (d - m) * (d - m) * log(d / m);
     }
-    if (d <= 0) bad = 1;
-    else if (d < m) eb = -w * (d - m) * (d - m) * log(d / m);
+    eb = warp_sum(eb);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+      out[EN_VMAX] = eb;
+      if (bad) *flag = 1;
+    }
   }
-  e = warp_sum(e);
-  eb = warp_sum(eb);
-  bad = __any_sync(0xffffffffu, bad);
-  for (int o = 16; o; o >>= 1) n_act += __shfl_xor_sync(0xffffffffu, n_act, o);
+  n_pl = __reduce_add_sync(0xffffffffu, n_pl);
   if (lane == 0) {
-    const size_t o = (size_t)k * a.rows_all + row;
-    a.row_e[2 * o] = e;
-    a.row_e[2 * o + 1] = eb;
-    a.row_bad[o] = bad;
     if (n_act) atomicAdd(&a.dc->barrier_terms, (unsigned long long)n_act);
-    if (p1 > p0) atomicAdd(&a.dc->energy_plane_evals, (unsigned long long)(p1 - p0));   // planes x trials really evaluated
+    if (n_pl) atomicAdd(&a.dc->energy_plane_evals, (unsigned long long)n_pl);   // planes x trials really evaluated
   }
+}
+
+// plane-barrier energy of one (trial, row): its V partials in order
+__device__ __forceinline__ double row_plane_sum(const double* row_e, size_t o, const uint32_t* pl_off, int row) {
+  const double* p = row_e + o * EN_REC;
+  const int V = en_vwarps(pl_off[row + 1] - pl_off[row]);
+  double s = p[0];
+  for (int v = 1; v < V; v++) s += p[v];
+  return s;
 }
 
 struct RobotEnergyArgs {
   const double *spline, *dir, *tstep, *ttime;
   const double *pslack, *tslack, *plambda, *tlambda, *convert;
   const double* row_e;
-  const int* row_bad;
+  const uint32_t* pl_off;
+  int* bad;                                     // robots x KT (raised by k_row_energy)
   double lambda, mu;
   int n_tr, P, T, robot_begin, rows_all, KT, k0;
   double* e_out;                                // robots x KT
@@ -153,15 +205,12 @@ struct RobotEnergyArgs {
 __global__ void __launch_bounds__(128) k_robot_energy(RobotEnergyArgs a) {
   const int robot = a.robot_begin + blockIdx.x, k = a.k0 + blockIdx.y;
   __shared__ double s_part[4];
-  __shared__ int s_bad;
-  if (threadIdx.x == 0) s_bad = 0;
-  __syncthreads();
+  const bool infeasible = a.bad[robot * a.KT + k] != 0;      // the row sums of an infeasible trial are incomplete: unused
   double e = 0;
-  int bad = 0;
-  for (int tr = threadIdx.x; tr < a.n_tr; tr += blockDim.x) {
-    size_t o = (size_t)k * a.rows_all + (size_t)robot * a.n_tr + tr;
-    e += a.lambda * a.row_e[2 * o] + a.lambda * a.row_e[2 * o + 1];
-    bad |= a.row_bad[o];
+  for (int tr = threadIdx.x; tr < a.n_tr && !infeasible; tr += blockDim.x) {
+    const int row = robot * a.n_tr + tr;
+    size_t o = (size_t)k * a.rows_all + row;
+    e += a.lambda * row_plane_sum(a.row_e, o, a.pl_off, row) + a.lambda * a.row_e[o * EN_REC + EN_VMAX];
   }
   // consensus terms, one thread per piece
   const double t = a.ttime[robot * a.KT + k];
@@ -188,13 +237,12 @@ __global__ void __launch_bounds__(128) k_robot_energy(RobotEnergyArgs a) {
     e += acc;
   }
   e = warp_sum(e);
-  if (bad) atomicOr(&s_bad, 1);
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   if (lane == 0) s_part[wp] = e;
   __syncthreads();
   if (threadIdx.x == 0) {
     double tot = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
-    a.e_out[robot * a.KT + k] = s_bad ? INFINITY : tot;
+    a.e_out[robot * a.KT + k] = infeasible ? INFINITY : tot;
   }
 }
 
@@ -221,11 +269,11 @@ __global__ void __launch_bounds__(32 * TOB_LS_TRIALS) k_robot_ls(RobotLsArgs b) 
   const int lane = threadIdx.x & 31, k = a.k0 + (threadIdx.x >> 5);   // one warp per trial point
   if (k < b.kte) {
     double e = 0;
-    int bad = 0;
-    for (int tr = lane; tr < a.n_tr; tr += 32) {
-      size_t o = (size_t)k * a.rows_all + (size_t)robot * a.n_tr + tr;
-      e += a.lambda * a.row_e[2 * o] + a.lambda * a.row_e[2 * o + 1];
-      bad |= a.row_bad[o];
+    const bool bad = a.bad[robot * a.KT + k] != 0;            // the row sums of an infeasible trial are incomplete: unused
+    for (int tr = lane; tr < a.n_tr && !bad; tr += 32) {
+      const int row = robot * a.n_tr + tr;
+      size_t o = (size_t)k * a.rows_all + row;
+      e += a.lambda * row_plane_sum(a.row_e, o, a.pl_off, row) + a.lambda * a.row_e[o * EN_REC + EN_VMAX];
     }
     const double t = a.ttime[robot * a.KT + k];
     const double st = (a.dir && a.tstep) ? a.tstep[robot * a.KT + k] : 0.0;
@@ -251,7 +299,6 @@ __global__ void __launch_bounds__(32 * TOB_LS_TRIALS) k_robot_ls(RobotLsArgs b) 
       e += acc;
     }
     e = warp_sum(e);
-    bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) a.e_out[robot * a.KT + k] = bad ? INFINITY : e;
   }
   __syncthreads();
@@ -269,6 +316,7 @@ __global__ void __launch_bounds__(32 * TOB_LS_TRIALS) k_robot_ls(RobotLsArgs b) 
     }
   }
   double s = b.tstep[u * KT + kte - 1] * 0.8;        // continue the ladder below the last rung that was evaluated
+  for (int k = 1; k < KT; k++) a.bad[u * KT + k] = 0;   // the trial slots are laid out anew: clear their infeasibility flags
   for (int k = 1; k < KT; k++) {
     b.tstep[u * KT + k] = s;
     // unfused like k_ls_init (api.cu is built without FMA contraction, this file with): a rung must get the same trial time
@@ -279,31 +327,45 @@ __global__ void __launch_bounds__(32 * TOB_LS_TRIALS) k_robot_ls(RobotLsArgs b) 
   atomicAdd(&b.dc->ls_pending[b.slot], 1);
 }
 
+// CTAs per row of an energy launch: heavy rows need their virtual warps side by side when the launch has few rows
+// (latency regime, a shard of a batch); with very many rows the grid is large anyway
+static int energy_vl(tob_ctx* c, int nrows) {
+  if (const char* e = getenv("TRAJOPT_B200_EN_VL")) { int v = atoi(e); if (v >= 1 && v <= EN_VMAX) return v; }
+  return nrows >= 32768 ? 4 : EN_VMAX;
+}
+
+static int energy_buffers(tob_ctx* c, int KT) {
+  TOB_CUDA(c, c->row_e.ensure((size_t)EN_REC * c->rows_all() * KT));
+  TOB_CUDA(c, c->row_bad.ensure((size_t)c->n_robots() * TOB_LS_TRIALS + 1));
+  return 0;
+}
+
 // Energies of trial points k0..k1-1 of robots [rb,re): trial spline = s_spline + tstep[u*KT+k]*dir, time ttime[u*KT+k].
 // dir/tstep may be null (current point).  e_dev: robots x KT.
 int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* tstep, const double* ttime, int KT, int k0,
                   int k1, double* e_dev) {
   const int rows_all = c->rows_all();
-  TOB_CUDA(c, c->row_e.ensure((size_t)2 * rows_all * KT));
-  TOB_CUDA(c, c->row_bad.ensure((size_t)rows_all * KT));
+  TOB_TRY(energy_buffers(c, KT));
+  TOB_CUDA(c, cudaMemsetAsync(c->row_bad.p + (size_t)rb * KT, 0, (size_t)(re - rb) * KT * sizeof(int), c->stream));
   EnergyArgs a;
   a.spline = c->s_spline.p; a.dir = dir; a.tstep = tstep; a.ttime = ttime; a.basis = c->d_basis.p;
   a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p;
   a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
   a.n_tr = c->n_tr; a.res = c->prm.res; a.T = c->T; a.row_begin = rb * c->n_tr; a.rows_all = rows_all; a.KT = KT; a.k0 = k0;
-  a.row_e = c->row_e.p; a.row_bad = c->row_bad.p; a.done = nullptr; a.dc = c->dc.p;
+  a.row_e = c->row_e.p; a.bad = c->row_bad.p; a.done = nullptr; a.dc = c->dc.p;
   const int nrows = (re - rb) * c->n_tr, nk = k1 - k0;
+  a.VL = energy_vl(c, nrows);
   {
     Prof prof(c, K_ROW_ENERGY);
     a.nk = nk;
     if (nk > EN_MAXT) return fail_msg(c, "energy_trials: too many trial points in one launch");
-    k_row_energy<<<nrows, 32 * nk, 0, c->stream>>>(a);
+    k_row_energy<<<dim3(nrows, a.VL), 32 * nk, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
   RobotEnergyArgs b;
   b.spline = c->s_spline.p; b.dir = dir; b.tstep = tstep; b.ttime = ttime;
   b.pslack = c->s_pslack.p; b.tslack = c->s_tslack.p; b.plambda = c->s_plambda.p; b.tlambda = c->s_tlambda.p;
-  b.convert = c->d_convert.p; b.row_e = c->row_e.p; b.row_bad = c->row_bad.p;
+  b.convert = c->d_convert.p; b.row_e = c->row_e.p; b.pl_off = c->pl_off.p; b.bad = c->row_bad.p;
   b.lambda = c->prm.lambda; b.mu = c->prm.mu; b.n_tr = c->n_tr; b.P = c->prm.piece_num; b.T = c->T; b.robot_begin = rb;
   b.rows_all = rows_all; b.KT = KT; b.k0 = k0; b.e_out = e_dev;
   {
@@ -311,6 +373,14 @@ int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* t
     k_robot_energy<<<dim3(re - rb, nk), 128, 0, c->stream>>>(b);
     TOB_LAUNCH_CHECK(c);
   }
+  return 0;
+}
+
+// the infeasibility flags of robots [rb,re) start cleared at the beginning of a line search (k_robot_ls clears the slots it
+// lays out anew for the following rounds)
+int line_search_begin(tob_ctx* c, int rb, int re) {
+  TOB_TRY(energy_buffers(c, TOB_LS_TRIALS));
+  TOB_CUDA(c, cudaMemsetAsync(c->row_bad.p + (size_t)rb * TOB_LS_TRIALS, 0, (size_t)(re - rb) * TOB_LS_TRIALS * sizeof(int), c->stream));
   return 0;
 }
 
@@ -322,17 +392,19 @@ int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int kte
   a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p;
   a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
   a.n_tr = c->n_tr; a.res = c->prm.res; a.T = c->T; a.row_begin = rb * c->n_tr; a.rows_all = rows_all; a.KT = KT; a.k0 = k0;
-  a.row_e = c->row_e.p; a.row_bad = c->row_bad.p; a.done = c->s_done.p; a.dc = c->dc.p;
+  a.row_e = c->row_e.p; a.bad = c->row_bad.p; a.done = c->s_done.p; a.dc = c->dc.p;
+  const int nrows = (re - rb) * c->n_tr;
+  a.VL = energy_vl(c, nrows);
   {
     Prof prof(c, K_ROW_ENERGY);
     a.nk = kte - k0;
-    k_row_energy<<<(re - rb) * c->n_tr, 32 * (kte - k0), 0, c->stream>>>(a);
+    k_row_energy<<<dim3(nrows, a.VL), 32 * (kte - k0), 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
   RobotLsArgs b;
   b.e.spline = c->s_spline.p; b.e.dir = c->s_dir.p; b.e.tstep = c->s_tstep.p; b.e.ttime = c->s_ttime.p;
   b.e.pslack = c->s_pslack.p; b.e.tslack = c->s_tslack.p; b.e.plambda = c->s_plambda.p; b.e.tlambda = c->s_tlambda.p;
-  b.e.convert = c->d_convert.p; b.e.row_e = c->row_e.p; b.e.row_bad = c->row_bad.p;
+  b.e.convert = c->d_convert.p; b.e.row_e = c->row_e.p; b.e.pl_off = c->pl_off.p; b.e.bad = c->row_bad.p;
   b.e.lambda = c->prm.lambda; b.e.mu = c->prm.mu; b.e.n_tr = c->n_tr; b.e.P = c->prm.piece_num; b.e.T = c->T; b.e.robot_begin = rb;
   b.e.rows_all = rows_all; b.e.KT = KT; b.e.k0 = k0; b.e.e_out = c->s_etr.p;
   b.wolfe = c->s_wolfe.p; b.ptime = c->s_ptime.p; b.tdir = c->s_tdir.p;

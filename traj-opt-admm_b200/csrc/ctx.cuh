@@ -56,6 +56,7 @@ struct DBuf {
 #define TOB_OVF_CAND 1u      // broadphase produced more candidates than cand_cap
 #define TOB_OVF_LIVE 8u      // persistent-plane mode: live planes + new planes exceed live_cap
 #define TOB_OVF_REMOTE 16u   // sharded: another rank overflowed (every rank repeats the iteration, only the flagged ones grow)
+#define TOB_OVF_RETRY (TOB_OVF_CAND | TOB_OVF_LIVE | TOB_OVF_REMOTE)   // the iteration is repeated: whatever ran on the incomplete plane set is void
 #define TOB_ERR_SOLVE 32u    // Newton system not positive definite (Cholesky pivot / Schur complement <= 0): nothing is committed
 #define TOB_LS_MAXROUNDS 8   // most Armijo rounds launched ahead of the host (the count is a run-time choice, see ls_policy)
 struct DevCounts {
@@ -183,8 +184,8 @@ struct tob_ctx {
   tob::DBuf<uint32_t> self_hits;      // inter-robot CCD: colliding (slot, pair) ids [cap] + count [2] + the sorted list [cap]; cap = all tasks
 
   // energy / gradient / solve scratch
-  tob::DBuf<double> row_e;
-  tob::DBuf<int> row_bad;
+  tob::DBuf<double> row_e;            // trials x rows x TOB_EN_REC
+  tob::DBuf<int> row_bad;             // robots x TOB_LS_TRIALS: trial infeasible (some d <= 0)
   tob::DBuf<double> row_terms;
   tob::DBuf<double> pc_g, pc_h;
   tob::DBuf<int> pc_flag;
@@ -338,6 +339,8 @@ int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* t
 // one Armijo round of robots [rb,re) (decoupled): trial energies k0..kte-1 (kte <= TOB_LS_TRIALS) + the ladder decision, robots that
 // are already done are skipped on the device; robots still backtracking are counted in dc->ls_pending[slot]
 int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int kte, int slot);
+int line_search_begin(tob_ctx* c, int rb, int re);   // clears the infeasibility flags of the robots' trial slots
+#define TOB_EN_REC 9   // doubles per (trial, row) in row_e: 8 plane-energy partials + the bound energy (barrier.cu: EN_REC)
 int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd);
 int row_blocks(tob_ctx* c, int tr, int which, double* out_dev);
 // comm.cu: in-place exchange of robot-indexed device arrays between the ranks (no-op when the context is not sharded)

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
     W += t * s_gt;
     a.wolfe[robot] = -W;
     a.status[robot] = s_fail;
-    if (s_fail && a.dc) atomicOr(&a.dc->overflow, TOB_ERR_SOLVE);
+    if (s_fail && a.dc && !(a.dc->overflow & TOB_OVF_RETRY)) atomicOr(&a.dc->overflow, TOB_ERR_SOLVE);
   }
 }
 
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(1024) k_solve_bcr(BcrArgs a) {
       double* o = a.cpl_part + 7 * (size_t)robot;
       o[0] = AY; o[1] = AZ; o[2] = GG; o[3] = s_h; o[4] = s_gt; o[5] = ZG; o[6] = YG;
       a.status[robot] = s_fail;
-      if (s_fail && a.dc) atomicOr(&a.dc->overflow, TOB_ERR_SOLVE);
+      if (s_fail && a.dc && !(a.dc->overflow & TOB_OVF_RETRY)) atomicOr(&a.dc->overflow, TOB_ERR_SOLVE);
     }
     double* o = a.cpl_zyg + (size_t)robot * N * BS * 2;
     for (int e = tid; e < N * BS; e += blockDim.x) {
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(1024) k_solve_bcr(BcrArgs a) {
     W += t * s_gt;
     a.wolfe[robot] = -W;
     a.status[robot] = s_fail;
-    if (s_fail && a.dc) atomicOr(&a.dc->overflow, TOB_ERR_SOLVE);
+    if (s_fail && a.dc && !(a.dc->overflow & TOB_OVF_RETRY)) atomicOr(&a.dc->overflow, TOB_ERR_SOLVE);
   }
 }
 
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(256) k_couple_finish(const double* __restrict_
       AY += p[0]; AZ += p[1]; GG += p[2]; HT += p[3]; GT += p[4]; ZG += p[5]; YG += p[6];
     }
     const double schur = HT - AY;
-    if (!(schur > 0)) atomicOr(&dc->overflow, TOB_ERR_SOLVE);
+    if (!(schur > 0) && !(dc->overflow & TOB_OVF_RETRY)) atomicOr(&dc->overflow, TOB_ERR_SOLVE);
     const double t = (AZ - GT) / schur;
     s_t = t;
     const double gn = sqrt(GG + GT * GT) / double(U);
