@@ -118,10 +118,13 @@ __global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
     const uint32_t stride = 32u * (uint32_t)V;
     double4 nxt = make_double4(0, 0, 0, 0);
     if (p < p1) nxt = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * p);
-    for (uint32_t base = p0 + (uint32_t)v * 32u; base < p1; base += stride, p += stride) {
+    uint32_t trip = 0;
+    for (uint32_t base = p0 + (uint32_t)v * 32u; base < p1; base += stride, p += stride, trip++) {
       const double4 pl = nxt;
       const bool have = p < p1;
       if (p + stride < p1) nxt = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * (p + stride));
+      // the flag of the trial is polled every fourth chunk; the load is issued here and consumed after the distances
+      const int seen = (trip & 3u) == 0 ? *flag : 0;
       double d[6];
       bool bad = false;
       unsigned cnt = 0;
@@ -135,12 +138,28 @@ __global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
         cnt += __popc(bm);             // uniform
       }
       n_pl += have;
-      if (__any_sync(0xffffffffu, bad) || *flag) { stop = true; if (lane == 0) *flag = 1; break; }
+      if (__any_sync(0xffffffffu, bad) || seen) { stop = true; if (lane == 0) *flag = 1; break; }
       __syncwarp();
-      for (unsigned t = lane; t < cnt; t += 32) {
-        const double dd = q[t], dm = dd - m;
-        e += (dm * dm) * log(dd * inv_m);
+      // the queued terms on dense lanes, 2 / 4 / 6 independent logarithm chains at a time (an FP64 result takes ~40 cycles
+      // here: one chain after the other would cost a chunk 3x the latency); a slot beyond the queue evaluates log(1) * 0
+#define EN_TERM(r)                                              \
+  double e##r;                                                  \
+  {                                                             \
+    const unsigned t = lane + 32u * r;                          \
+    const double dd = t < cnt ? q[t] : m, dm = dd - m;          \
+    e##r = (dm * dm) * log(dd * inv_m);                         \
+  }
+      if (cnt > 128u) {
+        EN_TERM(0) EN_TERM(1) EN_TERM(2) EN_TERM(3) EN_TERM(4) EN_TERM(5)
+        e += ((e0 + e1) + (e2 + e3)) + (e4 + e5);
+      } else if (cnt > 64u) {
+        EN_TERM(0) EN_TERM(1) EN_TERM(2) EN_TERM(3)
+        e += (e0 + e1) + (e2 + e3);
+      } else if (cnt > 0u) {
+        EN_TERM(0) EN_TERM(1)
+        e += e0 + e1;
       }
+#undef EN_TERM
       n_act += cnt;                    // counted once per warp below (uniform value)
       __syncwarp();
     }
