@@ -272,3 +272,28 @@ def test_multi_executable_links_unchanged_and_matches(tmp_path, decouple):
     assert len(out["ref"]["ccd len"]) == sc["uav_num"] and len(out["dev"]["ccd len"]) == sc["uav_num"]
     for key in ("ccd time", "ccd len"):
         assert np.allclose(out["dev"][key], out["ref"][key], rtol=2e-2, atol=0), key
+
+
+@pytest.mark.parametrize("decouple", [1, 0])
+def test_multi_executable_on_two_gpus_equals_one_gpu(tmp_path, decouple):
+    """Main/multiPathPlanning3D.cpp, unchanged, with TRAJOPT_B200_GPUS=2: the session shards the robots over two GPUs (one
+    context + one host thread per GPU, NCCL exchange inside the library) and must reproduce the one-GPU run exactly:
+    same stopping iteration, same printed trajectory lengths / durations"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = os.path.join(HOST, "multiPathPlanning3D")
+    if not os.path.exists(exe):
+        pytest.skip("executable not built (needs /root/reference at build time)")
+    sc = scenes.cross(n_pts=4000, seed=3)
+    out = {}
+    for gpus in (1, 2):
+        root = str(tmp_path / ("g%d_%d" % (gpus, decouple)))
+        scenes.write_reference_files(sc, root, "cross.obj", {"stop": 1.0 if decouple else 0.5, "exit": 1, "decouple": decouple})
+        env = dict(os.environ, TRAJOPT_B200_GPUS=str(gpus))
+        r = subprocess.run([exe, "cross.obj"], cwd=root, capture_output=True, text=True, timeout=900, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        vals = {key: re.findall(r"^%s:([-+0-9.eE]+)" % key, r.stdout, flags=re.M) for key in ("ccd time", "ccd len")}
+        out[gpus] = (vals, _result_iter(os.path.join(root, "result", "cross.obj_result_file_multi.txt")))
+    assert out[1][1] is not None and out[1][1] > 2
+    assert out[1] == out[2]

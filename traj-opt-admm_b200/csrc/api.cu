@@ -1391,7 +1391,9 @@ int tob_states_download(tob_ctx* c, tob_state* states, int n_robots) {
   TOB_CUDA(c, cudaMemcpyAsync(h_pl, c->s_plambda.p, U * n_ps * sizeof(double), cudaMemcpyDeviceToHost, st));
   TOB_CUDA(c, cudaMemcpyAsync(h_tl, c->s_tlambda.p, U * n_ts * sizeof(double), cudaMemcpyDeviceToHost, st));
   TOB_CUDA(c, cudaStreamSynchronize(st));
-  for (size_t u = 0; u < U; u++) {
+  // a sharded context returns the robots it owns (the other slots of `states` are left untouched: their owners write them)
+  const size_t ub = c->sharded() ? (size_t)c->own_begin : 0, ue = c->sharded() ? (size_t)c->own_end : U;
+  for (size_t u = ub; u < ue; u++) {
     memcpy(states[u].spline, h_sp + u * n_sp, n_sp * sizeof(double));
     *states[u].piece_time = h_pt[u];
     memcpy(states[u].p_slack, h_ps + u * n_ps, n_ps * sizeof(double));

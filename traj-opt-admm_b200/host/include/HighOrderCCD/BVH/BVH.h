@@ -30,7 +30,7 @@ class BVH {
     tob_host::Session& S = tob_host::Session::get();
     if (V.cols() != 3) throw std::runtime_error("BVH::InitPointcloud: V must be n x 3");
     Eigen::MatrixXd Vc = V;   // contiguous column-major copy (V may be an expression)
-    S.check(tob_cloud_upload(S.ctx(), Vc.data(), (uint32_t)Vc.rows()), "tob_cloud_upload");
+    S.upload_cloud(Vc.data(), (uint32_t)Vc.rows());     // replicated on every GPU of the session
   }
 
   // BVH.cpp:95-133: points within d of the box of a 2-point edge

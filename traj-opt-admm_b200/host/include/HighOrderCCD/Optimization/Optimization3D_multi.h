@@ -133,9 +133,7 @@ class Optimization3D_multi {
       st[i].spline = spline_list[i].data(); st[i].p_slack = p_slack_list[i].data(); st[i].t_slack = t_slack_list[i].data();
       st[i].p_lambda = p_lambda_list[i].data(); st[i].t_lambda = t_lambda_list[i].data();
     }
-    double gn = 0;
-    S.check(tob_optimization(S.ctx(), st.data(), uav_num, mode, &gn), "tob_optimization");
-    gnorm = gn;
+    gnorm = S.optimization(st.data(), uav_num, mode);   // all GPUs of the session (TRAJOPT_B200_GPUS), robots sharded
     double w = 0;
     if (tob_last_wolfe(S.ctx(), &w) == 0) wolfe = w;
   }

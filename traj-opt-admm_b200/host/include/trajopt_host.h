@@ -6,7 +6,11 @@
 // reference tree.  Session::sync() mirrors the globals the hot path reads into the device context whenever they change:
 //   piece_num, res, uav_num, is_optimal_plane, lambda, margin, offset, mu, vel_limit, acc_limit, ks, kt   -> tob_set_params
 //   subdivide_tree (basis + parameter range), convert_list, M_dynamic, kdop_matrix                      -> tob_set_tables
-// One process-wide context (Main constructs only a BVH object and passes it around).
+// One process-wide session (Main constructs only a BVH object and passes it around).  It owns one
+// context per GPU: TRAJOPT_B200_GPUS=N (default 1) makes the multi-UAV iterations of Main/multiPathPlanning3D.cpp run with
+// the robots sharded over N GPUs -- one context and one host thread per GPU, the per-iteration exchange on NCCL inside the
+// library (tob_nccl_init_all) -- without any change to the caller; the result is bitwise the one of a single GPU.  Function-
+// level entry points always use the first context.
 // Errors of the C ABI become std::runtime_error: there is no CPU fallback.
 #ifndef TRAJOPT_HOST_H
 #define TRAJOPT_HOST_H
@@ -15,6 +19,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "HighOrderCCD/Utils/CCDUtils.h"
@@ -33,9 +38,40 @@ class Session {
     return s;
   }
   tob_ctx* ctx() { return ctx_; }
+  int gpus() const { return (int)all_.size(); }
 
   void check(int rc, const char* what) {
     if (rc) throw std::runtime_error(std::string(what) + ": " + tob_last_error(ctx_));
+  }
+
+  // BVH::InitPointcloud: the cloud (and its LBVH) is replicated on every GPU of the session
+  void upload_cloud(const double* V, uint32_t n) {
+    for (size_t g = 0; g < all_.size(); g++)
+      if (tob_cloud_upload(all_[g], V, n)) throw std::runtime_error(std::string("tob_cloud_upload: ") + tob_last_error(all_[g]));
+  }
+
+  // one multi-UAV ADMM iteration over all GPUs of the session: every context gets all the states (it uses the robots it
+  // owns) and writes back the robots it owns; the threads only exist for the duration of the call
+  double optimization(tob_state* st, int n_robots, int mode) {
+    const int G = (int)all_.size();
+    if (G == 1 || n_robots < G) {
+      double gn = 0;
+      check(tob_optimization(ctx_, st, n_robots, mode, &gn), "tob_optimization");
+      return gn;
+    }
+    if (!sharded_) {
+      if (tob_nccl_init_all(all_.data(), G)) throw std::runtime_error(std::string("tob_nccl_init_all: ") + tob_last_error(all_[0]));
+      sharded_ = true;
+    }
+    std::vector<int> rc(G, 0);
+    std::vector<double> gn(G, 0.0);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; g++)
+      th.emplace_back([&, g]() { rc[g] = tob_optimization(all_[g], st, n_robots, mode, &gn[g]); });
+    for (auto& t : th) t.join();
+    for (int g = 0; g < G; g++)
+      if (rc[g]) throw std::runtime_error(std::string("tob_optimization (GPU ") + std::to_string(g) + "): " + tob_last_error(all_[g]));
+    return gn[0];
   }
 
   // globals -> device (cheap compare; uploads only on change)
@@ -47,7 +83,8 @@ class Session {
     p.lambda = lambda; p.margin = margin; p.offset = offset; p.mu = mu;
     p.vel_limit = vel_limit; p.acc_limit = acc_limit; p.ks = ks; p.kt = kt;
     if (!have_params_ || std::memcmp(&p, &last_, sizeof(p)) != 0) {
-      check(tob_set_params(ctx_, &p), "tob_set_params");
+      for (size_t g = 0; g < all_.size(); g++)
+        if (tob_set_params(all_[g], &p)) throw std::runtime_error(std::string("tob_set_params: ") + tob_last_error(all_[g]));
       last_ = p; have_params_ = true; tables_.clear();
     }
     const size_t n_tr = (size_t)piece_num * res;
@@ -68,7 +105,8 @@ class Session {
     std::memcpy(md, M_dynamic.data(), 36 * sizeof(double));
     std::memcpy(kd, kdop_matrix.data(), 147 * sizeof(double));
     if (t != tables_) {
-      check(tob_set_tables(ctx_, basis, weight, conv, md, kd), "tob_set_tables");
+      for (size_t g = 0; g < all_.size(); g++)
+        if (tob_set_tables(all_[g], basis, weight, conv, md, kd)) throw std::runtime_error(std::string("tob_set_tables: ") + tob_last_error(all_[g]));
       tables_.swap(t);
     }
   }
@@ -78,18 +116,27 @@ class Session {
   void ensure_cloud() {
     if (tob_cloud_size(ctx_) == 0) {
       const double far_away[3] = {1e300, 1e300, 1e300};
-      check(tob_cloud_upload(ctx_, far_away, 1), "tob_cloud_upload");
+      upload_cloud(far_away, 1);
     }
   }
 
  private:
   Session() {
     const char* dev = std::getenv("TRAJOPT_B200_DEVICE");
-    if (tob_ctx_create(dev ? std::atoi(dev) : 0, &ctx_)) throw std::runtime_error(std::string("tob_ctx_create: ") + tob_last_error(nullptr));
+    const char* ng = std::getenv("TRAJOPT_B200_GPUS");
+    const int first = dev ? std::atoi(dev) : 0, n = ng && std::atoi(ng) > 1 ? std::atoi(ng) : 1;
+    for (int g = 0; g < n; g++) {
+      tob_ctx* c = nullptr;
+      if (tob_ctx_create(first + g, &c)) throw std::runtime_error(std::string("tob_ctx_create: ") + tob_last_error(nullptr));
+      all_.push_back(c);
+    }
+    ctx_ = all_[0];
   }
-  ~Session() { tob_ctx_destroy(ctx_); }
+  ~Session() { for (size_t g = 0; g < all_.size(); g++) tob_ctx_destroy(all_[g]); }
   Session(const Session&);
-  tob_ctx* ctx_ = nullptr;
+  tob_ctx* ctx_ = nullptr;            // first context: function-level entry points
+  std::vector<tob_ctx*> all_;         // one context per GPU
+  bool sharded_ = false;
   tob_params last_;
   bool have_params_ = false;
   std::vector<double> tables_;
