@@ -302,6 +302,14 @@ class _Base:
             return self.edge_collision(edge, d, int(n))
         return ids[:n]
 
+    def read_obj(self, path, cap=1 << 16):
+        """Mesh::readOBJ of the reference (vertex block of an OBJ file, with its quirks)"""
+        V = np.zeros((cap, 3), order="F")
+        n = self._f("read_obj", C.c_long)(str(path).encode(), _d(V), C.c_long(cap))
+        if n > cap:
+            return self.read_obj(path, int(n))
+        return V[:n].copy(order="F")
+
     def gjk_dcd(self, A, B, d):
         A = F(np.atleast_2d(A)); B = F(np.atleast_2d(B))
         return bool(self._f("gjk_dcd", C.c_int)(_d(A), C.c_int(A.shape[0]), _d(B), C.c_int(B.shape[0]), C.c_double(d)))

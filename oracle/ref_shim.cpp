@@ -635,4 +635,13 @@ int ref_gjk_dcd(const double* A, int na, const double* B, int nb, double d) {
   return CCD::GJKDCD(map_mat(A, na, 3), map_mat(B, nb, 3), d) ? 1 : 0;
 }
 
+// Mesh::readOBJ (HighOrderCCD/Utils/CCDUtils.h:317-391): returns the vertex count, fills V (n x 3 col-major) up to cap rows
+long ref_read_obj(const char* path, double* V, long cap) {
+  Eigen::MatrixXd M;
+  Mesh::readOBJ(std::string(path), M);
+  const long n = M.rows();
+  for (long i = 0; i < n && i < cap; i++) for (int k = 0; k < 3; k++) V[i + cap * k] = M(i, k);
+  return n;
+}
+
 }  // extern "C"

@@ -102,6 +102,23 @@ def rawcsv(src, dst, workload=None):
             traffic[k.replace("tob::", "")] = tot
             f.write("  dram bytes per launch (read+write)                                   %.0f\n\n" % tot)
     if workload:
+        # per-kernel measured columns for bench.py (`kernels[*].gbs_dram_ncu`, `fp64_pipe_active_pct_ncu`, `roofline.traffic`)
+        mj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_metrics.json")
+        cur = json.load(open(mj)) if os.path.exists(mj) else {}
+        ent = {}
+        for k, lst in per.items():
+            def mean(m):
+                vals = [_num(d[m]) for d in lst if m in d and _num(d[m]) is not None]
+                return sum(vals) / len(vals) if vals else None
+            ent[k.replace("tob::", "")] = {"dram_bytes": traffic[k.replace("tob::", "")],
+                                           "fp64_pipe_pct": mean("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                                           "warps_active_pct": mean("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                                           "lanes_per_inst": mean("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                                           "registers": mean("launch__registers_per_thread"), "launches_captured": len(lst)}
+        cur[workload] = ent
+        cur["_note"] = ("per launch, from one `ncu --set full --clock-control none` capture per round (profiles/run_ncu_r02.sh): "
+                        "dram_bytes = dram__bytes_read.sum + dram__bytes_write.sum; keyed by bench workload (batch<problems on the GPU>), then kernel")
+        json.dump(cur, open(mj, "w"), indent=1, sort_keys=True)
         tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_traffic.json")
         cur = json.load(open(tj)) if os.path.exists(tj) else {}
         cur[workload] = traffic
