@@ -416,9 +416,17 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(pe, op=dist.ReduceOp.SUM)
     total_ms, e2e_s = float(tt[0]), float(tt[1])
-    if rank != 0:
+
+    def teardown():
+        # orderly: the context (and the NCCL communicator it owns) goes first, on every rank, then torch's process group
+        sys.stdout.flush()
+        s.close()
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
+
+    if rank != 0:
+        teardown()
         return
 
     # sharded: ONE problem over all ranks (strong); batch: every problem of every rank iterates once per step (strong: the
@@ -509,9 +517,8 @@ def run_ours(args):
         else:
             sc["coupled"] = coupled
             out["cpu_baseline"] = cpu_single(sc, P, budget_s=25.0, max_iters=6)
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    OUT.emit(json.dumps(out))
+    teardown()
 
 
 def run_reference(args):
@@ -535,10 +542,29 @@ def run_reference(args):
            "config": describe(args, world),
            "cpu_baseline": cb,
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    OUT.emit(json.dumps(out))
+
+
+class QuietStdout:
+    """the driver reads ONE JSON line from stdout: whatever libraries print there while the bench runs (NCCL's version banner
+    at the first communicator, ...) is sent to stderr; the result line goes to the real stdout"""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.fd = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.fd, (line + "\n").encode())
+
+
+OUT = None
 
 
 def main():
+    global OUT
+    OUT = QuietStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -287,7 +287,8 @@ static int separate_resident(tob_ctx* c, int rb, int re, int with_self) {
 // round r >= 1 evaluates trials 1..8 (round 0 also trial 0 = the current point, the "e" of the reference)
 static int ls_round(tob_ctx* c, int rb, int re, int wolfe_idx, bool coupled, int round, int slot) {
   cudaStream_t st = c->stream;
-  if (!coupled) return line_search_round(c, rb, re, wolfe_idx, round == 0 ? 0 : 1, round == 0 ? c->ls_kte0 : c->ls_kte, slot);
+  if (!coupled) return line_search_round(c, rb, re, wolfe_idx, round == 0 ? 0 : 1, round == 0 ? c->ls_kte0 : c->ls_kte, slot,
+                                         round == 0 && !c->ls_e0_ready ? 0 : 1);
   TOB_TRY(energy_trials(c, rb, re, c->s_dir.p, c->s_tstep.p, c->s_ttime.p, TOB_LS_TRIALS, round == 0 ? 0 : 1, TOB_LS_TRIALS, c->s_etr.p));
   TOB_TRY(exchange_robots(c, c->s_etr.p, TOB_LS_TRIALS, sizeof(double)));   // joint Armijo: every rank sums all robots in robot order
   k_armijo_coupled<<<1, 32, 0, st>>>(c->n_robots(), c->s_etr.p, c->s_wolfe.p, c->s_ptime.p, c->s_tdir.p, c->s_step.p, c->s_ptrial.p,
@@ -428,6 +429,7 @@ static int iterate_launch(tob_ctx* c, int mode) {
     wolfe_idx = U > 1 ? U - 1 : -1;
   }
   if (!coupled) TOB_TRY(line_search_begin(c, rb, re));
+  c->ls_e0_ready = !coupled;         // gradient_blocks ran at this very point with these planes: slot 0 holds E(x)
   TOB_TRY(ls_launch_ahead(c, rb, re, wolfe_idx, coupled));
   // (5) step, slack + dual: guarded on the device (see iterate_once)
   TOB_TRY(apply_step(c, rb, re, true, coupled));
@@ -1260,6 +1262,7 @@ int tob_line_search(tob_ctx* c, int robot, tob_state* st, const double* directio
                                      c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p, c->ls_rounds);
   TOB_LAUNCH_CHECK(c);
   TOB_TRY(line_search_begin(c, robot, robot + 1));
+  c->ls_e0_ready = false;            // function-level call: the starting point is evaluated by the energy kernel
   TOB_TRY(line_search(c, robot, robot + 1, -1));
   TOB_CUDA(c, cudaMemcpyAsync(st->spline, c->s_spline.p + (size_t)robot * 3 * T, 3 * T * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   TOB_CUDA(c, cudaMemcpyAsync(st->piece_time, c->s_ptime.p + robot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));

@@ -78,15 +78,20 @@ __global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
   const int lane = threadIdx.x & 31, kk = threadIdx.x >> 5, k = a.k0 + kk;
   __shared__ double sPall[EN_MAXT][18], sBzall[EN_MAXT][18];
   __shared__ double sQ[EN_MAXT][192];          // in-band terms of one chunk (32 planes x 6 control points)
-  if (a.done && a.done[robot]) return;
-  if (a.dc->overflow) return;      // the plane CSR of this iteration was not built: the host grows the buffers and retries
+  // all the words that decide whether this CTA has anything to do are loaded before the first test (one memory round trip
+  // for the many CTAs of a launch that leave at once: rows with few planes have V = 1, robots that are done, ...)
   const uint32_t p0 = a.pl_off[row], p1 = a.pl_off[row + 1];
+  const int is_done = a.done ? a.done[robot] : 0;
+  const uint32_t ovf = a.dc->overflow;
+  const int seen0 = a.bad[robot * a.KT + k];    // plain (cached) load: a stale 0 only costs the work the flag would have saved
   const int V = en_vwarps(p1 - p0);
   const int g = blockIdx.y;
   if (g >= V) return;              // nothing for this CTA (virtual warp 0 also carries the bound terms)
+  if (is_done) return;
+  if (ovf) return;                 // the plane CSR of this iteration was not built: the host grows the buffers and retries
   volatile int* flag = a.bad + robot * a.KT + k;
   double* out = a.row_e + ((size_t)k * a.rows_all + row) * EN_REC;
-  if (*flag) return;               // the trial is already known to be infeasible: its energy is +inf whatever this row adds
+  if (seen0) return;               // the trial is already known to be infeasible: its energy is +inf whatever this row adds
   double* sP = sPall[kk];
   double* sBz = sBzall[kk];
   if (lane < 18) {
@@ -123,8 +128,9 @@ __global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
       const double4 pl = nxt;
       const bool have = p < p1;
       if (p + stride < p1) nxt = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * (p + stride));
-      // the flag of the trial is polled every fourth chunk; the load is issued here and consumed after the distances
-      const int seen = (trip & 3u) == 0 ? *flag : 0;
+      // the flag of the trial is polled every eighth chunk (an L2 round trip on a word that every warp of the trial reads):
+      // rows of fewer than 8 chunks per virtual warp never poll; the load is issued here and consumed after the distances
+      const int seen = (trip & 7u) == 7u ? *flag : 0;
       double d[6];
       bool bad = false;
       unsigned cnt = 0;
@@ -140,26 +146,16 @@ __global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
       n_pl += have;
       if (__any_sync(0xffffffffu, bad) || seen) { stop = true; if (lane == 0) *flag = 1; break; }
       __syncwarp();
-      // the queued terms on dense lanes, 2 / 4 / 6 independent logarithm chains at a time (an FP64 result takes ~40 cycles
-      // here: one chain after the other would cost a chunk 3x the latency); a slot beyond the queue evaluates log(1) * 0
-#define EN_TERM(r)                                              \
-  double e##r;                                                  \
-  {                                                             \
-    const unsigned t = lane + 32u * r;                          \
-    const double dd = t < cnt ? q[t] : m, dm = dd - m;          \
-    e##r = (dm * dm) * log(dd * inv_m);                         \
-  }
-      if (cnt > 128u) {
-        EN_TERM(0) EN_TERM(1) EN_TERM(2) EN_TERM(3) EN_TERM(4) EN_TERM(5)
-        e += ((e0 + e1) + (e2 + e3)) + (e4 + e5);
-      } else if (cnt > 64u) {
-        EN_TERM(0) EN_TERM(1) EN_TERM(2) EN_TERM(3)
-        e += (e0 + e1) + (e2 + e3);
-      } else if (cnt > 0u) {
-        EN_TERM(0) EN_TERM(1)
-        e += e0 + e1;
+      // the queued terms on dense lanes, three independent logarithm chains at a time (an FP64 result takes ~40 cycles here:
+      // one chain after the other would cost a chunk 3x the latency; six at a time cost registers, i.e. resident warps);
+      // a slot beyond the queue evaluates log(1) * 0
+      for (unsigned t0 = lane; t0 < cnt + lane; t0 += 96u) {      // uniform trip count: ceil(cnt / 96)
+        const unsigned t1 = t0 + 32u, t2 = t0 + 64u;
+        const double d0 = t0 < cnt ? q[t0] : m, d1 = t1 < cnt ? q[t1] : m, d2 = t2 < cnt ? q[t2] : m;
+        const double m0 = d0 - m, m1 = d1 - m, m2 = d2 - m;
+        const double l0 = log(d0 * inv_m), l1 = log(d1 * inv_m), l2 = log(d2 * inv_m);
+        e += ((m0 * m0) * l0 + (m1 * m1) * l1) + (m2 * m2) * l2;
       }
-#undef EN_TERM
       n_act += cnt;                    // counted once per warp below (uniform value)
       __syncwarp();
     }
@@ -403,21 +399,23 @@ int line_search_begin(tob_ctx* c, int rb, int re) {
   return 0;
 }
 
-int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int kte, int slot) {
+// k0e: first trial the ENERGY launch evaluates (k0, or k0 + 1 = 1 when slot 0 was already written by the gradient pass at
+// the same point); the robot kernel always sums trials k0 .. kte-1
+int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int kte, int slot, int k0e) {
   const int rows_all = c->rows_all(), KT = TOB_LS_TRIALS;
-  if (kte < 2 || kte > KT || k0 >= kte) return fail_msg(c, "line_search_round: bad trial range");
+  if (kte < 2 || kte > KT || k0 >= kte || k0e < k0 || k0e >= kte) return fail_msg(c, "line_search_round: bad trial range");
   EnergyArgs a;
   a.spline = c->s_spline.p; a.dir = c->s_dir.p; a.tstep = c->s_tstep.p; a.ttime = c->s_ttime.p; a.basis = c->d_basis.p;
   a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p;
   a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
-  a.n_tr = c->n_tr; a.res = c->prm.res; a.T = c->T; a.row_begin = rb * c->n_tr; a.rows_all = rows_all; a.KT = KT; a.k0 = k0;
+  a.n_tr = c->n_tr; a.res = c->prm.res; a.T = c->T; a.row_begin = rb * c->n_tr; a.rows_all = rows_all; a.KT = KT; a.k0 = k0e;
   a.row_e = c->row_e.p; a.bad = c->row_bad.p; a.done = c->s_done.p; a.dc = c->dc.p;
   const int nrows = (re - rb) * c->n_tr;
   a.VL = energy_vl(c, nrows);
   {
     Prof prof(c, K_ROW_ENERGY);
-    a.nk = kte - k0;
-    k_row_energy<<<dim3(nrows, a.VL), 32 * (kte - k0), 0, c->stream>>>(a);
+    a.nk = kte - k0e;
+    k_row_energy<<<dim3(nrows, a.VL), 32 * (kte - k0e), 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
   RobotLsArgs b;
@@ -449,6 +447,10 @@ struct RowGradArgs {
   int n_tr, row_begin;
   double* terms;           // rows x ROW_REC
   DevCounts* dc;           // barrier_terms counter
+  // by-product: barrier energy of the CURRENT point (trial slot 0 of the line search that follows): the logarithms of the
+  // gradient are the logarithms of the energy, so the line search does not evaluate its starting point again
+  double* row_e;           // trials x rows_all x EN_REC (slot 0 is written), may be null
+  int rows_all;
 };
 
 __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
@@ -456,12 +458,13 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
   const int robot = row / a.n_tr, tr = row - robot * a.n_tr;
   __shared__ double sP[18];
   __shared__ double s_red[4][54];
-  __shared__ double s_gt[9], s_ht[9];
+  __shared__ double s_gt[9], s_ht[9], s_eb[9], s_en[4];
   if (a.dc->overflow) return;      // the plane CSR of this iteration was not built (see k_row_energy)
   if (threadIdx.x < 18) sP[threadIdx.x] = a.P[(size_t)18 * row + threadIdx.x];
   __syncthreads();
   const double w = a.weight[tr], m = a.margin, inv_m = 1.0 / m;
   double acc[54];
+  double en = 0;
   unsigned n_act = 0;
 #pragma unroll
   for (int i = 0; i < 54; i++) acc[i] = 0;
@@ -479,6 +482,7 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
       const double lg = log(act ? d * inv_m : 1.0), dm = act ? d - m : 0.0, id = 1.0 / (act ? d : 1.0);
       const double e1 = -w * (2 * dm * lg + dm * dm * id);
       const double e2 = -w * (2 * lg + 4 * dm * id - dm * dm * id * id);
+      en += (dm * dm) * lg;
       double* q = acc + 9 * j;
       q[0] += e2 * cxx; q[1] += e2 * cxy; q[2] += e2 * cxz; q[3] += e2 * cyy; q[4] += e2 * cyz; q[5] += e2 * czz;
       q[6] += e1 * pl.x; q[7] += e1 * pl.y; q[8] += e1 * pl.z;
@@ -493,14 +497,17 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
       double v = warp_sum(acc[i]);
       if (lane == 0) s_red[wp][i] = v;
     }
+    en = warp_sum(en);
+    if (lane == 0) s_en[wp] = en;
   } else {
     for (int i = lane; i < 54; i += 32) s_red[wp][i] = 0.0;
+    if (lane == 0) s_en[wp] = 0.0;
   }
   // bound terms, threads 0..8
   double* out = a.terms + (size_t)ROW_REC * row;
   if (threadIdx.x < 9) {
     const double t = a.ptime[robot];
-    double px, py, pz, dn, d, g_t = 0, h_t = 0, coef, e3k;
+    double px, py, pz, dn, d, g_t = 0, h_t = 0, coef, e3k, eb = 0;
     double M3[6] = {0, 0, 0, 0, 0, 0}, g3[3] = {0, 0, 0}, pg3[3] = {0, 0, 0};
     bool vel = threadIdx.x < 5;
     double val;   // v or a of the reference
@@ -523,6 +530,7 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
       double lg = log(d / m), dm = d - m;
       double e1 = -w * (2 * dm * lg + dm * dm / d);
       double e2 = -w * (2 * lg + 4 * dm / d - dm * dm / (d * d));
+      eb = -w * dm * dm * lg;
       if (vel) {
         g_t = e1 * val / (t * t);
         h_t = -2 * e1 * val / (t * t * t) + e2 * val * val / (t * t * t * t);
@@ -547,7 +555,7 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
     double* o = out + (size_t)TERM_SZ * (6 + threadIdx.x);
     for (int i = 0; i < 6; i++) o[i] = M3[i];
     for (int i = 0; i < 3; i++) { o[6 + i] = g3[i]; o[9 + i] = pg3[i]; }
-    s_gt[threadIdx.x] = g_t; s_ht[threadIdx.x] = h_t;
+    s_gt[threadIdx.x] = g_t; s_ht[threadIdx.x] = h_t; s_eb[threadIdx.x] = eb;
   }
   __syncthreads();
   if (threadIdx.x < 54) {
@@ -559,10 +567,17 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
     if (q < 3) o[9 + q] = 0.0;   // plane terms carry no time coupling
   }
   if (threadIdx.x == 64) {
-    double g = 0, h = 0;
-    for (int i = 0; i < 9; i++) { g += s_gt[i]; h += s_ht[i]; }
+    double g = 0, h = 0, eb = 0;
+    for (int i = 0; i < 9; i++) { g += s_gt[i]; h += s_ht[i]; eb += s_eb[i]; }
     out[ROW_TERMS * TERM_SZ] = g;
     out[ROW_TERMS * TERM_SZ + 1] = h;
+    if (a.row_e) {                  // record of (trial 0, row): the whole plane energy in partial 0, zeros in the others
+      double* re = a.row_e + (size_t)row * EN_REC;
+      re[0] = -w * ((s_en[0] + s_en[1]) + (s_en[2] + s_en[3]));
+#pragma unroll
+      for (int v = 1; v < EN_VMAX; v++) re[v] = 0.0;
+      re[EN_VMAX] = eb;
+    }
   }
 }
 
@@ -894,7 +909,7 @@ int row_blocks(tob_ctx* c, int tr, int which, double* out_dev) {
   RowGradArgs a;
   a.P = c->geo.P.p; a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p; a.ptime = c->s_ptime.p;
   a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
-  a.n_tr = c->n_tr; a.row_begin = tr; a.terms = c->row_terms.p; a.dc = c->dc.p;
+  a.n_tr = c->n_tr; a.row_begin = tr; a.terms = c->row_terms.p; a.dc = c->dc.p; a.row_e = nullptr; a.rows_all = c->rows_all();
   k_row_grad<<<1, 128, 0, c->stream>>>(a);
   TOB_LAUNCH_CHECK(c);
   k_row_expand<<<1, 128, 0, c->stream>>>(c->row_terms.p + (size_t)ROW_REC * tr, c->d_basis.p + (size_t)36 * tr, which, out_dev);
@@ -914,6 +929,8 @@ int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd) {
   a.P = c->geo.P.p; a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p; a.ptime = c->s_ptime.p;
   a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
   a.n_tr = c->n_tr; a.row_begin = rb * c->n_tr; a.terms = c->row_terms.p; a.dc = c->dc.p;
+  TOB_TRY(energy_buffers(c, TOB_LS_TRIALS));
+  a.row_e = c->row_e.p; a.rows_all = rows_total;
   {
     Prof prof(c, K_ROW_GRAD);
     k_row_grad<<<(re - rb) * c->n_tr, 128, 0, c->stream>>>(a);

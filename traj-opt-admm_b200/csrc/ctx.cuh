@@ -219,6 +219,7 @@ struct tob_ctx {
   // most robots accept one of the first two rungs, so the first round only evaluates those for everybody (throughput),
   // and the few robots that keep backtracking get 8 rungs per later round
   int ls_kte0 = TOB_LS_TRIALS, ls_kte = TOB_LS_TRIALS, ls_rounds = 2;
+  bool ls_e0_ready = false;           // trial slot 0 (the current point) already holds its energy: written by the gradient pass
 
   // optional per-kernel CUDA-event timing (bench.py roofline): off by default
   bool prof_on = false;
@@ -338,7 +339,7 @@ int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* t
                   int k1, double* e_dev);
 // one Armijo round of robots [rb,re) (decoupled): trial energies k0..kte-1 (kte <= TOB_LS_TRIALS) + the ladder decision, robots that
 // are already done are skipped on the device; robots still backtracking are counted in dc->ls_pending[slot]
-int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int kte, int slot);
+int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int kte, int slot, int k0e);
 int line_search_begin(tob_ctx* c, int rb, int re);   // clears the infeasibility flags of the robots' trial slots
 #define TOB_EN_REC 9   // doubles per (trial, row) in row_e: 8 plane-energy partials + the bound energy (barrier.cu: EN_REC)
 int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd);
