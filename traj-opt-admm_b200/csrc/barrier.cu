@@ -63,50 +63,55 @@ struct EnergyArgs {
   const uint32_t* pl_off;       // rows+1
   const double* weight;         // n_tr
   double margin, vel_limit, acc_limit;
-  int n_tr, res, T, row_begin, rows_all, KT, k0, nk;
-  int VL;                       // CTAs per row (gridDim.y): CTA g runs virtual warps g, g+VL, ...
+  int n_tr, res, T, row_begin, n_rows, rows_all, KT, k0, nk;
+  const uint32_t* items;        // (row << 3 | v) of every virtual warp v >= 1 of the context's rows (k_en_items), any order
   double* row_e;                // KT x rows_all x EN_REC
   int* bad;                     // robots x KT: trial infeasible (some d <= 0); raised here, cleared by the caller
   const int* done;              // per robot, may be null: robots whose line search has finished are skipped
-  DevCounts* dc;                // barrier_terms counter
+  DevCounts* dc;                // barrier_terms counter, n_en_items
 };
 
+// Every row with more than EN_VPLANES planes lists its virtual warps 1 .. V-1 here, once per plane set (after the CSR is
+// built): the energy launches then run one CTA per row for virtual warp 0 (+ the bound terms) and a fixed number of extra
+// CTAs that share the listed virtual warps, instead of V CTAs per row of which nearly all would find nothing to do.
+__global__ void __launch_bounds__(256) k_en_items(const uint32_t* __restrict__ pl_off, int rows_all, uint32_t* __restrict__ items,
+                                                  DevCounts* dc) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows_all || dc->overflow) return;
+  const int V = en_vwarps(pl_off[row + 1] - pl_off[row]);
+  if (V > 1) {
+    const uint32_t base = atomicAdd(&dc->n_en_items, (uint32_t)(V - 1));
+    for (int v = 1; v < V; v++) items[base + v - 1] = ((uint32_t)row << 3) | (uint32_t)(v - 1);
+  }
+}
+
 #define EN_MAXT TOB_LS_TRIALS
-__global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
-  const int row = a.row_begin + blockIdx.x;
+// one warp: virtual warp v of `row` for trial k (and, when v == 0, the bound terms of the row)
+__device__ __forceinline__ void en_virtual_warp(const EnergyArgs& a, int row, int v, int k, double* sP, double* sBz, double* q,
+                                                unsigned& n_act, unsigned& n_pl) {
+  const int lane = threadIdx.x & 31;
   const int robot = row / a.n_tr, tr = row - robot * a.n_tr;
-  const int lane = threadIdx.x & 31, kk = threadIdx.x >> 5, k = a.k0 + kk;
-  __shared__ double sPall[EN_MAXT][18], sBzall[EN_MAXT][18];
-  __shared__ double sQ[EN_MAXT][192];          // in-band terms of one chunk (32 planes x 6 control points)
-  // all the words that decide whether this CTA has anything to do are loaded before the first test (one memory round trip
-  // for the many CTAs of a launch that leave at once: rows with few planes have V = 1, robots that are done, ...)
+  // every word that decides whether there is anything to do is loaded before the first test: one memory round trip
   const uint32_t p0 = a.pl_off[row], p1 = a.pl_off[row + 1];
   const int is_done = a.done ? a.done[robot] : 0;
-  const uint32_t ovf = a.dc->overflow;
   const int seen0 = a.bad[robot * a.KT + k];    // plain (cached) load: a stale 0 only costs the work the flag would have saved
+  if (is_done || seen0) return;    // (an infeasible trial's energy is +inf whatever this row adds)
   const int V = en_vwarps(p1 - p0);
-  const int g = blockIdx.y;
-  if (g >= V) return;              // nothing for this CTA (virtual warp 0 also carries the bound terms)
-  if (is_done) return;
-  if (ovf) return;                 // the plane CSR of this iteration was not built: the host grows the buffers and retries
   volatile int* flag = a.bad + robot * a.KT + k;
   double* out = a.row_e + ((size_t)k * a.rows_all + row) * EN_REC;
-  if (seen0) return;               // the trial is already known to be infeasible: its energy is +inf whatever this row adds
-  double* sP = sPall[kk];
-  double* sBz = sBzall[kk];
   if (lane < 18) {
     const int mm = lane % 6, ax = lane / 6;
     const size_t gi = (size_t)robot * 3 * a.T + (size_t)ax * a.T + 3 * (tr / a.res) + mm;
-    double v = a.spline[gi];
-    if (a.dir && a.tstep) v = __dadd_rn(v, __dmul_rn(a.tstep[robot * a.KT + k], a.dir[gi]));
-    sBz[lane] = v;
+    double x = a.spline[gi];
+    if (a.dir && a.tstep) x = __dadd_rn(x, __dmul_rn(a.tstep[robot * a.KT + k], a.dir[gi]));
+    sBz[lane] = x;
   }
   __syncwarp();
   if (lane < 18) {
     const int j = lane % 6, ax = lane / 6;
     const double* B = a.basis + (size_t)36 * tr;
     double acc = 0;
-    for (int q = 0; q < 6; q++) acc = __dadd_rn(acc, __dmul_rn(B[j + 6 * q], sBz[q + 6 * ax]));
+    for (int i = 0; i < 6; i++) acc = __dadd_rn(acc, __dmul_rn(B[j + 6 * i], sBz[i + 6 * ax]));
     sP[lane] = acc;
   }
   __syncwarp();
@@ -114,10 +119,8 @@ __global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
   double cp[18];
 #pragma unroll
   for (int i = 0; i < 18; i++) cp[i] = sP[i];
-  double* q = sQ[kk];
-  unsigned n_act = 0, n_pl = 0;
   bool stop = false;
-  for (int v = g; v < V && !stop; v += a.VL) {
+  {
     double e = 0;
     uint32_t p = p0 + (uint32_t)v * 32u + lane;
     const uint32_t stride = 32u * (uint32_t)V;
@@ -156,15 +159,16 @@ __global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
         const double l0 = log(d0 * inv_m), l1 = log(d1 * inv_m), l2 = log(d2 * inv_m);
         e += ((m0 * m0) * l0 + (m1 * m1) * l1) + (m2 * m2) * l2;
       }
-      n_act += cnt;                    // counted once per warp below (uniform value)
+      n_act += cnt;                    // uniform value: counted once per warp by the caller
       __syncwarp();
     }
-    if (stop) break;
-    e = warp_sum(e) * -w;
-    if (lane == 0) out[v] = e;
+    if (!stop) {
+      e = warp_sum(e) * -w;
+      if (lane == 0) out[v] = e;
+    }
   }
   // bound terms: virtual warp 0 only; lanes 0..4 velocity, 5..8 acceleration
-  if (g == 0 && !stop) {
+  if (v == 0 && !stop) {
     double eb = 0;
     int bad = 0;
     if (lane < 9) {
@@ -188,6 +192,28 @@ __global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
     if (lane == 0) {
       out[EN_VMAX] = eb;
       if (bad) *flag = 1;
+    }
+  }
+  __syncwarp();
+}
+
+// grid = n_rows + extra CTAs; one warp per trial point of the launch (blockDim = 32 * nk).  CTA b < n_rows: virtual warp 0
+// of row b.  The extra CTAs share the listed virtual warps (v >= 1) of the heavy rows.
+__global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
+  const int lane = threadIdx.x & 31, kk = threadIdx.x >> 5, k = a.k0 + kk;
+  __shared__ double sPall[EN_MAXT][18], sBzall[EN_MAXT][18];
+  __shared__ double sQ[EN_MAXT][192];          // in-band terms of one chunk (32 planes x 6 control points)
+  if (a.dc->overflow) return;      // the plane CSR of this iteration was not built: the host grows the buffers and retries
+  unsigned n_act = 0, n_pl = 0;
+  if ((int)blockIdx.x < a.n_rows) {
+    en_virtual_warp(a, a.row_begin + (int)blockIdx.x, 0, k, sPall[kk], sBzall[kk], sQ[kk], n_act, n_pl);
+  } else {
+    const uint32_t n_items = a.dc->n_en_items, extra = gridDim.x - (uint32_t)a.n_rows;
+    for (uint32_t idx = blockIdx.x - (uint32_t)a.n_rows; idx < n_items; idx += extra) {
+      const uint32_t it = a.items[idx];
+      const int row = (int)(it >> 3), v = (int)(it & 7u) + 1;
+      if (row < a.row_begin || row >= a.row_begin + a.n_rows) continue;
+      en_virtual_warp(a, row, v, k, sPall[kk], sBzall[kk], sQ[kk], n_act, n_pl);
     }
   }
   n_pl = __reduce_add_sync(0xffffffffu, n_pl);
@@ -342,11 +368,17 @@ __global__ void __launch_bounds__(32 * TOB_LS_TRIALS) k_robot_ls(RobotLsArgs b) 
   atomicAdd(&b.dc->ls_pending[b.slot], 1);
 }
 
-// CTAs per row of an energy launch: heavy rows need their virtual warps side by side when the launch has few rows
-// (latency regime, a shard of a batch); with very many rows the grid is large anyway
-static int energy_vl(tob_ctx* c, int nrows) {
-  if (const char* e = getenv("TRAJOPT_B200_EN_VL")) { int v = atoi(e); if (v >= 1 && v <= EN_VMAX) return v; }
-  return nrows >= 32768 ? 4 : EN_VMAX;
+// extra CTAs of an energy launch (they share the listed virtual warps of the heavy rows)
+static int energy_extra(tob_ctx* c) { return 4 * c->sm_count; }
+
+// list the virtual warps v >= 1 of the current plane CSR (c->pl_off): after every plane pass / plane upload
+int energy_items(tob_ctx* c) {
+  const int rows = c->rows_all();
+  TOB_CUDA(c, c->en_items.ensure((size_t)(EN_VMAX - 1) * rows + 8));    // at most EN_VMAX - 1 listed virtual warps per row
+  TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->n_en_items, 0, sizeof(uint32_t), c->stream));
+  k_en_items<<<div_up(rows, 256), 256, 0, c->stream>>>(c->pl_off.p, rows, c->en_items.p, c->dc.p);
+  TOB_LAUNCH_CHECK(c);
+  return 0;
 }
 
 static int energy_buffers(tob_ctx* c, int KT) {
@@ -367,14 +399,14 @@ int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* t
   a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p;
   a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
   a.n_tr = c->n_tr; a.res = c->prm.res; a.T = c->T; a.row_begin = rb * c->n_tr; a.rows_all = rows_all; a.KT = KT; a.k0 = k0;
-  a.row_e = c->row_e.p; a.bad = c->row_bad.p; a.done = nullptr; a.dc = c->dc.p;
+  a.row_e = c->row_e.p; a.bad = c->row_bad.p; a.done = nullptr; a.dc = c->dc.p; a.items = c->en_items.p;
   const int nrows = (re - rb) * c->n_tr, nk = k1 - k0;
-  a.VL = energy_vl(c, nrows);
+  a.n_rows = nrows;
   {
     Prof prof(c, K_ROW_ENERGY);
     a.nk = nk;
     if (nk > EN_MAXT) return fail_msg(c, "energy_trials: too many trial points in one launch");
-    k_row_energy<<<dim3(nrows, a.VL), 32 * nk, 0, c->stream>>>(a);
+    k_row_energy<<<nrows + energy_extra(c), 32 * nk, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
   RobotEnergyArgs b;
@@ -409,13 +441,13 @@ int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int kte
   a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p;
   a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
   a.n_tr = c->n_tr; a.res = c->prm.res; a.T = c->T; a.row_begin = rb * c->n_tr; a.rows_all = rows_all; a.KT = KT; a.k0 = k0e;
-  a.row_e = c->row_e.p; a.bad = c->row_bad.p; a.done = c->s_done.p; a.dc = c->dc.p;
+  a.row_e = c->row_e.p; a.bad = c->row_bad.p; a.done = c->s_done.p; a.dc = c->dc.p; a.items = c->en_items.p;
   const int nrows = (re - rb) * c->n_tr;
-  a.VL = energy_vl(c, nrows);
+  a.n_rows = nrows;
   {
     Prof prof(c, K_ROW_ENERGY);
     a.nk = kte - k0e;
-    k_row_energy<<<dim3(nrows, a.VL), 32 * (kte - k0e), 0, c->stream>>>(a);
+    k_row_energy<<<nrows + energy_extra(c), 32 * (kte - k0e), 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
   RobotLsArgs b;

@@ -63,11 +63,13 @@ struct DevCounts {
   uint32_t n_cand;           // candidates of the last broadphase fill (may exceed the capacity -> overflow)
   uint32_t n_planes;         // planes of the last pack
   uint32_t n_planes_ob;      // ... of which obstacle planes
+  uint32_t n_surv;           // candidates that passed the 49-DOP gate of the last narrowphase (reset with n_cand)
+  uint32_t n_en_items;       // listed virtual warps (v >= 1) of the rows with more than 256 planes (barrier.cu: k_en_items)
   uint32_t overflow;         // TOB_OVF_* bits, sticky until the host clears them
   int32_t ls_pending[TOB_LS_MAXROUNDS + 1];   // robots still backtracking after Armijo round r (last entry: host scratch)
   int32_t ls_rounds;                          // rounds launched ahead in this iteration (written by k_ls_init)
   uint32_t iters_done;       // iterations fully committed (apply step + slack update ran)
-  uint32_t pad;
+  uint32_t pad0;
   unsigned long long dcd_candidates, planes, ccd_candidates, energy_plane_evals, barrier_terms;   // cumulative since reset
   // persistent-plane mode ("optimal_plane": 1)
   uint32_t n_live;           // live (row, point) obstacle planes
@@ -162,6 +164,7 @@ struct tob_ctx {
   // planes: candidate-indexed scratch, then packed CSR over ALL rows
   tob::DBuf<double> cpl;              // cand x 4 (cx,cy,cz,d)
   tob::DBuf<uint32_t> cflag, cflag_off;
+  tob::DBuf<uint32_t> surv;           // cand: candidates that passed the 49-DOP gate
   tob::DBuf<uint32_t> csum;           // accepted planes per 128-candidate chunk, scanned in place
   tob::DBuf<uint32_t> selfpre;        // rows+1: exclusive scan of the inter-robot plane count per row
   tob::DBuf<uint32_t> selfcnt;        // rows: inter-robot planes per row (integer atomics of k_self_planes)
@@ -184,6 +187,7 @@ struct tob_ctx {
   tob::DBuf<uint32_t> self_hits;      // inter-robot CCD: colliding (slot, pair) ids [cap] + count [2] + the sorted list [cap]; cap = all tasks
 
   // energy / gradient / solve scratch
+  tob::DBuf<uint32_t> en_items;       // virtual warps v >= 1 of the heavy rows of the current plane set (row << 3 | v - 1)
   tob::DBuf<double> row_e;            // trials x rows x TOB_EN_REC
   tob::DBuf<int> row_bad;             // robots x TOB_LS_TRIALS: trial infeasible (some d <= 0)
   tob::DBuf<double> row_terms;
@@ -340,7 +344,8 @@ int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* t
 // one Armijo round of robots [rb,re) (decoupled): trial energies k0..kte-1 (kte <= TOB_LS_TRIALS) + the ladder decision, robots that
 // are already done are skipped on the device; robots still backtracking are counted in dc->ls_pending[slot]
 int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int kte, int slot, int k0e);
-int line_search_begin(tob_ctx* c, int rb, int re);   // clears the infeasibility flags of the robots' trial slots
+int line_search_begin(tob_ctx* c, int rb, int re);
+int energy_items(tob_ctx* c);   // after every new plane CSR: lists the extra virtual warps of the heavy rows   // clears the infeasibility flags of the robots' trial slots
 #define TOB_EN_REC 9   // doubles per (trial, row) in row_e: 8 plane-energy partials + the bound energy (barrier.cu: EN_REC)
 int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd);
 int row_blocks(tob_ctx* c, int tr, int which, double* out_dev);
