@@ -368,8 +368,14 @@ __global__ void __launch_bounds__(32 * TOB_LS_TRIALS) k_robot_ls(RobotLsArgs b) 
   atomicAdd(&b.dc->ls_pending[b.slot], 1);
 }
 
-// extra CTAs of an energy launch (they share the listed virtual warps of the heavy rows)
-static int energy_extra(tob_ctx* c) { return 4 * c->sm_count; }
+// extra CTAs of an energy launch (they share the listed virtual warps of the heavy rows; those without an item leave at
+// once): few when the launch has few rows (latency regime), up to 32 per SM when it has many -- measured on the
+// 1024-problem batch: with 4 per SM the 36 k listed virtual warps ran on 8 warps per SM
+static int energy_extra(tob_ctx* c, int nrows) {
+  if (const char* e = getenv("TRAJOPT_B200_EN_EXTRA")) { int v = atoi(e); if (v >= 1 && v <= 256) return v * c->sm_count; }
+  const int lo = 4 * c->sm_count, hi = 32 * c->sm_count, want = nrows / 2;
+  return want < lo ? lo : (want > hi ? hi : want);
+}
 
 // list the virtual warps v >= 1 of the current plane CSR (c->pl_off): after every plane pass / plane upload
 int energy_items(tob_ctx* c) {
@@ -406,7 +412,7 @@ int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* t
     Prof prof(c, K_ROW_ENERGY);
     a.nk = nk;
     if (nk > EN_MAXT) return fail_msg(c, "energy_trials: too many trial points in one launch");
-    k_row_energy<<<nrows + energy_extra(c), 32 * nk, 0, c->stream>>>(a);
+    k_row_energy<<<nrows + energy_extra(c, nrows), 32 * nk, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
   RobotEnergyArgs b;
@@ -447,7 +453,7 @@ int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int kte
   {
     Prof prof(c, K_ROW_ENERGY);
     a.nk = kte - k0e;
-    k_row_energy<<<nrows + energy_extra(c), 32 * (kte - k0e), 0, c->stream>>>(a);
+    k_row_energy<<<nrows + energy_extra(c, nrows), 32 * (kte - k0e), 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
   RobotLsArgs b;

@@ -63,7 +63,7 @@ struct DevCounts {
   uint32_t n_cand;           // candidates of the last broadphase fill (may exceed the capacity -> overflow)
   uint32_t n_planes;         // planes of the last pack
   uint32_t n_planes_ob;      // ... of which obstacle planes
-  uint32_t n_surv;           // candidates that passed the 49-DOP gate of the last narrowphase (reset with n_cand)
+  uint32_t pad1;
   uint32_t n_en_items;       // listed virtual warps (v >= 1) of the rows with more than 256 planes (barrier.cu: k_en_items)
   uint32_t overflow;         // TOB_OVF_* bits, sticky until the host clears them
   int32_t ls_pending[TOB_LS_MAXROUNDS + 1];   // robots still backtracking after Armijo round r (last entry: host scratch)
@@ -164,7 +164,6 @@ struct tob_ctx {
   // planes: candidate-indexed scratch, then packed CSR over ALL rows
   tob::DBuf<double> cpl;              // cand x 4 (cx,cy,cz,d)
   tob::DBuf<uint32_t> cflag, cflag_off;
-  tob::DBuf<uint32_t> surv;           // cand: candidates that passed the 49-DOP gate
   tob::DBuf<uint32_t> csum;           // accepted planes per 128-candidate chunk, scanned in place
   tob::DBuf<uint32_t> selfpre;        // rows+1: exclusive scan of the inter-robot plane count per row
   tob::DBuf<uint32_t> selfcnt;        // rows: inter-robot planes per row (integer atomics of k_self_planes)

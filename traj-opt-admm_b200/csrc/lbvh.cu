@@ -319,7 +319,6 @@ __global__ void __launch_bounds__(1024) k_bp_top(uint32_t* bsum, uint32_t nblk, 
   if (threadIdx.x == 0) {
     bsum[nblk] = total;
     dc->n_cand = total;
-    dc->n_surv = 0;
     if (total > cap) dc->overflow |= TOB_OVF_CAND;
     else if (count_as == 1) dc->dcd_candidates += total;
   }
@@ -472,7 +471,6 @@ int ensure_query_buffers(tob_ctx* c) {
   TOB_CUDA(c, c->cand_row.ensure(c->cand_cap + 1));
   TOB_CUDA(c, c->cpl.ensure(4 * c->cand_cap + 4));
   TOB_CUDA(c, c->cflag.ensure(c->cand_cap + 1));
-  TOB_CUDA(c, c->surv.ensure(c->cand_cap + 1));
   TOB_CUDA(c, c->en_items.ensure((size_t)7 * rows + 8));   // barrier.cu: energy_items (EN_VMAX - 1 per row)
   TOB_CUDA(c, c->csum.ensure(c->cand_cap / 128 + 4)   /* >= chunks + 1 for any chunk size >= 128 */);
   TOB_CUDA(c, c->selfpre.ensure(rows + 2));

@@ -31,8 +31,10 @@ __device__ __forceinline__ void load_pts6(const double* __restrict__ src, double
 }
 
 // ---- obstacle planes -------------------------------------------------------------------------------------------
-// The candidate array is cut into chunks (np_per_of); per chunk the number of accepted planes goes to csum[chunk];
-// k_np_top scans the counts and k_pack scatters, so the planes keep the candidate order.
+// Candidates are processed in chunks of NP_CHUNK (one CTA iteration).  Inside a chunk: every thread runs the cheap
+// 49-DOP gate for NP_PER candidates, the survivors are compacted (ballot + prefix), and the threads then run GJK + plane
+// for the survivors, so the expensive divergent part executes on dense warps instead of on ~30 % of the lanes.
+// Per chunk the number of accepted planes goes to csum[chunk]; k_np_top scans it and k_pack scatters.
 struct NarrowArgs {
   DevCounts* dc;
   uint32_t cap;
@@ -43,9 +45,8 @@ struct NarrowArgs {
   double* cpl;       // cap x 4
   uint32_t* cflag;   // cap
   uint32_t* csum;    // chunks + 1
-  uint32_t* surv;    // cap: candidates that passed the 49-DOP gate (any order)
   const unsigned long long* live_key;   // persistent-plane mode: sorted keys of the live planes (else nullptr)
-  uint32_t np_grid;                     // reference grid of the chunk size (np_per_of): k_np_top / k_pack / k_live_compact agree on it
+  uint32_t np_grid;                     // CTAs of the narrowphase grid (np_per_of)
 };
 
 // index of the first key >= x in the sorted array k[0..n)
@@ -71,87 +72,99 @@ __device__ __forceinline__ uint32_t np_per_of(uint32_t n, uint32_t grid) {
   return 1;
 }
 
-// Two kernels instead of one fused (gate -> block compaction -> GJK) kernel: the 49-DOP gate needs ~40 registers and is
-// bound by its loads, GJK + plane needs 128 and is bound by the FP64 pipe.  Fused, the gate ran at the GJK phase's occupancy
-// (16 warps / SM) behind block barriers, and the register pressure of carrying both phases spilled ~6 GB of local traffic
-// per launch on the batched workload (ncu, round 1).  Split, the gate runs at full occupancy and appends the survivors to a
-// list (order irrelevant: every result is written to candidate-indexed arrays), and the GJK kernel runs on dense warps.
-#define NPG_THREADS 256
-
-// gate: one candidate per thread (grid-stride), 49-DOP test against the row's precomputed extents, survivors appended with
-// one atomic per warp.  Also resets the per-chunk plane counts that the GJK kernel accumulates.
-__global__ void __launch_bounds__(NPG_THREADS) k_np_gate(NarrowArgs a) {
+// MINB = resident CTAs per SM the register allocation is made for (4: 128 registers, 5: 102, 6: 85, 8: 64)
+template <int MINB>
+__global__ void __launch_bounds__(NP_THREADS, MINB) k_narrow(NarrowArgs a) {
   __shared__ double s_kdop[3 * TOB_KDOP_AXES];
+  __shared__ uint32_t s_surv[NP_CHUNK];
+  __shared__ uint32_t s_w[NP_THREADS / 32];
   for (int i = threadIdx.x; i < 3 * TOB_KDOP_AXES; i += blockDim.x) s_kdop[i] = a.kdop[i];
   const uint32_t n = a.dc->n_cand;
   if (n > a.cap) return;
-  const uint32_t chunk_sz = np_per_of(n, a.np_grid) * NP_THREADS;
+  const uint32_t per = np_per_of(n, a.np_grid), chunk_sz = per * NP_THREADS;
+  const uint32_t n_chunks = (n + chunk_sz - 1) / chunk_sz;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t n_live = a.live_key ? a.dc->n_live : 0u;
-  const uint32_t lane = threadIdx.x & 31;
-  unsigned w_groups = 0;
+  unsigned w_groups = 0, w_iters = 0;   // counted work of this thread
   __syncthreads();
-  const uint32_t n32 = (n + 31u) & ~31u, stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += stride) {
-    bool pass = false;
-    if (i < n) {
-      const uint32_t p = a.cand_pt[i], row = a.cand_row[i];
-      const double pt[3] = {a.px[p], a.py[p], a.pz[p]};
-      a.cflag[i] = 0;
-      if (i % chunk_sz == 0) a.csum[i / chunk_sz] = 0;
-      pass = kdop_point_overlap(a.klo + (size_t)TOB_KDOP_AXES * row, a.khi + (size_t)TOB_KDOP_AXES * row, s_kdop, pt, a.dist, &w_groups);
-      if (pass && n_live) {   // is_seperate[tr_id][ob_id] (Optimization3D_admm.h:128): a live pair keeps its plane
-        const unsigned long long key = ((unsigned long long)row << 32) | p;
-        const uint32_t at = lower_bound_u64(a.live_key, n_live, key);
-        if (at < n_live && a.live_key[at] == key) pass = false;
+  for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    uint32_t n_surv = 0;   // uniform
+    // the candidates of this thread are gathered first (index -> row / point -> coordinates are two dependent global loads
+    // each; one after the other behind the block barriers of the compaction they cost four round trips instead of one)
+    uint32_t c_row[NP_PER];
+    double c_pt[NP_PER][3];
+#pragma unroll
+    for (uint32_t q = 0; q < NP_PER; q++) {
+      const uint32_t i = chunk * chunk_sz + q * NP_THREADS + tid;
+      c_row[q] = 0; c_pt[q][0] = c_pt[q][1] = c_pt[q][2] = 0.0;
+      if (q < per && i < n) {
+        const uint32_t p = a.cand_pt[i];
+        c_row[q] = a.cand_row[i];
+        c_pt[q][0] = a.px[p]; c_pt[q][1] = a.py[p]; c_pt[q][2] = a.pz[p];
       }
     }
-    const uint32_t bm = __ballot_sync(0xffffffffu, pass);
-    if (bm) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&a.dc->n_surv, (uint32_t)__popc(bm));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (pass) a.surv[base + __popc(bm & ((1u << lane) - 1u))] = i;
+#pragma unroll
+    for (uint32_t q = 0; q < NP_PER; q++) {
+      if (q >= per) break;   // uniform
+      const uint32_t loc = q * NP_THREADS + tid, i = chunk * chunk_sz + loc;
+      bool pass = false;
+      if (i < n) {
+        const uint32_t row = c_row[q];
+        pass = kdop_point_overlap(a.klo + (size_t)TOB_KDOP_AXES * row, a.khi + (size_t)TOB_KDOP_AXES * row, s_kdop, c_pt[q], a.dist,
+                                  &w_groups);
+        a.cflag[i] = 0;
+      }
+      const uint32_t bm = __ballot_sync(0xffffffffu, pass);
+      __syncthreads();                 // s_w of the previous pass has been consumed
+      if (lane == 0) s_w[w] = __popc(bm);
+      __syncthreads();
+      uint32_t base = n_surv, tot = 0;
+#pragma unroll
+      for (int k = 0; k < NP_THREADS / 32; k++) {
+        if (k < (int)w) base += s_w[k];
+        tot += s_w[k];
+      }
+      if (pass) s_surv[base + __popc(bm & ((1u << lane) - 1u))] = loc;
+      n_surv += tot;
     }
-  }
-  w_groups = __reduce_add_sync(0xffffffffu, w_groups);
-  if (lane == 0 && w_groups) atomicAdd(&a.dc->np_kdop_groups, (unsigned long long)w_groups);
-}
-
-// GJK + plane for the survivors of the gate, one per thread on dense warps; the accepted planes of a candidate chunk are
-// counted with integer atomics (k_np_top scans the counts, k_pack scatters in candidate order: deterministic)
-__global__ void __launch_bounds__(NP_THREADS, 4) k_np_gjk(NarrowArgs a) {
-  const uint32_t n = a.dc->n_cand;
-  if (n > a.cap) return;
-  const uint32_t chunk_sz = np_per_of(n, a.np_grid) * NP_THREADS;
-  const uint32_t n_s = a.dc->n_surv;
-  const uint32_t lane = threadIdx.x & 31;
-  unsigned w_iters = 0;
-  const uint32_t n32 = (n_s + 31u) & ~31u, stride = gridDim.x * blockDim.x;
-  for (uint32_t sidx = blockIdx.x * blockDim.x + threadIdx.x; sidx < n32; sidx += stride) {
-    bool ok = false;
-    uint32_t chunk = 0xffffffffu;
-    if (sidx < n_s) {
-      const uint32_t ii = a.surv[sidx];
+    __syncthreads();
+    uint32_t ok = 0;
+    for (uint32_t sidx = tid; sidx < n_surv; sidx += NP_THREADS) {
+      const uint32_t ii = chunk * chunk_sz + s_surv[sidx];
       const uint32_t row = a.cand_row[ii], p = a.cand_pt[ii];
+      if (n_live) {   // is_seperate[tr_id][ob_id] (Optimization3D_admm.h:128): a live pair keeps its plane
+        const unsigned long long key = ((unsigned long long)row << 32) | p;
+        const uint32_t at = lower_bound_u64(a.live_key, n_live, key);
+        if (at < n_live && a.live_key[at] == key) continue;
+      }
       const double pt[3] = {a.px[p], a.py[p], a.pz[p]};
       double P[6][3], c[3], d;
       load_pts6(a.P + (size_t)18 * row, P);
       if (plane_point(P, pt, a.dist, a.offset, c, &d, &w_iters)) {
-        ok = true;
-        chunk = ii / chunk_sz;
+        ok++;
         *reinterpret_cast<double4*>(a.cpl + (size_t)4 * ii) = make_double4(c[0], c[1], c[2], d);
         a.cflag[ii] = 1;
       }
     }
-    // one atomic per (warp, chunk): the survivors of a warp come from one or two chunks
-    const uint32_t okm = __ballot_sync(0xffffffffu, ok);
-    if (ok) {
-      const uint32_t peers = __match_any_sync(okm, chunk);
-      if (lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(a.csum + chunk, (uint32_t)__popc(peers));
+    // accepted planes of the chunk (integer sum: order-independent)
+    for (int o = 16; o; o >>= 1) ok += __shfl_xor_sync(0xffffffffu, ok, o);
+    __syncthreads();
+    if (lane == 0) s_w[w] = ok;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t cnt = 0;
+      for (int k = 0; k < NP_THREADS / 32; k++) cnt += s_w[k];
+      a.csum[chunk] = cnt;
     }
   }
-  w_iters = __reduce_add_sync(0xffffffffu, w_iters);
-  if (lane == 0 && w_iters) atomicAdd(&a.dc->np_gjk_iters, (unsigned long long)w_iters);
+  for (int o = 16; o; o >>= 1) {
+    w_groups += __shfl_xor_sync(0xffffffffu, w_groups, o);
+    w_iters += __shfl_xor_sync(0xffffffffu, w_iters, o);
+  }
+  if (lane == 0 && w_groups) {
+    atomicAdd(&a.dc->np_kdop_groups, (unsigned long long)w_groups);
+    atomicAdd(&a.dc->np_gjk_iters, (unsigned long long)w_iters);
+  }
 }
 
 // ---- inter-robot planes ----------------------------------------------------------------------------------------
@@ -612,15 +625,15 @@ int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self) {
   }
   a.live_key = live ? c->live_key.p : nullptr;
   a.np_grid = (uint32_t)c->sm_count * 4;
-  a.surv = c->surv.p;
   {
     Prof prof(c, K_NARROW);
-    k_np_gate<<<c->sm_count * 8, NPG_THREADS, 0, st>>>(a);
-    TOB_LAUNCH_CHECK(c);
-  }
-  {
-    Prof prof(c, K_NARROW);
-    k_np_gjk<<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
+    static int occ = -1;
+    if (occ < 0) { const char* e = getenv("TRAJOPT_B200_NP_OCC"); occ = e ? atoi(e) : 4; }
+    a.np_grid = (uint32_t)c->sm_count * 4;
+    if (occ == 8) k_narrow<8><<<c->sm_count * 8, NP_THREADS, 0, st>>>(a);
+    else if (occ == 6) k_narrow<6><<<c->sm_count * 6, NP_THREADS, 0, st>>>(a);
+    else if (occ == 5) k_narrow<5><<<c->sm_count * 5, NP_THREADS, 0, st>>>(a);
+    else k_narrow<4><<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
   bool ws = with_self && c->n_robots() > 1;
