@@ -85,7 +85,8 @@ def batch_order(total):
     """the order batch_partition deals the problems in (expected pair work, then cloud size)"""
     from trajopt import scenes
     meta = [scenes.batch_member_meta(k) for k in range(total)]
-    return sorted(range(total), key=lambda k: (-(meta[k][0] if meta[k][1] < 0.3 else 0), -meta[k][0], k)), meta
+    cost = [scenes.batch_cost(n, r) for n, r in meta]
+    return sorted(range(total), key=lambda k: (-cost[k], k)), meta
 
 
 def describe(args, world):
@@ -97,7 +98,7 @@ def describe(args, world):
         pts = sum(scenes.batch_member_meta(k)[0] for k in range(total))
         wl = ("batch: %d independent single-UAV problems, tube clouds 1e4..1e6 pts (%.1f M pts in total), 8 Bezier pieces "
               "(64 sub-segments) each, 3D.json params" % (total, pts / 1e6))
-        mg = "single" if world == 1 else "independent problems dealt over the ranks by expected work, no communication"
+        mg = "single" if world == 1 else "independent problems dealt over the ranks by expected cost (longest first to the least loaded rank), no communication"
     else:
         shape = {"forest": (1, args.points or 1_000_000, 64), "bridge": (1, args.points or 100_000, 8),
                  "cross8": (8, args.points or 50_000, 8), "circle64": (64, args.points or 20_000, 8),

@@ -369,11 +369,11 @@ __global__ void __launch_bounds__(32 * TOB_LS_TRIALS) k_robot_ls(RobotLsArgs b) 
 }
 
 // extra CTAs of an energy launch (they share the listed virtual warps of the heavy rows; those without an item leave at
-// once): few when the launch has few rows (latency regime), up to 32 per SM when it has many -- measured on the
+// once): few when the launch has few rows (latency regime), up to 64 per SM when it has many -- measured on the
 // 1024-problem batch: with 4 per SM the 36 k listed virtual warps ran on 8 warps per SM
 static int energy_extra(tob_ctx* c, int nrows) {
   if (const char* e = getenv("TRAJOPT_B200_EN_EXTRA")) { int v = atoi(e); if (v >= 1 && v <= 256) return v * c->sm_count; }
-  const int lo = 4 * c->sm_count, hi = 32 * c->sm_count, want = nrows / 2;
+  const int lo = 4 * c->sm_count, hi = 64 * c->sm_count, want = nrows;     // measured: 8192 rows 0.86 ms at 32+ per SM, 1.37 at 4
   return want < lo ? lo : (want > hi ? hi : want);
 }
 
