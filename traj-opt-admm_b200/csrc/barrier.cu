@@ -75,12 +75,13 @@ struct EnergyArgs {
 // built): the energy launches then run one CTA per row for virtual warp 0 (+ the bound terms) and a fixed number of extra
 // CTAs that share the listed virtual warps, instead of V CTAs per row of which nearly all would find nothing to do.
 __global__ void __launch_bounds__(256) k_en_items(const uint32_t* __restrict__ pl_off, int rows_all, uint32_t* __restrict__ items,
-                                                  DevCounts* dc) {
+                                                  uint32_t* __restrict__ item_base, DevCounts* dc) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows_all || dc->overflow) return;
   const int V = en_vwarps(pl_off[row + 1] - pl_off[row]);
   if (V > 1) {
     const uint32_t base = atomicAdd(&dc->n_en_items, (uint32_t)(V - 1));
+    item_base[row] = base;         // item of (row, v) sits at base + v - 1: where the gradient pass leaves its partial sums
     for (int v = 1; v < V; v++) items[base + v - 1] = ((uint32_t)row << 3) | (uint32_t)(v - 1);
   }
 }
@@ -382,7 +383,8 @@ int energy_items(tob_ctx* c) {
   const int rows = c->rows_all();
   TOB_CUDA(c, c->en_items.ensure((size_t)(EN_VMAX - 1) * rows + 8));    // at most EN_VMAX - 1 listed virtual warps per row
   TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->n_en_items, 0, sizeof(uint32_t), c->stream));
-  k_en_items<<<div_up(rows, 256), 256, 0, c->stream>>>(c->pl_off.p, rows, c->en_items.p, c->dc.p);
+  TOB_CUDA(c, c->en_item_base.ensure((size_t)rows + 1));
+  k_en_items<<<div_up(rows, 256), 256, 0, c->stream>>>(c->pl_off.p, rows, c->en_items.p, c->en_item_base.p, c->dc.p);
   TOB_LAUNCH_CHECK(c);
   return 0;
 }
@@ -390,6 +392,14 @@ int energy_items(tob_ctx* c) {
 static int energy_buffers(tob_ctx* c, int KT) {
   TOB_CUDA(c, c->row_e.ensure((size_t)EN_REC * c->rows_all() * KT));
   TOB_CUDA(c, c->row_bad.ensure((size_t)c->n_robots() * TOB_LS_TRIALS + 1));
+  return 0;
+}
+
+// partial plane sums of the listed parts of heavy rows (k_row_grad): one 54-vector per item
+static int grad_buffers(tob_ctx* c) {
+  TOB_CUDA(c, c->en_items.ensure((size_t)(EN_VMAX - 1) * c->rows_all() + 8));
+  TOB_CUDA(c, c->en_item_base.ensure((size_t)c->rows_all() + 1));
+  TOB_CUDA(c, c->gpart.ensure((size_t)54 * ((size_t)(EN_VMAX - 1) * c->rows_all() + 8)));
   return 0;
 }
 
@@ -482,24 +492,24 @@ struct RowGradArgs {
   const double* weight;
   const double* ptime;     // per robot (current)
   double margin, vel_limit, acc_limit;
-  int n_tr, row_begin;
-  double* terms;           // rows x ROW_REC
-  DevCounts* dc;           // barrier_terms counter
+  int n_tr, row_begin, n_rows;
+  double* terms;           // rows x ROW_REC: bound terms, and the plane terms of part 0
+  // rows with more than EN_VPLANES planes are cut into V = en_vwarps(planes) parts (chunks of 128 planes dealt round-robin)
+  // like the energy: part 0 runs in the row's own CTA, parts 1 .. V-1 are listed items shared by the extra CTAs; the plane
+  // sums of item i (54 doubles) go to gpart[i] and are added in part order by whoever reads the row (row_plane_term)
+  const uint32_t* items;
+  double* gpart;           // items x 54
+  DevCounts* dc;           // barrier_terms counter, n_en_items
   // by-product: barrier energy of the CURRENT point (trial slot 0 of the line search that follows): the logarithms of the
   // gradient are the logarithms of the energy, so the line search does not evaluate its starting point again
-  double* row_e;           // trials x rows_all x EN_REC (slot 0 is written), may be null
+  double* row_e;           // trials x rows_all x EN_REC (slot 0 is written: one partial per part), may be null
   int rows_all;
 };
 
-__global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
-  const int row = a.row_begin + blockIdx.x;
-  const int robot = row / a.n_tr, tr = row - robot * a.n_tr;
-  __shared__ double sP[18];
-  __shared__ double s_red[4][54];
-  __shared__ double s_gt[9], s_ht[9], s_eb[9], s_en[4];
-  if (a.dc->overflow) return;      // the plane CSR of this iteration was not built (see k_row_energy)
-  if (threadIdx.x < 18) sP[threadIdx.x] = a.P[(size_t)18 * row + threadIdx.x];
-  __syncthreads();
+// part v of `row` by the whole CTA (128 threads): sums of the plane terms -> s_red[4][54] per warp, energy -> s_en[4]
+__device__ __forceinline__ void grad_part(const RowGradArgs& a, int row, int v, int V, const double* sP, double (*s_red)[54],
+                                          double* s_en) {
+  const int tr = row % a.n_tr;
   const double w = a.weight[tr], m = a.margin, inv_m = 1.0 / m;
   double acc[54];
   double en = 0;
@@ -507,7 +517,8 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
 #pragma unroll
   for (int i = 0; i < 54; i++) acc[i] = 0;
   const uint32_t k0 = a.pl_off[row], k1 = a.pl_off[row + 1];
-  for (uint32_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+  const uint32_t first = k0 + (uint32_t)v * 128u, stride = 128u * (uint32_t)V;
+  for (uint32_t k = first + threadIdx.x; k < k1; k += stride) {
     const double4 pl = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * k);
     const double cxx = pl.x * pl.x, cxy = pl.x * pl.y, cxz = pl.x * pl.z, cyy = pl.y * pl.y, cyz = pl.y * pl.z, czz = pl.z * pl.z;
     // branch-free like k_row_energy: a term outside the band contributes e1 = e2 = 0 through log(1) and dm = 0, so the six
@@ -529,11 +540,11 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   for (int o = 16; o; o >>= 1) n_act += __shfl_xor_sync(0xffffffffu, n_act, o);
   if (lane == 0 && n_act) atomicAdd(&a.dc->barrier_terms, (unsigned long long)n_act);
-  if (k0 + 32u * wp < k1) {            // this warp streamed at least one plane (warp-uniform)
+  if (first + 32u * wp < k1) {         // this warp streamed at least one plane (warp-uniform)
 #pragma unroll
     for (int i = 0; i < 54; i++) {
-      double v = warp_sum(acc[i]);
-      if (lane == 0) s_red[wp][i] = v;
+      double x = warp_sum(acc[i]);
+      if (lane == 0) s_red[wp][i] = x;
     }
     en = warp_sum(en);
     if (lane == 0) s_en[wp] = en;
@@ -541,6 +552,42 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
     for (int i = lane; i < 54; i += 32) s_red[wp][i] = 0.0;
     if (lane == 0) s_en[wp] = 0.0;
   }
+}
+
+// grid = n_rows + extra CTAs.  CTA b < n_rows: part 0 of row b and its bound terms; the extra CTAs share the listed parts.
+__global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
+  __shared__ double sP[18];
+  __shared__ double s_red[4][54];
+  __shared__ double s_gt[9], s_ht[9], s_eb[9], s_en[4];
+  if (a.dc->overflow) return;      // the plane CSR of this iteration was not built (see k_row_energy)
+  if ((int)blockIdx.x >= a.n_rows) {
+    const uint32_t n_items = a.dc->n_en_items, extra = gridDim.x - (uint32_t)a.n_rows;
+    for (uint32_t idx = blockIdx.x - (uint32_t)a.n_rows; idx < n_items; idx += extra) {
+      const uint32_t it = a.items[idx];
+      const int row = (int)(it >> 3), v = (int)(it & 7u) + 1;
+      if (row < a.row_begin || row >= a.row_begin + a.n_rows) continue;     // uniform
+      __syncthreads();             // sP / s_red of the previous item have been consumed
+      if (threadIdx.x < 18) sP[threadIdx.x] = a.P[(size_t)18 * row + threadIdx.x];
+      __syncthreads();
+      const int V = en_vwarps(a.pl_off[row + 1] - a.pl_off[row]);
+      grad_part(a, row, v, V, sP, s_red, s_en);
+      __syncthreads();
+      if (threadIdx.x < 54) {
+        const int i = threadIdx.x;
+        a.gpart[(size_t)54 * idx + i] = (s_red[0][i] + s_red[1][i]) + (s_red[2][i] + s_red[3][i]);
+      }
+      if (threadIdx.x == 64 && a.row_e)
+        a.row_e[(size_t)row * EN_REC + v] = -a.weight[row % a.n_tr] * ((s_en[0] + s_en[1]) + (s_en[2] + s_en[3]));
+    }
+    return;
+  }
+  const int row = a.row_begin + blockIdx.x;
+  const int robot = row / a.n_tr, tr = row - robot * a.n_tr;
+  if (threadIdx.x < 18) sP[threadIdx.x] = a.P[(size_t)18 * row + threadIdx.x];
+  __syncthreads();
+  const double w = a.weight[tr], m = a.margin;
+  const int V = en_vwarps(a.pl_off[row + 1] - a.pl_off[row]);
+  grad_part(a, row, 0, V, sP, s_red, s_en);
   // bound terms, threads 0..8
   double* out = a.terms + (size_t)ROW_REC * row;
   if (threadIdx.x < 9) {
@@ -598,10 +645,10 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
   __syncthreads();
   if (threadIdx.x < 54) {
     int i = threadIdx.x;
-    double v = (s_red[0][i] + s_red[1][i]) + (s_red[2][i] + s_red[3][i]);
+    double x = (s_red[0][i] + s_red[1][i]) + (s_red[2][i] + s_red[3][i]);
     int j = i / 9, q = i - 9 * j;
     double* o = out + (size_t)TERM_SZ * j;
-    o[q] = v;
+    o[q] = x;
     if (q < 3) o[9 + q] = 0.0;   // plane terms carry no time coupling
   }
   if (threadIdx.x == 64) {
@@ -609,14 +656,25 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
     for (int i = 0; i < 9; i++) { g += s_gt[i]; h += s_ht[i]; eb += s_eb[i]; }
     out[ROW_TERMS * TERM_SZ] = g;
     out[ROW_TERMS * TERM_SZ + 1] = h;
-    if (a.row_e) {                  // record of (trial 0, row): the whole plane energy in partial 0, zeros in the others
+    if (a.row_e) {                  // record of (trial 0, row): partial 0 of the plane energy (parts >= 1: the extra CTAs)
       double* re = a.row_e + (size_t)row * EN_REC;
       re[0] = -w * ((s_en[0] + s_en[1]) + (s_en[2] + s_en[3]));
-#pragma unroll
-      for (int v = 1; v < EN_VMAX; v++) re[v] = 0.0;
       re[EN_VMAX] = eb;
     }
   }
+}
+
+// plane-term value q (< 9) of term tt (< 6) of `row`: part 0 from the row record, parts 1 .. V-1 from the item records
+__device__ __forceinline__ double row_plane_term(const double* __restrict__ terms, const double* __restrict__ gpart,
+                                                 const uint32_t* __restrict__ item_base, const uint32_t* __restrict__ pl_off, size_t row,
+                                                 int tt, int q) {
+  double x = terms[(size_t)ROW_REC * row + TERM_SZ * tt + q];
+  const int V = en_vwarps(pl_off[row + 1] - pl_off[row]);
+  if (V > 1) {
+    const size_t base = item_base[row];
+    for (int v = 1; v < V; v++) x += gpart[(size_t)54 * (base + v - 1) + 9 * tt + q];
+  }
+  return x;
 }
 
 // ---- block-cooperative PSD projection of one 19x19 block (Gradient_admm.h:40-53) ------------------------------------------
@@ -793,6 +851,8 @@ __device__ __forceinline__ int cta384_psd_shift19(double* s_H) {
 // ---- gradient: per-piece 19x19 block -----------------------------------------------------------------------------
 struct PieceArgs {
   const double *terms, *basis, *convert;
+  const double* gpart;            // partial plane sums of the heavy rows (k_row_grad)
+  const uint32_t *item_base, *pl_off;
   const double *spline, *ptime, *pslack, *tslack, *plambda, *tlambda;
   double lambda, mu;
   int n_tr, res, P, T, robot_begin, project_psd;
@@ -826,7 +886,8 @@ __global__ void __launch_bounds__(384) k_piece(PieceArgs a) {
     int term = i / TERM_SZ, q = i - TERM_SZ * term;
     int rr = term / ROW_TERMS, tt = term - ROW_TERMS * rr;
     size_t row = (size_t)robot * a.n_tr + sp * a.res + rr;
-    s_t[i] = a.terms[(size_t)ROW_REC * row + TERM_SZ * tt + q];
+    s_t[i] = (tt < 6 && q < 9) ? row_plane_term(a.terms, a.gpart, a.item_base, a.pl_off, row, tt, q)
+                               : a.terms[(size_t)ROW_REC * row + TERM_SZ * tt + q];
   }
   if (threadIdx.x < 36) {
     // x1 = C^T (C bz - p_slack), x2 = C^T lambda ; index [m][k]
@@ -908,8 +969,15 @@ __global__ void __launch_bounds__(384) k_piece(PieceArgs a) {
 // ---- function-level: one row's block in piece coordinates ------------------------------------------------------------
 // which = 0: Gradient_admm::local_plane_barrier_gradient :331-407 (terms 0..5); which = 1: local_bound_gradient :409-572
 // (terms 6..14, plus g_t, h_t and the mixed time column).  out: g[18] | H[324 col-major] | g_t | h_t | partgrad[18]
-__global__ void k_row_expand(const double* __restrict__ terms, const double* __restrict__ B, int which, double* __restrict__ out) {
+__global__ void k_row_expand(const double* __restrict__ terms_all, const double* __restrict__ gpart, const uint32_t* __restrict__ item_base,
+                             const uint32_t* __restrict__ pl_off, int row, const double* __restrict__ B, int which,
+                             double* __restrict__ out) {
   __shared__ double s_a[ROW_TERMS * 6];
+  __shared__ double terms[ROW_REC];
+  for (int i = threadIdx.x; i < ROW_REC; i += blockDim.x) {
+    const int tt = i / TERM_SZ, q = i - TERM_SZ * tt;
+    terms[i] = (tt < 6 && q < 9) ? row_plane_term(terms_all, gpart, item_base, pl_off, (size_t)row, tt, q) : terms_all[(size_t)ROW_REC * row + i];
+  }
   const int t0 = which ? 6 : 0, t1 = which ? ROW_TERMS : 6;
   for (int i = threadIdx.x; i < ROW_TERMS * 6; i += blockDim.x) {
     const int tt = i / 6, mm = i - 6 * tt;
@@ -944,13 +1012,16 @@ __global__ void k_row_expand(const double* __restrict__ terms, const double* __r
 // geo.P of robot 0 and the resident planes must be current; fills out_dev[362]
 int row_blocks(tob_ctx* c, int tr, int which, double* out_dev) {
   TOB_CUDA(c, c->row_terms.ensure((size_t)ROW_REC * c->rows_all()));
+  TOB_TRY(grad_buffers(c));
   RowGradArgs a;
   a.P = c->geo.P.p; a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p; a.ptime = c->s_ptime.p;
   a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
-  a.n_tr = c->n_tr; a.row_begin = tr; a.terms = c->row_terms.p; a.dc = c->dc.p; a.row_e = nullptr; a.rows_all = c->rows_all();
-  k_row_grad<<<1, 128, 0, c->stream>>>(a);
+  a.n_tr = c->n_tr; a.row_begin = tr; a.n_rows = 1; a.terms = c->row_terms.p; a.dc = c->dc.p; a.row_e = nullptr; a.rows_all = c->rows_all();
+  a.items = c->en_items.p; a.gpart = c->gpart.p;
+  k_row_grad<<<1 + energy_extra(c, 1), 128, 0, c->stream>>>(a);
   TOB_LAUNCH_CHECK(c);
-  k_row_expand<<<1, 128, 0, c->stream>>>(c->row_terms.p + (size_t)ROW_REC * tr, c->d_basis.p + (size_t)36 * tr, which, out_dev);
+  k_row_expand<<<1, 128, 0, c->stream>>>(c->row_terms.p, c->gpart.p, c->en_item_base.p, c->pl_off.p, tr, c->d_basis.p + (size_t)36 * tr, which,
+                                         out_dev);
   TOB_LAUNCH_CHECK(c);
   return 0;
 }
@@ -966,16 +1037,18 @@ int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd) {
   RowGradArgs a;
   a.P = c->geo.P.p; a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p; a.ptime = c->s_ptime.p;
   a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
-  a.n_tr = c->n_tr; a.row_begin = rb * c->n_tr; a.terms = c->row_terms.p; a.dc = c->dc.p;
+  a.n_tr = c->n_tr; a.row_begin = rb * c->n_tr; a.n_rows = (re - rb) * c->n_tr; a.terms = c->row_terms.p; a.dc = c->dc.p;
   TOB_TRY(energy_buffers(c, TOB_LS_TRIALS));
-  a.row_e = c->row_e.p; a.rows_all = rows_total;
+  TOB_TRY(grad_buffers(c));
+  a.row_e = c->row_e.p; a.rows_all = rows_total; a.items = c->en_items.p; a.gpart = c->gpart.p;
   {
     Prof prof(c, K_ROW_GRAD);
-    k_row_grad<<<(re - rb) * c->n_tr, 128, 0, c->stream>>>(a);
+    k_row_grad<<<a.n_rows + energy_extra(c, a.n_rows), 128, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
   PieceArgs b;
   b.terms = c->row_terms.p; b.basis = c->d_basis.p; b.convert = c->d_convert.p;
+  b.gpart = c->gpart.p; b.item_base = c->en_item_base.p; b.pl_off = c->pl_off.p;
   b.spline = c->s_spline.p; b.ptime = c->s_ptime.p; b.pslack = c->s_pslack.p; b.tslack = c->s_tslack.p;
   b.plambda = c->s_plambda.p; b.tlambda = c->s_tlambda.p;
   b.lambda = c->prm.lambda; b.mu = c->prm.mu; b.n_tr = c->n_tr; b.res = c->prm.res; b.P = P; b.T = c->T;

@@ -187,6 +187,8 @@ struct tob_ctx {
 
   // energy / gradient / solve scratch
   tob::DBuf<uint32_t> en_items;       // virtual warps v >= 1 of the heavy rows of the current plane set (row << 3 | v - 1)
+  tob::DBuf<uint32_t> en_item_base;   // rows: position of the row's first item
+  tob::DBuf<double> gpart;            // items x 54: partial plane sums of the gradient pass
   tob::DBuf<double> row_e;            // trials x rows x TOB_EN_REC
   tob::DBuf<int> row_bad;             // robots x TOB_LS_TRIALS: trial infeasible (some d <= 0)
   tob::DBuf<double> row_terms;

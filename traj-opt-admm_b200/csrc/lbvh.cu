@@ -425,7 +425,9 @@ void bp_args(tob_ctx* c, int row_base, int rows, double d, BpArgs& a) {
   a.dc = c->dc.p;
   // enough CTAs to cover the machine a few times over, at most BP_THREADS tasks each
   uint32_t tpc = a.n_tasks / (4u * (uint32_t)c->sm_count);
-  a.tpc = tpc < 16u ? 16u : (tpc > (uint32_t)BP_THREADS ? (uint32_t)BP_THREADS : tpc);
+  static int tpc_cap = -1;
+  if (tpc_cap < 0) { const char* e = getenv("TRAJOPT_B200_BP_TPC"); tpc_cap = e ? atoi(e) : BP_THREADS; if (tpc_cap < 16 || tpc_cap > BP_THREADS) tpc_cap = BP_THREADS; }
+  a.tpc = tpc < 16u ? 16u : (tpc > (uint32_t)tpc_cap ? (uint32_t)tpc_cap : tpc);
 }
 
 // same for an arbitrary row range [row_base, row_base+rows) of geo.box (tob_box_query uses row 0 with a caller box)
@@ -472,6 +474,8 @@ int ensure_query_buffers(tob_ctx* c) {
   TOB_CUDA(c, c->cpl.ensure(4 * c->cand_cap + 4));
   TOB_CUDA(c, c->cflag.ensure(c->cand_cap + 1));
   TOB_CUDA(c, c->en_items.ensure((size_t)7 * rows + 8));   // barrier.cu: energy_items (EN_VMAX - 1 per row)
+  TOB_CUDA(c, c->en_item_base.ensure(rows + 1));
+  TOB_CUDA(c, c->gpart.ensure((size_t)54 * (7 * rows + 8)));
   TOB_CUDA(c, c->csum.ensure(c->cand_cap / 128 + 4)   /* >= chunks + 1 for any chunk size >= 128 */);
   TOB_CUDA(c, c->selfpre.ensure(rows + 2));
   TOB_CUDA(c, c->selfcnt.ensure(rows + 2));
