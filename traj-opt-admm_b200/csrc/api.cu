@@ -108,7 +108,7 @@ __global__ void k_fill_int(int* p, int n, int v) {
 // out the first batch of trial points: k=0 the current point, k=1.. the ladder step, step*0.8, step*0.8*0.8, ...
 __global__ void k_ls_init(int rb, int re, const int* kmax, const double* steps_tab, const double* selfstep, int use_self,
                           const double* ptime, const double* tdir, double* step, double* tstep, double* ttime, int* done,
-                          DevCounts* dc, int ls_rounds) {
+                          DevCounts* dc, int ls_rounds, int* bad) {
   int u = rb + blockIdx.x * blockDim.x + threadIdx.x;
   if (u == rb) {
     for (int r = 0; r < TOB_LS_MAXROUNDS + 1; r++) dc->ls_pending[r] = 0;
@@ -131,6 +131,7 @@ __global__ void k_ls_init(int rb, int re, const int* kmax, const double* steps_t
     s *= 0.8;
   }
   done[u] = 0;
+  for (int k = 0; k < TOB_LS_TRIALS; k++) bad[u * TOB_LS_TRIALS + k] = 0;   // infeasibility flags of the trial slots (barrier.cu)
 }
 
 // coupled mode (Optimization3D_multi::update_spline :585-636): ONE step and ONE piece time for all robots.
@@ -360,10 +361,15 @@ static int ensure_iter_buffers(tob_ctx* c) {
 // travel with the second exchange so that all ranks agree on whether the iteration commits.
 // few rows: cover 8 rungs per launch (latency); many rows: one rung per round (throughput), more rounds ahead
 static void ls_policy(tob_ctx* c, int rb, int re, bool coupled) {
-  const bool many = !coupled && (long long)(re - rb) * c->n_tr >= 4096;
-  c->ls_kte0 = many ? 3 : TOB_LS_TRIALS;
-  c->ls_kte = TOB_LS_TRIALS;
-  c->ls_rounds = many ? 3 : 2;
+  // few rows (latency regime): one launch covers 8 rungs, 2 rounds ahead.  Many rows (throughput regime, >= 8192): most
+  // robots accept the first rung, so round 0 evaluates only that one (the energy of the current point comes from the
+  // gradient pass) and the robots that keep backtracking get 4 rungs per later round, 5 rounds ahead = 17 rungs before the
+  // host has to continue a search.  Measured on the 1024-problem batch: (3, 9, 3) 4.89 ms of energy kernels per iteration,
+  // (3, 5, 4) 4.09, (2, 5, 4) 3.76, (2, 9, 3) 5.11.
+  const bool many = !coupled && (long long)(re - rb) * c->n_tr >= 8192;
+  c->ls_kte0 = many ? 2 : TOB_LS_TRIALS;
+  c->ls_kte = many ? 5 : TOB_LS_TRIALS;
+  c->ls_rounds = many ? 5 : 2;
   if (const char* e = getenv("TRAJOPT_B200_LS")) {          // "kte0,kte,rounds": tuning / experiments
     int k0 = 0, k = 0, r = 0;
     if (!coupled && sscanf(e, "%d,%d,%d", &k0, &k, &r) == 3 && k0 >= 2 && k0 <= TOB_LS_TRIALS && k >= 2 && k <= TOB_LS_TRIALS &&
@@ -424,11 +430,10 @@ static int iterate_launch(tob_ctx* c, int mode) {
   } else {
     k_ls_init<<<div_up(re - rb, 64), 64, 0, st>>>(rb, re, c->kmax.p, c->d_steps.p, c->s_selfstep.p, U > 1 ? 1 : 0, c->s_ptime.p,
                                                   c->s_tdir.p, c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p,
-                                                  c->ls_rounds);
+                                                  c->ls_rounds, c->row_bad.p);
     TOB_LAUNCH_CHECK(c);
     wolfe_idx = U > 1 ? U - 1 : -1;
   }
-  if (!coupled) TOB_TRY(line_search_begin(c, rb, re));
   c->ls_e0_ready = !coupled;         // gradient_blocks ran at this very point with these planes: slot 0 holds E(x)
   TOB_TRY(ls_launch_ahead(c, rb, re, wolfe_idx, coupled));
   // (5) step, slack + dual: guarded on the device (see iterate_once)
@@ -1258,10 +1263,10 @@ int tob_line_search(tob_ctx* c, int robot, tob_state* st, const double* directio
     TOB_TRY(upload(c, c->s_selfstep, step_io, 1, robot));
     use_self = 1;
   }
-  k_ls_init<<<1, 64, 0, c->stream>>>(robot, robot + 1, c->kmax.p, c->d_steps.p, c->s_selfstep.p, use_self, c->s_ptime.p, c->s_tdir.p,
-                                     c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p, c->ls_rounds);
-  TOB_LAUNCH_CHECK(c);
   TOB_TRY(line_search_begin(c, robot, robot + 1));
+  k_ls_init<<<1, 64, 0, c->stream>>>(robot, robot + 1, c->kmax.p, c->d_steps.p, c->s_selfstep.p, use_self, c->s_ptime.p, c->s_tdir.p,
+                                     c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p, c->ls_rounds, c->row_bad.p);
+  TOB_LAUNCH_CHECK(c);
   c->ls_e0_ready = false;            // function-level call: the starting point is evaluated by the energy kernel
   TOB_TRY(line_search(c, robot, robot + 1, -1));
   TOB_CUDA(c, cudaMemcpyAsync(st->spline, c->s_spline.p + (size_t)robot * 3 * T, 3 * T * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

@@ -379,10 +379,11 @@ static int energy_extra(tob_ctx* c, int nrows) {
 }
 
 // list the virtual warps v >= 1 of the current plane CSR (c->pl_off): after every plane pass / plane upload
-int energy_items(tob_ctx* c) {
+// reset: the item counter is not already zero (the plane pass zeroes it in k_np_top)
+int energy_items(tob_ctx* c, bool reset) {
   const int rows = c->rows_all();
   TOB_CUDA(c, c->en_items.ensure((size_t)(EN_VMAX - 1) * rows + 8));    // at most EN_VMAX - 1 listed virtual warps per row
-  TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->n_en_items, 0, sizeof(uint32_t), c->stream));
+  if (reset) TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->n_en_items, 0, sizeof(uint32_t), c->stream));
   TOB_CUDA(c, c->en_item_base.ensure((size_t)rows + 1));
   k_en_items<<<div_up(rows, 256), 256, 0, c->stream>>>(c->pl_off.p, rows, c->en_items.p, c->en_item_base.p, c->dc.p);
   TOB_LAUNCH_CHECK(c);
@@ -439,12 +440,11 @@ int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* t
   return 0;
 }
 
-// the infeasibility flags of robots [rb,re) start cleared at the beginning of a line search (k_robot_ls clears the slots it
-// lays out anew for the following rounds)
+// buffers of a line search (the infeasibility flags of the trial slots are cleared by k_ls_init, and by k_robot_ls for the
+// slots it lays out anew)
 int line_search_begin(tob_ctx* c, int rb, int re) {
-  TOB_TRY(energy_buffers(c, TOB_LS_TRIALS));
-  TOB_CUDA(c, cudaMemsetAsync(c->row_bad.p + (size_t)rb * TOB_LS_TRIALS, 0, (size_t)(re - rb) * TOB_LS_TRIALS * sizeof(int), c->stream));
-  return 0;
+  (void)rb; (void)re;
+  return energy_buffers(c, TOB_LS_TRIALS);
 }
 
 // k0e: first trial the ENERGY launch evaluates (k0, or k0 + 1 = 1 when slot 0 was already written by the gradient pass at

@@ -346,7 +346,7 @@ int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* t
 // are already done are skipped on the device; robots still backtracking are counted in dc->ls_pending[slot]
 int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int kte, int slot, int k0e);
 int line_search_begin(tob_ctx* c, int rb, int re);
-int energy_items(tob_ctx* c);   // after every new plane CSR: lists the extra virtual warps of the heavy rows   // clears the infeasibility flags of the robots' trial slots
+int energy_items(tob_ctx* c, bool reset);   // after every new plane CSR: lists the extra virtual warps of the heavy rows   // clears the infeasibility flags of the robots' trial slots
 #define TOB_EN_REC 9   // doubles per (trial, row) in row_e: 8 plane-energy partials + the bound energy (barrier.cu: EN_REC)
 int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd);
 int row_blocks(tob_ctx* c, int tr, int which, double* out_dev);

@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(1024) k_np_top(PackArgs a) {
     a.selfpre[row] = (a.with_self && row >= a.self_begin && row < a.self_end) ? a.selfcnt[row] : 0u;
   __syncthreads();
   const uint32_t self_total = cta1024_scan_inplace(a.selfpre, (uint32_t)a.rows_all);
+  if (threadIdx.x == 0) a.dc->n_en_items = 0;     // the listed parts of heavy rows are rebuilt from the new CSR (barrier.cu)
   if (threadIdx.x == 0 && a.live) {
     a.csum[n_chunks] = ob_total;
     a.selfpre[a.rows_all] = 0;
@@ -598,13 +599,13 @@ static int pack_rows(tob_ctx* c, int rb, int re, bool ws, bool live = false) {
     k_np_top<<<1, 1024, 0, st>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
-  if (live) { TOB_TRY(live_rows(c)); return energy_items(c); }
+  if (live) { TOB_TRY(live_rows(c)); return energy_items(c, false); }
   {
     Prof prof(c, K_PACK);
     k_pack<<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
-  return energy_items(c);
+  return energy_items(c, false);   // k_np_top zeroed the counter
 }
 
 // candidates (c->cand_*, c->row_off, dc->n_cand) + row geometry must be current.  Leaves the packed plane CSR.
@@ -674,7 +675,7 @@ int pack_planes_from_host(tob_ctx* c, int rb, int re, const uint32_t* offsets, c
   TOB_CUDA(c, cudaMemcpyAsync(c->pl.p, pl.data(), (4 * np + 4) * sizeof(double), cudaMemcpyHostToDevice, st));
   TOB_CUDA(c, cudaMemcpyAsync(c->pl_row.p, prow.data(), (np + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   TOB_CUDA(c, cudaMemcpyAsync(&c->dc.p->n_planes, np32, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-  TOB_TRY(energy_items(c));
+  TOB_TRY(energy_items(c, true));
   TOB_CUDA(c, cudaStreamSynchronize(st));
   c->n_planes = np;
   return 0;
