@@ -5,6 +5,9 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# new device allocations of the library are filled with 0xFF bytes in the tests: reads of never-written memory must not pass
+# by the luck of zero pages (csrc/ctx.cuh: poison_allocations)
+os.environ.setdefault("TRAJOPT_B200_POISON", "1")
 sys.path.insert(0, os.path.join(ROOT, "traj-opt-admm_b200"))
 sys.path.insert(0, ROOT)
 

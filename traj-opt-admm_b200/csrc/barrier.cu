@@ -872,6 +872,9 @@ __global__ void __launch_bounds__(384) k_piece(PieceArgs a) {
   double* s_x = s_L + 361;                // 36: x1 (18) x2 (18) as [m][k]
   double* s_sc = s_x + 36;                // gt, ht
   const double* C = a.convert + (size_t)36 * sp;
+  // the plane CSR of this iteration was not built (candidate overflow: the host grows the buffers and repeats the
+  // iteration): pl_off / the listed parts are stale, nothing below may be indexed with them
+  if (a.dc->overflow & TOB_OVF_RETRY) return;
   for (int i = threadIdx.x; i < nterm * 6; i += blockDim.x) {
     int term = i / 6, mm = i - 6 * term;
     int rr = term / ROW_TERMS, tt = term - ROW_TERMS * rr;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <string>
@@ -21,6 +22,15 @@ namespace tob {
 inline std::atomic<unsigned long long>& alloc_generation() {   // process-wide: contexts of several host threads share it
   static std::atomic<unsigned long long> g{0};
   return g;
+}
+
+// TRAJOPT_B200_POISON=1 (set by tests/conftest.py): every new device allocation is filled with 0xFF bytes (NaN doubles,
+// 0xffffffff indices), so that a read of memory nobody wrote shows up in the tests instead of depending on what the
+// allocator hands out (a fresh process gets zero pages, a long-lived one does not)
+inline bool poison_allocations() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("TRAJOPT_B200_POISON"); on = (e && e[0] && e[0] != '0') ? 1 : 0; }
+  return on == 1;
 }
 
 // growable device buffer (contents are NOT preserved on growth); owns its allocation (move-only)
@@ -45,6 +55,7 @@ struct DBuf {
     alloc_generation()++;
     cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
     if (e == cudaSuccess) cap = want;
+    if (e == cudaSuccess && poison_allocations()) e = cudaMemset(p, 0xff, want * sizeof(T));
     return e;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
