@@ -552,8 +552,8 @@ TOB_HD void kdop_extents(const double (*pts)[3], const double* kdop, double* lo,
 // a time is a ~200-cycle dependent chain per axis, ~10 k cycles for a candidate that passes).  Same comparisons, same
 // decision as the axis-by-axis loop of the reference (CCD.h:376-389).
 TOB_HD bool kdop_point_overlap(const double* lo, const double* hi, const double* kdop, const double* q, double d,
-                               unsigned* groups = nullptr) {
-  for (int g = 0; g < TOB_KDOP_AXES; g += 7) {
+                               unsigned* groups = nullptr, int axis_begin = 0, int axis_end = TOB_KDOP_AXES) {
+  for (int g = axis_begin; g < axis_end; g += 7) {
     bool sep = false;
     if (groups) ++*groups;            // work counter (bench.py roofline): 7-axis groups really evaluated
 #pragma unroll

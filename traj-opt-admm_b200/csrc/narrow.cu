@@ -73,10 +73,33 @@ __device__ __forceinline__ uint32_t np_per_of(uint32_t n, uint32_t grid) {
 }
 
 // MINB = resident CTAs per SM the register allocation is made for (4: 128 registers, 5: 102, 6: 85, 8: 64)
+// block-wide stable compaction step: the threads with `keep` append `value` to list[count ...] in thread order; returns the
+// new count (uniform).  Two barriers; s_w is scratch of NP_THREADS / 32 words.
+__device__ __forceinline__ uint32_t np_append(bool keep, uint32_t value, uint32_t* list, uint32_t count, uint32_t* s_w) {
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t bm = __ballot_sync(0xffffffffu, keep);
+  __syncthreads();                 // s_w of the previous step has been consumed
+  if (lane == 0) s_w[w] = __popc(bm);
+  __syncthreads();
+  uint32_t base = count, tot = 0;
+#pragma unroll
+  for (int k = 0; k < NP_THREADS / 32; k++) {
+    if (k < (int)w) base += s_w[k];
+    tot += s_w[k];
+  }
+  if (keep) list[base + __popc(bm & ((1u << lane) - 1u))] = value;
+  return count + tot;
+}
+
+// The 49-DOP gate runs in two stages with a compaction in between: 44 % of the candidates of the batched workload are
+// rejected, on average after 1.7 of the 7 axis groups, while the others need all 7 -- thread-per-candidate over all groups
+// left 20 of 32 lanes active (ncu).  Stage 1 (the first NP_GATE1 axes) runs on every candidate, stage 2 (the rest) and GJK on
+// dense survivor lists.
+#define NP_GATE1 14
 template <int MINB>
 __global__ void __launch_bounds__(NP_THREADS, MINB) k_narrow(NarrowArgs a) {
   __shared__ double s_kdop[3 * TOB_KDOP_AXES];
-  __shared__ uint32_t s_surv[NP_CHUNK];
+  __shared__ uint32_t s_surv[NP_CHUNK], s_surv2[NP_CHUNK];
   __shared__ uint32_t s_w[NP_THREADS / 32];
   for (int i = threadIdx.x; i < 3 * TOB_KDOP_AXES; i += blockDim.x) s_kdop[i] = a.kdop[i];
   const uint32_t n = a.dc->n_cand;
@@ -88,7 +111,7 @@ __global__ void __launch_bounds__(NP_THREADS, MINB) k_narrow(NarrowArgs a) {
   unsigned w_groups = 0, w_iters = 0;   // counted work of this thread
   __syncthreads();
   for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    uint32_t n_surv = 0;   // uniform
+    uint32_t n_surv = 0, n_surv2 = 0;   // uniform
     // the candidates of this thread are gathered first (index -> row / point -> coordinates are two dependent global loads
     // each; one after the other behind the block barriers of the compaction they cost four round trips instead of one)
     uint32_t c_row[NP_PER];
@@ -103,6 +126,7 @@ __global__ void __launch_bounds__(NP_THREADS, MINB) k_narrow(NarrowArgs a) {
         c_pt[q][0] = a.px[p]; c_pt[q][1] = a.py[p]; c_pt[q][2] = a.pz[p];
       }
     }
+    // stage 1: the first NP_GATE1 axes, every candidate
 #pragma unroll
     for (uint32_t q = 0; q < NP_PER; q++) {
       if (q >= per) break;   // uniform
@@ -111,32 +135,38 @@ __global__ void __launch_bounds__(NP_THREADS, MINB) k_narrow(NarrowArgs a) {
       if (i < n) {
         const uint32_t row = c_row[q];
         pass = kdop_point_overlap(a.klo + (size_t)TOB_KDOP_AXES * row, a.khi + (size_t)TOB_KDOP_AXES * row, s_kdop, c_pt[q], a.dist,
-                                  &w_groups);
+                                  &w_groups, 0, NP_GATE1);
         a.cflag[i] = 0;
       }
-      const uint32_t bm = __ballot_sync(0xffffffffu, pass);
-      __syncthreads();                 // s_w of the previous pass has been consumed
-      if (lane == 0) s_w[w] = __popc(bm);
-      __syncthreads();
-      uint32_t base = n_surv, tot = 0;
-#pragma unroll
-      for (int k = 0; k < NP_THREADS / 32; k++) {
-        if (k < (int)w) base += s_w[k];
-        tot += s_w[k];
-      }
-      if (pass) s_surv[base + __popc(bm & ((1u << lane) - 1u))] = loc;
-      n_surv += tot;
+      n_surv = np_append(pass, loc, s_surv, n_surv, s_w);
     }
     __syncthreads();
-    uint32_t ok = 0;
-    for (uint32_t sidx = tid; sidx < n_surv; sidx += NP_THREADS) {
-      const uint32_t ii = chunk * chunk_sz + s_surv[sidx];
-      const uint32_t row = a.cand_row[ii], p = a.cand_pt[ii];
-      if (n_live) {   // is_seperate[tr_id][ob_id] (Optimization3D_admm.h:128): a live pair keeps its plane
-        const unsigned long long key = ((unsigned long long)row << 32) | p;
-        const uint32_t at = lower_bound_u64(a.live_key, n_live, key);
-        if (at < n_live && a.live_key[at] == key) continue;
+    // stage 2: the remaining axes on the dense list of stage-1 survivors
+    for (uint32_t s0 = 0; s0 < n_surv; s0 += NP_THREADS) {      // uniform trip count
+      const uint32_t sidx = s0 + tid;
+      bool pass = false;
+      uint32_t loc = 0;
+      if (sidx < n_surv) {
+        loc = s_surv[sidx];
+        const uint32_t ii = chunk * chunk_sz + loc;
+        const uint32_t row = a.cand_row[ii], p = a.cand_pt[ii];
+        const double pt[3] = {a.px[p], a.py[p], a.pz[p]};
+        pass = kdop_point_overlap(a.klo + (size_t)TOB_KDOP_AXES * row, a.khi + (size_t)TOB_KDOP_AXES * row, s_kdop, pt, a.dist, &w_groups,
+                                  NP_GATE1, TOB_KDOP_AXES);
+        if (pass && n_live) {   // is_seperate[tr_id][ob_id] (Optimization3D_admm.h:128): a live pair keeps its plane
+          const unsigned long long key = ((unsigned long long)row << 32) | p;
+          const uint32_t at = lower_bound_u64(a.live_key, n_live, key);
+          if (at < n_live && a.live_key[at] == key) pass = false;
+        }
       }
+      n_surv2 = np_append(pass, loc, s_surv2, n_surv2, s_w);
+    }
+    __syncthreads();
+    // GJK + plane on the dense list of gate survivors
+    uint32_t ok = 0;
+    for (uint32_t sidx = tid; sidx < n_surv2; sidx += NP_THREADS) {
+      const uint32_t ii = chunk * chunk_sz + s_surv2[sidx];
+      const uint32_t row = a.cand_row[ii], p = a.cand_pt[ii];
       const double pt[3] = {a.px[p], a.py[p], a.pz[p]};
       double P[6][3], c[3], d;
       load_pts6(a.P + (size_t)18 * row, P);
