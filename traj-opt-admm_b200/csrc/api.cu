@@ -387,9 +387,21 @@ static int iterate_launch(tob_ctx* c, int mode) {
   cudaStream_t st = c->stream;
   const bool coupled = mode == 1;
   const bool shard = c->sharded() && U > 1;
-  // (1) control points of every robot are needed for the inter-robot planes
-  if (shard) TOB_TRY(exchange_robots(c, c->s_spline.p, (size_t)3 * c->T, sizeof(double)));
-  TOB_TRY(separate_resident(c, rb, re, U > 1));
+  // (1) planes.  The control points of the other robots are only needed for the inter-robot planes: the all-gather runs on
+  // the side stream next to the obstacle pass of the owned robots (rows, broadphase, 49-DOP + GJK)
+  if (shard) {
+    TOB_TRY(exchange_fork(c));
+    TOB_TRY(exchange_robots(c, c->s_spline.p, (size_t)3 * c->T, sizeof(double)));
+    TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, rb, re, 1));
+    TOB_TRY(broadphase(c, rb, re, c->prm.offset + c->prm.margin, 1));
+    TOB_TRY(narrowphase_planes(c, rb, re, -1));
+    TOB_TRY(exchange_join(c));
+    if (rb > 0) TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, 0, rb, 1));
+    if (re < U) TOB_TRY(compute_rows(c, c->s_spline.p, nullptr, nullptr, re, U, 1));
+    TOB_TRY(narrowphase_finish(c, rb, re, 1));
+  } else {
+    TOB_TRY(separate_resident(c, rb, re, U > 1));
+  }
   // (2) Newton direction (geo.P of the owned rows is still current from the plane pass)
   TOB_TRY(gradient_blocks(c, rb, re, 1));
   if (coupled) TOB_TRY(solve_coupled(c));
@@ -397,9 +409,11 @@ static int iterate_launch(tob_ctx* c, int mode) {
   // (3) CCD step bound
   if (U > 1) {
     if (shard) {
-      // one grouped exchange: directions (+ wolfe, gnorm of the decoupled solves) and every rank's overflow / error bits
+      // one grouped exchange on the side stream: directions (+ wolfe, gnorm of the decoupled solves) and every rank's
+      // overflow / error bits; next to it the obstacle CCD of the owned robots, which needs their own directions only
       k_flags_pack<<<1, 1, 0, st>>>(c->dc.p, c->ovf_all.p, c->comm_rank);
       TOB_LAUNCH_CHECK(c);
+      TOB_TRY(exchange_fork(c));
       TOB_TRY(exchange_group_begin(c));
       TOB_TRY(exchange_robots(c, c->s_dir.p, (size_t)3 * c->T, sizeof(double)));
       if (!coupled) {
@@ -408,15 +422,22 @@ static int iterate_launch(tob_ctx* c, int mode) {
       }
       TOB_TRY(exchange_ranks(c, c->ovf_all.p));
       TOB_TRY(exchange_group_end(c));
+      TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, rb, re, 3));
+      TOB_TRY(ccd_position_steps(c, rb, re));
+      TOB_TRY(exchange_join(c));
       k_flags_merge<<<1, 1, 0, st>>>(c->dc.p, c->ovf_all.p, c->comm_rank, c->comm_world);
       TOB_LAUNCH_CHECK(c);
+      if (rb > 0) TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, 0, rb, 3));
+      if (re < U) TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, re, U, 3));
+    } else {
+      TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, 0, U, 3));
     }
-    TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, 0, U, 3));
     TOB_TRY(self_ccd_steps(c, coupled ? 1 : 0, c->s_selfstep.p));
+    if (!shard) TOB_TRY(ccd_position_steps(c, rb, re));
   } else {
     TOB_TRY(compute_rows(c, c->s_spline.p, c->s_dir.p, nullptr, rb, re, 3));
+    TOB_TRY(ccd_position_steps(c, rb, re));
   }
-  TOB_TRY(ccd_position_steps(c, rb, re));
   // (4) Armijo; multi-robot: every robot uses the LAST robot's wolfe (global overwritten, Optimization3D_multi.h:730,792)
   int wolfe_idx = -1;
   ls_policy(c, rb, re, coupled);

@@ -97,7 +97,29 @@ int comm_attach(tob_ctx* c, void* comm, bool owned) {
   c->ag = nullptr; c->ar = nullptr; c->cb_user = nullptr;
   if (c->have_params) shard_partition(c);
   TOB_CUDA(c, c->ovf_all.ensure((size_t)world + 1));
+  if (!c->comm_stream) {
+    TOB_CUDA(c, cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    TOB_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    TOB_CUDA(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  }
   if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; c->graph_mode = -1; }
+  return 0;
+}
+
+// fork: what follows on the exchange stream waits for everything enqueued on the main stream so far
+int exchange_fork(tob_ctx* c) {
+  if (!c->nccl_comm || !c->comm_stream) return 0;
+  TOB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+  TOB_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_fork, 0));
+  c->xs = c->comm_stream;
+  return 0;
+}
+// join: the main stream waits for the exchanges issued since the fork
+int exchange_join(tob_ctx* c) {
+  if (!c->xs) return 0;
+  TOB_CUDA(c, cudaEventRecord(c->ev_join, c->comm_stream));
+  TOB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  c->xs = nullptr;
   return 0;
 }
 
@@ -128,17 +150,18 @@ int exchange_robots(tob_ctx* c, void* buf, size_t elems_per_robot, size_t elem_s
     const size_t unit = elem_size == 8 || elem_size == 4 ? 1 : elem_size;   // other sizes travel as bytes
     const size_t stride = elems_per_robot * elem_size;                      // bytes per robot
     const int W = c->comm_world;
+    cudaStream_t xs = c->xs ? c->xs : c->stream;
     bool equal = true;
     for (int r = 1; r < W; r++) equal = equal && c->shard_count[r] == c->shard_count[0];
     char* base = (char*)buf;
     if (equal) {
       const size_t cnt = (size_t)c->shard_count[0] * elems_per_robot * unit;
-      TOB_NCCL(c, n->AllGather(base + (size_t)c->own_begin * stride, base, cnt, dt, comm, c->stream));
+      TOB_NCCL(c, n->AllGather(base + (size_t)c->own_begin * stride, base, cnt, dt, comm, xs));
     } else {
       TOB_NCCL(c, n->GroupStart());
       for (int r = 0; r < W; r++) {
         char* p = base + (size_t)c->shard_first[r] * stride;
-        TOB_NCCL(c, n->Broadcast(p, p, (size_t)c->shard_count[r] * elems_per_robot * unit, dt, r, comm, c->stream));
+        TOB_NCCL(c, n->Broadcast(p, p, (size_t)c->shard_count[r] * elems_per_robot * unit, dt, r, comm, xs));
       }
       TOB_NCCL(c, n->GroupEnd());
     }
@@ -156,7 +179,7 @@ int exchange_robots(tob_ctx* c, void* buf, size_t elems_per_robot, size_t elem_s
 int exchange_ranks(tob_ctx* c, double* buf) {
   if (c->nccl_comm) {
     NcclApi* n = nccl_api();
-    TOB_NCCL(c, n->AllGather(buf + c->comm_rank, buf, 1, ncclFloat64, (ncclComm_t)c->nccl_comm, c->stream));
+    TOB_NCCL(c, n->AllGather(buf + c->comm_rank, buf, 1, ncclFloat64, (ncclComm_t)c->nccl_comm, c->xs ? c->xs : c->stream));
     return 0;
   }
   if (c->ag && c->ag(buf, 1, c->cb_user)) return fail_msg(c, "all-gather callback failed");

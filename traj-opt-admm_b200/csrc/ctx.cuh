@@ -154,6 +154,11 @@ struct tob_ctx {
   tob::DBuf<double> ovf_all;          // one word per rank: its overflow / error bits of the current iteration
   tob::DBuf<double> cpl_part, cpl_zy; // coupled solve: 7 Schur sums per robot (exchanged) / z, y of the owned robots
   bool sharded() const { return ag != nullptr || nccl_comm != nullptr; }
+  // the NCCL exchanges of an iteration run on a side stream forked from / joined to `stream` (also inside the captured
+  // graph), next to the obstacle work of the owned robots that does not need the other robots' data
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t xs = nullptr;          // stream the exchange functions use (null: `stream`)
   bool states_valid = false;
   tob::DBuf<double> s_spline, s_ptime, s_pslack, s_tslack, s_plambda, s_tlambda;
   tob::DBuf<double> s_dir, s_tdir, s_wolfe, s_gnorm;
@@ -253,6 +258,9 @@ struct tob_ctx {
   ~tob_ctx() {                        // device buffers release themselves (DBuf); the rest is owned here
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
     tob::comm_release(this);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (comm_stream) cudaStreamDestroy(comm_stream);
     for (auto& r : prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : prof_pool) cudaEventDestroy(e);
     if (h_pinned) cudaFreeHost(h_pinned);
@@ -341,7 +349,8 @@ int grow_cand_capacity(tob_ctx* c, uint64_t need);
 // segments.cu : mode bits: 1 = k-DOP extents, 2 = direction rows + swept box, 4 = trial point spline+step*dir
 int compute_rows(tob_ctx* c, const double* spline_dev, const double* dir_dev, const double* step_dev, int rb, int re, int mode);
 // narrow.cu
-int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self);
+int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self);   // with_self < 0: obstacle candidates only, no packing
+int narrowphase_finish(tob_ctx* c, int rb, int re, int with_self);
 int pack_planes_from_host(tob_ctx* c, int rb, int re, const uint32_t* offsets, const double* cc, const double* dd);
 int ccd_position_steps(tob_ctx* c, int rb, int re);
 int self_planes(tob_ctx* c);
@@ -366,6 +375,8 @@ int exchange_robots(tob_ctx* c, void* buf, size_t elems_per_robot, size_t elem_s
 int exchange_ranks(tob_ctx* c, double* buf);    // one FP64 word per rank
 int exchange_group_begin(tob_ctx* c);
 int exchange_group_end(tob_ctx* c);
+int exchange_fork(tob_ctx* c);    // the exchanges that follow run on the side stream, after what is on the main stream now
+int exchange_join(tob_ctx* c);    // the main stream waits for them
 void shard_partition(tob_ctx* c);
 // solve.cu
 int solve_directions(tob_ctx* c, int rb, int re, int dense_shift);

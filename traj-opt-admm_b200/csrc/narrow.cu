@@ -667,9 +667,18 @@ int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self) {
     else k_narrow<4><<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
+  if (with_self < 0) return 0;      // obstacle part only: the caller finishes with narrowphase_finish()
   bool ws = with_self && c->n_robots() > 1;
   if (ws) TOB_TRY(self_planes(c));
   return pack_rows(c, rb, re, ws, live);
+}
+
+// second half of the plane pass when the first was launched with with_self < 0: inter-robot planes (need geo of ALL
+// robots), then the packing of both kinds into the CSR
+int narrowphase_finish(tob_ctx* c, int rb, int re, int with_self) {
+  bool ws = with_self && c->n_robots() > 1;
+  if (ws) TOB_TRY(self_planes(c));
+  return pack_rows(c, rb, re, ws, c->live_planes());
 }
 
 // inter-robot planes only (Optimization3D_multi::separate_self on empty lists): geo of ALL robots must be current
