@@ -40,7 +40,11 @@ UNIT = "iter/s"
 
 # ---- algorithmic work per unit.  The pair kernels are costed from COUNTED work (device counters: 49-DOP groups evaluated,
 # GJK rounds run, barrier terms inside the band), not from a worst-case constant per candidate; per-unit flop figures:
-FLOP_KDOP_GROUP = 7 * (5 + 2)           # one group of 7 axes against precomputed extents: level (3 mul 2 add) + 2 subtractions
+FLOP_KDOP_GROUP = 7 * (5 + 2)           # one group of 7 axes against precomputed extents: level (3 mul 2 add) + 2 subtractions.
+                                        # SINGLE precision since round 2 (filter of the gate, gjk.cuh: kdop_point_gate): reported
+                                        # as fp32 work, NOT in the FP64 roofline of k_narrow
+FLOP_KDOP_EXACT_AXIS = 7                # an axis the filter could not decide, re-tested in FP64
+FLOP_KDOP_SHIFT = 3                     # per gate call: the point relative to the row's centre (3 FP64 subtractions)
 FLOP_GJK61_ROUND = 45 + 120             # support over 6 points (30) + tests (15) + signed-volume sub-algorithm (S1D 30 / S2D 130 / S3D 330)
 FLOP_GJK121_ROUND = 75 + 120            # same with 12 swept points
 FLOP_PLANE_FINISH = 30                  # norm, normalise, d
@@ -62,7 +66,8 @@ def kernel_models(per_step, geo):
     e_evals = max(evals - planes, 0.0)                      # line-search passes (the gradient pass streams each plane once)
     g_share = planes / evals if evals else 0.0
     n_sys = 3 * (T - 4) + 1
-    np_flop = FLOP_KDOP_GROUP * per_step["np_kdop_groups"] + FLOP_GJK61_ROUND * per_step["np_gjk_iters"] + FLOP_PLANE_FINISH * planes
+    np_flop = (FLOP_GJK61_ROUND * per_step["np_gjk_iters"] + FLOP_PLANE_FINISH * planes
+               + FLOP_KDOP_EXACT_AXIS * per_step.get("np_kdop_exact", 0.0) + FLOP_KDOP_SHIFT * 2 * cand)
     ccd_flop = FLOP_KDOP_SWEPT * per_step["ccd_kdop_pass"] + FLOP_GJK121_ROUND * per_step["ccd_gjk_iters"]
     return {
         "k_rows": (0.0, rows * (18 + 6 + 2 * 49) * 8.0 * 2, "hbm"),
@@ -468,6 +473,8 @@ def run_ours(args):
                       "fp64_pipe_active_pct_ncu": m.get("fp64_pipe_pct"),
                       "frac": (flop / sec / 1e12 / fp64_peak) if bound == "fp64" and fp64_peak else byts / sec / 1e9 / hbm_peak,
                       "share_of_step": kms / tot_prof_ms if tot_prof_ms else None}
+        if name == "k_narrow":      # the 49-DOP gate runs through a single-precision filter: its work is not in the FP64 figure
+            ktab[name]["tflops_fp32_gate_counted"] = FLOP_KDOP_GROUP * per_step.get("np_kdop_groups", 0.0) / sec / 1e12
     roof = None
     if ktab:
         name = max(ktab, key=lambda k: ktab[k]["ms_per_step"])
@@ -501,7 +508,7 @@ def run_ours(args):
         "config": describe(args, world),
         "pair_evals_per_s": pair_evals / (total_ms * 1e-3),
         "pairs_per_step": {k: ctr[k] / args.steps for k in ("dcd_candidates", "planes", "ccd_candidates", "energy_plane_evals", "barrier_terms",
-                                                             "np_kdop_groups", "np_gjk_iters", "ccd_kdop_pass", "ccd_gjk_iters", "line_search_trials")},
+                                                             "np_kdop_groups", "np_gjk_iters", "np_kdop_exact", "ccd_kdop_pass", "ccd_gjk_iters", "line_search_trials")},
         "e2e": {"value": mult * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": state_bytes * world, "d2h_bytes_per_step": state_bytes * world},
         "gpu_launches": int(pe[1]),
         "clocks": sampler.summary(),

@@ -239,10 +239,11 @@ typedef struct tob_counters {
   uint64_t live_planes;          /* persistent-plane mode: live (sub-segment, point) planes */
   uint64_t refine_capped;        /* plane refinements stopped by a loop cap (the reference's loops are unbounded) */
   /* counted work (not a model): what the narrowphase / CCD kernels really executed */
-  uint64_t np_kdop_groups;       /* 7-axis groups of the 49-DOP gate evaluated (49 axes = 7 groups, early exit between groups) */
+  uint64_t np_kdop_groups;       /* 7-axis groups of the 49-DOP gate evaluated (49 axes = 7 groups, early exit between groups; FP32 filter) */
   uint64_t np_gjk_iters;         /* GJK(6,1) rounds run for the k-DOP survivors */
   uint64_t ccd_gjk_iters;        /* GJK(12,1) rounds run by the CCD ladder */
   uint64_t ccd_kdop_pass;        /* swept candidates that passed the swept 49-DOP gate */
+  uint64_t np_kdop_exact;        /* axes of the 49-DOP gate the single-precision filter left undecided (re-tested in FP64) */
 } tob_counters;
 int tob_get_counters(const tob_ctx* ctx, tob_counters* out);
 int tob_reset_counters(tob_ctx* ctx);

@@ -68,6 +68,12 @@ def _num(x):
         return None
 
 
+def _kname(full):
+    """'void tob::k_narrow<4, true>(NarrowArgs)' -> 'k_narrow' (the names bench.py uses)"""
+    n = full.split("(")[0].replace("void ", "").replace("tob::", "").strip()
+    return n.split("<")[0]
+
+
 def rawcsv(src, dst, workload=None):
     import json
     import os
@@ -76,7 +82,7 @@ def rawcsv(src, dst, workload=None):
     per = defaultdict(list)
     for r in rows[2:]:
         d = dict(zip(hdr, r))
-        per[d.get("Kernel Name", "?").split("(")[0]].append(d)
+        per[_kname(d.get("Kernel Name", "?"))].append(d)
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     traffic = {}
     with open(dst, "w") as f:

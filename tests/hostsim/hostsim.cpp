@@ -116,4 +116,40 @@ int hs_make_tables(int piece_num, int res, double* basis, double* weight, double
   return 0;
 }
 
+// single-precision filter of the 49-DOP gate against the plain FP64 gate: thresholds made exactly like segments.cu (k_rows)
+// for one row P (6 x 3 column-major), then n points.  out_f = filtered decision (stage 0..14 && stage 14..49 like k_narrow),
+// out_x = kdop_point_overlap; *n_exact = axes the filter handed to the FP64 fallback.
+int hs_kdop_gate_batch(const double* P, const double* pts, int n, const double* kdop, double d, unsigned char* out_f,
+                       unsigned char* out_x, unsigned long long* n_exact) {
+  double a[6][3];
+  load<6>(P, a);
+  double lo[TOB_KDOP_AXES], hi[TOB_KDOP_AXES];
+  kdop_extents<6>(a, kdop, lo, hi);
+  double m[3];
+  for (int k = 0; k < 3; k++) {
+    double l = INFINITY, h = -INFINITY;
+    for (int j = 0; j < 6; j++) { if (a[j][k] < l) l = a[j][k]; if (a[j][k] > h) h = a[j][k]; }
+    m[k] = 0.5 * (l + h);
+  }
+  float kf[TOB_KF_ROW], kdf[3 * TOB_KDOP_AXES], tmag = 0.f;
+  for (int k = 0; k < 3 * TOB_KDOP_AXES; k++) kdf[k] = (float)kdop[k];
+  for (int k = 0; k < TOB_KDOP_AXES; k++) {
+    const double x = kdop[3 * k], y = kdop[3 * k + 1], z = kdop[3 * k + 2];
+    const float tm = kdop_gate_thresholds(lo[k], hi[k], d, x * m[0] + y * m[1] + z * m[2], &kf[2 * k], &kf[2 * k + 1]);
+    tmag = fmaxf(tmag, tm);
+    if (!(tm <= 3.0e38f)) tmag = INFINITY;
+  }
+  kf[2 * TOB_KDOP_AXES] = kdop_gate_allowance(tmag, m, d);
+  kf[2 * TOB_KDOP_AXES + 1] = 0.f;
+  unsigned groups = 0, exact = 0;
+  for (int i = 0; i < n; i++) {
+    const double q[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    out_f[i] = kdop_point_gate(kf, m, kdf, lo, hi, kdop, q, d, &groups, &exact, 0, 14) &&
+               kdop_point_gate(kf, m, kdf, lo, hi, kdop, q, d, &groups, &exact, 14, TOB_KDOP_AXES);
+    out_x[i] = kdop_point_overlap(lo, hi, kdop, q, d);
+  }
+  *n_exact = exact;
+  return 0;
+}
+
 }  // extern "C"

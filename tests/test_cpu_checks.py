@@ -219,3 +219,44 @@ def test_library_fails_loudly_without_gpu():
     with pytest.raises(RuntimeError) as ei:
         api.Solver(4)
     assert "no CUDA device" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_hostsim_kdop_filter_equals_fp64_gate(hostsim, gs):
+    """The single-precision filter of k_narrow's 49-DOP gate (csrc/gjk.cuh: kdop_point_gate, thresholds as made by
+    segments.cu) must take the decision of the FP64 gate (CCD::KDOPDCD, CCD.h:354-413) for every point: random points
+    around the hull, points placed ON each threshold (lv = lo - d, lv = hi + d) and one / a few ulps to either side,
+    large coordinate offsets, tiny hulls."""
+    kd = np.ascontiguousarray(gs["tab_kdop"])
+    rng = np.random.Generator(np.random.PCG64(77))
+    hostsim.hs_kdop_gate_batch.restype = C.c_int
+    total_exact = 0
+    total = 0
+    axes = kd.reshape(49, 3)
+    for trial in range(60):
+        scale = [1.0, 1.0, 0.05, 30.0][trial % 4]
+        shift = [0.0, 7.0, 250.0, -3.0e4, 1.0e7][trial % 5]
+        P = rng.normal(size=(6, 3)) * 0.4 * scale + rng.normal(size=3) * 3 + shift
+        d = [0.2, 0.05, 1e-3, 0.0][trial % 4] * scale
+        lo = (P @ axes.T).min(axis=0); hi = (P @ axes.T).max(axis=0)
+        pts = [P.mean(axis=0) + rng.normal(size=(3000, 3)) * (0.5 * scale + d)]
+        # points on the thresholds: start from a point near the hull, move it along axis k until its level hits the threshold
+        base = P.mean(axis=0) + rng.normal(size=(49, 3)) * 0.1 * scale
+        for sgn, thr in ((-1.0, lo - d), (1.0, hi + d)):
+            lv = np.einsum("ij,ij->i", base, axes)
+            on = base + ((thr - lv)[:, None]) * axes
+            for ulps in (0, 1, -1, 3, -3, 40, -40, 1000, -1000):
+                p = on.copy()
+                j = np.argmax(np.abs(axes), axis=1)
+                x = p[np.arange(49), j]
+                p[np.arange(49), j] = x + ulps * np.spacing(np.abs(x))
+                pts.append(p)
+        pts = np.ascontiguousarray(np.concatenate(pts))
+        n = len(pts)
+        of = np.zeros(n, dtype=np.uint8); ox = np.zeros(n, dtype=np.uint8); ne = C.c_ulonglong(0)
+        hostsim.hs_kdop_gate_batch(D(np.asfortranarray(P)), D(pts), n, D(kd), C.c_double(d),
+                                   of.ctypes.data_as(C.POINTER(C.c_ubyte)), ox.ctypes.data_as(C.POINTER(C.c_ubyte)), C.byref(ne))
+        assert np.array_equal(of, ox), (trial, int((of != ox).sum()))
+        assert 0 < ox[:3000].sum() < 3000          # the random part exercises both outcomes
+        if shift == 0.0 or abs(shift) < 10:
+            total_exact += ne.value; total += 3000
+    assert total_exact > 0                         # the threshold points reach the FP64 fallback

@@ -59,3 +59,71 @@ def test_multi_uav_result_independent_of_line_search_schedule():
     ref = run(sc, sts, None, 6, uav_num=len(sts))
     for policy in ("3,9,3", "9,9,2", "2,3,8"):
         assert same(ref, run(sc, sts, policy, 6, uav_num=len(sts))), policy
+
+
+# ---- many rows (>= 8192: the throughput regime picks other kernel variants and another line-search policy) ------------------
+def _batch(n=130):
+    rng = np.random.Generator(np.random.PCG64(5))
+    return [scenes.tube(int(rng.integers(1200, 4000)), 100 + i, float(rng.uniform(0.14, 0.5))) for i in range(n)]
+
+
+def _run_batch(scs, sts, iters, env):
+    keys = ("TRAJOPT_B200_LS", "TRAJOPT_B200_EN_OCC", "TRAJOPT_B200_NP_FILTER", "TRAJOPT_B200_CCD_OCC", "TRAJOPT_B200_NP_OCC")
+    for k in keys:
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    try:
+        s = api.Solver(8, uav_num=len(scs), ks=1e-8)
+        s.init_pointclouds([sc["V"] for sc in scs])
+        s.states_upload(sts)
+        for _ in range(iters):
+            s.iterate(1, mode=2)
+        return s.states_download(sts), s.counters()
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+
+
+def test_many_rows_result_independent_of_kernel_variants_and_schedule():
+    """130 independent problems = 8320 rows.  The default run (occupancy variants of k_row_energy / k_bp_ccd, the
+    single-precision filter of the 49-DOP gate, the many-row line-search policy) must be bitwise equal to the run with every
+    variant switched off, to other line-search schedules, and -- problem by problem -- to a single-problem context."""
+    scs = _batch()
+    sts = [scenes.initial_states(sc)[0] for sc in scs]
+    ref, cref = _run_batch(scs, sts, 5, {})
+    assert cref["np_kdop_groups"] > 0
+    for env in ({"TRAJOPT_B200_EN_OCC": "0", "TRAJOPT_B200_NP_FILTER": "0", "TRAJOPT_B200_CCD_OCC": "4"},
+                {"TRAJOPT_B200_EN_OCC": "2", "TRAJOPT_B200_LS": "2,5,5", "TRAJOPT_B200_CCD_OCC": "12"},
+                {"TRAJOPT_B200_LS": "2,2,16"}, {"TRAJOPT_B200_LS": "2,3,9"}, {"TRAJOPT_B200_LS": "9,9,2", "TRAJOPT_B200_NP_OCC": "6"}):
+        got, cgot = _run_batch(scs, sts, 5, env)
+        assert same(ref, got), env
+        assert cgot["planes"] == cref["planes"] and cgot["dcd_candidates"] == cref["dcd_candidates"], env
+        if env.get("TRAJOPT_B200_NP_FILTER") == "0":
+            assert cgot["np_kdop_exact"] == 0 and cgot["np_kdop_groups"] == cref["np_kdop_groups"]
+    for u in (0, 57, 129):
+        s1 = api.Solver(8, uav_num=1, ks=1e-8)
+        s1.init_pointcloud(scs[u]["V"])
+        s1.states_upload([sts[u]])
+        s1.iterate(5)
+        assert same([ref[u]], s1.states_download([sts[u]])), u
+
+
+def test_kdop_filter_same_planes_as_fp64_gate():
+    """plane sets (offsets, c, d) with the single-precision gate filter on and off: bit-identical (forest-like scene, 64 pieces)"""
+    sc = scenes.forest(n_pts=200_000, seed=2)
+    st = scenes.initial_states(sc)[0]
+    P = len(sc["way_points"][0]) - 1
+    out = []
+    for filt in ("1", "0"):
+        os.environ["TRAJOPT_B200_NP_FILTER"] = filt
+        try:
+            s = api.Solver(P, ks=sc["ks"])
+            s.init_pointcloud(sc["V"])
+            out.append(s.separate_plane(st["spline"]) + (s.counters(),))
+        finally:
+            os.environ.pop("TRAJOPT_B200_NP_FILTER", None)
+    (o1, c1, d1, k1), (o0, c0, d0, k0) = out
+    assert len(d1) > 1000
+    assert np.array_equal(o1, o0) and np.array_equal(c1, c0) and np.array_equal(d1, d0)
+    assert k0["np_kdop_exact"] == 0 and k1["np_kdop_groups"] == k0["np_kdop_groups"]
+    assert k1["np_kdop_exact"] < 1e-3 * 7 * k1["np_kdop_groups"]        # the fallback is rare

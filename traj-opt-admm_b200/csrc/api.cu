@@ -345,6 +345,7 @@ static int ensure_iter_buffers(tob_ctx* c) {
   if (c->live_planes()) TOB_TRY(ensure_live_buffers(c, c->live_cap ? c->live_cap : 1));
   TOB_CUDA(c, c->geo.P.ensure(18 * rows)); TOB_CUDA(c, c->geo.D.ensure(18 * rows)); TOB_CUDA(c, c->geo.box.ensure(6 * rows));
   TOB_CUDA(c, c->geo.klo.ensure(TOB_KDOP_AXES * rows)); TOB_CUDA(c, c->geo.khi.ensure(TOB_KDOP_AXES * rows));
+  TOB_CUDA(c, c->geo.kf.ensure(TOB_KF_ROW * rows)); TOB_CUDA(c, c->geo.kc.ensure(4 * rows));
   TOB_CUDA(c, c->row_e.ensure(TOB_EN_REC * rows * TOB_LS_TRIALS)); TOB_CUDA(c, c->row_bad.ensure(U * TOB_LS_TRIALS + 1));
   TOB_CUDA(c, c->pc_g.ensure(19 * U * P)); TOB_CUDA(c, c->pc_h.ensure(361 * U * P)); TOB_CUDA(c, c->pc_flag.ensure(U * P));
   if (U > 1 && c->cloud_n1.empty()) {   // inter-robot scratch (never used by independent problems)
@@ -1466,6 +1467,7 @@ int tob_get_counters(const tob_ctx* cc, tob_counters* out) {
   out->np_gjk_iters = c->h_dc->np_gjk_iters;
   out->ccd_gjk_iters = c->h_dc->ccd_gjk_iters;
   out->ccd_kdop_pass = c->h_dc->ccd_kdop_pass;
+  out->np_kdop_exact = c->h_dc->np_kdop_exact;
   return 0;
 }
 int tob_reset_counters(tob_ctx* c) {
@@ -1473,7 +1475,7 @@ int tob_reset_counters(tob_ctx* c) {
   cudaSetDevice(c->device);
   memset(&c->ctr, 0, sizeof(c->ctr));
   TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->dcd_candidates, 0, 5 * sizeof(unsigned long long), c->stream));
-  TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->np_kdop_groups, 0, 4 * sizeof(unsigned long long), c->stream));
+  TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->np_kdop_groups, 0, 5 * sizeof(unsigned long long), c->stream));
   return 0;
 }
 

@@ -68,6 +68,8 @@ struct EnergyArgs {
   double* row_e;                // KT x rows_all x EN_REC
   int* bad;                     // robots x KT: trial infeasible (some d <= 0); raised here, cleared by the caller
   const int* done;              // per robot, may be null: robots whose line search has finished are skipped
+  const int* pending;           // may be null; else the robots still backtracking after the previous Armijo round: 0 = this
+                                // round (launched ahead of the host, inside the graph) has nothing to do and every CTA leaves
   DevCounts* dc;                // barrier_terms counter, n_en_items
 };
 
@@ -88,6 +90,9 @@ __global__ void __launch_bounds__(256) k_en_items(const uint32_t* __restrict__ p
 
 #define EN_MAXT TOB_LS_TRIALS
 // one warp: virtual warp v of `row` for trial k (and, when v == 0, the bound terms of the row)
+// CP_SHARED: the 18 control-point coordinates are read from shared memory in every chunk (uniform address: one broadcast per
+// load) instead of living in 36 registers -- the variants that trade registers for resident warps
+template <bool CP_SHARED>
 __device__ __forceinline__ void en_virtual_warp(const EnergyArgs& a, int row, int v, int k, double* sP, double* sBz, double* q,
                                                 unsigned& n_act, unsigned& n_pl) {
   const int lane = threadIdx.x & 31;
@@ -118,8 +123,11 @@ __device__ __forceinline__ void en_virtual_warp(const EnergyArgs& a, int row, in
   __syncwarp();
   const double w = a.weight[tr], m = a.margin, inv_m = 1.0 / m;
   double cp[18];
+  const volatile double* vP = sP;
+  if (!CP_SHARED) {
 #pragma unroll
-  for (int i = 0; i < 18; i++) cp[i] = sP[i];
+    for (int i = 0; i < 18; i++) cp[i] = sP[i];
+  }
   bool stop = false;
   {
     double e = 0;
@@ -140,7 +148,8 @@ __device__ __forceinline__ void en_virtual_warp(const EnergyArgs& a, int row, in
       unsigned cnt = 0;
 #pragma unroll
       for (int j = 0; j < 6; j++) {
-        d[j] = cp[j] * pl.x + cp[j + 6] * pl.y + cp[j + 12] * pl.z + pl.w;
+        if (CP_SHARED) d[j] = vP[j] * pl.x + vP[j + 6] * pl.y + vP[j + 12] * pl.z + pl.w;
+        else d[j] = cp[j] * pl.x + cp[j + 6] * pl.y + cp[j + 12] * pl.z + pl.w;
         bad |= have && (d[j] <= 0);
         const bool act = have && d[j] > 0 && d[j] < m;
         const unsigned bm = __ballot_sync(0xffffffffu, act);
@@ -200,21 +209,27 @@ __device__ __forceinline__ void en_virtual_warp(const EnergyArgs& a, int row, in
 
 // grid = n_rows + extra CTAs; one warp per trial point of the launch (blockDim = 32 * nk).  CTA b < n_rows: virtual warp 0
 // of row b.  The extra CTAs share the listed virtual warps (v >= 1) of the heavy rows.
-__global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
+// MAXT = most trial points (warps) of a launch of this variant, MINB = resident CTAs per SM its registers are allotted for:
+// the kernel waits on plane loads (ncu: long scoreboard, 20 % of the warp slots in use with 106 registers), so the variants
+// for the short launches of the many-row line-search policy trade registers for resident warps.
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(32 * MAXT, MINB) k_row_energy(EnergyArgs a) {
+  constexpr bool CPS = MINB > 1;
   const int lane = threadIdx.x & 31, kk = threadIdx.x >> 5, k = a.k0 + kk;
-  __shared__ double sPall[EN_MAXT][18], sBzall[EN_MAXT][18];
-  __shared__ double sQ[EN_MAXT][192];          // in-band terms of one chunk (32 planes x 6 control points)
+  __shared__ double sPall[MAXT][18], sBzall[MAXT][18];
+  __shared__ double sQ[MAXT][192];          // in-band terms of one chunk (32 planes x 6 control points)
   if (a.dc->overflow) return;      // the plane CSR of this iteration was not built: the host grows the buffers and retries
+  if (a.pending && *a.pending == 0) return;
   unsigned n_act = 0, n_pl = 0;
   if ((int)blockIdx.x < a.n_rows) {
-    en_virtual_warp(a, a.row_begin + (int)blockIdx.x, 0, k, sPall[kk], sBzall[kk], sQ[kk], n_act, n_pl);
+    en_virtual_warp<CPS>(a, a.row_begin + (int)blockIdx.x, 0, k, sPall[kk], sBzall[kk], sQ[kk], n_act, n_pl);
   } else {
     const uint32_t n_items = a.dc->n_en_items, extra = gridDim.x - (uint32_t)a.n_rows;
     for (uint32_t idx = blockIdx.x - (uint32_t)a.n_rows; idx < n_items; idx += extra) {
       const uint32_t it = a.items[idx];
       const int row = (int)(it >> 3), v = (int)(it & 7u) + 1;
       if (row < a.row_begin || row >= a.row_begin + a.n_rows) continue;
-      en_virtual_warp(a, row, v, k, sPall[kk], sBzall[kk], sQ[kk], n_act, n_pl);
+      en_virtual_warp<CPS>(a, row, v, k, sPall[kk], sBzall[kk], sQ[kk], n_act, n_pl);
     }
   }
   n_pl = __reduce_add_sync(0xffffffffu, n_pl);
@@ -222,6 +237,18 @@ __global__ void __launch_bounds__(32 * EN_MAXT) k_row_energy(EnergyArgs a) {
     if (n_act) atomicAdd(&a.dc->barrier_terms, (unsigned long long)n_act);
     if (n_pl) atomicAdd(&a.dc->energy_plane_evals, (unsigned long long)n_pl);   // planes x trials really evaluated
   }
+}
+
+// variant by the number of trial points of the launch; many rows (throughput regime): the occupancy variants
+static void launch_row_energy(tob_ctx* c, const EnergyArgs& a, int grid, int nk, int nrows) {
+  const char* e = getenv("TRAJOPT_B200_EN_OCC");       // 0: one variant for everything (A/B measurements, tests)
+  const int occ = e ? atoi(e) : 1;
+  const bool many = occ && nrows >= 8192;
+  if (many && nk == 1) k_row_energy<1, 28><<<grid, 32, 0, c->stream>>>(a);
+  else if (many && nk == 2) k_row_energy<2, 14><<<grid, 64, 0, c->stream>>>(a);
+  else if (many && nk <= 4 && occ == 2) k_row_energy<4, 8><<<grid, 32 * nk, 0, c->stream>>>(a);
+  else if (many && nk <= 4) k_row_energy<4, 6><<<grid, 32 * nk, 0, c->stream>>>(a);
+  else k_row_energy<EN_MAXT, 1><<<grid, 32 * nk, 0, c->stream>>>(a);
 }
 
 // plane-barrier energy of one (trial, row): its V partials in order
@@ -416,14 +443,14 @@ int energy_trials(tob_ctx* c, int rb, int re, const double* dir, const double* t
   a.pl = c->pl.p; a.pl_off = c->pl_off.p; a.weight = c->d_weight.p;
   a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
   a.n_tr = c->n_tr; a.res = c->prm.res; a.T = c->T; a.row_begin = rb * c->n_tr; a.rows_all = rows_all; a.KT = KT; a.k0 = k0;
-  a.row_e = c->row_e.p; a.bad = c->row_bad.p; a.done = nullptr; a.dc = c->dc.p; a.items = c->en_items.p;
+  a.row_e = c->row_e.p; a.bad = c->row_bad.p; a.done = nullptr; a.dc = c->dc.p; a.items = c->en_items.p; a.pending = nullptr;
   const int nrows = (re - rb) * c->n_tr, nk = k1 - k0;
   a.n_rows = nrows;
   {
     Prof prof(c, K_ROW_ENERGY);
     a.nk = nk;
     if (nk > EN_MAXT) return fail_msg(c, "energy_trials: too many trial points in one launch");
-    k_row_energy<<<nrows + energy_extra(c, nrows), 32 * nk, 0, c->stream>>>(a);
+    launch_row_energy(c, a, nrows + energy_extra(c, nrows), nk, nrows);
     TOB_LAUNCH_CHECK(c);
   }
   RobotEnergyArgs b;
@@ -458,12 +485,14 @@ int line_search_round(tob_ctx* c, int rb, int re, int wolfe_idx, int k0, int kte
   a.margin = c->prm.margin; a.vel_limit = c->prm.vel_limit; a.acc_limit = c->prm.acc_limit;
   a.n_tr = c->n_tr; a.res = c->prm.res; a.T = c->T; a.row_begin = rb * c->n_tr; a.rows_all = rows_all; a.KT = KT; a.k0 = k0e;
   a.row_e = c->row_e.p; a.bad = c->row_bad.p; a.done = c->s_done.p; a.dc = c->dc.p; a.items = c->en_items.p;
+  // rounds 1.. of the sequence launched ahead: slot r counts the robots that round r left backtracking (k_robot_ls)
+  a.pending = (slot >= 1 && slot < TOB_LS_MAXROUNDS) ? &c->dc.p->ls_pending[slot - 1] : nullptr;
   const int nrows = (re - rb) * c->n_tr;
   a.n_rows = nrows;
   {
     Prof prof(c, K_ROW_ENERGY);
     a.nk = kte - k0e;
-    k_row_energy<<<nrows + energy_extra(c, nrows), 32 * (kte - k0e), 0, c->stream>>>(a);
+    launch_row_energy(c, a, nrows + energy_extra(c, nrows), kte - k0e, nrows);
     TOB_LAUNCH_CHECK(c);
   }
   RobotLsArgs b;

@@ -36,6 +36,7 @@ struct BpArgs {
   // one cloud per robot (batched independent problems): row r walks level-1 nodes [row_l1[r], row_l1[r] + n1(r)) and its
   // tasks are [row_task[r], row_task[r+1]); null = one shared cloud, n1 nodes for every row
   const uint32_t *row_task, *row_l1;
+  const uint32_t* cta_row;     // per-robot clouds, whole-context query: row of the first task of every CTA (host-built), or null
 };
 
 struct BpShared {
@@ -124,8 +125,10 @@ __device__ __forceinline__ uint32_t cta1024_scan_inplace(uint32_t* v, uint32_t n
   return carry;
 }
 
-// task (relative to the first queried row) -> global row, global level-1 node, "first node of its row"
-__device__ __forceinline__ void bp_task(const BpArgs& a, uint32_t t, uint32_t* row, uint32_t* nd, bool* first) {
+// task (relative to the first queried row) -> global row, global level-1 node, "first node of its row".
+// row_hint: a row known to be <= the task's row (per-robot clouds: the row of the CTA's first task, found once per CTA by
+// binary search; the tasks of a CTA are consecutive, so every thread then walks a few rows forward instead of searching)
+__device__ __forceinline__ void bp_task(const BpArgs& a, uint32_t t, uint32_t* row, uint32_t* nd, bool* first, uint32_t row_hint) {
   if (a.row_task == nullptr) {
     const uint32_t r = t / a.n1;
     *row = a.row_base + r;
@@ -134,14 +137,26 @@ __device__ __forceinline__ void bp_task(const BpArgs& a, uint32_t t, uint32_t* r
     return;
   }
   const uint32_t tg = t + a.row_task[a.row_base];
-  uint32_t lo = a.row_base, hi = a.row_base + a.rows;      // largest row with row_task[row] <= tg
+  uint32_t lo = row_hint;
+  const uint32_t last = a.row_base + a.rows - 1;
+  while (lo < last && a.row_task[lo + 1] <= tg) lo++;      // largest row with row_task[row] <= tg
+  *row = lo;
+  *nd = a.row_l1[lo] + (tg - a.row_task[lo]);
+  *first = tg == a.row_task[lo];
+}
+
+// row of the first task of this CTA (per-robot clouds): from the host-built table, else by binary search (16 dependent
+// loads on the critical path of every CTA of a 65536-row batch); a.row_base when all rows share one cloud
+__device__ __forceinline__ uint32_t bp_first_row(const BpArgs& a) {
+  if (a.row_task == nullptr) return a.row_base;
+  if (a.cta_row != nullptr) return a.cta_row[blockIdx.x];
+  const uint32_t tg = blockIdx.x * a.tpc + a.row_task[a.row_base];
+  uint32_t lo = a.row_base, hi = a.row_base + a.rows;
   while (hi - lo > 1) {
     const uint32_t mid = (lo + hi) >> 1;
     if (a.row_task[mid] <= tg) lo = mid; else hi = mid;
   }
-  *row = lo;
-  *nd = a.row_l1[lo] + (tg - a.row_task[lo]);
-  *first = tg == a.row_task[lo];
+  return lo;
 }
 
 // phases A + B + item prefix.  Returns the number of items of this CTA; *my_rank = hit tasks before this thread's task.
@@ -153,7 +168,7 @@ __device__ __forceinline__ uint32_t bp_prepare(const BpArgs& a, BpShared& s, uin
   double q[6] = {0, 0, 0, 0, 0, 0};
   if (tid < a.tpc && t < a.n_tasks) {
     bool first;
-    bp_task(a, t, &row, &nd, &first);
+    bp_task(a, t, &row, &nd, &first, bp_first_row(a));
     const double* qb = a.box + (size_t)6 * row;
     double nlo[3], nhi[3];
 #pragma unroll
@@ -190,13 +205,11 @@ __device__ __forceinline__ uint32_t bp_prepare(const BpArgs& a, BpShared& s, uin
   return n_items;
 }
 
-// item j -> hit task h (binary search over item_base, uniform in the warp) and the leaf it addresses
+// item j -> hit task h and the leaf it addresses.  *h_out is a cursor: a warp visits its items in increasing order, so the
+// search walks forward from the task of the previous item (start with 0); uniform in the warp
 __device__ __forceinline__ void bp_item(const BpArgs& a, const BpShared& s, uint32_t j, uint32_t* h_out, uint32_t* row, uint32_t* leaf) {
-  uint32_t lo = 0, hi = s.n_hit;            // largest h with item_base[h] <= j
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (s.item_base[mid] <= j) lo = mid; else hi = mid;
-  }
+  uint32_t lo = *h_out;                     // largest h with item_base[h] <= j
+  while (lo + 1 < s.n_hit && s.item_base[lo + 1] <= j) lo++;
   const uint32_t k = j - s.item_base[lo];
   const uint32_t lb = __fns(s.lmask[lo], 0, k + 1);
   *h_out = lo;

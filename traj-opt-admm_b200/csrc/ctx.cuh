@@ -13,6 +13,7 @@
 #define TOB_MAX_LEVELS 8
 #define TOB_LS_TRIALS 9      // line-search trial points per launch: index 0 = current point, 1..8 = ladder rungs
 #define TOB_LADDER 400       // longest 0.8^k ladder the CCD kernels will walk
+#define TOB_KF_ROW 100       // floats per row of the single-precision 49-DOP filter: 49 x (below, above) thresholds, allowance, pad
 
 struct tob_ctx;
 
@@ -69,7 +70,7 @@ struct DBuf {
 #define TOB_OVF_REMOTE 16u   // sharded: another rank overflowed (every rank repeats the iteration, only the flagged ones grow)
 #define TOB_OVF_RETRY (TOB_OVF_CAND | TOB_OVF_LIVE | TOB_OVF_REMOTE)   // the iteration is repeated: whatever ran on the incomplete plane set is void
 #define TOB_ERR_SOLVE 32u    // Newton system not positive definite (Cholesky pivot / Schur complement <= 0): nothing is committed
-#define TOB_LS_MAXROUNDS 8   // most Armijo rounds launched ahead of the host (the count is a run-time choice, see ls_policy)
+#define TOB_LS_MAXROUNDS 16  // most Armijo rounds launched ahead of the host (the count is a run-time choice, see ls_policy)
 struct DevCounts {
   uint32_t n_cand;           // candidates of the last broadphase fill (may exceed the capacity -> overflow)
   uint32_t n_planes;         // planes of the last pack
@@ -92,6 +93,7 @@ struct DevCounts {
   unsigned long long np_gjk_iters;     // GJK(6,1) rounds (support + sub-algorithm) run by k_narrow
   unsigned long long ccd_gjk_iters;    // GJK(12,1) rounds run by the CCD ladder of k_bp_ccd
   unsigned long long ccd_kdop_pass;    // swept candidates that passed the swept 49-DOP gate (each runs >= 1 ladder rung)
+  unsigned long long np_kdop_exact;    // axes of the 49-DOP gate the single-precision filter could not decide (re-tested in FP64)
 };
 
 // per-row (robot x sub-segment) geometry produced by segments.cu, indexed by GLOBAL row = robot*n_tr + tr
@@ -101,6 +103,10 @@ struct RowGeom {
   DBuf<double> box;    // rows x 6   lo xyz, hi xyz
   DBuf<double> klo;    // rows x 49  k-DOP extents of P
   DBuf<double> khi;    // rows x 49
+  // single-precision filter of the 49-DOP gate of k_narrow (gjk.cuh: kdop_point_gate): per row TOB_KF_ROW floats =
+  // 49 x (below threshold, above threshold) relative to the row's centre, then the row's error allowance; kc = the centre
+  DBuf<float> kf;      // rows x TOB_KF_ROW
+  DBuf<double> kc;     // rows x 4 (centre xyz, unused)
 };
 
 struct Level {         // one level of the 32-wide LBVH, SoA boxes
@@ -138,6 +144,8 @@ struct tob_ctx {
   std::vector<uint32_t> cloud_n1, cloud_l1;       // level-1 node count / first level-1 node of each cloud
   std::vector<uint32_t> h_row_task;
   tob::DBuf<uint32_t> row_task, row_l1;           // rows+1: exclusive prefix of broadphase tasks per row; first level-1 node
+  tob::DBuf<uint32_t> cta_row;                    // row of the first task of every CTA of a whole-context query
+  uint32_t cta_row_tpc = 0;                       // ... for this many tasks per CTA
   int n_levels = 0;
   tob::Level lvl[TOB_MAX_LEVELS];
 

@@ -568,6 +568,70 @@ TOB_HD bool kdop_point_overlap(const double* lo, const double* hi, const double*
   return true;
 }
 
+// ---- single-precision filter of the same gate -----------------------------------------------------------------------
+// The gate's outcome is the OR of 98 comparisons (some axis separates), so the order of the axes is free and a comparison
+// whose outcome is certain needs no FP64 arithmetic.  Per row, segments.cu stores for every axis k the two thresholds of
+//     below_k  <=>  lv < lo_k - d        above_k  <=>  hi_k < lv - d        (lv = level of the point on axis k, FP64)
+// relative to the row's centre m, rounded to float:  TL_k = (lo_k - d) - a_k.m,  TH_k = (hi_k + d) - a_k.m.  The point is
+// shifted by m in FP64 and rounded to float, its level is three single-precision operations, and a comparison counts as
+// decided only when it clears the threshold by more than the allowance
+//     E = 2^-21 (|q - m|_1 + max_k |T_k|) + 2^-40 (|m|_1 + d + max_k |T_k|)
+// which bounds (with a factor > 1.3 to spare) the sum of: both float conversions of the point and of the axis (2 x 2^-24
+// |q-m|_1), the three roundings of the level (3 x 2^-24 |q-m|_1), the float conversion of the threshold and the rounding of
+// the difference (2^-24 (2 |T| + |q-m|_1)), and every FP64 rounding of the reference expression and of the threshold
+// (< 2^-48 of the magnitudes involved).  Undecided comparisons (and anything non-finite) are re-tested with the reference
+// arithmetic, so the decision is the reference's bit for bit; on the benchmark scenes fewer than 1 in 10^4 axes are.
+#define TOB_KF_EPS32 4.76837158203125e-07f      // 2^-21
+#define TOB_KF_EPS64 9.094947017729282e-13      // 2^-40
+
+struct alignas(8) KfPair { float x, y; };
+// thresholds of one row: kf[2k] = TL_k, kf[2k+1] = TH_k, kf[98] = allowance without the point's part (segments.cu)
+TOB_HD bool kdop_point_gate(const float* __restrict__ kf, const double* __restrict__ centre, const float* kdop_f,
+                            const double* lo, const double* hi, const double* kdop, const double* q, double d,
+                            unsigned* groups, unsigned* exact, int axis_begin, int axis_end) {
+  const float q0 = (float)(q[0] - centre[0]), q1 = (float)(q[1] - centre[1]), q2 = (float)(q[2] - centre[2]);
+  const float E = fmaf(TOB_KF_EPS32, (fabsf(q0) + fabsf(q1)) + fabsf(q2), kf[2 * TOB_KDOP_AXES]);
+  const KfPair* __restrict__ th = reinterpret_cast<const KfPair*>(kf);
+  for (int g = axis_begin; g < axis_end; g += 7) {
+    bool sep = false;
+    unsigned unc = 0;
+    if (groups) ++*groups;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int k = g + j;
+      const float lv = fmaf(kdop_f[3 * k], q0, fmaf(kdop_f[3 * k + 1], q1, kdop_f[3 * k + 2] * q2));
+      const KfPair t = th[k];
+      const float tl = lv - t.x, thh = lv - t.y;
+      sep = sep | (tl < -E) | (thh > E);
+      if (!(fabsf(tl) > E) | !(fabsf(thh) > E)) unc |= 1u << j;      // also taken by NaN / inf
+    }
+    if (sep) return false;
+    if (unc) {                      // rare: the reference arithmetic for the axes the filter could not decide
+      for (int j = 0; j < 7; ++j)
+        if ((unc >> j) & 1u) {
+          const int k = g + j;
+          if (exact) ++*exact;
+          const double lv = kdop_level(kdop[3 * k], kdop[3 * k + 1], kdop[3 * k + 2], q);
+          if (lv < lo[k] - d || hi[k] < lv - d) return false;
+        }
+    }
+  }
+  return true;
+}
+
+// what segments.cu stores for one axis of one row (am = a_k . m in FP64); returns max(|TL|, |TH|)
+TOB_HD float kdop_gate_thresholds(double lo, double hi, double d, double am, float* tl, float* th) {
+  *tl = (float)((lo - d) - am);
+  *th = (float)((hi + d) - am);
+  return fmaxf(fabsf(*tl), fabsf(*th));
+}
+// allowance of a row without the point's part; tmag = max over the axes of kdop_gate_thresholds
+TOB_HD float kdop_gate_allowance(float tmag, const double* centre, double d) {
+  const double s = (fabs(centre[0]) + fabs(centre[1]) + fabs(centre[2])) + fabs(d) + (double)tmag;
+  // rounded up: the product and the sum are inflated by a factor that exceeds their own rounding
+  return (TOB_KF_EPS32 * tmag + (float)(TOB_KF_EPS64 * s)) * 1.0000005f + 1e-37f;
+}
+
 // two precomputed extent sets with gap d
 TOB_HD bool kdop_sets_overlap(const double* loA, const double* hiA, const double* loB, const double* hiB, double d) {
   for (int g = 0; g < TOB_KDOP_AXES; g += 7) {       // groups of 7 axes: 28 loads in flight instead of 4 behind every branch

@@ -248,6 +248,8 @@ int lbvh_build(tob_ctx* c, const double* V_host, uint32_t n) {
 // one cloud per robot slot (batched independent problems): clouds are concatenated, each padded to a multiple of 1024
 // points so that neither a leaf (32 points) nor a level-1 node (32 leaves) straddles two clouds.  Per row the broadphase
 // then walks only the level-1 nodes of its own cloud (row_task / row_l1).
+static uint32_t bp_tpc(tob_ctx* c, uint32_t n_tasks);
+
 int lbvh_build_batch(tob_ctx* c, const double* const* V_host, const uint32_t* n, int n_clouds) {
   if (n_clouds != c->n_robots()) return fail_msg(c, "tob_cloud_upload_batch: one cloud per robot slot (uav_num) is required");
   size_t total = 0;
@@ -283,6 +285,20 @@ int lbvh_build_batch(tob_ctx* c, const double* const* V_host, const uint32_t* n,
   TOB_CUDA(c, c->row_task.ensure(rows + 1)); TOB_CUDA(c, c->row_l1.ensure(rows + 1));
   TOB_CUDA(c, cudaMemcpyAsync(c->row_task.p, rt.data(), (rows + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
   TOB_CUDA(c, cudaMemcpyAsync(c->row_l1.p, rl.data(), (rows + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  // row of the first task of every CTA of a whole-context query (bp.cuh: bp_first_row)
+  {
+    const uint32_t n_tasks = (uint32_t)acc, tpc = bp_tpc(c, n_tasks), nblk = (n_tasks + tpc - 1) / tpc;
+    std::vector<uint32_t> cr(nblk + 1);
+    uint32_t r = 0;
+    for (uint32_t b = 0; b < nblk; b++) {
+      const uint32_t tg = b * tpc;
+      while (r + 1 < (uint32_t)rows && rt[r + 1] <= tg) r++;
+      cr[b] = r;
+    }
+    TOB_CUDA(c, c->cta_row.ensure(nblk + 1));
+    TOB_CUDA(c, cudaMemcpyAsync(c->cta_row.p, cr.data(), nblk * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    c->cta_row_tpc = tpc;
+  }
   TOB_CUDA(c, cudaStreamSynchronize(c->stream));
   c->h_row_task = rt;
   return 0;
@@ -296,8 +312,9 @@ __global__ void __launch_bounds__(BP_THREADS) k_bp_count(BpArgs a) {
   const uint32_t n_items = bp_prepare(a, s, &rank);
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   uint32_t cnt = 0;
+  uint32_t h = 0;                                          // bp_item cursor
   for (uint32_t j = w; j < n_items; j += BP_WARPS) {
-    uint32_t h, row, leaf;
+    uint32_t row, leaf;
     bp_item(a, s, j, &h, &row, &leaf);
     double x, y, z;
     const bool ok = bp_point_test(a, s, h, leaf * 32 + lane, &x, &y, &z);
@@ -342,10 +359,11 @@ __global__ void __launch_bounds__(BP_THREADS) k_bp_fill(BpArgs a) {
   const uint32_t n_hit = s.n_hit;
   const uint32_t cta_base = a.bsum[blockIdx.x];
   uint32_t run = 0;
+  uint32_t h = 0;                                          // bp_item cursor (a warp's items increase across batches too)
   for (uint32_t b0 = 0; b0 < n_items; b0 += BP_BATCH) {
     const uint32_t nb = min((uint32_t)BP_BATCH, n_items - b0);
     for (uint32_t jj = w; jj < nb; jj += BP_WARPS) {
-      uint32_t h, row, leaf;
+      uint32_t row, leaf;
       bp_item(a, s, b0 + jj, &h, &row, &leaf);
       double x, y, z;
       const bool ok = bp_point_test(a, s, h, leaf * 32 + lane, &x, &y, &z);
@@ -394,7 +412,7 @@ __global__ void __launch_bounds__(BP_THREADS) k_bp_fill(BpArgs a) {
   if (tid < a.tpc && t < a.n_tasks) {
     uint32_t row, nd;
     bool first;
-    bp_task(a, t, &row, &nd, &first);
+    bp_task(a, t, &row, &nd, &first, bp_first_row(a));
     if (first) a.row_off[row] = cta_base + s_taskcand[rank];
   }
 }
@@ -405,6 +423,14 @@ int broadphase(tob_ctx* c, int rb, int re, double d, int count_as) {
   return broadphase_rows(c, rb * c->n_tr, (re - rb) * c->n_tr, d, count_as);
 }
 
+// tasks per CTA: enough CTAs to cover the machine a few times over, at most BP_THREADS tasks each
+static uint32_t bp_tpc(tob_ctx* c, uint32_t n_tasks) {
+  uint32_t tpc = n_tasks / (4u * (uint32_t)c->sm_count);
+  static int tpc_cap = -1;
+  if (tpc_cap < 0) { const char* e = getenv("TRAJOPT_B200_BP_TPC"); tpc_cap = e ? atoi(e) : BP_THREADS; if (tpc_cap < 16 || tpc_cap > BP_THREADS) tpc_cap = BP_THREADS; }
+  return tpc < 16u ? 16u : (tpc > (uint32_t)tpc_cap ? (uint32_t)tpc_cap : tpc);
+}
+
 void bp_args(tob_ctx* c, int row_base, int rows, double d, BpArgs& a) {
   a.box = c->geo.box.p;
   a.rows = rows; a.n1 = c->lvl[1].count; a.n_tasks = (uint32_t)rows * a.n1; a.d = d; a.row_base = (uint32_t)row_base;
@@ -413,6 +439,7 @@ void bp_args(tob_ctx* c, int row_base, int rows, double d, BpArgs& a) {
     a.row_task = c->row_task.p; a.row_l1 = c->row_l1.p;
     a.n_tasks = c->h_row_task[row_base + rows] - c->h_row_task[row_base];
   }
+  a.cta_row = nullptr;
   a.rows_all = (uint32_t)c->rows_all();
   for (int k = 0; k < 3; k++) {
     a.l1lo[k] = c->lvl[1].lo[k]; a.l1hi[k] = c->lvl[1].hi[k];
@@ -424,10 +451,8 @@ void bp_args(tob_ctx* c, int row_base, int rows, double d, BpArgs& a) {
   a.cand_cap = (uint32_t)c->cand_cap;
   a.dc = c->dc.p;
   // enough CTAs to cover the machine a few times over, at most BP_THREADS tasks each
-  uint32_t tpc = a.n_tasks / (4u * (uint32_t)c->sm_count);
-  static int tpc_cap = -1;
-  if (tpc_cap < 0) { const char* e = getenv("TRAJOPT_B200_BP_TPC"); tpc_cap = e ? atoi(e) : BP_THREADS; if (tpc_cap < 16 || tpc_cap > BP_THREADS) tpc_cap = BP_THREADS; }
-  a.tpc = tpc < 16u ? 16u : (tpc > (uint32_t)tpc_cap ? (uint32_t)tpc_cap : tpc);
+  a.tpc = bp_tpc(c, a.n_tasks);
+  a.cta_row = (!c->cloud_n1.empty() && row_base == 0 && rows == c->rows_all() && a.tpc == c->cta_row_tpc && c->cta_row.p) ? c->cta_row.p : nullptr;
 }
 
 // same for an arbitrary row range [row_base, row_base+rows) of geo.box (tob_box_query uses row 0 with a caller box)

@@ -41,6 +41,8 @@ struct NarrowArgs {
   const uint32_t *cand_pt, *cand_row;
   const double *px, *py, *pz;
   const double *P, *klo, *khi, *kdop;
+  const float* kf;   // rows x TOB_KF_ROW: single-precision filter of the gate (segments.cu), with its centres kc (rows x 4)
+  const double* kc;
   double dist, offset;
   double* cpl;       // cap x 4
   uint32_t* cflag;   // cap
@@ -95,20 +97,35 @@ __device__ __forceinline__ uint32_t np_append(bool keep, uint32_t value, uint32_
 // rejected, on average after 1.7 of the 7 axis groups, while the others need all 7 -- thread-per-candidate over all groups
 // left 20 of 32 lanes active (ncu).  Stage 1 (the first NP_GATE1 axes) runs on every candidate, stage 2 (the rest) and GJK on
 // dense survivor lists.
+// FILT: the gate runs through the single-precision filter (gjk.cuh: kdop_point_gate; same decisions, the FP64 pipe is left to
+// GJK); false = every axis in the reference arithmetic (TRAJOPT_B200_NP_FILTER=0, kept for A/B measurements)
 #define NP_GATE1 14
-template <int MINB>
+template <bool FILT>
+__device__ __forceinline__ bool np_gate(const NarrowArgs& a, uint32_t row, const double* s_kdop, const float* s_kdop_f, const double* pt,
+                                        unsigned* groups, unsigned* exact, int axis_begin, int axis_end) {
+  const double *lo = a.klo + (size_t)TOB_KDOP_AXES * row, *hi = a.khi + (size_t)TOB_KDOP_AXES * row;
+  if (FILT) {
+    const double2 c01 = *reinterpret_cast<const double2*>(a.kc + (size_t)4 * row);
+    const double centre[3] = {c01.x, c01.y, a.kc[(size_t)4 * row + 2]};
+    return kdop_point_gate(a.kf + (size_t)TOB_KF_ROW * row, centre, s_kdop_f, lo, hi, s_kdop, pt, a.dist, groups, exact, axis_begin, axis_end);
+  }
+  return kdop_point_overlap(lo, hi, s_kdop, pt, a.dist, groups, axis_begin, axis_end);
+}
+
+template <int MINB, bool FILT>
 __global__ void __launch_bounds__(NP_THREADS, MINB) k_narrow(NarrowArgs a) {
   __shared__ double s_kdop[3 * TOB_KDOP_AXES];
+  __shared__ float s_kdop_f[3 * TOB_KDOP_AXES];
   __shared__ uint32_t s_surv[NP_CHUNK], s_surv2[NP_CHUNK];
   __shared__ uint32_t s_w[NP_THREADS / 32];
-  for (int i = threadIdx.x; i < 3 * TOB_KDOP_AXES; i += blockDim.x) s_kdop[i] = a.kdop[i];
+  for (int i = threadIdx.x; i < 3 * TOB_KDOP_AXES; i += blockDim.x) { s_kdop[i] = a.kdop[i]; s_kdop_f[i] = (float)a.kdop[i]; }
   const uint32_t n = a.dc->n_cand;
   if (n > a.cap) return;
   const uint32_t per = np_per_of(n, a.np_grid), chunk_sz = per * NP_THREADS;
   const uint32_t n_chunks = (n + chunk_sz - 1) / chunk_sz;
   const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t n_live = a.live_key ? a.dc->n_live : 0u;
-  unsigned w_groups = 0, w_iters = 0;   // counted work of this thread
+  unsigned w_groups = 0, w_iters = 0, w_exact = 0;   // counted work of this thread
   __syncthreads();
   for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     uint32_t n_surv = 0, n_surv2 = 0;   // uniform
@@ -134,8 +151,7 @@ __global__ void __launch_bounds__(NP_THREADS, MINB) k_narrow(NarrowArgs a) {
       bool pass = false;
       if (i < n) {
         const uint32_t row = c_row[q];
-        pass = kdop_point_overlap(a.klo + (size_t)TOB_KDOP_AXES * row, a.khi + (size_t)TOB_KDOP_AXES * row, s_kdop, c_pt[q], a.dist,
-                                  &w_groups, 0, NP_GATE1);
+        pass = np_gate<FILT>(a, row, s_kdop, s_kdop_f, c_pt[q], &w_groups, &w_exact, 0, NP_GATE1);
         a.cflag[i] = 0;
       }
       n_surv = np_append(pass, loc, s_surv, n_surv, s_w);
@@ -151,8 +167,7 @@ __global__ void __launch_bounds__(NP_THREADS, MINB) k_narrow(NarrowArgs a) {
         const uint32_t ii = chunk * chunk_sz + loc;
         const uint32_t row = a.cand_row[ii], p = a.cand_pt[ii];
         const double pt[3] = {a.px[p], a.py[p], a.pz[p]};
-        pass = kdop_point_overlap(a.klo + (size_t)TOB_KDOP_AXES * row, a.khi + (size_t)TOB_KDOP_AXES * row, s_kdop, pt, a.dist, &w_groups,
-                                  NP_GATE1, TOB_KDOP_AXES);
+        pass = np_gate<FILT>(a, row, s_kdop, s_kdop_f, pt, &w_groups, &w_exact, NP_GATE1, TOB_KDOP_AXES);
         if (pass && n_live) {   // is_seperate[tr_id][ob_id] (Optimization3D_admm.h:128): a live pair keeps its plane
           const unsigned long long key = ((unsigned long long)row << 32) | p;
           const uint32_t at = lower_bound_u64(a.live_key, n_live, key);
@@ -190,10 +205,12 @@ __global__ void __launch_bounds__(NP_THREADS, MINB) k_narrow(NarrowArgs a) {
   for (int o = 16; o; o >>= 1) {
     w_groups += __shfl_xor_sync(0xffffffffu, w_groups, o);
     w_iters += __shfl_xor_sync(0xffffffffu, w_iters, o);
+    w_exact += __shfl_xor_sync(0xffffffffu, w_exact, o);
   }
   if (lane == 0 && w_groups) {
     atomicAdd(&a.dc->np_kdop_groups, (unsigned long long)w_groups);
     atomicAdd(&a.dc->np_gjk_iters, (unsigned long long)w_iters);
+    if (w_exact) atomicAdd(&a.dc->np_kdop_exact, (unsigned long long)w_exact);
   }
 }
 
@@ -647,7 +664,8 @@ int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self) {
   a.dc = c->dc.p; a.cap = (uint32_t)c->cand_cap; a.cand_pt = c->cand_pt.p; a.cand_row = c->cand_row.p;
   a.px = c->px.p; a.py = c->py.p; a.pz = c->pz.p;
   a.P = c->geo.P.p; a.klo = c->geo.klo.p; a.khi = c->geo.khi.p; a.kdop = c->d_kdop.p;
-  a.dist = c->prm.offset + c->prm.margin; a.offset = c->prm.offset;
+  a.kf = c->geo.kf.p; a.kc = c->geo.kc.p;
+  a.dist = c->prm.offset + c->prm.margin; a.offset = c->prm.offset;     // the filter's thresholds are made for this gap (segments.cu)
   a.cpl = c->cpl.p; a.cflag = c->cflag.p; a.csum = c->csum.p;
   const bool live = c->live_planes();
   if (live) {
@@ -658,13 +676,14 @@ int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self) {
   a.np_grid = (uint32_t)c->sm_count * 4;
   {
     Prof prof(c, K_NARROW);
-    static int occ = -1;
-    if (occ < 0) { const char* e = getenv("TRAJOPT_B200_NP_OCC"); occ = e ? atoi(e) : 4; }
+    const char *eo = getenv("TRAJOPT_B200_NP_OCC"), *ef = getenv("TRAJOPT_B200_NP_FILTER");   // A/B measurements, tests
+    const int occ = eo ? atoi(eo) : 4, filt = ef ? atoi(ef) : 1;
     a.np_grid = (uint32_t)c->sm_count * 4;
-    if (occ == 8) k_narrow<8><<<c->sm_count * 8, NP_THREADS, 0, st>>>(a);
-    else if (occ == 6) k_narrow<6><<<c->sm_count * 6, NP_THREADS, 0, st>>>(a);
-    else if (occ == 5) k_narrow<5><<<c->sm_count * 5, NP_THREADS, 0, st>>>(a);
-    else k_narrow<4><<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
+    if (!filt) k_narrow<4, false><<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
+    else if (occ == 8) k_narrow<8, true><<<c->sm_count * 8, NP_THREADS, 0, st>>>(a);
+    else if (occ == 6) k_narrow<6, true><<<c->sm_count * 6, NP_THREADS, 0, st>>>(a);
+    else if (occ == 5) k_narrow<5, true><<<c->sm_count * 5, NP_THREADS, 0, st>>>(a);
+    else k_narrow<4, true><<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
   if (with_self < 0) return 0;      // obstacle part only: the caller finishes with narrowphase_finish()
@@ -741,7 +760,11 @@ __device__ __forceinline__ void moved_points(const double (*P)[3], const double 
     }
 }
 
-__global__ void __launch_bounds__(BP_THREADS, 4) k_bp_ccd(CcdArgs a) {
+// MINB: resident CTAs per SM the registers are allotted for.  The traversal needs few registers, the ladder (swept 49-DOP +
+// GJK on 12 + 1 points) many; with thousands of rows nearly every CTA only traverses (377 k of 73 M point tests reach the ladder
+// on the 1024-problem batch), so the many-row launch takes the variant with more resident warps and lets the rare ladder spill.
+template <int MINB>
+__global__ void __launch_bounds__(BP_THREADS, MINB) k_bp_ccd(CcdArgs a) {
   __shared__ BpShared s;
   __shared__ double s_kdop[3 * TOB_KDOP_AXES];
   for (int i = threadIdx.x; i < 3 * TOB_KDOP_AXES; i += blockDim.x) s_kdop[i] = a.kdop[i];
@@ -750,8 +773,9 @@ __global__ void __launch_bounds__(BP_THREADS, 4) k_bp_ccd(CcdArgs a) {
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   uint32_t cnt = 0;
   unsigned w_iters = 0, w_pass = 0;
+  uint32_t h = 0;                                          // bp_item cursor
   for (uint32_t j = w; j < n_items; j += BP_WARPS) {
-    uint32_t h, row, leaf;
+    uint32_t row, leaf;
     bp_item(a.bp, s, j, &h, &row, &leaf);
     double q[1][3];
     const bool ok = bp_point_test(a.bp, s, h, leaf * 32 + lane, &q[0][0], &q[0][1], &q[0][2]);
@@ -800,7 +824,13 @@ int ccd_position_steps(tob_ctx* c, int rb, int re) {
   a.kmax = c->kmax.p;
   if (a.bp.n_tasks) {
     Prof prof(c, K_CCD);
-    k_bp_ccd<<<div_up((size_t)a.bp.n_tasks, a.bp.tpc), BP_THREADS, 0, c->stream>>>(a);
+    const char* e = getenv("TRAJOPT_B200_CCD_OCC");
+    const int occ = e ? atoi(e) : 0;
+    const int grid = div_up((size_t)a.bp.n_tasks, a.bp.tpc);
+    const int use = occ ? occ : (a.bp.rows >= 8192 ? 8 : 4);
+    if (use >= 12) k_bp_ccd<12><<<grid, BP_THREADS, 0, c->stream>>>(a);
+    else if (use >= 8) k_bp_ccd<8><<<grid, BP_THREADS, 0, c->stream>>>(a);
+    else k_bp_ccd<4><<<grid, BP_THREADS, 0, c->stream>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
   return 0;
@@ -962,8 +992,9 @@ __global__ void __launch_bounds__(BP_THREADS, 4) k_bp_edge(EdgeArgs a) {
   const uint32_t n_items = bp_prepare(a.bp, s, &rank);
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const double d2 = a.d * a.d;
+  uint32_t h = 0;                                          // bp_item cursor
   for (uint32_t j = w; j < n_items; j += BP_WARPS) {
-    uint32_t h, row, leaf;
+    uint32_t row, leaf;
     bp_item(a.bp, s, j, &h, &row, &leaf);
     double q[1][3];
     const bool ok = bp_point_test(a.bp, s, h, leaf * 32 + lane, &q[0][0], &q[0][1], &q[0][2]);
@@ -1008,7 +1039,7 @@ int edge_validity(tob_ctx* c, const double* edges_host, int n, double d, uint8_t
     EdgeArgs a;
     a.bp.box = c->scratch.p + (size_t)6 * b0;
     a.bp.rows = (uint32_t)nb; a.bp.n1 = n1; a.bp.n_tasks = (uint32_t)nb * n1; a.bp.row_base = 0; a.bp.rows_all = (uint32_t)nb;
-    a.bp.d = d; a.bp.row_task = nullptr; a.bp.row_l1 = nullptr;
+    a.bp.d = d; a.bp.row_task = nullptr; a.bp.row_l1 = nullptr; a.bp.cta_row = nullptr;
     for (int k = 0; k < 3; k++) {
       a.bp.l1lo[k] = c->lvl[1].lo[k]; a.bp.l1hi[k] = c->lvl[1].hi[k];
       a.bp.l0lo[k] = c->lvl[0].lo[k]; a.bp.l0hi[k] = c->lvl[0].hi[k];

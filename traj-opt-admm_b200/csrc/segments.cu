@@ -19,12 +19,15 @@ struct RowArgs {
   const double* basis;    // n_tr x 36
   const double* kdop;     // 147
   double *P, *D, *box, *klo, *khi;
+  float* kf;              // rows x TOB_KF_ROW: single-precision filter of the 49-DOP gate (gjk.cuh: kdop_point_gate)
+  double* kc;             // rows x 4: the centre the filter's thresholds refer to
+  double gate_d;          // gap of the gate the thresholds are made for (offset + margin)
   int n_tr, res, T, row_begin, row_end, mode;
   int* kmax;              // mode & 2: per-robot CCD ladder exponent, reset here for the fused CCD kernel
 };
 
 __global__ void __launch_bounds__(128) k_rows(RowArgs a) {
-  __shared__ double sP[4][18], sQ[4][18], sBz[4][18], sBd[4][18];
+  __shared__ double sP[4][18], sQ[4][18], sBz[4][18], sBd[4][18], sM[4][3];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int row = a.row_begin + blockIdx.x * 4 + w;
   const bool live = row < a.row_end;
@@ -71,8 +74,11 @@ __global__ void __launch_bounds__(128) k_rows(RowArgs a) {
     }
     a.box[(size_t)6 * row + lane] = lo;
     a.box[(size_t)6 * row + 3 + lane] = hi;
+    sM[w][lane] = 0.5 * (lo + hi);      // centre of the filter's thresholds: any point near the row would do
   }
+  __syncwarp();
   if (live && (a.mode & 1)) {
+    float tmag = 0.f;
     for (int k = lane; k < TOB_KDOP_AXES; k += 32) {
       double x = a.kdop[3 * k], y = a.kdop[3 * k + 1], z = a.kdop[3 * k + 2];
       double lo = INFINITY, hi = -INFINITY;
@@ -83,7 +89,19 @@ __global__ void __launch_bounds__(128) k_rows(RowArgs a) {
       }
       a.klo[(size_t)TOB_KDOP_AXES * row + k] = lo;
       a.khi[(size_t)TOB_KDOP_AXES * row + k] = hi;
+      float tl, th;
+      const float tm = kdop_gate_thresholds(lo, hi, a.gate_d, x * sM[w][0] + y * sM[w][1] + z * sM[w][2], &tl, &th);
+      tmag = fmaxf(tmag, tm);
+      if (!(tm <= 3.0e38f)) tmag = INFINITY;     // NaN / overflow: the allowance becomes infinite, every axis is re-tested
+      a.kf[(size_t)TOB_KF_ROW * row + 2 * k] = tl;
+      a.kf[(size_t)TOB_KF_ROW * row + 2 * k + 1] = th;
     }
+    for (int o = 16; o; o >>= 1) tmag = fmaxf(tmag, __shfl_xor_sync(0xffffffffu, tmag, o));
+    if (lane == 0) {
+      a.kf[(size_t)TOB_KF_ROW * row + 2 * TOB_KDOP_AXES] = kdop_gate_allowance(tmag, sM[w], a.gate_d);
+      a.kf[(size_t)TOB_KF_ROW * row + 2 * TOB_KDOP_AXES + 1] = 0.f;
+    }
+    if (lane < 4) a.kc[(size_t)4 * row + lane] = lane < 3 ? sM[w][lane] : 0.0;
   }
 }
 
@@ -94,10 +112,13 @@ int compute_rows(tob_ctx* c, const double* spline_dev, const double* dir_dev, co
   TOB_CUDA(c, c->geo.box.ensure((size_t)6 * rows));
   TOB_CUDA(c, c->geo.klo.ensure((size_t)TOB_KDOP_AXES * rows));
   TOB_CUDA(c, c->geo.khi.ensure((size_t)TOB_KDOP_AXES * rows));
+  TOB_CUDA(c, c->geo.kf.ensure((size_t)TOB_KF_ROW * rows));
+  TOB_CUDA(c, c->geo.kc.ensure((size_t)4 * rows));
   RowArgs a;
   a.spline = spline_dev; a.dir = dir_dev; a.step = step_dev;
   a.basis = c->d_basis.p; a.kdop = c->d_kdop.p;
   a.P = c->geo.P.p; a.D = c->geo.D.p; a.box = c->geo.box.p; a.klo = c->geo.klo.p; a.khi = c->geo.khi.p;
+  a.kf = c->geo.kf.p; a.kc = c->geo.kc.p; a.gate_d = c->prm.offset + c->prm.margin;
   a.n_tr = c->n_tr; a.res = c->prm.res; a.T = c->T; a.row_begin = rb * c->n_tr; a.row_end = re * c->n_tr; a.mode = mode;
   a.kmax = c->kmax.p;
   if (re > rb) {
