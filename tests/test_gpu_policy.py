@@ -68,7 +68,8 @@ def _batch(n=130):
 
 
 def _run_batch(scs, sts, iters, env):
-    keys = ("TRAJOPT_B200_LS", "TRAJOPT_B200_EN_OCC", "TRAJOPT_B200_NP_FILTER", "TRAJOPT_B200_CCD_OCC", "TRAJOPT_B200_NP_OCC")
+    keys = ("TRAJOPT_B200_LS", "TRAJOPT_B200_EN_OCC", "TRAJOPT_B200_NP_FILTER", "TRAJOPT_B200_CCD_OCC", "TRAJOPT_B200_NP_OCC",
+            "TRAJOPT_B200_PACK_GRID")
     for k in keys:
         os.environ.pop(k, None)
     os.environ.update(env)
@@ -94,7 +95,8 @@ def test_many_rows_result_independent_of_kernel_variants_and_schedule():
     assert cref["np_kdop_groups"] > 0
     for env in ({"TRAJOPT_B200_EN_OCC": "0", "TRAJOPT_B200_NP_FILTER": "0", "TRAJOPT_B200_CCD_OCC": "4"},
                 {"TRAJOPT_B200_EN_OCC": "2", "TRAJOPT_B200_LS": "2,5,5", "TRAJOPT_B200_CCD_OCC": "12"},
-                {"TRAJOPT_B200_LS": "2,2,16"}, {"TRAJOPT_B200_LS": "2,3,9"}, {"TRAJOPT_B200_LS": "9,9,2", "TRAJOPT_B200_NP_OCC": "6"}):
+                {"TRAJOPT_B200_LS": "2,2,16", "TRAJOPT_B200_PACK_GRID": "4"}, {"TRAJOPT_B200_LS": "2,3,9"},
+                {"TRAJOPT_B200_LS": "9,9,2", "TRAJOPT_B200_NP_OCC": "6"}):
         got, cgot = _run_batch(scs, sts, 5, env)
         assert same(ref, got), env
         assert cgot["planes"] == cref["planes"] and cgot["dcd_candidates"] == cref["dcd_candidates"], env

@@ -649,7 +649,13 @@ static int pack_rows(tob_ctx* c, int rb, int re, bool ws, bool live = false) {
   if (live) { TOB_TRY(live_rows(c)); return energy_items(c, false); }
   {
     Prof prof(c, K_PACK);
-    k_pack<<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
+    // chunks as k_narrow cut them (np_grid), but spread over every resident CTA slot: the scatter is a chain of dependent loads
+    // (flag -> row -> plane) per thread, bound by the number of warps in flight (ncu: 33 cycles of long-scoreboard stall per issue
+    // at 4 CTAs per SM, 0.33 of the HBM peak; 16 per SM: 0.182 -> 0.089 ms on a 128-problem shard of the batch)
+    const char* e = getenv("TRAJOPT_B200_PACK_GRID");
+    int per_sm = e ? atoi(e) : 16;
+    if (per_sm < 1 || per_sm > 32) per_sm = 16;
+    k_pack<<<c->sm_count * per_sm, NP_THREADS, 0, st>>>(a);
     TOB_LAUNCH_CHECK(c);
   }
   return energy_items(c, false);   // k_np_top zeroed the counter
