@@ -508,7 +508,7 @@ def run_ours(args):
         "config": describe(args, world),
         "pair_evals_per_s": pair_evals / (total_ms * 1e-3),
         "pairs_per_step": {k: ctr[k] / args.steps for k in ("dcd_candidates", "planes", "ccd_candidates", "energy_plane_evals", "barrier_terms",
-                                                             "np_kdop_groups", "np_gjk_iters", "np_kdop_exact", "ccd_kdop_pass", "ccd_gjk_iters", "line_search_trials")},
+                                                             "np_kdop_groups", "np_gjk_iters", "np_kdop_exact", "np_band", "ccd_kdop_pass", "ccd_gjk_iters", "line_search_trials")},
         "e2e": {"value": mult * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": state_bytes * world, "d2h_bytes_per_step": state_bytes * world},
         "gpu_launches": int(pe[1]),
         "clocks": sampler.summary(),

@@ -244,6 +244,7 @@ typedef struct tob_counters {
   uint64_t ccd_gjk_iters;        /* GJK(12,1) rounds run by the CCD ladder */
   uint64_t ccd_kdop_pass;        /* swept candidates that passed the swept 49-DOP gate */
   uint64_t np_kdop_exact;        /* axes of the 49-DOP gate the single-precision filter left undecided (re-tested in FP64) */
+  uint64_t np_band;              /* pairs whose GJK distance fell within 1e-6 (relative) of the gap: the only ones that need axes 15..49 of the gate */
 } tob_counters;
 int tob_get_counters(const tob_ctx* ctx, tob_counters* out);
 int tob_reset_counters(tob_ctx* ctx);

@@ -69,7 +69,7 @@ def _batch(n=130):
 
 def _run_batch(scs, sts, iters, env):
     keys = ("TRAJOPT_B200_LS", "TRAJOPT_B200_EN_OCC", "TRAJOPT_B200_NP_FILTER", "TRAJOPT_B200_CCD_OCC", "TRAJOPT_B200_NP_OCC",
-            "TRAJOPT_B200_PACK_GRID")
+            "TRAJOPT_B200_PACK_GRID", "TRAJOPT_B200_NP_BAND", "TRAJOPT_B200_NP_GATE1")
     for k in keys:
         os.environ.pop(k, None)
     os.environ.update(env)
@@ -96,12 +96,18 @@ def test_many_rows_result_independent_of_kernel_variants_and_schedule():
     for env in ({"TRAJOPT_B200_EN_OCC": "0", "TRAJOPT_B200_NP_FILTER": "0", "TRAJOPT_B200_CCD_OCC": "4"},
                 {"TRAJOPT_B200_EN_OCC": "2", "TRAJOPT_B200_LS": "2,5,5", "TRAJOPT_B200_CCD_OCC": "12"},
                 {"TRAJOPT_B200_LS": "2,2,16", "TRAJOPT_B200_PACK_GRID": "4"}, {"TRAJOPT_B200_LS": "2,3,9"},
-                {"TRAJOPT_B200_LS": "9,9,2", "TRAJOPT_B200_NP_OCC": "6"}):
+                {"TRAJOPT_B200_LS": "9,9,2", "TRAJOPT_B200_NP_OCC": "6"},
+                {"TRAJOPT_B200_NP_BAND": "0"}, {"TRAJOPT_B200_NP_BAND": "0", "TRAJOPT_B200_NP_FILTER": "0", "TRAJOPT_B200_NP_GATE1": "49"},
+                {"TRAJOPT_B200_NP_GATE1": "7"}):
         got, cgot = _run_batch(scs, sts, 5, env)
         assert same(ref, got), env
         assert cgot["planes"] == cref["planes"] and cgot["dcd_candidates"] == cref["dcd_candidates"], env
         if env.get("TRAJOPT_B200_NP_FILTER") == "0":
-            assert cgot["np_kdop_exact"] == 0 and cgot["np_kdop_groups"] == cref["np_kdop_groups"]
+            assert cgot["np_kdop_exact"] == 0
+            if "TRAJOPT_B200_NP_GATE1" not in env:
+                assert cgot["np_kdop_groups"] == cref["np_kdop_groups"]
+        if env.get("TRAJOPT_B200_NP_BAND") == "0":      # every accepted pair went through the rest of the gate
+            assert cgot["np_band"] >= cgot["planes"] > 0
     for u in (0, 57, 129):
         s1 = api.Solver(8, uav_num=1, ks=1e-8)
         s1.init_pointcloud(scs[u]["V"])
@@ -129,3 +135,32 @@ def test_kdop_filter_same_planes_as_fp64_gate():
     assert np.array_equal(o1, o0) and np.array_equal(c1, c0) and np.array_equal(d1, d0)
     assert k0["np_kdop_exact"] == 0 and k1["np_kdop_groups"] == k0["np_kdop_groups"]
     assert k1["np_kdop_exact"] < 1e-3 * 7 * k1["np_kdop_groups"]        # the fallback is rare
+
+
+def test_gate_implied_by_gjk_distance_same_planes_as_full_gate():
+    """Plane sets with the 49-DOP gate cut short by the GJK distance (default: axes 15..49 only for pairs within 1e-6 of the
+    gap) against the reference order (all 49 axes first, then GJK: TRAJOPT_B200_NP_GATE1=49) and against the forced band
+    (rest of the gate for every accepted pair): bit-identical offsets and planes; the band itself is nearly empty."""
+    sc = scenes.forest(n_pts=200_000, seed=2)
+    st = scenes.initial_states(sc)[0]
+    P = len(sc["way_points"][0]) - 1
+    out = []
+    keys = ("TRAJOPT_B200_NP_BAND", "TRAJOPT_B200_NP_GATE1", "TRAJOPT_B200_NP_FILTER")
+    for env in ({}, {"TRAJOPT_B200_NP_GATE1": "49", "TRAJOPT_B200_NP_FILTER": "0"}, {"TRAJOPT_B200_NP_BAND": "0"},
+                {"TRAJOPT_B200_NP_GATE1": "7"}, {"TRAJOPT_B200_NP_GATE1": "28"}):
+        os.environ.update(env)
+        try:
+            s = api.Solver(P, ks=sc["ks"])
+            s.init_pointcloud(sc["V"])
+            out.append(s.separate_plane(st["spline"]) + (s.counters(),))
+        finally:
+            for k in keys:
+                os.environ.pop(k, None)
+    o0, c0, d0, k0 = out[0]
+    assert len(d0) > 1000
+    for o, c, d, k in out[1:]:
+        assert np.array_equal(o, o0) and np.array_equal(c, c0) and np.array_equal(d, d0)
+        assert k["planes"] == k0["planes"]
+    assert k0["np_band"] <= 1e-4 * k0["planes"] + 2
+    assert out[1][3]["np_band"] <= 1e-4 * k0["planes"] + 2 and out[2][3]["np_band"] >= k0["planes"]
+    assert k0["np_kdop_groups"] < out[1][3]["np_kdop_groups"]       # the point of it: fewer axes evaluated

@@ -1468,6 +1468,7 @@ int tob_get_counters(const tob_ctx* cc, tob_counters* out) {
   out->ccd_gjk_iters = c->h_dc->ccd_gjk_iters;
   out->ccd_kdop_pass = c->h_dc->ccd_kdop_pass;
   out->np_kdop_exact = c->h_dc->np_kdop_exact;
+  out->np_band = c->h_dc->np_band;
   return 0;
 }
 int tob_reset_counters(tob_ctx* c) {
@@ -1475,7 +1476,7 @@ int tob_reset_counters(tob_ctx* c) {
   cudaSetDevice(c->device);
   memset(&c->ctr, 0, sizeof(c->ctr));
   TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->dcd_candidates, 0, 5 * sizeof(unsigned long long), c->stream));
-  TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->np_kdop_groups, 0, 5 * sizeof(unsigned long long), c->stream));
+  TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->np_kdop_groups, 0, 6 * sizeof(unsigned long long), c->stream));
   return 0;
 }
 

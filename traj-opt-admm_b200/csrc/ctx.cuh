@@ -94,6 +94,7 @@ struct DevCounts {
   unsigned long long ccd_gjk_iters;    // GJK(12,1) rounds run by the CCD ladder of k_bp_ccd
   unsigned long long ccd_kdop_pass;    // swept candidates that passed the swept 49-DOP gate (each runs >= 1 ladder rung)
   unsigned long long np_kdop_exact;    // axes of the 49-DOP gate the single-precision filter could not decide (re-tested in FP64)
+  unsigned long long np_band;          // pairs whose GJK distance fell inside the band where the rest of the gate had to be evaluated
 };
 
 // per-row (robot x sub-segment) geometry produced by segments.cu, indexed by GLOBAL row = robot*n_tr + tr

@@ -682,16 +682,23 @@ TOB_HD void swept_points(const double (*P)[3], const double (*D)[3], double t0, 
 // against the compiled reference)
 TOB_HD double eig_norm3(const double* c) { return sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]); }
 
-// segment (6 pts) vs obstacle point: plane n.x + d >= 0 (Separate.h:18-163)
-TOB_HD bool plane_point(const double (*P)[3], const double* q, double distance, double offset, double* c, double* d,
-                        unsigned* gjk_iters = nullptr) {
+// segment (6 pts) vs obstacle point: plane n.x + d >= 0 (Separate.h:18-163), in two halves so that a caller can look at the
+// distance before it decides (narrow.cu): witness + its norm, then normal and offset.  plane_point() is the two in a row.
+TOB_HD double plane_point_witness(const double (*P)[3], const double* q, double* c, unsigned* gjk_iters = nullptr) {
   double Bq[1][3] = {{q[0], q[1], q[2]}};
   gjk_witness<6, 1>(P, Bq, c, gjk_iters);
-  double cn = eig_norm3(c);
-  if (cn > distance) return false;
+  return eig_norm3(c);
+}
+TOB_HD void plane_point_finish(const double* q, double offset, double cn, double* c, double* d) {
   c[0] /= cn; c[1] /= cn; c[2] /= cn;
   double d0 = -c[0] * q[0] - c[1] * q[1] - c[2] * q[2];
   *d = d0 - offset;
+}
+TOB_HD bool plane_point(const double (*P)[3], const double* q, double distance, double offset, double* c, double* d,
+                        unsigned* gjk_iters = nullptr) {
+  const double cn = plane_point_witness(P, q, c, gjk_iters);
+  if (cn > distance) return false;
+  plane_point_finish(q, offset, cn, c, d);
   return true;
 }
 

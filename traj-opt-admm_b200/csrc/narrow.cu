@@ -44,6 +44,8 @@ struct NarrowArgs {
   const float* kf;   // rows x TOB_KF_ROW: single-precision filter of the gate (segments.cu), with its centres kc (rows x 4)
   const double* kc;
   double dist, offset;
+  double gate_skip;  // |witness| <= gate_skip: the rest of the gate is implied (see k_narrow); dist * (1 - 1e-6), or -1: never
+  int gate1;         // axes of the gate that run on every candidate (a multiple of 7)
   double* cpl;       // cap x 4
   uint32_t* cflag;   // cap
   uint32_t* csum;    // chunks + 1
@@ -74,7 +76,6 @@ __device__ __forceinline__ uint32_t np_per_of(uint32_t n, uint32_t grid) {
   return 1;
 }
 
-// MINB = resident CTAs per SM the register allocation is made for (4: 128 registers, 5: 102, 6: 85, 8: 64)
 // block-wide stable compaction step: the threads with `keep` append `value` to list[count ...] in thread order; returns the
 // new count (uniform).  Two barriers; s_w is scratch of NP_THREADS / 32 words.
 __device__ __forceinline__ uint32_t np_append(bool keep, uint32_t value, uint32_t* list, uint32_t count, uint32_t* s_w) {
@@ -93,13 +94,21 @@ __device__ __forceinline__ uint32_t np_append(bool keep, uint32_t value, uint32_
   return count + tot;
 }
 
-// The 49-DOP gate runs in two stages with a compaction in between: 44 % of the candidates of the batched workload are
-// rejected, on average after 1.7 of the 7 axis groups, while the others need all 7 -- thread-per-candidate over all groups
-// left 20 of 32 lanes active (ncu).  Stage 1 (the first NP_GATE1 axes) runs on every candidate, stage 2 (the rest) and GJK on
-// dense survivor lists.
-// FILT: the gate runs through the single-precision filter (gjk.cuh: kdop_point_gate; same decisions, the FP64 pipe is left to
-// GJK); false = every axis in the reference arithmetic (TRAJOPT_B200_NP_FILTER=0, kept for A/B measurements)
 #define NP_GATE1 14
+// A pair gets a plane iff the 49-DOP gate passes (CCD::KDOPDCD) AND the GJK distance is <= dist (Separate::opengjk), both with
+// the same gap dist = offset + margin (Optimization3D_admm.h:113-160).  The two tests are not independent: the gate is a
+// conservative filter of the distance test.  The axes are unit vectors and the GJK witness is a convex combination of
+// vertices of hull - point, so |witness| >= the true distance, and a true distance <= dist puts the point inside every slab
+// widened by dist.  A pair with |witness| <= dist * (1 - 1e-6) therefore passes the gate by a margin (2e-7 for dist = 0.2)
+// that is seven orders of magnitude above the rounding of either computation (1e-14), and the gate need not be evaluated for
+// it; a pair with |witness| > dist gets no plane whatever the gate says.  Only inside the band in between -- and for a NaN
+// witness -- is the gate's own arithmetic decisive, and there it is evaluated as the reference does.  So: the first NP_GATE1
+// axes run on every candidate (they reject 40 % of them after one or two groups of 7 axes, far cheaper than GJK), the survivors
+// are compacted and run GJK on dense warps, and the remaining axes run for the pairs in the band only (counted:
+// DevCounts::np_band).  Before, 56 % of the candidates paid all 49 axes and then GJK.
+// gate_skip = dist * (1 - 1e-6); -1 (TRAJOPT_B200_NP_BAND=0, tests) evaluates the remaining axes for every accepted pair.
+// FILT: the gate runs through the single-precision filter (gjk.cuh: kdop_point_gate; same decisions); false = every axis in
+// the reference arithmetic (TRAJOPT_B200_NP_FILTER=0, kept for A/B measurements)
 template <bool FILT>
 __device__ __forceinline__ bool np_gate(const NarrowArgs& a, uint32_t row, const double* s_kdop, const float* s_kdop_f, const double* pt,
                                         unsigned* groups, unsigned* exact, int axis_begin, int axis_end) {
@@ -112,23 +121,28 @@ __device__ __forceinline__ bool np_gate(const NarrowArgs& a, uint32_t row, const
   return kdop_point_overlap(lo, hi, s_kdop, pt, a.dist, groups, axis_begin, axis_end);
 }
 
+// MINB = resident CTAs per SM the register allocation is made for (4: 128 registers, 5: 102, 6: 85, 8: 64)
 template <int MINB, bool FILT>
 __global__ void __launch_bounds__(NP_THREADS, MINB) k_narrow(NarrowArgs a) {
   __shared__ double s_kdop[3 * TOB_KDOP_AXES];
-  __shared__ float s_kdop_f[3 * TOB_KDOP_AXES];
-  __shared__ uint32_t s_surv[NP_CHUNK], s_surv2[NP_CHUNK];
+  __shared__ float s_kdop_f[FILT ? 3 * TOB_KDOP_AXES : 1];
+  __shared__ uint32_t s_surv[NP_CHUNK];
   __shared__ uint32_t s_w[NP_THREADS / 32];
-  for (int i = threadIdx.x; i < 3 * TOB_KDOP_AXES; i += blockDim.x) { s_kdop[i] = a.kdop[i]; s_kdop_f[i] = (float)a.kdop[i]; }
+  for (int i = threadIdx.x; i < 3 * TOB_KDOP_AXES; i += blockDim.x) {
+    s_kdop[i] = a.kdop[i];
+    if (FILT) s_kdop_f[i] = (float)a.kdop[i];
+  }
   const uint32_t n = a.dc->n_cand;
   if (n > a.cap) return;
   const uint32_t per = np_per_of(n, a.np_grid), chunk_sz = per * NP_THREADS;
   const uint32_t n_chunks = (n + chunk_sz - 1) / chunk_sz;
   const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t n_live = a.live_key ? a.dc->n_live : 0u;
-  unsigned w_groups = 0, w_iters = 0, w_exact = 0;   // counted work of this thread
+  const int gate1 = a.gate1;
+  unsigned w_groups = 0, w_iters = 0, w_exact = 0, w_band = 0;   // counted work of this thread
   __syncthreads();
   for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    uint32_t n_surv = 0, n_surv2 = 0;   // uniform
+    uint32_t n_surv = 0;   // uniform
     // the candidates of this thread are gathered first (index -> row / point -> coordinates are two dependent global loads
     // each; one after the other behind the block barriers of the compaction they cost four round trips instead of one)
     uint32_t c_row[NP_PER];
@@ -143,7 +157,7 @@ __global__ void __launch_bounds__(NP_THREADS, MINB) k_narrow(NarrowArgs a) {
         c_pt[q][0] = a.px[p]; c_pt[q][1] = a.py[p]; c_pt[q][2] = a.pz[p];
       }
     }
-    // stage 1: the first NP_GATE1 axes, every candidate
+    // the first axes of the gate, every candidate
 #pragma unroll
     for (uint32_t q = 0; q < NP_PER; q++) {
       if (q >= per) break;   // uniform
@@ -151,41 +165,33 @@ __global__ void __launch_bounds__(NP_THREADS, MINB) k_narrow(NarrowArgs a) {
       bool pass = false;
       if (i < n) {
         const uint32_t row = c_row[q];
-        pass = np_gate<FILT>(a, row, s_kdop, s_kdop_f, c_pt[q], &w_groups, &w_exact, 0, NP_GATE1);
+        pass = np_gate<FILT>(a, row, s_kdop, s_kdop_f, c_pt[q], &w_groups, &w_exact, 0, gate1);
         a.cflag[i] = 0;
       }
       n_surv = np_append(pass, loc, s_surv, n_surv, s_w);
     }
     __syncthreads();
-    // stage 2: the remaining axes on the dense list of stage-1 survivors
-    for (uint32_t s0 = 0; s0 < n_surv; s0 += NP_THREADS) {      // uniform trip count
-      const uint32_t sidx = s0 + tid;
-      bool pass = false;
-      uint32_t loc = 0;
-      if (sidx < n_surv) {
-        loc = s_surv[sidx];
-        const uint32_t ii = chunk * chunk_sz + loc;
-        const uint32_t row = a.cand_row[ii], p = a.cand_pt[ii];
-        const double pt[3] = {a.px[p], a.py[p], a.pz[p]};
-        pass = np_gate<FILT>(a, row, s_kdop, s_kdop_f, pt, &w_groups, &w_exact, NP_GATE1, TOB_KDOP_AXES);
-        if (pass && n_live) {   // is_seperate[tr_id][ob_id] (Optimization3D_admm.h:128): a live pair keeps its plane
-          const unsigned long long key = ((unsigned long long)row << 32) | p;
-          const uint32_t at = lower_bound_u64(a.live_key, n_live, key);
-          if (at < n_live && a.live_key[at] == key) pass = false;
-        }
-      }
-      n_surv2 = np_append(pass, loc, s_surv2, n_surv2, s_w);
-    }
-    __syncthreads();
-    // GJK + plane on the dense list of gate survivors
+    // GJK + plane on the dense list of survivors
     uint32_t ok = 0;
-    for (uint32_t sidx = tid; sidx < n_surv2; sidx += NP_THREADS) {
-      const uint32_t ii = chunk * chunk_sz + s_surv2[sidx];
+    for (uint32_t sidx = tid; sidx < n_surv; sidx += NP_THREADS) {
+      const uint32_t ii = chunk * chunk_sz + s_surv[sidx];
       const uint32_t row = a.cand_row[ii], p = a.cand_pt[ii];
+      if (n_live) {   // is_seperate[tr_id][ob_id] (Optimization3D_admm.h:128): a live pair keeps its plane
+        const unsigned long long key = ((unsigned long long)row << 32) | p;
+        const uint32_t at = lower_bound_u64(a.live_key, n_live, key);
+        if (at < n_live && a.live_key[at] == key) continue;
+      }
       const double pt[3] = {a.px[p], a.py[p], a.pz[p]};
       double P[6][3], c[3], d;
       load_pts6(a.P + (size_t)18 * row, P);
-      if (plane_point(P, pt, a.dist, a.offset, c, &d, &w_iters)) {
+      const double cn = plane_point_witness(P, pt, c, &w_iters);
+      bool acc = !(cn > a.dist);
+      if (acc && !(cn <= a.gate_skip)) {      // inside the band (or NaN): the gate's own arithmetic decides
+        w_band++;
+        acc = np_gate<FILT>(a, row, s_kdop, s_kdop_f, pt, &w_groups, &w_exact, gate1, TOB_KDOP_AXES);
+      }
+      if (acc) {
+        plane_point_finish(pt, a.offset, cn, c, &d);
         ok++;
         *reinterpret_cast<double4*>(a.cpl + (size_t)4 * ii) = make_double4(c[0], c[1], c[2], d);
         a.cflag[ii] = 1;
@@ -206,11 +212,13 @@ __global__ void __launch_bounds__(NP_THREADS, MINB) k_narrow(NarrowArgs a) {
     w_groups += __shfl_xor_sync(0xffffffffu, w_groups, o);
     w_iters += __shfl_xor_sync(0xffffffffu, w_iters, o);
     w_exact += __shfl_xor_sync(0xffffffffu, w_exact, o);
+    w_band += __shfl_xor_sync(0xffffffffu, w_band, o);
   }
   if (lane == 0 && w_groups) {
     atomicAdd(&a.dc->np_kdop_groups, (unsigned long long)w_groups);
     atomicAdd(&a.dc->np_gjk_iters, (unsigned long long)w_iters);
     if (w_exact) atomicAdd(&a.dc->np_kdop_exact, (unsigned long long)w_exact);
+    if (w_band) atomicAdd(&a.dc->np_band, (unsigned long long)w_band);
   }
 }
 
@@ -683,7 +691,11 @@ int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self) {
   {
     Prof prof(c, K_NARROW);
     const char *eo = getenv("TRAJOPT_B200_NP_OCC"), *ef = getenv("TRAJOPT_B200_NP_FILTER");   // A/B measurements, tests
+    const char *eb = getenv("TRAJOPT_B200_NP_BAND"), *eg = getenv("TRAJOPT_B200_NP_GATE1");
     const int occ = eo ? atoi(eo) : 4, filt = ef ? atoi(ef) : 1;
+    a.gate_skip = (eb && atoi(eb) == 0) ? -1.0 : a.dist * (1.0 - 1e-6);
+    a.gate1 = eg ? atoi(eg) : NP_GATE1;
+    if (a.gate1 < 7 || a.gate1 > TOB_KDOP_AXES || a.gate1 % 7) a.gate1 = NP_GATE1;
     a.np_grid = (uint32_t)c->sm_count * 4;
     if (!filt) k_narrow<4, false><<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
     else if (occ == 8) k_narrow<8, true><<<c->sm_count * 8, NP_THREADS, 0, st>>>(a);
