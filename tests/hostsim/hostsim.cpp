@@ -153,3 +153,17 @@ int hs_kdop_gate_batch(const double* P, const double* pts, int n, const double* 
 }
 
 }  // extern "C"
+
+// ---- fastlog.cuh: the barrier kernels' logarithm, host build (tests/test_cpu_checks.py::test_fast_log) ----
+#include "../../traj-opt-admm_b200/csrc/fastlog.cuh"
+extern "C" void hs_fast_log(const double* x, int n, double* out) {
+  for (int i = 0; i < n; i++) out[i] = tob::tob_log_pos(x[i], tob::kLogTabHost);
+}
+extern "C" void hs_ref_logl(const double* x, int n, double* out_hi, double* out_lo) {
+  // long-double logarithm split in two doubles (64-bit mantissa: 11 more bits than the value under test)
+  for (int i = 0; i < n; i++) {
+    long double l = logl((long double)x[i]);
+    out_hi[i] = (double)l;
+    out_lo[i] = (double)(l - (long double)out_hi[i]);
+  }
+}

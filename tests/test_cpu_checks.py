@@ -260,3 +260,39 @@ def test_hostsim_kdop_filter_equals_fp64_gate(hostsim, gs):
         if shift == 0.0 or abs(shift) < 10:
             total_exact += ne.value; total += 3000
     assert total_exact > 0                         # the threshold points reach the FP64 fallback
+
+
+def test_fast_log(hostsim):
+    """csrc/fastlog.cuh (the logarithm of the barrier kernels) against the host's long-double logarithm: at most 2 ulp over the
+    band 0 < x <= 1 the barrier uses (random, log-uniform down to 1e-12, next to 1, every bin edge), a few ulp above 1, the
+    library's answers for everything that is not a positive normal number; the bin that holds 1.0 is the exact one."""
+    import struct
+    rng = np.random.default_rng(0)
+
+    def ulps(x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n = len(x)
+        o, hi, lo = np.empty(n), np.empty(n), np.empty(n)
+        hostsim.hs_fast_log(D(x), n, D(o))
+        hostsim.hs_ref_logl(D(x), n, D(hi), D(lo))
+        with np.errstate(invalid="ignore"):
+            return np.abs((o - hi) - lo) / np.maximum(np.spacing(np.abs(hi)), 5e-324), o
+
+    edges = []
+    for e in (-40, -3, -1, 0):
+        for i in range(129):
+            h = 0x3FE6AAAB + (i << 13)
+            for d in (-1, 0, 1):
+                v = struct.unpack("<d", struct.pack("<Q", ((h + d) << 32) | (0xFFFFFFFF if d < 0 else 0)))[0]
+                edges.append(v * 2.0 ** e)
+    edges = np.array(edges)
+    for x in (rng.uniform(0, 1, 400_000), 10 ** rng.uniform(-12, 0, 400_000), 1 - 10 ** rng.uniform(-16, -2, 200_000),
+              edges[edges <= 1.0]):
+        u, _ = ulps(x)
+        assert u.max() <= 2.0, u.max()
+    for x in (10 ** rng.uniform(-300, 300, 200_000), 1 + 10 ** rng.uniform(-16, -1, 200_000), edges):
+        u, _ = ulps(x)
+        assert u.max() <= 6.0, u.max()
+    _, o = ulps(np.array([1.0, 0.0, -1.0, np.inf, np.nan, 5e-324, 2.0 ** -1022]))
+    assert o[0] == 0.0 and o[1] == -np.inf and np.isnan(o[2]) and o[3] == np.inf and np.isnan(o[4])
+    assert o[5] == np.log(5e-324) and abs(o[6] - np.log(2.0 ** -1022)) < 1e-12

@@ -19,12 +19,21 @@
 
 #include "ctx.cuh"
 #include "dense.cuh"
+#include "fastlog.cuh"
 
 namespace tob {
 
 #define ROW_TERMS 15
 #define TERM_SZ 12                 // M3: xx xy xz yy yz zz | g3 | pg3
 #define ROW_REC (ROW_TERMS * TERM_SZ + 2)
+
+// table of tob_log_pos (fastlog.cuh); the barrier kernels copy it to shared memory
+__device__ const LogTabEntry g_logtab[TOB_LOGTAB_N] = {
+#include "logtab.inc"
+};
+__device__ __forceinline__ void load_logtab(LogTabEntry* s_lt) {
+  for (int i = threadIdx.x; i < TOB_LOGTAB_N; i += blockDim.x) s_lt[i] = g_logtab[i];
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -94,7 +103,7 @@ __global__ void __launch_bounds__(256) k_en_items(const uint32_t* __restrict__ p
 // load) instead of living in 36 registers -- the variants that trade registers for resident warps
 template <bool CP_SHARED>
 __device__ __forceinline__ void en_virtual_warp(const EnergyArgs& a, int row, int v, int k, double* sP, double* sBz, double* q,
-                                                unsigned& n_act, unsigned& n_pl) {
+                                                const LogTabEntry* s_lt, unsigned& n_act, unsigned& n_pl) {
   const int lane = threadIdx.x & 31;
   const int robot = row / a.n_tr, tr = row - robot * a.n_tr;
   // every word that decides whether there is anything to do is loaded before the first test: one memory round trip
@@ -166,7 +175,7 @@ __device__ __forceinline__ void en_virtual_warp(const EnergyArgs& a, int row, in
         const unsigned t1 = t0 + 32u, t2 = t0 + 64u;
         const double d0 = t0 < cnt ? q[t0] : m, d1 = t1 < cnt ? q[t1] : m, d2 = t2 < cnt ? q[t2] : m;
         const double m0 = d0 - m, m1 = d1 - m, m2 = d2 - m;
-        const double l0 = log(d0 * inv_m), l1 = log(d1 * inv_m), l2 = log(d2 * inv_m);
+        const double l0 = tob_log_pos(d0 * inv_m, s_lt), l1 = tob_log_pos(d1 * inv_m, s_lt), l2 = tob_log_pos(d2 * inv_m, s_lt);
         e += ((m0 * m0) * l0 + (m1 * m1) * l1) + (m2 * m2) * l2;
       }
       n_act += cnt;                    // uniform value: counted once per warp by the caller
@@ -218,18 +227,21 @@ __global__ void __launch_bounds__(32 * MAXT, MINB) k_row_energy(EnergyArgs a) {
   const int lane = threadIdx.x & 31, kk = threadIdx.x >> 5, k = a.k0 + kk;
   __shared__ double sPall[MAXT][18], sBzall[MAXT][18];
   __shared__ double sQ[MAXT][192];          // in-band terms of one chunk (32 planes x 6 control points)
+  __shared__ LogTabEntry s_lt[TOB_LOGTAB_N];
   if (a.dc->overflow) return;      // the plane CSR of this iteration was not built: the host grows the buffers and retries
   if (a.pending && *a.pending == 0) return;
+  load_logtab(s_lt);
+  __syncthreads();
   unsigned n_act = 0, n_pl = 0;
   if ((int)blockIdx.x < a.n_rows) {
-    en_virtual_warp<CPS>(a, a.row_begin + (int)blockIdx.x, 0, k, sPall[kk], sBzall[kk], sQ[kk], n_act, n_pl);
+    en_virtual_warp<CPS>(a, a.row_begin + (int)blockIdx.x, 0, k, sPall[kk], sBzall[kk], sQ[kk], s_lt, n_act, n_pl);
   } else {
     const uint32_t n_items = a.dc->n_en_items, extra = gridDim.x - (uint32_t)a.n_rows;
     for (uint32_t idx = blockIdx.x - (uint32_t)a.n_rows; idx < n_items; idx += extra) {
       const uint32_t it = a.items[idx];
       const int row = (int)(it >> 3), v = (int)(it & 7u) + 1;
       if (row < a.row_begin || row >= a.row_begin + a.n_rows) continue;
-      en_virtual_warp<CPS>(a, row, v, k, sPall[kk], sBzall[kk], sQ[kk], n_act, n_pl);
+      en_virtual_warp<CPS>(a, row, v, k, sPall[kk], sBzall[kk], sQ[kk], s_lt, n_act, n_pl);
     }
   }
   n_pl = __reduce_add_sync(0xffffffffu, n_pl);
@@ -537,7 +549,7 @@ struct RowGradArgs {
 
 // part v of `row` by the whole CTA (128 threads): sums of the plane terms -> s_red[4][54] per warp, energy -> s_en[4]
 __device__ __forceinline__ void grad_part(const RowGradArgs& a, int row, int v, int V, const double* sP, double (*s_red)[54],
-                                          double* s_en) {
+                                          double* s_en, const LogTabEntry* s_lt) {
   const int tr = row % a.n_tr;
   const double w = a.weight[tr], m = a.margin, inv_m = 1.0 / m;
   double acc[54];
@@ -557,7 +569,7 @@ __device__ __forceinline__ void grad_part(const RowGradArgs& a, int row, int v, 
       const double d = sP[j] * pl.x + sP[j + 6] * pl.y + sP[j + 12] * pl.z + pl.w;
       const bool act = d < m;
       n_act += act;
-      const double lg = log(act ? d * inv_m : 1.0), dm = act ? d - m : 0.0, id = 1.0 / (act ? d : 1.0);
+      const double lg = tob_log_pos(act ? d * inv_m : 1.0, s_lt), dm = act ? d - m : 0.0, id = 1.0 / (act ? d : 1.0);
       const double e1 = -w * (2 * dm * lg + dm * dm * id);
       const double e2 = -w * (2 * lg + 4 * dm * id - dm * dm * id * id);
       en += (dm * dm) * lg;
@@ -588,7 +600,9 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
   __shared__ double sP[18];
   __shared__ double s_red[4][54];
   __shared__ double s_gt[9], s_ht[9], s_eb[9], s_en[4];
+  __shared__ LogTabEntry s_lt[TOB_LOGTAB_N];
   if (a.dc->overflow) return;      // the plane CSR of this iteration was not built (see k_row_energy)
+  load_logtab(s_lt);               // visible after the first barrier below (both paths have one before grad_part)
   if ((int)blockIdx.x >= a.n_rows) {
     const uint32_t n_items = a.dc->n_en_items, extra = gridDim.x - (uint32_t)a.n_rows;
     for (uint32_t idx = blockIdx.x - (uint32_t)a.n_rows; idx < n_items; idx += extra) {
@@ -599,7 +613,7 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
       if (threadIdx.x < 18) sP[threadIdx.x] = a.P[(size_t)18 * row + threadIdx.x];
       __syncthreads();
       const int V = en_vwarps(a.pl_off[row + 1] - a.pl_off[row]);
-      grad_part(a, row, v, V, sP, s_red, s_en);
+      grad_part(a, row, v, V, sP, s_red, s_en, s_lt);
       __syncthreads();
       if (threadIdx.x < 54) {
         const int i = threadIdx.x;
@@ -616,7 +630,7 @@ __global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
   __syncthreads();
   const double w = a.weight[tr], m = a.margin;
   const int V = en_vwarps(a.pl_off[row + 1] - a.pl_off[row]);
-  grad_part(a, row, 0, V, sP, s_red, s_en);
+  grad_part(a, row, 0, V, sP, s_red, s_en, s_lt);
   // bound terms, threads 0..8
   double* out = a.terms + (size_t)ROW_REC * row;
   if (threadIdx.x < 9) {
