@@ -559,8 +559,11 @@ __device__ __forceinline__ void grad_part(const RowGradArgs& a, int row, int v, 
   for (int i = 0; i < 54; i++) acc[i] = 0;
   const uint32_t k0 = a.pl_off[row], k1 = a.pl_off[row + 1];
   const uint32_t first = k0 + (uint32_t)v * 128u, stride = 128u * (uint32_t)V;
+  double4 nxt = make_double4(0, 0, 0, 0);
+  if (first + threadIdx.x < k1) nxt = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * (first + threadIdx.x));
   for (uint32_t k = first + threadIdx.x; k < k1; k += stride) {
-    const double4 pl = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * k);
+    const double4 pl = nxt;       // the next plane of this thread is in flight while this one is evaluated
+    if (k + stride < k1) nxt = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * (k + stride));
     const double cxx = pl.x * pl.x, cxy = pl.x * pl.y, cxz = pl.x * pl.z, cyy = pl.y * pl.y, cyz = pl.y * pl.z, czz = pl.z * pl.z;
     // branch-free like k_row_energy: a term outside the band contributes e1 = e2 = 0 through log(1) and dm = 0, so the six
     // log / reciprocal chains of a plane are independent and interleave

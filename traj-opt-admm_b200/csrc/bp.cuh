@@ -214,13 +214,16 @@ __device__ __forceinline__ uint32_t bp_prepare(const BpArgs& a, BpShared& s, uin
   return n_items;
 }
 
-// item j -> hit task h and the leaf it addresses.  *h_out is a cursor: a warp visits its items in increasing order, so the
+// item j -> hit task h and the leaf it addresses (called by all 32 lanes of a warp with the same j).  *h_out is a cursor: a warp visits its items in increasing order, so the
 // search walks forward from the task of the previous item (start with 0); uniform in the warp
 __device__ __forceinline__ void bp_item(const BpArgs& a, const BpShared& s, uint32_t j, uint32_t* h_out, uint32_t* row, uint32_t* leaf) {
   uint32_t lo = *h_out;                     // largest h with item_base[h] <= j
   while (lo + 1 < s.n_hit && s.item_base[lo + 1] <= j) lo++;
   const uint32_t k = j - s.item_base[lo];
-  const uint32_t lb = __fns(s.lmask[lo], 0, k + 1);
+  // position of the k-th set bit of the (warp-uniform) leaf mask: lane l owns bit l, the lane whose bit is set with k set bits
+  // below it answers (__fns is emulated in software: it was 20 % of the stall samples of k_bp_count, profiles/r02z_hot_*)
+  const uint32_t m = s.lmask[lo], lane = threadIdx.x & 31;
+  const uint32_t lb = (uint32_t)__ffs(__ballot_sync(0xffffffffu, ((m >> lane) & 1u) && (uint32_t)__popc(m & ((1u << lane) - 1u)) == k)) - 1u;
   *h_out = lo;
   *row = s.hit_row[lo];
   *leaf = s.hit_nd[lo] * 32 + lb;
