@@ -448,7 +448,7 @@ def run_ours(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "MEASURED_PEAKS.json (burst copy)" if "hbm_gbs" in peaks else "fallback of B200_PROFILING.md"
-    per_step = {k: pctr[k] / float(psteps) for k in pctr}
+    per_step = {k: pctr[k] / float(psteps) for k in pctr if not isinstance(pctr[k], list)}
     geo = {"rows": (count if sharded else U) * P * 8, "P": P, "T": T, "U": count if sharded else U}
     models = kernel_models(per_step, geo)
     tot_prof_ms = sum(v[0] for v in prof.values())
@@ -510,6 +510,7 @@ def run_ours(args):
         "pairs_per_step": {k: ctr[k] / args.steps for k in ("dcd_candidates", "planes", "ccd_candidates", "energy_plane_evals", "barrier_terms",
                                                              "np_kdop_groups", "np_gjk_iters", "np_kdop_exact", "np_band", "ccd_kdop_pass", "ccd_gjk_iters", "line_search_trials")},
         "e2e": {"value": mult * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": state_bytes * world, "d2h_bytes_per_step": state_bytes * world},
+        "ls_rung_hist_per_step": [x / args.steps for x in ctr.get("ls_rung_hist", [])],
         "gpu_launches": int(pe[1]),
         "clocks": sampler.summary(),
         "roofline": roof,

@@ -69,7 +69,7 @@ def _batch(n=130):
 
 def _run_batch(scs, sts, iters, env):
     keys = ("TRAJOPT_B200_LS", "TRAJOPT_B200_EN_OCC", "TRAJOPT_B200_NP_FILTER", "TRAJOPT_B200_CCD_OCC", "TRAJOPT_B200_NP_OCC",
-            "TRAJOPT_B200_PACK_GRID", "TRAJOPT_B200_NP_BAND", "TRAJOPT_B200_NP_GATE1")
+            "TRAJOPT_B200_PACK_GRID", "TRAJOPT_B200_NP_BAND", "TRAJOPT_B200_NP_GATE1", "TRAJOPT_B200_NP_PMEM")
     for k in keys:
         os.environ.pop(k, None)
     os.environ.update(env)
@@ -98,7 +98,7 @@ def test_many_rows_result_independent_of_kernel_variants_and_schedule():
                 {"TRAJOPT_B200_LS": "2,2,16", "TRAJOPT_B200_PACK_GRID": "4"}, {"TRAJOPT_B200_LS": "2,3,9"},
                 {"TRAJOPT_B200_LS": "9,9,2", "TRAJOPT_B200_NP_OCC": "6"},
                 {"TRAJOPT_B200_NP_BAND": "0"}, {"TRAJOPT_B200_NP_BAND": "0", "TRAJOPT_B200_NP_FILTER": "0", "TRAJOPT_B200_NP_GATE1": "49"},
-                {"TRAJOPT_B200_NP_GATE1": "7"}):
+                {"TRAJOPT_B200_NP_GATE1": "7"}, {"TRAJOPT_B200_NP_PMEM": "5"}, {"TRAJOPT_B200_NP_PMEM": "4"}):
         got, cgot = _run_batch(scs, sts, 5, env)
         assert same(ref, got), env
         assert cgot["planes"] == cref["planes"] and cgot["dcd_candidates"] == cref["dcd_candidates"], env
@@ -145,9 +145,9 @@ def test_gate_implied_by_gjk_distance_same_planes_as_full_gate():
     st = scenes.initial_states(sc)[0]
     P = len(sc["way_points"][0]) - 1
     out = []
-    keys = ("TRAJOPT_B200_NP_BAND", "TRAJOPT_B200_NP_GATE1", "TRAJOPT_B200_NP_FILTER")
+    keys = ("TRAJOPT_B200_NP_BAND", "TRAJOPT_B200_NP_GATE1", "TRAJOPT_B200_NP_FILTER", "TRAJOPT_B200_NP_PMEM")
     for env in ({}, {"TRAJOPT_B200_NP_GATE1": "49", "TRAJOPT_B200_NP_FILTER": "0"}, {"TRAJOPT_B200_NP_BAND": "0"},
-                {"TRAJOPT_B200_NP_GATE1": "7"}, {"TRAJOPT_B200_NP_GATE1": "28"}):
+                {"TRAJOPT_B200_NP_GATE1": "7"}, {"TRAJOPT_B200_NP_GATE1": "28"}, {"TRAJOPT_B200_NP_PMEM": "6"}):
         os.environ.update(env)
         try:
             s = api.Solver(P, ks=sc["ks"])
@@ -164,3 +164,27 @@ def test_gate_implied_by_gjk_distance_same_planes_as_full_gate():
     assert k0["np_band"] <= 1e-4 * k0["planes"] + 2
     assert out[1][3]["np_band"] <= 1e-4 * k0["planes"] + 2 and out[2][3]["np_band"] >= k0["planes"]
     assert k0["np_kdop_groups"] < out[1][3]["np_kdop_groups"]       # the point of it: fewer axes evaluated
+
+
+def test_broadphase_item_records_same_candidates():
+    """The fill pass scatters from the item records of the count pass (default), repeats the tests (TRAJOPT_B200_BP_REC=0), or
+    does either per CTA when the records run out of room (a capacity of 300 records): identical candidate lists and planes."""
+    sc = scenes.forest(n_pts=200_000, seed=2)
+    st = scenes.initial_states(sc)[0]
+    P = len(sc["way_points"][0]) - 1
+    out = []
+    for rec in (None, "0", "300"):
+        if rec is not None:
+            os.environ["TRAJOPT_B200_BP_REC"] = rec
+        try:
+            s = api.Solver(P, ks=sc["ks"])
+            s.init_pointcloud(sc["V"])
+            out.append(s.dcd_collision(st["spline"], 0.2) + s.ccd_collision(st["spline"], 0.05 * np.ones_like(st["spline"]), 0.1)
+                       + s.separate_plane(st["spline"]))
+        finally:
+            os.environ.pop("TRAJOPT_B200_BP_REC", None)
+    assert len(out[0][1]) > 10_000
+    for o in out[1:]:
+        assert len(o) == len(out[0])
+        for x, y in zip(out[0], o):
+            assert np.array_equal(x, y)

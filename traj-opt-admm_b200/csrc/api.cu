@@ -288,7 +288,7 @@ static int separate_resident(tob_ctx* c, int rb, int re, int with_self) {
 // round r >= 1 evaluates trials 1..8 (round 0 also trial 0 = the current point, the "e" of the reference)
 static int ls_round(tob_ctx* c, int rb, int re, int wolfe_idx, bool coupled, int round, int slot) {
   cudaStream_t st = c->stream;
-  if (!coupled) return line_search_round(c, rb, re, wolfe_idx, round == 0 ? 0 : 1, round == 0 ? c->ls_kte0 : c->ls_kte, slot,
+  if (!coupled) return line_search_round(c, rb, re, wolfe_idx, round == 0 ? 0 : 1, round == 0 ? c->ls_kte0 : (round == 1 ? c->ls_kte1 : c->ls_kte), slot,
                                          round == 0 && !c->ls_e0_ready ? 0 : 1);
   TOB_TRY(energy_trials(c, rb, re, c->s_dir.p, c->s_tstep.p, c->s_ttime.p, TOB_LS_TRIALS, round == 0 ? 0 : 1, TOB_LS_TRIALS, c->s_etr.p));
   TOB_TRY(exchange_robots(c, c->s_etr.p, TOB_LS_TRIALS, sizeof(double)));   // joint Armijo: every rank sums all robots in robot order
@@ -371,11 +371,13 @@ static void ls_policy(tob_ctx* c, int rb, int re, bool coupled) {
   c->ls_kte0 = many ? 2 : TOB_LS_TRIALS;
   c->ls_kte = many ? 5 : TOB_LS_TRIALS;
   c->ls_rounds = many ? 5 : 2;
-  if (const char* e = getenv("TRAJOPT_B200_LS")) {          // "kte0,kte,rounds": tuning / experiments
-    int k0 = 0, k = 0, r = 0;
-    if (!coupled && sscanf(e, "%d,%d,%d", &k0, &k, &r) == 3 && k0 >= 2 && k0 <= TOB_LS_TRIALS && k >= 2 && k <= TOB_LS_TRIALS &&
-        r >= 1 && r <= TOB_LS_MAXROUNDS) {
-      c->ls_kte0 = k0; c->ls_kte = k; c->ls_rounds = r;
+  c->ls_kte1 = c->ls_kte;
+  if (const char* e = getenv("TRAJOPT_B200_LS")) {          // "kte0,kte,rounds[,kte1]": tuning / experiments
+    int k0 = 0, k = 0, r = 0, k1 = 0;
+    const int got = coupled ? 0 : sscanf(e, "%d,%d,%d,%d", &k0, &k, &r, &k1);
+    if (got >= 3 && k0 >= 2 && k0 <= TOB_LS_TRIALS && k >= 2 && k <= TOB_LS_TRIALS && r >= 1 && r <= TOB_LS_MAXROUNDS) {
+      c->ls_kte0 = k0; c->ls_kte = k; c->ls_rounds = r; c->ls_kte1 = k;
+      if (got == 4 && k1 >= 2 && k1 <= TOB_LS_TRIALS) c->ls_kte1 = k1;
     }
   }
 }
@@ -510,7 +512,7 @@ static int iterate_submit(tob_ctx* c, int mode) {
   }
   TOB_CUDA(c, cudaGraphLaunch(c->graph_exec, c->stream));
   c->ctr.kernel_launches += c->graph_nodes;
-  c->ctr.line_search_trials += (uint64_t)(c->own_end - c->own_begin) * ((c->ls_kte0 - 1) + (c->ls_kte - 1) * (c->ls_rounds - 1));
+  c->ctr.line_search_trials += (uint64_t)(c->own_end - c->own_begin) * ((c->ls_kte0 - 1) + (c->ls_rounds > 1 ? c->ls_kte1 - 1 : 0) + (c->ls_kte - 1) * (c->ls_rounds > 2 ? c->ls_rounds - 2 : 0));
   if (c->n_robots() > 1 && mode != 2) c->ctr.self_pairs += (uint64_t)2 * c->n_tr * (c->n_robots() * (c->n_robots() - 1) / 2);
   return 0;
 }
@@ -1469,6 +1471,7 @@ int tob_get_counters(const tob_ctx* cc, tob_counters* out) {
   out->ccd_kdop_pass = c->h_dc->ccd_kdop_pass;
   out->np_kdop_exact = c->h_dc->np_kdop_exact;
   out->np_band = c->h_dc->np_band;
+  for (int i = 0; i < 8; i++) out->ls_rung_hist[i] = c->h_dc->ls_hist[i];
   return 0;
 }
 int tob_reset_counters(tob_ctx* c) {
@@ -1476,7 +1479,7 @@ int tob_reset_counters(tob_ctx* c) {
   cudaSetDevice(c->device);
   memset(&c->ctr, 0, sizeof(c->ctr));
   TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->dcd_candidates, 0, 5 * sizeof(unsigned long long), c->stream));
-  TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->np_kdop_groups, 0, 6 * sizeof(unsigned long long), c->stream));
+  TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->np_kdop_groups, 0, 14 * sizeof(unsigned long long), c->stream));
   return 0;
 }
 

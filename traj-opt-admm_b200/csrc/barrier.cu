@@ -390,6 +390,9 @@ __global__ void __launch_bounds__(32 * TOB_LS_TRIALS) k_robot_ls(RobotLsArgs b) 
   for (int k = 1; k < kte; k++) {
     const double s = b.tstep[u * KT + k];
     if (!(e0 - 1e-4 * w * s < a.e_out[u * KT + k])) {
+      // accepted rung of the ladder that started at step[u] (work counter: the line-search policy is tuned on this histogram)
+      const int rung = (int)lrint(log(s / b.step[u]) / log(0.8));
+      atomicAdd(&b.dc->ls_hist[rung < 0 ? 0 : (rung > 7 ? 7 : rung)], 1ull);
       b.step[u] = s;
       b.ptrial[u] = b.ttime[u * KT + k];
       b.done[u] = 1;

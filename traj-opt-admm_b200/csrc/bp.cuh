@@ -37,6 +37,9 @@ struct BpArgs {
   // tasks are [row_task[r], row_task[r+1]); null = one shared cloud, n1 nodes for every row
   const uint32_t *row_task, *row_l1;
   const uint32_t* cta_row;     // per-robot clouds, whole-context query: row of the first task of every CTA (host-built), or null
+  // item records count -> fill (rec_cap = 0: none, the fill pass repeats the tests)
+  uint32_t *rec_row, *rec_leaf, *rec_pm, *cta_ibase, *cta_nitems, *row_li;
+  uint32_t rec_cap;
 };
 
 struct BpShared {
@@ -169,15 +172,20 @@ __device__ __forceinline__ uint32_t bp_first_row(const BpArgs& a) {
 }
 
 // phases A + B + item prefix.  Returns the number of items of this CTA; *my_rank = hit tasks before this thread's task.
-__device__ __forceinline__ uint32_t bp_prepare(const BpArgs& a, BpShared& s, uint32_t* my_rank) {
+// *my_row / *my_first (optional): the row of this thread's task and whether it is the first task of its row.
+__device__ __forceinline__ uint32_t bp_prepare(const BpArgs& a, BpShared& s, uint32_t* my_rank, uint32_t* my_row = nullptr,
+                                              bool* my_first = nullptr) {
   const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const uint32_t t = blockIdx.x * a.tpc + tid;
   bool hit = false;
   uint32_t row = 0, nd = 0;
   double q[6] = {0, 0, 0, 0, 0, 0};
+  if (my_first) *my_first = false;
   if (tid < a.tpc && t < a.n_tasks) {
     bool first;
     bp_task(a, t, &row, &nd, &first, bp_first_row(a));
+    if (my_row) *my_row = row;
+    if (my_first) *my_first = first;
     const double* qb = a.box + (size_t)6 * row;
     double nlo[3], nhi[3];
 #pragma unroll

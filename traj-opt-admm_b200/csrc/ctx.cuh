@@ -75,7 +75,7 @@ struct DevCounts {
   uint32_t n_cand;           // candidates of the last broadphase fill (may exceed the capacity -> overflow)
   uint32_t n_planes;         // planes of the last pack
   uint32_t n_planes_ob;      // ... of which obstacle planes
-  uint32_t pad1;
+  uint32_t bp_items;         // item records handed out by the broadphase count pass (reset by the fill pass)
   uint32_t n_en_items;       // listed virtual warps (v >= 1) of the rows with more than 256 planes (barrier.cu: k_en_items)
   uint32_t overflow;         // TOB_OVF_* bits, sticky until the host clears them
   int32_t ls_pending[TOB_LS_MAXROUNDS + 1];   // robots still backtracking after Armijo round r (last entry: host scratch)
@@ -95,6 +95,7 @@ struct DevCounts {
   unsigned long long ccd_kdop_pass;    // swept candidates that passed the swept 49-DOP gate (each runs >= 1 ladder rung)
   unsigned long long np_kdop_exact;    // axes of the 49-DOP gate the single-precision filter could not decide (re-tested in FP64)
   unsigned long long np_band;          // pairs whose GJK distance fell inside the band where the rest of the gate had to be evaluated
+  unsigned long long ls_hist[8];       // decoupled line searches by the ladder rung that was accepted: 1, 2, .. 7, 8 and deeper
 };
 
 // per-row (robot x sub-segment) geometry produced by segments.cu, indexed by GLOBAL row = robot*n_tr + tr
@@ -180,6 +181,10 @@ struct tob_ctx {
   tob::DBuf<uint32_t> task_cnt, task_off, scan_tmp;
   tob::DBuf<uint32_t> bsum;           // per-CTA totals of the broadphase count pass, scanned in place
   tob::DBuf<uint32_t> cand_pt, cand_row;
+  // what the count pass found per item (hit task x hit leaf), so that the fill pass scatters without testing again:
+  // row, leaf and point mask of item i of a CTA at rec_*[cta_ibase[cta] + i]; row_li = local item index where a row starts
+  tob::DBuf<uint32_t> rec_row, rec_leaf, rec_pm, cta_ibase, cta_nitems, row_li;
+  uint64_t rec_cap = 0;
   tob::DBuf<uint32_t> row_off;        // (all rows)+1 candidate offsets; rows outside the queried range are empty
   uint64_t cand_cap = 0;              // capacity (candidates) of cand_pt / cand_row / cpl / cflag; planes: cand_cap + self
   uint64_t n_cand = 0;                // host mirror, valid after sync_counts()
@@ -249,6 +254,7 @@ struct tob_ctx {
   // most robots accept one of the first two rungs, so the first round only evaluates those for everybody (throughput),
   // and the few robots that keep backtracking get 8 rungs per later round
   int ls_kte0 = TOB_LS_TRIALS, ls_kte = TOB_LS_TRIALS, ls_rounds = 2;
+  int ls_kte1 = TOB_LS_TRIALS;        // trial slots of round 1 (round 0: ls_kte0, rounds 2..: ls_kte)
   bool ls_e0_ready = false;           // trial slot 0 (the current point) already holds its energy: written by the gradient pass
 
   // optional per-kernel CUDA-event timing (bench.py roofline): off by default

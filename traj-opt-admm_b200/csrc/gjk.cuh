@@ -457,6 +457,73 @@ TOB_HD void gjk_witness(const double (*A)[3], const double (*B)[3], double* vout
   if (iters) *iters += (unsigned)k;   // work counter (bench.py roofline): support + sub-algorithm rounds really executed
 }
 
+#if defined(__CUDACC__)
+// gjk_witness<6, 1> with the six hull vertices read from memory in every round instead of living in 36 registers for the
+// whole loop (gP: 6x3 column-major, the row's control points, L1-resident; q: the point).  Same operands, same operations,
+// same order -- the loads are pinned (asm volatile) so that the compiler does not hoist them back out of the loop.  What it
+// buys is register room: the narrowphase kernel is bound by the latency of its dependent FP64 chains at 4 warps per scheduler.
+__device__ __forceinline__ double ld_pinned(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void gjk_witness_6pt_mem(const double* __restrict__ gP, const double* q, double* vout, unsigned* iters) {
+  Simplex s;
+  s.lam[0] = s.lam[1] = s.lam[2] = s.lam[3] = 0;
+  s.wid[0] = s.wid[1] = s.wid[2] = s.wid[3] = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i) { s.v[i][0] = 0; s.v[i][1] = 0; s.v[i][2] = 0; }
+  double v[3], vm[3], w[3], sa[3];
+  const double eps_rel2 = 1e-5 * 1e-5;
+  const double eps_tot = 1e-15;
+  double wmax = 0;
+  s.n = 1;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    sa[i] = ld_pinned(gP + 6 * i);
+    v[i] = sa[i] - q[i];
+    s.v[0][i] = v[i];
+  }
+  int k = 0;
+  do {
+    k++;
+    vm[0] = -v[0]; vm[1] = -v[1]; vm[2] = -v[2];
+    {   // support_max<6>(A, sa, vm)
+      double best = dot3(sa, vm);
+      double bx = sa[0], by = sa[1], bz = sa[2];
+      double px[6], py[6], pz[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { px[i] = ld_pinned(gP + i); py[i] = ld_pinned(gP + 6 + i); pz[i] = ld_pinned(gP + 12 + i); }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const double pt[3] = {px[i], py[i], pz[i]};
+        double sv = dot3(pt, vm);
+        if (sv > best) { best = sv; bx = px[i]; by = py[i]; bz = pz[i]; }
+      }
+      sa[0] = bx; sa[1] = by; sa[2] = bz;
+    }
+    w[0] = sa[0] - q[0]; w[1] = sa[1] - q[1]; w[2] = sa[2] - q[2];
+    double vv = nrm2(v);
+    if ((vv - dot3(v, w)) <= eps_rel2 * vv) break;
+    if (vv < eps_rel2) break;
+    put_vertex(s, s.n, w);
+    s.n++;
+    if (s.n == 4) sv_tet(s, v);
+    else if (s.n == 3) sv_tri(s, v);
+    else if (s.n == 2) sv_line(s, v);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (i < s.n) {
+        double tn = nrm2(s.v[i]);
+        if (tn > wmax) wmax = tn;
+      }
+    if (nrm2(v) <= (eps_tot * eps_tot * wmax)) break;
+  } while ((s.n != 4) && (k != 50));
+  vout[0] = v[0]; vout[1] = v[1]; vout[2] = v[2];
+  if (iters) *iters += (unsigned)k;
+}
+#endif
+
 // runtime-sized variants (function-level entry points CCD::GJKDCD with edges / arbitrary vertex counts, CCD.h:17-114)
 TOB_HD void support_max_n(const double (*pts)[3], int n, double* cur, const double* dir) {
   double best = dot3(cur, dir);

@@ -308,9 +308,26 @@ int lbvh_build_batch(tob_ctx* c, const double* const* V_host, const uint32_t* n,
 // count pass: candidates per CTA (bp.cuh explains the walk)
 __global__ void __launch_bounds__(BP_THREADS) k_bp_count(BpArgs a) {
   __shared__ BpShared s;
-  uint32_t rank;
-  const uint32_t n_items = bp_prepare(a, s, &rank);
+  __shared__ uint32_t s_ibase;
+  uint32_t rank, my_row;
+  bool my_first;
+  const uint32_t n_items = bp_prepare(a, s, &rank, &my_row, &my_first);
   const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // room for this CTA's item records (row, leaf, point mask): the fill pass then scatters without walking the tree again.
+  // The order in which CTAs get their room is arbitrary and irrelevant (candidate positions come from the scanned totals).
+  if (threadIdx.x == 0) {
+    uint32_t ib = 0xffffffffu;
+    if (a.rec_cap && n_items) {
+      ib = atomicAdd(&a.dc->bp_items, n_items);
+      if (ib > a.rec_cap || n_items > a.rec_cap - ib) ib = 0xffffffffu;     // no room: the fill pass repeats the tests for this CTA
+    } else if (a.rec_cap) ib = 0;
+    s_ibase = ib;
+    a.cta_ibase[blockIdx.x] = ib;
+    a.cta_nitems[blockIdx.x] = n_items;
+  }
+  if (my_first && a.rec_cap) a.row_li[my_row] = s.item_base[rank];          // items of this CTA in front of the row's first task
+  __syncthreads();
+  const uint32_t ibase = s_ibase;
   uint32_t cnt = 0;
   uint32_t h = 0;                                          // bp_item cursor
   // two items of the warp in flight: the point loads of the second are issued before the first is tested (the kernel waits
@@ -324,7 +341,12 @@ __global__ void __launch_bounds__(BP_THREADS) k_bp_count(BpArgs a) {
     const uint32_t p0 = leaf0 * 32 + lane, p1 = (two ? leaf1 : leaf0) * 32 + lane;
     const double pa[3] = {a.px[p0], a.py[p0], a.pz[p0]}, pb[3] = {a.px[p1], a.py[p1], a.pz[p1]};
     const bool ok0 = box_hit3(pa, pa, s.hit_q[h0], a.d), ok1 = two && box_hit3(pb, pb, s.hit_q[h], a.d);
-    cnt += __popc(__ballot_sync(0xffffffffu, ok0)) + __popc(__ballot_sync(0xffffffffu, ok1));
+    const uint32_t pm0 = __ballot_sync(0xffffffffu, ok0), pm1 = __ballot_sync(0xffffffffu, ok1);
+    cnt += __popc(pm0) + __popc(pm1);
+    if (ibase != 0xffffffffu && lane == 0) {
+      a.rec_row[ibase + j] = row0; a.rec_leaf[ibase + j] = leaf0; a.rec_pm[ibase + j] = pm0;
+      if (two) { a.rec_row[ibase + j + BP_WARPS] = row1; a.rec_leaf[ibase + j + BP_WARPS] = leaf1; a.rec_pm[ibase + j + BP_WARPS] = pm1; }
+    }
   }
   __syncthreads();
   if (lane == 0) s.wtmp[w] = cnt;
@@ -359,7 +381,59 @@ __global__ void __launch_bounds__(BP_THREADS) k_bp_fill(BpArgs a) {
   if (blockIdx.x == 0)
     for (uint32_t g = tid; g <= a.rows_all; g += BP_THREADS)
       if (g < a.row_base || g >= a.row_base + a.rows) a.row_off[g] = g < a.row_base ? 0u : total;
+  if (blockIdx.x == 0 && tid == 0) a.dc->bp_items = 0;     // the records of this query are handed out: room for the next count pass
   if (total > a.cand_cap) return;   // overflow: the host grows the buffers and runs the query again
+  const uint32_t ibase = a.rec_cap ? a.cta_ibase[blockIdx.x] : 0xffffffffu;
+  if (ibase != 0xffffffffu) {
+    // the count pass left (row, leaf, point mask) of every item of this CTA: prefix over the masks and scatter
+    const uint32_t n_it = a.cta_nitems[blockIdx.x], cta_base = a.bsum[blockIdx.x];
+    const uint32_t t = blockIdx.x * a.tpc + tid;
+    uint32_t row = 0, nd, li = 0xffffffffu, off = 0;
+    bool first = false;
+    if (tid < a.tpc && t < a.n_tasks) {
+      bp_task(a, t, &row, &nd, &first, bp_first_row(a));
+      if (first) li = a.row_li[row];
+    }
+    uint32_t run = 0;
+    for (uint32_t b0 = 0; b0 < n_it; b0 += BP_BATCH) {
+      const uint32_t nb = min((uint32_t)BP_BATCH, n_it - b0);
+      constexpr int PER = BP_BATCH / BP_THREADS;
+      uint32_t loc[PER], sum = 0;
+#pragma unroll
+      for (int i = 0; i < PER; i++) {                          // PER consecutive items per thread
+        const uint32_t jj = tid * PER + i;
+        uint32_t pm = 0;
+        if (jj < nb) {
+          pm = a.rec_pm[ibase + b0 + jj];
+          s_pm[jj] = pm; s_leaf[jj] = a.rec_leaf[ibase + b0 + jj]; s_row[jj] = a.rec_row[ibase + b0 + jj];
+        }
+        loc[i] = (uint32_t)__popc(pm);
+        sum += loc[i];
+      }
+      uint32_t btot;
+      uint32_t e = bp_block_excl(sum, s.wtmp, &btot);          // two barriers: s_pm / s_leaf / s_row are visible afterwards
+#pragma unroll
+      for (int i = 0; i < PER; i++) {
+        const uint32_t jj = tid * PER + i;
+        if (jj < nb) s_pre[jj] = e;
+        e += loc[i];
+      }
+      __syncthreads();
+      if (first && li >= b0 && li < b0 + nb) off = run + s_pre[li - b0];
+      for (uint32_t jj = w; jj < nb; jj += BP_WARPS) {
+        const uint32_t pm = s_pm[jj];
+        if (pm & (1u << lane)) {
+          const uint32_t pos = cta_base + run + s_pre[jj] + __popc(pm & ((1u << lane) - 1u));
+          a.cand_pt[pos] = s_leaf[jj] * 32 + lane;
+          a.cand_row[pos] = s_row[jj];
+        }
+      }
+      run += btot;
+      __syncthreads();
+    }
+    if (first) a.row_off[row] = cta_base + (li >= n_it ? run : off);
+    return;
+  }
   uint32_t rank;
   const uint32_t n_items = bp_prepare(a, s, &rank);
   const uint32_t n_hit = s.n_hit;
@@ -463,6 +537,8 @@ void bp_args(tob_ctx* c, int row_base, int rows, double d, BpArgs& a) {
   a.cand_pt = c->cand_pt.p; a.cand_row = c->cand_row.p; a.row_off = c->row_off.p;
   a.cand_cap = (uint32_t)c->cand_cap;
   a.dc = c->dc.p;
+  a.rec_row = c->rec_row.p; a.rec_leaf = c->rec_leaf.p; a.rec_pm = c->rec_pm.p; a.cta_ibase = c->cta_ibase.p; a.cta_nitems = c->cta_nitems.p;
+  a.row_li = c->row_li.p; a.rec_cap = (uint32_t)c->rec_cap;
   // enough CTAs to cover the machine a few times over, at most BP_THREADS tasks each
   a.tpc = bp_tpc(c, a.n_tasks);
   a.cta_row = (!c->cloud_n1.empty() && row_base == 0 && rows == c->rows_all() && a.tpc == c->cta_row_tpc && c->cta_row.p) ? c->cta_row.p : nullptr;
@@ -506,6 +582,15 @@ int ensure_query_buffers(tob_ctx* c) {
   const size_t nblk = tasks / 16 + 4 * (size_t)c->sm_count + 2;   // tasks per CTA >= 16
   const size_t self_max = c->cloud_n1.empty() ? rows * (U > 1 ? U - 1 : 0) : 0;   // independent problems have no inter-robot planes
   TOB_CUDA(c, c->bsum.ensure(nblk + 1));
+  {
+    // item records of the count pass: an item (hit leaf of a hit level-1 node) yields 32 x (hit fraction) candidates, so a
+    // quarter of the candidate capacity is ample; a CTA that finds no room makes the fill pass repeat its tests
+    const char* e = getenv("TRAJOPT_B200_BP_REC");      // 0: no records; > 1: that many (tests: most CTAs find no room)
+    const long rec_on = e ? atol(e) : 1;
+    c->rec_cap = rec_on ? (rec_on > 1 ? (uint64_t)rec_on : c->cand_cap / 4 + 4096) : 0;
+    TOB_CUDA(c, c->rec_row.ensure(c->rec_cap + 1)); TOB_CUDA(c, c->rec_leaf.ensure(c->rec_cap + 1)); TOB_CUDA(c, c->rec_pm.ensure(c->rec_cap + 1));
+    TOB_CUDA(c, c->cta_ibase.ensure(nblk + 1)); TOB_CUDA(c, c->cta_nitems.ensure(nblk + 1)); TOB_CUDA(c, c->row_li.ensure(rows + 2));
+  }
   TOB_CUDA(c, c->row_off.ensure(rows + 2));
   TOB_CUDA(c, c->cand_pt.ensure(c->cand_cap + 1));
   TOB_CUDA(c, c->cand_row.ensure(c->cand_cap + 1));

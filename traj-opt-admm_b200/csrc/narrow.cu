@@ -122,7 +122,8 @@ __device__ __forceinline__ bool np_gate(const NarrowArgs& a, uint32_t row, const
 }
 
 // MINB = resident CTAs per SM the register allocation is made for (4: 128 registers, 5: 102, 6: 85, 8: 64)
-template <int MINB, bool FILT>
+// PMEM: the hull vertices are read from memory in every GJK round (gjk.cuh: gjk_witness_6pt_mem) instead of held in registers
+template <int MINB, bool FILT, bool PMEM = false>
 __global__ void __launch_bounds__(NP_THREADS, MINB) k_narrow(NarrowArgs a) {
   __shared__ double s_kdop[3 * TOB_KDOP_AXES];
   __shared__ float s_kdop_f[FILT ? 3 * TOB_KDOP_AXES : 1];
@@ -182,9 +183,15 @@ __global__ void __launch_bounds__(NP_THREADS, MINB) k_narrow(NarrowArgs a) {
         if (at < n_live && a.live_key[at] == key) continue;
       }
       const double pt[3] = {a.px[p], a.py[p], a.pz[p]};
-      double P[6][3], c[3], d;
-      load_pts6(a.P + (size_t)18 * row, P);
-      const double cn = plane_point_witness(P, pt, c, &w_iters);
+      double c[3], d, cn;
+      if (PMEM) {
+        gjk_witness_6pt_mem(a.P + (size_t)18 * row, pt, c, &w_iters);
+        cn = eig_norm3(c);
+      } else {
+        double P[6][3];
+        load_pts6(a.P + (size_t)18 * row, P);
+        cn = plane_point_witness(P, pt, c, &w_iters);
+      }
       bool acc = !(cn > a.dist);
       if (acc && !(cn <= a.gate_skip)) {      // inside the band (or NaN): the gate's own arithmetic decides
         w_band++;
@@ -697,7 +704,14 @@ int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self) {
     a.gate1 = eg ? atoi(eg) : NP_GATE1;
     if (a.gate1 < 7 || a.gate1 > TOB_KDOP_AXES || a.gate1 % 7) a.gate1 = NP_GATE1;
     a.np_grid = (uint32_t)c->sm_count * 4;
-    if (!filt) k_narrow<4, false><<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
+    const char* em = getenv("TRAJOPT_B200_NP_PMEM");
+    // default: hull vertices from L1, registers for 5 CTAs per SM (measured on a 128-problem shard: 1.025 ms with the vertices
+    // in registers at 4 CTAs per SM, 1.001 / 0.959 / 0.990 ms with PMEM at 4 / 5 / 6); 0 = the register variants below
+    const int pmem = em ? atoi(em) : 5;
+    if (pmem == 4) k_narrow<4, false, true><<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
+    else if (pmem == 5) k_narrow<5, false, true><<<c->sm_count * 5, NP_THREADS, 0, st>>>(a);
+    else if (pmem == 6) k_narrow<6, false, true><<<c->sm_count * 6, NP_THREADS, 0, st>>>(a);
+    else if (!filt) k_narrow<4, false><<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
     else if (occ == 8) k_narrow<8, true><<<c->sm_count * 8, NP_THREADS, 0, st>>>(a);
     else if (occ == 6) k_narrow<6, true><<<c->sm_count * 6, NP_THREADS, 0, st>>>(a);
     else if (occ == 5) k_narrow<5, true><<<c->sm_count * 5, NP_THREADS, 0, st>>>(a);

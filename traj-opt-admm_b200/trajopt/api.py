@@ -35,7 +35,7 @@ class TobCounters(C.Structure):
                 ("ccd_candidates", C.c_uint64), ("energy_plane_evals", C.c_uint64), ("self_pairs", C.c_uint64),
                 ("line_search_trials", C.c_uint64), ("barrier_terms", C.c_uint64), ("live_planes", C.c_uint64),
                 ("refine_capped", C.c_uint64), ("np_kdop_groups", C.c_uint64), ("np_gjk_iters", C.c_uint64),
-                ("ccd_gjk_iters", C.c_uint64), ("ccd_kdop_pass", C.c_uint64), ("np_kdop_exact", C.c_uint64), ("np_band", C.c_uint64)]
+                ("ccd_gjk_iters", C.c_uint64), ("ccd_kdop_pass", C.c_uint64), ("np_kdop_exact", C.c_uint64), ("np_band", C.c_uint64), ("ls_rung_hist", C.c_uint64 * 8)]
 
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_void_p)
@@ -371,7 +371,7 @@ class Solver:
     def counters(self):
         c = TobCounters()
         self.lib.tob_get_counters(self.ctx, C.byref(c))
-        return {k: getattr(c, k) for k, _ in TobCounters._fields_}
+        return {k: (list(getattr(c, k)) if k == "ls_rung_hist" else getattr(c, k)) for k, _ in TobCounters._fields_}
 
     def reset_counters(self):
         self.lib.tob_reset_counters(self.ctx)
