@@ -41,8 +41,8 @@ UNIT = "iter/s"
 # ---- algorithmic work per unit.  The pair kernels are costed from COUNTED work (device counters: 49-DOP groups evaluated,
 # GJK rounds run, barrier terms inside the band), not from a worst-case constant per candidate; per-unit flop figures:
 FLOP_KDOP_GROUP = 7 * (5 + 2)           # one group of 7 axes against precomputed extents: level (3 mul 2 add) + 2 subtractions.
-                                        # SINGLE precision since round 2 (filter of the gate, gjk.cuh: kdop_point_gate): reported
-                                        # as fp32 work, NOT in the FP64 roofline of k_narrow
+                                        # FP64 in the default narrowphase variant; with the single-precision filter of the gate
+                                        # (TRAJOPT_B200_NP_PMEM=0: gjk.cuh kdop_point_gate) reported as fp32 work instead
 FLOP_KDOP_EXACT_AXIS = 7                # an axis the filter could not decide, re-tested in FP64
 FLOP_KDOP_SHIFT = 3                     # per gate call: the point relative to the row's centre (3 FP64 subtractions)
 FLOP_GJK61_ROUND = 45 + 120             # support over 6 points (30) + tests (15) + signed-volume sub-algorithm (S1D 30 / S2D 130 / S3D 330)
@@ -50,10 +50,14 @@ FLOP_GJK121_ROUND = 75 + 120            # same with 12 swept points
 FLOP_PLANE_FINISH = 30                  # norm, normalise, d
 FLOP_KDOP_SWEPT = 49 * (13 * 5 + 4)     # swept 49-DOP of a candidate that passes (general 12+1 point version)
 FLOP_PER_PLANE_EVAL = 36.0              # 6 control points x (3 mul + 3 add)
-FLOP_PER_ACTIVE_TERM_E = 45.0           # energy: 2 sub, 3 mul, 1 div, log ~35 DFMA-equivalents
-FLOP_PER_ACTIVE_TERM_G = 116.0          # gradient: e1, e2 (~95) + 3 + 6 accumulates x 2
+FLOP_PER_ACTIVE_TERM_E = 20.0           # energy: 2 sub, 3 mul, 1 add, table logarithm 13 (csrc/fastlog.cuh; the library log was ~35)
+FLOP_PER_ACTIVE_TERM_G = 75.0           # gradient: logarithm 13, reciprocal ~8, e1 / e2 ~30, 9 accumulates x 2, products of c
 BYTES_PER_PLANE = 32.0
 BYTES_PER_BUILD_POINT = 128.0           # SURVEY 8(d) U-build
+
+
+# the gate of the narrowphase runs in FP64 unless the register variant with the single-precision filter is selected
+GATE_FP32 = os.environ.get("TRAJOPT_B200_NP_PMEM") == "0" and os.environ.get("TRAJOPT_B200_NP_FILTER", "1") != "0"
 
 
 def kernel_models(per_step, geo):
@@ -68,6 +72,8 @@ def kernel_models(per_step, geo):
     n_sys = 3 * (T - 4) + 1
     np_flop = (FLOP_GJK61_ROUND * per_step["np_gjk_iters"] + FLOP_PLANE_FINISH * planes
                + FLOP_KDOP_EXACT_AXIS * per_step.get("np_kdop_exact", 0.0) + FLOP_KDOP_SHIFT * 2 * cand)
+    if not GATE_FP32:
+        np_flop += FLOP_KDOP_GROUP * per_step.get("np_kdop_groups", 0.0) - FLOP_KDOP_SHIFT * 2 * cand
     ccd_flop = FLOP_KDOP_SWEPT * per_step["ccd_kdop_pass"] + FLOP_GJK121_ROUND * per_step["ccd_gjk_iters"]
     return {
         "k_rows": (0.0, rows * (18 + 6 + 2 * 49) * 8.0 * 2, "hbm"),
@@ -474,7 +480,7 @@ def run_ours(args):
                       "frac": (flop / sec / 1e12 / fp64_peak) if bound == "fp64" and fp64_peak else byts / sec / 1e9 / hbm_peak,
                       "share_of_step": kms / tot_prof_ms if tot_prof_ms else None}
         if name == "k_narrow":      # the 49-DOP gate runs through a single-precision filter: its work is not in the FP64 figure
-            ktab[name]["tflops_fp32_gate_counted"] = FLOP_KDOP_GROUP * per_step.get("np_kdop_groups", 0.0) / sec / 1e12
+            ktab[name]["tflops_fp32_gate_counted"] = (1.0 if GATE_FP32 else 0.0) * FLOP_KDOP_GROUP * per_step.get("np_kdop_groups", 0.0) / sec / 1e12
     roof = None
     if ktab:
         name = max(ktab, key=lambda k: ktab[k]["ms_per_step"])
@@ -508,7 +514,7 @@ def run_ours(args):
         "config": describe(args, world),
         "pair_evals_per_s": pair_evals / (total_ms * 1e-3),
         "pairs_per_step": {k: ctr[k] / args.steps for k in ("dcd_candidates", "planes", "ccd_candidates", "energy_plane_evals", "barrier_terms",
-                                                             "np_kdop_groups", "np_gjk_iters", "np_kdop_exact", "np_band", "ccd_kdop_pass", "ccd_gjk_iters", "line_search_trials")},
+                                                             "np_kdop_groups", "np_gjk_iters", "np_kdop_exact", "np_band", "ccd_kdop_pass", "ccd_gjk_iters", "line_search_trials", "ls_rungs_skipped")},
         "e2e": {"value": mult * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": state_bytes * world, "d2h_bytes_per_step": state_bytes * world},
         "ls_rung_hist_per_step": [x / args.steps for x in ctr.get("ls_rung_hist", [])],
         "gpu_launches": int(pe[1]),

@@ -245,7 +245,8 @@ typedef struct tob_counters {
   uint64_t ccd_kdop_pass;        /* swept candidates that passed the swept 49-DOP gate */
   uint64_t np_kdop_exact;        /* axes of the 49-DOP gate the single-precision filter left undecided (re-tested in FP64) */
   uint64_t np_band;              /* pairs whose GJK distance fell within 1e-6 (relative) of the gap: the only ones that need axes 15..49 of the gate */
-  uint64_t ls_rung_hist[8];      /* decoupled line searches by accepted rung of the 0.8 ladder: [0] = the first trial step .. [7] = the eighth or deeper */
+  uint64_t ls_rung_hist[8];      /* decoupled line searches by accepted rung of the 0.8 ladder (counted from the first rung that was evaluated): [0] .. [7] = the eighth or deeper */
+  uint64_t ls_rungs_skipped;     /* rungs not evaluated because a velocity / acceleration bound is violated for certain at that step (their energy is +inf) */
 } tob_counters;
 int tob_get_counters(const tob_ctx* ctx, tob_counters* out);
 int tob_reset_counters(tob_ctx* ctx);

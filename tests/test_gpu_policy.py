@@ -51,6 +51,14 @@ def test_single_uav_result_independent_of_line_search_schedule():
     for policy in ("3,9,3", "9,9,2", "2,3,8", "5,5,4"):
         assert same(ref, run(sc, sts, policy, 10)), policy
     assert same(ref, run(sc, sts, None, 10, one_call=True))
+    # the ladder with every rung evaluated (default: the rungs that violate a bound for certain are skipped, k_ls_bound_mask)
+    for skip in ("0",):
+        os.environ["TRAJOPT_B200_LS_SKIP"] = skip
+        try:
+            assert same(ref, run(sc, sts, None, 10)), skip
+            assert same(ref, run(sc, sts, "2,3,8", 10)), skip
+        finally:
+            os.environ.pop("TRAJOPT_B200_LS_SKIP", None)
 
 
 def test_multi_uav_result_independent_of_line_search_schedule():
@@ -59,6 +67,12 @@ def test_multi_uav_result_independent_of_line_search_schedule():
     ref = run(sc, sts, None, 6, uav_num=len(sts))
     for policy in ("3,9,3", "9,9,2", "2,3,8"):
         assert same(ref, run(sc, sts, policy, 6, uav_num=len(sts))), policy
+    for skip in ("0",):
+        os.environ["TRAJOPT_B200_LS_SKIP"] = skip
+        try:
+            assert same(ref, run(sc, sts, None, 6, uav_num=len(sts))), skip
+        finally:
+            os.environ.pop("TRAJOPT_B200_LS_SKIP", None)
 
 
 # ---- many rows (>= 8192: the throughput regime picks other kernel variants and another line-search policy) ------------------
@@ -69,7 +83,7 @@ def _batch(n=130):
 
 def _run_batch(scs, sts, iters, env):
     keys = ("TRAJOPT_B200_LS", "TRAJOPT_B200_EN_OCC", "TRAJOPT_B200_NP_FILTER", "TRAJOPT_B200_CCD_OCC", "TRAJOPT_B200_NP_OCC",
-            "TRAJOPT_B200_PACK_GRID", "TRAJOPT_B200_NP_BAND", "TRAJOPT_B200_NP_GATE1", "TRAJOPT_B200_NP_PMEM")
+            "TRAJOPT_B200_PACK_GRID", "TRAJOPT_B200_NP_BAND", "TRAJOPT_B200_NP_GATE1", "TRAJOPT_B200_NP_PMEM", "TRAJOPT_B200_LS_SKIP")
     for k in keys:
         os.environ.pop(k, None)
     os.environ.update(env)
@@ -98,7 +112,9 @@ def test_many_rows_result_independent_of_kernel_variants_and_schedule():
                 {"TRAJOPT_B200_LS": "2,2,16", "TRAJOPT_B200_PACK_GRID": "4"}, {"TRAJOPT_B200_LS": "2,3,9"},
                 {"TRAJOPT_B200_LS": "9,9,2", "TRAJOPT_B200_NP_OCC": "6"},
                 {"TRAJOPT_B200_NP_BAND": "0"}, {"TRAJOPT_B200_NP_BAND": "0", "TRAJOPT_B200_NP_FILTER": "0", "TRAJOPT_B200_NP_GATE1": "49"},
-                {"TRAJOPT_B200_NP_GATE1": "7"}, {"TRAJOPT_B200_NP_PMEM": "5"}, {"TRAJOPT_B200_NP_PMEM": "4"}):
+                {"TRAJOPT_B200_NP_GATE1": "7"}, {"TRAJOPT_B200_NP_PMEM": "5"}, {"TRAJOPT_B200_NP_PMEM": "4"},
+                {"TRAJOPT_B200_LS_SKIP": "0"}, {"TRAJOPT_B200_LS_SKIP": "0", "TRAJOPT_B200_LS": "2,5,5,2"}, {"TRAJOPT_B200_LS": "2,3,6,2"},
+                {"TRAJOPT_B200_LS": "2,5,3,3"}):
         got, cgot = _run_batch(scs, sts, 5, env)
         assert same(ref, got), env
         assert cgot["planes"] == cref["planes"] and cgot["dcd_candidates"] == cref["dcd_candidates"], env

@@ -66,6 +66,7 @@ static int alloc_states(tob_ctx* c) {
   TOB_CUDA(c, c->s_dir.ensure((size_t)U * 3 * T));
   TOB_CUDA(c, c->s_tdir.ensure(U)); TOB_CUDA(c, c->s_wolfe.ensure(U)); TOB_CUDA(c, c->s_gnorm.ensure(U));
   TOB_CUDA(c, c->s_step.ensure(U)); TOB_CUDA(c, c->s_selfstep.ensure(U)); TOB_CUDA(c, c->s_ptrial.ensure(U));
+  TOB_CUDA(c, c->s_lsmask.ensure(U));
   TOB_CUDA(c, c->s_e0.ensure(U)); TOB_CUDA(c, c->s_e1.ensure(U));
   TOB_CUDA(c, c->s_tstep.ensure((size_t)U * TOB_LS_TRIALS)); TOB_CUDA(c, c->s_ttime.ensure((size_t)U * TOB_LS_TRIALS));
   TOB_CUDA(c, c->s_etr.ensure((size_t)U * TOB_LS_TRIALS));
@@ -104,17 +105,9 @@ __global__ void k_fill_int(int* p, int n, int v) {
   if (i < n) p[i] = v;
 }
 
-// step = min(self step, 0.8^kmax); clamp so the piece time stays positive (Optimization3D_admm.h:521-524); then lay
-// out the first batch of trial points: k=0 the current point, k=1.. the ladder step, step*0.8, step*0.8*0.8, ...
-__global__ void k_ls_init(int rb, int re, const int* kmax, const double* steps_tab, const double* selfstep, int use_self,
-                          const double* ptime, const double* tdir, double* step, double* tstep, double* ttime, int* done,
-                          DevCounts* dc, int ls_rounds, int* bad) {
-  int u = rb + blockIdx.x * blockDim.x + threadIdx.x;
-  if (u == rb) {
-    for (int r = 0; r < TOB_LS_MAXROUNDS + 1; r++) dc->ls_pending[r] = 0;
-    dc->ls_rounds = ls_rounds;
-  }
-  if (u >= re) return;
+// first step of the ladder: min(self step, 0.8^kmax), clamped so the piece time stays positive (Optimization3D_admm.h:521-524)
+__device__ __forceinline__ double ls_base_step(int u, const int* kmax, const double* steps_tab, const double* selfstep, int use_self,
+                                               const double* ptime, const double* tdir) {
   double s = steps_tab[kmax[u]];
   if (use_self) {
     double ss = selfstep[u];
@@ -122,6 +115,93 @@ __global__ void k_ls_init(int rb, int re, const int* kmax, const double* steps_t
     s = ss;
   }
   if (ptime[u] + s * tdir[u] <= 0) s = -0.95 * ptime[u] / tdir[u];
+  return s;
+}
+
+// Rungs of the 0.8 ladder at which a velocity / acceleration bound of some sub-segment is violated FOR CERTAIN: the
+// reference's energy is +inf there (Energy_admm.h:98-170 returns at the first d <= 0) and its Armijo loop moves on
+// (Optimization3D_admm.h:537-544).  On the batched workload the step the CCD bound allows shortens the piece time so much
+// that the first 8 to 12 rungs violate the velocity bound: evaluated, each costs a pass of k_row_energy up to the first
+// warp that meets the violation, and the round that finally is feasible evaluates four rungs of which the first is accepted.
+// One thread per (row, rung) of the first 32 rungs evaluates the row's nine bound terms -- trial control points
+// basis (x + s dir) and trial time like k_row_energy -- and sets the rung's bit when some d < -1e-9 (limit + 1): six orders of
+// magnitude above what the evaluation order can change.  k_ls_init starts the ladder behind the leading set bits; every
+// rung from there on is evaluated as before, so a rung is skipped only when its energy is known to be +inf.
+struct LsMaskArgs {
+  int rb, re, n_tr, res, T, use_self;
+  const int* kmax;
+  const double *steps_tab, *selfstep, *ptime, *tdir, *spline, *dir, *basis, *weight;
+  double vel_limit, acc_limit;
+  unsigned* mask;       // per robot
+};
+__global__ void __launch_bounds__(128) k_ls_bound_mask(LsMaskArgs a) {
+  const int rung = threadIdx.x & 31;
+  const int ri = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (ri >= (a.re - a.rb) * a.n_tr) return;
+  const int u = a.rb + ri / a.n_tr, tr = ri % a.n_tr;
+  double s = ls_base_step(u, a.kmax, a.steps_tab, a.selfstep, a.use_self, a.ptime, a.tdir);
+  for (int k = 0; k < rung; k++) s *= 0.8;
+  const double t = a.ptime[u] + s * a.tdir[u];
+  const double w = a.weight[tr];
+  const double* B = a.basis + (size_t)36 * tr;
+  double P[18];
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++) {
+    double bz[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const size_t gi = (size_t)u * 3 * a.T + (size_t)ax * a.T + 3 * (tr / a.res) + i;
+      bz[i] = a.spline[gi] + s * a.dir[gi];
+    }
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      double acc = 0;
+#pragma unroll
+      for (int i = 0; i < 6; i++) acc += B[j + 6 * i] * bz[i];
+      P[j + 6 * ax] = acc;
+    }
+  }
+  bool bad = false;
+  const double mv = 1e-9 * (a.vel_limit + 1.0), ma = 1e-9 * (a.acc_limit + 1.0);
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const double vx = 5 * (P[j + 1] - P[j]), vy = 5 * (P[j + 7] - P[j + 6]), vz = 5 * (P[j + 13] - P[j + 12]);
+    const double d = a.vel_limit - sqrt(vx * vx + vy * vy + vz * vz) / (w * t);
+    bad |= d < -mv;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const double ax = 20 * (P[j + 2] - 2 * P[j + 1] + P[j]), ay = 20 * (P[j + 8] - 2 * P[j + 7] + P[j + 6]),
+                 az = 20 * (P[j + 14] - 2 * P[j + 13] + P[j + 12]);
+    const double d = a.acc_limit - sqrt(ax * ax + ay * ay + az * az) / (w * w * t * t);
+    bad |= d < -ma;
+  }
+  // the 32 rungs of this row: one word, merged into the robot's mask
+  const unsigned m = __ballot_sync(0xffffffffu, bad);
+  if (rung == 0 && m) atomicOr(a.mask + u, m);
+}
+
+// lay out the first batch of trial points: k=0 the current point, k=1.. the ladder step, step*0.8, step*0.8*0.8, ...
+__global__ void k_ls_init(int rb, int re, const int* kmax, const double* steps_tab, const double* selfstep, int use_self,
+                          const double* ptime, const double* tdir, double* step, double* tstep, double* ttime, int* done,
+                          DevCounts* dc, int ls_rounds, int* bad, const unsigned* bmask) {
+  int u = rb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (u == rb) {
+    for (int r = 0; r < TOB_LS_MAXROUNDS + 1; r++) dc->ls_pending[r] = 0;
+    dc->ls_rounds = ls_rounds;
+  }
+  if (u >= re) return;
+  double s = ls_base_step(u, kmax, steps_tab, selfstep, use_self, ptime, tdir);
+  int n_skip = 0;
+  if (bmask) {
+    // leading rungs at which a velocity / acceleration bound is violated for certain (k_ls_bound_mask): the reference's
+    // energy is +inf there and its loop moves on -- so does this one, without evaluating them.  The steps are the same
+    // products s * 0.8 * 0.8 ... the evaluated ladder would have formed.
+    const unsigned m = bmask[u];
+    const int lead = m == 0xffffffffu ? 32 : __ffs(~m) - 1;
+    for (; n_skip < lead; n_skip++) s *= 0.8;
+  }
+  if (n_skip) atomicAdd(&dc->ls_skipped, (unsigned long long)n_skip);
   step[u] = s;
   tstep[u * TOB_LS_TRIALS] = 0.0;
   ttime[u * TOB_LS_TRIALS] = ptime[u];
@@ -452,9 +532,25 @@ static int iterate_launch(tob_ctx* c, int mode) {
     TOB_LAUNCH_CHECK(c);
     wolfe_idx = 0;
   } else {
+    // largest step at which every plane still has all its control points on the right side (one pass over the planes)
+    const unsigned* bmask = nullptr;
+    {
+      const char* e = getenv("TRAJOPT_B200_LS_SKIP");      // 0: every rung of the ladder is evaluated (tests, A/B)
+      if (!e || atoi(e) != 0) {
+        TOB_CUDA(c, cudaMemsetAsync(c->s_lsmask.p + rb, 0, (size_t)(re - rb) * sizeof(unsigned), st));
+        LsMaskArgs m;
+        m.rb = rb; m.re = re; m.n_tr = c->n_tr; m.res = c->prm.res; m.T = c->T; m.use_self = U > 1 ? 1 : 0;
+        m.kmax = c->kmax.p; m.steps_tab = c->d_steps.p; m.selfstep = c->s_selfstep.p; m.ptime = c->s_ptime.p; m.tdir = c->s_tdir.p;
+        m.spline = c->s_spline.p; m.dir = c->s_dir.p; m.basis = c->d_basis.p; m.weight = c->d_weight.p;
+        m.vel_limit = c->prm.vel_limit; m.acc_limit = c->prm.acc_limit; m.mask = c->s_lsmask.p;
+        k_ls_bound_mask<<<div_up((re - rb) * c->n_tr, 4), 128, 0, st>>>(m);
+        TOB_LAUNCH_CHECK(c);
+        bmask = c->s_lsmask.p;
+      }
+    }
     k_ls_init<<<div_up(re - rb, 64), 64, 0, st>>>(rb, re, c->kmax.p, c->d_steps.p, c->s_selfstep.p, U > 1 ? 1 : 0, c->s_ptime.p,
                                                   c->s_tdir.p, c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p,
-                                                  c->ls_rounds, c->row_bad.p);
+                                                  c->ls_rounds, c->row_bad.p, bmask);
     TOB_LAUNCH_CHECK(c);
     wolfe_idx = U > 1 ? U - 1 : -1;
   }
@@ -1289,7 +1385,7 @@ int tob_line_search(tob_ctx* c, int robot, tob_state* st, const double* directio
   }
   TOB_TRY(line_search_begin(c, robot, robot + 1));
   k_ls_init<<<1, 64, 0, c->stream>>>(robot, robot + 1, c->kmax.p, c->d_steps.p, c->s_selfstep.p, use_self, c->s_ptime.p, c->s_tdir.p,
-                                     c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p, c->ls_rounds, c->row_bad.p);
+                                     c->s_step.p, c->s_tstep.p, c->s_ttime.p, c->s_done.p, c->dc.p, c->ls_rounds, c->row_bad.p, nullptr);
   TOB_LAUNCH_CHECK(c);
   c->ls_e0_ready = false;            // function-level call: the starting point is evaluated by the energy kernel
   TOB_TRY(line_search(c, robot, robot + 1, -1));
@@ -1472,6 +1568,7 @@ int tob_get_counters(const tob_ctx* cc, tob_counters* out) {
   out->np_kdop_exact = c->h_dc->np_kdop_exact;
   out->np_band = c->h_dc->np_band;
   for (int i = 0; i < 8; i++) out->ls_rung_hist[i] = c->h_dc->ls_hist[i];
+  out->ls_rungs_skipped = c->h_dc->ls_skipped;
   return 0;
 }
 int tob_reset_counters(tob_ctx* c) {
@@ -1479,7 +1576,7 @@ int tob_reset_counters(tob_ctx* c) {
   cudaSetDevice(c->device);
   memset(&c->ctr, 0, sizeof(c->ctr));
   TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->dcd_candidates, 0, 5 * sizeof(unsigned long long), c->stream));
-  TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->np_kdop_groups, 0, 14 * sizeof(unsigned long long), c->stream));
+  TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->np_kdop_groups, 0, 15 * sizeof(unsigned long long), c->stream));
   return 0;
 }
 

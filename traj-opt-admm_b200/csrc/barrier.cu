@@ -351,10 +351,35 @@ __global__ void __launch_bounds__(32 * TOB_LS_TRIALS) k_robot_ls(RobotLsArgs b) 
   if (k < b.kte) {
     double e = 0;
     const bool bad = a.bad[robot * a.KT + k] != 0;            // the row sums of an infeasible trial are incomplete: unused
-    for (int tr = lane; tr < a.n_tr && !bad; tr += 32) {
-      const int row = robot * a.n_tr + tr;
-      size_t o = (size_t)k * a.rows_all + row;
-      e += a.lambda * row_plane_sum(a.row_e, o, a.pl_off, row) + a.lambda * a.row_e[o * EN_REC + EN_VMAX];
+    // four rows of the lane per step, every load of the four issued before the first use (the loop was a chain of dependent
+    // L2 round trips: plane count -> partials, 16 times over for a 512-row trajectory); summed in the same order as before
+    for (int tr0 = lane; tr0 < a.n_tr && !bad; tr0 += 128) {
+      int V[4];
+      double p0[4], pb[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int tr = tr0 + 32 * i;
+        V[i] = 0; p0[i] = 0; pb[i] = 0;
+        if (tr < a.n_tr) {
+          const int row = robot * a.n_tr + tr;
+          const size_t o = ((size_t)k * a.rows_all + row) * EN_REC;
+          V[i] = en_vwarps(a.pl_off[row + 1] - a.pl_off[row]);
+          p0[i] = a.row_e[o];
+          pb[i] = a.row_e[o + EN_VMAX];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int tr = tr0 + 32 * i;
+        if (tr < a.n_tr) {
+          double sum = p0[i];
+          if (V[i] > 1) {
+            const double* p = a.row_e + ((size_t)k * a.rows_all + (robot * a.n_tr + tr)) * EN_REC;
+            for (int v = 1; v < V[i]; v++) sum += p[v];
+          }
+          e += a.lambda * sum + a.lambda * pb[i];
+        }
+      }
     }
     const double t = a.ttime[robot * a.KT + k];
     const double st = (a.dir && a.tstep) ? a.tstep[robot * a.KT + k] : 0.0;

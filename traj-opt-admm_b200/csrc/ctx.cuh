@@ -96,6 +96,7 @@ struct DevCounts {
   unsigned long long np_kdop_exact;    // axes of the 49-DOP gate the single-precision filter could not decide (re-tested in FP64)
   unsigned long long np_band;          // pairs whose GJK distance fell inside the band where the rest of the gate had to be evaluated
   unsigned long long ls_hist[8];       // decoupled line searches by the ladder rung that was accepted: 1, 2, .. 7, 8 and deeper
+  unsigned long long ls_skipped;       // ladder rungs not evaluated: a velocity / acceleration bound is violated for certain there (k_ls_bound_mask)
 };
 
 // per-row (robot x sub-segment) geometry produced by segments.cu, indexed by GLOBAL row = robot*n_tr + tr
@@ -173,6 +174,7 @@ struct tob_ctx {
   tob::DBuf<double> s_spline, s_ptime, s_pslack, s_tslack, s_plambda, s_tlambda;
   tob::DBuf<double> s_dir, s_tdir, s_wolfe, s_gnorm;
   tob::DBuf<double> s_step, s_selfstep, s_ptrial, s_e0, s_e1;
+  tob::DBuf<unsigned> s_lsmask;       // per robot: rungs 0..31 at which a velocity / acceleration bound is violated for certain
   tob::DBuf<double> s_tstep, s_ttime, s_etr;   // batched line-search trials: robots x TOB_LS_TRIALS
   tob::DBuf<int> s_done, solve_status;
 

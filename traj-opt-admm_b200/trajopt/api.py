@@ -35,7 +35,7 @@ class TobCounters(C.Structure):
                 ("ccd_candidates", C.c_uint64), ("energy_plane_evals", C.c_uint64), ("self_pairs", C.c_uint64),
                 ("line_search_trials", C.c_uint64), ("barrier_terms", C.c_uint64), ("live_planes", C.c_uint64),
                 ("refine_capped", C.c_uint64), ("np_kdop_groups", C.c_uint64), ("np_gjk_iters", C.c_uint64),
-                ("ccd_gjk_iters", C.c_uint64), ("ccd_kdop_pass", C.c_uint64), ("np_kdop_exact", C.c_uint64), ("np_band", C.c_uint64), ("ls_rung_hist", C.c_uint64 * 8)]
+                ("ccd_gjk_iters", C.c_uint64), ("ccd_kdop_pass", C.c_uint64), ("np_kdop_exact", C.c_uint64), ("np_band", C.c_uint64), ("ls_rung_hist", C.c_uint64 * 8), ("ls_rungs_skipped", C.c_uint64)]
 
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_void_p)
