@@ -442,16 +442,20 @@ static int ensure_iter_buffers(tob_ctx* c) {
 // travel with the second exchange so that all ranks agree on whether the iteration commits.
 // few rows: cover 8 rungs per launch (latency); many rows: one rung per round (throughput), more rounds ahead
 static void ls_policy(tob_ctx* c, int rb, int re, bool coupled) {
-  // few rows (latency regime): one launch covers 8 rungs, 2 rounds ahead.  Many rows (throughput regime, >= 8192): most
-  // robots accept the first rung, so round 0 evaluates only that one (the energy of the current point comes from the
-  // gradient pass) and the robots that keep backtracking get 4 rungs per later round, 5 rounds ahead = 17 rungs before the
-  // host has to continue a search.  Measured on the 1024-problem batch: (3, 9, 3) 4.89 ms of energy kernels per iteration,
-  // (3, 5, 4) 4.09, (2, 5, 4) 3.76, (2, 9, 3) 5.11.
+  // The ladder starts behind the rungs that violate a bound for certain (k_ls_bound_mask), and then the first evaluated rung
+  // is accepted by nearly every search (tob_counters.ls_rung_hist: 127.9 of 128 per iteration of a batch shard, 1.0 of 1 on the
+  // forest scene): round 0 evaluates that rung alone (the energy of the current point comes from the gradient pass).
+  // Few rows (latency regime): a search that goes on gets 8 rungs in the one further round launched ahead.  Many rows
+  // (throughput regime, >= 8192): 2 rungs in round 1, 4 in round 2 = 7 rungs before the host has to continue a search; every
+  // round launched ahead costs 14 us when nobody is left in it.  Measured (ms per iteration, kte0,kte,rounds[,kte1]):
+  // batch shard 2,5,5 2.176 / 2,5,3,3 2.160 / 2,5,2,3 2.148 / 2,5,4,3 2.168; forest 9,9,2 0.324 / 5,9,2 0.315 / 2,9,2 0.304;
+  // 64 UAVs 9,9,2 0.389 / 2,9,2 0.350.  Before the mask: (3,9,3) 4.89 ms of energy kernels per iteration of the whole batch,
+  // (3,5,4) 4.09, (2,5,4) 3.76, (2,9,3) 5.11.
   const bool many = !coupled && (long long)(re - rb) * c->n_tr >= 8192;
-  c->ls_kte0 = many ? 2 : TOB_LS_TRIALS;
+  c->ls_kte0 = coupled ? TOB_LS_TRIALS : 2;
   c->ls_kte = many ? 5 : TOB_LS_TRIALS;
-  c->ls_rounds = many ? 5 : 2;
-  c->ls_kte1 = c->ls_kte;
+  c->ls_rounds = many ? 3 : 2;
+  c->ls_kte1 = many ? 3 : TOB_LS_TRIALS;
   if (const char* e = getenv("TRAJOPT_B200_LS")) {          // "kte0,kte,rounds[,kte1]": tuning / experiments
     int k0 = 0, k = 0, r = 0, k1 = 0;
     const int got = coupled ? 0 : sscanf(e, "%d,%d,%d,%d", &k0, &k, &r, &k1);

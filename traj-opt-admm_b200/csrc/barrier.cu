@@ -575,48 +575,63 @@ struct RowGradArgs {
   int rows_all;
 };
 
-// part v of `row` by the whole CTA (128 threads): sums of the plane terms -> s_red[4][54] per warp, energy -> s_en[4]
+// part v of `row` by the whole CTA (128 threads): sums of the plane terms -> s_red[4][54] per warp, energy -> s_en[4].
+// A plane is shared by TWO threads: lanes 0-15 of a warp take control points 0..2 of 16 planes, lanes 16-31 control points
+// 3..5 of the same planes (the second load of a plane is an L1 hit).  27 accumulators per thread instead of 54: the kernel
+// ran at 234 registers = 8 warps per SM with the FP64 pipe a third busy, waiting on its own dependent chains.  A chunk of 128
+// planes takes the CTA two steps of 64; the sums stay a function of the row's plane count only.
 __device__ __forceinline__ void grad_part(const RowGradArgs& a, int row, int v, int V, const double* sP, double (*s_red)[54],
                                           double* s_en, const LogTabEntry* s_lt) {
   const int tr = row % a.n_tr;
   const double w = a.weight[tr], m = a.margin, inv_m = 1.0 / m;
-  double acc[54];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, half = lane >> 4;
+  const uint32_t pslot = (uint32_t)wp * 16u + (uint32_t)(lane & 15);      // plane of this thread inside a step of 64
+  double acc[27];
   double en = 0;
   unsigned n_act = 0;
 #pragma unroll
-  for (int i = 0; i < 54; i++) acc[i] = 0;
+  for (int i = 0; i < 27; i++) acc[i] = 0;
+  double cp[9];                 // the thread's three control points: x, y, z
+#pragma unroll
+  for (int jj = 0; jj < 3; jj++) { cp[jj] = sP[3 * half + jj]; cp[3 + jj] = sP[3 * half + jj + 6]; cp[6 + jj] = sP[3 * half + jj + 12]; }
   const uint32_t k0 = a.pl_off[row], k1 = a.pl_off[row + 1];
   const uint32_t first = k0 + (uint32_t)v * 128u, stride = 128u * (uint32_t)V;
+  // step i: planes first + (i / 2) * stride + (i % 2) * 64 + [0, 64)
   double4 nxt = make_double4(0, 0, 0, 0);
-  if (first + threadIdx.x < k1) nxt = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * (first + threadIdx.x));
-  for (uint32_t k = first + threadIdx.x; k < k1; k += stride) {
+  if (first + pslot < k1) nxt = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * (first + pslot));
+  for (uint32_t cb = first, i = 0; cb < k1; i++, cb += (i & 1u) ? 0u : stride) {     // uniform in the CTA
+    const uint32_t k = cb + (i & 1u) * 64u + pslot;
     const double4 pl = nxt;       // the next plane of this thread is in flight while this one is evaluated
-    if (k + stride < k1) nxt = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * (k + stride));
+    {
+      const uint32_t cbn = cb + ((i & 1u) ? stride : 0u), kn = cbn + ((i + 1u) & 1u) * 64u + pslot;
+      if (cbn < k1 && kn < k1) nxt = *reinterpret_cast<const double4*>(a.pl + (size_t)4 * kn);
+    }
+    if (k >= k1) continue;
     const double cxx = pl.x * pl.x, cxy = pl.x * pl.y, cxz = pl.x * pl.z, cyy = pl.y * pl.y, cyz = pl.y * pl.z, czz = pl.z * pl.z;
-    // branch-free like k_row_energy: a term outside the band contributes e1 = e2 = 0 through log(1) and dm = 0, so the six
-    // log / reciprocal chains of a plane are independent and interleave
+    // branch-free like k_row_energy: a term outside the band contributes e1 = e2 = 0 through log(1) and dm = 0, so the three
+    // log / reciprocal chains of the thread are independent and interleave
 #pragma unroll
-    for (int j = 0; j < 6; j++) {
-      const double d = sP[j] * pl.x + sP[j + 6] * pl.y + sP[j + 12] * pl.z + pl.w;
+    for (int jj = 0; jj < 3; jj++) {
+      const double d = cp[jj] * pl.x + cp[3 + jj] * pl.y + cp[6 + jj] * pl.z + pl.w;
       const bool act = d < m;
       n_act += act;
       const double lg = tob_log_pos(act ? d * inv_m : 1.0, s_lt), dm = act ? d - m : 0.0, id = 1.0 / (act ? d : 1.0);
       const double e1 = -w * (2 * dm * lg + dm * dm * id);
       const double e2 = -w * (2 * lg + 4 * dm * id - dm * dm * id * id);
       en += (dm * dm) * lg;
-      double* q = acc + 9 * j;
+      double* q = acc + 9 * jj;
       q[0] += e2 * cxx; q[1] += e2 * cxy; q[2] += e2 * cxz; q[3] += e2 * cyy; q[4] += e2 * cyz; q[5] += e2 * czz;
       q[6] += e1 * pl.x; q[7] += e1 * pl.y; q[8] += e1 * pl.z;
     }
   }
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   for (int o = 16; o; o >>= 1) n_act += __shfl_xor_sync(0xffffffffu, n_act, o);
   if (lane == 0 && n_act) atomicAdd(&a.dc->barrier_terms, (unsigned long long)n_act);
-  if (first + 32u * wp < k1) {         // this warp streamed at least one plane (warp-uniform)
+  if (first + 16u * wp < k1) {         // this warp streamed at least one plane (warp-uniform)
 #pragma unroll
-    for (int i = 0; i < 54; i++) {
-      double x = warp_sum(acc[i]);
-      if (lane == 0) s_red[wp][i] = x;
+    for (int i = 0; i < 27; i++) {
+      double x = acc[i];
+      for (int o = 8; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);       // inside the half warp
+      if ((lane & 15) == 0) s_red[wp][27 * half + i] = x;                        // control point 3 * half + i / 9, value i % 9
     }
     en = warp_sum(en);
     if (lane == 0) s_en[wp] = en;
@@ -627,7 +642,7 @@ __device__ __forceinline__ void grad_part(const RowGradArgs& a, int row, int v, 
 }
 
 // grid = n_rows + extra CTAs.  CTA b < n_rows: part 0 of row b and its bound terms; the extra CTAs share the listed parts.
-__global__ void __launch_bounds__(128) k_row_grad(RowGradArgs a) {
+__global__ void __launch_bounds__(128, 4) k_row_grad(RowGradArgs a) {
   __shared__ double sP[18];
   __shared__ double s_red[4][54];
   __shared__ double s_gt[9], s_ht[9], s_eb[9], s_en[4];
