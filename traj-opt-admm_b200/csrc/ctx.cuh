@@ -81,7 +81,7 @@ struct DevCounts {
   int32_t ls_pending[TOB_LS_MAXROUNDS + 1];   // robots still backtracking after Armijo round r (last entry: host scratch)
   int32_t ls_rounds;                          // rounds launched ahead in this iteration (written by k_ls_init)
   uint32_t iters_done;       // iterations fully committed (apply step + slack update ran)
-  uint32_t pad0;
+  uint32_t np_next;          // next chunk of candidates a CTA of k_narrow takes (reset by k_np_top, which runs behind it)
   unsigned long long dcd_candidates, planes, ccd_candidates, energy_plane_evals, barrier_terms;   // cumulative since reset
   // persistent-plane mode ("optimal_plane": 1)
   uint32_t n_live;           // live (row, point) obstacle planes

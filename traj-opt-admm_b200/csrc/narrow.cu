@@ -142,7 +142,15 @@ __global__ void __launch_bounds__(NP_THREADS, MINB) k_narrow(NarrowArgs a) {
   const int gate1 = a.gate1;
   unsigned w_groups = 0, w_iters = 0, w_exact = 0, w_band = 0;   // counted work of this thread
   __syncthreads();
-  for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+  // chunks are handed out on demand: a chunk costs between a few gate tests and 512 GJK runs, and with ~20 chunks per CTA (the
+  // shard one of eight GPUs gets of the batch) a fixed deal left the grid waiting for its unluckiest CTAs.  Which CTA runs a
+  // chunk does not matter: planes and flags are stored by candidate index, the count by chunk.
+  __shared__ uint32_t s_chunk;
+  for (;;) {
+    if (tid == 0) s_chunk = atomicAdd(&a.dc->np_next, 1u);
+    __syncthreads();
+    const uint32_t chunk = s_chunk;
+    if (chunk >= n_chunks) break;
     uint32_t n_surv = 0;   // uniform
     // the candidates of this thread are gathered first (index -> row / point -> coordinates are two dependent global loads
     // each; one after the other behind the block barriers of the compaction they cost four round trips instead of one)
@@ -340,6 +348,7 @@ __global__ void __launch_bounds__(1024) k_np_top(PackArgs a) {
   __syncthreads();
   const uint32_t self_total = cta1024_scan_inplace(a.selfpre, (uint32_t)a.rows_all);
   if (threadIdx.x == 0) a.dc->n_en_items = 0;     // the listed parts of heavy rows are rebuilt from the new CSR (barrier.cu)
+  if (threadIdx.x == 0) a.dc->np_next = 0;        // k_narrow has handed out its chunks: ready for the next plane pass
   if (threadIdx.x == 0 && a.live) {
     a.csum[n_chunks] = ob_total;
     a.selfpre[a.rows_all] = 0;
