@@ -64,16 +64,28 @@ __device__ __forceinline__ uint32_t lower_bound_u64(const unsigned long long* __
 }
 
 #define NP_THREADS 128
-#define NP_PER 4
+#define NP_PER 8
 #define NP_CHUNK (NP_THREADS * NP_PER)   // most candidates per CTA iteration; their k-DOP survivors fill the GJK phase densely
 
-// Candidates per thread and chunk (1, 2 or 4), chosen on the device from the candidate count so that a small query (one
+// Candidates per thread and chunk (1, 2, 4 or 8), chosen on the device from the candidate count so that a small query (one
 // UAV: ~1e5 candidates) still spreads over every CTA of the grid instead of serialising two GJK rounds on half of them.
 // k_narrow, k_np_top, k_pack and k_live_compact must agree: all derive it from (n_cand, np_grid).
-__device__ __forceinline__ uint32_t np_per_of(uint32_t n, uint32_t grid) {
-  if ((n + NP_CHUNK - 1) / NP_CHUNK >= grid) return 4;
-  if ((n + 2 * NP_THREADS - 1) / (2 * NP_THREADS) >= grid) return 2;
-  return 1;
+// grid: CTAs the chunks should cover; its top three bits, when set, cap the result (TRAJOPT_B200_NP_CHUNK: A/B measurements)
+__device__ __forceinline__ uint32_t np_per_of(uint32_t n, uint32_t grid_and_cap) {
+  const uint32_t grid = grid_and_cap & 0x1fffffffu, cap = grid_and_cap >> 29;
+  uint32_t per = 1;
+  if ((n + 8 * NP_THREADS - 1) / (8 * NP_THREADS) >= 4 * grid) per = 8;      // at least ~20 chunks per CTA of the grid
+  else if ((n + 4 * NP_THREADS - 1) / (4 * NP_THREADS) >= grid) per = 4;
+  else if ((n + 2 * NP_THREADS - 1) / (2 * NP_THREADS) >= grid) per = 2;
+  return cap && per > cap ? cap : per;
+}
+static uint32_t np_grid_of(const tob_ctx* c) {
+  uint32_t g = (uint32_t)c->sm_count * 4;
+  if (const char* e = getenv("TRAJOPT_B200_NP_CHUNK")) {      // 128 / 256 / 512: most candidates per chunk
+    const int v = atoi(e);
+    if (v == 128) g |= 1u << 29; else if (v == 256) g |= 2u << 29; else if (v == 512) g |= 4u << 29;
+  }
+  return g;
 }
 
 // block-wide stable compaction step: the threads with `keep` append `value` to list[count ...] in thread order; returns the
@@ -601,7 +613,7 @@ static int live_rows(tob_ctx* c) {
   a.px = c->px.p; a.py = c->py.p; a.pz = c->pz.p; a.P = c->geo.P.p;
   a.offset = c->prm.offset; a.margin = c->prm.margin;
   a.pl = c->pl.p; a.pl_row = c->pl_row.p; a.pl_off = c->pl_off.p;
-  a.np_grid = (uint32_t)c->sm_count * 4;
+  a.np_grid = np_grid_of(c);
   {
     Prof prof(c, K_PACK);
     k_live_compact<<<c->sm_count * 4, NP_THREADS, 0, st>>>(a);
@@ -664,7 +676,7 @@ static int pack_rows(tob_ctx* c, int rb, int re, bool ws, bool live = false) {
   a.selfcnt = c->selfcnt.p;
   a.self_ok = c->self_ok.p; a.cpl = c->cpl.p; a.self_pl = c->self_pl.p;
   a.pl = c->pl.p; a.pl_row = c->pl_row.p; a.pl_off = c->pl_off.p;
-  a.live = live ? 1 : 0; a.live_cap = (uint32_t)c->live_cap; a.np_grid = (uint32_t)c->sm_count * 4;
+  a.live = live ? 1 : 0; a.live_cap = (uint32_t)c->live_cap; a.np_grid = np_grid_of(c);
   {
     Prof prof(c, K_SCAN);
     k_np_top<<<1, 1024, 0, st>>>(a);
@@ -703,7 +715,7 @@ int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self) {
     TOB_TRY(ensure_live_buffers(c, c->live_cap ? c->live_cap : 1));
   }
   a.live_key = live ? c->live_key.p : nullptr;
-  a.np_grid = (uint32_t)c->sm_count * 4;
+  a.np_grid = np_grid_of(c);
   {
     Prof prof(c, K_NARROW);
     const char *eo = getenv("TRAJOPT_B200_NP_OCC"), *ef = getenv("TRAJOPT_B200_NP_FILTER");   // A/B measurements, tests
@@ -712,7 +724,7 @@ int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self) {
     a.gate_skip = (eb && atoi(eb) == 0) ? -1.0 : a.dist * (1.0 - 1e-6);
     a.gate1 = eg ? atoi(eg) : NP_GATE1;
     if (a.gate1 < 7 || a.gate1 > TOB_KDOP_AXES || a.gate1 % 7) a.gate1 = NP_GATE1;
-    a.np_grid = (uint32_t)c->sm_count * 4;
+    a.np_grid = np_grid_of(c);
     const char* em = getenv("TRAJOPT_B200_NP_PMEM");
     // default: hull vertices from L1, registers for 5 CTAs per SM (measured on a 128-problem shard: 1.025 ms with the vertices
     // in registers at 4 CTAs per SM, 1.001 / 0.959 / 0.990 ms with PMEM at 4 / 5 / 6); 0 = the register variants below
