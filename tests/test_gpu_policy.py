@@ -83,7 +83,8 @@ def _batch(n=130):
 
 def _run_batch(scs, sts, iters, env):
     keys = ("TRAJOPT_B200_LS", "TRAJOPT_B200_EN_OCC", "TRAJOPT_B200_NP_FILTER", "TRAJOPT_B200_CCD_OCC", "TRAJOPT_B200_NP_OCC",
-            "TRAJOPT_B200_PACK_GRID", "TRAJOPT_B200_NP_BAND", "TRAJOPT_B200_NP_GATE1", "TRAJOPT_B200_NP_PMEM", "TRAJOPT_B200_LS_SKIP")
+            "TRAJOPT_B200_PACK_GRID", "TRAJOPT_B200_NP_BAND", "TRAJOPT_B200_NP_GATE1", "TRAJOPT_B200_NP_PMEM", "TRAJOPT_B200_LS_SKIP", "TRAJOPT_B200_PIECE_CTA",
+            "TRAJOPT_B200_NP_CHUNK")
     for k in keys:
         os.environ.pop(k, None)
     os.environ.update(env)
@@ -114,7 +115,8 @@ def test_many_rows_result_independent_of_kernel_variants_and_schedule():
                 {"TRAJOPT_B200_NP_BAND": "0"}, {"TRAJOPT_B200_NP_BAND": "0", "TRAJOPT_B200_NP_FILTER": "0", "TRAJOPT_B200_NP_GATE1": "49"},
                 {"TRAJOPT_B200_NP_GATE1": "7"}, {"TRAJOPT_B200_NP_PMEM": "5"}, {"TRAJOPT_B200_NP_PMEM": "4"},
                 {"TRAJOPT_B200_LS_SKIP": "0"}, {"TRAJOPT_B200_LS_SKIP": "0", "TRAJOPT_B200_LS": "2,5,5,2"}, {"TRAJOPT_B200_LS": "2,3,6,2"},
-                {"TRAJOPT_B200_LS": "2,5,3,3"}):
+                {"TRAJOPT_B200_LS": "2,5,3,3"}, {"TRAJOPT_B200_PIECE_CTA": "128", "TRAJOPT_B200_NP_CHUNK": "256"},
+                {"TRAJOPT_B200_PIECE_CTA": "384", "TRAJOPT_B200_NP_CHUNK": "128"}):
         got, cgot = _run_batch(scs, sts, 5, env)
         assert same(ref, got), env
         assert cgot["planes"] == cref["planes"] and cgot["dcd_candidates"] == cref["dcd_candidates"], env

@@ -832,8 +832,12 @@ __device__ __forceinline__ void warp_tridiag19(const double* s_H, double* s_d, d
   if (lane == N - 1) { s_d[N - 1] = a[N - 1]; s_e[N - 1] = 0.0; }
 }
 
-__device__ __forceinline__ int cta384_psd_shift19(double* s_H) {
-  constexpr int N = 19, NW = 12;
+// NWP = warps of the CTA (12, or 4 where many blocks are in flight: the multisection then evaluates three of the 384 shifts of a
+// round per thread and the Cholesky test three elements per thread -- the same shifts and the same operations, so the result
+// does not depend on the variant)
+template <int NWP>
+__device__ __forceinline__ int cta_psd_shift19(double* s_H) {
+  constexpr int N = 19, NW = 12, SP = NW / NWP;
   __shared__ double s_col[2][N + 1], s_v[N + 1], s_w[N + 1], s_d[N + 1], s_e[N + 1], s_e2[N + 1];
   __shared__ int s_first[2][NW];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -870,29 +874,33 @@ __device__ __forceinline__ int cta384_psd_shift19(double* s_H) {
     const double stop = 1e-14 * sc;
     for (int round = 0; round < 8; round++) {
       const int b = round & 1;
-      const double x = lo + (hi - lo) * ((tid + 1) / (double)(NT + 1));
-      int cnt = 0;
-      double q0 = 1.0, q1 = dd[0] - x;
-      bool neg = q1 < 0;                                   // sign of the last non-zero term
-      if (neg) cnt++;
 #pragma unroll
-      for (int i = 1; i < N; i++) {
-        const double t = e2[i] * q0;
-        double q2 = fma(dd[i] - x, q1, -t);
-        if (i % 6 == 0) {
-          const double m = fabs(q2);
-          if (m > 1e100) { q2 *= 1e-100; q1 *= 1e-100; }
-          else if (m < 1e-100 && m > 0) { q2 *= 1e100; q1 *= 1e100; }
+      for (int sp = 0; sp < SP; sp++) {
+        const int idx = sp * 32 * NWP + tid;               // shift of this thread: virtual warp sp * NWP + w of the 12
+        const double x = lo + (hi - lo) * ((idx + 1) / (double)(NT + 1));
+        int cnt = 0;
+        double q0 = 1.0, q1 = dd[0] - x;
+        bool neg = q1 < 0;                                   // sign of the last non-zero term
+        if (neg) cnt++;
+#pragma unroll
+        for (int i = 1; i < N; i++) {
+          const double t = e2[i] * q0;
+          double q2 = fma(dd[i] - x, q1, -t);
+          if (i % 6 == 0) {
+            const double m = fabs(q2);
+            if (m > 1e100) { q2 *= 1e-100; q1 *= 1e-100; }
+            else if (m < 1e-100 && m > 0) { q2 *= 1e100; q1 *= 1e100; }
+          }
+          if (q2 != 0) {
+            const bool n2 = q2 < 0;
+            cnt += (n2 != neg);
+            neg = n2;
+          }
+          q0 = q1; q1 = q2;
         }
-        if (q2 != 0) {
-          const bool n2 = q2 < 0;
-          cnt += (n2 != neg);
-          neg = n2;
-        }
-        q0 = q1; q1 = q2;
+        const unsigned mk = __ballot_sync(full, cnt >= 1);
+        if (lane == 0) s_first[b][sp * NWP + w] = mk ? (sp * NWP + w) * 32 + (__ffs(mk) - 1) : -1;
       }
-      const unsigned mk = __ballot_sync(full, cnt >= 1);
-      if (lane == 0) s_first[b][w] = mk ? w * 32 + (__ffs(mk) - 1) : -1;
       __syncthreads();
       int f = -1;
       for (int ww = 0; ww < NW; ww++)
@@ -911,20 +919,27 @@ __device__ __forceinline__ int cta384_psd_shift19(double* s_H) {
   bool llt_ok = mn > 0;
   if (fabs(mn) <= band) {
     // borderline: the reference's decision is the outcome of Eigen's unblocked LLT on these very operands
-    const int i = tid % N, j = tid / N;
-    const bool act = tid < N * N;
-    double aij = act ? s_H[tid] : 0.0;
+    constexpr int EPT = (N * N + 32 * NWP - 1) / (32 * NWP);     // elements per thread
+    double aij[EPT];
+#pragma unroll
+    for (int q = 0; q < EPT; q++) { const int e = tid + q * 32 * NWP; aij[q] = e < N * N ? s_H[e] : 0.0; }
     llt_ok = true;
     __syncthreads();
     for (int k = 0; k < N; k++) {
       double* col = s_col[k & 1];
-      if (act && j == k && i >= k) col[i] = aij;
+#pragma unroll
+      for (int q = 0; q < EPT; q++) {
+        const int e = tid + q * 32 * NWP, i = e % N, j = e / N;
+        if (e < N * N && j == k && i >= k) col[i] = aij[q];
+      }
       __syncthreads();
       const double x = col[k];
       if (!(x > 0)) { llt_ok = false; break; }             // uniform
-      if (act && j > k && i >= j) {
-        const double lkk = sqrt(x);
-        aij -= (col[i] / lkk) * (col[j] / lkk);
+      const double lkk = sqrt(x);
+#pragma unroll
+      for (int q = 0; q < EPT; q++) {
+        const int e = tid + q * 32 * NWP, i = e % N, j = e / N;
+        if (e < N * N && j > k && i >= j) aij[q] -= (col[i] / lkk) * (col[j] / lkk);
       }
     }
   }
@@ -950,7 +965,8 @@ struct PieceArgs {
   DevCounts* dc;         // planes x gradient passes counter
 };
 
-__global__ void __launch_bounds__(384) k_piece(PieceArgs a) {
+template <int NWP>
+__global__ void __launch_bounds__(32 * NWP) k_piece(PieceArgs a) {
   extern __shared__ double sm[];
   const int robot = a.robot_begin + blockIdx.x / a.P, sp = blockIdx.x % a.P;
   const int nterm = a.res * ROW_TERMS;
@@ -1051,7 +1067,7 @@ __global__ void __launch_bounds__(384) k_piece(PieceArgs a) {
   __syncthreads();
   // PSD projection of Gradient_admm.h:40-53 by the whole CTA
   if (a.project_psd) {
-    const int flag = cta384_psd_shift19(s_H);
+    const int flag = cta_psd_shift19<NWP>(s_H);
     if (threadIdx.x == 0) a.pc_flag[pb] = flag;
   }
   __syncthreads();
@@ -1149,7 +1165,12 @@ int gradient_blocks(tob_ctx* c, int rb, int re, int project_psd) {
   size_t smem = ((size_t)c->prm.res * ROW_TERMS * (6 + TERM_SZ) + 361 * 2 + 36 + 2) * sizeof(double);
   {
     Prof prof(c, K_PIECE);
-    k_piece<<<(re - rb) * P, 384, smem, c->stream>>>(b);
+    // many blocks: 128-thread CTAs (the tridiagonalisation of a block runs on ONE warp: with 384 threads and two CTAs per SM
+    // two warps per SM worked while 22 waited at the barrier behind it; same results, see cta_psd_shift19)
+    const char* e = getenv("TRAJOPT_B200_PIECE_CTA");
+    const int small = e ? atoi(e) == 128 : (re - rb) * P >= 1024;
+    if (small) k_piece<4><<<(re - rb) * P, 128, smem, c->stream>>>(b);
+    else k_piece<12><<<(re - rb) * P, 384, smem, c->stream>>>(b);
     TOB_LAUNCH_CHECK(c);
   }
   return 0;
