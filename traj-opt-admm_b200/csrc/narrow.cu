@@ -31,10 +31,11 @@ __device__ __forceinline__ void load_pts6(const double* __restrict__ src, double
 }
 
 // ---- obstacle planes -------------------------------------------------------------------------------------------
-// Candidates are processed in chunks of NP_CHUNK (one CTA iteration).  Inside a chunk: every thread runs the cheap
-// 49-DOP gate for NP_PER candidates, the survivors are compacted (ballot + prefix), and the threads then run GJK + plane
-// for the survivors, so the expensive divergent part executes on dense warps instead of on ~30 % of the lanes.
-// Per chunk the number of accepted planes goes to csum[chunk]; k_np_top scans it and k_pack scatters.
+// Candidates are processed in chunks of up to NP_CHUNK (one CTA iteration; a CTA takes its next chunk from an atomic
+// ticket).  Inside a chunk: every thread runs the first axes of the 49-DOP gate for up to NP_PER candidates, the survivors
+// are compacted (ballot + prefix), and the threads then run GJK + plane for the survivors, so the expensive divergent part
+// executes on dense warps instead of on ~30 % of the lanes.  Per chunk the number of accepted planes goes to csum[chunk];
+// k_np_top scans it and k_pack scatters.
 struct NarrowArgs {
   DevCounts* dc;
   uint32_t cap;
