@@ -726,6 +726,9 @@ int narrowphase_planes(tob_ctx* c, int rb, int re, int with_self) {
     a.gate1 = eg ? atoi(eg) : NP_GATE1;
     if (a.gate1 < 7 || a.gate1 > TOB_KDOP_AXES || a.gate1 % 7) a.gate1 = NP_GATE1;
     a.np_grid = np_grid_of(c);
+    // chunk ticket of k_narrow: k_np_top leaves it at zero, but a plane pass that was abandoned between the two (an error
+    // return) must not starve the next one
+    TOB_CUDA(c, cudaMemsetAsync(&c->dc.p->np_next, 0, sizeof(uint32_t), st));
     const char* em = getenv("TRAJOPT_B200_NP_PMEM");
     // default: hull vertices from L1, registers for 5 CTAs per SM (measured on a 128-problem shard: 1.025 ms with the vertices
     // in registers at 4 CTAs per SM, 1.001 / 0.959 / 0.990 ms with PMEM at 4 / 5 / 6); 0 = the register variants below
