@@ -78,7 +78,8 @@ def kernel_models(per_step, geo):
     return {
         "k_rows": (0.0, rows * (18 + 6 + 2 * 49) * 8.0 * 2, "hbm"),
         "k_bp_count": (0.0, 48.0 * rows + 24.0 * cand, "hbm"),
-        "k_bp_fill": (0.0, 48.0 * rows + 28.0 * cand, "hbm"),
+        "k_bp_fill": (0.0, 4.0 * rows + 8.0 * cand, "hbm"),      # scatter from the count pass's records: (point, row) per candidate
+                                                                  # written (+ 12 B per item record read, not counted: items are not)
         "k_bp_ccd": (ccd_flop, 48.0 * rows + 24.0 * ccd, "hbm"),
         "k_narrow": (np_flop, 28.0 * cand + 32.0 * planes, "fp64"),
         "k_pack": (0.0, 4.0 * cand + 72.0 * planes, "hbm"),
