@@ -167,3 +167,38 @@ extern "C" void hs_ref_logl(const double* x, int n, double* out_hi, double* out_
     out_lo[i] = (double)(l - (long double)out_hi[i]);
   }
 }
+
+// ---- the narrowphase decision of k_narrow in the product's own arithmetic, both orders, for one row and n points
+// (tests/test_cpu_checks.py::test_hostsim_narrow_rule): ref = all 49 axes, then GJK (the reference's order);
+// cut = the first `gate1` axes, GJK, the remaining axes only when the witness is not shorter than skip = dist (1 - 1e-6)
+extern "C" int hs_narrow_rule(const double* P, const double* pts, int n, const double* kdop, double dist, double offset, int gate1,
+                              unsigned char* ok_ref, double* pl_ref, unsigned char* ok_cut, double* pl_cut, unsigned long long* n_band,
+                              unsigned long long* groups_ref, unsigned long long* groups_cut) {
+  double a[6][3];
+  load<6>(P, a);
+  double lo[TOB_KDOP_AXES], hi[TOB_KDOP_AXES];
+  kdop_extents<6>(a, kdop, lo, hi);
+  const double skip = dist * (1.0 - 1e-6);
+  unsigned gr = 0, gc = 0;
+  unsigned long long band = 0;
+  for (int i = 0; i < n; i++) {
+    const double q[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    double c[3], d;
+    ok_ref[i] = 0; ok_cut[i] = 0;
+    for (int k = 0; k < 4; k++) { pl_ref[4 * i + k] = 0; pl_cut[4 * i + k] = 0; }
+    if (kdop_point_overlap(lo, hi, kdop, q, dist, &gr) && plane_point(a, q, dist, offset, c, &d)) {
+      ok_ref[i] = 1; pl_ref[4 * i] = c[0]; pl_ref[4 * i + 1] = c[1]; pl_ref[4 * i + 2] = c[2]; pl_ref[4 * i + 3] = d;
+    }
+    if (kdop_point_overlap(lo, hi, kdop, q, dist, &gc, 0, gate1)) {
+      const double cn = plane_point_witness(a, q, c);
+      bool acc = !(cn > dist);
+      if (acc && !(cn <= skip)) { band++; acc = kdop_point_overlap(lo, hi, kdop, q, dist, &gc, gate1, TOB_KDOP_AXES); }
+      if (acc) {
+        plane_point_finish(q, offset, cn, c, &d);
+        ok_cut[i] = 1; pl_cut[4 * i] = c[0]; pl_cut[4 * i + 1] = c[1]; pl_cut[4 * i + 2] = c[2]; pl_cut[4 * i + 3] = d;
+      }
+    }
+  }
+  *n_band = band; *groups_ref = gr; *groups_cut = gc;
+  return 0;
+}

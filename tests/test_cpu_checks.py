@@ -296,3 +296,37 @@ def test_fast_log(hostsim):
     _, o = ulps(np.array([1.0, 0.0, -1.0, np.inf, np.nan, 5e-324, 2.0 ** -1022]))
     assert o[0] == 0.0 and o[1] == -np.inf and np.isnan(o[2]) and o[3] == np.inf and np.isnan(o[4])
     assert o[5] == np.log(5e-324) and abs(o[6] - np.log(2.0 ** -1022)) < 1e-12
+
+
+def test_hostsim_narrow_rule(hostsim, gs):
+    """k_narrow's decision in the product's own arithmetic (host build of gjk.cuh): the first 14 axes of the gate, GJK, the
+    other 35 axes only for a witness within 1e-6 of the gap -- against the reference's order (all 49 axes, then GJK): the same
+    pairs get a plane, with the same bits, and less than half of the axis groups is evaluated.  Rows: the hulls of the golden
+    point-primitive vectors; points: a cloud around each hull, plus points placed at the gap itself (inside the band, where the
+    rest of the gate does run)."""
+    kd = np.ascontiguousarray(gs["tab_kdop"], dtype=np.float64)
+    rng = np.random.default_rng(11)
+    dist, offset = 0.2, 0.1
+    tot_planes = tot_band = g_ref = g_cut = 0
+    for r in range(0, len(gs["pp_P"]), max(1, len(gs["pp_P"]) // 12)):
+        Pm = np.asfortranarray(gs["pp_P"][r])
+        centre = Pm.mean(axis=0)
+        pts = centre + rng.normal(0, 0.22, size=(4000, 3))
+        # points at the gap: witness length = dist up to rounding, some inside the band
+        dirs = rng.normal(size=(200, 3)); dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+        far = Pm[np.argmax(np.linalg.norm(Pm - centre, axis=1))]          # a vertex of the hull, pushed outwards
+        out = (far - centre) / np.linalg.norm(far - centre)
+        dirs = dirs + 2.0 * out; dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+        edge = far + dirs * (dist * (1 - rng.uniform(0, 2e-6, size=(200, 1))))
+        pts = np.ascontiguousarray(np.vstack([pts, edge]))
+        n = len(pts)
+        ok_r = np.zeros(n, np.uint8); ok_c = np.zeros(n, np.uint8); pl_r = np.zeros((n, 4)); pl_c = np.zeros((n, 4))
+        nb, gr, gc = C.c_ulonglong(0), C.c_ulonglong(0), C.c_ulonglong(0)
+        hostsim.hs_narrow_rule(D(Pm), D(pts), n, D(kd), C.c_double(dist), C.c_double(offset), 14,
+                               ok_r.ctypes.data_as(C.POINTER(C.c_ubyte)), D(pl_r), ok_c.ctypes.data_as(C.POINTER(C.c_ubyte)), D(pl_c),
+                               C.byref(nb), C.byref(gr), C.byref(gc))
+        assert np.array_equal(ok_r, ok_c)
+        assert np.array_equal(pl_r.view(np.uint64), pl_c.view(np.uint64))
+        tot_planes += int(ok_r.sum()); tot_band += nb.value; g_ref += gr.value; g_cut += gc.value
+    assert tot_planes > 5000 and tot_band > 20, (tot_planes, tot_band)
+    assert g_cut < 0.5 * g_ref
